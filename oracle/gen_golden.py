@@ -1,0 +1,167 @@
+"""TEST INFRASTRUCTURE ONLY -- freeze reference runs as golden fixtures.
+
+Runs the reference's OWN agents (imported from /root/reference through
+oracle/ref_loader.py, unmodified) on the float64 env restatement
+(oracle/pyenvs.py) with every random draw recorded (oracle/trace.py), and writes
+``tests/golden/<name>.npz`` holding the configuration, the decision trace, the
+resulting tree in canonical DFS form, the root statistics and the action
+``fit()`` returned.  The C oracle and the CUDA engine replay the trace and must
+reproduce the tree: integers bit-exact, float64 totals to 1e-9 relative.
+
+Usage (build container only; /root/reference does not exist on the GPU box):
+    python -m oracle.gen_golden            # writes all fixtures
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+
+from oracle import pyenvs, ref_loader
+from oracle import trace as T
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+# name -> scenario.  agent: reference class key in ref_loader.load(); budget: "to_max_depth" | "zero"
+# describes what that class does AT HEAD.
+SCENARIOS = {
+    # C2-like: the only agent with working depth-budgeted rollouts
+    "hash_cartpole": dict(agent="MctsHash", env="CartPole-v1", n_sim=150, C=1.0, gamma=0.99, max_depth=500,
+                          budget="to_max_depth", env_seed=0, rng_seed=1),
+    # small max_depth + large C: exercises budget exhaustion, wide exploration and many UCB ties
+    "hash_cartpole_shallow": dict(agent="MctsHash", env="CartPole-v1", n_sim=200, C=8.0, gamma=0.9, max_depth=6,
+                                  budget="to_max_depth", env_seed=3, rng_seed=2),
+    # C1: vanilla Mcts on FrozenLake (zero-length rollouts at HEAD)
+    "mcts_lake": dict(agent="Mcts", env="FrozenLake-v1", n_sim=100, C=0.5, gamma=1.0, max_depth=1000,
+                      budget="zero", env_seed=0, rng_seed=3),
+    "mcts_lake_long": dict(agent="Mcts", env="FrozenLake-v1", n_sim=600, C=0.5, gamma=0.95, max_depth=1000,
+                           budget="zero", env_seed=0, rng_seed=4),
+    # MctsHash on FrozenLake (obs wrapped as np.int64 so that .tobytes() exists): integer env + real rollouts
+    "hash_lake": dict(agent="MctsHash", env="FrozenLake-v1", n_sim=300, C=0.5, gamma=0.9, max_depth=30,
+                      budget="to_max_depth", env_seed=0, rng_seed=5),
+    # C3-like: APW on Pendulum; k=60, alpha=0.8 widens on every simulation (tree depth 1)
+    "apw_pendulum_c3": dict(agent="MctsApw", env="Pendulum-v1", n_sim=200, C=1.0, gamma=0.99, max_depth=200,
+                            alpha=0.8, k=60, budget="zero", env_seed=0, rng_seed=6),
+    # narrow widening so that UCB fires and the tree gets deep
+    "apw_pendulum_narrow": dict(agent="MctsApw", env="Pendulum-v1", n_sim=300, C=2.0, gamma=0.95, max_depth=200,
+                                alpha=0.4, k=1, budget="zero", env_seed=1, rng_seed=7),
+    "apw_voo_pendulum": dict(agent="MctsApw", env="Pendulum-v1", n_sim=120, C=2.0, gamma=0.95, max_depth=200,
+                             alpha=0.5, k=2, budget="zero", env_seed=2, rng_seed=8,
+                             expansion="voo", epsilon=0.5, voo_n_samples=3, voo_max_try=50),
+    # SPW (with the state_variable shim) on CartPole: k=1 always re-expands; k=0.4 resamples and descends
+    "spw_cartpole_k1": dict(agent="MctsSpw", env="CartPole-v1", n_sim=150, C=1.0, gamma=0.99, max_depth=500,
+                            alpha=0.5, k=1, budget="zero", env_seed=0, rng_seed=9),
+    "spw_cartpole_descend": dict(agent="MctsSpw", env="CartPole-v1", n_sim=200, C=1.0, gamma=0.9, max_depth=500,
+                                 alpha=0.3, k=0.4, budget="zero", env_seed=4, rng_seed=10),
+    # C4-like: DPW (state_variable + index-UCB shims) on MountainCarContinuous
+    "dpw_mountaincar_c4": dict(agent="MctsDpw", env="MountainCarContinuous-v0", n_sim=400, C=1.0, gamma=0.99,
+                               max_depth=500, alpha1=0.5, k1=1, alpha2=0.5, k2=1, budget="zero", env_seed=0,
+                               rng_seed=11),
+    "dpw_mountaincar_descend": dict(agent="MctsDpw", env="MountainCarContinuous-v0", n_sim=300, C=0.5, gamma=0.95,
+                                    max_depth=500, alpha1=0.4, k1=1, alpha2=0.2, k2=0.5, budget="zero",
+                                    env_seed=5, rng_seed=12),
+}
+
+
+class _LakeHashEnv(pyenvs.FrozenLakeEnv):
+    """FrozenLake whose observation is np.int64 (has .tobytes()) so MctsHash can key it."""
+
+    def step(self, a):
+        out = super().step(a)
+        return (np.int64(out[0]),) + tuple(out[1:])
+
+
+def run_scenario(name: str, sc: dict):
+    R = ref_loader.load()
+    env_name = sc["env"]
+    agent_key = sc["agent"]
+    api = 5 if agent_key == "Mcts" else 4  # mcts.py:79-82 indexes vals[0..2]; the others unpack 4 (mcts_hash.py:93)
+    if env_name == "FrozenLake-v1" and agent_key == "MctsHash":
+        env = _LakeHashEnv(api=4, seed=sc["env_seed"])
+    else:
+        env = pyenvs.make(env_name, api=api, seed=sc["env_seed"])
+    obs = env.reset()
+    if api == 5:
+        obs = obs[0]
+    root_state = pyenvs.env_state_vector(env)
+    tr = T.Trace()
+    env.action_space = T.RecordingSpace(env.action_space, tr)
+    n_actions = getattr(env.action_space, "n", None)
+    root_data = obs
+    if env_name == "FrozenLake-v1" and agent_key == "MctsHash":
+        root_data = np.array([0, 0])  # fit() indexes root_data[0], root_data[1] (mcts_hash.py:37-38)
+    common = dict(root_data=root_data, env=env, n_sim=sc["n_sim"], C=sc["C"], action_selection_fn=R.ucb1,
+                  gamma=sc["gamma"], rollout_selection_fn=R.continuous_default_policy, max_depth=sc["max_depth"],
+                  n_actions=n_actions, x_values=[], y_values=[], depths=[])
+    if agent_key in ("Mcts", "MctsHash"):
+        param = R.MctsParameters(**common)
+    elif agent_key == "MctsApw":
+        if sc.get("expansion") == "voo":
+            ae = R.voo(sc["epsilon"], R.continuous_default_policy, sc["voo_n_samples"], sc["voo_max_try"])
+        else:
+            ae = R.continuous_default_policy
+        param = R.PwParameters(**common, alpha=sc["alpha"], k=sc["k"], action_expansion_function=ae)
+    elif agent_key == "MctsSpw":
+        param = R.SpwParams(**common, alpha=sc["alpha"], k=sc["k"], action_expansion_function=None,
+                            state_variable="state")
+    elif agent_key == "MctsDpw":
+        common["action_selection_fn"] = R.ucb1_index
+        param = R.DpwParams(**common, alphaApw=sc["alpha1"], kApw=sc["k1"], alphaSpw=sc["alpha2"], kSpw=sc["k2"],
+                            state_variable="state")
+    else:
+        raise KeyError(agent_key)
+    agent = getattr(R, agent_key)(param)
+    fit_error = ""
+    steps0 = pyenvs.STEP_COUNTER[0]
+    with T.recording(tr, sc["rng_seed"]):
+        try:
+            action = agent.fit()
+        except ValueError as e:
+            # mcts_double_...:41 decodes a 4-byte float32 key with dtype=float (8 bytes): HEAD bug.
+            fit_error = str(e)
+            action = None
+    kinds, vals = tr.arrays()
+    assert kinds[-1] == T.K_CHOICE, "fit() ends with the arg-max tie-break pick"
+    ser = T.serialise_reference_tree(agent.root)
+    ch = list(agent.root.actions.values())
+    root_action = np.array([float(np.asarray(c.data, dtype=np.float64).reshape(-1)[0]) for c in ch])
+    root_na = np.array([c.na for c in ch], dtype=np.int64)
+    root_total = np.array([c.total for c in ch], dtype=np.float64)
+    if action is None:
+        q = root_total / root_na
+        best = np.flatnonzero(q == q.max())[int(vals[-1])]
+        action_val = root_action[best]
+    elif agent_key == "MctsSpw":
+        action_val = float(root_action[int(action)])  # fit returns an INDEX into the sorted actions (:38)
+    else:
+        action_val = float(np.asarray(action, dtype=np.float64).reshape(-1)[0])
+    out = dict(
+        config=np.array(json.dumps(dict(sc, name=name, n_actions=n_actions, fit_error=fit_error))),
+        root_state=root_state,
+        trace_kind=kinds, trace_value=vals,
+        q_values=np.asarray(agent.q_values, dtype=np.float64),
+        root_action=root_action, root_na=root_na, root_total=root_total,
+        fit_action=np.float64(action_val),
+        env_steps=np.int64(pyenvs.STEP_COUNTER[0] - steps0),
+        **{f"tree_{k}": v for k, v in ser.items()},
+    )
+    return out
+
+
+def main(names=None):
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    for name, sc in SCENARIOS.items():
+        if names and name not in names:
+            continue
+        out = run_scenario(name, sc)
+        path = os.path.join(GOLDEN_DIR, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: trace={len(out['trace_kind'])} records={len(out['tree_kind'])} "
+              f"max_depth={out['tree_depth'].max()} root_children={len(out['root_na'])} "
+              f"fit_action={float(out['fit_action']):.6g} size={os.path.getsize(path)}B")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])
