@@ -1,0 +1,155 @@
+/* isla_b200.h -- C ABI of the B200-native MCTS engine (libisla_b200.so).
+ *
+ * Drop-in boundary for ONE hot path of LorenzoBonanni/IslaMcts: the simulate loop inside
+ * Mcts / MctsHash / MctsApw / MctsSpw / MctsDpw .fit()  (UCB1 selection, progressive-widening
+ * expansion, random rollout with discounted return, value backup).  The reference has no FFI; its
+ * boundary is the Python class API, so each entry point cites the Python it replaces
+ * (paths relative to the reference tree).  Host binding: islamcts_b200/_lib.py (ctypes);
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every `*_dev` pointer is DEVICE memory owned by the caller;
+ *   - all work is enqueued on the `stream` argument (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream); no call synchronises the device unless its comment says so;
+ *   - every function returns 0 on success or a negative isla_status; isla_last_error() gives text;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     ISLA_ERR_CUDA.
+ */
+#ifndef ISLA_B200_H
+#define ISLA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISLA_ABI_VERSION 1
+
+typedef enum {
+    ISLA_OK = 0,
+    ISLA_ERR_INVALID = -1,      /* bad argument / unsupported combination (Python: NotImplementedError) */
+    ISLA_ERR_CUDA = -2,         /* CUDA runtime error, text in isla_last_error() */
+    ISLA_ERR_CAPACITY = -3,     /* node capacity of the device tree exhausted */
+    ISLA_ERR_TRACE = -4         /* scripted run: trace exhausted / kind mismatch / value out of range */
+} isla_status;
+
+/* environments (gym ids the Python layer recognises) */
+enum { ISLA_ENV_CARTPOLE = 0, ISLA_ENV_PENDULUM = 1, ISLA_ENV_MOUNTAINCAR = 2, ISLA_ENV_FROZENLAKE = 3 };
+/* agents: islaMcts/agents/{mcts,mcts_hash}.py ; mcts_action_... ; mcts_state_... ; mcts_double_... */
+enum { ISLA_AGENT_VANILLA = 0, ISLA_AGENT_APW = 1, ISLA_AGENT_SPW = 2, ISLA_AGENT_DPW = 3 };
+/* rollout budget: MctsHash depth accounting (mcts_hash.py:34,116,126) or the zero-length rollouts the
+ * other four agents perform at HEAD (mcts.py:27 + abstract_mcts.py:83) */
+enum { ISLA_BUDGET_TO_MAX_DEPTH = 0, ISLA_BUDGET_ZERO = 1 };
+enum { ISLA_EXPAND_RANDOM = 0, ISLA_EXPAND_VOO = 1 };
+enum { ISLA_PRECISION_F32 = 0, ISLA_PRECISION_F64 = 1 };   /* env arithmetic; tree statistics are always f64 */
+enum { ISLA_KERNEL_AUTO = 0, ISLA_KERNEL_THREAD_PER_TREE = 1, ISLA_KERNEL_CTA_PER_TREE = 2 };
+/* decision-trace kinds of the scripted (parity) mode */
+enum { ISLA_K_CHOICE = 0, ISLA_K_SAMPLE_D = 1, ISLA_K_SAMPLE_C = 2, ISLA_K_CHOICES = 3, ISLA_K_U01 = 4, ISLA_K_UNIFORM = 5 };
+
+/* Replaces the MctsParameters / PwParameters / DpwParameters records
+ * (agents/parameters/mcts_parameters.py:8-31, pw_parameters.py:7-11, dpw_parameters.py:6-13). */
+typedef struct {
+    int32_t env_id;             /* ISLA_ENV_*   (param.env, identified by the Python layer) */
+    int32_t agent;              /* ISLA_AGENT_* */
+    int32_t n_actions;          /* param.n_actions (discrete agents) */
+    int32_t max_depth;          /* param.max_depth */
+    int32_t budget_mode;        /* ISLA_BUDGET_* */
+    int32_t rollouts_per_leaf;  /* build extension: mean of R rollouts backed up as ONE visit */
+    int32_t expansion;          /* ISLA_EXPAND_*  (param.action_expansion_function) */
+    int32_t voo_n_samples;
+    int32_t voo_max_try;
+    int32_t precision;          /* ISLA_PRECISION_* */
+    int32_t kernel;             /* ISLA_KERNEL_* */
+    int32_t block_threads;      /* CTA-per-tree kernel: threads per tree (multiple of 32); 0 = auto */
+    int32_t sim_capacity;       /* max cumulative simulations per tree the workspace is sized for */
+    int32_t reserved0;
+    double C;                   /* param.C */
+    double gamma;               /* param.gamma */
+    double alpha1, k1;          /* PwParameters.alpha/k ; DpwParameters.alphaApw/kApw */
+    double alpha2, k2;          /* DpwParameters.alphaSpw/kSpw */
+    double epsilon;             /* voo epsilon */
+    uint64_t seed;              /* Philox key */
+    uint64_t tree_id_base;      /* global id of tree 0 of this engine (rank offset under sharding) */
+    int64_t n_trees;            /* independent trees held by this engine */
+} isla_config;
+
+typedef struct isla_engine isla_engine;
+
+/* Byte layout of the workspace so that host code can decode the device tree (lazy node proxies). */
+typedef struct {
+    int32_t kernel;             /* resolved ISLA_KERNEL_* */
+    int32_t state_dim;
+    int32_t real_bytes;         /* 4 or 8 */
+    int32_t n_actions;
+    int64_t slots_per_tree;     /* thread-per-tree: record slots per tree */
+    int64_t rec_offset, rec_stride;         /* thread-per-tree: 32-byte edge records */
+    int64_t state_offset, state_stride;     /* env states, state_dim reals per slot */
+    int64_t meta_offset;                    /* per-tree int32[8]: alloc, sims, rng words consumed, fault, ... */
+    int64_t path_offset;
+    int64_t counters_offset;                /* int64[8] device counters */
+    /* CTA-per-tree (general) pools, offsets of the per-tree blocks and their strides */
+    int64_t s_cap, a_cap;                   /* state / action node capacity per tree */
+    int64_t pool_offset, pool_stride;       /* bytes per tree of the general node pool */
+    int64_t total_bytes;
+} isla_layout;
+
+const char* isla_last_error(void);
+int isla_abi_version(void);
+/* number of visible CUDA devices (0 without a GPU); never fails */
+int isla_device_count(void);
+
+/* Sizing + creation.  The workspace is caller-owned device memory (e.g. a torch uint8 tensor),
+ * >= isla_engine_workspace_bytes(cfg), 256-byte aligned. */
+int64_t isla_engine_workspace_bytes(const isla_config* cfg);
+int isla_engine_create(const isla_config* cfg, void* workspace_dev, int64_t workspace_bytes, isla_engine** out);
+int isla_engine_destroy(isla_engine* e);
+int isla_engine_layout(const isla_engine* e, isla_layout* out);
+
+/* Agent(param) + param.root_data / param.env:  root env states, double [n_trees][state_dim]
+ * (FrozenLake: the cell index as a double).  Clears the trees (replaces constructing a new agent,
+ * sweep.py:186-189). */
+int isla_engine_set_roots(isla_engine* e, const double* roots_dev, void* stream);
+
+/* fit(): the `for s in range(n_sim)` loop (mcts.py:24-27, mcts_hash.py:30-34, mcts_action_...:25-30,
+ * mcts_state_...:23-26, mcts_double_...:24-27) for all trees.  Calling it again continues the trees. */
+int isla_engine_run(isla_engine* e, int32_t n_sim, void* stream);
+
+/* Parity mode: tree `tree` consumes a recorded decision trace (kinds uint8, values double, device). */
+int isla_engine_run_scripted(isla_engine* e, int64_t tree, int32_t n_sim, const uint8_t* kinds_dev,
+                             const double* values_dev, int64_t trace_len, void* stream);
+
+/* End of fit(): q = total/na per root child and the uniformly random arg-max
+ * (mcts_hash.py:42-50).  Discrete agents: na/total are [n_trees][n_actions] by ACTION index.
+ * best_dev[n_trees] = chosen action index.  scripted_pos >= 0 replaces the tie-break draw. */
+int isla_engine_root_stats(isla_engine* e, int64_t* na_dev, double* total_dev, void* stream);
+int isla_engine_best(isla_engine* e, int32_t scripted_pos, int32_t* best_dev, void* stream);
+
+/* Device counters int64[8]: [0] env steps executed, [1] rollout steps, [2] tree levels visited,
+ * [3] simulations, [4] nodes created, [5] faults.  SYNCHRONISES the stream. */
+int isla_engine_counters(isla_engine* e, int64_t out_host[8], void* stream);
+
+/* Root-parallel merge (north_star (4)): per-root sums over the trees that share a root.
+ * group_dev[n_trees] = root id in [0, n_roots); outputs [n_roots][n_actions], zero-filled first.
+ * The caller then all-reduces the two arrays over NCCL. */
+int isla_merge_root_stats(const int64_t* na_dev, const double* total_dev, const int32_t* group_dev,
+                          int64_t n_trees, int32_t n_actions, int64_t n_roots, int64_t* na_out_dev,
+                          double* total_out_dev, void* stream);
+
+/* gym env.step over a batch (parity of the dynamics): states [n][state_dim], actions [n] (discrete:
+ * index as a real), precision selects float/double buffers for states/actions/rewards. */
+int isla_env_step(int32_t env_id, int32_t precision, const void* states_dev, const void* actions_dev, int64_t n,
+                  void* next_states_dev, void* rewards_dev, uint8_t* terminated_dev, void* stream);
+
+/* AbstractStateNode.rollout (abstract_mcts.py:72-91) over a batch: trajectory i starts at
+ * states[i] (or, if states_dev == NULL, at the gym reset distribution, Philox reset stream, index i),
+ * plays uniformly random actions (stream (seed, tree=i, sim, j=0)) for at most `budget` steps,
+ * returns sum r*gamma^t (double) and the steps taken. */
+int isla_rollout(int32_t env_id, int32_t precision, const void* states_dev, int64_t n, int32_t budget, double gamma,
+                 uint64_t seed, uint32_t sim, double* returns_dev, int32_t* steps_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISLA_B200_H */

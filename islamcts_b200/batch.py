@@ -1,0 +1,92 @@
+"""Root-parallel batched search: many independent vanilla trees per GPU, root statistics merged per root.
+
+This is the public call for BASELINE config C5 ("65 536 independent CartPole trees x nsim=1000 sharded
+across 1/2/4/8 B200 with NCCL root-statistics merge") and north_star subsystem (4).  The reference's only
+parallel construct is joblib over whole experiments (islaMcts/experiment_runner.py:305-306); here the
+unit of sharding is the tree:
+
+    tree i  ->  rank (i // trees_per_rank); trees of one root group are summed on the rank (one kernel),
+    then ONE all-reduce(sum) of the dense [n_roots, A] (na:int64, total:float64) arrays over NCCL;
+    every rank then takes q = total/na and the arg-max locally (mcts_hash.py:42-50).
+
+No communication happens during the search itself.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import engine as E
+
+
+class RootParallelSearch:
+    def __init__(self, env: str | int = "CartPole-v1", trees_per_rank: int = 65536, n_sim: int = 1000, C: float = 1.0,
+                 gamma: float = 0.99, max_depth: int = 500, n_roots: int | None = None, seed: int = 0,
+                 precision: int = _lib.PRECISION_F32, budget_mode: int = _lib.BUDGET_TO_MAX_DEPTH,
+                 device="cuda:0", process_group=None, rank: int = 0, world_size: int = 1):
+        self.env_id = E.ENV_NAMES[env] if isinstance(env, str) else int(env)
+        self.device = torch.device(device)
+        self.rank, self.world = int(rank), int(world_size)
+        self.pg = process_group
+        self.trees = int(trees_per_rank)
+        self.n_sim = int(n_sim)
+        self.A = E.N_ACTIONS[self.env_id]
+        self.S = E.STATE_DIM[self.env_id]
+        # root groups: every rank holds trees_per_rank/n_roots trees of each of the n_roots roots
+        self.n_roots = int(n_roots) if n_roots else self.trees
+        if self.trees % self.n_roots:
+            raise ValueError("trees_per_rank must be a multiple of n_roots")
+        self.engine = E.Engine(self.env_id, agent=_lib.AGENT_VANILLA, n_trees=self.trees, sim_capacity=self.n_sim,
+                               max_depth=max_depth, C_=C, gamma=gamma, budget_mode=budget_mode, precision=precision,
+                               kernel=_lib.KERNEL_THREAD_PER_TREE, seed=seed, tree_id_base=self.rank * self.trees,
+                               device=self.device)
+        per = self.trees // self.n_roots
+        self.group = (torch.arange(self.trees, device=self.device, dtype=torch.int32) // per).contiguous()
+        self._roots_dev = torch.empty((self.trees, self.S), dtype=torch.float64, device=self.device)
+        self._out_host = None
+
+    # roots_of_groups: [n_roots, S]; each group's trees all start from that root
+    def expand_roots(self, roots_of_groups: torch.Tensor) -> torch.Tensor:
+        return roots_of_groups.to(self.device, torch.float64)[self.group.long()].contiguous()
+
+    def search_device(self, tree_roots_dev: torch.Tensor):
+        """Device-resident pass: roots [trees, S] float64 on the GPU -> merged (na, total) [n_roots, A]."""
+        eng = self.engine
+        eng.set_roots(tree_roots_dev)
+        eng.run(self.n_sim)
+        na, tot = eng.root_stats()
+        mna, mtot = E.merge_root_stats(na, tot, self.group, self.n_roots)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(mna, op=dist.ReduceOp.SUM, group=self.pg)
+            dist.all_reduce(mtot, op=dist.ReduceOp.SUM, group=self.pg)
+        return mna, mtot
+
+    @staticmethod
+    def pick(mna: torch.Tensor, mtot: torch.Tensor) -> torch.Tensor:
+        """q = total/na per root, arg-max (first maximum; exact ties between merged float sums do not occur)."""
+        q = torch.where(mna > 0, mtot / mna.clamp(min=1).to(torch.float64), torch.full_like(mtot, -float("inf")))
+        return q.argmax(dim=1).to(torch.int32)
+
+    def fit(self, roots_host: torch.Tensor):
+        """End-to-end call with HOST buffers: roots [n_roots, S] float64 (pinned) -> dict of host tensors."""
+        if self._out_host is None:
+            self._out_host = dict(
+                action=torch.empty(self.n_roots, dtype=torch.int32).pin_memory(),
+                na=torch.empty((self.n_roots, self.A), dtype=torch.int64).pin_memory(),
+                total=torch.empty((self.n_roots, self.A), dtype=torch.float64).pin_memory())
+        g = roots_host.to(self.device, non_blocking=True)
+        mna, mtot = self.search_device(self.expand_roots(g))
+        act = self.pick(mna, mtot)
+        self._out_host["action"].copy_(act, non_blocking=True)
+        self._out_host["na"].copy_(mna, non_blocking=True)
+        self._out_host["total"].copy_(mtot, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._out_host
+
+    def h2d_bytes(self) -> int:
+        return self.n_roots * self.S * 8
+
+    def d2h_bytes(self) -> int:
+        return self.n_roots * (4 + self.A * 16)

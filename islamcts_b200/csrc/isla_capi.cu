@@ -1,0 +1,184 @@
+// C ABI of libisla_b200.so (declared in include/isla_b200.h): engine handle, dispatch between the
+// thread-per-tree and CTA-per-tree kernels, the root-statistics merge and error reporting.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "isla_envs.cuh"
+#include "isla_internal.h"
+
+namespace isla {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return ISLA_ERR_CUDA;
+}
+
+static int resolve_kernel(const isla_config& c) {
+    if (c.kernel == ISLA_KERNEL_THREAD_PER_TREE || c.kernel == ISLA_KERNEL_CTA_PER_TREE) return c.kernel;
+    const bool tpt_ok = c.agent == ISLA_AGENT_VANILLA && env_n_actions(c.env_id) > 0 && c.rollouts_per_leaf <= 1;
+    // many independent narrow trees -> one thread each; few / wide / leaf-parallel trees -> one CTA each
+    return (tpt_ok && c.n_trees >= 1024) ? ISLA_KERNEL_THREAD_PER_TREE : ISLA_KERNEL_CTA_PER_TREE;
+}
+
+static int validate(const isla_config& c) {
+    if (c.env_id < 0 || c.env_id >= ENV_COUNT) { set_error("unknown env_id %d", c.env_id); return ISLA_ERR_INVALID; }
+    if (c.agent < ISLA_AGENT_VANILLA || c.agent > ISLA_AGENT_DPW) { set_error("unknown agent %d", c.agent); return ISLA_ERR_INVALID; }
+    if (c.n_trees < 1) { set_error("n_trees must be >= 1"); return ISLA_ERR_INVALID; }
+    if (c.sim_capacity < 1) { set_error("sim_capacity must be >= 1"); return ISLA_ERR_INVALID; }
+    if (c.max_depth < 0) { set_error("max_depth must be >= 0"); return ISLA_ERR_INVALID; }
+    if (c.precision != ISLA_PRECISION_F32 && c.precision != ISLA_PRECISION_F64) { set_error("bad precision"); return ISLA_ERR_INVALID; }
+    const int A = env_n_actions(c.env_id);
+    if ((c.agent == ISLA_AGENT_VANILLA || c.agent == ISLA_AGENT_SPW) && A == 0) {
+        set_error("agent %d needs a discrete action space; env %d is continuous", c.agent, c.env_id); return ISLA_ERR_INVALID;
+    }
+    if ((c.agent == ISLA_AGENT_APW || c.agent == ISLA_AGENT_DPW) && A != 0) {
+        set_error("agent %d samples a continuous Box; env %d is discrete", c.agent, c.env_id); return ISLA_ERR_INVALID;
+    }
+    if ((c.agent == ISLA_AGENT_SPW || c.agent == ISLA_AGENT_DPW) && c.env_id == ISLA_ENV_PENDULUM) {
+        set_error("spw/dpw poke the observation into the env state; Pendulum's observation is not its state"); return ISLA_ERR_INVALID;
+    }
+    return 0;
+}
+
+static int fill_layout(const isla_config& cfg, isla_layout& lay) {
+    memset(&lay, 0, sizeof lay);
+    const int rc = validate(cfg);
+    if (rc) return rc;
+    return resolve_kernel(cfg) == ISLA_KERNEL_THREAD_PER_TREE ? tpt_fill_layout(cfg, lay) : cta_fill_layout(cfg, lay);
+}
+
+__global__ void merge_root_stats_kernel(const int64_t* na, const double* total, const int32_t* group, long long n_trees,
+                                        int A, unsigned long long* na_out, double* total_out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_trees * A) return;
+    const long long tree = i / A;
+    const int a = (int)(i % A);
+    const long long g = group ? group[tree] : tree;
+    atomicAdd(na_out + g * A + a, (unsigned long long)na[i]);
+    atomicAdd(total_out + g * A + a, total[i]);
+}
+
+}  // namespace isla
+
+using namespace isla;
+
+extern "C" {
+
+const char* isla_last_error(void) { return g_err; }
+int isla_abi_version(void) { return ISLA_ABI_VERSION; }
+int isla_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int64_t isla_engine_workspace_bytes(const isla_config* cfg) {
+    if (!cfg) { set_error("null config"); return ISLA_ERR_INVALID; }
+    isla_layout lay;
+    const int rc = fill_layout(*cfg, lay);
+    return rc ? rc : lay.total_bytes;
+}
+
+int isla_engine_create(const isla_config* cfg, void* workspace_dev, int64_t workspace_bytes, isla_engine** out) {
+    if (!cfg || !out) { set_error("null argument"); return ISLA_ERR_INVALID; }
+    isla_layout lay;
+    int rc = fill_layout(*cfg, lay);
+    if (rc) return rc;
+    if (isla_device_count() < 1) { set_error("no CUDA device: libisla_b200 has no CPU fallback"); return ISLA_ERR_CUDA; }
+    if (!workspace_dev || workspace_bytes < lay.total_bytes) {
+        set_error("workspace too small: %lld < %lld bytes", (long long)workspace_bytes, (long long)lay.total_bytes);
+        return ISLA_ERR_INVALID;
+    }
+    if (((uintptr_t)workspace_dev & 255u) != 0) { set_error("workspace must be 256-byte aligned"); return ISLA_ERR_INVALID; }
+    isla_engine* e = new (std::nothrow) isla_engine();
+    if (!e) { set_error("out of host memory"); return ISLA_ERR_INVALID; }
+    e->cfg = *cfg; e->lay = lay; e->ws = (char*)workspace_dev; e->kernel = lay.kernel; e->roots_set = false;
+    int dev = 0;
+    ISLA_CUDA_OK(cudaGetDevice(&dev));
+    ISLA_CUDA_OK(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, dev));
+    *out = e;
+    return ISLA_OK;
+}
+
+int isla_engine_destroy(isla_engine* e) { delete e; return ISLA_OK; }
+
+int isla_engine_layout(const isla_engine* e, isla_layout* out) {
+    if (!e || !out) { set_error("null argument"); return ISLA_ERR_INVALID; }
+    *out = e->lay;
+    return ISLA_OK;
+}
+
+int isla_engine_set_roots(isla_engine* e, const double* roots_dev, void* stream) {
+    if (!e || !roots_dev) { set_error("null argument"); return ISLA_ERR_INVALID; }
+    const int rc = e->kernel == ISLA_KERNEL_THREAD_PER_TREE ? tpt_set_roots(e, roots_dev, (cudaStream_t)stream)
+                                                            : cta_set_roots(e, roots_dev, (cudaStream_t)stream);
+    if (rc == 0) e->roots_set = true;
+    return rc;
+}
+
+int isla_engine_run(isla_engine* e, int32_t n_sim, void* stream) {
+    if (!e) { set_error("null engine"); return ISLA_ERR_INVALID; }
+    if (!e->roots_set) { set_error("isla_engine_set_roots must be called before run"); return ISLA_ERR_INVALID; }
+    if (n_sim < 0) { set_error("n_sim < 0"); return ISLA_ERR_INVALID; }
+    if (n_sim == 0) return ISLA_OK;
+    return e->kernel == ISLA_KERNEL_THREAD_PER_TREE ? tpt_run(e, n_sim, -1, nullptr, nullptr, 0, (cudaStream_t)stream)
+                                                    : cta_run(e, n_sim, -1, nullptr, nullptr, 0, (cudaStream_t)stream);
+}
+
+int isla_engine_run_scripted(isla_engine* e, int64_t tree, int32_t n_sim, const uint8_t* kinds_dev, const double* values_dev,
+                             int64_t trace_len, void* stream) {
+    if (!e) { set_error("null engine"); return ISLA_ERR_INVALID; }
+    if (!e->roots_set) { set_error("isla_engine_set_roots must be called before run"); return ISLA_ERR_INVALID; }
+    if (tree < 0 || tree >= e->cfg.n_trees) { set_error("tree index out of range"); return ISLA_ERR_INVALID; }
+    if (trace_len > 0 && (!kinds_dev || !values_dev)) { set_error("null trace"); return ISLA_ERR_INVALID; }
+    if (n_sim <= 0) return ISLA_OK;
+    return e->kernel == ISLA_KERNEL_THREAD_PER_TREE ? tpt_run(e, n_sim, tree, kinds_dev, values_dev, trace_len, (cudaStream_t)stream)
+                                                    : cta_run(e, n_sim, tree, kinds_dev, values_dev, trace_len, (cudaStream_t)stream);
+}
+
+int isla_engine_root_stats(isla_engine* e, int64_t* na_dev, double* total_dev, void* stream) {
+    if (!e || !na_dev || !total_dev) { set_error("null argument"); return ISLA_ERR_INVALID; }
+    return e->kernel == ISLA_KERNEL_THREAD_PER_TREE ? tpt_root_stats(e, na_dev, total_dev, (cudaStream_t)stream)
+                                                    : cta_root_stats(e, na_dev, total_dev, (cudaStream_t)stream);
+}
+
+int isla_engine_best(isla_engine* e, int32_t scripted_pos, int32_t* best_dev, void* stream) {
+    if (!e || !best_dev) { set_error("null argument"); return ISLA_ERR_INVALID; }
+    return e->kernel == ISLA_KERNEL_THREAD_PER_TREE ? tpt_best(e, scripted_pos, best_dev, (cudaStream_t)stream)
+                                                    : cta_best(e, scripted_pos, best_dev, (cudaStream_t)stream);
+}
+
+int isla_engine_counters(isla_engine* e, int64_t out_host[8], void* stream) {
+    if (!e || !out_host) { set_error("null argument"); return ISLA_ERR_INVALID; }
+    ISLA_CUDA_OK(cudaMemcpyAsync(out_host, e->ws + e->lay.counters_offset, 64, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    ISLA_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    return ISLA_OK;
+}
+
+int isla_merge_root_stats(const int64_t* na_dev, const double* total_dev, const int32_t* group_dev, int64_t n_trees,
+                          int32_t n_actions, int64_t n_roots, int64_t* na_out_dev, double* total_out_dev, void* stream) {
+    if (!na_dev || !total_dev || !na_out_dev || !total_out_dev || n_trees < 0 || n_actions < 1 || n_roots < 1) {
+        set_error("bad argument"); return ISLA_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    ISLA_CUDA_OK(cudaMemsetAsync(na_out_dev, 0, (size_t)(n_roots * n_actions) * 8, st));
+    ISLA_CUDA_OK(cudaMemsetAsync(total_out_dev, 0, (size_t)(n_roots * n_actions) * 8, st));
+    const long long n = n_trees * n_actions;
+    if (n == 0) return ISLA_OK;
+    merge_root_stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(na_dev, total_dev, group_dev, n_trees, n_actions,
+                                                                         (unsigned long long*)na_out_dev, total_out_dev);
+    ISLA_CUDA_OK(cudaGetLastError());
+    return ISLA_OK;
+}
+
+}  // extern "C"

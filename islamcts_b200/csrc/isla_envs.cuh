@@ -1,0 +1,178 @@
+// On-device environment dynamics: CartPole-v1, Pendulum-v1, MountainCarContinuous-v0, FrozenLake-v1.
+//
+// Replaces gym's env.step() on the hot path (reference call sites: islaMcts/agents/mcts.py:79,
+// mcts_hash.py:93, abstract_mcts.py:85).  The arithmetic is third-party Gymnasium, absent from
+// /root/reference and unpinned by it; the definitions followed are the ones SURVEY.md section 8c restates.
+//
+// Two arithmetic modes, chosen at compile time by the state type T:
+//   float  : the fast path (state in registers, FMA contraction allowed, fp32 trig).
+//   double : "faithful" mode.  Every product/sum is rounded separately (no FMA contraction) in the
+//            same order as the float64 reference arithmetic, so that whole searches can be compared
+//            count-for-count with the CPU oracle.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "isla_philox.cuh"
+
+namespace isla {
+
+enum : int { ENV_CARTPOLE = 0, ENV_PENDULUM = 1, ENV_MOUNTAINCAR = 2, ENV_FROZENLAKE = 3, ENV_COUNT = 4 };
+
+template <typename T> struct Ar;
+template <> struct Ar<double> {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ void sincos(double x, double& s, double& c) { s = ::sin(x); c = ::cos(x); }
+    static __device__ __forceinline__ double cosine(double x) { return ::cos(x); }
+    static __device__ __forceinline__ double sine(double x) { return ::sin(x); }
+    static __device__ __forceinline__ double fmodulo(double a, double b) { return ::fmod(a, b); }
+    static __device__ __forceinline__ double fmin_(double a, double b) { return ::fmin(a, b); }
+    static __device__ __forceinline__ double fmax_(double a, double b) { return ::fmax(a, b); }
+};
+template <> struct Ar<float> {
+    static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+    static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+    static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
+    static __device__ __forceinline__ float div(float a, float b) { return a / b; }
+    static __device__ __forceinline__ void sincos(float x, float& s, float& c) { ::sincosf(x, &s, &c); }
+    static __device__ __forceinline__ float cosine(float x) { return ::cosf(x); }
+    static __device__ __forceinline__ float sine(float x) { return ::sinf(x); }
+    static __device__ __forceinline__ float fmodulo(float a, float b) { return ::fmodf(a, b); }
+    static __device__ __forceinline__ float fmin_(float a, float b) { return ::fminf(a, b); }
+    static __device__ __forceinline__ float fmax_(float a, float b) { return ::fmaxf(a, b); }
+};
+
+template <int ENV> struct EnvTraits;
+template <> struct EnvTraits<ENV_CARTPOLE>    { static constexpr int S = 4, A = 2; static constexpr bool kContinuous = false; };
+template <> struct EnvTraits<ENV_PENDULUM>    { static constexpr int S = 2, A = 0; static constexpr bool kContinuous = true;  };
+template <> struct EnvTraits<ENV_MOUNTAINCAR> { static constexpr int S = 2, A = 0; static constexpr bool kContinuous = true;  };
+template <> struct EnvTraits<ENV_FROZENLAKE>  { static constexpr int S = 1, A = 4; static constexpr bool kContinuous = false; };
+
+__host__ __device__ inline int env_state_dim(int env) { return env == ENV_CARTPOLE ? 4 : env == ENV_FROZENLAKE ? 1 : 2; }
+__host__ __device__ inline int env_n_actions(int env) { return env == ENV_CARTPOLE ? 2 : env == ENV_FROZENLAKE ? 4 : 0; }
+__host__ __device__ inline void env_action_bounds(int env, float& lo, float& hi) {
+    if (env == ENV_PENDULUM) { lo = -2.0f; hi = 2.0f; } else { lo = -1.0f; hi = 1.0f; }
+}
+
+// step(): advances s in place, returns `terminated`, writes the reward.
+template <int ENV, typename T> struct Env;
+
+template <typename T> struct Env<ENV_CARTPOLE, T> {
+    using A_ = Ar<T>;
+    static __device__ __forceinline__ bool step(T (&s)[4], T action, T& reward) {
+        constexpr T gravity = T(9.8), masspole = T(0.1), total_mass = T(0.1 + 1.0), length = T(0.5),
+                    polemass_length = T(0.1 * 0.5), force_mag = T(10.0), tau = T(0.02),
+                    th_lim = T(12 * 2 * 3.141592653589793 / 360), x_lim = T(2.4), four_thirds = T(4.0 / 3.0);
+        const T x = s[0], x_dot = s[1], theta = s[2], theta_dot = s[3];
+        const T force = (action >= T(0.5)) ? force_mag : -force_mag;
+        T sintheta, costheta;
+        A_::sincos(theta, sintheta, costheta);
+        const T temp = A_::div(A_::add(force, A_::mul(A_::mul(polemass_length, A_::mul(theta_dot, theta_dot)), sintheta)), total_mass);
+        const T thetaacc = A_::div(A_::sub(A_::mul(gravity, sintheta), A_::mul(costheta, temp)),
+                                   A_::mul(length, A_::sub(four_thirds, A_::div(A_::mul(masspole, A_::mul(costheta, costheta)), total_mass))));
+        const T xacc = A_::sub(temp, A_::div(A_::mul(A_::mul(polemass_length, thetaacc), costheta), total_mass));
+        s[0] = A_::add(x, A_::mul(tau, x_dot));
+        s[1] = A_::add(x_dot, A_::mul(tau, xacc));
+        s[2] = A_::add(theta, A_::mul(tau, theta_dot));
+        s[3] = A_::add(theta_dot, A_::mul(tau, thetaacc));
+        reward = T(1.0);
+        return (s[0] < -x_lim) || (s[0] > x_lim) || (s[2] < -th_lim) || (s[2] > th_lim);
+    }
+};
+
+template <typename T> struct Env<ENV_PENDULUM, T> {
+    using A_ = Ar<T>;
+    static __device__ __forceinline__ bool step(T (&s)[2], T action, T& reward) {
+        constexpr T max_speed = T(8.0), max_torque = T(2.0), dt = T(0.05), pi = T(3.141592653589793),
+                    two_pi = T(2 * 3.141592653589793), c_sin = T(3 * 10.0 / (2 * 1.0)), c_u = T(3.0 / (1.0 * (1.0 * 1.0)));
+        const T th = s[0], thdot = s[1];
+        const T u = A_::fmin_(A_::fmax_(action, -max_torque), max_torque);
+        T ang = A_::fmodulo(A_::add(th, pi), two_pi);
+        if (ang < T(0)) ang = A_::add(ang, two_pi);
+        ang = A_::sub(ang, pi);
+        const T costs = A_::add(A_::add(A_::mul(ang, ang), A_::mul(T(0.1), A_::mul(thdot, thdot))), A_::mul(T(0.001), A_::mul(u, u)));
+        T newthdot = A_::add(thdot, A_::mul(A_::add(A_::mul(c_sin, A_::sine(th)), A_::mul(c_u, u)), dt));
+        newthdot = A_::fmin_(A_::fmax_(newthdot, -max_speed), max_speed);
+        s[0] = A_::add(th, A_::mul(newthdot, dt));
+        s[1] = newthdot;
+        reward = -costs;
+        return false;
+    }
+};
+
+template <typename T> struct Env<ENV_MOUNTAINCAR, T> {
+    using A_ = Ar<T>;
+    static __device__ __forceinline__ bool step(T (&s)[2], T action, T& reward) {
+        constexpr T min_position = T(-1.2), max_position = T(0.6), max_speed = T(0.07), goal_position = T(0.45),
+                    goal_velocity = T(0.0), power = T(0.0015);
+        T position = s[0], velocity = s[1];
+        const T force = A_::fmin_(A_::fmax_(action, T(-1.0)), T(1.0));
+        velocity = A_::add(velocity, A_::sub(A_::mul(force, power), A_::mul(T(0.0025), A_::cosine(A_::mul(T(3), position)))));
+        velocity = A_::fmin_(A_::fmax_(velocity, -max_speed), max_speed);
+        position = A_::add(position, velocity);
+        position = A_::fmin_(A_::fmax_(position, min_position), max_position);
+        if (position == min_position && velocity < T(0)) velocity = T(0);
+        const bool term = (position >= goal_position) && (velocity >= goal_velocity);
+        reward = A_::sub(term ? T(100.0) : T(0.0), A_::mul(A_::mul(action, action), T(0.1)));
+        // gym keeps the state as float32
+        s[0] = T(float(position));
+        s[1] = T(float(velocity));
+        return term;
+    }
+};
+
+template <typename T> struct Env<ENV_FROZENLAKE, T> {
+    // 4x4 map SFFF/FHFH/FFFH/HFFG, is_slippery=False.  holes {5,7,11,12}, goal 15.
+    static __device__ __forceinline__ bool step(T (&s)[1], T action, T& reward) {
+        constexpr unsigned kHole = (1u << 5) | (1u << 7) | (1u << 11) | (1u << 12), kGoal = 1u << 15;
+        int cell = (int)s[0];
+        if (((kHole | kGoal) >> cell) & 1u) { reward = T(0); return true; }  // stepping from a terminal cell
+        int row = cell >> 2, col = cell & 3;
+        const int a = (int)action;
+        if (a == 0) col = max(col - 1, 0);
+        else if (a == 1) row = min(row + 1, 3);
+        else if (a == 2) col = min(col + 1, 3);
+        else row = max(row - 1, 0);
+        cell = row * 4 + col;
+        s[0] = T(cell);
+        reward = ((kGoal >> cell) & 1u) ? T(1) : T(0);
+        return ((kHole | kGoal) >> cell) & 1u;
+    }
+};
+
+// gym reset distributions driven by the Philox reset stream (synthetic roots; bench + tests)
+template <int ENV, typename T>
+__device__ __forceinline__ void env_reset(uint64_t seed, uint32_t index, T (&s)[EnvTraits<ENV>::S]) {
+    uint32_t r[4];
+    philox4x32_10(0u, 0u, index, kStreamReset, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    if constexpr (ENV == ENV_CARTPOLE) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s[i] = T(__dadd_rn(-0.05, __dmul_rn(0.1, u32_to_d01(r[i]))));
+    } else if constexpr (ENV == ENV_PENDULUM) {
+        s[0] = T(__dadd_rn(-3.141592653589793, __dmul_rn(2 * 3.141592653589793, u32_to_d01(r[0]))));
+        s[1] = T(__dadd_rn(-1.0, __dmul_rn(2.0, u32_to_d01(r[1]))));
+    } else if constexpr (ENV == ENV_MOUNTAINCAR) {
+        s[0] = T(float(__dadd_rn(-0.6, __dmul_rn(0.2, u32_to_d01(r[0])))));
+        s[1] = T(0);
+    } else {
+        s[0] = T(0);
+    }
+}
+
+// env.action_space.sample() from a stream: Discrete -> index, Box -> float32 value
+template <int ENV, typename T>
+__device__ __forceinline__ T sample_action(Stream& st) {
+    if constexpr (EnvTraits<ENV>::kContinuous) {
+        float lo, hi;
+        env_action_bounds(ENV, lo, hi);
+        return T(box_sample_f32(st.next(), lo, hi));
+    } else {
+        return T(mulhi_u32(st.next(), (uint32_t)EnvTraits<ENV>::A));
+    }
+}
+
+}  // namespace isla

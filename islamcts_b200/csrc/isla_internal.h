@@ -1,0 +1,85 @@
+// Internal declarations shared by the translation units of libisla_b200.so.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#include "../../include/isla_b200.h"
+
+namespace isla {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define ISLA_CUDA_OK(expr)                                                   \
+    do {                                                                     \
+        cudaError_t _e = (expr);                                             \
+        if (_e != cudaSuccess) return ::isla::cuda_fail(_e, #expr);          \
+    } while (0)
+
+// ---------------------------------------------------------------- thread-per-tree (vanilla) layout
+// One 32-byte EDGE record per (parent state, action): the reference's ActionNode
+// (agents/abstract_mcts.py:145-156) fused with its single StateNode child (deterministic envs:
+// exactly one child per action node).  The A records of one parent form one
+// aligned block, so a parent's UCB scan is ONE 32*A-byte contiguous load.
+struct __align__(16) EdgeRec {
+    double total_in;   // ActionNode.total
+    double g_first;    // return backed up when the child StateNode was created (StateNode.total = g_first + sum of its edges' totals)
+    int32_t na_in;     // ActionNode.na
+    float r_in;        // reward of stepping this edge (deterministic env)
+    int32_t block;     // block index of the child state's own edges (0 = none yet)
+    uint32_t flags;    // bit0 terminal child; bits 8..15 insertion rank among siblings
+};
+static_assert(sizeof(EdgeRec) == 32, "edge record is one 32-byte sector");
+constexpr uint32_t kFlagTerminal = 1u;
+
+// per-tree meta words
+enum : int { META_ALLOC = 0, META_SIMS = 1, META_RNG = 2, META_FAULT = 3, META_WORDS = 8 };
+// device counters
+enum : int { CNT_ENV_STEPS = 0, CNT_ROLLOUT_STEPS = 1, CNT_LEVELS = 2, CNT_SIMS = 3, CNT_NODES = 4, CNT_FAULTS = 5 };
+
+struct TptParams {
+    EdgeRec* recs;
+    void* states;
+    int32_t* meta;
+    int2* path;
+    unsigned long long* counters;
+    const uint8_t* trace_kinds;
+    const double* trace_values;
+    long long trace_len;
+    long long n_trees;
+    long long slots_per_tree;
+    long long scripted_tree;
+    unsigned long long seed;
+    unsigned long long tree_id_base;
+    double C, gamma;
+    int n_sim, max_depth, budget_mode, block_cap, ln_table_n;
+};
+
+}  // namespace isla
+
+struct isla_engine {
+    isla_config cfg;
+    isla_layout lay;
+    char* ws;
+    int kernel;
+    int sm_count;
+    bool roots_set;
+};
+
+namespace isla {
+// thread-per-tree engine (isla_tree_tpt.cu)
+int tpt_fill_layout(const isla_config& cfg, isla_layout& lay);
+int tpt_set_roots(isla_engine* e, const double* roots_dev, cudaStream_t st);
+int tpt_run(isla_engine* e, int n_sim, long long scripted_tree, const uint8_t* kinds, const double* values,
+            long long trace_len, cudaStream_t st);
+int tpt_root_stats(isla_engine* e, int64_t* na_dev, double* total_dev, cudaStream_t st);
+int tpt_best(isla_engine* e, int scripted_pos, int32_t* best_dev, cudaStream_t st);
+// CTA-per-tree engine (isla_tree_cta.cu)
+int cta_fill_layout(const isla_config& cfg, isla_layout& lay);
+int cta_set_roots(isla_engine* e, const double* roots_dev, cudaStream_t st);
+int cta_run(isla_engine* e, int n_sim, long long scripted_tree, const uint8_t* kinds, const double* values,
+            long long trace_len, cudaStream_t st);
+int cta_root_stats(isla_engine* e, int64_t* na_dev, double* total_dev, cudaStream_t st);
+int cta_best(isla_engine* e, int scripted_pos, int32_t* best_dev, cudaStream_t st);
+}  // namespace isla

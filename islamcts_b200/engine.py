@@ -1,0 +1,268 @@
+"""Host-side handle of the device MCTS engine (thin wrapper over the C ABI in include/isla_b200.h).
+
+PyTorch is plumbing here: it owns the device workspace / IO tensors and the CUDA stream; every
+computation is a hand-written sm_100a kernel inside libisla_b200.so.  No CPU fallback exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import IslaConfig, IslaLayout, check
+
+ENV_NAMES = {
+    "CartPole-v1": _lib.ENV_CARTPOLE, "CartPole-v0": _lib.ENV_CARTPOLE,
+    "Pendulum-v1": _lib.ENV_PENDULUM,
+    "MountainCarContinuous-v0": _lib.ENV_MOUNTAINCAR,
+    "FrozenLake-v1": _lib.ENV_FROZENLAKE,
+}
+STATE_DIM = {_lib.ENV_CARTPOLE: 4, _lib.ENV_PENDULUM: 2, _lib.ENV_MOUNTAINCAR: 2, _lib.ENV_FROZENLAKE: 1}
+N_ACTIONS = {_lib.ENV_CARTPOLE: 2, _lib.ENV_PENDULUM: 0, _lib.ENV_MOUNTAINCAR: 0, _lib.ENV_FROZENLAKE: 4}
+ACTION_BOUNDS = {_lib.ENV_PENDULUM: (-2.0, 2.0), _lib.ENV_MOUNTAINCAR: (-1.0, 1.0)}
+
+_REC_DTYPE = np.dtype([("total", "<f8"), ("g_first", "<f8"), ("na", "<i4"), ("r", "<f4"), ("block", "<i4"), ("flags", "<u4")])
+
+
+def _require_cuda(device) -> torch.device:
+    dev = torch.device(device)
+    if dev.type != "cuda" or not torch.cuda.is_available():
+        raise _lib.IslaError(_lib.ERR_CUDA, "a CUDA device is required: islamcts_b200 has no CPU fallback")
+    return dev
+
+
+def _stream_ptr(dev) -> int:
+    return int(torch.cuda.current_stream(dev).cuda_stream)
+
+
+class Engine:
+    """A batch of independent search trees living in HBM.
+
+    Parameters mirror ``isla_config``; see include/isla_b200.h for the reference lines each replaces.
+    """
+
+    def __init__(self, env_id: int, agent: int = _lib.AGENT_VANILLA, n_trees: int = 1, sim_capacity: int = 1000,
+                 max_depth: int = 500, C_: float = 1.0, gamma: float = 0.99, n_actions: int | None = None,
+                 budget_mode: int = _lib.BUDGET_TO_MAX_DEPTH, rollouts_per_leaf: int = 1,
+                 expansion: int = _lib.EXPAND_RANDOM, epsilon: float = 0.7, voo_n_samples: int = 5,
+                 voo_max_try: int = 1000, alpha1: float = 0.0, k1: float = 1.0, alpha2: float = 0.0, k2: float = 1.0,
+                 precision: int = _lib.PRECISION_F32, kernel: int = _lib.KERNEL_AUTO, block_threads: int = 0,
+                 seed: int = 0, tree_id_base: int = 0, device="cuda:0"):
+        self.device = _require_cuda(device)
+        self.lib = _lib.load()
+        if n_actions is None:
+            n_actions = N_ACTIONS[env_id]
+        self.cfg = IslaConfig(env_id, agent, int(n_actions or 0), int(max_depth), budget_mode, int(rollouts_per_leaf),
+                              expansion, int(voo_n_samples), int(voo_max_try), precision, kernel, int(block_threads),
+                              int(sim_capacity), 0, float(C_), float(gamma), float(alpha1), float(k1), float(alpha2),
+                              float(k2), float(epsilon), int(seed), int(tree_id_base), int(n_trees))
+        nbytes = check(self.lib.isla_engine_workspace_bytes(C.byref(self.cfg)))
+        with torch.cuda.device(self.device):
+            self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+            base = self.workspace.data_ptr()
+            self._ws_off = (-base) % 256
+            handle = C.c_void_p()
+            check(self.lib.isla_engine_create(C.byref(self.cfg), C.c_void_p(base + self._ws_off), nbytes, C.byref(handle)))
+        self._h = handle
+        self.layout = IslaLayout()
+        check(self.lib.isla_engine_layout(self._h, C.byref(self.layout)))
+        self.n_trees = int(n_trees)
+        self.state_dim = STATE_DIM[env_id]
+        self.n_actions = int(n_actions or 0)
+        self.env_id = env_id
+        self._keep = []
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.isla_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ the fit() loop
+    def set_roots(self, roots):
+        """roots: [n_trees, state_dim] float64 (numpy / torch, host or device)."""
+        t = torch.as_tensor(roots, dtype=torch.float64).reshape(self.n_trees, self.state_dim)
+        t = t.to(self.device, non_blocking=True).contiguous()
+        with torch.cuda.device(self.device):
+            check(self.lib.isla_engine_set_roots(self._h, C.c_void_p(t.data_ptr()), C.c_void_p(_stream_ptr(self.device))))
+        self._roots = t
+        return self
+
+    def run(self, n_sim: int):
+        with torch.cuda.device(self.device):
+            check(self.lib.isla_engine_run(self._h, int(n_sim), C.c_void_p(_stream_ptr(self.device))))
+        return self
+
+    def run_scripted(self, tree: int, n_sim: int, kinds, values):
+        k = torch.as_tensor(np.ascontiguousarray(kinds, dtype=np.uint8)).to(self.device)
+        v = torch.as_tensor(np.ascontiguousarray(values, dtype=np.float64)).to(self.device)
+        self._keep = [k, v]
+        with torch.cuda.device(self.device):
+            check(self.lib.isla_engine_run_scripted(self._h, int(tree), int(n_sim), C.c_void_p(k.data_ptr()),
+                                                    C.c_void_p(v.data_ptr()), int(k.numel()),
+                                                    C.c_void_p(_stream_ptr(self.device))))
+        return self
+
+    def root_stats(self):
+        """(na int64 [n_trees, A], total float64 [n_trees, A]) device tensors, by ACTION index."""
+        na = torch.empty((self.n_trees, self.n_actions), dtype=torch.int64, device=self.device)
+        tot = torch.empty((self.n_trees, self.n_actions), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.isla_engine_root_stats(self._h, C.c_void_p(na.data_ptr()), C.c_void_p(tot.data_ptr()),
+                                                  C.c_void_p(_stream_ptr(self.device))))
+        return na, tot
+
+    def best(self, scripted_pos: int = -1):
+        out = torch.empty((self.n_trees,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.isla_engine_best(self._h, int(scripted_pos), C.c_void_p(out.data_ptr()),
+                                            C.c_void_p(_stream_ptr(self.device))))
+        return out
+
+    def counters(self) -> dict:
+        out = (C.c_int64 * 8)()
+        with torch.cuda.device(self.device):
+            check(self.lib.isla_engine_counters(self._h, out, C.c_void_p(_stream_ptr(self.device))))
+        return dict(env_steps=out[0], rollout_steps=out[1], levels=out[2], sims=out[3], nodes=out[4], faults=out[5])
+
+    # ------------------------------------------------------------------ host views of the device tree
+    def _ws_bytes(self, offset: int, nbytes: int) -> np.ndarray:
+        lo = self._ws_off + int(offset)
+        return self.workspace[lo: lo + int(nbytes)].cpu().numpy()
+
+    def tree_meta(self, tree: int = 0) -> dict:
+        m = self._ws_bytes(self.layout.meta_offset + tree * 32, 32).view(np.int32)
+        return dict(alloc=int(m[0]), sims=int(m[1]), rng_words=int(m[2]), fault=int(m[3]), trace_pos=int(m[4]))
+
+    def raw_records(self, tree: int = 0) -> np.ndarray:
+        L = self.layout
+        return self._ws_bytes(L.rec_offset + tree * L.rec_stride, L.rec_stride).view(_REC_DTYPE)
+
+    def raw_states(self, tree: int = 0) -> np.ndarray:
+        L = self.layout
+        dt = np.float32 if L.real_bytes == 4 else np.float64
+        return self._ws_bytes(L.state_offset + tree * L.state_stride, L.state_stride).view(dt).reshape(-1, L.state_dim)
+
+    def export_tree(self, tree: int = 0) -> dict:
+        """Canonical DFS serialisation (same format as oracle/trace.py) decoded on the host."""
+        if self.layout.kernel == _lib.KERNEL_THREAD_PER_TREE:
+            return _export_tpt(self.raw_records(tree), self.n_actions)
+        from .tree_export import export_pool  # CTA-per-tree general pools
+        return export_pool(self, tree)
+
+
+def _export_tpt(rec: np.ndarray, A: int) -> dict:
+    kinds, depths, counts, totals, terms, fans, acts = [], [], [], [], [], [], []
+
+    def children(block):
+        """visited edges of a block in insertion (rank) order -> list of (action, slot)"""
+        if block == 0:
+            return []
+        out = []
+        for a in range(A):
+            r = rec[block * A + a]
+            if r["na"] > 0:
+                out.append((int((r["flags"] >> 8) & 0xFF), a, block * A + a))
+        out.sort()
+        return [(a, s) for _, a, s in out]
+
+    # stack entries: ("S", slot or -1 for root, depth) / ("A", action, slot, depth)
+    stack = [("S", -1, 0)]
+    while stack:
+        item = stack.pop()
+        if item[0] == "S":
+            _, slot, d = item
+            if slot < 0:
+                ch = children(1)
+                ns = sum(int(rec[s]["na"]) for _, s in ch)
+                tot = float(sum(float(rec[s]["total"]) for _, s in ch))
+                term = 0
+            else:
+                r = rec[slot]
+                term = int(r["flags"] & 1)
+                if term:
+                    ch, ns, tot = [], int(r["na"]), 0.0
+                else:
+                    ch = children(int(r["block"]))
+                    ns = 1 + sum(int(rec[s]["na"]) for _, s in ch)
+                    tot = float(r["g_first"]) + float(sum(float(rec[s]["total"]) for _, s in ch))
+            kinds.append(0); depths.append(d); counts.append(ns); totals.append(tot); terms.append(term)
+            fans.append(len(ch)); acts.append(0.0)
+            for a, s in reversed(ch):
+                stack.append(("A", a, s, d))
+        else:
+            _, a, slot, d = item
+            r = rec[slot]
+            kinds.append(1); depths.append(d); counts.append(int(r["na"])); totals.append(float(r["total"]))
+            terms.append(0); fans.append(1); acts.append(float(a))
+            stack.append(("S", slot, d + 1))
+    return dict(kind=np.asarray(kinds, np.uint8), depth=np.asarray(depths, np.int32), count=np.asarray(counts, np.int64),
+                total=np.asarray(totals, np.float64), terminal=np.asarray(terms, np.uint8),
+                fanout=np.asarray(fans, np.int32), action=np.asarray(acts, np.float64))
+
+
+# ---------------------------------------------------------------------- stateless batched primitives
+def _real(precision):
+    return torch.float64 if precision == _lib.PRECISION_F64 else torch.float32
+
+
+def env_step(env_id: int, states, actions, precision: int = _lib.PRECISION_F32, device="cuda:0"):
+    """gym ``env.step`` over a batch on the device.  Returns (next_states, rewards, terminated)."""
+    dev = _require_cuda(device)
+    lib = _lib.load()
+    dt = _real(precision)
+    S = STATE_DIM[env_id]
+    s = torch.as_tensor(states).to(dev, dt).reshape(-1, S).contiguous()
+    a = torch.as_tensor(actions).to(dev, dt).reshape(-1).contiguous()
+    n = s.shape[0]
+    ns = torch.empty_like(s)
+    r = torch.empty(n, dtype=dt, device=dev)
+    t = torch.empty(n, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.isla_env_step(env_id, precision, C.c_void_p(s.data_ptr()), C.c_void_p(a.data_ptr()), n,
+                                C.c_void_p(ns.data_ptr()), C.c_void_p(r.data_ptr()), C.c_void_p(t.data_ptr()),
+                                C.c_void_p(_stream_ptr(dev))))
+    return ns, r, t
+
+
+def rollout(env_id: int, states, n: int | None = None, budget: int = 500, gamma: float = 0.99, seed: int = 0,
+            sim: int = 0, precision: int = _lib.PRECISION_F32, device="cuda:0"):
+    """Random-policy rollouts (abstract_mcts.py:72-91).  states=None starts from the reset distribution."""
+    dev = _require_cuda(device)
+    lib = _lib.load()
+    dt = _real(precision)
+    if states is not None:
+        s = torch.as_tensor(states).to(dev, dt).reshape(-1, STATE_DIM[env_id]).contiguous()
+        n = s.shape[0]
+        sp = C.c_void_p(s.data_ptr())
+    else:
+        sp = C.c_void_p(0)
+    ret = torch.empty(n, dtype=torch.float64, device=dev)
+    steps = torch.empty(n, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.isla_rollout(env_id, precision, sp, int(n), int(budget), float(gamma), int(seed), int(sim),
+                               C.c_void_p(ret.data_ptr()), C.c_void_p(steps.data_ptr()), C.c_void_p(_stream_ptr(dev))))
+    return ret, steps
+
+
+def merge_root_stats(na, total, group, n_roots: int):
+    """Per-root sums over trees sharing a root (the local half of the root-parallel merge)."""
+    lib = _lib.load()
+    dev = na.device
+    n_trees, A = na.shape
+    na_out = torch.empty((n_roots, A), dtype=torch.int64, device=dev)
+    tot_out = torch.empty((n_roots, A), dtype=torch.float64, device=dev)
+    gp = C.c_void_p(group.data_ptr()) if group is not None else C.c_void_p(0)
+    with torch.cuda.device(dev):
+        check(lib.isla_merge_root_stats(C.c_void_p(na.data_ptr()), C.c_void_p(total.data_ptr()), gp, n_trees, A,
+                                        int(n_roots), C.c_void_p(na_out.data_ptr()), C.c_void_p(tot_out.data_ptr()),
+                                        C.c_void_p(_stream_ptr(dev))))
+    return na_out, tot_out

@@ -1,0 +1,115 @@
+"""CUDA env dynamics and rollouts vs the CPU oracle (called through the C ABI)."""
+import numpy as np
+import pytest
+
+from oracle import coracle
+
+pytestmark = pytest.mark.gpu
+
+ENVS = [0, 1, 2, 3]
+
+
+def _random_states(env_id, n, rng):
+    if env_id == 0:
+        s = rng.uniform([-2.3, -2.0, -0.2, -2.5], [2.3, 2.0, 0.2, 2.5], size=(n, 4))
+        a = rng.integers(0, 2, n).astype(np.float64)
+    elif env_id == 1:
+        s = rng.uniform([-12.0, -8.0], [12.0, 8.0], size=(n, 2))
+        a = rng.uniform(-2.5, 2.5, n).astype(np.float32).astype(np.float64)
+    elif env_id == 2:
+        s = rng.uniform([-1.2, -0.07], [0.6, 0.07], size=(n, 2)).astype(np.float32).astype(np.float64)
+        a = rng.uniform(-1.2, 1.2, n).astype(np.float32).astype(np.float64)
+    else:
+        s = rng.integers(0, 16, size=(n, 1)).astype(np.float64)
+        a = rng.integers(0, 4, n).astype(np.float64)
+    return s, a
+
+
+@pytest.mark.parametrize("env_id", ENVS)
+def test_env_step_f64_matches_oracle(env_id):
+    from islamcts_b200 import engine as E
+    rng = np.random.default_rng(env_id)
+    s, a = _random_states(env_id, 4096, rng)
+    ns, r, t = E.env_step(env_id, s, a, precision=1)
+    ns, r, t = ns.cpu().numpy(), r.cpu().numpy(), t.cpu().numpy()
+    for i in range(len(s)):
+        ens, er, et, _ = coracle.env_step(env_id, s[i], a[i])
+        # same IEEE operations in the same order; CUDA and glibc sin/cos may differ in the last ulp
+        np.testing.assert_allclose(ns[i], ens, rtol=1e-13, atol=1e-15)
+        assert r[i] == pytest.approx(er, rel=1e-13, abs=1e-15)
+        assert bool(t[i]) == et
+
+
+@pytest.mark.parametrize("env_id", ENVS)
+def test_env_step_f32_within_1e5(env_id):
+    """north_star: continuous env states and rewards under identical fed-in actions within 1e-5 relative (fp32)."""
+    from islamcts_b200 import engine as E
+    rng = np.random.default_rng(10 + env_id)
+    s, a = _random_states(env_id, 4096, rng)
+    s = s.astype(np.float32).astype(np.float64)  # feed values exactly representable in fp32
+    ns, r, t = E.env_step(env_id, s, a, precision=0)
+    ns, r, t = ns.cpu().numpy().astype(np.float64), r.cpu().numpy().astype(np.float64), t.cpu().numpy()
+    mism = 0
+    for i in range(len(s)):
+        ens, er, et, _ = coracle.env_step(env_id, s[i], a[i])
+        if env_id == 3:
+            assert ns[i][0] == ens[0] and r[i] == er and bool(t[i]) == et   # FrozenLake: bit-exact
+            continue
+        scale = np.maximum(np.abs(ens), np.abs(s[i]))  # relative to the state magnitude
+        assert np.all(np.abs(ns[i] - ens) <= 1e-5 * scale + 1e-7), (i, ns[i], ens)
+        assert abs(r[i] - er) <= 1e-5 * max(1.0, abs(er))
+        mism += int(bool(t[i]) != et)
+    assert mism <= 2  # a threshold crossing decided differently in fp32 needs a state within 1e-7 of it
+
+
+@pytest.mark.parametrize("env_id", ENVS)
+def test_scripted_trajectories_short_horizon(env_id):
+    """Same fed-in action sequence for 25 steps from reset states; fp32 device vs float64 oracle."""
+    from islamcts_b200 import engine as E
+    import torch
+    rng = np.random.default_rng(20 + env_id)
+    n, T = 512, 25
+    s0 = np.stack([coracle.env_reset(env_id, 7, i) for i in range(n)])
+    _, acts = _random_states(env_id, n * T, rng)
+    acts = acts.reshape(T, n)
+    dev_s = torch.as_tensor(s0, dtype=torch.float32)
+    cpu_s = s0.astype(np.float32).astype(np.float64)
+    alive = np.ones(n, bool)
+    for k in range(T):
+        ns, r, t = E.env_step(env_id, dev_s, acts[k], precision=0)
+        dev_s = ns
+        got = ns.cpu().numpy().astype(np.float64)
+        for i in np.flatnonzero(alive):
+            ens, er, et, _ = coracle.env_step(env_id, cpu_s[i], acts[k][i])
+            cpu_s[i] = ens
+            tol = 1e-5 * np.maximum(1.0, np.abs(ens)) * (1 + k)  # round-off grows along the trajectory
+            assert np.all(np.abs(got[i] - ens) <= tol), (env_id, k, i, got[i], ens)
+            if et or bool(t[i].item()):
+                alive[i] = False
+
+
+@pytest.mark.parametrize("env_id,budget,gamma", [(0, 500, 0.99), (1, 200, 0.99), (2, 500, 0.99), (3, 1000, 1.0), (0, 7, 0.9)])
+def test_rollout_f64_matches_oracle_streams(env_id, budget, gamma):
+    from islamcts_b200 import engine as E
+    n = 1500
+    s0 = np.stack([coracle.env_reset(env_id, 3, i) for i in range(n)])
+    ret, steps = E.rollout(env_id, s0, budget=budget, gamma=gamma, seed=99, sim=5, precision=1)
+    ret, steps = ret.cpu().numpy(), steps.cpu().numpy()
+    for i in range(n):
+        eret, esteps = coracle.rollout(env_id, s0[i], budget, gamma, 99, i, 5, 0)
+        assert steps[i] == esteps, (i, steps[i], esteps)
+        assert ret[i] == pytest.approx(eret, rel=1e-11, abs=1e-11)
+
+
+def test_rollout_reset_distribution_and_f32_agreement():
+    from islamcts_b200 import engine as E
+    n = 20000
+    ret64, st64 = E.rollout(0, None, n=n, budget=500, gamma=0.99, seed=5, sim=0, precision=1)
+    ret32, st32 = E.rollout(0, None, n=n, budget=500, gamma=0.99, seed=5, sim=0, precision=0)
+    st64, st32 = st64.cpu().numpy(), st32.cpu().numpy()
+    # device-side reset == oracle reset (first few) and fp32 rollouts end on the same step almost always
+    for i in range(64):
+        eret, esteps = coracle.rollout(0, coracle.env_reset(0, 5, i), 500, 0.99, 5, i, 0, 0)
+        assert st64[i] == esteps
+    assert (st64 != st32).mean() < 2e-3
+    assert 15 < st64.mean() < 30   # random CartPole episodes last ~22 steps

@@ -1,0 +1,142 @@
+"""Thread-per-tree vanilla engine vs the reference goldens and the CPU oracle (through the C ABI)."""
+import numpy as np
+import pytest
+
+from oracle import coracle
+from tests.golden_util import assert_tree_equal, engine_kwargs, load_golden
+
+pytestmark = pytest.mark.gpu
+
+VANILLA_GOLDENS = ["hash_cartpole", "hash_cartpole_shallow", "mcts_lake", "mcts_lake_long", "hash_lake"]
+
+
+def _engine_from_golden(g, precision, kernel, n_trees=1):
+    from islamcts_b200.engine import Engine
+    kw = engine_kwargs(g["config"])
+    return Engine(kw["env_id"], agent=kw["agent"], n_trees=n_trees, sim_capacity=g["config"]["n_sim"] + 8,
+                  max_depth=kw["max_depth"], C_=kw["C"], gamma=kw["gamma"], n_actions=kw["n_actions"],
+                  budget_mode=kw["budget_mode"], precision=precision, kernel=kernel)
+
+
+@pytest.mark.parametrize("name", VANILLA_GOLDENS)
+@pytest.mark.parametrize("precision", [1, 0])
+def test_scripted_trace_rebuilds_reference_tree_tpt(name, precision):
+    """Replay the reference's decision trace: integer counts bit-exact, totals to 1e-9 (f64 env) / 1e-6 (f32 env)."""
+    g = load_golden(name)
+    eng = _engine_from_golden(g, precision, kernel=1)
+    eng.set_roots(g["root_state"][None, :])
+    kinds, vals = g["trace_kind"], g["trace_value"]
+    eng.run_scripted(0, g["config"]["n_sim"], kinds, vals)
+    meta = eng.tree_meta(0)
+    assert meta["fault"] == 0, meta
+    assert meta["trace_pos"] == len(kinds) - 1
+    assert meta["sims"] == g["config"]["n_sim"]
+    got = eng.export_tree(0)
+    tol = 1e-9 if precision == 1 else 1e-6
+    assert_tree_equal(got, g, rtol=tol, atol=tol, label=f"{name}/p{precision}: ")
+    # end of fit(): arg-max with the recorded tie-break position
+    best = int(eng.best(scripted_pos=int(vals[-1])).cpu()[0])
+    assert float(best) == float(g["fit_action"])
+    na, tot = eng.root_stats()
+    na, tot = na.cpu().numpy()[0], tot.cpu().numpy()[0]
+    for a, n_, t_ in zip(g["root_action"].astype(int), g["root_na"], g["root_total"]):
+        assert na[a] == n_
+        assert tot[a] == pytest.approx(t_, rel=tol, abs=tol)
+
+
+@pytest.mark.parametrize("env_id,n_sim,max_depth,C,gamma", [(0, 300, 500, 1.0, 0.99), (0, 200, 12, 4.0, 0.9),
+                                                             (3, 300, 40, 0.5, 0.95), (3, 100, 1000, 0.5, 1.0)])
+def test_free_running_f64_equals_oracle_bit_for_bit(env_id, n_sim, max_depth, C, gamma):
+    """Same Philox streams on both sides: every tree's root counts are identical, totals to 1e-9."""
+    from islamcts_b200.engine import Engine
+    n_trees, A = 192, (2 if env_id == 0 else 4)
+    roots = np.stack([coracle.env_reset(env_id, 11, i) for i in range(n_trees)])
+    eng = Engine(env_id, n_trees=n_trees, sim_capacity=n_sim, max_depth=max_depth, C_=C, gamma=gamma, precision=1,
+                 kernel=1, seed=1234, tree_id_base=1000)
+    eng.set_roots(roots).run(n_sim)
+    na, tot = eng.root_stats()
+    na, tot = na.cpu().numpy(), tot.cpu().numpy()
+    cfg = coracle.make_config(env_id, n_actions=A, max_depth=max_depth, C_=C, gamma=gamma, seed=1234, tree_id=1000)
+    ena, etot, ecnt = coracle.run_many(cfg, roots, n_sim, n_threads=8)
+    np.testing.assert_array_equal(na, ena)
+    np.testing.assert_allclose(tot, etot, rtol=1e-9, atol=1e-9)
+    cnt = eng.counters()
+    assert cnt["faults"] == 0 and cnt["sims"] == n_trees * n_sim
+    assert cnt["levels"] == ecnt["levels"]
+    assert cnt["rollout_steps"] == ecnt["rollout_steps"]
+    # a full tree, not just the root: tree 5 against the oracle's serialisation
+    c5 = coracle.make_config(env_id, n_actions=A, max_depth=max_depth, C_=C, gamma=gamma, seed=1234, tree_id=1005)
+    t5 = coracle.Tree(c5, roots[5])
+    t5.run(n_sim)
+    exp = {"tree_" + k: v for k, v in t5.serialise().items()}
+    assert_tree_equal(eng.export_tree(5), exp)
+    # arg-max pick draws from the same tree stream
+    best = eng.best().cpu().numpy()
+    _, rank, act = t5.best()
+    assert best[5] == int(act)
+
+
+def test_free_running_f32_env_agrees_with_f64_oracle_statistically():
+    """fp32 env on the device vs float64 oracle: FrozenLake identical; CartPole trees identical unless a
+    rollout's termination threshold is crossed differently in fp32 (rare) -- >= 97% identical trees."""
+    from islamcts_b200.engine import Engine
+    for env_id, A, thresh in [(3, 4, 1.0), (0, 2, 0.97)]:
+        n_trees, n_sim = 256, 200
+        roots = np.stack([coracle.env_reset(env_id, 21, i) for i in range(n_trees)])
+        eng = Engine(env_id, n_trees=n_trees, sim_capacity=n_sim, max_depth=100, C_=1.0, gamma=0.95, precision=0, kernel=1, seed=77)
+        eng.set_roots(roots).run(n_sim)
+        na = eng.root_stats()[0].cpu().numpy()
+        cfg = coracle.make_config(env_id, n_actions=A, max_depth=100, C_=1.0, gamma=0.95, seed=77)
+        ena, etot, _ = coracle.run_many(cfg, roots, n_sim, n_threads=8)
+        same = (na == ena).all(axis=1).mean()
+        assert same >= thresh, (env_id, same)
+        assert (na.sum(axis=1) == n_sim).all()
+
+
+def test_fit_twice_continues_the_tree_and_capacity_fault_is_loud():
+    from islamcts_b200.engine import Engine
+    roots = np.stack([coracle.env_reset(0, 1, i) for i in range(64)])
+    eng = Engine(0, n_trees=64, sim_capacity=100, precision=1, kernel=1, seed=3)
+    eng.set_roots(roots).run(50).run(50)
+    na = eng.root_stats()[0].cpu().numpy()
+    assert (na.sum(axis=1) == 100).all()          # "calling fit() twice continues the same tree"
+    one = Engine(0, n_trees=64, sim_capacity=100, precision=1, kernel=1, seed=3)
+    one.set_roots(roots).run(100)
+    np.testing.assert_array_equal(na, one.root_stats()[0].cpu().numpy())
+    eng.run(50)                                    # beyond sim_capacity: every tree reports a fault
+    assert eng.counters()["faults"] > 0
+
+
+def test_c5_shape_invariants_full_size():
+    """BASELINE C5 shape on one GPU: 65 536 CartPole trees x 1000 sims; integer invariants of SURVEY 8(a)."""
+    from islamcts_b200.engine import Engine
+    import torch
+    n_trees, n_sim = 65536, 1000
+    roots = np.stack([coracle.env_reset(0, 0, i) for i in range(4096)])
+    roots = np.tile(roots, (16, 1))
+    eng = Engine(0, n_trees=n_trees, sim_capacity=n_sim, max_depth=500, C_=1.0, gamma=0.99, precision=0, kernel=1, seed=0)
+    eng.set_roots(roots).run(n_sim)
+    na, tot = eng.root_stats()
+    torch.cuda.synchronize()
+    assert bool((na.sum(dim=1) == n_sim).all())   # root ns = sum na = n_sim
+    cnt = eng.counters()
+    assert cnt["faults"] == 0 and cnt["sims"] == n_trees * n_sim
+    assert cnt["nodes"] <= n_trees * n_sim        # at most one new node per simulation
+    q = (tot / na.clamp(min=1)).cpu().numpy()
+    assert np.isfinite(q).all() and q.max() <= 100.0 + 1e-9   # sum gamma^t < 1/(1-gamma)
+
+
+def test_merge_root_stats_matches_numpy():
+    from islamcts_b200 import engine as E
+    import torch
+    rng = np.random.default_rng(0)
+    n_trees, A, R = 5000, 2, 37
+    na = torch.as_tensor(rng.integers(0, 1000, (n_trees, A)), device="cuda:0")
+    tot = torch.as_tensor(rng.normal(size=(n_trees, A)), device="cuda:0")
+    grp = torch.as_tensor(rng.integers(0, R, n_trees).astype(np.int32), device="cuda:0")
+    mna, mtot = E.merge_root_stats(na, tot, grp, R)
+    ena = np.zeros((R, A), np.int64); etot = np.zeros((R, A))
+    np.add.at(ena, grp.cpu().numpy(), na.cpu().numpy())
+    np.add.at(etot, grp.cpu().numpy(), tot.cpu().numpy())
+    np.testing.assert_array_equal(mna.cpu().numpy(), ena)
+    np.testing.assert_allclose(mtot.cpu().numpy(), etot, rtol=1e-12, atol=1e-12)
