@@ -64,7 +64,7 @@ typedef struct {
     int32_t kernel;             /* ISLA_KERNEL_* */
     int32_t block_threads;      /* CTA-per-tree kernel: threads per tree (multiple of 32); 0 = auto */
     int32_t sim_capacity;       /* max cumulative simulations per tree the workspace is sized for */
-    int32_t reserved0;
+    int32_t tuning;             /* experiment flags for A/B timing; 0 = defaults */
     double C;                   /* param.C */
     double gamma;               /* param.gamma */
     double alpha1, k1;          /* PwParameters.alpha/k ; DpwParameters.alphaApw/kApw */
@@ -89,6 +89,8 @@ typedef struct {
     int64_t meta_offset;                    /* per-tree int32[8]: alloc, sims, rng words consumed, fault, ... */
     int64_t path_offset;
     int64_t counters_offset;                /* int64[8] device counters */
+    int64_t ln_offset, ln_count;            /* double ln(n), n < ln_count  (host libm log, like numpy)  */
+    int64_t disc_offset, disc_count;        /* double gamma**t, t < disc_count (host libm pow, like CPython) */
     /* CTA-per-tree (general) pools, offsets of the per-tree blocks and their strides */
     int64_t s_cap, a_cap;                   /* state / action node capacity per tree */
     int64_t pool_offset, pool_stride;       /* bytes per tree of the general node pool */

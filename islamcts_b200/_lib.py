@@ -34,7 +34,7 @@ class IslaConfig(C.Structure):
         ("env_id", C.c_int32), ("agent", C.c_int32), ("n_actions", C.c_int32), ("max_depth", C.c_int32),
         ("budget_mode", C.c_int32), ("rollouts_per_leaf", C.c_int32), ("expansion", C.c_int32),
         ("voo_n_samples", C.c_int32), ("voo_max_try", C.c_int32), ("precision", C.c_int32),
-        ("kernel", C.c_int32), ("block_threads", C.c_int32), ("sim_capacity", C.c_int32), ("reserved0", C.c_int32),
+        ("kernel", C.c_int32), ("block_threads", C.c_int32), ("sim_capacity", C.c_int32), ("tuning", C.c_int32),
         ("C", C.c_double), ("gamma", C.c_double), ("alpha1", C.c_double), ("k1", C.c_double),
         ("alpha2", C.c_double), ("k2", C.c_double), ("epsilon", C.c_double),
         ("seed", C.c_uint64), ("tree_id_base", C.c_uint64), ("n_trees", C.c_int64),
@@ -46,7 +46,8 @@ class IslaLayout(C.Structure):
         ("kernel", C.c_int32), ("state_dim", C.c_int32), ("real_bytes", C.c_int32), ("n_actions", C.c_int32),
         ("slots_per_tree", C.c_int64), ("rec_offset", C.c_int64), ("rec_stride", C.c_int64),
         ("state_offset", C.c_int64), ("state_stride", C.c_int64), ("meta_offset", C.c_int64),
-        ("path_offset", C.c_int64), ("counters_offset", C.c_int64), ("s_cap", C.c_int64), ("a_cap", C.c_int64),
+        ("path_offset", C.c_int64), ("counters_offset", C.c_int64), ("ln_offset", C.c_int64), ("ln_count", C.c_int64),
+        ("disc_offset", C.c_int64), ("disc_count", C.c_int64), ("s_cap", C.c_int64), ("a_cap", C.c_int64),
         ("pool_offset", C.c_int64), ("pool_stride", C.c_int64), ("total_bytes", C.c_int64),
     ]
 

@@ -2,8 +2,10 @@
 // thread-per-tree and CTA-per-tree kernels, the root-statistics merge and error reporting.
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "isla_envs.cuh"
 #include "isla_internal.h"
@@ -21,6 +23,27 @@ void set_error(const char* fmt, ...) {
 int cuda_fail(cudaError_t e, const char* what) {
     set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
     return ISLA_ERR_CUDA;
+}
+
+// ln(n) and gamma**t are computed on the HOST with the C library -- the same libm calls numpy's np.log
+// (utils/action_selection_functions.py:21) and CPython's pow(gamma, t) (agents/abstract_mcts.py:87) end in --
+// so mathematically tied UCB scores stay bit-identical ties on the device.
+void add_table_layout(const isla_config& cfg, isla_layout& lay, int64_t& off) {
+    auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
+    lay.ln_count = (int64_t)cfg.sim_capacity + 8;
+    lay.disc_count = (int64_t)cfg.max_depth + 2;
+    lay.ln_offset = off; off = up(off + lay.ln_count * 8);
+    lay.disc_offset = off; off = up(off + lay.disc_count * 8);
+}
+int upload_tables(isla_engine* e) {
+    std::vector<double> ln((size_t)e->lay.ln_count), disc((size_t)e->lay.disc_count);
+    ln[0] = 0.0;
+    for (size_t i = 1; i < ln.size(); ++i) ln[i] = std::log((double)i);
+    for (size_t t = 0; t < disc.size(); ++t) disc[t] = std::pow(e->cfg.gamma, (double)t);
+    ISLA_CUDA_OK(cudaMemcpy(e->ws + e->lay.ln_offset, ln.data(), ln.size() * 8, cudaMemcpyHostToDevice));
+    ISLA_CUDA_OK(cudaMemcpy(e->ws + e->lay.disc_offset, disc.data(), disc.size() * 8, cudaMemcpyHostToDevice));
+    ISLA_CUDA_OK(cudaDeviceSynchronize());
+    return 0;
 }
 
 static int resolve_kernel(const isla_config& c) {
@@ -106,6 +129,8 @@ int isla_engine_create(const isla_config* cfg, void* workspace_dev, int64_t work
     int dev = 0;
     ISLA_CUDA_OK(cudaGetDevice(&dev));
     ISLA_CUDA_OK(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, dev));
+    rc = upload_tables(e);
+    if (rc) { delete e; return rc; }
     *out = e;
     return ISLA_OK;
 }

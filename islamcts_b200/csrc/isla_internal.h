@@ -53,7 +53,9 @@ struct TptParams {
     unsigned long long seed;
     unsigned long long tree_id_base;
     double C, gamma;
-    int n_sim, max_depth, budget_mode, block_cap, ln_table_n;
+    const double* ln_table;    // host-computed ln(n)
+    const double* disc_table;  // host-computed gamma**t
+    int n_sim, max_depth, budget_mode, block_cap, ln_count, disc_count, ln_in_smem, tuning;
 };
 
 }  // namespace isla
@@ -69,6 +71,8 @@ struct isla_engine {
 
 namespace isla {
 // thread-per-tree engine (isla_tree_tpt.cu)
+int upload_tables(isla_engine* e);
+void add_table_layout(const isla_config& cfg, isla_layout& lay, int64_t& off);
 int tpt_fill_layout(const isla_config& cfg, isla_layout& lay);
 int tpt_set_roots(isla_engine* e, const double* roots_dev, cudaStream_t st);
 int tpt_run(isla_engine* e, int n_sim, long long scripted_tree, const uint8_t* kinds, const double* values,

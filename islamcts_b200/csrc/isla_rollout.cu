@@ -6,6 +6,9 @@
 //                    continuous_default_policy             (utils/action_selection_functions.py:46-47)
 // Roofline: FP32 issue rate (state never leaves registers; HBM traffic is one state read and one
 // 12-byte result write per trajectory).
+#include <cmath>
+#include <vector>
+
 #include "isla_envs.cuh"
 #include "isla_internal.h"
 #include "isla_philox.cuh"
@@ -32,8 +35,9 @@ __global__ void env_step_kernel(const T* __restrict__ states, const T* __restric
 
 template <int ENV, typename T>
 __global__ void __launch_bounds__(256) rollout_kernel(const T* __restrict__ states, long long n, int budget, double gamma,
-                                                      unsigned long long seed, unsigned sim, double* __restrict__ returns,
-                                                      int32_t* __restrict__ steps, unsigned long long* __restrict__ total_steps) {
+                                                      unsigned long long seed, unsigned sim, const double* __restrict__ disc_table,
+                                                      double* __restrict__ returns, int32_t* __restrict__ steps,
+                                                      unsigned long long* __restrict__ total_steps) {
     constexpr int S = EnvTraits<ENV>::S;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int t = 0;
@@ -47,14 +51,13 @@ __global__ void __launch_bounds__(256) rollout_kernel(const T* __restrict__ stat
         }
         Stream rs;
         rs.init(seed, sim, (uint32_t)i, 0u);
-        double R = 0.0, disc = 1.0;
+        double R = 0.0;
         bool done = false;
         while (!done && t < budget) {
             const T a = sample_action<ENV, T>(rs);
             T r;
             done = Env<ENV, T>::step(s, a, r);
-            R = __dadd_rn(R, __dmul_rn((double)r, disc));
-            disc = __dmul_rn(disc, gamma);
+            R = __dadd_rn(R, __dmul_rn((double)r, __ldg(disc_table + t)));  // r * pow(gamma, t), host libm pow
             ++t;
         }
         returns[i] = R;
@@ -86,14 +89,22 @@ template <typename T>
 int rollout_dispatch(int env, const void* s, long long n, int budget, double gamma, unsigned long long seed, unsigned sim,
                      double* ret, int32_t* steps, cudaStream_t st) {
     const unsigned grid = (unsigned)((n + 255) / 256);
+    // gamma**t table from the host libm (CPython's pow, agents/abstract_mcts.py:87), stream-ordered scratch
+    std::vector<double> h((size_t)(budget > 0 ? budget : 1));
+    for (size_t t = 0; t < h.size(); ++t) h[t] = std::pow(gamma, (double)t);
+    double* disc = nullptr;
+    ISLA_CUDA_OK(cudaMallocAsync((void**)&disc, h.size() * 8, st));
+    ISLA_CUDA_OK(cudaMemcpyAsync(disc, h.data(), h.size() * 8, cudaMemcpyHostToDevice, st));
+    ISLA_CUDA_OK(cudaStreamSynchronize(st));  // h is pageable host memory
     switch (env) {
-    case ENV_CARTPOLE: rollout_kernel<ENV_CARTPOLE, T><<<grid, 256, 0, st>>>((const T*)s, n, budget, gamma, seed, sim, ret, steps, nullptr); break;
-    case ENV_PENDULUM: rollout_kernel<ENV_PENDULUM, T><<<grid, 256, 0, st>>>((const T*)s, n, budget, gamma, seed, sim, ret, steps, nullptr); break;
-    case ENV_MOUNTAINCAR: rollout_kernel<ENV_MOUNTAINCAR, T><<<grid, 256, 0, st>>>((const T*)s, n, budget, gamma, seed, sim, ret, steps, nullptr); break;
-    case ENV_FROZENLAKE: rollout_kernel<ENV_FROZENLAKE, T><<<grid, 256, 0, st>>>((const T*)s, n, budget, gamma, seed, sim, ret, steps, nullptr); break;
-    default: set_error("unknown env %d", env); return ISLA_ERR_INVALID;
+    case ENV_CARTPOLE: rollout_kernel<ENV_CARTPOLE, T><<<grid, 256, 0, st>>>((const T*)s, n, budget, gamma, seed, sim, disc, ret, steps, nullptr); break;
+    case ENV_PENDULUM: rollout_kernel<ENV_PENDULUM, T><<<grid, 256, 0, st>>>((const T*)s, n, budget, gamma, seed, sim, disc, ret, steps, nullptr); break;
+    case ENV_MOUNTAINCAR: rollout_kernel<ENV_MOUNTAINCAR, T><<<grid, 256, 0, st>>>((const T*)s, n, budget, gamma, seed, sim, disc, ret, steps, nullptr); break;
+    case ENV_FROZENLAKE: rollout_kernel<ENV_FROZENLAKE, T><<<grid, 256, 0, st>>>((const T*)s, n, budget, gamma, seed, sim, disc, ret, steps, nullptr); break;
+    default: cudaFreeAsync(disc, st); set_error("unknown env %d", env); return ISLA_ERR_INVALID;
     }
     ISLA_CUDA_OK(cudaGetLastError());
+    ISLA_CUDA_OK(cudaFreeAsync(disc, st));
     return 0;
 }
 

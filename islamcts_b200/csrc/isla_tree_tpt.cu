@@ -46,9 +46,17 @@ struct TraceCursor {
     }
 };
 
+__device__ __forceinline__ int4 ldcg_256(const int4* p) {
+    int4 v;
+    asm volatile("ld.global.cg.L2::256B.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+template <bool PF256 = false>
 __device__ __forceinline__ EdgeRec load_rec(const EdgeRec* p) {
-    // L2-only loads: the records are updated through RED atomics at L2, never reuse L1
-    const int4 lo = __ldcg(reinterpret_cast<const int4*>(p));
+    // L2-only loads: the records are updated through RED atomics at L2, never reuse L1.
+    // PF256: ask L2 to fetch the whole 256-byte neighbourhood -- the blocks of the principal
+    // variation are allocated consecutively, so the next tree levels usually live there.
+    const int4 lo = PF256 ? ldcg_256(reinterpret_cast<const int4*>(p)) : __ldcg(reinterpret_cast<const int4*>(p));
     const int4 hi = __ldcg(reinterpret_cast<const int4*>(p) + 1);
     EdgeRec r;
     r.total_in = __hiloint2double(lo.y, lo.x);
@@ -72,9 +80,12 @@ template <int ENV, typename T, bool SCRIPTED>
 __global__ void __launch_bounds__(kTptBlock) tpt_search_kernel(const TptParams p) {
     constexpr int A = EnvTraits<ENV>::A;
     constexpr int S = EnvTraits<ENV>::S;
-    extern __shared__ double ln_table[];  // ln(n) for n < ln_table_n (same ::log as the direct path)
-    for (int i = threadIdx.x; i < p.ln_table_n; i += blockDim.x) ln_table[i] = i > 0 ? ::log((double)i) : 0.0;
-    __syncthreads();
+    extern __shared__ double ln_smem[];  // copy of the host-computed ln(n) table when it fits
+    if (p.ln_in_smem) {
+        for (int i = threadIdx.x; i < p.ln_count; i += blockDim.x) ln_smem[i] = p.ln_table[i];
+        __syncthreads();
+    }
+    const double* const ln_table = p.ln_in_smem ? ln_smem : p.ln_table;
 
     const long long tree = SCRIPTED ? p.scripted_tree : (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (tree >= p.n_trees) return;
@@ -120,7 +131,14 @@ __global__ void __launch_bounds__(kTptBlock) tpt_search_kernel(const TptParams p
                 nun = A;
             } else {
 #pragma unroll
-                for (int a = 0; a < A; ++a) { c[a] = load_rec(recs + (long long)blk * A + a); nun += (c[a].na_in == 0); }
+                for (int a = 0; a < A; ++a) {
+                    c[a] = (p.tuning & 2) ? load_rec<false>(recs + (long long)blk * A + a) : load_rec<true>(recs + (long long)blk * A + a);
+                    nun += (c[a].na_in == 0);
+                }
+                if (p.tuning & 4) {  // explicit look-ahead: the blocks 4 and 8 ahead of this one
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(recs + (long long)(blk + 4) * A));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(recs + (long long)(blk + 8) * A));
+                }
             }
             if (nun > 0) {
                 // ---- expansion: uniformly random unvisited action (mcts_hash.py:70-74)
@@ -153,8 +171,8 @@ __global__ void __launch_bounds__(kTptBlock) tpt_search_kernel(const TptParams p
                         for (int i = 0; i < S; ++i) __stcg(states + (long long)child * S + i, st[i]);
                     }
                     // ---- rollout (abstract_mcts.py:72-91), budget per mcts_hash.py:116
-                    int budget = p.budget_mode == ISLA_BUDGET_ZERO ? 0 : p.max_depth - (level + 1);
-                    double R = 0.0, disc = 1.0;
+                    const int budget = p.budget_mode == ISLA_BUDGET_ZERO ? 0 : min(p.max_depth - (level + 1), p.disc_count);
+                    double R = 0.0;
                     bool done = false;
                     Stream rs;
                     if constexpr (!SCRIPTED) rs.init(p.seed, sims_done, tree_id, 0u);
@@ -171,8 +189,7 @@ __global__ void __launch_bounds__(kTptBlock) tpt_search_kernel(const TptParams p
                         }
                         T rr;
                         done = Env<ENV, T>::step(st, act, rr);
-                        R = __dadd_rn(R, __dmul_rn((double)rr, disc));
-                        disc = __dmul_rn(disc, gamma);
+                        R = __dadd_rn(R, __dmul_rn((double)rr, __ldg(p.disc_table + t)));  // r * pow(gamma, t)
                         ++t;
                     }
                     c_roll += t; c_env += t;
@@ -183,32 +200,59 @@ __global__ void __launch_bounds__(kTptBlock) tpt_search_kernel(const TptParams p
                 ++c_nodes;
                 break;
             }
-            // ---- UCB1 over the A visited children (action_selection_functions.py:9-25), float64
+            // ---- UCB1 over the A visited children (action_selection_functions.py:9-25).
+            // The reference evaluates the scores in float64 and breaks exact ties at random.  An fp32
+            // screening pass (error < 1e-6 relative, tolerance 1e-5) settles the arg-max whenever it is
+            // unambiguous; only near-ties take the exact float64 path, so the DECISIONS are the float64 ones.
             int ns = (node != 0);
 #pragma unroll
             for (int a = 0; a < A; ++a) ns += c[a].na_in;
-            const double lg = ns < p.ln_table_n ? ln_table[ns] : ::log((double)ns);
-            double sc[A], best = -INFINITY;
-#pragma unroll
-            for (int a = 0; a < A; ++a) {
-                const double na = (double)c[a].na_in;
-                const double q = __ddiv_rn(c[a].total_in, na);
-                const double ex = __dmul_rn(Cexp, __dsqrt_rn(__ddiv_rn(lg, na)));
-                sc[a] = __dadd_rn(q, ex);
-                best = fmax(best, sc[a]);
-            }
-            int ties = 0;
-#pragma unroll
-            for (int a = 0; a < A; ++a) ties += (sc[a] == best);
-            int pos = (SCRIPTED || ties > 1) ? choice(ties) : 0;
-            // the tied set is ordered like node.actions (insertion order = rank)
+            const double lg = ns < p.ln_count ? ln_table[ns] : ::log((double)ns);
             int a_sel = 0;
-#pragma unroll
-            for (int rk = 0; rk < A; ++rk) {
+            bool settled = false;
+            if (!(p.tuning & 1)) {
+                const float lgf = (float)lg, Cf = (float)Cexp;
+                float sf[A], m1 = -INFINITY, scale = 0.f;
 #pragma unroll
                 for (int a = 0; a < A; ++a) {
-                    if ((int)((c[a].flags >> 8) & 0xffu) == rk && sc[a] == best) { if (pos == 0) a_sel = a; --pos; }
+                    const float naf = (float)c[a].na_in;
+                    const float qf = __fdividef((float)c[a].total_in, naf);
+                    const float ef = Cf * sqrtf(__fdividef(lgf, naf));
+                    sf[a] = qf + ef;
+                    m1 = fmaxf(m1, sf[a]);
+                    scale = fmaxf(scale, fabsf(qf) + fabsf(ef));
                 }
+                const float thr = m1 - 1e-5f * scale - 1e-30f;
+                int ncand = 0;
+#pragma unroll
+                for (int a = 0; a < A; ++a) { if (sf[a] >= thr) { ++ncand; a_sel = a; } }
+                settled = (ncand == 1);
+            }
+            int pos = 0;
+            if (!settled) {
+                double sc[A], best = -INFINITY;
+#pragma unroll
+                for (int a = 0; a < A; ++a) {
+                    const double na = (double)c[a].na_in;
+                    const double q = __ddiv_rn(c[a].total_in, na);
+                    const double ex = __dmul_rn(Cexp, __dsqrt_rn(__ddiv_rn(lg, na)));
+                    sc[a] = __dadd_rn(q, ex);
+                    best = fmax(best, sc[a]);
+                }
+                int ties = 0;
+#pragma unroll
+                for (int a = 0; a < A; ++a) ties += (sc[a] == best);
+                pos = (SCRIPTED || ties > 1) ? choice(ties) : 0;
+                // the tied set is ordered like node.actions (insertion order = rank)
+#pragma unroll
+                for (int rk = 0; rk < A; ++rk) {
+#pragma unroll
+                    for (int a = 0; a < A; ++a) {
+                        if ((int)((c[a].flags >> 8) & 0xffu) == rk && sc[a] == best) { if (pos == 0) a_sel = a; --pos; }
+                    }
+                }
+            } else if constexpr (SCRIPTED) {
+                (void)choice(1);  // the reference draws even when the maximum is unique
             }
             const int child = blk * A + a_sel;
             EdgeRec sel = c[0];
@@ -318,7 +362,7 @@ __global__ void tpt_best_kernel(const EdgeRec* recs, int32_t* meta, long long n_
 
 template <int ENV, typename T>
 int launch_search(const TptParams& p, bool scripted, cudaStream_t st) {
-    const size_t smem = (size_t)p.ln_table_n * sizeof(double);
+    const size_t smem = p.ln_in_smem ? (size_t)p.ln_count * sizeof(double) : 0;
     if (scripted) {
         tpt_search_kernel<ENV, T, true><<<1, 1, smem, st>>>(p);
     } else {
@@ -348,6 +392,7 @@ int tpt_fill_layout(const isla_config& cfg, isla_layout& lay) {
     lay.meta_offset = off; off = up(off + cfg.n_trees * META_WORDS * 4);
     lay.path_offset = off; off = up(off + cfg.n_trees * blocks * 8);
     lay.counters_offset = off; off = up(off + 8 * 8);
+    add_table_layout(cfg, lay, off);
     lay.s_cap = lay.a_cap = 0; lay.pool_offset = lay.pool_stride = 0;
     lay.total_bytes = off;
     return 0;
@@ -384,8 +429,11 @@ int tpt_run(isla_engine* e, int n_sim, long long scripted_tree, const uint8_t* k
     p.C = e->cfg.C; p.gamma = e->cfg.gamma;
     p.n_sim = n_sim; p.max_depth = e->cfg.max_depth; p.budget_mode = e->cfg.budget_mode;
     p.block_cap = e->cfg.sim_capacity + 2;
-    const long long want = (long long)e->cfg.sim_capacity + 4;
-    p.ln_table_n = (int)(want * 8 <= 40 * 1024 ? want : 0);
+    p.ln_table = (const double*)(e->ws + L.ln_offset);
+    p.disc_table = (const double*)(e->ws + L.disc_offset);
+    p.ln_count = (int)L.ln_count; p.disc_count = (int)L.disc_count;
+    p.ln_in_smem = (L.ln_count * 8 <= 32 * 1024) ? 1 : 0;
+    p.tuning = e->cfg.tuning;
     const bool scripted = scripted_tree >= 0;
     const bool f64 = e->cfg.precision == ISLA_PRECISION_F64;
     switch (e->cfg.env_id) {

@@ -49,14 +49,17 @@ class Engine:
                  expansion: int = _lib.EXPAND_RANDOM, epsilon: float = 0.7, voo_n_samples: int = 5,
                  voo_max_try: int = 1000, alpha1: float = 0.0, k1: float = 1.0, alpha2: float = 0.0, k2: float = 1.0,
                  precision: int = _lib.PRECISION_F32, kernel: int = _lib.KERNEL_AUTO, block_threads: int = 0,
-                 seed: int = 0, tree_id_base: int = 0, device="cuda:0"):
+                 seed: int = 0, tree_id_base: int = 0, device="cuda:0", tuning: int | None = None):
+        import os
+        if tuning is None:
+            tuning = int(os.environ.get("ISLA_TUNING", "0"))
         self.device = _require_cuda(device)
         self.lib = _lib.load()
         if n_actions is None:
             n_actions = N_ACTIONS[env_id]
         self.cfg = IslaConfig(env_id, agent, int(n_actions or 0), int(max_depth), budget_mode, int(rollouts_per_leaf),
                               expansion, int(voo_n_samples), int(voo_max_try), precision, kernel, int(block_threads),
-                              int(sim_capacity), 0, float(C_), float(gamma), float(alpha1), float(k1), float(alpha2),
+                              int(sim_capacity), int(tuning), float(C_), float(gamma), float(alpha1), float(k1), float(alpha2),
                               float(k2), float(epsilon), int(seed), int(tree_id_base), int(n_trees))
         nbytes = check(self.lib.isla_engine_workspace_bytes(C.byref(self.cfg)))
         with torch.cuda.device(self.device):

@@ -176,6 +176,7 @@ typedef struct {
     int first_act, last_act, n_act;   /* actions dict, insertion order */
     int next_sibling;      /* next entry of the parent's children dict */
     int64_t visit_disc[ORC_MAX_DISCRETE]; /* vanilla/spw: visit_actions ndarray */
+    int blk;               /* instrumentation only: order in which nodes were first descended into */
 } snode;
 
 typedef struct {
@@ -195,7 +196,7 @@ struct orc_tree {
     const uint8_t* tk; const double* tv; int64_t tlen, tpos; int fault;
     stream_t tree_stream, roll_stream;
     uint32_t sim_index; /* cumulative over run() calls */
-    int64_t c_env_steps, c_roll_steps, c_levels, c_sims, c_expand_steps;
+    int64_t c_env_steps, c_roll_steps, c_levels, c_sims, c_expand_steps, c_seq; int next_blk, cur_parent_blk;
 };
 
 static int new_snode(orc_tree* t, const float* obs) {
@@ -512,6 +513,10 @@ static double state_visit(orc_tree* t, int sidx, int level) {
     const orc_config* c = &t->cfg;
     int aidx, disc = -1;
     t->c_levels++;
+    /* instrumentation: would the device tree's block of this node directly follow its parent's? */
+    if (t->S[sidx].blk == 0) t->S[sidx].blk = ++t->next_blk;
+    if (level > 0 && t->S[sidx].blk == t->cur_parent_blk + 1) t->c_seq++;
+    t->cur_parent_blk = t->S[sidx].blk;
     if (c->agent == ORC_AGENT_VANILLA || c->agent == ORC_AGENT_SPW) {
         /* mcts.py:55-62 */
         int cand[ORC_MAX_DISCRETE], nc = 0;
@@ -662,7 +667,7 @@ int64_t orc_tree_serialise(const orc_tree* t, int64_t cap, uint8_t* kind, int32_
 
 void orc_tree_counters(const orc_tree* t, int64_t out[8]) {
     out[0] = t->c_env_steps; out[1] = t->c_roll_steps; out[2] = t->c_levels; out[3] = t->c_sims;
-    out[4] = t->nS; out[5] = t->nA; out[6] = t->c_expand_steps; out[7] = 0;
+    out[4] = t->nS; out[5] = t->nA; out[6] = t->c_expand_steps; out[7] = t->c_seq;
 }
 
 int orc_rollout(int env_id, const double* state, int budget, double gamma, uint64_t seed, uint64_t tree,
