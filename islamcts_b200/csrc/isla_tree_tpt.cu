@@ -76,10 +76,20 @@ __device__ __forceinline__ void store_rec(EdgeRec* p, const EdgeRec& r) {
     __stcg(reinterpret_cast<int4*>(p) + 1, hi);
 }
 
+// One simulation = three warp-converged phases.  Every lane owns a tree, but the lanes of a warp walk
+// their phases in lock-step so that the SIMT width is not lost to divergence:
+//   phase 1  descent      all lanes advance one tree level per iteration until each has found its
+//                          leaf parent (or a terminal edge); lanes that are done idle until the deepest is
+//   phase 2  expand+roll   the pending expansions step the env once, then all rollouts advance one env
+//                          step per iteration (state in registers)
+//   phase 3  backup        levels are walked backwards in lock-step, path entries fetched four at a time
+enum : int { MODE_DESCEND = 0, MODE_EXPAND = 1, MODE_BACKUP = 2, MODE_IDLE = 3 };
+
 template <int ENV, typename T, bool SCRIPTED>
 __global__ void __launch_bounds__(kTptBlock) tpt_search_kernel(const TptParams p) {
     constexpr int A = EnvTraits<ENV>::A;
     constexpr int S = EnvTraits<ENV>::S;
+    constexpr unsigned kFull = 0xffffffffu;
     extern __shared__ double ln_smem[];  // copy of the host-computed ln(n) table when it fits
     if (p.ln_in_smem) {
         for (int i = threadIdx.x; i < p.ln_count; i += blockDim.x) ln_smem[i] = p.ln_table[i];
@@ -87,24 +97,28 @@ __global__ void __launch_bounds__(kTptBlock) tpt_search_kernel(const TptParams p
     }
     const double* const ln_table = p.ln_in_smem ? ln_smem : p.ln_table;
 
-    const long long tree = SCRIPTED ? p.scripted_tree : (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tree >= p.n_trees) return;
+    // scripted (parity) mode drives ONE tree from lane 0 of a single warp; the other lanes are dummies
+    const long long tree = SCRIPTED ? (threadIdx.x == 0 ? p.scripted_tree : p.n_trees)
+                                    : (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = tree < p.n_trees;
+    const long long tix = valid ? tree : 0;
 
-    EdgeRec* const recs = p.recs + tree * p.slots_per_tree;
-    T* const states = reinterpret_cast<T*>(p.states) + tree * p.slots_per_tree * S;
-    int32_t* const meta = p.meta + tree * META_WORDS;
-    int2* const path = p.path + tree;  // level-major: path[level * n_trees]
+    EdgeRec* const recs = p.recs + tix * p.slots_per_tree;
+    T* const states = reinterpret_cast<T*>(p.states) + tix * p.slots_per_tree * S;
+    int32_t* const meta = p.meta + tix * META_WORDS;
+    int2* const path = p.path + tix;  // level-major: path[level * n_trees]
 
-    int alloc = meta[META_ALLOC];
-    uint32_t sims_done = (uint32_t)meta[META_SIMS];
-    int fault = meta[META_FAULT];
-    const uint32_t tree_id = (uint32_t)(p.tree_id_base + (unsigned long long)tree);
+    int alloc = valid ? meta[META_ALLOC] : 0;
+    uint32_t sims_done = valid ? (uint32_t)meta[META_SIMS] : 0u;
+    int fault = valid ? meta[META_FAULT] : 0;
+    const uint32_t tree_id = (uint32_t)(p.tree_id_base + (unsigned long long)tix);
     Stream ts;
-    ts.resume(p.seed, 0u, tree_id, kStreamTree, (uint32_t)meta[META_RNG]);
+    ts.resume(p.seed, 0u, tree_id, kStreamTree, valid ? (uint32_t)meta[META_RNG] : 0u);
     TraceCursor tc{p.trace_kinds, p.trace_values, p.trace_len, 0, 0};
 
     unsigned long long c_env = 0, c_roll = 0, c_levels = 0, c_nodes = 0;
     const double gamma = p.gamma, Cexp = p.C;
+    const float Cf = (float)p.C;
 
     auto choice = [&](int n) -> int {  // np.random.choice(candidates) -> position
         if constexpr (SCRIPTED) {
@@ -117,191 +131,228 @@ __global__ void __launch_bounds__(kTptBlock) tpt_search_kernel(const TptParams p
     };
 
     int s_done = 0;
-    for (; s_done < p.n_sim && !fault; ++s_done) {
-        int node = 0, blk = 1, level = 0;
+    for (int sim = 0; sim < p.n_sim; ++sim) {
+        const bool live = valid && !fault;
+        int mode = live ? MODE_DESCEND : MODE_IDLE;
+        int node = 0, blk = 1, level = 0, exp_a = 0, exp_rank = 0;
         bool fresh = false;  // block just allocated: all children unvisited, nothing to load
         double G = 0.0;
-        for (;;) {
-            ++c_levels;
-            EdgeRec c[A];
-            int nun = 0;
-            if (fresh) {
+
+        // ------------------------------------------------------------------ phase 1: descent
+        while (__any_sync(kFull, mode == MODE_DESCEND)) {
+            if (mode == MODE_DESCEND) {
+                ++c_levels;
+                EdgeRec c[A];
+                int nun = 0;
+                if (fresh) {
 #pragma unroll
-                for (int a = 0; a < A; ++a) { c[a] = EdgeRec{0.0, 0.0, 0, 0.f, 0, 0u}; }
-                nun = A;
-            } else {
-#pragma unroll
-                for (int a = 0; a < A; ++a) {
-                    c[a] = (p.tuning & 2) ? load_rec<false>(recs + (long long)blk * A + a) : load_rec<true>(recs + (long long)blk * A + a);
-                    nun += (c[a].na_in == 0);
-                }
-                if (p.tuning & 4) {  // explicit look-ahead: the blocks 4 and 8 ahead of this one
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(recs + (long long)(blk + 4) * A));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(recs + (long long)(blk + 8) * A));
-                }
-            }
-            if (nun > 0) {
-                // ---- expansion: uniformly random unvisited action (mcts_hash.py:70-74)
-                const int pos = choice(nun);
-                int a_sel = 0, seen = 0;
-#pragma unroll
-                for (int a = 0; a < A; ++a) { if (c[a].na_in == 0) { if (seen == pos) a_sel = a; ++seen; } }
-                T st[S];
-                if constexpr (S == 4 && sizeof(T) == 4) {
-                    const float4 v = __ldcg(reinterpret_cast<const float4*>(states + (long long)node * S));
-                    st[0] = v.x; st[1] = v.y; st[2] = v.z; st[3] = v.w;
+                    for (int a = 0; a < A; ++a) { c[a] = EdgeRec{0.0, 0.0, 0, 0.f, 0, 0u}; }
+                    nun = A;
                 } else {
-#pragma unroll
-                    for (int i = 0; i < S; ++i) st[i] = __ldcg(states + (long long)node * S + i);
-                }
-                T r;
-                const bool term = Env<ENV, T>::step(st, T(a_sel), r);
-                ++c_env;
-                const int child = blk * A + a_sel;
-                EdgeRec nr;
-                nr.na_in = 1; nr.r_in = (float)r; nr.block = 0; nr.flags = (uint32_t)(A - nun) << 8;
-                if (term) {
-                    // terminal child: total += r, na += 1, child.ns += 1 (mcts_hash.py:96-107)
-                    G = (double)r; nr.total_in = G; nr.g_first = 0.0; nr.flags |= kFlagTerminal;
-                } else {
-                    if constexpr (S == 4 && sizeof(T) == 4) {
-                        __stcg(reinterpret_cast<float4*>(states + (long long)child * S), make_float4(st[0], st[1], st[2], st[3]));
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < S; ++i) __stcg(states + (long long)child * S + i, st[i]);
-                    }
-                    // ---- rollout (abstract_mcts.py:72-91), budget per mcts_hash.py:116
-                    const int budget = p.budget_mode == ISLA_BUDGET_ZERO ? 0 : min(p.max_depth - (level + 1), p.disc_count);
-                    double R = 0.0;
-                    bool done = false;
-                    Stream rs;
-                    if constexpr (!SCRIPTED) rs.init(p.seed, sims_done, tree_id, 0u);
-                    int t = 0;
-                    while (!done && t < budget) {
-                        T act;
-                        if constexpr (SCRIPTED) {
-                            const int v = (int)tc.take(ISLA_K_SAMPLE_D);
-                            if (v < 0 || v >= A) { if (!tc.fault) tc.fault = ISLA_ERR_TRACE; }
-                            act = T(v);
-                            if (tc.fault) break;
-                        } else {
-                            act = sample_action<ENV, T>(rs);
-                        }
-                        T rr;
-                        done = Env<ENV, T>::step(st, act, rr);
-                        R = __dadd_rn(R, __dmul_rn((double)rr, __ldg(p.disc_table + t)));  // r * pow(gamma, t)
-                        ++t;
-                    }
-                    c_roll += t; c_env += t;
-                    G = __dadd_rn((double)r, __dmul_rn(gamma, R));
-                    nr.total_in = G; nr.g_first = G;
-                }
-                store_rec(recs + child, nr);
-                ++c_nodes;
-                break;
-            }
-            // ---- UCB1 over the A visited children (action_selection_functions.py:9-25).
-            // The reference evaluates the scores in float64 and breaks exact ties at random.  An fp32
-            // screening pass (error < 1e-6 relative, tolerance 1e-5) settles the arg-max whenever it is
-            // unambiguous; only near-ties take the exact float64 path, so the DECISIONS are the float64 ones.
-            int ns = (node != 0);
-#pragma unroll
-            for (int a = 0; a < A; ++a) ns += c[a].na_in;
-            const double lg = ns < p.ln_count ? ln_table[ns] : ::log((double)ns);
-            int a_sel = 0;
-            bool settled = false;
-            if (!(p.tuning & 1)) {
-                const float lgf = (float)lg, Cf = (float)Cexp;
-                float sf[A], m1 = -INFINITY, scale = 0.f;
-#pragma unroll
-                for (int a = 0; a < A; ++a) {
-                    const float naf = (float)c[a].na_in;
-                    const float qf = __fdividef((float)c[a].total_in, naf);
-                    const float ef = Cf * sqrtf(__fdividef(lgf, naf));
-                    sf[a] = qf + ef;
-                    m1 = fmaxf(m1, sf[a]);
-                    scale = fmaxf(scale, fabsf(qf) + fabsf(ef));
-                }
-                const float thr = m1 - 1e-5f * scale - 1e-30f;
-                int ncand = 0;
-#pragma unroll
-                for (int a = 0; a < A; ++a) { if (sf[a] >= thr) { ++ncand; a_sel = a; } }
-                settled = (ncand == 1);
-            }
-            int pos = 0;
-            if (!settled) {
-                double sc[A], best = -INFINITY;
-#pragma unroll
-                for (int a = 0; a < A; ++a) {
-                    const double na = (double)c[a].na_in;
-                    const double q = __ddiv_rn(c[a].total_in, na);
-                    const double ex = __dmul_rn(Cexp, __dsqrt_rn(__ddiv_rn(lg, na)));
-                    sc[a] = __dadd_rn(q, ex);
-                    best = fmax(best, sc[a]);
-                }
-                int ties = 0;
-#pragma unroll
-                for (int a = 0; a < A; ++a) ties += (sc[a] == best);
-                pos = (SCRIPTED || ties > 1) ? choice(ties) : 0;
-                // the tied set is ordered like node.actions (insertion order = rank)
-#pragma unroll
-                for (int rk = 0; rk < A; ++rk) {
 #pragma unroll
                     for (int a = 0; a < A; ++a) {
-                        if ((int)((c[a].flags >> 8) & 0xffu) == rk && sc[a] == best) { if (pos == 0) a_sel = a; --pos; }
+                        c[a] = (p.tuning & 2) ? load_rec<true>(recs + (long long)blk * A + a) : load_rec<false>(recs + (long long)blk * A + a);
+                        nun += (c[a].na_in == 0);
                     }
                 }
-            } else if constexpr (SCRIPTED) {
-                (void)choice(1);  // the reference draws even when the maximum is unique
-            }
-            const int child = blk * A + a_sel;
-            EdgeRec sel = c[0];
+                if (nun > 0) {
+                    // uniformly random unvisited action (mcts_hash.py:70-74); expanded in phase 2
+                    const int pos = choice(nun);
+                    int seen = 0;
 #pragma unroll
-            for (int a = 1; a < A; ++a) if (a == a_sel) sel = c[a];
-            if (sel.flags & kFlagTerminal) {
-                // terminal child re-visited: total += r, na += 1 (mcts_hash.py:96-107)
-                G = (double)sel.r_in;
-                atomicAdd(&recs[child].total_in, G);
-                atomicAdd(&recs[child].na_in, 1);
-                break;
-            }
-            path[(long long)level * p.n_trees] = make_int2(child, __float_as_int(sel.r_in));
-            ++level;
-            node = child;
-            blk = sel.block;
-            fresh = false;
-            if (blk == 0) {
-                if (alloc >= p.block_cap) { fault = ISLA_ERR_CAPACITY; break; }
-                blk = alloc++;
-                recs[child].block = blk;
-                fresh = true;
+                    for (int a = 0; a < A; ++a) { if (c[a].na_in == 0) { if (seen == pos) exp_a = a; ++seen; } }
+                    exp_rank = A - nun;
+                    mode = MODE_EXPAND;
+                } else {
+                    // UCB1 over the A visited children (action_selection_functions.py:9-25).  The reference
+                    // evaluates the scores in float64 and breaks exact ties at random.  An fp32 screening pass
+                    // (error < 1e-6 relative, tolerance 1e-5) settles the arg-max whenever it is unambiguous;
+                    // only near-ties take the exact float64 path, so the DECISIONS are the float64 ones.
+                    int ns = (node != 0);
+#pragma unroll
+                    for (int a = 0; a < A; ++a) ns += c[a].na_in;
+                    const double lg = ns < p.ln_count ? ln_table[ns] : ::log((double)ns);
+                    int a_sel = 0;
+                    bool settled = false;
+                    if (!(p.tuning & 1)) {
+                        const float lgf = (float)lg;
+                        float sf[A], m1 = -INFINITY, scale = 0.f;
+#pragma unroll
+                        for (int a = 0; a < A; ++a) {
+                            const float naf = (float)c[a].na_in;
+                            const float qf = __fdividef((float)c[a].total_in, naf);
+                            const float ef = Cf * sqrtf(__fdividef(lgf, naf));
+                            sf[a] = qf + ef;
+                            m1 = fmaxf(m1, sf[a]);
+                            scale = fmaxf(scale, fabsf(qf) + fabsf(ef));
+                        }
+                        const float thr = m1 - 1e-5f * scale - 1e-30f;
+                        int ncand = 0;
+#pragma unroll
+                        for (int a = 0; a < A; ++a) { if (sf[a] >= thr) { ++ncand; a_sel = a; } }
+                        settled = (ncand == 1);
+                    }
+                    if (!settled) {
+                        double sc[A], best = -INFINITY;
+#pragma unroll
+                        for (int a = 0; a < A; ++a) {
+                            const double na = (double)c[a].na_in;
+                            const double q = __ddiv_rn(c[a].total_in, na);
+                            const double ex = __dmul_rn(Cexp, __dsqrt_rn(__ddiv_rn(lg, na)));
+                            sc[a] = __dadd_rn(q, ex);
+                            best = fmax(best, sc[a]);
+                        }
+                        int ties = 0;
+#pragma unroll
+                        for (int a = 0; a < A; ++a) ties += (sc[a] == best);
+                        int pos = (SCRIPTED || ties > 1) ? choice(ties) : 0;
+                        // the tied set is ordered like node.actions (insertion order = rank)
+#pragma unroll
+                        for (int rk = 0; rk < A; ++rk) {
+#pragma unroll
+                            for (int a = 0; a < A; ++a) {
+                                if ((int)((c[a].flags >> 8) & 0xffu) == rk && sc[a] == best) { if (pos == 0) a_sel = a; --pos; }
+                            }
+                        }
+                    } else if constexpr (SCRIPTED) {
+                        (void)choice(1);  // the reference draws even when the maximum is unique
+                    }
+                    const int child = blk * A + a_sel;
+                    EdgeRec sel = c[0];
+#pragma unroll
+                    for (int a = 1; a < A; ++a) if (a == a_sel) sel = c[a];
+                    if (sel.flags & kFlagTerminal) {
+                        // terminal child re-visited: total += r, na += 1 (mcts_hash.py:96-107)
+                        G = (double)sel.r_in;
+                        atomicAdd(&recs[child].total_in, G);
+                        atomicAdd(&recs[child].na_in, 1);
+                        mode = MODE_BACKUP;
+                    } else {
+                        path[(long long)level * p.n_trees] = make_int2(child, __float_as_int(sel.r_in));
+                        ++level;
+                        node = child;
+                        blk = sel.block;
+                        fresh = false;
+                        if (blk == 0) {
+                            if (alloc >= p.block_cap) { fault = ISLA_ERR_CAPACITY; mode = MODE_IDLE; }
+                            else { blk = alloc++; recs[child].block = blk; fresh = true; }
+                        }
+                    }
+                }
             }
         }
-        if (fault) break;
-        if constexpr (SCRIPTED) { if (tc.fault) { fault = tc.fault; break; } }
-        // ---- backup: G <- r + gamma*G up the recorded path (mcts_hash.py:126-131, 79-81)
-        for (int l = level - 1; l >= 0; --l) {
-            const int2 e = path[(long long)l * p.n_trees];
-            G = __dadd_rn((double)__int_as_float(e.y), __dmul_rn(gamma, G));
-            atomicAdd(&recs[e.x].total_in, G);
-            atomicAdd(&recs[e.x].na_in, 1);
+
+        // ------------------------------------------------------------------ phase 2: expansion + rollout
+        T st[S];
+        T r_exp = T(0);
+        bool rolling = false;
+        int budget = 0;
+        if (mode == MODE_EXPAND) {
+            if constexpr (S == 4 && sizeof(T) == 4) {
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(states + (long long)node * S));
+                st[0] = v.x; st[1] = v.y; st[2] = v.z; st[3] = v.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < S; ++i) st[i] = __ldcg(states + (long long)node * S + i);
+            }
+            const bool term = Env<ENV, T>::step(st, T(exp_a), r_exp);
+            ++c_env;
+            if (term) {
+                G = (double)r_exp;  // terminal child: total += r, na += 1, child.ns += 1 (mcts_hash.py:96-107)
+            } else {
+                const int child = blk * A + exp_a;
+                if constexpr (S == 4 && sizeof(T) == 4) {
+                    __stcg(reinterpret_cast<float4*>(states + (long long)child * S), make_float4(st[0], st[1], st[2], st[3]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < S; ++i) __stcg(states + (long long)child * S + i, st[i]);
+                }
+                budget = p.budget_mode == ISLA_BUDGET_ZERO ? 0 : min(p.max_depth - (level + 1), p.disc_count);  // mcts_hash.py:116
+                rolling = true;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < S; ++i) st[i] = T(0);
         }
-        ++sims_done;
+        // rollout (abstract_mcts.py:72-91): one env step per iteration for every lane still playing
+        {
+            double R = 0.0;
+            Stream rs;
+            rs.init(p.seed, sims_done, tree_id, 0u);
+            int t = 0;
+            bool go = rolling && budget > 0;
+            while (__any_sync(kFull, go)) {
+                if (go) {
+                    T act;
+                    if constexpr (SCRIPTED) {
+                        const int v = (int)tc.take(ISLA_K_SAMPLE_D);
+                        if (v < 0 || v >= A) { if (!tc.fault) tc.fault = ISLA_ERR_TRACE; }
+                        act = T(tc.fault ? 0 : v);
+                    } else {
+                        act = sample_action<ENV, T>(rs);
+                    }
+                    T rr;
+                    const bool done = Env<ENV, T>::step(st, act, rr);
+                    R = __dadd_rn(R, __dmul_rn((double)rr, __ldg(p.disc_table + t)));  // r * pow(gamma, t)
+                    ++t;
+                    go = !done && t < budget;
+                    if constexpr (SCRIPTED) { if (tc.fault) go = false; }
+                }
+            }
+            c_roll += t; c_env += t;
+            if (rolling) G = __dadd_rn((double)r_exp, __dmul_rn(gamma, R));
+        }
+        if (mode == MODE_EXPAND) {
+            EdgeRec nr;
+            nr.na_in = 1; nr.r_in = (float)r_exp; nr.block = 0; nr.flags = (uint32_t)exp_rank << 8;
+            nr.total_in = G;
+            if (rolling) { nr.g_first = G; } else { nr.g_first = 0.0; nr.flags |= kFlagTerminal; }
+            store_rec(recs + blk * A + exp_a, nr);
+            ++c_nodes;
+            mode = MODE_BACKUP;
+        }
+        if constexpr (SCRIPTED) { if (tc.fault && !fault) { fault = tc.fault; mode = MODE_IDLE; } }
+
+        // ------------------------------------------------------------------ phase 3: backup
+        // G <- r + gamma*G up the recorded path (mcts_hash.py:126-131, 79-81); fire-and-forget REDs
+        const int my_levels = (mode == MODE_BACKUP) ? level : 0;
+        int max_levels = my_levels;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) max_levels = max(max_levels, __shfl_xor_sync(kFull, max_levels, o));
+        for (int l0 = max_levels - 1; l0 >= 0; l0 -= 4) {
+            int2 e[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int l = l0 - j;
+                if (l >= 0 && l < my_levels) e[j] = __ldcg(path + (long long)l * p.n_trees);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int l = l0 - j;
+                if (l >= 0 && l < my_levels) {
+                    G = __dadd_rn((double)__int_as_float(e[j].y), __dmul_rn(gamma, G));
+                    atomicAdd(&recs[e[j].x].total_in, G);
+                    atomicAdd(&recs[e[j].x].na_in, 1);
+                }
+            }
+        }
+        if (mode == MODE_BACKUP) { ++sims_done; ++s_done; }
     }
 
-    meta[META_ALLOC] = alloc;
-    meta[META_SIMS] = (int32_t)sims_done;
-    meta[META_RNG] = (int32_t)ts.consumed();
-    meta[META_FAULT] = fault;
-    if constexpr (SCRIPTED) meta[4] = (int32_t)tc.pos;
-
-    // counters (once per thread at kernel end)
-    atomicAdd(p.counters + CNT_ENV_STEPS, c_env);
-    atomicAdd(p.counters + CNT_ROLLOUT_STEPS, c_roll);
-    atomicAdd(p.counters + CNT_LEVELS, c_levels);
-    atomicAdd(p.counters + CNT_SIMS, (unsigned long long)s_done);
-    atomicAdd(p.counters + CNT_NODES, c_nodes);
-    if (fault) atomicAdd(p.counters + CNT_FAULTS, 1ull);
+    if (valid) {
+        meta[META_ALLOC] = alloc;
+        meta[META_SIMS] = (int32_t)sims_done;
+        meta[META_RNG] = (int32_t)ts.consumed();
+        meta[META_FAULT] = fault;
+        if constexpr (SCRIPTED) meta[4] = (int32_t)tc.pos;
+        // counters (once per thread at kernel end)
+        atomicAdd(p.counters + CNT_ENV_STEPS, c_env);
+        atomicAdd(p.counters + CNT_ROLLOUT_STEPS, c_roll);
+        atomicAdd(p.counters + CNT_LEVELS, c_levels);
+        atomicAdd(p.counters + CNT_SIMS, (unsigned long long)s_done);
+        atomicAdd(p.counters + CNT_NODES, c_nodes);
+        if (fault) atomicAdd(p.counters + CNT_FAULTS, 1ull);
+    }
 }
 
 template <typename T>
@@ -364,7 +415,7 @@ template <int ENV, typename T>
 int launch_search(const TptParams& p, bool scripted, cudaStream_t st) {
     const size_t smem = p.ln_in_smem ? (size_t)p.ln_count * sizeof(double) : 0;
     if (scripted) {
-        tpt_search_kernel<ENV, T, true><<<1, 1, smem, st>>>(p);
+        tpt_search_kernel<ENV, T, true><<<1, 32, smem, st>>>(p);
     } else {
         const unsigned grid = (unsigned)((p.n_trees + kTptBlock - 1) / kTptBlock);
         tpt_search_kernel<ENV, T, false><<<grid, kTptBlock, smem, st>>>(p);
