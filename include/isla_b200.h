@@ -91,6 +91,7 @@ typedef struct {
     int64_t counters_offset;                /* int64[8] device counters */
     int64_t ln_offset, ln_count;            /* double ln(n), n < ln_count  (host libm log, like numpy)  */
     int64_t disc_offset, disc_count;        /* double gamma**t, t < disc_count (host libm pow, like CPython) */
+    int64_t pw1_offset, pw2_offset;         /* double[ln_count]: ceil(k1*n**alpha1) and k*n**alpha widening caps (host libm) */
     /* CTA-per-tree (general) pools, offsets of the per-tree blocks and their strides */
     int64_t s_cap, a_cap;                   /* state / action node capacity per tree */
     int64_t pool_offset, pool_stride;       /* bytes per tree of the general node pool */
@@ -126,7 +127,18 @@ int isla_engine_run_scripted(isla_engine* e, int64_t tree, int32_t n_sim, const 
  * (mcts_hash.py:42-50).  Discrete agents: na/total are [n_trees][n_actions] by ACTION index.
  * best_dev[n_trees] = chosen action index.  scripted_pos >= 0 replaces the tie-break draw. */
 int isla_engine_root_stats(isla_engine* e, int64_t* na_dev, double* total_dev, void* stream);
-int isla_engine_best(isla_engine* e, int32_t scripted_pos, int32_t* best_dev, void* stream);
+/* best_rank_dev[n_trees]: position of the chosen child in root.actions (insertion order; spw/dpw: after the
+ * persistent key-sorted re-ordering of mcts_state_...:29 / mcts_double_...:30); best_action_dev[n_trees]
+ * (optional, may be NULL): its action value (discrete agents: the action index). */
+int isla_engine_best(isla_engine* e, int32_t scripted_pos, int32_t* best_rank_dev, double* best_action_dev, void* stream);
+/* Root children of one tree in root.actions order (continuous-action agents: apw/dpw): action value,
+ * ActionNode.na, ActionNode.total; count_dev[0] = number of children (may exceed cap). */
+int isla_engine_root_children(isla_engine* e, int64_t tree, int32_t cap, double* action_dev, int64_t* na_dev,
+                              double* total_dev, int32_t* count_dev, void* stream);
+/* CTA-per-tree engine: byte offsets of the SoA arrays inside one tree's pool, for host-side decoding
+ * (order: s_total, s_term_reward, s_ns, s_flags, s_coff, s_ccap, s_ccnt, s_state, a_total, a_value, a_na,
+ *  a_visits, a_child, ipool, path_s, path_a, path_r, path_flag, meta, end). */
+int isla_engine_pool_offsets(const isla_engine* e, int64_t out[24]);
 
 /* Device counters int64[8]: [0] env steps executed, [1] rollout steps, [2] tree levels visited,
  * [3] simulations, [4] nodes created, [5] faults.  SYNCHRONISES the stream. */

@@ -47,7 +47,8 @@ class IslaLayout(C.Structure):
         ("slots_per_tree", C.c_int64), ("rec_offset", C.c_int64), ("rec_stride", C.c_int64),
         ("state_offset", C.c_int64), ("state_stride", C.c_int64), ("meta_offset", C.c_int64),
         ("path_offset", C.c_int64), ("counters_offset", C.c_int64), ("ln_offset", C.c_int64), ("ln_count", C.c_int64),
-        ("disc_offset", C.c_int64), ("disc_count", C.c_int64), ("s_cap", C.c_int64), ("a_cap", C.c_int64),
+        ("disc_offset", C.c_int64), ("disc_count", C.c_int64), ("pw1_offset", C.c_int64), ("pw2_offset", C.c_int64),
+        ("s_cap", C.c_int64), ("a_cap", C.c_int64),
         ("pool_offset", C.c_int64), ("pool_stride", C.c_int64), ("total_bytes", C.c_int64),
     ]
 
@@ -66,7 +67,9 @@ SYMBOLS = {
     "isla_engine_run": (C.c_int, [_P, C.c_int32, _P]),
     "isla_engine_run_scripted": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, C.c_int64, _P]),
     "isla_engine_root_stats": (C.c_int, [_P, _P, _P, _P]),
-    "isla_engine_best": (C.c_int, [_P, C.c_int32, _P, _P]),
+    "isla_engine_best": (C.c_int, [_P, C.c_int32, _P, _P, _P]),
+    "isla_engine_root_children": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, _P, _P]),
+    "isla_engine_pool_offsets": (C.c_int, [_P, _P]),
     "isla_engine_counters": (C.c_int, [_P, _P, _P]),
     "isla_merge_root_stats": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int64, _P, _P, _P]),
     "isla_env_step": (C.c_int, [C.c_int32, C.c_int32, _P, _P, C.c_int64, _P, _P, _P, _P]),

@@ -34,6 +34,8 @@ void add_table_layout(const isla_config& cfg, isla_layout& lay, int64_t& off) {
     lay.disc_count = (int64_t)cfg.max_depth + 2;
     lay.ln_offset = off; off = up(off + lay.ln_count * 8);
     lay.disc_offset = off; off = up(off + lay.disc_count * 8);
+    lay.pw1_offset = off; off = up(off + lay.ln_count * 8);
+    lay.pw2_offset = off; off = up(off + lay.ln_count * 8);
 }
 int upload_tables(isla_engine* e) {
     std::vector<double> ln((size_t)e->lay.ln_count), disc((size_t)e->lay.disc_count);
@@ -42,6 +44,18 @@ int upload_tables(isla_engine* e) {
     for (size_t t = 0; t < disc.size(); ++t) disc[t] = std::pow(e->cfg.gamma, (double)t);
     ISLA_CUDA_OK(cudaMemcpy(e->ws + e->lay.ln_offset, ln.data(), ln.size() * 8, cudaMemcpyHostToDevice));
     ISLA_CUDA_OK(cudaMemcpy(e->ws + e->lay.disc_offset, disc.data(), disc.size() * 8, cudaMemcpyHostToDevice));
+    // progressive-widening caps, again with the host libm pow (python: k * ns ** alpha):
+    //   pw1[n] = ceil(k1 * n**alpha1)  state-node test  (mcts_action_...:62, mcts_double_...:56)
+    //   pw2[n] = k * n**alpha          action-node test (mcts_state_...:97 with (k, alpha); mcts_double_...:87 with (kSpw, alphaSpw))
+    std::vector<double> pw1(ln.size()), pw2(ln.size());
+    const double kk = e->cfg.agent == ISLA_AGENT_SPW ? e->cfg.k1 : e->cfg.k2;
+    const double al = e->cfg.agent == ISLA_AGENT_SPW ? e->cfg.alpha1 : e->cfg.alpha2;
+    for (size_t n = 0; n < ln.size(); ++n) {
+        pw1[n] = std::ceil(e->cfg.k1 * std::pow((double)n, e->cfg.alpha1));
+        pw2[n] = kk * std::pow((double)n, al);
+    }
+    ISLA_CUDA_OK(cudaMemcpy(e->ws + e->lay.pw1_offset, pw1.data(), pw1.size() * 8, cudaMemcpyHostToDevice));
+    ISLA_CUDA_OK(cudaMemcpy(e->ws + e->lay.pw2_offset, pw2.data(), pw2.size() * 8, cudaMemcpyHostToDevice));
     ISLA_CUDA_OK(cudaDeviceSynchronize());
     return 0;
 }
@@ -177,10 +191,27 @@ int isla_engine_root_stats(isla_engine* e, int64_t* na_dev, double* total_dev, v
                                                     : cta_root_stats(e, na_dev, total_dev, (cudaStream_t)stream);
 }
 
-int isla_engine_best(isla_engine* e, int32_t scripted_pos, int32_t* best_dev, void* stream) {
+int isla_engine_best(isla_engine* e, int32_t scripted_pos, int32_t* best_dev, double* best_action_dev, void* stream) {
     if (!e || !best_dev) { set_error("null argument"); return ISLA_ERR_INVALID; }
-    return e->kernel == ISLA_KERNEL_THREAD_PER_TREE ? tpt_best(e, scripted_pos, best_dev, (cudaStream_t)stream)
-                                                    : cta_best(e, scripted_pos, best_dev, (cudaStream_t)stream);
+    return e->kernel == ISLA_KERNEL_THREAD_PER_TREE ? tpt_best(e, scripted_pos, best_dev, best_action_dev, (cudaStream_t)stream)
+                                                    : cta_best(e, scripted_pos, best_dev, best_action_dev, (cudaStream_t)stream);
+}
+
+int isla_engine_root_children(isla_engine* e, int64_t tree, int32_t cap, double* action_dev, int64_t* na_dev, double* total_dev,
+                              int32_t* count_dev, void* stream) {
+    if (!e || !count_dev || (cap > 0 && (!action_dev || !na_dev || !total_dev))) { set_error("null argument"); return ISLA_ERR_INVALID; }
+    if (tree < 0 || tree >= e->cfg.n_trees) { set_error("tree index out of range"); return ISLA_ERR_INVALID; }
+    if (e->kernel != ISLA_KERNEL_CTA_PER_TREE) { set_error("root_children: CTA-per-tree engine only (use root_stats)"); return ISLA_ERR_INVALID; }
+    return cta_root_children(e, tree, cap, action_dev, na_dev, total_dev, count_dev, (cudaStream_t)stream);
+}
+
+int isla_engine_pool_offsets(const isla_engine* e, int64_t out[24]) {
+    if (!e || !out) { set_error("null argument"); return ISLA_ERR_INVALID; }
+    if (e->kernel != ISLA_KERNEL_CTA_PER_TREE) { set_error("pool_offsets: CTA-per-tree engine only"); return ISLA_ERR_INVALID; }
+    long long tmp[24];
+    cta_pool_offsets(e, tmp);
+    for (int i = 0; i < 24; ++i) out[i] = tmp[i];
+    return ISLA_OK;
 }
 
 int isla_engine_counters(isla_engine* e, int64_t out_host[8], void* stream) {

@@ -78,12 +78,15 @@ int tpt_set_roots(isla_engine* e, const double* roots_dev, cudaStream_t st);
 int tpt_run(isla_engine* e, int n_sim, long long scripted_tree, const uint8_t* kinds, const double* values,
             long long trace_len, cudaStream_t st);
 int tpt_root_stats(isla_engine* e, int64_t* na_dev, double* total_dev, cudaStream_t st);
-int tpt_best(isla_engine* e, int scripted_pos, int32_t* best_dev, cudaStream_t st);
+int tpt_best(isla_engine* e, int scripted_pos, int32_t* best_dev, double* best_action_dev, cudaStream_t st);
 // CTA-per-tree engine (isla_tree_cta.cu)
 int cta_fill_layout(const isla_config& cfg, isla_layout& lay);
 int cta_set_roots(isla_engine* e, const double* roots_dev, cudaStream_t st);
 int cta_run(isla_engine* e, int n_sim, long long scripted_tree, const uint8_t* kinds, const double* values,
             long long trace_len, cudaStream_t st);
 int cta_root_stats(isla_engine* e, int64_t* na_dev, double* total_dev, cudaStream_t st);
-int cta_best(isla_engine* e, int scripted_pos, int32_t* best_dev, cudaStream_t st);
+int cta_best(isla_engine* e, int scripted_pos, int32_t* best_dev, double* best_action_dev, cudaStream_t st);
+int cta_root_children(isla_engine* e, long long tree, int cap, double* action, int64_t* na, double* total, int32_t* count,
+                      cudaStream_t st);
+void cta_pool_offsets(const isla_engine* e, long long out[24]);
 }  // namespace isla

@@ -1,12 +1,829 @@
-// CTA-per-tree general engine (vanilla / APW / SPW / DPW, leaf-parallel rollout batches).
-// Placeholder until the kernel lands: every entry point fails loudly (no CPU fallback).
+// CTA-per-tree general MCTS engine: vanilla / APW / SPW / DPW, leaf-parallel rollout batches, VOO.
+// Serves the single-tree configurations (BASELINE C1-C4) and any agent the thread-per-tree kernel
+// does not cover.
+//
+// Reference semantics followed (paths under islaMcts/):
+//   state node   vanilla/spw  agents/mcts.py:46-67, mcts_state_progressive_widening_hash.py:47-67
+//                apw          agents/mcts_action_progressive_widening_hash.py:52-84  (cap test :62)
+//                dpw          agents/mcts_double_progressive_widening_hash.py:49-75  (cap test :56)
+//   action node  vanilla/apw  agents/mcts_hash.py:87-131, mcts_action_...:89-136
+//                spw          agents/mcts_state_...:72-130   (cap :97, inverse-visit resampling :116-119)
+//                dpw          agents/mcts_double_...:79-135  (cap :87, resampling :119-129)
+//   ucb1         utils/action_selection_functions.py:9-25 ;  voo  :139-205
+//   rollout      agents/abstract_mcts.py:72-91 ;  end of fit()  agents/mcts_hash.py:42-50
+//
+// Execution model (B200-first, not the reference's recursion):
+//   * one CTA owns one tree; its node pools (SoA, indices not pointers) live in HBM and stay
+//     L2-resident for single-tree work;
+//   * warp 0 runs the sequential select/expand/backup logic with REPLICATED scalar state (every lane
+//     holds the same cursors and RNG stream, lane 0 does the writes) and uses its 32 lanes for the wide
+//     scans: UCB arg-max over up to 10^4 progressive-widening children, action de-duplication, VOO
+//     Voronoi tests -- shuffle-reduced, children visited in insertion order so tie-breaks match;
+//   * ALL threads of the CTA play the leaf's R rollouts (one trajectory per thread and pass, env state
+//     in registers, own Philox stream (seed, sim, tree, j)); returns are reduced in a fixed
+//     power-of-two tree in shared memory, so results do not depend on the CTA size;
+//   * the descent records (state, action, reward) per level; backup walks it backwards.
+// Envs on the device are deterministic, hence an action node has at most ONE child state;
+// the dict-overwrite quirks of spw/dpw (a13, a14) are reproduced on that single slot.
+#include <cmath>
+
+#include "isla_envs.cuh"
 #include "isla_internal.h"
+#include "isla_philox.cuh"
 
 namespace isla {
-static int nope() { set_error("CTA-per-tree engine not built yet"); return ISLA_ERR_INVALID; }
-int cta_fill_layout(const isla_config&, isla_layout&) { return nope(); }
-int cta_set_roots(isla_engine*, const double*, cudaStream_t) { return nope(); }
-int cta_run(isla_engine*, int, long long, const uint8_t*, const double*, long long, cudaStream_t) { return nope(); }
-int cta_root_stats(isla_engine*, int64_t*, double*, cudaStream_t) { return nope(); }
-int cta_best(isla_engine*, int, int32_t*, cudaStream_t) { return nope(); }
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kMaxRollSmem = 4096;  // doubles of shared memory for the rollout reduction
+
+struct Pool {
+    // state nodes
+    double* s_total; double* s_term_reward; int* s_ns; int* s_flags; int* s_coff; int* s_ccap; int* s_ccnt;
+    void* s_state;
+    // action nodes
+    double* a_total; double* a_value; int* a_na; int* a_visits; int* a_child;
+    // child index arrays, path
+    int* ipool; int* p_s; int* p_a; double* p_r; int* p_flag;
+    int* meta;
+};
+
+struct CtaParams {
+    char* pool_base; long long pool_stride;
+    long long s_cap, a_cap, i_cap;
+    long long off[24];
+    unsigned long long* counters;
+    const uint8_t* trace_kinds; const double* trace_values; long long trace_len;
+    long long n_trees, scripted_tree;
+    unsigned long long seed, tree_id_base;
+    double C, gamma, alpha1, k1, alpha2, k2, epsilon;
+    const double* disc_table; const double* ln_table; const double* pw1_table; const double* pw2_table;
+    int ln_count, disc_count;
+    int n_sim, max_depth, budget_mode, agent, n_actions, R, expansion, voo_n, voo_max_try, real_bytes;
+};
+
+enum : int { O_S_TOTAL = 0, O_S_TERMR, O_S_NS, O_S_FLAGS, O_S_COFF, O_S_CCAP, O_S_CCNT, O_S_STATE, O_A_TOTAL, O_A_VALUE,
+             O_A_NA, O_A_VISITS, O_A_CHILD, O_IPOOL, O_P_S, O_P_A, O_P_R, O_P_FLAG, O_META, O_COUNT };
+enum : int { CM_NS = 0, CM_NA = 1, CM_ITOP = 2, CM_SIMS = 3, CM_RNG = 4, CM_FAULT = 5, CM_TRACE_POS = 6, CM_WORDS = 8 };
+
+__device__ __forceinline__ Pool make_pool(const CtaParams& p, long long tree) {
+    char* b = p.pool_base + tree * p.pool_stride;
+    Pool q;
+    q.s_total = (double*)(b + p.off[O_S_TOTAL]); q.s_term_reward = (double*)(b + p.off[O_S_TERMR]);
+    q.s_ns = (int*)(b + p.off[O_S_NS]); q.s_flags = (int*)(b + p.off[O_S_FLAGS]);
+    q.s_coff = (int*)(b + p.off[O_S_COFF]); q.s_ccap = (int*)(b + p.off[O_S_CCAP]); q.s_ccnt = (int*)(b + p.off[O_S_CCNT]);
+    q.s_state = (void*)(b + p.off[O_S_STATE]);
+    q.a_total = (double*)(b + p.off[O_A_TOTAL]); q.a_value = (double*)(b + p.off[O_A_VALUE]);
+    q.a_na = (int*)(b + p.off[O_A_NA]); q.a_visits = (int*)(b + p.off[O_A_VISITS]); q.a_child = (int*)(b + p.off[O_A_CHILD]);
+    q.ipool = (int*)(b + p.off[O_IPOOL]);
+    q.p_s = (int*)(b + p.off[O_P_S]); q.p_a = (int*)(b + p.off[O_P_A]); q.p_r = (double*)(b + p.off[O_P_R]);
+    q.p_flag = (int*)(b + p.off[O_P_FLAG]);
+    q.meta = (int*)(b + p.off[O_META]);
+    return q;
+}
+
+struct Cursor {  // replicated in every lane of warp 0
+    const uint8_t* k; const double* v; long long len, pos; int fault;
+    __device__ __forceinline__ double take(int kind) {
+        if (fault) return 0.0;
+        if (pos >= len || k[pos] != kind) { fault = ISLA_ERR_TRACE; return 0.0; }
+        return v[pos++];
+    }
+};
+
+__device__ __forceinline__ double warp_max(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(kFull, x, o));
+    return x;
+}
+__device__ __forceinline__ double warp_min(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmin(x, __shfl_xor_sync(kFull, x, o));
+    return x;
+}
+
+template <int ENV, typename T, bool SCRIPTED>
+struct Search {
+    static constexpr int S = EnvTraits<ENV>::S;
+    const CtaParams& p;
+    Pool q;
+    int lane;
+    int nS, nA, itop, fault;
+    Stream ts;
+    Cursor tc;
+    uint32_t tree_id;
+    unsigned long long c_env = 0, c_roll = 0, c_levels = 0, c_nodes = 0;
+
+    __device__ Search(const CtaParams& p_, long long tree) : p(p_), q(make_pool(p_, tree)) {
+        lane = threadIdx.x & 31;
+        nS = q.meta[CM_NS]; nA = q.meta[CM_NA]; itop = q.meta[CM_ITOP]; fault = q.meta[CM_FAULT];
+        tree_id = (uint32_t)(p.tree_id_base + (unsigned long long)tree);
+        ts.resume(p.seed, 0u, tree_id, kStreamTree, (uint32_t)q.meta[CM_RNG]);
+        tc = Cursor{p.trace_kinds, p.trace_values, p.trace_len, 0, 0};
+    }
+
+    // ---------------------------------------------------------------- randomness (replicated)
+    __device__ int choice(int n) {
+        if constexpr (SCRIPTED) {
+            const int v = (int)tc.take(ISLA_K_CHOICE);
+            if (v < 0 || v >= n) { if (!tc.fault) tc.fault = ISLA_ERR_TRACE; return 0; }
+            return v;
+        } else {
+            return n > 1 ? (int)mulhi_u32(ts.next(), (uint32_t)n) : 0;
+        }
+    }
+    __device__ double tree_action() {  // env.action_space.sample() drawn from the tree stream
+        if constexpr (EnvTraits<ENV>::kContinuous) {
+            if constexpr (SCRIPTED) return (double)(float)tc.take(ISLA_K_SAMPLE_C);
+            float lo, hi; env_action_bounds(ENV, lo, hi);
+            return (double)box_sample_f32(ts.next(), lo, hi);
+        } else {
+            if constexpr (SCRIPTED) return (double)(int)tc.take(ISLA_K_SAMPLE_D);
+            return (double)mulhi_u32(ts.next(), (uint32_t)EnvTraits<ENV>::A);
+        }
+    }
+    __device__ double u01() {
+        if constexpr (SCRIPTED) return tc.take(ISLA_K_U01);
+        return u32_to_d01(ts.next());
+    }
+    __device__ double uniform(double lo, double hi) {
+        if constexpr (SCRIPTED) return tc.take(ISLA_K_UNIFORM);
+        return __dadd_rn(lo, __dmul_rn(__dsub_rn(hi, lo), u32_to_d01(ts.next())));
+    }
+
+    // ---------------------------------------------------------------- node pools
+    __device__ T* state_ptr(int s) { return reinterpret_cast<T*>(q.s_state) + (long long)s * S; }
+
+    __device__ int new_state(const T (&st)[S], bool terminal, double term_reward) {
+        if (nS >= p.s_cap) { fault = ISLA_ERR_CAPACITY; return 0; }
+        const int s = nS++;
+        if (lane == 0) {
+            q.s_total[s] = 0.0; q.s_term_reward[s] = term_reward; q.s_ns[s] = 0; q.s_flags[s] = terminal ? 1 : 0;
+            q.s_coff[s] = 0; q.s_ccap[s] = 0; q.s_ccnt[s] = 0;
+            T* d = state_ptr(s);
+#pragma unroll
+            for (int i = 0; i < S; ++i) {
+                T v = st[i];
+                // spw/dpw keep node.data = the float32 observation and poke it back into the env
+                if (p.agent == ISLA_AGENT_SPW || p.agent == ISLA_AGENT_DPW) v = T(float(v));
+                d[i] = v;
+            }
+        }
+        ++c_nodes;
+        return s;
+    }
+    __device__ int new_action(double value) {
+        if (nA >= p.a_cap) { fault = ISLA_ERR_CAPACITY; return 0; }
+        const int a = nA++;
+        if (lane == 0) { q.a_total[a] = 0.0; q.a_value[a] = value; q.a_na[a] = 0; q.a_visits[a] = 0; q.a_child[a] = -1; }
+        return a;
+    }
+    // append an action node to a state's child index array (insertion order), growing it by doubling
+    __device__ void append_action(int s, int a) {
+        int off = q.s_coff[s], cap = q.s_ccap[s], cnt = q.s_ccnt[s];
+        __syncwarp();
+        if (cnt == cap) {
+            const int ncap = cap == 0 ? 4 : cap * 2;
+            if (itop + ncap > p.i_cap) { fault = ISLA_ERR_CAPACITY; return; }
+            const int noff = itop;
+            itop += ncap;
+            for (int i = lane; i < cnt; i += 32) q.ipool[noff + i] = q.ipool[off + i];
+            off = noff; cap = ncap;
+            if (lane == 0) { q.s_coff[s] = off; q.s_ccap[s] = cap; }
+        }
+        if (lane == 0) { q.ipool[off + cnt] = a; q.s_ccnt[s] = cnt + 1; }
+        __syncwarp();
+    }
+
+    // ---------------------------------------------------------------- UCB1 (float64, exact tie semantics)
+    // returns the RANK (position in node.actions) of the chosen child
+    __device__ int ucb_pick(int s) {
+        const int off = q.s_coff[s], n = q.s_ccnt[s];
+        const int ns = q.s_ns[s];
+        const double lg = ns < p.ln_count ? p.ln_table[ns] : ::log((double)ns);
+        auto score = [&](int i) -> double {
+            const int a = q.ipool[off + i];
+            const double na = (double)q.a_na[a];
+            return __dadd_rn(__ddiv_rn(q.a_total[a], na), __dmul_rn(p.C, __dsqrt_rn(__ddiv_rn(lg, na))));
+        };
+        double best = -INFINITY;
+        for (int i = lane; i < n; i += 32) best = fmax(best, score(i));
+        best = warp_max(best);
+        int ties = 0, first = -1;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            const bool tie = i < n && score(i) == best;
+            const unsigned b = __ballot_sync(kFull, tie);
+            if (first < 0 && b) first = base + __ffs(b) - 1;
+            ties += __popc(b);
+        }
+        int pos = (SCRIPTED || ties > 1) ? choice(ties) : 0;
+        if (pos == 0) return first;
+        int seen = 0, pick = first;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            const bool tie = i < n && score(i) == best;
+            const unsigned b = __ballot_sync(kFull, tie);
+            const int c = __popc(b);
+            if (pos < seen + c) {
+                unsigned bb = b;
+                for (int k = 0; k < pos - seen; ++k) bb &= bb - 1;
+                pick = base + __ffs(bb) - 1;
+                break;
+            }
+            seen += c;
+        }
+        return pick;
+    }
+
+    // actions.get(action.tobytes()): rank of the child with the same bits, or -1
+    __device__ int find_action(int s, double value) {
+        const int off = q.s_coff[s], n = q.s_ccnt[s];
+        const long long want = __double_as_longlong(value);
+        int found = -1;
+        for (int base = 0; base < n && found < 0; base += 32) {
+            const int i = base + lane;
+            const bool hit = i < n && __double_as_longlong(q.a_value[q.ipool[off + i]]) == want;
+            const unsigned b = __ballot_sync(kFull, hit);
+            if (b) found = base + __ffs(b) - 1;
+        }
+        return found;
+    }
+
+    // voo (utils/action_selection_functions.py:139-205), one action dimension
+    __device__ double voo_expand(int s) {
+        const double pr = u01();
+        const int off = q.s_coff[s], n = q.s_ccnt[s];
+        if (pr <= p.epsilon || n == 0) return tree_action();
+        auto qv = [&](int i) -> double { const int a = q.ipool[off + i]; return __ddiv_rn(q.a_total[a], (double)q.a_na[a]); };
+        double qmax = -INFINITY;
+        for (int i = lane; i < n; i += 32) qmax = fmax(qmax, qv(i));
+        qmax = warp_max(qmax);
+        int ties = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            ties += __popc(__ballot_sync(kFull, i < n && qv(i) == qmax));
+        }
+        int pos = choice(ties), best = 0, seen = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            const unsigned b = __ballot_sync(kFull, i < n && qv(i) == qmax);
+            const int c = __popc(b);
+            if (pos < seen + c) { unsigned bb = b; for (int k = 0; k < pos - seen; ++k) bb &= bb - 1; best = base + __ffs(bb) - 1; break; }
+            seen += c;
+        }
+        const double abest = q.a_value[q.ipool[off + best]];
+        float lof, hif; env_action_bounds(ENV, lof, hif);
+        double out = abest, out_d = INFINITY;
+        int n_acc = 0, out_ties = 0;
+        // the accepted samples are reduced on the fly: keep the minimum distance, count its ties, and
+        // re-draw among them at the end exactly like np.random.choice(np.where(d == d.min())[0])
+        double acc_x[8], acc_d[8];
+        const int n_samples = p.voo_n < 8 ? p.voo_n : 8;
+        for (int k = 0; k < n_samples && !tc.fault; ++k) {
+            int n_try = 0;
+            double tmin = INFINITY; int tmin_ties = 0;  // closest tried sample (max_try fallback)
+            // the fallback needs the pos-th closest-tried sample: replay it from a saved stream position
+            Stream saved = ts; const long long saved_pos = tc.pos;
+            for (;;) {
+                const double x = uniform((double)lof, (double)hif);
+                const double db = fabs(__dsub_rn(x, abest));
+                if (db < tmin) { tmin = db; tmin_ties = 1; } else if (db == tmin) { ++tmin_ties; }
+                if (db == 0.0) break;  // :177-178 leaves the loop WITHOUT appending
+                bool ok = true;
+                for (int base = 0; base < n; base += 32) {
+                    const int i = base + lane;
+                    const bool bad = i < n && i != best && !(db <= fabs(__dsub_rn(x, q.a_value[q.ipool[off + i]])));
+                    if (__any_sync(kFull, bad)) { ok = false; break; }
+                }
+                if (ok) { acc_x[n_acc] = x; acc_d[n_acc] = db; ++n_acc; break; }
+                ++n_try;
+                if (n_try >= p.voo_max_try) {
+                    int pp = choice(tmin_ties);
+                    // replay the tried samples to find the pp-th one at distance tmin
+                    Stream after = ts; const long long after_pos = tc.pos;
+                    ts = saved; tc.pos = saved_pos;
+                    double pick = x;
+                    for (int j = 0; j < n_try; ++j) {
+                        const double xj = uniform((double)lof, (double)hif);
+                        if (fabs(__dsub_rn(xj, abest)) == tmin) { if (pp == 0) { pick = xj; } --pp; }
+                    }
+                    ts = after; tc.pos = after_pos;
+                    acc_x[n_acc] = pick; acc_d[n_acc] = tmin; ++n_acc;
+                    break;
+                }
+            }
+        }
+        for (int i = 0; i < n_acc; ++i) { if (acc_d[i] < out_d) { out_d = acc_d[i]; out_ties = 1; } else if (acc_d[i] == out_d) ++out_ties; }
+        if (n_acc > 0) {
+            int pp = choice(out_ties);
+            for (int i = 0; i < n_acc; ++i) if (acc_d[i] == out_d) { if (pp == 0) out = acc_x[i]; --pp; }
+        }
+        return out;
+    }
+};
+
+struct RollShared {
+    double leaf[4];
+    int budget, need, exit_flag;
+    unsigned sim;
+    double result;
+};
+
+template <int ENV, typename T, bool SCRIPTED>
+__global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
+    constexpr int S = EnvTraits<ENV>::S;
+    __shared__ RollShared sh;
+    __shared__ double red[kMaxRollSmem];
+    const long long tree = SCRIPTED ? p.scripted_tree : (long long)blockIdx.x;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    const bool leader = tid < 32;  // warp 0
+    const uint32_t tree_id = (uint32_t)(p.tree_id_base + (unsigned long long)tree);
+    const int R = p.R;
+    int P = 1;
+    while (P < R) P <<= 1;
+
+    Search<ENV, T, SCRIPTED> ctx(p, tree);
+    uint32_t sims_done = (uint32_t)ctx.q.meta[CM_SIMS];
+    int s_done = 0;
+    unsigned long long my_steps = 0;  // rollout env steps played by THIS thread
+
+    for (int sim = 0; sim < p.n_sim; ++sim) {
+        // ------------------------------------------------------------ warp 0: descent to the leaf
+        int level = 0;           // number of recorded path entries
+        bool need_roll = false;  // the leaf is a fresh non-terminal state: roll out from it
+        double G = 0.0, r_leaf = 0.0;
+        int leaf_a = -1, leaf_s = -1;
+        T cur[S];
+        if (leader && !ctx.fault) {
+            Pool& q = ctx.q;
+            int s = 0;
+            for (;;) {
+                ++ctx.c_levels;
+                // ---------------- state node: choose or create the action node
+                int a = -1, a_rank = -1;
+                const int n_act = q.s_ccnt[s], off = q.s_coff[s];
+                if (p.agent == ISLA_AGENT_VANILLA || p.agent == ISLA_AGENT_SPW) {
+                    // unvisited actions = those without a node (visit_actions[a] == 0), mcts.py:55-59
+                    unsigned have = 0;
+                    for (int i = 0; i < n_act; ++i) have |= 1u << (int)q.a_value[q.ipool[off + i]];
+                    const int nun = p.n_actions - __popc(have);
+                    if (nun > 0) {
+                        int pos = ctx.choice(nun), disc = 0;
+                        for (int k = 0; k < p.n_actions; ++k) if (!((have >> k) & 1u)) { if (pos == 0) disc = k; --pos; }
+                        a = ctx.new_action((double)disc);
+                        ctx.append_action(s, a);
+                    } else {
+                        a_rank = ctx.ucb_pick(s);
+                        a = q.ipool[off + a_rank];
+                    }
+                } else {
+                    // progressive widening of the action set: len(actions) <= ceil(k * ns**alpha)
+                    const int ns_now = q.s_ns[s];
+                    const double cap = ns_now < p.ln_count ? p.pw1_table[ns_now] : ceil(__dmul_rn(p.k1, pow((double)ns_now, p.alpha1)));
+                    if (n_act == 0 || (double)n_act <= cap) {
+                        double val;
+                        if (p.agent == ISLA_AGENT_APW && p.expansion == ISLA_EXPAND_VOO) val = ctx.voo_expand(s);
+                        else val = ctx.tree_action();  // dpw ignores --ae (mcts_double_...:57)
+                        const int old = ctx.find_action(s, val);
+                        if (p.agent == ISLA_AGENT_APW) {
+                            if (old >= 0) a = q.ipool[q.s_coff[s] + old];                  // reuse (:66-70)
+                            else { a = ctx.new_action(val); ctx.append_action(s, a); }
+                        } else {
+                            a = ctx.new_action(val);                                      // always a new node (:58-60)
+                            if (old >= 0) { if (lane == 0) q.ipool[q.s_coff[s] + old] = a; __syncwarp(); }
+                            else ctx.append_action(s, a);
+                        }
+                    } else {
+                        a_rank = ctx.ucb_pick(s);
+                        a = q.ipool[off + a_rank];
+                    }
+                }
+                if (ctx.fault || ctx.tc.fault) break;
+                // ---------------- action node: step the env from this state node's data
+                {
+                    const T* sp = ctx.state_ptr(s);
+#pragma unroll
+                    for (int i = 0; i < S; ++i) cur[i] = sp[i];
+                }
+                T rT;
+                const bool term = Env<ENV, T>::step(cur, T(q.a_value[a]), rT);
+                const double r = (double)rT;
+                ++ctx.c_env;
+                const int child = q.a_child[a];
+                bool descend = false, update_action = true;
+                if (p.agent == ISLA_AGENT_VANILLA || p.agent == ISLA_AGENT_APW) {
+                    if (term) {
+                        // terminal: get-or-create the flagged child; total += r; na += 1; child.ns += 1
+                        int c = child;
+                        if (c < 0) { c = ctx.new_state(cur, true, 0.0); if (lane == 0) q.a_child[a] = c; }
+                        __syncwarp();
+                        if (lane == 0 && !ctx.fault) { q.a_total[a] += r; q.a_na[a] += 1; q.s_ns[c] += 1; }
+                        G = r;
+                    } else if (child < 0) {
+                        const int c = ctx.new_state(cur, false, 0.0);
+                        if (lane == 0) q.a_child[a] = c;
+                        need_roll = true; leaf_a = a; leaf_s = c; r_leaf = r;
+                    } else {
+                        descend = true;
+                    }
+                } else {
+                    const double kk = p.agent == ISLA_AGENT_SPW ? p.k1 : p.k2;
+                    const double al = p.agent == ISLA_AGENT_SPW ? p.alpha1 : p.alpha2;
+                    const int n_child = child >= 0 ? 1 : 0;
+                    const int na_now = q.a_na[a];
+                    const double wcap = na_now < p.ln_count ? p.pw2_table[na_now] : __dmul_rn(kk, pow((double)na_now, al));
+                    if (p.agent == ISLA_AGENT_SPW && term) {
+                        // always a FRESH terminal child that overwrites the key (mcts_state_...:81-95)
+                        const int c = ctx.new_state(cur, true, r);
+                        if (lane == 0 && !ctx.fault) { q.a_child[a] = c; q.a_total[a] += r; q.a_na[a] += 1; q.s_ns[c] += 1; }
+                        G = r;
+                    } else if (n_child == 0 || (double)n_child <= wcap) {
+                        // widen: the new node REPLACES the child stored under the same observation key
+                        const bool t2 = (p.agent == ISLA_AGENT_DPW) && term;
+                        const int c = ctx.new_state(cur, t2, 0.0);
+                        if (lane == 0) q.a_child[a] = c;
+                        if (t2) {
+                            if (lane == 0 && !ctx.fault) { q.a_total[a] += r; q.a_na[a] += 1; q.s_ns[c] += 1; }
+                            G = r;
+                        } else {
+                            need_roll = true; leaf_a = a; leaf_s = c; r_leaf = r;
+                        }
+                    } else {
+                        // resample an existing child, weights na / ns_c (one candidate on a deterministic env)
+                        const bool child_term = q.s_flags[child] & 1;
+                        if (p.agent == ISLA_AGENT_DPW && child_term) {
+                            ctx.fault = ISLA_ERR_INVALID;  // reference: random.choices on an empty population raises
+                        } else {
+                            if constexpr (SCRIPTED) { (void)ctx.tc.take(ISLA_K_CHOICES); } else { (void)ctx.ts.next(); }
+                            if (p.agent == ISLA_AGENT_SPW && child_term) {
+                                const double tr = q.s_term_reward[child];
+                                if (lane == 0) { q.a_total[a] += tr; q.a_na[a] += 1; q.s_ns[child] += 1; }
+                                G = tr;
+                            } else {
+                                descend = true; update_action = false;  // self.total / self.na untouched (:126-130)
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (ctx.fault || ctx.tc.fault) break;
+                // record this level: the state node is always backed up, the action node unless skipped
+                if (level >= p.s_cap) { ctx.fault = ISLA_ERR_CAPACITY; break; }
+                if (lane == 0) {
+                    q.p_s[level] = s; q.p_a[level] = a; q.p_r[level] = r;
+                    q.p_flag[level] = (descend ? 1 : 0) | (update_action ? 2 : 0);
+                }
+                ++level;
+                if (!descend) break;
+                s = child;
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < S; ++i) sh.leaf[i] = (double)cur[i];
+                sh.budget = p.budget_mode == ISLA_BUDGET_ZERO ? 0 : max(0, min(p.max_depth - level, p.disc_count));
+                sh.need = (need_roll && !ctx.fault && !ctx.tc.fault) ? 1 : 0;
+                sh.sim = sims_done;
+            }
+        } else if (leader && lane == 0) {
+            sh.need = 0;
+        }
+        __syncthreads();
+
+        // ------------------------------------------------------------ all threads: R rollouts from the leaf
+        if (sh.need) {
+            const int budget = sh.budget;
+            if constexpr (SCRIPTED) {
+                // the trace scripts ONE rollout (R == 1), replayed by every lane of warp 0
+                if (leader) {
+                    T st[S];
+#pragma unroll
+                    for (int i = 0; i < S; ++i) st[i] = T(sh.leaf[i]);
+                    double Rr = 0.0; int t = 0; bool done = false;
+                    while (!done && t < budget && !ctx.tc.fault) {
+                        const T act = T(ctx.tree_action());
+                        if (ctx.tc.fault) break;
+                        T rr;
+                        done = Env<ENV, T>::step(st, act, rr);
+                        Rr = __dadd_rn(Rr, __dmul_rn((double)rr, p.disc_table[t]));
+                        ++t;
+                    }
+                    if (tid == 0) { my_steps += t; red[0] = Rr; }
+                }
+                __syncthreads();
+            } else {
+                for (int j0 = 0; j0 < P; j0 += nt) {
+                    const int j = j0 + tid;
+                    if (j < P) {
+                        double Rr = 0.0;
+                        if (j < R) {
+                            T st[S];
+#pragma unroll
+                            for (int i = 0; i < S; ++i) st[i] = T(sh.leaf[i]);
+                            Stream rs;
+                            rs.init(p.seed, sh.sim, tree_id, (uint32_t)j);
+                            int t = 0; bool done = false;
+                            while (!done && t < budget) {
+                                const T act = sample_action<ENV, T>(rs);
+                                T rr;
+                                done = Env<ENV, T>::step(st, act, rr);
+                                Rr = __dadd_rn(Rr, __dmul_rn((double)rr, __ldg(p.disc_table + t)));
+                                ++t;
+                            }
+                            my_steps += t;
+                        }
+                        red[j] = Rr;
+                    }
+                }
+                __syncthreads();
+                // fixed power-of-two tree: the sum does not depend on the CTA size
+                for (int stride = P >> 1; stride > 0; stride >>= 1) {
+                    for (int i = tid; i < stride; i += nt) red[i] = __dadd_rn(red[i], red[i + stride]);
+                    __syncthreads();
+                }
+            }
+        }
+
+        // ------------------------------------------------------------ warp 0: leaf update + backup
+        if (leader && !ctx.fault && !ctx.tc.fault && level > 0) {
+            Pool& q = ctx.q;
+            if (need_roll) {
+                const double mean = R == 1 ? red[0] : __ddiv_rn(red[0], (double)R);
+                G = __dadd_rn(r_leaf, __dmul_rn(p.gamma, mean));
+                if (lane == 0) { q.a_na[leaf_a] += 1; q.s_ns[leaf_s] += 1; q.a_total[leaf_a] += G; q.s_total[leaf_s] += G; }
+            }
+            // the deepest level's action node was updated above; unwind the recursion for the rest
+            if (lane == 0) {
+                double g = G;
+                for (int l = level - 1; l >= 0; --l) {
+                    const int s = q.p_s[l], a = q.p_a[l], fl = q.p_flag[l];
+                    if (l < level - 1) {
+                        g = __dadd_rn(q.p_r[l], __dmul_rn(p.gamma, g));       // r + gamma * build_tree_state(child)
+                        if (fl & 2) { q.a_total[a] += g; q.a_na[a] += 1; }
+                    }
+                    q.s_ns[s] += 1; q.a_visits[a] += 1; q.s_total[s] += g;      // mcts.py:63-66
+                }
+            }
+            __syncwarp();
+            ++sims_done; ++s_done;
+        }
+        __syncthreads();
+    }
+
+    if (my_steps) { atomicAdd(p.counters + CNT_ROLLOUT_STEPS, my_steps); atomicAdd(p.counters + CNT_ENV_STEPS, my_steps); }
+    if (leader) {
+        int flt = ctx.fault ? ctx.fault : ctx.tc.fault;
+        if (lane == 0) {
+            int* m = ctx.q.meta;
+            m[CM_NS] = ctx.nS; m[CM_NA] = ctx.nA; m[CM_ITOP] = ctx.itop; m[CM_SIMS] = (int)sims_done;
+            m[CM_RNG] = (int)ctx.ts.consumed(); m[CM_FAULT] = flt;
+            if constexpr (SCRIPTED) m[CM_TRACE_POS] = (int)ctx.tc.pos;
+            atomicAdd(p.counters + CNT_ENV_STEPS, ctx.c_env);
+            atomicAdd(p.counters + CNT_ROLLOUT_STEPS, ctx.c_roll);
+            atomicAdd(p.counters + CNT_LEVELS, ctx.c_levels);
+            atomicAdd(p.counters + CNT_SIMS, (unsigned long long)s_done);
+            atomicAdd(p.counters + CNT_NODES, ctx.c_nodes);
+            if (flt) atomicAdd(p.counters + CNT_FAULTS, 1ull);
+        }
+    }
+}
+
+// root state + empty pools
+template <typename T>
+__global__ void cta_set_roots_kernel(const CtaParams p, const double* roots, int S) {
+    const long long tree = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tree >= p.n_trees) return;
+    Pool q = make_pool(p, tree);
+    q.s_total[0] = 0.0; q.s_term_reward[0] = 0.0; q.s_ns[0] = 0; q.s_flags[0] = 0; q.s_coff[0] = 0; q.s_ccap[0] = 0; q.s_ccnt[0] = 0;
+    T* st = reinterpret_cast<T*>(q.s_state);
+    for (int i = 0; i < S; ++i) {
+        T v = (T)roots[tree * S + i];
+        if (p.agent == ISLA_AGENT_SPW || p.agent == ISLA_AGENT_DPW) v = T(float(v));  // root_data is the float32 observation
+        st[i] = v;
+    }
+    for (int i = 0; i < CM_WORDS; ++i) q.meta[i] = 0;
+    q.meta[CM_NS] = 1;
+}
+
+// discrete agents: root statistics by action index
+__global__ void cta_root_stats_kernel(const CtaParams p, int64_t* na_out, double* total_out) {
+    const long long tree = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tree >= p.n_trees) return;
+    Pool q = make_pool(p, tree);
+    const int A = p.n_actions;
+    for (int a = 0; a < A; ++a) { na_out[tree * A + a] = 0; total_out[tree * A + a] = 0.0; }
+    if (A == 0) return;
+    const int off = q.s_coff[0], n = q.s_ccnt[0];
+    for (int i = 0; i < n; ++i) {
+        const int a = q.ipool[off + i];
+        const int k = (int)q.a_value[a];
+        if (k >= 0 && k < A) { na_out[tree * A + k] = q.a_na[a]; total_out[tree * A + k] = q.a_total[a]; }
+    }
+}
+
+// End of fit(): spw/dpw first re-order root.actions by key (persistently), then q = total/na and the
+// uniformly random arg-max.  One thread per tree (root fan-out is small where the order matters).
+__global__ void cta_best_kernel(const CtaParams p, int scripted_pos, int32_t* best_rank_out, double* best_action_out) {
+    const long long tree = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tree >= p.n_trees) return;
+    Pool q = make_pool(p, tree);
+    const int off = q.s_coff[0], n = q.s_ccnt[0];
+    if (n == 0) { best_rank_out[tree] = -1; if (best_action_out) best_action_out[tree] = 0.0; return; }
+    if (p.agent == ISLA_AGENT_SPW || p.agent == ISLA_AGENT_DPW) {
+        for (int x = 1; x < n; ++x) {  // stable insertion sort == sorted(items)
+            const int cur = q.ipool[off + x];
+            const double kv = q.a_value[cur];
+            int y = x;
+            while (y > 0) {
+                const double pv = q.a_value[q.ipool[off + y - 1]];
+                bool less;
+                if (p.agent == ISLA_AGENT_SPW) less = kv < pv;
+                else {  // python bytes order of the little-endian float32 keys
+                    const unsigned ku = __float_as_uint((float)kv), pu = __float_as_uint((float)pv);
+                    const unsigned kb = __byte_perm(ku, 0, 0x0123), pb = __byte_perm(pu, 0, 0x0123);
+                    less = kb < pb;
+                }
+                if (!less) break;
+                q.ipool[off + y] = q.ipool[off + y - 1];
+                --y;
+            }
+            q.ipool[off + y] = cur;
+        }
+    }
+    double qmax = -INFINITY;
+    for (int i = 0; i < n; ++i) { const int a = q.ipool[off + i]; qmax = fmax(qmax, __ddiv_rn(q.a_total[a], (double)q.a_na[a])); }
+    int ties = 0;
+    for (int i = 0; i < n; ++i) { const int a = q.ipool[off + i]; ties += (__ddiv_rn(q.a_total[a], (double)q.a_na[a]) == qmax); }
+    int pos = 0;
+    if (scripted_pos >= 0) pos = scripted_pos < ties ? scripted_pos : ties - 1;
+    else if (ties > 1) {
+        Stream ts;
+        ts.resume(p.seed, 0u, (uint32_t)(p.tree_id_base + (unsigned long long)tree), kStreamTree, (uint32_t)q.meta[CM_RNG]);
+        pos = (int)mulhi_u32(ts.next(), (uint32_t)ties);
+        q.meta[CM_RNG] = (int)ts.consumed();
+    }
+    int pick = 0;
+    for (int i = 0; i < n; ++i) {
+        const int a = q.ipool[off + i];
+        if (__ddiv_rn(q.a_total[a], (double)q.a_na[a]) == qmax) { if (pos == 0) pick = i; --pos; }
+    }
+    best_rank_out[tree] = pick;
+    if (best_action_out) best_action_out[tree] = q.a_value[q.ipool[off + pick]];
+}
+
+__global__ void cta_root_children_kernel(const CtaParams p, long long tree, int cap, double* action, int64_t* na, double* total, int32_t* count) {
+    Pool q = make_pool(p, tree);
+    const int off = q.s_coff[0], n = q.s_ccnt[0];
+    if (threadIdx.x == 0 && blockIdx.x == 0) *count = n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n && i < cap; i += gridDim.x * blockDim.x) {
+        const int a = q.ipool[off + i];
+        action[i] = q.a_value[a]; na[i] = q.a_na[a]; total[i] = q.a_total[a];
+    }
+}
+
+CtaParams make_params(const isla_engine* e) {
+    CtaParams p;
+    const isla_layout& L = e->lay;
+    p.pool_base = e->ws + L.pool_offset; p.pool_stride = L.pool_stride;
+    p.s_cap = L.s_cap; p.a_cap = L.a_cap; p.i_cap = 2 * L.a_cap + 4 * L.s_cap + 64;
+    const int rb = L.real_bytes;
+    long long off = 0;
+    auto take = [&](int idx, long long bytes) { p.off[idx] = off; off = (off + bytes + 255) / 256 * 256; };
+    take(O_S_TOTAL, L.s_cap * 8); take(O_S_TERMR, L.s_cap * 8); take(O_S_NS, L.s_cap * 4); take(O_S_FLAGS, L.s_cap * 4);
+    take(O_S_COFF, L.s_cap * 4); take(O_S_CCAP, L.s_cap * 4); take(O_S_CCNT, L.s_cap * 4); take(O_S_STATE, L.s_cap * L.state_dim * rb);
+    take(O_A_TOTAL, L.a_cap * 8); take(O_A_VALUE, L.a_cap * 8); take(O_A_NA, L.a_cap * 4); take(O_A_VISITS, L.a_cap * 4);
+    take(O_A_CHILD, L.a_cap * 4); take(O_IPOOL, p.i_cap * 4);
+    take(O_P_S, L.s_cap * 4); take(O_P_A, L.s_cap * 4); take(O_P_R, L.s_cap * 8); take(O_P_FLAG, L.s_cap * 4);
+    take(O_META, CM_WORDS * 4);
+    p.off[O_COUNT] = off;
+    p.counters = (unsigned long long*)(e->ws + L.counters_offset);
+    p.trace_kinds = nullptr; p.trace_values = nullptr; p.trace_len = 0;
+    p.n_trees = e->cfg.n_trees; p.scripted_tree = -1;
+    p.seed = e->cfg.seed; p.tree_id_base = e->cfg.tree_id_base;
+    p.C = e->cfg.C; p.gamma = e->cfg.gamma; p.alpha1 = e->cfg.alpha1; p.k1 = e->cfg.k1; p.alpha2 = e->cfg.alpha2; p.k2 = e->cfg.k2;
+    p.epsilon = e->cfg.epsilon;
+    p.disc_table = (const double*)(e->ws + L.disc_offset); p.ln_table = (const double*)(e->ws + L.ln_offset);
+    p.pw1_table = (const double*)(e->ws + L.pw1_offset); p.pw2_table = (const double*)(e->ws + L.pw2_offset);
+    p.ln_count = (int)L.ln_count; p.disc_count = (int)L.disc_count;
+    p.n_sim = 0; p.max_depth = e->cfg.max_depth; p.budget_mode = e->cfg.budget_mode; p.agent = e->cfg.agent;
+    p.n_actions = e->cfg.n_actions; p.R = e->cfg.rollouts_per_leaf > 0 ? e->cfg.rollouts_per_leaf : 1;
+    p.expansion = e->cfg.expansion; p.voo_n = e->cfg.voo_n_samples; p.voo_max_try = e->cfg.voo_max_try; p.real_bytes = rb;
+    return p;
+}
+
+long long pool_bytes(const isla_config& cfg, long long s_cap, long long a_cap, int S, int rb) {
+    isla_engine tmp;
+    tmp.cfg = cfg; tmp.ws = nullptr;
+    tmp.lay.pool_offset = 0; tmp.lay.pool_stride = 0; tmp.lay.s_cap = s_cap; tmp.lay.a_cap = a_cap; tmp.lay.real_bytes = rb;
+    tmp.lay.state_dim = S; tmp.lay.counters_offset = 0; tmp.lay.disc_offset = 0; tmp.lay.ln_offset = 0; tmp.lay.ln_count = 0; tmp.lay.disc_count = 0; tmp.lay.pw1_offset = 0; tmp.lay.pw2_offset = 0;
+    return make_params(&tmp).off[O_COUNT];
+}
+
+int pick_threads(const isla_config& cfg) {
+    int nt = cfg.block_threads;
+    if (nt <= 0) {
+        const int R = cfg.rollouts_per_leaf > 0 ? cfg.rollouts_per_leaf : 1;
+        nt = 32;
+        while (nt < R && nt < 512) nt <<= 1;
+    }
+    nt = (nt + 31) / 32 * 32;
+    return nt > 512 ? 512 : nt;
+}
+
+template <int ENV, typename T>
+int launch(const CtaParams& p, int nt, bool scripted, cudaStream_t st) {
+    if (scripted) cta_search_kernel<ENV, T, true><<<1, nt, 0, st>>>(p);
+    else cta_search_kernel<ENV, T, false><<<(unsigned)p.n_trees, nt, 0, st>>>(p);
+    const cudaError_t err = cudaGetLastError();
+    return err == cudaSuccess ? 0 : cuda_fail(err, "cta_search_kernel launch");
+}
+
+template <typename T>
+int launch_env(const isla_engine* e, const CtaParams& p, int nt, bool scripted, cudaStream_t st) {
+    switch (e->cfg.env_id) {
+    case ISLA_ENV_CARTPOLE: return launch<ENV_CARTPOLE, T>(p, nt, scripted, st);
+    case ISLA_ENV_PENDULUM: return launch<ENV_PENDULUM, T>(p, nt, scripted, st);
+    case ISLA_ENV_MOUNTAINCAR: return launch<ENV_MOUNTAINCAR, T>(p, nt, scripted, st);
+    case ISLA_ENV_FROZENLAKE: return launch<ENV_FROZENLAKE, T>(p, nt, scripted, st);
+    }
+    set_error("unknown env %d", e->cfg.env_id);
+    return ISLA_ERR_INVALID;
+}
+
+}  // namespace
+
+int cta_fill_layout(const isla_config& cfg, isla_layout& lay) {
+    const int S = env_state_dim(cfg.env_id);
+    const int rb = cfg.precision == ISLA_PRECISION_F64 ? 8 : 4;
+    const int R = cfg.rollouts_per_leaf > 0 ? cfg.rollouts_per_leaf : 1;
+    if (R > kMaxRollSmem) { set_error("rollouts_per_leaf %d exceeds %d", R, kMaxRollSmem); return ISLA_ERR_INVALID; }
+    if ((cfg.agent == ISLA_AGENT_VANILLA || cfg.agent == ISLA_AGENT_SPW) && (cfg.n_actions < 1 || cfg.n_actions > 32 ||
+                                                                           cfg.n_actions != env_n_actions(cfg.env_id))) {
+        set_error("n_actions=%d does not match env (%d)", cfg.n_actions, env_n_actions(cfg.env_id)); return ISLA_ERR_INVALID;
+    }
+    if (cfg.expansion == ISLA_EXPAND_VOO && cfg.agent != ISLA_AGENT_APW) { set_error("voo expansion is an APW option"); return ISLA_ERR_INVALID; }
+    if (cfg.expansion == ISLA_EXPAND_VOO && (cfg.voo_n_samples < 1 || cfg.voo_n_samples > 8 || cfg.voo_max_try < 1)) {
+        set_error("voo: n_samples must be in [1, 8] and max_try >= 1"); return ISLA_ERR_INVALID;
+    }
+    auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
+    lay.kernel = ISLA_KERNEL_CTA_PER_TREE;
+    lay.state_dim = S; lay.real_bytes = rb; lay.n_actions = cfg.n_actions;
+    lay.s_cap = (int64_t)cfg.sim_capacity + 2; lay.a_cap = (int64_t)cfg.sim_capacity + 2;
+    lay.slots_per_tree = 0; lay.rec_offset = lay.rec_stride = lay.state_offset = lay.state_stride = lay.meta_offset = lay.path_offset = 0;
+    int64_t off = 0;
+    lay.pool_offset = off; lay.pool_stride = pool_bytes(cfg, lay.s_cap, lay.a_cap, S, rb); off = up(off + cfg.n_trees * lay.pool_stride);
+    lay.counters_offset = off; off = up(off + 64);
+    add_table_layout(cfg, lay, off);
+    lay.total_bytes = off;
+    return 0;
+}
+
+int cta_set_roots(isla_engine* e, const double* roots_dev, cudaStream_t st) {
+    CtaParams p = make_params(e);
+    ISLA_CUDA_OK(cudaMemsetAsync(e->ws + e->lay.counters_offset, 0, 64, st));
+    const unsigned grid = (unsigned)((e->cfg.n_trees + 127) / 128);
+    if (e->lay.real_bytes == 4) cta_set_roots_kernel<float><<<grid, 128, 0, st>>>(p, roots_dev, e->lay.state_dim);
+    else cta_set_roots_kernel<double><<<grid, 128, 0, st>>>(p, roots_dev, e->lay.state_dim);
+    ISLA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int cta_run(isla_engine* e, int n_sim, long long scripted_tree, const uint8_t* kinds, const double* values,
+            long long trace_len, cudaStream_t st) {
+    CtaParams p = make_params(e);
+    p.n_sim = n_sim; p.scripted_tree = scripted_tree; p.trace_kinds = kinds; p.trace_values = values; p.trace_len = trace_len;
+    const bool scripted = scripted_tree >= 0;
+    if (scripted && p.R != 1) { set_error("scripted runs need rollouts_per_leaf == 1"); return ISLA_ERR_INVALID; }
+    const int nt = scripted ? 32 : pick_threads(e->cfg);
+    return e->lay.real_bytes == 8 ? launch_env<double>(e, p, nt, scripted, st) : launch_env<float>(e, p, nt, scripted, st);
+}
+
+int cta_root_stats(isla_engine* e, int64_t* na_dev, double* total_dev, cudaStream_t st) {
+    if (e->cfg.n_actions < 1) { set_error("root_stats by action index needs a discrete agent; use isla_engine_root_children"); return ISLA_ERR_INVALID; }
+    CtaParams p = make_params(e);
+    cta_root_stats_kernel<<<(unsigned)((e->cfg.n_trees + 127) / 128), 128, 0, st>>>(p, na_dev, total_dev);
+    ISLA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int cta_best(isla_engine* e, int scripted_pos, int32_t* best_dev, double* best_action_dev, cudaStream_t st) {
+    CtaParams p = make_params(e);
+    cta_best_kernel<<<(unsigned)((e->cfg.n_trees + 127) / 128), 128, 0, st>>>(p, scripted_pos, best_dev, best_action_dev);
+    ISLA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int cta_root_children(isla_engine* e, long long tree, int cap, double* action, int64_t* na, double* total, int32_t* count,
+                      cudaStream_t st) {
+    CtaParams p = make_params(e);
+    cta_root_children_kernel<<<8, 256, 0, st>>>(p, tree, cap, action, na, total, count);
+    ISLA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+void cta_pool_offsets(const isla_engine* e, long long out[24]) {
+    CtaParams p = make_params(e);
+    for (int i = 0; i < 24; ++i) out[i] = i <= O_COUNT ? p.off[i] : 0;
+}
+
 }  // namespace isla

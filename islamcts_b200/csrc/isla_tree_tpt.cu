@@ -380,7 +380,7 @@ __global__ void tpt_root_stats_kernel(const EdgeRec* recs, long long n_trees, lo
 // end of fit(): q = total/na over the root's children, uniformly random arg-max (mcts_hash.py:42-50)
 __global__ void tpt_best_kernel(const EdgeRec* recs, int32_t* meta, long long n_trees, long long slots_per_tree, int A,
                                 unsigned long long seed, unsigned long long tree_id_base, int scripted_pos,
-                                int32_t* best_out) {
+                                int32_t* best_out, double* best_action_out) {
     const long long tree = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (tree >= n_trees) return;
     double q[16];
@@ -394,7 +394,7 @@ __global__ void tpt_best_kernel(const EdgeRec* recs, int32_t* meta, long long n_
         if (r.na_in > 0) best = fmax(best, q[a]);
     }
     for (int a = 0; a < A; ++a) ties += (rank[a] >= 0 && q[a] == best);
-    if (ties == 0) { best_out[tree] = -1; return; }
+    if (ties == 0) { best_out[tree] = -1; if (best_action_out) best_action_out[tree] = 0.0; return; }
     int pos = 0;
     if (scripted_pos >= 0) pos = scripted_pos < ties ? scripted_pos : ties - 1;
     else if (ties > 1) {
@@ -408,7 +408,8 @@ __global__ void tpt_best_kernel(const EdgeRec* recs, int32_t* meta, long long n_
     for (int rk = 0; rk < A; ++rk)
         for (int a = 0; a < A; ++a)
             if (rank[a] == rk && q[a] == best) { if (pos == 0) sel = a; --pos; }
-    best_out[tree] = sel;
+    best_out[tree] = sel >= 0 ? rank[sel] : -1;
+    if (best_action_out) best_action_out[tree] = (double)sel;
 }
 
 template <int ENV, typename T>
@@ -507,11 +508,11 @@ int tpt_root_stats(isla_engine* e, int64_t* na_dev, double* total_dev, cudaStrea
     return 0;
 }
 
-int tpt_best(isla_engine* e, int scripted_pos, int32_t* best_dev, cudaStream_t st) {
+int tpt_best(isla_engine* e, int scripted_pos, int32_t* best_dev, double* best_action_dev, cudaStream_t st) {
     const isla_layout& L = e->lay;
     tpt_best_kernel<<<(unsigned)((e->cfg.n_trees + 255) / 256), 256, 0, st>>>(
         (const EdgeRec*)(e->ws + L.rec_offset), (int32_t*)(e->ws + L.meta_offset), e->cfg.n_trees, L.slots_per_tree,
-        L.n_actions, e->cfg.seed, e->cfg.tree_id_base, scripted_pos, best_dev);
+        L.n_actions, e->cfg.seed, e->cfg.tree_id_base, scripted_pos, best_dev, best_action_dev);
     ISLA_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -124,11 +124,27 @@ class Engine:
         return na, tot
 
     def best(self, scripted_pos: int = -1):
-        out = torch.empty((self.n_trees,), dtype=torch.int32, device=self.device)
+        """End of fit(): (rank in root.actions, action value) per tree -- device tensors (int32, float64)."""
+        rank = torch.empty((self.n_trees,), dtype=torch.int32, device=self.device)
+        act = torch.empty((self.n_trees,), dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
-            check(self.lib.isla_engine_best(self._h, int(scripted_pos), C.c_void_p(out.data_ptr()),
-                                            C.c_void_p(_stream_ptr(self.device))))
-        return out
+            check(self.lib.isla_engine_best(self._h, int(scripted_pos), C.c_void_p(rank.data_ptr()),
+                                            C.c_void_p(act.data_ptr()), C.c_void_p(_stream_ptr(self.device))))
+        return rank, act
+
+    def root_children(self, tree: int = 0):
+        """(action, na, total) numpy arrays of one tree's root children in root.actions order (CTA engine)."""
+        cnt = torch.zeros(1, dtype=torch.int32, device=self.device)
+        cap = max(16, int(self.layout.a_cap))
+        a = torch.empty(cap, dtype=torch.float64, device=self.device)
+        na = torch.empty(cap, dtype=torch.int64, device=self.device)
+        tot = torch.empty(cap, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.isla_engine_root_children(self._h, int(tree), cap, C.c_void_p(a.data_ptr()),
+                                                     C.c_void_p(na.data_ptr()), C.c_void_p(tot.data_ptr()),
+                                                     C.c_void_p(cnt.data_ptr()), C.c_void_p(_stream_ptr(self.device))))
+        n = int(cnt.item())
+        return a[:n].cpu().numpy(), na[:n].cpu().numpy(), tot[:n].cpu().numpy()
 
     def counters(self) -> dict:
         out = (C.c_int64 * 8)()
@@ -142,8 +158,18 @@ class Engine:
         return self.workspace[lo: lo + int(nbytes)].cpu().numpy()
 
     def tree_meta(self, tree: int = 0) -> dict:
+        if self.layout.kernel == _lib.KERNEL_CTA_PER_TREE:
+            off = self.pool_offsets()
+            m = self._ws_bytes(self.layout.pool_offset + tree * self.layout.pool_stride + off[18], 32).view(np.int32)
+            return dict(state_nodes=int(m[0]), action_nodes=int(m[1]), sims=int(m[3]), rng_words=int(m[4]),
+                        fault=int(m[5]), trace_pos=int(m[6]))
         m = self._ws_bytes(self.layout.meta_offset + tree * 32, 32).view(np.int32)
         return dict(alloc=int(m[0]), sims=int(m[1]), rng_words=int(m[2]), fault=int(m[3]), trace_pos=int(m[4]))
+
+    def pool_offsets(self):
+        out = (C.c_int64 * 24)()
+        check(self.lib.isla_engine_pool_offsets(self._h, out))
+        return [int(x) for x in out]
 
     def raw_records(self, tree: int = 0) -> np.ndarray:
         L = self.layout

@@ -287,8 +287,9 @@ static void env_set_from_obs(orc_tree* t, const float* obs) {
  * SURVEY 8a) share the leaf state; rollout j draws from stream (seed, tree, sim, j). */
 static double do_rollout(orc_tree* t, int budget) {
     const int R = t->cfg.rollouts_per_leaf > 0 ? t->cfg.rollouts_per_leaf : 1;
+    int P = 1; while (P < R) P <<= 1;
     double leaf[4]; memcpy(leaf, t->env, sizeof leaf);
-    double sum = 0;
+    double* x = (double*)calloc((size_t)P, sizeof(double));
     for (int j = 0; j < R; ++j) {
         memcpy(t->env, leaf, sizeof leaf);
         if (!scripted(t)) stream_init(&t->roll_stream, t->cfg.seed, t->sim_index, (uint32_t)t->cfg.tree_id, (uint32_t)j);
@@ -300,8 +301,14 @@ static double do_rollout(orc_tree* t, int budget) {
             reward += r * pow(t->cfg.gamma, depth);
             done = term; depth++; t->c_roll_steps++;
         }
-        sum += reward;
+        x[j] = reward;
     }
+    /* R > 1 is a build extension with no reference: the batch mean is DEFINED as the fixed
+     * power-of-two pairwise tree below (zero padded), divided by R -- the order the CUDA engine uses. */
+    for (int stride = P >> 1; stride > 0; stride >>= 1)
+        for (int i = 0; i < stride; ++i) x[i] = x[i] + x[i + stride];
+    double sum = x[0];
+    free(x);
     return R == 1 ? sum : sum / R;
 }
 

@@ -1,0 +1,138 @@
+"""CTA-per-tree general engine (vanilla / APW / SPW / DPW / VOO / leaf-parallel batches) vs the reference
+goldens and the CPU oracle, through the C ABI."""
+import numpy as np
+import pytest
+
+from oracle import coracle
+from tests.golden_util import assert_tree_equal, engine_kwargs, golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(kw, n_trees, sim_capacity, precision, **extra):
+    from islamcts_b200.engine import Engine
+    kw = dict(kw)
+    return Engine(kw.pop("env_id"), agent=kw.pop("agent"), n_trees=n_trees, sim_capacity=sim_capacity,
+                  C_=kw.pop("C"), precision=precision, kernel=2, **kw, **extra)
+
+
+@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("precision", [1, 0])
+def test_scripted_trace_rebuilds_reference_tree_cta(name, precision):
+    """All five agents: replaying the reference's decision trace rebuilds the reference's tree."""
+    g = load_golden(name)
+    cfg = g["config"]
+    eng = _engine(engine_kwargs(cfg), 1, cfg["n_sim"] + 8, precision)
+    eng.set_roots(g["root_state"][None, :])
+    kinds, vals = g["trace_kind"], g["trace_value"]
+    eng.run_scripted(0, cfg["n_sim"], kinds, vals)
+    meta = eng.tree_meta(0)
+    assert meta["fault"] == 0, meta
+    assert meta["trace_pos"] == len(kinds) - 1 and meta["sims"] == cfg["n_sim"]
+    rank, act = eng.best(scripted_pos=int(vals[-1]))           # also applies the spw/dpw root re-ordering
+    # float32 env: rewards of Pendulum/MountainCar differ in the 7th digit -> totals to 2e-5; counts stay exact
+    tol = 1e-9 if precision == 1 else 2e-5
+    assert float(act.cpu()[0]) == pytest.approx(float(g["fit_action"]), abs=1e-12)
+    assert_tree_equal(eng.export_tree(0), g, rtol=tol, atol=tol, label=f"{name}/p{precision}: ")
+    a, na, tot = eng.root_children(0)
+    np.testing.assert_array_equal(na, g["root_na"])
+    np.testing.assert_allclose(a, g["root_action"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(tot, g["root_total"], rtol=tol, atol=tol)
+
+
+FREE = {
+    "vanilla_cartpole": dict(env_id=0, agent=0, n_actions=2, max_depth=60, C=1.0, gamma=0.97),
+    "vanilla_lake": dict(env_id=3, agent=0, n_actions=4, max_depth=30, C=0.5, gamma=0.9),
+    "apw_pendulum": dict(env_id=1, agent=1, max_depth=25, C=2.0, gamma=0.95, alpha1=0.45, k1=1.0),
+    "apw_voo_pendulum": dict(env_id=1, agent=1, max_depth=15, C=2.0, gamma=0.95, alpha1=0.5, k1=2.0, expansion=1,
+                             epsilon=0.4, voo_n_samples=3, voo_max_try=20),
+    "apw_mountaincar_c3like": dict(env_id=2, agent=1, max_depth=40, C=1.0, gamma=0.99, alpha1=0.8, k1=60.0),
+    "spw_cartpole_descend": dict(env_id=0, agent=2, n_actions=2, max_depth=40, C=1.0, gamma=0.9, alpha1=0.3, k1=0.4),
+    "spw_cartpole_k1": dict(env_id=0, agent=2, n_actions=2, max_depth=40, C=1.0, gamma=0.9, alpha1=0.5, k1=1.0),
+    "dpw_mountaincar_c4like": dict(env_id=2, agent=3, max_depth=50, C=1.0, gamma=0.99, alpha1=0.5, k1=1.0, alpha2=0.5, k2=1.0),
+    "dpw_mountaincar_descend": dict(env_id=2, agent=3, max_depth=50, C=0.5, gamma=0.95, alpha1=0.4, k1=1.0, alpha2=0.2, k2=0.5),
+}
+
+
+@pytest.mark.parametrize("name", sorted(FREE))
+@pytest.mark.parametrize("R", [1, 24])
+def test_free_running_f64_equals_oracle(name, R):
+    """Budgeted rollouts for every agent (no runnable reference exists for apw/spw/dpw with rollouts, SURVEY 8c iv):
+    the CUDA engine and the C oracle share the Philox streams, so whole trees must agree node for node."""
+    kw = FREE[name]
+    n_trees, n_sim = 24, 160
+    roots = np.stack([coracle.env_reset(kw["env_id"], 5, i) for i in range(n_trees)])
+    eng = _engine(kw, n_trees, n_sim, 1, rollouts_per_leaf=R, seed=2024, tree_id_base=70)
+    eng.set_roots(roots).run(n_sim)
+    assert eng.counters()["faults"] == 0
+    okw = dict(kw)
+    conf_kw = dict(agent=okw.pop("agent"), n_actions=okw.pop("n_actions", 0), C_=okw.pop("C"), rollouts_per_leaf=R, seed=2024)
+    env_id = okw.pop("env_id")
+    levels = 0
+    for i in range(n_trees):
+        t = coracle.Tree(coracle.make_config(env_id, tree_id=70 + i, **conf_kw, **okw), roots[i])
+        assert t.run(n_sim) == 0
+        exp = {"tree_" + k: v for k, v in t.serialise().items()}
+        assert_tree_equal(eng.export_tree(i), exp, rtol=1e-9, atol=1e-9, label=f"{name}/tree{i}: ")
+        levels += t.counters()["levels"]
+        if i == 3:
+            rank, act = eng.best()
+            rc, erank, eact = t.best()
+            assert int(rank.cpu()[3]) == erank and float(act.cpu()[3]) == eact
+    assert eng.counters()["levels"] == levels
+
+
+def test_result_independent_of_cta_size_and_equal_to_thread_per_tree():
+    from islamcts_b200.engine import Engine
+    n_trees, n_sim = 64, 150
+    roots = np.stack([coracle.env_reset(0, 9, i) for i in range(n_trees)])
+    out = []
+    for nt in (32, 128, 512):
+        e = Engine(0, n_trees=n_trees, sim_capacity=n_sim, max_depth=80, gamma=0.98, precision=0, kernel=2,
+                   rollouts_per_leaf=100, block_threads=nt, seed=5)
+        e.set_roots(roots).run(n_sim)
+        na, tot = e.root_stats()
+        out.append((na.cpu().numpy(), tot.cpu().numpy()))
+    for na, tot in out[1:]:
+        np.testing.assert_array_equal(na, out[0][0])
+        np.testing.assert_array_equal(tot, out[0][1])          # bit-identical: fixed reduction tree
+    a = Engine(0, n_trees=n_trees, sim_capacity=n_sim, max_depth=80, gamma=0.98, precision=0, kernel=2, seed=5)
+    b = Engine(0, n_trees=n_trees, sim_capacity=n_sim, max_depth=80, gamma=0.98, precision=0, kernel=1, seed=5)
+    a.set_roots(roots).run(n_sim); b.set_roots(roots).run(n_sim)
+    np.testing.assert_array_equal(a.root_stats()[0].cpu().numpy(), b.root_stats()[0].cpu().numpy())
+    np.testing.assert_array_equal(a.root_stats()[1].cpu().numpy(), b.root_stats()[1].cpu().numpy())
+    assert_tree_equal(a.export_tree(7), {"tree_" + k: v for k, v in b.export_tree(7).items()}, rtol=0, atol=0)
+
+
+def test_c2_shape_leaf_parallel_4096_matches_oracle():
+    """BASELINE C2: one CartPole tree, nsim=1000, max_depth=500, gamma=0.99, 4096 rollouts per leaf."""
+    from islamcts_b200.engine import Engine
+    root = coracle.env_reset(0, 0, 0)
+    eng = Engine(0, n_trees=1, sim_capacity=300, max_depth=500, C_=1.0, gamma=0.99, precision=1, kernel=2,
+                 rollouts_per_leaf=4096, seed=1)
+    eng.set_roots(root[None, :]).run(300)
+    t = coracle.Tree(coracle.make_config(0, n_actions=2, max_depth=500, C_=1.0, gamma=0.99, rollouts_per_leaf=4096, seed=1), root)
+    t.run(300)
+    assert_tree_equal(eng.export_tree(0), {"tree_" + k: v for k, v in t.serialise().items()}, rtol=1e-9, atol=1e-9)
+    c = eng.counters()
+    assert c["faults"] == 0 and c["sims"] == 300 and c["rollout_steps"] == t.counters()["rollout_steps"]
+
+
+def test_c3_c4_shapes_run_at_full_size():
+    """BASELINE C3 (APW Pendulum, k=60, alpha=0.8, nsim=10000, max_depth=200) and C4 (DPW MountainCarContinuous,
+    alpha=0.5, nsim=10000, max_depth=500): integer invariants + the widening arithmetic SURVEY 8a computes."""
+    from islamcts_b200.engine import Engine
+    e3 = Engine(1, agent=1, n_trees=1, sim_capacity=10000, max_depth=200, C_=1.0, gamma=0.99, alpha1=0.8, k1=60.0,
+                precision=0, kernel=2, rollouts_per_leaf=32, seed=3)
+    e3.set_roots(coracle.env_reset(1, 0, 0)[None, :]).run(10000)
+    a, na, tot = e3.root_children(0)
+    assert e3.counters()["faults"] == 0
+    assert len(a) >= 9990 and na.sum() == 10000      # the root widens on (almost) every simulation: tree depth 1
+    e4 = Engine(2, agent=3, n_trees=1, sim_capacity=10000, max_depth=500, C_=1.0, gamma=0.99, alpha1=0.5, k1=1.0,
+                alpha2=0.5, k2=1.0, precision=0, kernel=2, rollouts_per_leaf=32, seed=4)
+    e4.set_roots(coracle.env_reset(2, 0, 0)[None, :]).run(10000)
+    a, na, tot = e4.root_children(0)
+    assert e4.counters()["faults"] == 0
+    assert len(a) == 101 and na.sum() == 10000       # the root reaches 101 children, 9 899 UCB picks
+    ser = e4.export_tree(0)
+    assert ser["count"][0] == 10000 and ser["depth"].max() == 1

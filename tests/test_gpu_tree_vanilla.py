@@ -35,8 +35,8 @@ def test_scripted_trace_rebuilds_reference_tree_tpt(name, precision):
     tol = 1e-9 if precision == 1 else 1e-6
     assert_tree_equal(got, g, rtol=tol, atol=tol, label=f"{name}/p{precision}: ")
     # end of fit(): arg-max with the recorded tie-break position
-    best = int(eng.best(scripted_pos=int(vals[-1])).cpu()[0])
-    assert float(best) == float(g["fit_action"])
+    rank, act = eng.best(scripted_pos=int(vals[-1]))
+    assert float(act.cpu()[0]) == float(g["fit_action"])
     na, tot = eng.root_stats()
     na, tot = na.cpu().numpy()[0], tot.cpu().numpy()[0]
     for a, n_, t_ in zip(g["root_action"].astype(int), g["root_na"], g["root_total"]):
@@ -71,9 +71,9 @@ def test_free_running_f64_equals_oracle_bit_for_bit(env_id, n_sim, max_depth, C,
     exp = {"tree_" + k: v for k, v in t5.serialise().items()}
     assert_tree_equal(eng.export_tree(5), exp)
     # arg-max pick draws from the same tree stream
-    best = eng.best().cpu().numpy()
+    best_rank, best_act = eng.best()
     _, rank, act = t5.best()
-    assert best[5] == int(act)
+    assert int(best_act.cpu()[5]) == int(act) and int(best_rank.cpu()[5]) == rank
 
 
 def test_free_running_f32_env_agrees_with_f64_oracle_statistically():
