@@ -1,0 +1,288 @@
+"""Host-side mirror of islaMcts/agents/abstract_mcts.py: the agent API in front of the device engine.
+
+``Agent(param).fit()`` keeps the reference's contract (agents/abstract_mcts.py:12-49, agents/mcts_hash.py:22-50):
+synchronous, returns the action of the arg-max-q root child, ``fit()`` again continues the same tree, and
+afterwards ``agent.root`` / ``agent.q_values`` can be inspected.  The simulate loop itself runs inside
+libisla_b200.so; the node objects the reference builds while searching are replaced by lazy proxies decoded
+from the device tree on first access.
+"""
+from __future__ import annotations
+
+from typing import Any
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..engine import ENV_NAMES, N_ACTIONS, STATE_DIM, Engine
+from .parameters.mcts_parameters import MctsParameters
+
+_LAKE_MAP = ("SFFF", "FHFH", "FFFH", "HFFG")
+
+
+def identify_env(env) -> int:
+    """gym-style env object -> engine env id.  Anything else: NotImplementedError (no CPU fallback)."""
+    u = getattr(env, "unwrapped", env)
+    name = getattr(getattr(u, "spec", None), "id", None) or getattr(u, "spec_id", None) or type(u).__name__
+    low = str(name).lower()
+    if "cartpole" in low:
+        return _lib.ENV_CARTPOLE
+    if "pendulum" in low:
+        return _lib.ENV_PENDULUM
+    if "mountaincar" in low and ("continuous" in low or hasattr(getattr(u, "action_space", None), "low")):
+        return _lib.ENV_MOUNTAINCAR
+    if "frozenlake" in low:
+        desc = getattr(u, "desc", None)
+        if desc is not None:
+            rows = tuple("".join(c.decode() if isinstance(c, bytes) else str(c) for c in r) for r in np.asarray(desc))
+            if rows != _LAKE_MAP:
+                raise NotImplementedError(f"FrozenLake map {rows} is not on the device (only the default 4x4 map)")
+        P = getattr(u, "P", None)
+        if P is not None and len(P[0][0]) != 1:
+            raise NotImplementedError("FrozenLake is_slippery=True is not on the device yet (SURVEY 8f)")
+        return _lib.ENV_FROZENLAKE
+    raise NotImplementedError(f"environment {name!r} has no device implementation (supported: {sorted(ENV_NAMES)})")
+
+
+def env_root_state(env, env_id: int) -> np.ndarray:
+    u = getattr(env, "unwrapped", env)
+    if env_id == _lib.ENV_FROZENLAKE:
+        return np.array([float(int(u.s))], dtype=np.float64)
+    st = getattr(u, "state", None)
+    if st is None:
+        raise ValueError("env.unwrapped.state is None: call env.reset() before fit()")
+    return np.asarray(st, dtype=np.float64).reshape(-1)[: STATE_DIM[env_id]].copy()
+
+
+def _kind(fn, what):
+    k = getattr(fn, "isla_kind", None)
+    if k is None and getattr(fn, "__name__", "") in ("ucb1", "continuous_default_policy"):
+        k = {"ucb1": "ucb1", "continuous_default_policy": "random"}[fn.__name__]   # the reference's own functions
+    if k is None:
+        raise NotImplementedError(f"{what}={fn!r} cannot run on the device: use the callables of "
+                                  f"islamcts_b200.utils.action_selection_functions (no CPU fallback by design)")
+    return k
+
+
+# --------------------------------------------------------------------------- lazy node proxies
+class AbstractStateNode:
+    __slots__ = ("data", "param", "terminal", "total", "ns", "actions", "terminal_reward", "visit_actions")
+
+    def __init__(self, data: Any, param):
+        self.data, self.param = data, param
+        self.terminal, self.total, self.ns = False, 0, 0
+        self.actions: dict = {}
+        self.terminal_reward = None
+        self.visit_actions = None
+
+    def get_depth_max(self, depth: int = 0):
+        # agents/abstract_mcts.py:120-130
+        depth += 1
+        depths = [a.get_depth_max(depth) for a in self.actions.values()]
+        return max(depths) if depths else depth
+
+    def get_depth_mean(self, depth: int = 0):
+        # agents/abstract_mcts.py:132-142
+        depth += 1
+        depths = []
+        for a in self.actions.values():
+            depths.extend(a.get_depth_mean(depth))
+        return depths if depths else [depth]
+
+
+class AbstractActionNode:
+    __slots__ = ("data", "total", "na", "children", "param")
+
+    def __init__(self, data: Any, param):
+        self.data, self.param = data, param
+        self.total, self.na = 0, 0
+        self.children: dict = {}
+
+    @property
+    def q_value(self):
+        return self.total / self.na   # ZeroDivisionError when na == 0, like the reference (:154-156)
+
+    def get_depth_max(self, depth):
+        depths = [s.get_depth_max(depth) for s in self.children.values()]
+        return max(depths) if depths else depth
+
+    def get_depth_mean(self, depth=0, root=False):
+        depths = []
+        for s in self.children.values():
+            depths.extend(s.get_depth_mean(depth))
+        if root:
+            return float(np.mean(depths)) if depths else depth
+        return depths
+
+
+class AbstractMcts:
+    """Common driver.  Subclasses set AGENT (engine enum), HEAD_BUDGET (what the class does at reference HEAD)."""
+
+    AGENT = _lib.AGENT_VANILLA
+    HEAD_ZERO_ROLLOUTS = True      # Mcts/APW/SPW/DPW start the recursion at max_depth
+    DISCRETE = True
+
+    def __init__(self, param: MctsParameters):
+        self.param = param
+        self.data: Any = None
+        self.q_values = None
+        self.trajectories_x: list = []
+        self.trajectories_y: list = []
+        self.param.depths = []
+        self._engine: Engine | None = None
+        self._engine_key = None
+        self._root_proxy = None
+        self._root_stub = AbstractStateNode(param.root_data, param)
+        self.root_statistics = None
+
+    # ``agent.root.data = observation`` is assigned by callers before fit() (sweep.py:189)
+    @property
+    def root(self):
+        if self._engine is None:
+            return self._root_stub
+        if self._root_proxy is None:
+            self._root_proxy = self._build_proxy()
+        return self._root_proxy
+
+    @root.setter
+    def root(self, value):
+        self._root_stub = value
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _engine_kwargs(self, env_id):
+        p = self.param
+        if _kind(p.action_selection_fn, "action_selection_fn") != "ucb1":
+            raise NotImplementedError("action_selection_fn must be ucb1")
+        if _kind(p.rollout_selection_fn, "rollout_selection_fn") != "random":
+            raise NotImplementedError("rollout_selection_fn must be continuous_default_policy (env.action_space.sample())")
+        if p.depth_mode not in ("budgeted", "reference_head"):
+            raise ValueError("depth_mode must be 'budgeted' or 'reference_head'")
+        zero = p.depth_mode == "reference_head" and self.HEAD_ZERO_ROLLOUTS
+        kw = dict(agent=self.AGENT, n_trees=int(p.n_trees), max_depth=int(p.max_depth), C_=float(p.C), gamma=float(p.gamma),
+                  budget_mode=_lib.BUDGET_ZERO if zero else _lib.BUDGET_TO_MAX_DEPTH,
+                  rollouts_per_leaf=int(p.rollouts_per_leaf),
+                  precision=_lib.PRECISION_F64 if p.precision == "f64" else _lib.PRECISION_F32, device=p.device)
+        if self.DISCRETE:
+            n = N_ACTIONS[env_id]
+            if n == 0:
+                raise NotImplementedError(f"{type(self).__name__} needs a discrete action space")
+            if p.n_actions is not None and int(p.n_actions) != n:
+                raise ValueError(f"n_actions={p.n_actions} but the environment has {n} actions")
+            kw["n_actions"] = n
+        elif N_ACTIONS[env_id] != 0:
+            raise NotImplementedError(f"{type(self).__name__} samples a continuous Box action space")
+        self._agent_kwargs(kw)
+        return kw
+
+    def _agent_kwargs(self, kw):
+        pass
+
+    def _ensure_engine(self, env_id, root_state):
+        p = self.param
+        kw = self._engine_kwargs(env_id)
+        key = (env_id, tuple(sorted((k, v) for k, v in kw.items())), tuple(root_state.tolist()))
+        if self._engine is not None and key == self._engine_key and self._sims_done + p.n_sim <= self._capacity:
+            return                                     # fit() again continues the same tree
+        if self._engine is not None and key == self._engine_key:
+            raise _lib.IslaError(_lib.ERR_CAPACITY, "tree capacity exhausted; create a new agent")
+        seed = p.seed if p.seed is not None else int(np.random.randint(0, 2**31 - 1))
+        self._capacity = max(4 * int(p.n_sim), 64)
+        self._engine = Engine(env_id, sim_capacity=self._capacity, seed=seed, **kw)
+        self._engine.set_roots(np.tile(root_state[None, :], (int(p.n_trees), 1)))
+        self._engine_key = key
+        self._sims_done = 0
+
+    # ------------------------------------------------------------------ fit
+    def fit(self):
+        """Builds the tree(s) on the device and returns the best action (reference: mcts_hash.py:22-50)."""
+        p = self.param
+        if p.env is None:
+            raise ValueError("param.env is None")
+        env_id = identify_env(p.env)
+        root_state = env_root_state(p.env, env_id)
+        self._ensure_engine(env_id, root_state)
+        eng = self._engine
+        eng.run(int(p.n_sim))
+        self._sims_done += int(p.n_sim)
+        self._root_proxy = None
+        cnt = eng.counters()
+        if cnt["faults"]:
+            raise _lib.IslaError(_lib.ERR_CAPACITY, f"device search reported faults: {cnt}")
+        return self._finish(eng, env_id)
+
+    def _finish(self, eng, env_id):
+        rank, act = eng.best()
+        if int(self.param.n_trees) > 1:
+            return self._finish_ensemble(eng)
+        rank0, act0 = int(rank[0].item()), float(act[0].item())
+        self._fill_q_values(eng)
+        return self._format_action(rank0, act0)
+
+    def _fill_q_values(self, eng):
+        if eng.layout.kernel == _lib.KERNEL_CTA_PER_TREE:
+            a, na, tot = eng.root_children(0)
+        else:
+            na_t, tot_t = eng.root_stats()
+            rec = eng.raw_records(0)
+            A = eng.n_actions
+            order = sorted((int((rec[A + k]["flags"] >> 8) & 0xFF), k) for k in range(A) if rec[A + k]["na"] > 0)
+            a = np.array([k for _, k in order], dtype=np.float64)
+            na = np.array([int(na_t[0, k]) for _, k in order])
+            tot = np.array([float(tot_t[0, k]) for _, k in order])
+        self.root_statistics = dict(action=a, na=na, total=tot)
+        self.q_values = tot / na
+
+    def _finish_ensemble(self, eng):
+        """Root-parallel ensemble (n_trees > 1, discrete agents): root statistics summed over the trees."""
+        from ..engine import merge_root_stats
+        na, tot = eng.root_stats()
+        group = torch.zeros(eng.n_trees, dtype=torch.int32, device=na.device)   # every tree shares the one root
+        mna, mtot = merge_root_stats(na, tot, group, 1)
+        na0, tot0 = mna[0].cpu().numpy(), mtot[0].cpu().numpy()
+        seen = na0 > 0
+        q = np.where(seen, tot0 / np.maximum(na0, 1), -np.inf)
+        self.root_statistics = dict(action=np.flatnonzero(seen).astype(np.float64), na=na0[seen], total=tot0[seen])
+        self.q_values = q[seen]
+        best = np.flatnonzero(q == q.max())
+        return np.int64(np.random.choice(best))
+
+    def _format_action(self, rank, action_value):
+        return np.int64(int(action_value))
+
+    # ------------------------------------------------------------------ proxies
+    def _make_state(self, data):
+        return AbstractStateNode(data, self.param)
+
+    def _build_proxy(self):
+        ser = self._engine.export_tree(0)
+        kind, depth, count, total = ser["kind"], ser["depth"], ser["count"], ser["total"]
+        term, action = ser["terminal"], ser["action"]
+        root = self._make_state(self._root_stub.data)
+        root.ns, root.total = int(count[0]), float(total[0])
+        stack = [(root, 0)]              # (node object, depth) of the open state nodes
+        cur_action = None
+        space = getattr(self.param.env, "action_space", None)
+        dtype = getattr(space, "dtype", np.float32)
+        for i in range(1, len(kind)):
+            if kind[i] == 1:             # action node: child of the open state node at this depth
+                while stack[-1][1] > depth[i]:
+                    stack.pop()
+                parent = stack[-1][0]
+                if self.DISCRETE:
+                    data = int(action[i]); key = data
+                else:
+                    data = np.array([action[i]], dtype=np.float64 if action[i] != np.float32(action[i]) else dtype)
+                    key = data.tobytes()
+                node = AbstractActionNode(data, self.param)
+                node.na, node.total = int(count[i]), float(total[i])
+                parent.actions[key] = node
+                cur_action = node
+            else:                        # state node: the single child of the action node just emitted
+                st = self._make_state(None)
+                st.ns, st.total, st.terminal = int(count[i]), float(total[i]), bool(term[i])
+                cur_action.children[len(cur_action.children)] = st
+                stack.append((st, int(depth[i])))
+        return root
+
+    def visualize(self, extension: str = "0") -> None:
+        raise NotImplementedError("graphviz drawing is out of scope (SURVEY section 2, row 1)")

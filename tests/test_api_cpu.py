@@ -1,0 +1,93 @@
+"""Host-side API mirror: what can be checked without a GPU (construction, proxies, error behaviour).
+Known-answer values come from the reference's own unit tests (/root/reference/tests/agents/)."""
+import numpy as np
+import pytest
+
+from islamcts_b200.agents.abstract_mcts import AbstractActionNode, AbstractStateNode, identify_env
+from islamcts_b200.agents.parameters.dpw_parameters import DpwParameters
+from islamcts_b200.agents.parameters.mcts_parameters import MctsParameters
+from islamcts_b200.agents.parameters.pw_parameters import PwParameters
+from islamcts_b200.utils.action_selection_functions import continuous_default_policy, genetic_policy2, ucb1, voo
+from islamcts_b200.utils.agent_factory import get_agent
+
+
+def _params(**kw):
+    base = dict(root_data=np.zeros(4, np.float32), env=None, n_sim=10, C=1, action_selection_fn=ucb1, gamma=0.9,
+                rollout_selection_fn=continuous_default_policy, max_depth=5, n_actions=2)
+    base.update(kw)
+    return MctsParameters(**base)
+
+
+def test_q_value_known_answers():
+    # /root/reference/tests/agents/test_abstract_mcts.py:28-40: q = total/na = 10/2; na == 0 -> ZeroDivisionError
+    a = AbstractActionNode(data=1, param=None)
+    a.total, a.na = 10, 2
+    assert a.q_value == 5
+    a.na = 0
+    with pytest.raises(ZeroDivisionError):
+        _ = a.q_value
+
+
+def test_parameter_records_accept_both_reference_forms():
+    p = _params()                                                          # README.md:67-77 form (no x/y/depths)
+    assert p.x_values == [] and p.depths == []
+    q = PwParameters(root_data=None, env=None, n_sim=1, C=1, action_selection_fn=ucb1, gamma=0.5,
+                     rollout_selection_fn=continuous_default_policy, max_depth=5, n_actions=10, alpha=0, k=1,
+                     action_expansion_function=continuous_default_policy, x_values=None, y_values=None, depths=None)  # sweep.py:93-110 form
+    assert q.alpha == 0 and q.k == 1
+    d = DpwParameters(root_data=None, env=None, n_sim=1, C=1, action_selection_fn=ucb1, gamma=0.5,
+                      rollout_selection_fn=continuous_default_policy, max_depth=5, n_actions=10, alphaApw=0.5, kApw=1,
+                      alphaSpw=0.1, kSpw=1, x_values=None, y_values=None, depths=None, state_variable="state")
+    assert (d.alphaApw, d.kApw, d.alphaSpw, d.kSpw) == (0.5, 1, 0.1, 1)
+    with pytest.raises(TypeError):
+        MctsParameters(root_data=None)                                     # the core fields stay required
+
+
+def test_agent_factory_dispatch_and_errors():
+    # /root/reference/islaMcts/utils/agent_factory.py:16-46
+    assert type(get_agent("vanilla", _params(root_data=0))).__name__ == "Mcts"
+    assert type(get_agent("vanilla", _params())).__name__ == "MctsHash"
+    with pytest.raises(NotImplementedError):
+        get_agent("apw", _params(root_data=0))                              # hashable obs -> NotImplementedError
+    with pytest.raises(NotImplementedError):
+        get_agent("no_such_agent", _params())
+
+
+def test_unknown_callables_and_envs_fail_loudly():
+    from islamcts_b200.agents.mcts_hash import MctsHash
+
+    class FakeCartPole:
+        spec_id = "CartPole-v1"
+        state = np.zeros(4)
+        unwrapped = property(lambda self: self)
+
+    ag = MctsHash(_params(env=FakeCartPole(), rollout_selection_fn=lambda node: 0))
+    with pytest.raises(NotImplementedError):
+        ag.fit()                                                            # a Python callable cannot run on the device
+    with pytest.raises(NotImplementedError):
+        identify_env(type("Acrobot", (), {})())
+    with pytest.raises(NotImplementedError):
+        genetic_policy2(0.7, continuous_default_policy)                     # SURVEY 8f "next" row
+    v = voo(0.7, continuous_default_policy, 5)
+    assert (v.isla_kind, v.epsilon, v.n_samples, v.max_try) == ("voo", 0.7, 5, 1000)
+
+
+def test_depth_statistics_of_proxies():
+    # agents/abstract_mcts.py:120-142,190-209: root -> a0 -> s1 -> a1 -> s2 ; root -> a2 -> s3
+    root, s1, s2, s3 = (AbstractStateNode(None, None) for _ in range(4))
+    a0, a1, a2 = (AbstractActionNode(i, None) for i in range(3))
+    root.actions = {0: a0, 1: a2}; a0.children = {0: s1}; s1.actions = {0: a1}; a1.children = {0: s2}; a2.children = {0: s3}
+    assert root.get_depth_max(0) == 3
+    assert sorted(root.get_depth_mean(0)) == [2, 3]
+    assert a0.get_depth_max(0) == 2 and a0.get_depth_mean(0, True) == 2.0
+
+
+def test_compat_package_paths():
+    from oracle import ref_loader
+    ref_loader.unload()
+    from islaMcts.agents.mcts_hash import MctsHash
+    from islaMcts.agents.mcts_action_progressive_widening_hash import MctsActionProgressiveWideningHash  # noqa: F401
+    from islaMcts.agents.parameters.mcts_parameters import MctsParameters as P2
+    from islaMcts.utils.action_selection_functions import ucb1 as u2
+    import islamcts_b200.agents.mcts_hash as real
+    assert MctsHash is real.MctsHash and P2 is MctsParameters and u2 is ucb1

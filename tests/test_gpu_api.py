@@ -1,0 +1,139 @@
+"""The drop-in Python API end to end on the device: README example, return types, proxies, statistics."""
+import numpy as np
+import pytest
+
+from oracle import coracle
+
+pytestmark = pytest.mark.gpu
+
+
+def test_readme_example_frozenlake_reaches_goal():
+    """README.md:99-121 of the reference, verbatim flow, with the device-backed env instead of gym."""
+    from islamcts_b200 import envs
+    from islamcts_b200.agents.mcts import Mcts
+    from islamcts_b200.agents.parameters.mcts_parameters import MctsParameters
+    from islamcts_b200.utils.action_selection_functions import continuous_default_policy, ucb1
+    np.random.seed(0)
+    real_env = envs.make("FrozenLake-v1").unwrapped
+    observation, _ = real_env.reset()
+    parameters = MctsParameters(C=0.5, n_sim=100, root_data=observation, env=real_env, action_selection_fn=ucb1,
+                                max_depth=1000, gamma=1, rollout_selection_fn=continuous_default_policy,
+                                n_actions=real_env.action_space.n)
+    done, steps, reward = False, 0, 0.0
+    while not done and steps < 30:
+        parameters.env = real_env
+        agent = Mcts(param=parameters)
+        action = agent.fit()
+        assert isinstance(action, np.int64) and 0 <= action < 4
+        observation, reward, done, _, _ = real_env.step(action)
+        parameters.root_data = observation
+        steps += 1
+    assert done and reward == 1.0 and observation == 15      # the agent reaches the goal
+
+
+def test_mctshash_cartpole_contract():
+    from islamcts_b200 import envs
+    from islamcts_b200.agents.mcts_hash import MctsHash
+    from islamcts_b200.agents.parameters.mcts_parameters import MctsParameters
+    from islamcts_b200.utils.action_selection_functions import continuous_default_policy, ucb1
+    env = envs.make("CartPole-v1", api=4, seed=3)
+    obs = env.reset()
+    p = MctsParameters(root_data=obs, env=env, n_sim=300, C=1, action_selection_fn=ucb1, gamma=0.99,
+                       rollout_selection_fn=continuous_default_policy, max_depth=500, n_actions=2, seed=11)
+    agent = MctsHash(p)
+    agent.root.data = obs                                   # sweep.py:189 assigns this before fit()
+    a = agent.fit()
+    assert isinstance(a, np.int64) and a in (0, 1)
+    assert agent.q_values.shape == (2,) and agent.q_values[int(np.argmax(agent.q_values))] == agent.q_values.max()
+    root = agent.root
+    assert root.ns == 300 and set(root.actions) == {0, 1}
+    assert sum(c.na for c in root.actions.values()) == 300
+    assert root.total == pytest.approx(sum(c.total for c in root.actions.values()), rel=1e-12)
+    node = root.actions[int(a)]
+    assert node.q_value == pytest.approx(agent.q_values.max())
+    assert node.get_depth_max(0) >= 2 and node.get_depth_mean(0, True) >= 1
+    # invariants of SURVEY 8(a) on the whole proxy tree: non-root non-terminal ns = 1 + sum na ; na = sum child ns
+    stack = [(root, True)]
+    while stack:
+        s, is_root = stack.pop()
+        if not s.terminal and s.actions:
+            assert s.ns == (0 if is_root else 1) + sum(c.na for c in s.actions.values())
+        for c in s.actions.values():
+            assert c.na == sum(ch.ns for ch in c.children.values())
+            stack.extend((ch, False) for ch in c.children.values())
+    agent.fit()                                             # calling fit() twice continues the same tree
+    assert agent.root.ns == 600
+    # the oracle with the same Philox key builds the same root statistics (f32 env: identical here)
+    t = coracle.Tree(coracle.make_config(0, n_actions=2, max_depth=500, C_=1.0, gamma=0.99, seed=11), env.state)
+    t.run(600)
+    ea, ena, etot = t.root_children()
+    np.testing.assert_array_equal(agent.root_statistics["na"], ena)
+
+
+def test_pw_agents_return_types_and_keys():
+    from islamcts_b200 import envs
+    from islamcts_b200.agents import MctsApw, MctsDpw, MctsSpw
+    from islamcts_b200.agents.parameters.dpw_parameters import DpwParameters
+    from islamcts_b200.agents.parameters.pw_parameters import PwParameters
+    from islamcts_b200.utils.action_selection_functions import continuous_default_policy, ucb1, voo
+    common = dict(n_sim=400, C=1, action_selection_fn=ucb1, gamma=0.95, rollout_selection_fn=continuous_default_policy,
+                  max_depth=40, seed=5)
+    env = envs.make("Pendulum-v1", api=4, seed=1)
+    obs = env.reset()
+    for ae in (continuous_default_policy, voo(0.7, continuous_default_policy, 5)):
+        ag = MctsApw(PwParameters(root_data=obs, env=env, n_actions=None, alpha=0.5, k=1, action_expansion_function=ae, **common))
+        a = ag.fit()
+        assert isinstance(a, np.ndarray) and a.shape == (1,) and -2 <= a[0] <= 2
+        assert a.tobytes() in ag.root.actions or ae is not continuous_default_policy   # sweep.py:196 lookup
+        assert len(ag.root.actions) == len(ag.q_values) and ag.root.ns == 400
+    env = envs.make("MountainCarContinuous-v0", api=4, seed=2)
+    obs = env.reset()
+    ag = MctsDpw(DpwParameters(root_data=obs, env=env, n_actions=None, alphaApw=0.5, kApw=1, alphaSpw=0.5, kSpw=1,
+                               state_variable="state", **common))
+    a = ag.fit()
+    assert a.dtype == np.float32 and a.tobytes() in ag.root.actions
+    keys = list(ag.root.actions)
+    assert keys == sorted(keys)                            # dpw re-orders root.actions by key bytes (:30)
+    env = envs.make("CartPole-v1", api=4, seed=3)
+    obs = env.reset()
+    ag = MctsSpw(PwParameters(root_data=obs, env=env, n_actions=2, alpha=0.3, k=0.4, action_expansion_function=None,
+                              state_variable="state", **common))
+    idx = ag.fit()
+    assert isinstance(idx, int) and idx in (0, 1)
+
+
+def test_root_q_statistics_agree_with_oracle_within_ci():
+    """north_star: root Q estimates (an RNG-independent statistic) agree within a stated confidence interval.
+    256 device trees (fp32 env, Philox key A) vs 256 oracle trees (float64 env, key B): per-action mean root Q
+    within 3.5 standard errors (99.95% two-sided) and mean visit share within 3.5 s.e."""
+    from islamcts_b200.engine import Engine
+    n_trees, n_sim = 256, 200
+    root = coracle.env_reset(0, 123, 0)
+    roots = np.tile(root[None, :], (n_trees, 1))
+    eng = Engine(0, n_trees=n_trees, sim_capacity=n_sim, max_depth=500, C_=1.0, gamma=0.99, precision=0, seed=1001)
+    eng.set_roots(roots).run(n_sim)
+    na, tot = eng.root_stats()
+    na, tot = na.cpu().numpy(), tot.cpu().numpy()
+    cfg = coracle.make_config(0, n_actions=2, max_depth=500, C_=1.0, gamma=0.99, seed=2002)
+    ena, etot, _ = coracle.run_many(cfg, roots, n_sim, n_threads=8)
+    for a in range(2):
+        qg, qc = tot[:, a] / na[:, a], etot[:, a] / ena[:, a]
+        se = np.sqrt(qg.var(ddof=1) / n_trees + qc.var(ddof=1) / n_trees)
+        assert abs(qg.mean() - qc.mean()) < 3.5 * se, (a, qg.mean(), qc.mean(), se)
+        sg, sc = na[:, a] / n_sim, ena[:, a] / n_sim
+        se = np.sqrt(sg.var(ddof=1) / n_trees + sc.var(ddof=1) / n_trees)
+        assert abs(sg.mean() - sc.mean()) < 3.5 * se + 1e-9
+
+
+def test_ensemble_fit_merges_root_statistics():
+    from islamcts_b200 import envs
+    from islamcts_b200.agents.mcts_hash import MctsHash
+    from islamcts_b200.agents.parameters.mcts_parameters import MctsParameters
+    from islamcts_b200.utils.action_selection_functions import continuous_default_policy, ucb1
+    env = envs.make("CartPole-v1", api=4, seed=8)
+    obs = env.reset()
+    p = MctsParameters(root_data=obs, env=env, n_sim=100, C=1, action_selection_fn=ucb1, gamma=0.99,
+                       rollout_selection_fn=continuous_default_policy, max_depth=200, n_actions=2, seed=4, n_trees=2048)
+    ag = MctsHash(p)
+    a = ag.fit()
+    assert a in (0, 1) and ag.root_statistics["na"].sum() == 2048 * 100
