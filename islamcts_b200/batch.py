@@ -16,7 +16,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, sharding
 from . import engine as E
 
 
@@ -35,14 +35,12 @@ class RootParallelSearch:
         self.S = E.STATE_DIM[self.env_id]
         # root groups: every rank holds trees_per_rank/n_roots trees of each of the n_roots roots
         self.n_roots = int(n_roots) if n_roots else self.trees
-        if self.trees % self.n_roots:
-            raise ValueError("trees_per_rank must be a multiple of n_roots")
+        self.plan = sharding.plan(self.rank, self.world, self.trees, self.n_roots)
         self.engine = E.Engine(self.env_id, agent=_lib.AGENT_VANILLA, n_trees=self.trees, sim_capacity=self.n_sim,
                                max_depth=max_depth, C_=C, gamma=gamma, budget_mode=budget_mode, precision=precision,
-                               kernel=_lib.KERNEL_THREAD_PER_TREE, seed=seed, tree_id_base=self.rank * self.trees,
+                               kernel=_lib.KERNEL_THREAD_PER_TREE, seed=seed, tree_id_base=self.plan.tree_id_base,
                                device=self.device)
-        per = self.trees // self.n_roots
-        self.group = (torch.arange(self.trees, device=self.device, dtype=torch.int32) // per).contiguous()
+        self.group = torch.as_tensor(self.plan.group, device=self.device).contiguous()
         self._roots_dev = torch.empty((self.trees, self.S), dtype=torch.float64, device=self.device)
         self._out_host = None
 
@@ -58,16 +56,10 @@ class RootParallelSearch:
         na, tot = eng.root_stats()
         mna, mtot = E.merge_root_stats(na, tot, self.group, self.n_roots)
         if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(mna, op=dist.ReduceOp.SUM, group=self.pg)
-            dist.all_reduce(mtot, op=dist.ReduceOp.SUM, group=self.pg)
+            sharding.all_reduce_root_stats(mna, mtot, self.pg)
         return mna, mtot
 
-    @staticmethod
-    def pick(mna: torch.Tensor, mtot: torch.Tensor) -> torch.Tensor:
-        """q = total/na per root, arg-max (first maximum; exact ties between merged float sums do not occur)."""
-        q = torch.where(mna > 0, mtot / mna.clamp(min=1).to(torch.float64), torch.full_like(mtot, -float("inf")))
-        return q.argmax(dim=1).to(torch.int32)
+    pick = staticmethod(sharding.pick)
 
     def fit(self, roots_host: torch.Tensor):
         """End-to-end call with HOST buffers: roots [n_roots, S] float64 (pinned) -> dict of host tensors."""

@@ -1,0 +1,106 @@
+#!/usr/bin/env python
+"""CLI mirror of the reference's sweep.py: same flag names, types and defaults (sweep.py:22-47 of the reference;
+--n_angles/--n_accelerations of sweep_vanilla.py:45-48 are accepted and ignored until DiscreteCurveEnv is on the
+device).  --environment is effective here (the reference parses and ignores it, sweep.py:173).  wandb / plotting
+are out of scope; results are printed as JSON lines."""
+from __future__ import annotations
+
+import argparse
+import json
+import time
+
+import numpy as np
+
+
+def argument_parser():
+    p = argparse.ArgumentParser(formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    p.add_argument('--environment', default="CartPole-v1", type=str, help='The environment to run')
+    p.add_argument('--algorithm', default="vanilla", type=str, help='The algorithm to run')
+    p.add_argument('--nsim', default=1000, type=int, help='The number of simulation the algorithm will run')
+    p.add_argument('--c', default=1, type=float, help='exploration-exploitation factor')
+    p.add_argument('--as', default="ucb", type=str, help='the function to select actions during simulations')
+    p.add_argument('--ae', default="random", type=str, help='the function to select actions to add to the tree')
+    p.add_argument('--gamma', default=0.5, type=float, help='discount factor')
+    p.add_argument('--rollout', default='random', type=str, help='the function to select actions during rollout')
+    p.add_argument('--max_depth', default=500, type=int, help='max number of steps during rollout')
+    p.add_argument('--n_actions', default=10, type=int, help='number of actions for vanilla mcts')
+    p.add_argument('--alpha1', default=0, type=float, help='alpha')
+    p.add_argument('--alpha2', default=0.1, type=float, help='alpha2')
+    p.add_argument('--k1', default=1, type=int, help='k1')
+    p.add_argument('--k2', default=1, type=int, help='k2')
+    p.add_argument('--epsilon', default=0.7, type=float, help='epsilon value for epsilon greedy strategies')
+    p.add_argument('--genetic_default', default="random", type=str, help='the default policy for the genetic algorithm')
+    p.add_argument('--n_sample', default=5, type=int, help='the number of samples taken by the genetic algorithm or by voo')
+    p.add_argument('--n_episodes', default=100, type=int, help='the number of episodes for each experiment')
+    p.add_argument('--group', default="", type=str, help='the group of the run')
+    p.add_argument('--n_angles', default=5, type=int)
+    p.add_argument('--n_accelerations', default=19, type=int)
+    # build-only flags
+    p.add_argument('--n_trees', default=1, type=int, help='root-parallel ensemble size')
+    p.add_argument('--rollouts_per_leaf', default=1, type=int)
+    p.add_argument('--seed', default=None, type=int)
+    p.add_argument('--depth_mode', default="budgeted", choices=["budgeted", "reference_head"])
+    p.add_argument('--precision', default="f32", choices=["f32", "f64"])
+    p.add_argument('--max_steps', default=100, type=int, help='real steps per episode (the reference stops at 100, sweep.py:206)')
+    return p
+
+
+def get_function(name, args):
+    from islamcts_b200.utils.action_selection_functions import continuous_default_policy, ucb1, voo
+    if name == "ucb":
+        return ucb1
+    if name == "random":
+        return continuous_default_policy
+    if name == "voo":
+        return voo(epsilon=args["epsilon"], default_policy=get_function(args["genetic_default"], args), n_samples=args["n_sample"])
+    raise NotImplementedError(f"--{name}: not on the device yet (genetic / genetic2 are SURVEY 8f rows)")
+
+
+def create_agent(args, env, observation):
+    from islamcts_b200.agents import Mcts, MctsApw, MctsDpw, MctsHash, MctsSpw
+    from islamcts_b200.agents.parameters.dpw_parameters import DpwParameters
+    from islamcts_b200.agents.parameters.mcts_parameters import MctsParameters
+    from islamcts_b200.agents.parameters.pw_parameters import PwParameters
+    n_act = getattr(env.action_space, "n", None)
+    common = dict(root_data=observation, env=env, n_sim=args["nsim"], C=args["c"], action_selection_fn=get_function(args["as"], args),
+                  gamma=args["gamma"], rollout_selection_fn=get_function(args["rollout"], args), max_depth=args["max_depth"],
+                  n_actions=n_act, x_values=None, y_values=None, depths=None, n_trees=args["n_trees"],
+                  rollouts_per_leaf=args["rollouts_per_leaf"], seed=args["seed"], depth_mode=args["depth_mode"],
+                  precision=args["precision"])
+    algo = args["algorithm"]
+    if algo == "vanilla":
+        cls = Mcts if isinstance(observation, (int, np.integer)) else MctsHash
+        return cls(MctsParameters(**common))
+    if algo == "apw":
+        return MctsApw(PwParameters(**common, alpha=args["alpha1"], k=args["k1"], action_expansion_function=get_function(args["ae"], args)))
+    if algo == "spw":
+        return MctsSpw(PwParameters(**common, alpha=args["alpha1"], k=args["k1"], action_expansion_function=None))
+    if algo == "dpw":
+        return MctsDpw(DpwParameters(**common, alphaApw=args["alpha1"], kApw=args["k1"], alphaSpw=args["alpha2"], kSpw=args["k2"]))
+    raise NotImplementedError(algo)
+
+
+def main(argv=None):
+    args = argument_parser().parse_args(argv).__dict__
+    from islamcts_b200 import envs
+    rewards = []
+    for ep in range(args["n_episodes"]):
+        env = envs.make(args["environment"], api=4, seed=None if args["seed"] is None else args["seed"] + ep)
+        observation = env.reset()
+        done, total_reward, n_steps, t0 = False, 0.0, 0, time.time()
+        while not done and n_steps < args["max_steps"]:
+            agent = create_agent(args, env.unwrapped, observation)      # a new agent (tree) every real step, sweep.py:186
+            agent.root.data = observation
+            action = agent.fit()
+            observation, reward, done, _ = env.step(action)
+            total_reward += reward
+            n_steps += 1
+        rewards.append(total_reward)
+        print(json.dumps({"episode": ep, "total_reward": total_reward, "n_steps": n_steps, "seconds": time.time() - t0,
+                          "n_actions": len(agent.q_values)}), flush=True)
+    print(json.dumps({"mean_reward": float(np.mean(rewards)), "max_reward": float(np.max(rewards)),
+                      "min_reward": float(np.min(rewards))}), flush=True)
+
+
+if __name__ == '__main__':
+    main()
