@@ -83,11 +83,12 @@ typedef struct {
     int32_t state_dim;
     int32_t real_bytes;         /* 4 or 8 */
     int32_t n_actions;
-    int64_t slots_per_tree;     /* thread-per-tree: record slots per tree */
-    int64_t rec_offset, rec_stride;         /* thread-per-tree: 32-byte edge records */
+    int64_t slots_per_tree;     /* thread-per-tree: edge slots per tree = blocks * A; slot = block * A + action */
+    int64_t rec_offset, rec_stride;         /* thread-per-tree: node blocks {double total[A]; int32 na[A]; uint32 link[A]} */
     int64_t state_offset, state_stride;     /* env states, state_dim reals per slot */
-    int64_t meta_offset;                    /* per-tree int32[8]: alloc, sims, rng words consumed, fault, ... */
-    int64_t path_offset;
+    int64_t gfirst_offset, gfirst_stride;   /* double per slot: return backed up when the child state was created */
+    int64_t meta_offset;                    /* per-tree int32[8]: alloc, sims, rng words consumed, fault, trace pos, pending */
+    int64_t path_offset, pathg_offset;      /* level-major scratch: uint32 (block<<2|action) and double G per level */
     int64_t counters_offset;                /* int64[8] device counters */
     int64_t ln_offset, ln_count;            /* double ln(n), n < ln_count  (host libm log, like numpy)  */
     int64_t disc_offset, disc_count;        /* double gamma**t, t < disc_count (host libm pow, like CPython) */

@@ -223,12 +223,10 @@ class AbstractMcts:
             a, na, tot = eng.root_children(0)
         else:
             na_t, tot_t = eng.root_stats()
-            rec = eng.raw_records(0)
-            A = eng.n_actions
-            order = sorted((int((rec[A + k]["flags"] >> 8) & 0xFF), k) for k in range(A) if rec[A + k]["na"] > 0)
-            a = np.array([k for _, k in order], dtype=np.float64)
-            na = np.array([int(na_t[0, k]) for _, k in order])
-            tot = np.array([float(tot_t[0, k]) for _, k in order])
+            order = eng.root_order(0)
+            a = np.array(order, dtype=np.float64)
+            na = np.array([int(na_t[0, k]) for k in order])
+            tot = np.array([float(tot_t[0, k]) for k in order])
         self.root_statistics = dict(action=a, na=na, total=tot)
         self.q_values = tot / na
 

@@ -18,31 +18,34 @@ int cuda_fail(cudaError_t e, const char* what);
     } while (0)
 
 // ---------------------------------------------------------------- thread-per-tree (vanilla) layout
-// One 32-byte EDGE record per (parent state, action): the reference's ActionNode
-// (agents/abstract_mcts.py:145-156) fused with its single StateNode child (deterministic envs:
-// exactly one child per action node).  The A records of one parent form one
-// aligned block, so a parent's UCB scan is ONE 32*A-byte contiguous load.
-struct __align__(16) EdgeRec {
-    double total_in;   // ActionNode.total
-    double g_first;    // return backed up when the child StateNode was created (StateNode.total = g_first + sum of its edges' totals)
-    int32_t na_in;     // ActionNode.na
-    float r_in;        // reward of stepping this edge (deterministic env)
-    int32_t block;     // block index of the child state's own edges (0 = none yet)
-    uint32_t flags;    // bit0 terminal child; bits 8..15 insertion rank among siblings
-};
-static_assert(sizeof(EdgeRec) == 32, "edge record is one 32-byte sector");
-constexpr uint32_t kFlagTerminal = 1u;
+// One NODE BLOCK per expanded state node: the statistics of its A outgoing edges, i.e. the reference's
+// A ActionNodes (agents/abstract_mcts.py:145-156), each fused with its single StateNode child
+// (deterministic envs: exactly one child per action node).  16 bytes per edge:
+//   double total[A]   ActionNode.total
+//   int32  na[A]      ActionNode.na
+//   uint32 link[A]    bits 0..27 block index of the child state's own block (0 = none yet),
+//                     bit 28 child is terminal, bit 29 the terminal step's reward is 1, bits 30..31 insertion rank
+// A = 2 -> one 32-byte sector per UCB scan, A = 4 -> 64 bytes.  Cold per-edge data (the env state of the
+// child and g_first, the return backed up at its creation) live in separate arrays indexed by
+// slot = block * A + action.  Rewards are not stored: the envs of this kernel have a constant reward on
+// non-terminal steps (CartPole 1, FrozenLake 0) and a 0/1 reward on the terminal step.
+constexpr uint32_t kLinkBlockMask = 0x0fffffffu;
+constexpr uint32_t kLinkTerminal = 1u << 28;
+constexpr uint32_t kLinkRewardOne = 1u << 29;
+constexpr int kLinkRankShift = 30;
 
 // per-tree meta words
-enum : int { META_ALLOC = 0, META_SIMS = 1, META_RNG = 2, META_FAULT = 3, META_WORDS = 8 };
+enum : int { META_ALLOC = 0, META_SIMS = 1, META_RNG = 2, META_FAULT = 3, META_TRACE_POS = 4, META_PENDING = 5, META_WORDS = 8 };
 // device counters
 enum : int { CNT_ENV_STEPS = 0, CNT_ROLLOUT_STEPS = 1, CNT_LEVELS = 2, CNT_SIMS = 3, CNT_NODES = 4, CNT_FAULTS = 5 };
 
 struct TptParams {
-    EdgeRec* recs;
+    char* blocks;          // node blocks, A * 16 bytes each
     void* states;
+    double* gfirst;
     int32_t* meta;
-    int2* path;
+    uint32_t* path_b;      // [level][tree]  block << 2 | action of the edge descended through
+    double* path_g;        // [level][tree]  return G backed up through that edge (pending until the next descent)
     unsigned long long* counters;
     const uint8_t* trace_kinds;
     const double* trace_values;

@@ -23,7 +23,12 @@ STATE_DIM = {_lib.ENV_CARTPOLE: 4, _lib.ENV_PENDULUM: 2, _lib.ENV_MOUNTAINCAR: 2
 N_ACTIONS = {_lib.ENV_CARTPOLE: 2, _lib.ENV_PENDULUM: 0, _lib.ENV_MOUNTAINCAR: 0, _lib.ENV_FROZENLAKE: 4}
 ACTION_BOUNDS = {_lib.ENV_PENDULUM: (-2.0, 2.0), _lib.ENV_MOUNTAINCAR: (-1.0, 1.0)}
 
-_REC_DTYPE = np.dtype([("total", "<f8"), ("g_first", "<f8"), ("na", "<i4"), ("r", "<f4"), ("block", "<i4"), ("flags", "<u4")])
+LINK_BLOCK_MASK, LINK_TERMINAL, LINK_REWARD_ONE, LINK_RANK_SHIFT = 0x0FFFFFFF, 1 << 28, 1 << 29, 30
+
+
+def _block_dtype(A):
+    # node block of the thread-per-tree engine (isla_internal.h): {double total[A]; int32 na[A]; uint32 link[A]}
+    return np.dtype([("total", "<f8", (A,)), ("na", "<i4", (A,)), ("link", "<u4", (A,))])
 
 
 def _require_cuda(device) -> torch.device:
@@ -171,9 +176,19 @@ class Engine:
         check(self.lib.isla_engine_pool_offsets(self._h, out))
         return [int(x) for x in out]
 
-    def raw_records(self, tree: int = 0) -> np.ndarray:
+    def raw_blocks(self, tree: int = 0) -> np.ndarray:
         L = self.layout
-        return self._ws_bytes(L.rec_offset + tree * L.rec_stride, L.rec_stride).view(_REC_DTYPE)
+        return self._ws_bytes(L.rec_offset + tree * L.rec_stride, L.rec_stride).view(_block_dtype(self.n_actions))
+
+    def raw_gfirst(self, tree: int = 0) -> np.ndarray:
+        L = self.layout
+        return self._ws_bytes(L.gfirst_offset + tree * L.gfirst_stride, L.gfirst_stride).view(np.float64)
+
+    def root_order(self, tree: int = 0):
+        """Visited root actions of a thread-per-tree tree in insertion order (root.actions order)."""
+        b = self.raw_blocks(tree)[1]
+        order = sorted((int(b["link"][k] >> LINK_RANK_SHIFT), k) for k in range(self.n_actions) if b["na"][k] > 0)
+        return [k for _, k in order]
 
     def raw_states(self, tree: int = 0) -> np.ndarray:
         L = self.layout
@@ -183,56 +198,49 @@ class Engine:
     def export_tree(self, tree: int = 0) -> dict:
         """Canonical DFS serialisation (same format as oracle/trace.py) decoded on the host."""
         if self.layout.kernel == _lib.KERNEL_THREAD_PER_TREE:
-            return _export_tpt(self.raw_records(tree), self.n_actions)
+            return _export_tpt(self.raw_blocks(tree), self.raw_gfirst(tree), self.n_actions)
         from .tree_export import export_pool  # CTA-per-tree general pools
         return export_pool(self, tree)
 
 
-def _export_tpt(rec: np.ndarray, A: int) -> dict:
+def _export_tpt(blocks: np.ndarray, gfirst: np.ndarray, A: int) -> dict:
     kinds, depths, counts, totals, terms, fans, acts = [], [], [], [], [], [], []
 
     def children(block):
-        """visited edges of a block in insertion (rank) order -> list of (action, slot)"""
+        """visited edges of a block in insertion (rank) order -> list of (action, na, total, link)"""
         if block == 0:
             return []
-        out = []
-        for a in range(A):
-            r = rec[block * A + a]
-            if r["na"] > 0:
-                out.append((int((r["flags"] >> 8) & 0xFF), a, block * A + a))
+        b = blocks[block]
+        out = [(int(b["link"][a] >> LINK_RANK_SHIFT), a) for a in range(A) if b["na"][a] > 0]
         out.sort()
-        return [(a, s) for _, a, s in out]
+        return [(a, int(b["na"][a]), float(b["total"][a]), int(b["link"][a]), block * A + a) for _, a in out]
 
-    # stack entries: ("S", slot or -1 for root, depth) / ("A", action, slot, depth)
-    stack = [("S", -1, 0)]
+    # stack entries: ("S", edge tuple or None for the root, depth) / ("A", edge tuple, depth)
+    stack = [("S", None, 0)]
     while stack:
-        item = stack.pop()
-        if item[0] == "S":
-            _, slot, d = item
-            if slot < 0:
+        kind, edge, d = stack.pop()
+        if kind == "S":
+            if edge is None:
                 ch = children(1)
-                ns = sum(int(rec[s]["na"]) for _, s in ch)
-                tot = float(sum(float(rec[s]["total"]) for _, s in ch))
-                term = 0
+                ns, tot, term = sum(c[1] for c in ch), float(sum(c[2] for c in ch)), 0
             else:
-                r = rec[slot]
-                term = int(r["flags"] & 1)
+                _, na, _, link, slot = edge
+                term = 1 if link & LINK_TERMINAL else 0
                 if term:
-                    ch, ns, tot = [], int(r["na"]), 0.0
+                    ch, ns, tot = [], na, 0.0
                 else:
-                    ch = children(int(r["block"]))
-                    ns = 1 + sum(int(rec[s]["na"]) for _, s in ch)
-                    tot = float(r["g_first"]) + float(sum(float(rec[s]["total"]) for _, s in ch))
+                    ch = children(link & LINK_BLOCK_MASK)
+                    ns = 1 + sum(c[1] for c in ch)
+                    tot = float(gfirst[slot]) + float(sum(c[2] for c in ch))
             kinds.append(0); depths.append(d); counts.append(ns); totals.append(tot); terms.append(term)
             fans.append(len(ch)); acts.append(0.0)
-            for a, s in reversed(ch):
-                stack.append(("A", a, s, d))
+            for c in reversed(ch):
+                stack.append(("A", c, d))
         else:
-            _, a, slot, d = item
-            r = rec[slot]
-            kinds.append(1); depths.append(d); counts.append(int(r["na"])); totals.append(float(r["total"]))
+            a, na, total, link, slot = edge
+            kinds.append(1); depths.append(d); counts.append(na); totals.append(total)
             terms.append(0); fans.append(1); acts.append(float(a))
-            stack.append(("S", slot, d + 1))
+            stack.append(("S", edge, d + 1))
     return dict(kind=np.asarray(kinds, np.uint8), depth=np.asarray(depths, np.int32), count=np.asarray(counts, np.int64),
                 total=np.asarray(totals, np.float64), terminal=np.asarray(terms, np.uint8),
                 fanout=np.asarray(fans, np.int32), action=np.asarray(acts, np.float64))

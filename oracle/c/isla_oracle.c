@@ -197,6 +197,8 @@ struct orc_tree {
     stream_t tree_stream, roll_stream;
     uint32_t sim_index; /* cumulative over run() calls */
     int64_t c_env_steps, c_roll_steps, c_levels, c_sims, c_expand_steps, c_seq; int next_blk, cur_parent_blk;
+    /* instrumentation only: common prefix of consecutive simulation paths */
+    int prev_path[4096], cur_path[4096], prev_len, cur_len; int64_t c_common, c_prevlen;
 };
 
 static int new_snode(orc_tree* t, const float* obs) {
@@ -524,6 +526,7 @@ static double state_visit(orc_tree* t, int sidx, int level) {
     if (t->S[sidx].blk == 0) t->S[sidx].blk = ++t->next_blk;
     if (level > 0 && t->S[sidx].blk == t->cur_parent_blk + 1) t->c_seq++;
     t->cur_parent_blk = t->S[sidx].blk;
+    if (t->cur_len < 4096) t->cur_path[t->cur_len++] = sidx;
     if (c->agent == ORC_AGENT_VANILLA || c->agent == ORC_AGENT_SPW) {
         /* mcts.py:55-62 */
         int cand[ORC_MAX_DISCRETE], nc = 0;
@@ -591,7 +594,11 @@ int orc_tree_run(orc_tree* t, int n_sim, const uint8_t* kinds, const double* val
         /* fit(): param.env = my_deepcopy(initial_env, ...) -- mcts_hash.py:31 ; spw/dpw poke root_data */
         memcpy(t->env, t->root_state, sizeof t->env);
         if (t->cfg.agent == ORC_AGENT_SPW || t->cfg.agent == ORC_AGENT_DPW) env_set_from_obs(t, t->S[0].obs);
+        t->cur_len = 0;
         state_visit(t, 0, 0);
+        { int k = 0; while (k < t->cur_len && k < t->prev_len && t->cur_path[k] == t->prev_path[k]) ++k;
+          t->c_common += k; t->c_prevlen += t->prev_len;
+          memcpy(t->prev_path, t->cur_path, sizeof(int) * t->cur_len); t->prev_len = t->cur_len; }
         t->sim_index++; t->c_sims++;
     }
     return t->fault;
@@ -675,6 +682,7 @@ int64_t orc_tree_serialise(const orc_tree* t, int64_t cap, uint8_t* kind, int32_
 void orc_tree_counters(const orc_tree* t, int64_t out[8]) {
     out[0] = t->c_env_steps; out[1] = t->c_roll_steps; out[2] = t->c_levels; out[3] = t->c_sims;
     out[4] = t->nS; out[5] = t->nA; out[6] = t->c_expand_steps; out[7] = t->c_seq;
+    if (getenv("ORC_PATH_STATS")) { out[6] = t->c_common; out[7] = t->c_prevlen; }
 }
 
 int orc_rollout(int env_id, const double* state, int budget, double gamma, uint64_t seed, uint64_t tree,
