@@ -93,6 +93,7 @@ typedef struct {
     int64_t ln_offset, ln_count;            /* double ln(n), n < ln_count  (host libm log, like numpy)  */
     int64_t disc_offset, disc_count;        /* double gamma**t, t < disc_count (host libm pow, like CPython) */
     int64_t pw1_offset, pw2_offset;         /* double[ln_count]: ceil(k1*n**alpha1) and k*n**alpha widening caps (host libm) */
+    int64_t cumdisc_offset;                 /* double[disc_count]: sum_{t<n} gamma**t accumulated like `reward += 1.0 * pow(gamma, t)` */
     /* CTA-per-tree (general) pools, offsets of the per-tree blocks and their strides */
     int64_t s_cap, a_cap;                   /* state / action node capacity per tree */
     int64_t pool_offset, pool_stride;       /* bytes per tree of the general node pool */

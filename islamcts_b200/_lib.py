@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libisla_b200.so")
+LIB_PATH = os.environ.get("ISLA_LIB_PATH") or os.path.join(_HERE, "lib", "libisla_b200.so")  # override: A/B experiments only
 
 ISLA_OK = 0
 ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_TRACE = -1, -2, -3, -4
@@ -47,7 +47,7 @@ class IslaLayout(C.Structure):
         ("slots_per_tree", C.c_int64), ("rec_offset", C.c_int64), ("rec_stride", C.c_int64),
         ("state_offset", C.c_int64), ("state_stride", C.c_int64), ("gfirst_offset", C.c_int64), ("gfirst_stride", C.c_int64),
         ("meta_offset", C.c_int64), ("path_offset", C.c_int64), ("pathg_offset", C.c_int64), ("counters_offset", C.c_int64), ("ln_offset", C.c_int64), ("ln_count", C.c_int64),
-        ("disc_offset", C.c_int64), ("disc_count", C.c_int64), ("pw1_offset", C.c_int64), ("pw2_offset", C.c_int64),
+        ("disc_offset", C.c_int64), ("disc_count", C.c_int64), ("pw1_offset", C.c_int64), ("pw2_offset", C.c_int64), ("cumdisc_offset", C.c_int64),
         ("s_cap", C.c_int64), ("a_cap", C.c_int64),
         ("pool_offset", C.c_int64), ("pool_stride", C.c_int64), ("total_bytes", C.c_int64),
     ]

@@ -36,6 +36,7 @@ void add_table_layout(const isla_config& cfg, isla_layout& lay, int64_t& off) {
     lay.disc_offset = off; off = up(off + lay.disc_count * 8);
     lay.pw1_offset = off; off = up(off + lay.ln_count * 8);
     lay.pw2_offset = off; off = up(off + lay.ln_count * 8);
+    lay.cumdisc_offset = off; off = up(off + lay.disc_count * 8);
 }
 int upload_tables(isla_engine* e) {
     std::vector<double> ln((size_t)e->lay.ln_count), disc((size_t)e->lay.disc_count);
@@ -44,6 +45,11 @@ int upload_tables(isla_engine* e) {
     for (size_t t = 0; t < disc.size(); ++t) disc[t] = std::pow(e->cfg.gamma, (double)t);
     ISLA_CUDA_OK(cudaMemcpy(e->ws + e->lay.ln_offset, ln.data(), ln.size() * 8, cudaMemcpyHostToDevice));
     ISLA_CUDA_OK(cudaMemcpy(e->ws + e->lay.disc_offset, disc.data(), disc.size() * 8, cudaMemcpyHostToDevice));
+    // sum_{t<n} 1.0 * gamma**t accumulated left to right, exactly like `reward += vals[1] * pow(gamma, t)` with
+    // reward 1 on every step (agents/abstract_mcts.py:87): the return of an n-step CartPole rollout
+    std::vector<double> cum(disc.size());
+    { double acc = 0.0; for (size_t n = 0; n < cum.size(); ++n) { cum[n] = acc; acc = acc + 1.0 * disc[n]; } }
+    ISLA_CUDA_OK(cudaMemcpy(e->ws + e->lay.cumdisc_offset, cum.data(), cum.size() * 8, cudaMemcpyHostToDevice));
     // progressive-widening caps, again with the host libm pow (python: k * ns ** alpha):
     //   pw1[n] = ceil(k1 * n**alpha1)  state-node test  (mcts_action_...:62, mcts_double_...:56)
     //   pw2[n] = k * n**alpha          action-node test (mcts_state_...:97 with (k, alpha); mcts_double_...:87 with (kSpw, alphaSpw))

@@ -58,6 +58,7 @@ struct TptParams {
     double C, gamma;
     const double* ln_table;    // host-computed ln(n)
     const double* disc_table;  // host-computed gamma**t
+    const double* cum_table;   // host-computed sum_{t<n} gamma**t (left-to-right)
     int n_sim, max_depth, budget_mode, block_cap, ln_count, disc_count, ln_in_smem, tuning;
 };
 

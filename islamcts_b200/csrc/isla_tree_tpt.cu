@@ -41,13 +41,24 @@ namespace {
 
 constexpr int kTptBlock = 64;
 constexpr int kRing = 8;        // path entries are staged this many levels ahead (cp.async ring)
-constexpr int kBlockAhead = 4;  // node blocks are prefetched into L2 this many levels ahead
+constexpr int kBlockAhead = 4; // node blocks are prefetched into L2 this many levels ahead
 constexpr unsigned kFull = 0xffffffffu;
 
 // Reward structure of the envs this kernel supports (checked at expansion time)
 template <int ENV> struct Rewards;
-template <> struct Rewards<ENV_CARTPOLE> { static constexpr double kInterior = 1.0; };
-template <> struct Rewards<ENV_FROZENLAKE> { static constexpr double kInterior = 0.0; };
+// rollout_return(): the value of `reward += r_t * pow(gamma, t)` (abstract_mcts.py:87) after n steps, in closed
+// form and bit-identical to the left-to-right float64 sum: CartPole pays 1 on every step (host-accumulated
+// prefix table), FrozenLake pays 0 until the last step (0.0 + ... + r * gamma**(n-1) is exact).
+template <> struct Rewards<ENV_CARTPOLE> {
+    static constexpr double kInterior = 1.0;
+    static __device__ __forceinline__ double rollout_return(int n, double, const double*, const double* cum) { return __ldg(cum + n); }
+};
+template <> struct Rewards<ENV_FROZENLAKE> {
+    static constexpr double kInterior = 0.0;
+    static __device__ __forceinline__ double rollout_return(int n, double last_r, const double* disc, const double*) {
+        return n > 0 ? __dmul_rn(last_r, __ldg(disc + (n - 1))) : 0.0;
+    }
+};
 
 struct TraceCursor {
     const uint8_t* k;
@@ -69,13 +80,26 @@ template <int A> struct NodeBlock {
 };
 static_assert(sizeof(NodeBlock<2>) == 32 && sizeof(NodeBlock<4>) == 64, "node block is one or two sectors");
 
-template <int A>
+__device__ __forceinline__ int4 ldcg_line(const int4* p) {
+    // L2-only load that asks L2 to fetch the whole 128-byte line on a miss: the blocks of the principal
+    // variation are allocated consecutively, so the next levels' blocks usually share the line, and one
+    // 128-byte DRAM access replaces up to four row-missing 32-byte ones
+    int4 v;
+    asm volatile("ld.global.cg.L2::128B.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void touch_line(const void* p) {
+    int v;
+    asm volatile("ld.global.cg.L2::128B.s32 %0, [%1];" : "=r"(v) : "l"(p));
+}
+
+template <int A, bool LINE = false>
 __device__ __forceinline__ NodeBlock<A> load_block(const char* base, int blk) {
     // L2-only loads (ld.global.cg): blocks are also updated by RED atomics at L2
     NodeBlock<A> b;
     const int4* p = reinterpret_cast<const int4*>(base + (long long)blk * (A * 16));
     if constexpr (A == 2) {
-        const int4 lo = __ldcg(p), hi = __ldcg(p + 1);
+        const int4 lo = LINE ? ldcg_line(p) : __ldcg(p), hi = __ldcg(p + 1);
         b.total[0] = __hiloint2double(lo.y, lo.x); b.total[1] = __hiloint2double(lo.w, lo.z);
         b.na[0] = hi.x; b.na[1] = hi.y; b.link[0] = (uint32_t)hi.z; b.link[1] = (uint32_t)hi.w;
     } else {
@@ -110,7 +134,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 enum : int { MODE_DESCEND = 0, MODE_EXPAND = 1, MODE_RETURN = 2, MODE_IDLE = 3 };
 
 template <int ENV, typename T, bool SCRIPTED>
-__global__ void __launch_bounds__(kTptBlock) tpt_search_kernel(const TptParams p) {
+__global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParams p) {
     constexpr int A = EnvTraits<ENV>::A;
     constexpr int S = EnvTraits<ENV>::S;
     constexpr double kInterior = Rewards<ENV>::kInterior;
@@ -187,6 +211,10 @@ __global__ void __launch_bounds__(kTptBlock) tpt_search_kernel(const TptParams p
         bool fresh = false;              // block just allocated: all children unvisited, nothing to load
         bool on_old = live && plen > 0;  // still walking the previous simulation's path
         double G = 0.0;
+        NodeBlock<A> cnext;              // block of the NEXT level, loaded ahead along the old path
+        int cnext_blk = -1;
+#pragma unroll
+        for (int a = 0; a < A; ++a) { cnext.total[a] = 0.0; cnext.na[a] = 0; cnext.link[a] = 0u; }
 
         // stage the first kRing entries of the old path
 #pragma unroll
@@ -206,8 +234,10 @@ __global__ void __launch_bounds__(kTptBlock) tpt_search_kernel(const TptParams p
             const bool pend = walking && it < plen;
             const uint32_t pb = pend ? ring_b[slot_r][tid] : 0u;
             const double pg = pend ? ring_g[slot_r][tid] : 0.0;
-            if (walking && it + kBlockAhead < plen)
-                prefetch_l2(blocks + (long long)(ring_b[(it + kBlockAhead) & (kRing - 1)][tid] >> 2) * (A * 16));
+            if (walking && it + kBlockAhead < plen) {
+                const char* pf = blocks + (long long)(ring_b[(it + kBlockAhead) & (kRing - 1)][tid] >> 2) * (A * 16);
+                if (p.tuning & 4) touch_line(pf); else prefetch_l2(pf);
+            }
             // refill the ring slot just consumed with level it + kRing
             if (walking && it + kRing < plen) {
                 cp_async4(&ring_b[slot_r][tid], path_b + (long long)(it + kRing) * p.n_trees);
@@ -221,8 +251,17 @@ __global__ void __launch_bounds__(kTptBlock) tpt_search_kernel(const TptParams p
                 if (fresh) {
 #pragma unroll
                     for (int a = 0; a < A; ++a) { c.total[a] = 0.0; c.na[a] = 0; c.link[a] = 0u; }
+                } else if (blk == cnext_blk) {
+                    c = cnext;                    // already in registers: loaded one level ahead
                 } else {
-                    c = load_block<A>(blocks, blk);
+                    c = (p.tuning & 2) ? load_block<A, true>(blocks, blk) : load_block<A, false>(blocks, blk);
+                }
+                // 99.7 % of the time the descent stays on the old path: start loading the next level's block now,
+                // so that its latency overlaps this level's UCB arithmetic instead of following it
+                cnext_blk = -1;
+                if (walking && it + 1 < plen) {
+                    cnext_blk = (int)(ring_b[(it + 1) & (kRing - 1)][tid] >> 2);
+                    cnext = load_block<A, false>(blocks, cnext_blk);
                 }
                 int pa = -1;
                 if (pend) {
@@ -379,10 +418,10 @@ __global__ void __launch_bounds__(kTptBlock) tpt_search_kernel(const TptParams p
         }
         // rollout (abstract_mcts.py:72-91): one env step per iteration for every lane still playing
         {
-            double R = 0.0;
             Stream rs;
             rs.init(p.seed, sims_done, tree_id, 0u);
             int t = 0;
+            T last_r = T(0);
             bool go = rolling && budget > 0;
             while (__any_sync(kFull, go)) {
                 if (go) {
@@ -394,16 +433,17 @@ __global__ void __launch_bounds__(kTptBlock) tpt_search_kernel(const TptParams p
                     } else {
                         act = sample_action<ENV, T>(rs);
                     }
-                    T rr;
-                    const bool done = Env<ENV, T>::step(st, act, rr);
-                    R = __dadd_rn(R, __dmul_rn((double)rr, __ldg(p.disc_table + t)));  // r * pow(gamma, t)
+                    const bool done = Env<ENV, T>::step(st, act, last_r);
                     ++t;
                     go = !done && t < budget;
                     if constexpr (SCRIPTED) { if (tc.fault) go = false; }
                 }
             }
             c_roll += t; c_env += t;
-            if (rolling) G = __dadd_rn((double)r_exp, __dmul_rn(gamma, R));
+            if (rolling) {
+                const double R = Rewards<ENV>::rollout_return(t, (double)last_r, p.disc_table, p.cum_table);
+                G = __dadd_rn((double)r_exp, __dmul_rn(gamma, R));
+            }
         }
         if (mode == MODE_EXPAND) {
             // the new edge: na = 1, total = G; the child's cold record keeps the creation return
@@ -588,6 +628,7 @@ int tpt_run(isla_engine* e, int n_sim, long long scripted_tree, const uint8_t* k
     p.block_cap = e->cfg.sim_capacity + 2;
     p.ln_table = (const double*)(e->ws + L.ln_offset);
     p.disc_table = (const double*)(e->ws + L.disc_offset);
+    p.cum_table = (const double*)(e->ws + L.cumdisc_offset);
     p.ln_count = (int)L.ln_count; p.disc_count = (int)L.disc_count;
     p.ln_in_smem = (L.ln_count * 8 <= 32 * 1024) ? 1 : 0;
     p.tuning = e->cfg.tuning;
