@@ -279,6 +279,16 @@ def run_isla(args):
         "gpu_launches": 5 * args.steps,
         "clocks": clk,
     }
+    if not args.no_extras and world == 1:
+        line["extras"] = other_configs(dev)
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tr = json.load(f)
+        if tr.get("nsim") == args.nsim and tr.get("trees") == args.trees:
+            line["roofline"]["traffic"] = tr["dram_bytes_per_launch"]
+            line["roofline"]["traffic_source"] = tr["source"]
+    except Exception:
+        pass
     if not args.no_cpu_baseline and world == 1:
         cores_avail = os.cpu_count() or 1
         w, s, st = cpu_baseline_python(args, 1, args.cpu_trees or 3)
@@ -293,6 +303,74 @@ def run_isla(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_configs(dev):
+    """Secondary measurements (NOT the headline): BASELINE configs C1-C4 on the CTA-per-tree engine and the
+    rollout micro-benchmark R of SURVEY 8(d).  CUDA events, 1 warm-up + best of 3."""
+    import torch
+    from islamcts_b200 import _lib
+    from islamcts_b200 import engine as E
+    from islamcts_b200.engine import Engine
+
+    def timeit(fn, reps=3):
+        fn(); torch.cuda.synchronize(dev)
+        best = 1e30
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize(dev)
+            best = min(best, e0.elapsed_time(e1))
+        return best * 1e-3
+
+    out = {}
+    g = torch.Generator().manual_seed(7)
+    # C1: vanilla FrozenLake nsim=100 C=0.5 gamma=1 max_depth=1000: one tree, and 65 536 trees (thread-per-tree)
+    for name, nt, kern in (("c1_frozenlake_1tree", 1, _lib.KERNEL_CTA_PER_TREE), ("c1_frozenlake_65536trees", 65536, _lib.KERNEL_THREAD_PER_TREE)):
+        eng = Engine(_lib.ENV_FROZENLAKE, n_trees=nt, sim_capacity=100, max_depth=1000, C_=0.5, gamma=1.0, kernel=kern, seed=1, device=dev)
+        roots = torch.zeros((nt, 1), dtype=torch.float64, device=dev)
+        t = timeit(lambda: eng.set_roots(roots).run(100))
+        out[name] = {"sims_per_s": nt * 100 / t, "ms": t * 1e3}
+    # C2: one CartPole tree, nsim=1000, 4096 rollouts per leaf
+    eng = Engine(_lib.ENV_CARTPOLE, n_trees=1, sim_capacity=1000, max_depth=500, C_=1.0, gamma=0.99, kernel=_lib.KERNEL_CTA_PER_TREE,
+                 rollouts_per_leaf=4096, seed=1, device=dev)
+    roots = (torch.rand((1, 4), generator=g, dtype=torch.float64) - 0.5) * 0.1
+    t = timeit(lambda: eng.set_roots(roots).run(1000))
+    c = eng.counters()
+    out["c2_cartpole_1tree_4096rollouts"] = {"sims_per_s": 1000 / t, "env_steps_per_s": c["env_steps"] / t, "ms": t * 1e3}
+    # the same shape as a batch of 296 trees (2 CTAs per SM): what the GPU does with C2 when it is not alone
+    eng = Engine(_lib.ENV_CARTPOLE, n_trees=296, sim_capacity=1000, max_depth=500, C_=1.0, gamma=0.99, kernel=_lib.KERNEL_CTA_PER_TREE,
+                 rollouts_per_leaf=4096, seed=1, device=dev)
+    roots = (torch.rand((296, 4), generator=g, dtype=torch.float64) - 0.5) * 0.1
+    t = timeit(lambda: eng.set_roots(roots).run(1000), reps=2)
+    c = eng.counters()
+    out["c2_cartpole_296trees_4096rollouts"] = {"sims_per_s": 296 * 1000 / t, "env_steps_per_s": c["env_steps"] / t, "ms": t * 1e3}
+    # C3: APW Pendulum k=60 alpha=0.8 nsim=10000 max_depth=200 ; C4: DPW MountainCarContinuous alpha=0.5 nsim=10000 max_depth=500
+    eng = Engine(_lib.ENV_PENDULUM, agent=_lib.AGENT_APW, n_trees=1, sim_capacity=10000, max_depth=200, C_=1.0, gamma=0.99, alpha1=0.8,
+                 k1=60.0, kernel=_lib.KERNEL_CTA_PER_TREE, rollouts_per_leaf=1, seed=1, device=dev)
+    roots = torch.tensor([[1.0, 0.3]], dtype=torch.float64)
+    t = timeit(lambda: eng.set_roots(roots).run(10000), reps=2)
+    c = eng.counters()
+    out["c3_apw_pendulum_1tree"] = {"sims_per_s": 10000 / t, "env_steps_per_s": c["env_steps"] / t, "ms": t * 1e3}
+    eng = Engine(_lib.ENV_MOUNTAINCAR, agent=_lib.AGENT_DPW, n_trees=1, sim_capacity=10000, max_depth=500, C_=1.0, gamma=0.99,
+                 alpha1=0.5, k1=1.0, alpha2=0.5, k2=1.0, kernel=_lib.KERNEL_CTA_PER_TREE, seed=1, device=dev)
+    roots = torch.tensor([[-0.5, 0.0]], dtype=torch.float64)
+    t = timeit(lambda: eng.set_roots(roots).run(10000), reps=2)
+    c = eng.counters()
+    out["c4_dpw_mountaincar_1tree"] = {"sims_per_s": 10000 / t, "env_steps_per_s": c["env_steps"] / t, "ms": t * 1e3}
+    # R: rollout micro-benchmark, 2^24 trajectories from the reset distribution, random policy, budget = max_depth
+    flop = {0: 36, 1: 27, 2: 27, 3: 6}
+    peak_fp32 = 148 * 128 * 2 * 1.965e9
+    for env_id, name, budget, gamma in ((0, "cartpole", 500, 0.99), (1, "pendulum", 200, 0.99), (2, "mountaincar", 500, 0.99), (3, "frozenlake", 1000, 1.0)):
+        n = 1 << 24 if env_id in (0, 3) else 1 << 21
+        steps = []
+        def run():
+            ret, st = E.rollout(env_id, None, n=n, budget=budget, gamma=gamma, seed=1234, sim=0, device=dev)
+            steps.append(st)
+        t = timeit(run, reps=2)
+        total = int(steps[-1].sum().item())
+        out["rollout_" + name] = {"trajectories": n, "env_steps_per_s": total / t, "mean_len": total / n, "ms": t * 1e3,
+                                  "fp32_roofline_frac": total / t * flop[env_id] / peak_fp32}
+    return out
 
 
 def main():

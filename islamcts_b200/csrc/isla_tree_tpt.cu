@@ -132,40 +132,51 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 enum : int { MODE_DESCEND = 0, MODE_EXPAND = 1, MODE_RETURN = 2, MODE_IDLE = 3 };
+constexpr int kLook = 6;  // path entries of the NEXT tree are fetched this many 32-level rounds ahead
 
+// One simulation of the 32 trees of a warp = four phases.
+//   1a  cooperative verification   for each tree in turn, the 32 lanes take 32 consecutive LEVELS of its
+//                                   previous path: apply the pending return to the level's block, re-evaluate
+//                                   UCB1, and vote whether the old decision still stands (it does on 99.7 % of
+//                                   the levels).  The first level that needs a draw or decides differently is
+//                                   handed to phase 1b; levels not reached are scattered with RED atomics.
+//   1b  serial continuation        every lane descends its own tree from the hand-over level (lock-step)
+//   2   expansion + rollout        one env step per iteration for every lane still playing
+//   3   return pass                G_l = r + gamma G_{l+1} written to the tree's path scratch (pending)
+// The decisions are those of the sequential algorithm: a level's UCB only reads its own block, which has
+// received exactly the updates an eager backup would have made; draws happen only in 1b, in path order.
 template <int ENV, typename T, bool SCRIPTED>
 __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParams p) {
     constexpr int A = EnvTraits<ENV>::A;
     constexpr int S = EnvTraits<ENV>::S;
     constexpr double kInterior = Rewards<ENV>::kInterior;
-    __shared__ uint32_t ring_b[kRing][kTptBlock];
-    __shared__ double ring_g[kRing][kTptBlock];
     extern __shared__ double ln_smem[];  // copy of the host-computed ln(n) table when it fits
     if (p.ln_in_smem) {
         for (int i = threadIdx.x; i < p.ln_count; i += blockDim.x) ln_smem[i] = p.ln_table[i];
         __syncthreads();
     }
     const double* const ln_table = p.ln_in_smem ? ln_smem : p.ln_table;
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x & 31;
 
     // scripted (parity) mode drives ONE tree from lane 0 of a single warp; the other lanes are dummies
     const long long tree = SCRIPTED ? (threadIdx.x == 0 ? p.scripted_tree : p.n_trees)
                                     : (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = tree < p.n_trees;
     const long long tix = valid ? tree : 0;
+    const long long warp_tree0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31);  // tree of lane 0 (free-running)
+    const long long path_cap = p.block_cap;
 
     char* const blocks = p.blocks + tix * p.slots_per_tree * 16;
     T* const states = reinterpret_cast<T*>(p.states) + tix * p.slots_per_tree * S;
     double* const gfirst = p.gfirst + tix * p.slots_per_tree;
     int32_t* const meta = p.meta + tix * META_WORDS;
-    uint32_t* const path_b = p.path_b + tix;  // level-major: [level * n_trees]
-    double* const path_g = p.path_g + tix;
+    uint32_t* const path_b = p.path_b + tix * path_cap;  // tree-major: [tree][level]
+    double* const path_g = p.path_g + tix * path_cap;
 
     int alloc = valid ? meta[META_ALLOC] : 0;
     uint32_t sims_done = valid ? (uint32_t)meta[META_SIMS] : 0u;
     int fault = valid ? meta[META_FAULT] : 0;
-    // returns of the previous path still to be applied: levels [pfrom, plen)
-    int plen = 0, pfrom = 0;
+    int plen = 0;  // levels of the previous path whose returns are still pending
     const uint32_t tree_id = (uint32_t)(p.tree_id_base + (unsigned long long)tix);
     Stream ts;
     ts.resume(p.seed, 0u, tree_id, kStreamTree, valid ? (uint32_t)meta[META_RNG] : 0u);
@@ -184,15 +195,60 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
             return n > 1 ? (int)mulhi_u32(ts.next(), (uint32_t)n) : 0;
         }
     };
-    // scatter the pending returns of old-path levels [pfrom, plen) (the new path has left the old one)
-    auto flush_pending = [&]() {
-        for (int l0 = pfrom; l0 < plen; l0 += 4) {
+    // UCB1 over the A visited children (action_selection_functions.py:9-25).  The reference evaluates the scores
+    // in float64 and breaks exact ties at random.  An fp32 screening pass (error < 1e-6 relative, tolerance 1e-5)
+    // settles the arg-max whenever it is unambiguous; only near-ties take the exact float64 path, so the DECISIONS
+    // are the float64 ones.  Returns the number of exactly tied maxima (1 = unique); a_sel = the first of them
+    // in insertion order; sc/best are filled when ties > 1 is possible.
+    auto ucb = [&](const NodeBlock<A>& c, bool nonroot, int& a_sel, double (&sc)[A], double& best) -> int {
+        int ns = nonroot ? 1 : 0;
+#pragma unroll
+        for (int a = 0; a < A; ++a) ns += c.na[a];
+        const double lg = ns < p.ln_count ? ln_table[ns] : ::log((double)ns);
+        if (!(p.tuning & 1)) {
+            const float lgf = (float)lg;
+            float sf[A], m1 = -INFINITY, scale = 0.f;
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+                const float naf = (float)c.na[a];
+                const float qf = __fdividef((float)c.total[a], naf);
+                const float ef = Cf * sqrtf(__fdividef(lgf, naf));
+                sf[a] = qf + ef;
+                m1 = fmaxf(m1, sf[a]);
+                scale = fmaxf(scale, fabsf(qf) + fabsf(ef));
+            }
+            const float thr = m1 - 1e-5f * scale - 1e-30f;
+            int ncand = 0;
+#pragma unroll
+            for (int a = 0; a < A; ++a) { if (sf[a] >= thr) { ++ncand; a_sel = a; } }
+            if (ncand == 1) return 1;
+        }
+        best = -INFINITY;
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            const double na = (double)c.na[a];
+            const double q = __ddiv_rn(c.total[a], na);
+            const double ex = __dmul_rn(Cexp, __dsqrt_rn(__ddiv_rn(lg, na)));
+            sc[a] = __dadd_rn(q, ex);
+            best = fmax(best, sc[a]);
+        }
+        int ties = 0, first_rank = A;
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            if (sc[a] == best) {
+                ++ties;
+                const int rk = (int)(c.link[a] >> kLinkRankShift);
+                if (rk < first_rank) { first_rank = rk; a_sel = a; }
+            }
+        }
+        return ties;
+    };
+    // scatter the pending returns of the own tree's levels [from, plen) with fire-and-forget atomics
+    auto flush_pending = [&](int from) {
+        for (int l0 = from; l0 < plen; l0 += 4) {
             uint32_t eb[4]; double eg[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) if (l0 + j < plen) {
-                eb[j] = __ldcg(path_b + (long long)(l0 + j) * p.n_trees);
-                eg[j] = __ldcg(path_g + (long long)(l0 + j) * p.n_trees);
-            }
+            for (int j = 0; j < 4; ++j) if (l0 + j < plen) { eb[j] = __ldcg(path_b + l0 + j); eg[j] = __ldcg(path_g + l0 + j); }
 #pragma unroll
             for (int j = 0; j < 4; ++j) if (l0 + j < plen) {
                 atomicAdd(total_ptr<A>(blocks, (int)(eb[j] >> 2), (int)(eb[j] & 3u)), eg[j]);
@@ -200,81 +256,118 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
                 ++c_flushed;
             }
         }
-        plen = 0; pfrom = 0;
+        plen = 0;
     };
 
     int s_done = 0;
     for (int sim = 0; sim < p.n_sim; ++sim) {
         const bool live = valid && !fault;
         int mode = live ? MODE_DESCEND : MODE_IDLE;
-        int node_slot = 0, blk = 1, level = 0, exp_a = 0, exp_rank = 0;
-        bool fresh = false;              // block just allocated: all children unvisited, nothing to load
-        bool on_old = live && plen > 0;  // still walking the previous simulation's path
-        double G = 0.0;
-        NodeBlock<A> cnext;              // block of the NEXT level, loaded ahead along the old path
-        int cnext_blk = -1;
-#pragma unroll
-        for (int a = 0; a < A; ++a) { cnext.total[a] = 0.0; cnext.na[a] = 0; cnext.link[a] = 0u; }
+        int level = 0;  // hand-over level of phase 1a = first level phase 1b decides
 
-        // stage the first kRing entries of the old path
+        // ------------------------------------------------------------------ phase 1a: cooperative verification
+        if constexpr (!SCRIPTED) {
+            const int my_plen = live ? plen : 0;
+            uint32_t cur[kLook], nxt[kLook];
+            {   // prologue: path entries of tree 0
+                const int L0 = __shfl_sync(kFull, my_plen, 0);
+                const uint32_t* pb0 = p.path_b + warp_tree0 * path_cap;
 #pragma unroll
-        for (int k = 0; k < kRing; ++k) {
-            if (on_old && k < plen) {
-                cp_async4(&ring_b[k][tid], path_b + (long long)k * p.n_trees);
-                cp_async8(&ring_g[k][tid], path_g + (long long)k * p.n_trees);
+                for (int k = 0; k < kLook; ++k) cur[k] = (k * 32 + lane < L0) ? __ldcg(pb0 + k * 32 + lane) : 0u;
             }
-            cp_async_commit();
+            for (int j = 0; j < 32; ++j) {
+                const int Lj = __shfl_sync(kFull, my_plen, j);
+                const int Ln = __shfl_sync(kFull, my_plen, (j + 1) & 31) * (j < 31);
+                const long long tj = warp_tree0 + j;
+                // look-ahead: the next tree's path entries travel while this tree is verified
+                {
+                    const uint32_t* pbn = p.path_b + (tj + 1) * path_cap;
+                    const double* pgn = p.path_g + (tj + 1) * path_cap;
+#pragma unroll
+                    for (int k = 0; k < kLook; ++k) {
+                        const int l = k * 32 + lane;
+                        nxt[k] = (l < Ln) ? __ldcg(pbn + l) : 0u;
+                        if (l < Ln && (lane & 15) == 0) prefetch_l2(pgn + l);
+                    }
+                }
+                if (Lj > 0) {
+                    char* const bj = p.blocks + tj * p.slots_per_tree * 16;
+                    const uint32_t* pbj = p.path_b + tj * path_cap;
+                    const double* pgj = p.path_g + tj * path_cap;
+                    int event = -1, applied = 0;
+                    for (int l0 = 0, k = 0; l0 < Lj && event < 0; l0 += 32, ++k) {
+                        const int l = l0 + lane;
+                        const bool act = l < Lj;
+                        uint32_t pb = 0u;
+                        if (k < kLook) {
+#pragma unroll
+                            for (int kk = 0; kk < kLook; ++kk) if (kk == k) pb = cur[kk];
+                        } else if (act) {
+                            pb = __ldcg(pbj + l);
+                        }
+                        bool my_event = false;
+                        if (act) {
+                            const double pg = __ldcg(pgj + l);
+                            const int blk = (int)(pb >> 2), pa = (int)(pb & 3u);
+                            NodeBlock<A> c = load_block<A, false>(bj, blk);
+#pragma unroll
+                            for (int a = 0; a < A; ++a) if (a == pa) {
+                                c.total[a] = __dadd_rn(c.total[a], pg);
+                                c.na[a] += 1;
+                                __stcg(total_ptr<A>(bj, blk, a), c.total[a]);
+                                __stcg(na_ptr<A>(bj, blk, a), c.na[a]);
+                            }
+                            int nun = 0;
+#pragma unroll
+                            for (int a = 0; a < A; ++a) nun += (c.na[a] == 0);
+                            int a_sel = -1;
+                            double sc[A], best;
+                            const int ties = nun > 0 ? 2 : ucb(c, l > 0, a_sel, sc, best);
+                            my_event = (ties != 1) || (a_sel != pa);
+                        }
+                        const unsigned ev = __ballot_sync(kFull, my_event);
+                        applied = min(l0 + 32, Lj);
+                        if (ev) event = l0 + __ffs(ev) - 1;
+                    }
+                    // levels the verification did not reach: scatter their pending returns
+                    for (int l = applied + lane; l < Lj; l += 32) {
+                        const uint32_t pb = __ldcg(pbj + l);
+                        const double pg = __ldcg(pgj + l);
+                        atomicAdd(total_ptr<A>(bj, (int)(pb >> 2), (int)(pb & 3u)), pg);
+                        atomicAdd(na_ptr<A>(bj, (int)(pb >> 2), (int)(pb & 3u)), 1);
+                    }
+                    __syncwarp();
+                    if (lane == j) { level = event >= 0 ? event : Lj - 1; plen = 0; }
+                }
+                // the next tree's blocks: requested now, read one tree later
+                {
+                    const char* bn = p.blocks + (tj + 1) * p.slots_per_tree * 16;
+#pragma unroll
+                    for (int k = 0; k < kLook; ++k) {
+                        if (k * 32 + lane < Ln) prefetch_l2(bn + (long long)(nxt[k] >> 2) * (A * 16));
+                        cur[k] = nxt[k];
+                    }
+                }
+            }
         }
 
-        // ------------------------------------------------------------------ phase 1: descent
-        for (int it = 0; __any_sync(kFull, mode == MODE_DESCEND); ++it) {
-            cp_async_wait<kRing - 1 - kBlockAhead>();  // entries of levels it .. it+kBlockAhead have landed
-            const int slot_r = it & (kRing - 1);
-            const bool walking = on_old && mode == MODE_DESCEND;
-            const bool pend = walking && it < plen;
-            const uint32_t pb = pend ? ring_b[slot_r][tid] : 0u;
-            const double pg = pend ? ring_g[slot_r][tid] : 0.0;
-            if (walking && it + kBlockAhead < plen) {
-                const char* pf = blocks + (long long)(ring_b[(it + kBlockAhead) & (kRing - 1)][tid] >> 2) * (A * 16);
-                if (p.tuning & 4) touch_line(pf); else prefetch_l2(pf);
-            }
-            // refill the ring slot just consumed with level it + kRing
-            if (walking && it + kRing < plen) {
-                cp_async4(&ring_b[slot_r][tid], path_b + (long long)(it + kRing) * p.n_trees);
-                cp_async8(&ring_g[slot_r][tid], path_g + (long long)(it + kRing) * p.n_trees);
-            }
-            cp_async_commit();
-
+        // ------------------------------------------------------------------ phase 1b: serial continuation
+        int node_slot = 0, blk = 1, exp_a = 0, exp_rank = 0;
+        bool fresh = false;  // block just allocated: all children unvisited, nothing to load
+        double G = 0.0;
+        if (mode == MODE_DESCEND && level > 0) {
+            const uint32_t prev = __ldcg(path_b + level - 1), here = __ldcg(path_b + level);
+            node_slot = (int)(prev >> 2) * A + (int)(prev & 3u);
+            blk = (int)(here >> 2);
+        }
+        while (__any_sync(kFull, mode == MODE_DESCEND)) {
             if (mode == MODE_DESCEND) {
-                ++c_levels;
                 NodeBlock<A> c;
                 if (fresh) {
 #pragma unroll
                     for (int a = 0; a < A; ++a) { c.total[a] = 0.0; c.na[a] = 0; c.link[a] = 0u; }
-                } else if (blk == cnext_blk) {
-                    c = cnext;                    // already in registers: loaded one level ahead
                 } else {
-                    c = (p.tuning & 2) ? load_block<A, true>(blocks, blk) : load_block<A, false>(blocks, blk);
-                }
-                // 99.7 % of the time the descent stays on the old path: start loading the next level's block now,
-                // so that its latency overlaps this level's UCB arithmetic instead of following it
-                cnext_blk = -1;
-                if (walking && it + 1 < plen) {
-                    cnext_blk = (int)(ring_b[(it + 1) & (kRing - 1)][tid] >> 2);
-                    cnext = load_block<A, false>(blocks, cnext_blk);
-                }
-                int pa = -1;
-                if (pend) {
-                    // lazy backup: apply the previous simulation's return to this block (it is in hand anyway)
-                    pa = (int)(pb & 3u);
-#pragma unroll
-                    for (int a = 0; a < A; ++a) if (a == pa) {
-                        c.total[a] = __dadd_rn(c.total[a], pg);
-                        c.na[a] += 1;
-                        __stcg(total_ptr<A>(blocks, blk, a), c.total[a]);
-                        __stcg(na_ptr<A>(blocks, blk, a), c.na[a]);
-                    }
-                    pfrom = it + 1;
+                    c = load_block<A, false>(blocks, blk);
                 }
                 int nun = 0;
 #pragma unroll
@@ -287,72 +380,23 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
 #pragma unroll
                     for (int a = 0; a < A; ++a) { if (c.na[a] == 0) { if (seen == pos) exp_a = a; ++seen; } }
                     exp_rank = A - nun;
-                    a_sel = exp_a;
                     mode = MODE_EXPAND;
                 } else {
-                    // UCB1 over the A visited children (action_selection_functions.py:9-25).  The reference
-                    // evaluates the scores in float64 and breaks exact ties at random.  An fp32 screening pass
-                    // (error < 1e-6 relative, tolerance 1e-5) settles the arg-max whenever it is unambiguous;
-                    // only near-ties take the exact float64 path, so the DECISIONS are the float64 ones.
-                    int ns = (node_slot != 0);
+                    double sc[A], best;
+                    const int ties = ucb(c, node_slot != 0, a_sel, sc, best);
+                    if (SCRIPTED || ties > 1) {
+                        int pos = choice(ties);
+                        if (ties > 1) {
+                            // the tied set is ordered like node.actions (insertion order = rank)
 #pragma unroll
-                    for (int a = 0; a < A; ++a) ns += c.na[a];
-                    const double lg = ns < p.ln_count ? ln_table[ns] : ::log((double)ns);
-                    bool settled = false;
-                    if (!(p.tuning & 1)) {
-                        const float lgf = (float)lg;
-                        float sf[A], m1 = -INFINITY, scale = 0.f;
+                            for (int rk = 0; rk < A; ++rk) {
 #pragma unroll
-                        for (int a = 0; a < A; ++a) {
-                            const float naf = (float)c.na[a];
-                            const float qf = __fdividef((float)c.total[a], naf);
-                            const float ef = Cf * sqrtf(__fdividef(lgf, naf));
-                            sf[a] = qf + ef;
-                            m1 = fmaxf(m1, sf[a]);
-                            scale = fmaxf(scale, fabsf(qf) + fabsf(ef));
-                        }
-                        const float thr = m1 - 1e-5f * scale - 1e-30f;
-                        int ncand = 0;
-#pragma unroll
-                        for (int a = 0; a < A; ++a) { if (sf[a] >= thr) { ++ncand; a_sel = a; } }
-                        settled = (ncand == 1);
-                    }
-                    if (!settled) {
-                        double sc[A], best = -INFINITY;
-#pragma unroll
-                        for (int a = 0; a < A; ++a) {
-                            const double na = (double)c.na[a];
-                            const double q = __ddiv_rn(c.total[a], na);
-                            const double ex = __dmul_rn(Cexp, __dsqrt_rn(__ddiv_rn(lg, na)));
-                            sc[a] = __dadd_rn(q, ex);
-                            best = fmax(best, sc[a]);
-                        }
-                        int ties = 0;
-#pragma unroll
-                        for (int a = 0; a < A; ++a) ties += (sc[a] == best);
-                        int pos = (SCRIPTED || ties > 1) ? choice(ties) : 0;
-                        // the tied set is ordered like node.actions (insertion order = rank)
-#pragma unroll
-                        for (int rk = 0; rk < A; ++rk) {
-#pragma unroll
-                            for (int a = 0; a < A; ++a) {
-                                if ((int)(c.link[a] >> kLinkRankShift) == rk && sc[a] == best) { if (pos == 0) a_sel = a; --pos; }
+                                for (int a = 0; a < A; ++a) {
+                                    if ((int)(c.link[a] >> kLinkRankShift) == rk && sc[a] == best) { if (pos == 0) a_sel = a; --pos; }
+                                }
                             }
                         }
-                    } else if constexpr (SCRIPTED) {
-                        (void)choice(1);  // the reference draws even when the maximum is unique
                     }
-                }
-                // leaving the previous path here?  then its deeper levels must be scattered now
-                if (on_old) {
-                    if (!pend || a_sel != pa || mode == MODE_EXPAND) {
-                        flush_pending();
-                        on_old = false;
-                    } else if (it + 1 >= plen) {
-                        on_old = false; plen = 0; pfrom = 0;  // the old path ended here; nothing deeper is pending
-                    }
-                }
-                if (mode == MODE_DESCEND) {
                     uint32_t lk = c.link[0];
 #pragma unroll
                     for (int a = 1; a < A; ++a) if (a == a_sel) lk = c.link[a];
@@ -366,7 +410,7 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
                         }
                         mode = MODE_RETURN;
                     } else {
-                        path_b[(long long)level * p.n_trees] = ((uint32_t)blk << 2) | (uint32_t)a_sel;
+                        path_b[level] = ((uint32_t)blk << 2) | (uint32_t)a_sel;
                         ++level;
                         node_slot = blk * A + a_sel;
                         int nb = (int)(lk & kLinkBlockMask);
@@ -380,7 +424,6 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
                 }
             }
         }
-        cp_async_wait<0>();
 
         // ------------------------------------------------------------------ phase 2: expansion + rollout
         T st[S];
@@ -461,20 +504,23 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
 
         // ------------------------------------------------------------------ phase 3: return pass
         // G_l = r + gamma * G_{l+1} up the recorded path (mcts_hash.py:126-131, 79-81).  The returns are only
-        // WRITTEN to the level-major scratch; the next descent applies them (or a flush scatters them).
+        // WRITTEN to the tree's path scratch; the next simulation's phase 1a applies them.
         if (mode == MODE_RETURN) {
+            c_levels += (unsigned long long)level + 1ull;
             for (int l = level - 1; l >= 0; --l) {
                 G = __dadd_rn(kInterior, __dmul_rn(gamma, G));
-                path_g[(long long)l * p.n_trees] = G;
+                path_g[l] = G;
             }
-            plen = level; pfrom = 0;
+            plen = level;
             ++sims_done; ++s_done;
+            if constexpr (SCRIPTED) flush_pending(0);  // the trace scripts a draw per level: no cooperative phase
         }
+        __syncwarp();
     }
 
     if (valid) {
         // leave the tree consistent for the host / the next launch: scatter what is still pending
-        if (plen > pfrom) flush_pending();
+        if (plen > 0) flush_pending(0);
         meta[META_ALLOC] = alloc;
         meta[META_SIMS] = (int32_t)sims_done;
         meta[META_RNG] = (int32_t)ts.consumed();
