@@ -268,26 +268,36 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
         // ------------------------------------------------------------------ phase 1a: cooperative verification
         if constexpr (!SCRIPTED) {
             const int my_plen = live ? plen : 0;
-            uint32_t cur[kLook], nxt[kLook];
-            {   // prologue: path entries of tree 0
-                const int L0 = __shfl_sync(kFull, my_plen, 0);
+            // software pipeline over the warp's trees: while tree j is verified, the path entries of tree j+2 are
+            // being loaded and the node blocks + returns of tree j+1 (entries loaded one tree earlier) are being
+            // prefetched into L2, so that a tree's rounds find their data on chip
+            uint32_t cur[kLook], nxt[kLook], nn[kLook];
+            {   // prologue: path entries of trees 0 and 1
+                const int L0 = __shfl_sync(kFull, my_plen, 0), L1 = __shfl_sync(kFull, my_plen, 1);
                 const uint32_t* pb0 = p.path_b + warp_tree0 * path_cap;
 #pragma unroll
-                for (int k = 0; k < kLook; ++k) cur[k] = (k * 32 + lane < L0) ? __ldcg(pb0 + k * 32 + lane) : 0u;
+                for (int k = 0; k < kLook; ++k) {
+                    cur[k] = (k * 32 + lane < L0) ? __ldcg(pb0 + k * 32 + lane) : 0u;
+                    nxt[k] = (k * 32 + lane < L1) ? __ldcg(pb0 + path_cap + k * 32 + lane) : 0u;
+                }
             }
             for (int j = 0; j < 32; ++j) {
                 const int Lj = __shfl_sync(kFull, my_plen, j);
                 const int Ln = __shfl_sync(kFull, my_plen, (j + 1) & 31) * (j < 31);
+                const int Lnn = __shfl_sync(kFull, my_plen, (j + 2) & 31) * (j < 30);
                 const long long tj = warp_tree0 + j;
-                // look-ahead: the next tree's path entries travel while this tree is verified
                 {
-                    const uint32_t* pbn = p.path_b + (tj + 1) * path_cap;
+                    const uint32_t* pbnn = p.path_b + (tj + 2) * path_cap;
                     const double* pgn = p.path_g + (tj + 1) * path_cap;
+                    const char* bn = p.blocks + (tj + 1) * p.slots_per_tree * 16;
 #pragma unroll
                     for (int k = 0; k < kLook; ++k) {
                         const int l = k * 32 + lane;
-                        nxt[k] = (l < Ln) ? __ldcg(pbn + l) : 0u;
-                        if (l < Ln && (lane & 15) == 0) prefetch_l2(pgn + l);
+                        nn[k] = (l < Lnn) ? __ldcg(pbnn + l) : 0u;
+                        if (l < Ln && !(p.tuning & 8)) {
+                            prefetch_l2(bn + (long long)(nxt[k] >> 2) * (A * 16));
+                            if ((lane & 15) == 0) prefetch_l2(pgn + l);
+                        }
                     }
                 }
                 if (Lj > 0) {
@@ -339,15 +349,8 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
                     __syncwarp();
                     if (lane == j) { level = event >= 0 ? event : Lj - 1; plen = 0; }
                 }
-                // the next tree's blocks: requested now, read one tree later
-                {
-                    const char* bn = p.blocks + (tj + 1) * p.slots_per_tree * 16;
 #pragma unroll
-                    for (int k = 0; k < kLook; ++k) {
-                        if (k * 32 + lane < Ln) prefetch_l2(bn + (long long)(nxt[k] >> 2) * (A * 16));
-                        cur[k] = nxt[k];
-                    }
-                }
+                for (int k = 0; k < kLook; ++k) { cur[k] = nxt[k]; nxt[k] = nn[k]; }
             }
         }
 
