@@ -60,14 +60,14 @@ struct CtaParams {
     const double* disc_table; const double* ln_table; const double* pw1_table; const double* pw2_table;
     int ln_count, disc_count;
     int n_sim, max_depth, budget_mode, agent, n_actions, R, expansion, voo_n, voo_max_try, real_bytes;
+    int pool_in_smem;  // the whole tree pool fits in shared memory: search there, copy back at the end
 };
 
 enum : int { O_S_TOTAL = 0, O_S_TERMR, O_S_NS, O_S_FLAGS, O_S_COFF, O_S_CCAP, O_S_CCNT, O_S_STATE, O_A_TOTAL, O_A_VALUE,
              O_A_NA, O_A_VISITS, O_A_CHILD, O_IPOOL, O_P_S, O_P_A, O_P_R, O_P_FLAG, O_META, O_COUNT };
 enum : int { CM_NS = 0, CM_NA = 1, CM_ITOP = 2, CM_SIMS = 3, CM_RNG = 4, CM_FAULT = 5, CM_TRACE_POS = 6, CM_WORDS = 8 };
 
-__device__ __forceinline__ Pool make_pool(const CtaParams& p, long long tree) {
-    char* b = p.pool_base + tree * p.pool_stride;
+__device__ __forceinline__ Pool make_pool_at(const CtaParams& p, char* b) {
     Pool q;
     q.s_total = (double*)(b + p.off[O_S_TOTAL]); q.s_term_reward = (double*)(b + p.off[O_S_TERMR]);
     q.s_ns = (int*)(b + p.off[O_S_NS]); q.s_flags = (int*)(b + p.off[O_S_FLAGS]);
@@ -80,6 +80,9 @@ __device__ __forceinline__ Pool make_pool(const CtaParams& p, long long tree) {
     q.p_flag = (int*)(b + p.off[O_P_FLAG]);
     q.meta = (int*)(b + p.off[O_META]);
     return q;
+}
+__device__ __forceinline__ Pool make_pool(const CtaParams& p, long long tree) {
+    return make_pool_at(p, p.pool_base + tree * p.pool_stride);
 }
 
 struct Cursor {  // replicated in every lane of warp 0
@@ -114,7 +117,7 @@ struct Search {
     uint32_t tree_id;
     unsigned long long c_env = 0, c_roll = 0, c_levels = 0, c_nodes = 0;
 
-    __device__ Search(const CtaParams& p_, long long tree) : p(p_), q(make_pool(p_, tree)) {
+    __device__ Search(const CtaParams& p_, long long tree, char* pool_bytes) : p(p_), q(make_pool_at(p_, pool_bytes)) {
         lane = threadIdx.x & 31;
         nS = q.meta[CM_NS]; nA = q.meta[CM_NA]; itop = q.meta[CM_ITOP]; fault = q.meta[CM_FAULT];
         tree_id = (uint32_t)(p.tree_id_base + (unsigned long long)tree);
@@ -343,7 +346,18 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
     int P = 1;
     while (P < R) P <<= 1;
 
-    Search<ENV, T, SCRIPTED> ctx(p, tree);
+    // Small trees (C1/C2-sized: <= ~1500 simulations) live in SHARED memory for the whole launch: the pool is copied
+    // in, every select/expand/backup access costs ~30 cycles instead of an L2 round trip, and it is copied back at
+    // the end.  Larger pools stay in HBM/L2.
+    extern __shared__ int4 pool_smem[];
+    char* const pool_global = p.pool_base + tree * p.pool_stride;
+    if (p.pool_in_smem) {
+        const int n16 = (int)(p.pool_stride >> 4);
+        const int4* src = reinterpret_cast<const int4*>(pool_global);
+        for (int i = tid; i < n16; i += nt) pool_smem[i] = src[i];
+        __syncthreads();
+    }
+    Search<ENV, T, SCRIPTED> ctx(p, tree, p.pool_in_smem ? reinterpret_cast<char*>(pool_smem) : pool_global);
     uint32_t sims_done = (uint32_t)ctx.q.meta[CM_SIMS];
     int s_done = 0;
     unsigned long long my_steps = 0;  // rollout env steps played by THIS thread
@@ -571,6 +585,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
     }
 
     if (my_steps) { atomicAdd(p.counters + CNT_ROLLOUT_STEPS, my_steps); atomicAdd(p.counters + CNT_ENV_STEPS, my_steps); }
+    bool copy_back = p.pool_in_smem;
     if (leader) {
         int flt = ctx.fault ? ctx.fault : ctx.tc.fault;
         if (lane == 0) {
@@ -585,6 +600,12 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
             atomicAdd(p.counters + CNT_NODES, ctx.c_nodes);
             if (flt) atomicAdd(p.counters + CNT_FAULTS, 1ull);
         }
+    }
+    if (copy_back) {
+        __syncthreads();
+        const int n16 = (int)(p.pool_stride >> 4);
+        int4* dst = reinterpret_cast<int4*>(pool_global);
+        for (int i = tid; i < n16; i += nt) dst[i] = pool_smem[i];
     }
 }
 
@@ -708,6 +729,8 @@ CtaParams make_params(const isla_engine* e) {
     p.n_sim = 0; p.max_depth = e->cfg.max_depth; p.budget_mode = e->cfg.budget_mode; p.agent = e->cfg.agent;
     p.n_actions = e->cfg.n_actions; p.R = e->cfg.rollouts_per_leaf > 0 ? e->cfg.rollouts_per_leaf : 1;
     p.expansion = e->cfg.expansion; p.voo_n = e->cfg.voo_n_samples; p.voo_max_try = e->cfg.voo_max_try; p.real_bytes = rb;
+    // 227 KB per CTA minus the static rollout-reduction buffer and bookkeeping
+    p.pool_in_smem = (off <= 190 * 1024 && !(e->cfg.tuning & 16)) ? 1 : 0;
     return p;
 }
 
@@ -732,8 +755,14 @@ int pick_threads(const isla_config& cfg) {
 
 template <int ENV, typename T>
 int launch(const CtaParams& p, int nt, bool scripted, cudaStream_t st) {
-    if (scripted) cta_search_kernel<ENV, T, true><<<1, nt, 0, st>>>(p);
-    else cta_search_kernel<ENV, T, false><<<(unsigned)p.n_trees, nt, 0, st>>>(p);
+    const size_t smem = p.pool_in_smem ? (size_t)p.pool_stride : 0;
+    if (scripted) {
+        if (smem) cudaFuncSetAttribute(cta_search_kernel<ENV, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cta_search_kernel<ENV, T, true><<<1, nt, smem, st>>>(p);
+    } else {
+        if (smem) cudaFuncSetAttribute(cta_search_kernel<ENV, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cta_search_kernel<ENV, T, false><<<(unsigned)p.n_trees, nt, smem, st>>>(p);
+    }
     const cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? 0 : cuda_fail(err, "cta_search_kernel launch");
 }

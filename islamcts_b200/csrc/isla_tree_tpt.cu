@@ -133,6 +133,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 
 enum : int { MODE_DESCEND = 0, MODE_EXPAND = 1, MODE_RETURN = 2, MODE_IDLE = 3 };
 constexpr int kLook = 6;  // path entries of the NEXT tree are fetched this many 32-level rounds ahead
+constexpr int kCoopMin = 16;  // deepest pending path in the warp below which phase 1a is skipped
 
 // One simulation of the 32 trees of a warp = four phases.
 //   1a  cooperative verification   for each tree in turn, the 32 lanes take 32 consecutive LEVELS of its
@@ -266,7 +267,14 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
         int level = 0;  // hand-over level of phase 1a = first level phase 1b decides
 
         // ------------------------------------------------------------------ phase 1a: cooperative verification
-        if constexpr (!SCRIPTED) {
+        // (shallow trees -- FrozenLake, the first simulations -- have nothing to verify in parallel: their pending
+        //  returns are scattered at once and the descent starts at the root)
+        int warp_max_plen = live ? plen : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) warp_max_plen = max(warp_max_plen, __shfl_xor_sync(kFull, warp_max_plen, o));
+        if (SCRIPTED || warp_max_plen < kCoopMin) {
+            if (live && plen > 0) flush_pending(0);
+        } else {
             const int my_plen = live ? plen : 0;
             // software pipeline over the warp's trees: while tree j is verified, the path entries of tree j+2 are
             // being loaded and the node blocks + returns of tree j+1 (entries loaded one tree earlier) are being
@@ -516,7 +524,6 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
             }
             plen = level;
             ++sims_done; ++s_done;
-            if constexpr (SCRIPTED) flush_pending(0);  // the trace scripts a draw per level: no cooperative phase
         }
         __syncwarp();
     }
