@@ -46,7 +46,8 @@ class IslaLayout(C.Structure):
         ("kernel", C.c_int32), ("state_dim", C.c_int32), ("real_bytes", C.c_int32), ("n_actions", C.c_int32),
         ("slots_per_tree", C.c_int64), ("rec_offset", C.c_int64), ("rec_stride", C.c_int64),
         ("state_offset", C.c_int64), ("state_stride", C.c_int64), ("gfirst_offset", C.c_int64), ("gfirst_stride", C.c_int64),
-        ("meta_offset", C.c_int64), ("path_offset", C.c_int64), ("pathg_offset", C.c_int64), ("counters_offset", C.c_int64), ("ln_offset", C.c_int64), ("ln_count", C.c_int64),
+        ("meta_offset", C.c_int64), ("path_offset", C.c_int64), ("pathg_offset", C.c_int64), ("pvown_offset", C.c_int64),
+        ("counters_offset", C.c_int64), ("ln_offset", C.c_int64), ("ln_count", C.c_int64),
         ("disc_offset", C.c_int64), ("disc_count", C.c_int64), ("pw1_offset", C.c_int64), ("pw2_offset", C.c_int64), ("cumdisc_offset", C.c_int64),
         ("s_cap", C.c_int64), ("a_cap", C.c_int64),
         ("pool_offset", C.c_int64), ("pool_stride", C.c_int64), ("total_bytes", C.c_int64),

@@ -44,8 +44,9 @@ struct TptParams {
     void* states;
     double* gfirst;
     int32_t* meta;
-    uint32_t* path_b;      // [level][tree]  block << 2 | action of the edge descended through
-    double* path_g;        // [level][tree]  return G backed up through that edge (pending until the next descent)
+    char* pv_sib;          // [tree][level]  PV cache, static half: edge id (block << 2 | action) + the siblings' statistics
+    char* pv_own;          // [tree][level]  PV cache, dynamic half: {double total; int32 na; int32 pad} of the edge taken
+    double* path_g;        // [tree][level]  return G backed up through that edge (pending until the next simulation)
     unsigned long long* counters;
     const uint8_t* trace_kinds;
     const double* trace_values;

@@ -132,20 +132,67 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 enum : int { MODE_DESCEND = 0, MODE_EXPAND = 1, MODE_RETURN = 2, MODE_IDLE = 3 };
-constexpr int kLook = 6;  // path entries of the NEXT tree are fetched this many 32-level rounds ahead
-constexpr int kCoopMin = 16;  // deepest pending path in the warp below which phase 1a is skipped
+constexpr int kCoopMin = 16;  // deepest cached path in the warp below which phase 1a is skipped
+
+// PV cache (per tree, per level of the last simulation's path; tree-major rows in HBM):
+//   PvOwn  16 B  {double total; int32 na; int32 pad}      statistics of the edge the path takes  (changes every simulation)
+//   PvSib  16 B (A=2) / 48 B (A=4)  {uint32 edge = block<<2|action; int32 na[A-1]; double total[A-1]}
+//                                                         the sibling edges                       (static while on the path)
+//   G       8 B  the return backed up through the edge, pending until the next simulation
+// While a level is cached, PvOwn is the AUTHORITATIVE copy of that edge's statistics; its node block in HBM is stale
+// for that one edge and is written back when the level leaves the path (or at the end of the launch).
+struct __align__(16) PvOwn { double total; int32_t na; int32_t pad; };
+template <int A> struct __align__(16) PvSib { uint32_t edge; int32_t na[A - 1]; double total[A - 1]; };
+static_assert(sizeof(PvOwn) == 16 && sizeof(PvSib<2>) == 16 && sizeof(PvSib<4>) == 48, "PV cache entry sizes");
+
+__device__ __forceinline__ PvOwn load_own(const char* row, int l) {
+    const int4 v = __ldcg(reinterpret_cast<const int4*>(row) + l);
+    PvOwn o; o.total = __hiloint2double(v.y, v.x); o.na = v.z; o.pad = 0; return o;
+}
+__device__ __forceinline__ void store_own(char* row, int l, double total, int na) {
+    __stcg(reinterpret_cast<int4*>(row) + l, make_int4(__double2loint(total), __double2hiint(total), na, 0));
+}
+template <int A> __device__ __forceinline__ PvSib<A> load_sib(const char* row, int l) {
+    PvSib<A> s;
+    const int4* p = reinterpret_cast<const int4*>(row + (long long)l * sizeof(PvSib<A>));
+    if constexpr (A == 2) {
+        const int4 v = __ldcg(p);
+        s.edge = (uint32_t)v.x; s.na[0] = v.y; s.total[0] = __hiloint2double(v.w, v.z);
+    } else {
+        const int4 v0 = __ldcg(p), v1 = __ldcg(p + 1), v2 = __ldcg(p + 2);
+        s.edge = (uint32_t)v0.x; s.na[0] = v0.y; s.na[1] = v0.z; s.na[2] = v0.w;
+        s.total[0] = __hiloint2double(v1.y, v1.x); s.total[1] = __hiloint2double(v1.w, v1.z); s.total[2] = __hiloint2double(v2.y, v2.x);
+    }
+    return s;
+}
+template <int A> __device__ __forceinline__ uint32_t load_edge(const char* row, int l) {
+    return __ldcg(reinterpret_cast<const uint32_t*>(row + (long long)l * sizeof(PvSib<A>)));
+}
+template <int A> __device__ __forceinline__ void store_sib(char* row, int l, const PvSib<A>& s) {
+    int4* p = reinterpret_cast<int4*>(row + (long long)l * sizeof(PvSib<A>));
+    if constexpr (A == 2) {
+        __stcg(p, make_int4((int)s.edge, s.na[0], __double2loint(s.total[0]), __double2hiint(s.total[0])));
+    } else {
+        __stcg(p, make_int4((int)s.edge, s.na[0], s.na[1], s.na[2]));
+        __stcg(p + 1, make_int4(__double2loint(s.total[0]), __double2hiint(s.total[0]), __double2loint(s.total[1]), __double2hiint(s.total[1])));
+        __stcg(p + 2, make_int4(__double2loint(s.total[2]), __double2hiint(s.total[2]), 0, 0));
+    }
+}
 
 // One simulation of the 32 trees of a warp = four phases.
-//   1a  cooperative verification   for each tree in turn, the 32 lanes take 32 consecutive LEVELS of its
-//                                   previous path: apply the pending return to the level's block, re-evaluate
-//                                   UCB1, and vote whether the old decision still stands (it does on 99.7 % of
-//                                   the levels).  The first level that needs a draw or decides differently is
-//                                   handed to phase 1b; levels not reached are scattered with RED atomics.
-//   1b  serial continuation        every lane descends its own tree from the hand-over level (lock-step)
+//   1a  cooperative verification   for each tree in turn, the 32 lanes take 32 consecutive LEVELS of its cached
+//                                   path: add the pending return to the level's own statistics, re-evaluate UCB1
+//                                   against the cached sibling statistics, and vote whether the old decision still
+//                                   stands (it does on 99.7 % of the levels).  All reads and writes are consecutive
+//                                   16-byte entries of one tree's rows; node blocks are not touched.  The first level
+//                                   that needs a draw or decides differently is handed to phase 1b; the levels from
+//                                   there on leave the cache (their statistics are written back to the node blocks).
+//   1b  serial continuation        every lane descends its own tree from the hand-over level on the node blocks
+//                                   (lock-step) and caches the levels it passes
 //   2   expansion + rollout        one env step per iteration for every lane still playing
-//   3   return pass                G_l = r + gamma G_{l+1} written to the tree's path scratch (pending)
-// The decisions are those of the sequential algorithm: a level's UCB only reads its own block, which has
-// received exactly the updates an eager backup would have made; draws happen only in 1b, in path order.
+//   3   return pass                G_l = r + gamma G_{l+1} written to the tree's pending-return row
+// The decisions are those of the sequential algorithm: a level's UCB sees exactly the statistics an eager backup
+// would have produced; draws happen only in 1b, in path order.
 template <int ENV, typename T, bool SCRIPTED>
 __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParams p) {
     constexpr int A = EnvTraits<ENV>::A;
@@ -166,18 +213,21 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
     const long long tix = valid ? tree : 0;
     const long long warp_tree0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31);  // tree of lane 0 (free-running)
     const long long path_cap = p.block_cap;
+    constexpr long long kSibBytes = sizeof(PvSib<A>);
 
     char* const blocks = p.blocks + tix * p.slots_per_tree * 16;
     T* const states = reinterpret_cast<T*>(p.states) + tix * p.slots_per_tree * S;
     double* const gfirst = p.gfirst + tix * p.slots_per_tree;
     int32_t* const meta = p.meta + tix * META_WORDS;
-    uint32_t* const path_b = p.path_b + tix * path_cap;  // tree-major: [tree][level]
+    char* const pv_sib = p.pv_sib + tix * path_cap * kSibBytes;  // tree-major rows: [tree][level]
+    char* const pv_own = p.pv_own + tix * path_cap * 16;
     double* const path_g = p.path_g + tix * path_cap;
 
     int alloc = valid ? meta[META_ALLOC] : 0;
     uint32_t sims_done = valid ? (uint32_t)meta[META_SIMS] : 0u;
     int fault = valid ? meta[META_FAULT] : 0;
-    int plen = 0;  // levels of the previous path whose returns are still pending
+    int plen = 0;        // cached levels [0, plen): PvOwn authoritative, node blocks stale for those edges
+    bool pend = false;   // the returns G_l of those levels are still to be added
     const uint32_t tree_id = (uint32_t)(p.tree_id_base + (unsigned long long)tix);
     Stream ts;
     ts.resume(p.seed, 0u, tree_id, kStreamTree, valid ? (uint32_t)meta[META_RNG] : 0u);
@@ -244,20 +294,19 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
         }
         return ties;
     };
-    // scatter the pending returns of the own tree's levels [from, plen) with fire-and-forget atomics
-    auto flush_pending = [&](int from) {
-        for (int l0 = from; l0 < plen; l0 += 4) {
-            uint32_t eb[4]; double eg[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) if (l0 + j < plen) { eb[j] = __ldcg(path_b + l0 + j); eg[j] = __ldcg(path_g + l0 + j); }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) if (l0 + j < plen) {
-                atomicAdd(total_ptr<A>(blocks, (int)(eb[j] >> 2), (int)(eb[j] & 3u)), eg[j]);
-                atomicAdd(na_ptr<A>(blocks, (int)(eb[j] >> 2), (int)(eb[j] & 3u)), 1);
-                ++c_flushed;
-            }
+    // write the cached statistics of the own tree's levels [from, plen) back to their node blocks (adding the
+    // pending return if there is one): those levels leave the cache
+    auto write_back = [&](int from) {
+        for (int l = from; l < plen; ++l) {
+            const PvOwn o = load_own(pv_own, l);
+            const uint32_t e = load_edge<A>(pv_sib, l);
+            const double g = pend ? __ldcg(path_g + l) : 0.0;
+            __stcg(total_ptr<A>(blocks, (int)(e >> 2), (int)(e & 3u)), pend ? __dadd_rn(o.total, g) : o.total);
+            __stcg(na_ptr<A>(blocks, (int)(e >> 2), (int)(e & 3u)), o.na + (pend ? 1 : 0));
+            ++c_flushed;
         }
-        plen = 0;
+        plen = from;
+        if (from == 0) pend = false;
     };
 
     int s_done = 0;
@@ -267,73 +316,63 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
         int level = 0;  // hand-over level of phase 1a = first level phase 1b decides
 
         // ------------------------------------------------------------------ phase 1a: cooperative verification
-        // (shallow trees -- FrozenLake, the first simulations -- have nothing to verify in parallel: their pending
-        //  returns are scattered at once and the descent starts at the root)
-        int warp_max_plen = live ? plen : 0;
+        // (shallow trees -- FrozenLake, the first simulations -- have nothing to verify in parallel: their cache is
+        //  written back at once and the descent starts at the root)
+        int warp_max_plen = (live && pend) ? plen : 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) warp_max_plen = max(warp_max_plen, __shfl_xor_sync(kFull, warp_max_plen, o));
         if (SCRIPTED || warp_max_plen < kCoopMin) {
-            if (live && plen > 0) flush_pending(0);
+            if (live && plen > 0) write_back(0);
         } else {
-            const int my_plen = live ? plen : 0;
-            // software pipeline over the warp's trees: while tree j is verified, the path entries of tree j+2 are
-            // being loaded and the node blocks + returns of tree j+1 (entries loaded one tree earlier) are being
-            // prefetched into L2, so that a tree's rounds find their data on chip
-            uint32_t cur[kLook], nxt[kLook], nn[kLook];
-            {   // prologue: path entries of trees 0 and 1
-                const int L0 = __shfl_sync(kFull, my_plen, 0), L1 = __shfl_sync(kFull, my_plen, 1);
-                const uint32_t* pb0 = p.path_b + warp_tree0 * path_cap;
-#pragma unroll
-                for (int k = 0; k < kLook; ++k) {
-                    cur[k] = (k * 32 + lane < L0) ? __ldcg(pb0 + k * 32 + lane) : 0u;
-                    nxt[k] = (k * 32 + lane < L1) ? __ldcg(pb0 + path_cap + k * 32 + lane) : 0u;
-                }
-            }
+            const int my_plen = (live && pend) ? plen : 0;
             for (int j = 0; j < 32; ++j) {
                 const int Lj = __shfl_sync(kFull, my_plen, j);
                 const int Ln = __shfl_sync(kFull, my_plen, (j + 1) & 31) * (j < 31);
-                const int Lnn = __shfl_sync(kFull, my_plen, (j + 2) & 31) * (j < 30);
                 const long long tj = warp_tree0 + j;
-                {
-                    const uint32_t* pbnn = p.path_b + (tj + 2) * path_cap;
-                    const double* pgn = p.path_g + (tj + 1) * path_cap;
-                    const char* bn = p.blocks + (tj + 1) * p.slots_per_tree * 16;
-#pragma unroll
-                    for (int k = 0; k < kLook; ++k) {
-                        const int l = k * 32 + lane;
-                        nn[k] = (l < Lnn) ? __ldcg(pbnn + l) : 0u;
-                        if (l < Ln && !(p.tuning & 8)) {
-                            prefetch_l2(bn + (long long)(nxt[k] >> 2) * (A * 16));
-                            if ((lane & 15) == 0) prefetch_l2(pgn + l);
-                        }
+                if (Ln > 0 && !(p.tuning & 8)) {
+                    // the next tree's rows (consecutive bytes) are requested while this tree is verified
+                    const char* on = p.pv_own + (tj + 1) * path_cap * 16;
+                    const char* sn = p.pv_sib + (tj + 1) * path_cap * kSibBytes;
+                    const double* gn = p.path_g + (tj + 1) * path_cap;
+                    for (int l = lane * 8; l < Ln; l += 256) {  // one 128-byte line of each row per lane and pass
+                        prefetch_l2(on + (long long)l * 16);
+                        prefetch_l2(sn + (long long)l * kSibBytes);
+                        if (kSibBytes > 16) { prefetch_l2(sn + (long long)l * kSibBytes + 128); prefetch_l2(sn + (long long)l * kSibBytes + 256); }
+                        if ((lane & 1) == 0) prefetch_l2(gn + l);
                     }
                 }
                 if (Lj > 0) {
                     char* const bj = p.blocks + tj * p.slots_per_tree * 16;
-                    const uint32_t* pbj = p.path_b + tj * path_cap;
-                    const double* pgj = p.path_g + tj * path_cap;
-                    int event = -1, applied = 0;
-                    for (int l0 = 0, k = 0; l0 < Lj && event < 0; l0 += 32, ++k) {
+                    char* const oj = p.pv_own + tj * path_cap * 16;
+                    const char* sj = p.pv_sib + tj * path_cap * kSibBytes;
+                    const double* gj = p.path_g + tj * path_cap;
+                    int event = -1, done_upto = 0;
+                    for (int l0 = 0; l0 < Lj && event < 0; l0 += 32) {
                         const int l = l0 + lane;
                         const bool act = l < Lj;
-                        uint32_t pb = 0u;
-                        if (k < kLook) {
-#pragma unroll
-                            for (int kk = 0; kk < kLook; ++kk) if (kk == k) pb = cur[kk];
-                        } else if (act) {
-                            pb = __ldcg(pbj + l);
-                        }
                         bool my_event = false;
+                        double new_total = 0.0; int new_na = 0; uint32_t edge = 0u;
                         if (act) {
-                            const double pg = __ldcg(pgj + l);
-                            const int blk = (int)(pb >> 2), pa = (int)(pb & 3u);
-                            NodeBlock<A> c = load_block<A, false>(bj, blk);
+                            const PvOwn o = load_own(oj, l);
+                            const PvSib<A> sb = load_sib<A>(sj, l);
+                            const double pg = __ldcg(gj + l);
+                            edge = sb.edge;
+                            const int pa = (int)(edge & 3u);
+                            new_total = __dadd_rn(o.total, pg);   // lazy backup: the return of the previous simulation
+                            new_na = o.na + 1;
+                            NodeBlock<A> c;
+                            int k = 0;
 #pragma unroll
-                            for (int a = 0; a < A; ++a) if (a == pa) {
-                                c.total[a] = __dadd_rn(c.total[a], pg);
-                                c.na[a] += 1;
-                                __stcg(total_ptr<A>(bj, blk, a), c.total[a]);
-                                __stcg(na_ptr<A>(bj, blk, a), c.na[a]);
+                            for (int a = 0; a < A; ++a) {
+                                c.link[a] = 0u;
+                                if (a == pa) { c.total[a] = new_total; c.na[a] = new_na; }
+                                else {
+                                    // siblings are stored in ascending action order
+                                    double st_ = sb.total[0]; int sn_ = sb.na[0];
+#pragma unroll
+                                    for (int q = 1; q < A - 1; ++q) if (q == k) { st_ = sb.total[q]; sn_ = sb.na[q]; }
+                                    c.total[a] = st_; c.na[a] = sn_; ++k;
+                                }
                             }
                             int nun = 0;
 #pragma unroll
@@ -344,21 +383,39 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
                             my_event = (ties != 1) || (a_sel != pa);
                         }
                         const unsigned ev = __ballot_sync(kFull, my_event);
-                        applied = min(l0 + 32, Lj);
                         if (ev) event = l0 + __ffs(ev) - 1;
+                        if (act) {
+                            // levels before the event stay cached (with the return added); the event level and
+                            // everything deeper leave the cache: their statistics go back to the node blocks
+                            if (event < 0 || l < event) store_own(oj, l, new_total, new_na);
+                            else {
+                                __stcg(total_ptr<A>(bj, (int)(edge >> 2), (int)(edge & 3u)), new_total);
+                                __stcg(na_ptr<A>(bj, (int)(edge >> 2), (int)(edge & 3u)), new_na);
+                            }
+                        }
+                        done_upto = min(l0 + 32, Lj);
                     }
-                    // levels the verification did not reach: scatter their pending returns
-                    for (int l = applied + lane; l < Lj; l += 32) {
-                        const uint32_t pb = __ldcg(pbj + l);
-                        const double pg = __ldcg(pgj + l);
-                        atomicAdd(total_ptr<A>(bj, (int)(pb >> 2), (int)(pb & 3u)), pg);
-                        atomicAdd(na_ptr<A>(bj, (int)(pb >> 2), (int)(pb & 3u)), 1);
+                    const int r = event >= 0 ? event : Lj - 1;
+                    if (event < 0) {
+                        // no event: the last cached level is handed over too (phase 1b re-decides it on its block)
+                        if (((Lj - 1) & 31) == lane) {
+                            const PvOwn o = load_own(oj, Lj - 1);
+                            const uint32_t e = load_edge<A>(sj, Lj - 1);
+                            __stcg(total_ptr<A>(bj, (int)(e >> 2), (int)(e & 3u)), o.total);
+                            __stcg(na_ptr<A>(bj, (int)(e >> 2), (int)(e & 3u)), o.na);
+                        }
+                    }
+                    // levels the verification did not reach leave the cache as well
+                    for (int l = done_upto + lane; l < Lj; l += 32) {
+                        const PvOwn o = load_own(oj, l);
+                        const uint32_t e = load_edge<A>(sj, l);
+                        const double pg = __ldcg(gj + l);
+                        __stcg(total_ptr<A>(bj, (int)(e >> 2), (int)(e & 3u)), __dadd_rn(o.total, pg));
+                        __stcg(na_ptr<A>(bj, (int)(e >> 2), (int)(e & 3u)), o.na + 1);
                     }
                     __syncwarp();
-                    if (lane == j) { level = event >= 0 ? event : Lj - 1; plen = 0; }
+                    if (lane == j) { level = r; plen = r; pend = false; }
                 }
-#pragma unroll
-                for (int k = 0; k < kLook; ++k) { cur[k] = nxt[k]; nxt[k] = nn[k]; }
             }
         }
 
@@ -367,7 +424,7 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
         bool fresh = false;  // block just allocated: all children unvisited, nothing to load
         double G = 0.0;
         if (mode == MODE_DESCEND && level > 0) {
-            const uint32_t prev = __ldcg(path_b + level - 1), here = __ldcg(path_b + level);
+            const uint32_t prev = load_edge<A>(pv_sib, level - 1), here = load_edge<A>(pv_sib, level);
             node_slot = (int)(prev >> 2) * A + (int)(prev & 3u);
             blk = (int)(here >> 2);
         }
@@ -421,8 +478,26 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
                         }
                         mode = MODE_RETURN;
                     } else {
-                        path_b[level] = ((uint32_t)blk << 2) | (uint32_t)a_sel;
+                        // this level joins the PV cache: own statistics + the siblings', as they are before the backup
+                        {
+                            PvSib<A> sb;
+                            sb.edge = ((uint32_t)blk << 2) | (uint32_t)a_sel;
+                            double ot = c.total[0]; int on_ = c.na[0];
+                            int k = 0;
+#pragma unroll
+                            for (int a = 0; a < A; ++a) {
+                                if (a == a_sel) { ot = c.total[a]; on_ = c.na[a]; }
+                                else {
+#pragma unroll
+                                    for (int q = 0; q < A - 1; ++q) if (q == k) { sb.total[q] = c.total[a]; sb.na[q] = c.na[a]; }
+                                    ++k;
+                                }
+                            }
+                            store_sib<A>(pv_sib, level, sb);
+                            store_own(pv_own, level, ot, on_);
+                        }
                         ++level;
+                        plen = level;
                         node_slot = blk * A + a_sel;
                         int nb = (int)(lk & kLinkBlockMask);
                         fresh = false;
@@ -515,22 +590,22 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
 
         // ------------------------------------------------------------------ phase 3: return pass
         // G_l = r + gamma * G_{l+1} up the recorded path (mcts_hash.py:126-131, 79-81).  The returns are only
-        // WRITTEN to the tree's path scratch; the next simulation's phase 1a applies them.
+        // WRITTEN to the tree's pending-return row; the next simulation's phase 1a adds them.
         if (mode == MODE_RETURN) {
             c_levels += (unsigned long long)level + 1ull;
             for (int l = level - 1; l >= 0; --l) {
                 G = __dadd_rn(kInterior, __dmul_rn(gamma, G));
                 path_g[l] = G;
             }
-            plen = level;
+            pend = level > 0;
             ++sims_done; ++s_done;
         }
         __syncwarp();
     }
 
     if (valid) {
-        // leave the tree consistent for the host / the next launch: scatter what is still pending
-        if (plen > 0) flush_pending(0);
+        // leave the tree consistent for the host / the next launch: the cached levels go back to their blocks
+        if (plen > 0) write_back(0);
         meta[META_ALLOC] = alloc;
         meta[META_SIMS] = (int32_t)sims_done;
         meta[META_RNG] = (int32_t)ts.consumed();
@@ -640,8 +715,9 @@ int tpt_fill_layout(const isla_config& cfg, isla_layout& lay) {
     lay.state_offset = off; lay.state_stride = lay.slots_per_tree * S * rb; off = up(off + cfg.n_trees * lay.state_stride);
     lay.gfirst_offset = off; lay.gfirst_stride = lay.slots_per_tree * 8; off = up(off + cfg.n_trees * lay.gfirst_stride);
     lay.meta_offset = off; off = up(off + cfg.n_trees * META_WORDS * 4);
-    lay.path_offset = off; off = up(off + cfg.n_trees * blocks * 4);
-    lay.pathg_offset = off; off = up(off + cfg.n_trees * blocks * 8);
+    lay.path_offset = off; off = up(off + cfg.n_trees * blocks * (A == 2 ? 16 : 48));   // PV cache, sibling half
+    lay.pathg_offset = off; off = up(off + cfg.n_trees * blocks * 8);                   // pending returns
+    lay.pvown_offset = off; off = up(off + cfg.n_trees * blocks * 16);                  // PV cache, own half
     lay.counters_offset = off; off = up(off + 8 * 8);
     add_table_layout(cfg, lay, off);
     lay.s_cap = lay.a_cap = 0; lay.pool_offset = lay.pool_stride = 0;
@@ -673,7 +749,8 @@ int tpt_run(isla_engine* e, int n_sim, long long scripted_tree, const uint8_t* k
     p.states = e->ws + L.state_offset;
     p.gfirst = (double*)(e->ws + L.gfirst_offset);
     p.meta = (int32_t*)(e->ws + L.meta_offset);
-    p.path_b = (uint32_t*)(e->ws + L.path_offset);
+    p.pv_sib = e->ws + L.path_offset;
+    p.pv_own = e->ws + L.pvown_offset;
     p.path_g = (double*)(e->ws + L.pathg_offset);
     p.counters = (unsigned long long*)(e->ws + L.counters_offset);
     p.trace_kinds = kinds; p.trace_values = values; p.trace_len = trace_len;
