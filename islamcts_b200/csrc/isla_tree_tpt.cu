@@ -347,15 +347,20 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
                     const char* sj = p.pv_sib + tj * path_cap * kSibBytes;
                     const double* gj = p.path_g + tj * path_cap;
                     int event = -1, done_upto = 0;
+                    double new_total = 0.0; int new_na = 0; uint32_t edge = 0u;
+                    // rounds are double-buffered: the entries of round r+1 are in flight while round r is evaluated
+                    PvOwn o_nx; PvSib<A> s_nx; double g_nx = 0.0;
+                    o_nx.total = 0.0; o_nx.na = 0; s_nx.edge = 0u;
+#pragma unroll
+                    for (int q = 0; q < A - 1; ++q) { s_nx.na[q] = 0; s_nx.total[q] = 0.0; }
+                    if (lane < Lj) { o_nx = load_own(oj, lane); s_nx = load_sib<A>(sj, lane); g_nx = __ldcg(gj + lane); }
                     for (int l0 = 0; l0 < Lj && event < 0; l0 += 32) {
                         const int l = l0 + lane;
                         const bool act = l < Lj;
+                        const PvOwn o = o_nx; const PvSib<A> sb = s_nx; const double pg = g_nx;
+                        if (l + 32 < Lj) { o_nx = load_own(oj, l + 32); s_nx = load_sib<A>(sj, l + 32); g_nx = __ldcg(gj + l + 32); }
                         bool my_event = false;
-                        double new_total = 0.0; int new_na = 0; uint32_t edge = 0u;
                         if (act) {
-                            const PvOwn o = load_own(oj, l);
-                            const PvSib<A> sb = load_sib<A>(sj, l);
-                            const double pg = __ldcg(gj + l);
                             edge = sb.edge;
                             const int pa = (int)(edge & 3u);
                             new_total = __dadd_rn(o.total, pg);   // lazy backup: the return of the previous simulation
@@ -386,8 +391,10 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
                         if (ev) event = l0 + __ffs(ev) - 1;
                         if (act) {
                             // levels before the event stay cached (with the return added); the event level and
-                            // everything deeper leave the cache: their statistics go back to the node blocks
-                            if (event < 0 || l < event) store_own(oj, l, new_total, new_na);
+                            // everything deeper leave the cache: their statistics go back to the node blocks.
+                            // Without an event the LAST level is handed over too (phase 1b re-decides it on its block).
+                            const bool leaves = (event >= 0 && l >= event) || (event < 0 && l == Lj - 1);
+                            if (!leaves) store_own(oj, l, new_total, new_na);
                             else {
                                 __stcg(total_ptr<A>(bj, (int)(edge >> 2), (int)(edge & 3u)), new_total);
                                 __stcg(na_ptr<A>(bj, (int)(edge >> 2), (int)(edge & 3u)), new_na);
@@ -396,15 +403,6 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
                         done_upto = min(l0 + 32, Lj);
                     }
                     const int r = event >= 0 ? event : Lj - 1;
-                    if (event < 0) {
-                        // no event: the last cached level is handed over too (phase 1b re-decides it on its block)
-                        if (((Lj - 1) & 31) == lane) {
-                            const PvOwn o = load_own(oj, Lj - 1);
-                            const uint32_t e = load_edge<A>(sj, Lj - 1);
-                            __stcg(total_ptr<A>(bj, (int)(e >> 2), (int)(e & 3u)), o.total);
-                            __stcg(na_ptr<A>(bj, (int)(e >> 2), (int)(e & 3u)), o.na);
-                        }
-                    }
                     // levels the verification did not reach leave the cache as well
                     for (int l = done_upto + lane; l < Lj; l += 32) {
                         const PvOwn o = load_own(oj, l);
