@@ -366,7 +366,7 @@ def other_configs(dev):
         def run():
             ret, st = E.rollout(env_id, None, n=n, budget=budget, gamma=gamma, seed=1234, sim=0, device=dev)
             steps.append(st)
-        t = timeit(run, reps=2)
+        t = timeit(run, reps=5)
         total = int(steps[-1].sum().item())
         out["rollout_" + name] = {"trajectories": n, "env_steps_per_s": total / t, "mean_len": total / n, "ms": t * 1e3,
                                   "fp32_roofline_frac": total / t * flop[env_id] / peak_fp32}

@@ -177,6 +177,24 @@ template <typename T> struct Env<ENV_FROZENLAKE, T> {
     }
 };
 
+// Reward structure.  Envs with kClosedForm pay a constant reward kInterior on every non-terminal step and 0/1 on the
+// terminal one; rollout_return() is then the value of `reward += r_t * pow(gamma, t)` (agents/abstract_mcts.py:87)
+// after n steps in closed form, bit-identical to the left-to-right float64 sum: CartPole pays 1 on every step
+// (host-accumulated prefix table `cum`), FrozenLake pays 0 until the last step (0.0 + ... + r * gamma**(n-1) is exact).
+template <int ENV> struct Rewards { static constexpr bool kClosedForm = false; };
+template <> struct Rewards<ENV_CARTPOLE> {
+    static constexpr bool kClosedForm = true;
+    static constexpr double kInterior = 1.0;
+    static __device__ __forceinline__ double rollout_return(int n, double, const double*, const double* cum) { return __ldg(cum + n); }
+};
+template <> struct Rewards<ENV_FROZENLAKE> {
+    static constexpr bool kClosedForm = true;
+    static constexpr double kInterior = 0.0;
+    static __device__ __forceinline__ double rollout_return(int n, double last_r, const double* disc, const double*) {
+        return n > 0 ? __dmul_rn(last_r, __ldg(disc + (n - 1))) : 0.0;
+    }
+};
+
 // gym reset distributions driven by the Philox reset stream (synthetic roots; bench + tests)
 template <int ENV, typename T>
 __device__ __forceinline__ void env_reset(uint64_t seed, uint32_t index, T (&s)[EnvTraits<ENV>::S]) {
@@ -204,7 +222,10 @@ __device__ __forceinline__ T sample_action(Stream& st) {
         env_action_bounds(ENV, lo, hi);
         return T(box_sample_f32(st.next(), lo, hi));
     } else {
-        return T(mulhi_u32(st.next(), (uint32_t)EnvTraits<ENV>::A));
+        constexpr int A = EnvTraits<ENV>::A;
+        if constexpr (A == 2) return T(st.next_bits(1));
+        else if constexpr (A == 4) return T(st.next_bits(2));
+        else return T(mulhi_u32(st.next(), (uint32_t)A));
     }
 }
 

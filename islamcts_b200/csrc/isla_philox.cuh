@@ -7,7 +7,8 @@
 //   tree stream    (blk, 0,   tree, 0x80000000)  selection / expansion / tie-break draws of one tree
 //   rollout stream (blk, sim, tree, j)           rollout j of simulation `sim` (cumulative index)
 //   reset stream   (0,   0,   idx,  0xC0000000)  synthetic root states
-// One 32-bit word per draw; discrete draws use the multiply-high map u*n>>32.
+// One 32-bit word per draw; discrete draws use the multiply-high map u*n>>32, except env.action_space.sample()
+// on a Discrete(2^k) space, which takes k bits (most significant first) from a 32-bit word of the stream.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -42,8 +43,11 @@ struct Stream {
     uint32_t k0, k1, c1, c2, c3, blk;
     uint32_t buf[4];
     int idx;
+    uint32_t bitbuf;  // reservoir of next_bits()
+    int bits_left;
     __device__ __forceinline__ void init(uint64_t seed, uint32_t c1_, uint32_t c2_, uint32_t c3_) {
         k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32); c1 = c1_; c2 = c2_; c3 = c3_; blk = 0; idx = 4;
+        bitbuf = 0u; bits_left = 0;
     }
     // resume a stream that has already consumed `consumed` words
     __device__ __forceinline__ void resume(uint64_t seed, uint32_t c1_, uint32_t c2_, uint32_t c3_, uint32_t consumed) {
@@ -58,6 +62,14 @@ struct Stream {
         // idx is 0..3: select without dynamic register indexing
         const uint32_t v = idx == 0 ? buf[0] : idx == 1 ? buf[1] : idx == 2 ? buf[2] : buf[3];
         ++idx;
+        return v;
+    }
+    // k bits (k divides 32), most significant first; a fresh word is drawn when the reservoir is empty
+    __device__ __forceinline__ uint32_t next_bits(int k) {
+        if (bits_left == 0) { bitbuf = next(); bits_left = 32; }
+        const uint32_t v = bitbuf >> (32 - k);
+        bitbuf <<= k;
+        bits_left -= k;
         return v;
     }
 };

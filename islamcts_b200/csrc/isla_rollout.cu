@@ -7,6 +7,8 @@
 // Roofline: FP32 issue rate (state never leaves registers; HBM traffic is one state read and one
 // 12-byte result write per trajectory).
 #include <cmath>
+#include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "isla_envs.cuh"
@@ -33,41 +35,103 @@ __global__ void env_step_kernel(const T* __restrict__ states, const T* __restric
     term[i] = t ? 1 : 0;
 }
 
+// One thread per trajectory, one launch-sized grid: for envs whose random episodes (almost) never end before the
+// budget (Pendulum, MountainCarContinuous) every lane runs the same number of steps and nothing is gained by refilling.
+template <int ENV, typename T>
+__global__ void __launch_bounds__(256) rollout_kernel_simple(const T* __restrict__ states, long long n, int budget,
+                                                             unsigned long long seed, unsigned sim,
+                                                             const double* __restrict__ disc_table, double* __restrict__ returns,
+                                                             int32_t* __restrict__ steps) {
+    constexpr int S = EnvTraits<ENV>::S;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    T s[S];
+    if (states) {
+#pragma unroll
+        for (int k = 0; k < S; ++k) s[k] = states[i * S + k];
+    } else {
+        env_reset<ENV, T>(seed, (uint32_t)i, s);
+    }
+    Stream rs;
+    rs.init(seed, sim, (uint32_t)i, 0u);
+    double R = 0.0;
+    bool done = false;
+    int t = 0;
+    while (!done && t < budget) {
+        const T a = sample_action<ENV, T>(rs);
+        T r;
+        done = Env<ENV, T>::step(s, a, r);
+        R = __dadd_rn(R, __dmul_rn((double)r, __ldg(disc_table + t)));  // r * pow(gamma, t), host libm pow
+        ++t;
+    }
+    returns[i] = R;
+    steps[i] = t;
+}
+
+// Persistent warps with lane refill: random-policy episodes have random lengths (CartPole: mean 22 steps, maximum over a
+// warp ~56), so a lane that finishes claims the next trajectory instead of idling.  Refills are batched (>= kRefillMin
+// idle lanes, warp-aggregated atomic) so that the refill code does not run in every iteration.
+constexpr int kRefillMin = 12;
+
 template <int ENV, typename T>
 __global__ void __launch_bounds__(256) rollout_kernel(const T* __restrict__ states, long long n, int budget, double gamma,
                                                       unsigned long long seed, unsigned sim, const double* __restrict__ disc_table,
-                                                      double* __restrict__ returns, int32_t* __restrict__ steps,
-                                                      unsigned long long* __restrict__ total_steps) {
+                                                      const double* __restrict__ cum_table, double* __restrict__ returns,
+                                                      int32_t* __restrict__ steps, unsigned long long* __restrict__ next) {
     constexpr int S = EnvTraits<ENV>::S;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int t = 0;
-    if (i < n) {
-        T s[S];
-        if (states) {
+    constexpr unsigned kFull = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    long long idx = -1;
+    bool active = false, exhausted = false;
+    T s[S];
 #pragma unroll
-            for (int k = 0; k < S; ++k) s[k] = states[i * S + k];
-        } else {
-            env_reset<ENV, T>(seed, (uint32_t)i, s);
+    for (int k = 0; k < S; ++k) s[k] = T(0);
+    Stream rs;
+    rs.init(seed, sim, 0u, 0u);
+    int t = 0;
+    double R = 0.0;
+    T last_r = T(0);
+    for (;;) {
+        const unsigned idle = __ballot_sync(kFull, !active);
+        if (!exhausted && (idle == kFull || __popc(idle) >= kRefillMin)) {
+            const int nidle = __popc(idle);
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(next, (unsigned long long)nidle);  // warp-aggregated claim
+            base = __shfl_sync(kFull, base, 0);
+            if (!active) {
+                const long long mine = (long long)base + __popc(idle & ((1u << lane) - 1u));
+                if (mine < n) {
+                    idx = mine;
+                    if (states) {
+#pragma unroll
+                        for (int k = 0; k < S; ++k) s[k] = states[idx * S + k];
+                    } else {
+                        env_reset<ENV, T>(seed, (uint32_t)idx, s);
+                    }
+                    rs.init(seed, sim, (uint32_t)idx, 0u);
+                    t = 0; R = 0.0; last_r = T(0);
+                    active = true;
+                }
+            }
+            exhausted = (long long)base + nidle >= n;
         }
-        Stream rs;
-        rs.init(seed, sim, (uint32_t)i, 0u);
-        double R = 0.0;
-        bool done = false;
-        while (!done && t < budget) {
-            const T a = sample_action<ENV, T>(rs);
-            T r;
-            done = Env<ENV, T>::step(s, a, r);
-            R = __dadd_rn(R, __dmul_rn((double)r, __ldg(disc_table + t)));  // r * pow(gamma, t), host libm pow
-            ++t;
+        if (__ballot_sync(kFull, active) == 0u) break;
+        if (active) {
+            bool fin = t >= budget;
+            if (!fin) {
+                const T a = sample_action<ENV, T>(rs);
+                const bool done = Env<ENV, T>::step(s, a, last_r);
+                if constexpr (!Rewards<ENV>::kClosedForm) R = __dadd_rn(R, __dmul_rn((double)last_r, __ldg(disc_table + t)));  // r * pow(gamma, t)
+                ++t;
+                fin = done || t >= budget;
+            }
+            if (fin) {
+                if constexpr (Rewards<ENV>::kClosedForm) R = Rewards<ENV>::rollout_return(t, (double)last_r, disc_table, cum_table);
+                returns[idx] = R;
+                steps[idx] = t;
+                active = false;
+            }
         }
-        returns[i] = R;
-        steps[i] = t;
-    }
-    if (total_steps) {
-        // block-level sum of executed steps -> one atomic per warp
-        unsigned v = (unsigned)t;
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if ((threadIdx.x & 31) == 0 && v) atomicAdd(total_steps, (unsigned long long)v);
     }
 }
 
@@ -85,27 +149,68 @@ int env_step_dispatch(int env, const void* s, const void* a, long long n, void* 
     return 0;
 }
 
+// gamma**t and its left-to-right prefix sums from the host libm (CPython's pow, agents/abstract_mcts.py:87).  The
+// device copies are cached per (device, gamma, length): later calls enqueue no copy and do not synchronise.
+struct DiscTables { int dev; double gamma; size_t m; double* ptr; };
+static std::mutex g_tab_mu;
+static std::vector<DiscTables> g_tabs;
+
+static int get_tables(double gamma, int budget, const double** disc, const double** cum) {
+    int dev = 0;
+    ISLA_CUDA_OK(cudaGetDevice(&dev));
+    const size_t m = (size_t)(budget > 0 ? budget : 1) + 1;
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    for (const DiscTables& t : g_tabs)
+        if (t.dev == dev && t.m >= m && std::memcmp(&t.gamma, &gamma, sizeof gamma) == 0) { *disc = t.ptr; *cum = t.ptr + t.m; return 0; }
+    std::vector<double> h(2 * m);
+    double acc = 0.0;
+    for (size_t t = 0; t < m; ++t) { h[t] = std::pow(gamma, (double)t); h[m + t] = acc; acc = acc + 1.0 * h[t]; }
+    double* p = nullptr;
+    ISLA_CUDA_OK(cudaMalloc((void**)&p, h.size() * 8));
+    ISLA_CUDA_OK(cudaMemcpy(p, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
+    ISLA_CUDA_OK(cudaDeviceSynchronize());
+    g_tabs.push_back(DiscTables{dev, gamma, m, p});
+    *disc = p; *cum = p + m;
+    return 0;
+}
+
+template <int ENV, typename T>
+int rollout_launch(const void* s, long long n, int budget, double gamma, unsigned long long seed, unsigned sim,
+                   const double* disc, const double* cum, double* ret, int32_t* steps, int sms, cudaStream_t st) {
+    if constexpr (Rewards<ENV>::kClosedForm) {
+        // random episode lengths: persistent grid (SM count x 6 resident CTAs of 256 threads at 40 registers), lane refill
+        const long long want = (n + 255) / 256;
+        const unsigned grid = (unsigned)(want < (long long)sms * 6 ? want : (long long)sms * 6);
+        unsigned long long* next = nullptr;
+        ISLA_CUDA_OK(cudaMallocAsync((void**)&next, 8, st));
+        ISLA_CUDA_OK(cudaMemsetAsync(next, 0, 8, st));
+        rollout_kernel<ENV, T><<<grid, 256, 0, st>>>((const T*)s, n, budget, gamma, seed, sim, disc, cum, ret, steps, next);
+        ISLA_CUDA_OK(cudaGetLastError());
+        ISLA_CUDA_OK(cudaFreeAsync(next, st));
+    } else {
+        rollout_kernel_simple<ENV, T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const T*)s, n, budget, seed, sim, disc, ret, steps);
+        ISLA_CUDA_OK(cudaGetLastError());
+    }
+    return 0;
+}
+
 template <typename T>
 int rollout_dispatch(int env, const void* s, long long n, int budget, double gamma, unsigned long long seed, unsigned sim,
                      double* ret, int32_t* steps, cudaStream_t st) {
-    const unsigned grid = (unsigned)((n + 255) / 256);
-    // gamma**t table from the host libm (CPython's pow, agents/abstract_mcts.py:87), stream-ordered scratch
-    std::vector<double> h((size_t)(budget > 0 ? budget : 1));
-    for (size_t t = 0; t < h.size(); ++t) h[t] = std::pow(gamma, (double)t);
-    double* disc = nullptr;
-    ISLA_CUDA_OK(cudaMallocAsync((void**)&disc, h.size() * 8, st));
-    ISLA_CUDA_OK(cudaMemcpyAsync(disc, h.data(), h.size() * 8, cudaMemcpyHostToDevice, st));
-    ISLA_CUDA_OK(cudaStreamSynchronize(st));  // h is pageable host memory
+    int dev = 0, sms = 148;
+    ISLA_CUDA_OK(cudaGetDevice(&dev));
+    ISLA_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const double *disc = nullptr, *cum = nullptr;
+    const int rc = get_tables(gamma, budget, &disc, &cum);
+    if (rc) return rc;
     switch (env) {
-    case ENV_CARTPOLE: rollout_kernel<ENV_CARTPOLE, T><<<grid, 256, 0, st>>>((const T*)s, n, budget, gamma, seed, sim, disc, ret, steps, nullptr); break;
-    case ENV_PENDULUM: rollout_kernel<ENV_PENDULUM, T><<<grid, 256, 0, st>>>((const T*)s, n, budget, gamma, seed, sim, disc, ret, steps, nullptr); break;
-    case ENV_MOUNTAINCAR: rollout_kernel<ENV_MOUNTAINCAR, T><<<grid, 256, 0, st>>>((const T*)s, n, budget, gamma, seed, sim, disc, ret, steps, nullptr); break;
-    case ENV_FROZENLAKE: rollout_kernel<ENV_FROZENLAKE, T><<<grid, 256, 0, st>>>((const T*)s, n, budget, gamma, seed, sim, disc, ret, steps, nullptr); break;
-    default: cudaFreeAsync(disc, st); set_error("unknown env %d", env); return ISLA_ERR_INVALID;
+    case ENV_CARTPOLE: return rollout_launch<ENV_CARTPOLE, T>(s, n, budget, gamma, seed, sim, disc, cum, ret, steps, sms, st);
+    case ENV_PENDULUM: return rollout_launch<ENV_PENDULUM, T>(s, n, budget, gamma, seed, sim, disc, cum, ret, steps, sms, st);
+    case ENV_MOUNTAINCAR: return rollout_launch<ENV_MOUNTAINCAR, T>(s, n, budget, gamma, seed, sim, disc, cum, ret, steps, sms, st);
+    case ENV_FROZENLAKE: return rollout_launch<ENV_FROZENLAKE, T>(s, n, budget, gamma, seed, sim, disc, cum, ret, steps, sms, st);
     }
-    ISLA_CUDA_OK(cudaGetLastError());
-    ISLA_CUDA_OK(cudaFreeAsync(disc, st));
-    return 0;
+    set_error("unknown env %d", env);
+    return ISLA_ERR_INVALID;
 }
 
 }  // namespace

@@ -44,22 +44,6 @@ constexpr int kRing = 8;        // path entries are staged this many levels ahea
 constexpr int kBlockAhead = 4; // node blocks are prefetched into L2 this many levels ahead
 constexpr unsigned kFull = 0xffffffffu;
 
-// Reward structure of the envs this kernel supports (checked at expansion time)
-template <int ENV> struct Rewards;
-// rollout_return(): the value of `reward += r_t * pow(gamma, t)` (abstract_mcts.py:87) after n steps, in closed
-// form and bit-identical to the left-to-right float64 sum: CartPole pays 1 on every step (host-accumulated
-// prefix table), FrozenLake pays 0 until the last step (0.0 + ... + r * gamma**(n-1) is exact).
-template <> struct Rewards<ENV_CARTPOLE> {
-    static constexpr double kInterior = 1.0;
-    static __device__ __forceinline__ double rollout_return(int n, double, const double*, const double* cum) { return __ldg(cum + n); }
-};
-template <> struct Rewards<ENV_FROZENLAKE> {
-    static constexpr double kInterior = 0.0;
-    static __device__ __forceinline__ double rollout_return(int n, double last_r, const double* disc, const double*) {
-        return n > 0 ? __dmul_rn(last_r, __ldg(disc + (n - 1))) : 0.0;
-    }
-};
-
 struct TraceCursor {
     const uint8_t* k;
     const double* v;

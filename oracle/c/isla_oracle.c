@@ -47,15 +47,23 @@ typedef struct {
     uint32_t blk;                /* c0: block counter */
     uint32_t buf[4];
     int idx;
+    uint32_t bitbuf; int bits_left; /* reservoir of stream_bits() */
 } stream_t;
 
 static void stream_init(stream_t* s, uint64_t seed, uint32_t c1, uint32_t c2, uint32_t c3) {
     s->k0 = (uint32_t)seed; s->k1 = (uint32_t)(seed >> 32);
-    s->c1 = c1; s->c2 = c2; s->c3 = c3; s->blk = 0; s->idx = 4;
+    s->c1 = c1; s->c2 = c2; s->c3 = c3; s->blk = 0; s->idx = 4; s->bitbuf = 0; s->bits_left = 0;
 }
 static uint32_t stream_u32(stream_t* s) {
     if (s->idx == 4) { orc_philox4x32(s->blk++, s->c1, s->c2, s->c3, s->k0, s->k1, s->buf); s->idx = 0; }
     return s->buf[s->idx++];
+}
+/* k bits (k divides 32), most significant first */
+static uint32_t stream_bits(stream_t* s, int k) {
+    if (s->bits_left == 0) { s->bitbuf = stream_u32(s); s->bits_left = 32; }
+    uint32_t v = s->bitbuf >> (32 - k);
+    s->bitbuf <<= k; s->bits_left -= k;
+    return v;
 }
 #define STREAM_TREE  0x80000000u
 #define STREAM_RESET 0xC0000000u
@@ -243,6 +251,9 @@ static double rnd_action(orc_tree* t, stream_t* st) {
             if (a < 0 || a >= nd) { if (!t->fault) t->fault = -3; return 0; }
             return a;
         }
+        /* Discrete(2) / Discrete(4): 1 / 2 bits of a stream word, most significant first */
+        if (nd == 2) return (double)stream_bits(st, 1);
+        if (nd == 4) return (double)stream_bits(st, 2);
         return (double)mulhi32(stream_u32(st), (uint32_t)nd);
     }
     if (scripted(t)) return (double)(float)trace_next(t, ORC_K_SAMPLE_C);
