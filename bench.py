@@ -375,6 +375,10 @@ def other_configs(dev):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner) are sent to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -10,24 +10,22 @@
 //   backup      the recursion unwind             mcts_hash.py:79-81,119-131
 //
 // B200-first design instead of the reference's object-per-node recursion:
-//   * Device tree = node blocks in HBM (isla_internal.h): the A edges of one state node are ONE
-//     32-byte sector (A=2) / 64 bytes (A=4); an edge's link word carries the block of the child, so a
-//     tree level costs one dependent 32 B load.  States and creation returns are cold side arrays.
-//   * Lazy backup.  Consecutive simulations share 99.7 % of their path (measured, CartPole C5).  The
-//     returns G_l of simulation s are therefore NOT scattered back with atomics; they are written to a
-//     compact level-major scratch and applied by simulation s+1 while it holds each block anyway: the
-//     block is read once and written once per simulation.  Where the new path leaves the old one, the
-//     rest of the old path is flushed with fire-and-forget RED atomics (rare).  The decisions are the
-//     same as with an eager backup: every block on the path sees its pending update before its UCB scan.
-//   * Path-predicted prefetch.  The old path also tells where the next descent will go: its entries
-//     stream through a shared-memory ring filled by cp.async (LDGSTS) eight levels ahead, and the node
-//     block four levels ahead is prefetched into L2, turning the serial DRAM misses of the pointer
-//     chase into pipelined ones.
-//   * Lanes of a warp walk converged phases (descent / expand+rollout / return pass) so that the SIMT
-//     width is not lost to divergence.
-//   * Visit counts and totals are exact: int32 counts, float64 totals, UCB decisions are the float64
-//     ones (fp32 screening settles only unambiguous arg-maxes), ln(n) and gamma^t come from host libm
-//     tables.  Env state and rollouts live in registers; Philox4x32-10 replaces numpy/gym RNGs.
+//   * Device tree = node blocks in HBM (isla_internal.h): the A edges of one state node are ONE 32-byte sector
+//     (A=2) / 64 bytes (A=4); an edge's link word carries the block of the child.  States and creation returns
+//     are cold side arrays.
+//   * PV cache + lazy backup.  Consecutive simulations share 99.7 % of their path (measured, CartPole C5).  The
+//     statistics of the path's edges therefore live in sequential per-tree rows (own 16 B + siblings 16 B + pending
+//     return 8 B per level); the returns G_l of simulation s are added by simulation s+1 when it re-evaluates the
+//     level, and the node blocks are only touched where the path changes.  Every level sees exactly the statistics
+//     an eager backup would have produced, so the decisions are those of the sequential algorithm.
+//   * Cooperative verification.  A warp owns 32 trees; for each tree in turn its 32 lanes re-evaluate UCB1 on 32
+//     consecutive LEVELS of the cached path and ballot whether the decisions stand -- a dependent pointer chase of
+//     ~180 levels becomes ~6 coalesced rounds.  Only the tail (first changed decision, tie-break draws, expansion)
+//     is walked serially on the node blocks, lock-step across the warp's trees.
+//   * Visit counts and totals are exact: int32 counts, float64 totals, UCB decisions are the float64 ones (fp32
+//     screening settles only unambiguous arg-maxes), ln(n) and gamma^t come from host libm tables.  Env state and
+//     rollouts live in registers; Philox4x32-10 replaces numpy/gym RNGs.
+// tuning bits (A/B timing only): 1 = no fp32 screening, 8 = no L2 prefetch of the next tree's rows.
 #include <cmath>
 #include <cstring>
 
@@ -40,8 +38,6 @@ namespace isla {
 namespace {
 
 constexpr int kTptBlock = 64;
-constexpr int kRing = 8;        // path entries are staged this many levels ahead (cp.async ring)
-constexpr int kBlockAhead = 4; // node blocks are prefetched into L2 this many levels ahead
 constexpr unsigned kFull = 0xffffffffu;
 
 struct TraceCursor {
@@ -64,26 +60,13 @@ template <int A> struct NodeBlock {
 };
 static_assert(sizeof(NodeBlock<2>) == 32 && sizeof(NodeBlock<4>) == 64, "node block is one or two sectors");
 
-__device__ __forceinline__ int4 ldcg_line(const int4* p) {
-    // L2-only load that asks L2 to fetch the whole 128-byte line on a miss: the blocks of the principal
-    // variation are allocated consecutively, so the next levels' blocks usually share the line, and one
-    // 128-byte DRAM access replaces up to four row-missing 32-byte ones
-    int4 v;
-    asm volatile("ld.global.cg.L2::128B.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ void touch_line(const void* p) {
-    int v;
-    asm volatile("ld.global.cg.L2::128B.s32 %0, [%1];" : "=r"(v) : "l"(p));
-}
-
-template <int A, bool LINE = false>
+template <int A>
 __device__ __forceinline__ NodeBlock<A> load_block(const char* base, int blk) {
     // L2-only loads (ld.global.cg): blocks are also updated by RED atomics at L2
     NodeBlock<A> b;
     const int4* p = reinterpret_cast<const int4*>(base + (long long)blk * (A * 16));
     if constexpr (A == 2) {
-        const int4 lo = LINE ? ldcg_line(p) : __ldcg(p), hi = __ldcg(p + 1);
+        const int4 lo = __ldcg(p), hi = __ldcg(p + 1);
         b.total[0] = __hiloint2double(lo.y, lo.x); b.total[1] = __hiloint2double(lo.w, lo.z);
         b.na[0] = hi.x; b.na[1] = hi.y; b.link[0] = (uint32_t)hi.z; b.link[1] = (uint32_t)hi.w;
     } else {
@@ -105,14 +88,6 @@ template <int A> __device__ __forceinline__ uint32_t* link_ptr(char* base, int b
     return reinterpret_cast<uint32_t*>(base + (long long)blk * (A * 16) + A * 12) + a;
 }
 
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 enum : int { MODE_DESCEND = 0, MODE_EXPAND = 1, MODE_RETURN = 2, MODE_IDLE = 3 };
@@ -417,7 +392,7 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
 #pragma unroll
                     for (int a = 0; a < A; ++a) { c.total[a] = 0.0; c.na[a] = 0; c.link[a] = 0u; }
                 } else {
-                    c = load_block<A, false>(blocks, blk);
+                    c = load_block<A>(blocks, blk);
                 }
                 int nun = 0;
 #pragma unroll

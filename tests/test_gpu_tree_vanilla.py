@@ -140,3 +140,36 @@ def test_merge_root_stats_matches_numpy():
     np.add.at(etot, grp.cpu().numpy(), tot.cpu().numpy())
     np.testing.assert_array_equal(mna.cpu().numpy(), ena)
     np.testing.assert_allclose(mtot.cpu().numpy(), etot, rtol=1e-12, atol=1e-12)
+
+
+def test_edge_cases_partial_warps_tiny_runs_and_trace_faults():
+    """Ragged / degenerate inputs: tree counts that are not a multiple of the warp or CTA size (the cooperative
+    phase walks 32 trees per warp), n_sim = 0 and 1, max_depth = 0 (no rollout at all), a truncated trace."""
+    from islamcts_b200.engine import Engine
+    for n_trees in (1, 33, 70):
+        roots = np.stack([coracle.env_reset(0, 2, i) for i in range(n_trees)])
+        eng = Engine(0, n_trees=n_trees, sim_capacity=160, max_depth=300, C_=1.0, gamma=0.99, precision=1, kernel=1, seed=8)
+        eng.set_roots(roots).run(0)
+        assert eng.counters()["sims"] == 0
+        eng.run(1).run(159)                      # deep enough for the cooperative phase (paths > 16 levels)
+        na, tot = eng.root_stats()
+        cfg = coracle.make_config(0, n_actions=2, max_depth=300, C_=1.0, gamma=0.99, seed=8)
+        ena, etot, ecnt = coracle.run_many(cfg, roots, 160, n_threads=4)
+        np.testing.assert_array_equal(na.cpu().numpy(), ena)
+        np.testing.assert_allclose(tot.cpu().numpy(), etot, rtol=1e-9, atol=1e-9)
+        c = eng.counters()
+        assert c["faults"] == 0 and c["levels"] == ecnt["levels"] and c["sims"] == n_trees * 160
+    # max_depth = 0: every leaf is evaluated by its step reward only
+    roots = np.stack([coracle.env_reset(0, 2, i) for i in range(40)])
+    eng = Engine(0, n_trees=40, sim_capacity=64, max_depth=0, C_=1.0, gamma=0.9, precision=1, kernel=1, seed=8)
+    eng.set_roots(roots).run(64)
+    assert eng.counters()["rollout_steps"] == 0
+    cfg = coracle.make_config(0, n_actions=2, max_depth=0, C_=1.0, gamma=0.9, seed=8)
+    ena, etot, _ = coracle.run_many(cfg, roots, 64, n_threads=4)
+    np.testing.assert_array_equal(eng.root_stats()[0].cpu().numpy(), ena)
+    # a truncated decision trace is reported, not silently ignored
+    g = load_golden("hash_cartpole")
+    eng = _engine_from_golden(g, 1, kernel=1)
+    eng.set_roots(g["root_state"][None, :])
+    eng.run_scripted(0, g["config"]["n_sim"], g["trace_kind"][:500], g["trace_value"][:500])
+    assert eng.tree_meta(0)["fault"] == -4 and eng.counters()["faults"] == 1
