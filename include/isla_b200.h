@@ -98,6 +98,7 @@ typedef struct {
     /* CTA-per-tree (general) pools, offsets of the per-tree blocks and their strides */
     int64_t s_cap, a_cap;                   /* state / action node capacity per tree */
     int64_t pool_offset, pool_stride;       /* bytes per tree of the general node pool */
+    int64_t hash_offset, hash_cap;          /* apw/dpw: per-tree action hash set, hash_cap 16-byte entries per tree (0 = none) */
     int64_t total_bytes;
 } isla_layout;
 

@@ -50,7 +50,8 @@ class IslaLayout(C.Structure):
         ("counters_offset", C.c_int64), ("ln_offset", C.c_int64), ("ln_count", C.c_int64),
         ("disc_offset", C.c_int64), ("disc_count", C.c_int64), ("pw1_offset", C.c_int64), ("pw2_offset", C.c_int64), ("cumdisc_offset", C.c_int64),
         ("s_cap", C.c_int64), ("a_cap", C.c_int64),
-        ("pool_offset", C.c_int64), ("pool_stride", C.c_int64), ("total_bytes", C.c_int64),
+        ("pool_offset", C.c_int64), ("pool_stride", C.c_int64), ("hash_offset", C.c_int64), ("hash_cap", C.c_int64),
+        ("total_bytes", C.c_int64),
     ]
 
 

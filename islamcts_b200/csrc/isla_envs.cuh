@@ -137,6 +137,48 @@ template <typename T> struct Env<ENV_PENDULUM, T> {
     }
 };
 
+// Fast float32 Pendulum / MountainCar (rollout inner loops).  The trigonometric argument is first reduced to
+// [-pi, pi] with a two-constant Cody-Waite step, where the hardware approximation (MUFU) has an absolute error
+// below 5e-7; everything else follows the float64 definition.  Within 1e-5 relative of it (tests/test_gpu_envs.py).
+__device__ __forceinline__ float reduce_pi(float x) {
+    const float k = rintf(x * 0.15915494309189535f);           // x / (2 pi)
+    return fmaf(k, -1.7484556e-7f, fmaf(k, -6.2831855f, x));     // x - k * 2pi, 2pi = 6.2831855 + (-1.7484556e-7)
+}
+template <> struct Env<ENV_PENDULUM, float> {
+    static __device__ __forceinline__ bool step(float (&s)[2], float action, float& reward) {
+        constexpr float max_speed = 8.0f, max_torque = 2.0f, dt = 0.05f, pi = 3.14159265358979f, two_pi = 6.28318530717959f;
+        const float th = s[0], thdot = s[1];
+        const float u = fminf(fmaxf(action, -max_torque), max_torque);
+        float ang = fmodf(th + pi, two_pi);
+        if (ang < 0.f) ang += two_pi;
+        ang -= pi;
+        const float costs = ang * ang + 0.1f * (thdot * thdot) + 0.001f * (u * u);
+        float newthdot = thdot + (15.0f * __sinf(reduce_pi(th)) + 3.0f * u) * dt;
+        newthdot = fminf(fmaxf(newthdot, -max_speed), max_speed);
+        s[0] = th + newthdot * dt;
+        s[1] = newthdot;
+        reward = -costs;
+        return false;
+    }
+};
+template <> struct Env<ENV_MOUNTAINCAR, float> {
+    static __device__ __forceinline__ bool step(float (&s)[2], float action, float& reward) {
+        constexpr float min_position = -1.2f, max_position = 0.6f, max_speed = 0.07f, goal_position = 0.45f, power = 0.0015f;
+        float position = s[0], velocity = s[1];
+        const float force = fminf(fmaxf(action, -1.0f), 1.0f);
+        velocity += force * power - 0.0025f * __cosf(reduce_pi(3.0f * position));
+        velocity = fminf(fmaxf(velocity, -max_speed), max_speed);
+        position += velocity;
+        position = fminf(fmaxf(position, min_position), max_position);
+        if (position == min_position && velocity < 0.f) velocity = 0.f;
+        const bool term = (position >= goal_position) && (velocity >= 0.f);
+        reward = (term ? 100.0f : 0.0f) - (action * action) * 0.1f;
+        s[0] = position;
+        s[1] = velocity;
+        return term;
+    }
+};
+
 template <typename T> struct Env<ENV_MOUNTAINCAR, T> {
     using A_ = Ar<T>;
     static __device__ __forceinline__ bool step(T (&s)[2], T action, T& reward) {

@@ -61,6 +61,7 @@ struct CtaParams {
     int ln_count, disc_count;
     int n_sim, max_depth, budget_mode, agent, n_actions, R, expansion, voo_n, voo_max_try, real_bytes;
     int pool_in_smem;  // the whole tree pool fits in shared memory: search there, copy back at the end
+    char* hash_base; long long hash_cap;  // per-tree action hash set (apw/dpw): hash_cap int4 entries per tree, 0 = none
 };
 
 enum : int { O_S_TOTAL = 0, O_S_TERMR, O_S_NS, O_S_FLAGS, O_S_COFF, O_S_CCAP, O_S_CCNT, O_S_STATE, O_A_TOTAL, O_A_VALUE,
@@ -115,9 +116,11 @@ struct Search {
     Stream ts;
     Cursor tc;
     uint32_t tree_id;
+    char* hash;  // this tree's action hash set (apw/dpw), HBM
     unsigned long long c_env = 0, c_roll = 0, c_levels = 0, c_nodes = 0;
 
     __device__ Search(const CtaParams& p_, long long tree, char* pool_bytes) : p(p_), q(make_pool_at(p_, pool_bytes)) {
+        hash = p.hash_base + tree * p.hash_cap * 16;
         lane = threadIdx.x & 31;
         nS = q.meta[CM_NS]; nA = q.meta[CM_NA]; itop = q.meta[CM_ITOP]; fault = q.meta[CM_FAULT];
         tree_id = (uint32_t)(p.tree_id_base + (unsigned long long)tree);
@@ -209,6 +212,17 @@ struct Search {
             const double na = (double)q.a_na[a];
             return __dadd_rn(__ddiv_rn(q.a_total[a], na), __dmul_rn(p.C, __dsqrt_rn(__ddiv_rn(lg, na))));
         };
+        if (n <= 32) {
+            // narrow node (vanilla, spw, young pw nodes): one score per lane, one max, one ballot
+            const double mine = lane < n ? score(lane) : -INFINITY;
+            const double top = warp_max(mine);
+            const unsigned b = __ballot_sync(kFull, lane < n && mine == top);
+            const int nt = __popc(b);
+            int pos = (SCRIPTED || nt > 1) ? choice(nt) : 0;
+            unsigned bb = b;
+            for (int k = 0; k < pos; ++k) bb &= bb - 1;
+            return __ffs(bb) - 1;
+        }
         double best = -INFINITY;
         for (int i = lane; i < n; i += 32) best = fmax(best, score(i));
         best = warp_max(best);
@@ -239,8 +253,40 @@ struct Search {
         return pick;
     }
 
-    // actions.get(action.tobytes()): rank of the child with the same bits, or -1
+    // actions.get(action.tobytes()) through the per-tree hash set {action bits, state node} -> rank in the state's child
+    // array (open addressing, linear probing; capacity is a power of two >= 2 x action capacity).  Replaces an O(n)
+    // scan of the children, which dominated wide progressive-widening roots (C3: 10 000 children).
+    __device__ __forceinline__ unsigned long long hash_slot(int s, long long bits) const {
+        unsigned long long h = (unsigned long long)bits * 0x9E3779B97F4A7C15ull;
+        h ^= (unsigned long long)(unsigned)s * 0xC2B2AE3D27D4EB4Full;
+        h ^= h >> 29;
+        return h & (unsigned long long)(p.hash_cap - 1);
+    }
     __device__ int find_action(int s, double value) {
+        if (p.hash_cap == 0) return find_action_scan(s, value);
+        const long long want = __double_as_longlong(value);
+        unsigned long long h = hash_slot(s, want);
+        for (;;) {
+            const int4 e = reinterpret_cast<const int4*>(hash)[h];   // {bits lo, bits hi, state, rank}
+            if (e.z < 0) return -1;
+            if (e.z == s && e.x == (int)(unsigned)(want & 0xffffffffll) && e.y == (int)(want >> 32)) return e.w;
+            h = (h + 1) & (unsigned long long)(p.hash_cap - 1);
+        }
+    }
+    // record (state, action bits) -> rank; an existing key is overwritten (dpw replaces the node under the same key)
+    __device__ void hash_put(int s, double value, int rank) {
+        if (p.hash_cap == 0) return;
+        const long long bits = __double_as_longlong(value);
+        unsigned long long h = hash_slot(s, bits);
+        for (;;) {
+            const int4 e = reinterpret_cast<const int4*>(hash)[h];
+            if (e.z < 0 || (e.z == s && e.x == (int)(unsigned)(bits & 0xffffffffll) && e.y == (int)(bits >> 32))) break;
+            h = (h + 1) & (unsigned long long)(p.hash_cap - 1);
+        }
+        if (lane == 0) reinterpret_cast<int4*>(hash)[h] = make_int4((int)(unsigned)(bits & 0xffffffffll), (int)(bits >> 32), s, rank);
+        __syncwarp();
+    }
+    __device__ int find_action_scan(int s, double value) {
         const int off = q.s_coff[s], n = q.s_ccnt[s];
         const long long want = __double_as_longlong(value);
         int found = -1;
@@ -402,11 +448,11 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                         const int old = ctx.find_action(s, val);
                         if (p.agent == ISLA_AGENT_APW) {
                             if (old >= 0) a = q.ipool[q.s_coff[s] + old];                  // reuse (:66-70)
-                            else { a = ctx.new_action(val); ctx.append_action(s, a); }
+                            else { a = ctx.new_action(val); ctx.append_action(s, a); ctx.hash_put(s, val, q.s_ccnt[s] - 1); }
                         } else {
                             a = ctx.new_action(val);                                      // always a new node (:58-60)
                             if (old >= 0) { if (lane == 0) q.ipool[q.s_coff[s] + old] = a; __syncwarp(); }
-                            else ctx.append_action(s, a);
+                            else { ctx.append_action(s, a); ctx.hash_put(s, val, q.s_ccnt[s] - 1); }
                         }
                     } else {
                         a_rank = ctx.ucb_pick(s);
@@ -670,6 +716,21 @@ __global__ void cta_best_kernel(const CtaParams p, int scripted_pos, int32_t* be
             }
             q.ipool[off + y] = cur;
         }
+        if (p.hash_cap > 0) {  // the ranks stored in the action hash set follow the new order
+            int4* hash = reinterpret_cast<int4*>(p.hash_base + tree * p.hash_cap * 16);
+            for (int i = 0; i < n; ++i) {
+                const long long bits = __double_as_longlong(q.a_value[q.ipool[off + i]]);
+                unsigned long long h = (unsigned long long)bits * 0x9E3779B97F4A7C15ull;
+                h ^= h >> 29;  // state 0: the state term of Search::hash_slot vanishes
+                h &= (unsigned long long)(p.hash_cap - 1);
+                for (;;) {
+                    const int4 e = hash[h];
+                    if (e.z < 0) break;
+                    if (e.z == 0 && e.x == (int)(unsigned)(bits & 0xffffffffll) && e.y == (int)(bits >> 32)) { hash[h].w = i; break; }
+                    h = (h + 1) & (unsigned long long)(p.hash_cap - 1);
+                }
+            }
+        }
     }
     double qmax = -INFINITY;
     for (int i = 0; i < n; ++i) { const int a = q.ipool[off + i]; qmax = fmax(qmax, __ddiv_rn(q.a_total[a], (double)q.a_na[a])); }
@@ -731,6 +792,7 @@ CtaParams make_params(const isla_engine* e) {
     p.expansion = e->cfg.expansion; p.voo_n = e->cfg.voo_n_samples; p.voo_max_try = e->cfg.voo_max_try; p.real_bytes = rb;
     // 227 KB per CTA minus the static rollout-reduction buffer and bookkeeping
     p.pool_in_smem = (off <= 190 * 1024 && !(e->cfg.tuning & 16)) ? 1 : 0;
+    p.hash_base = e->ws ? e->ws + L.hash_offset : nullptr; p.hash_cap = L.hash_cap;
     return p;
 }
 
@@ -738,7 +800,7 @@ long long pool_bytes(const isla_config& cfg, long long s_cap, long long a_cap, i
     isla_engine tmp;
     tmp.cfg = cfg; tmp.ws = nullptr;
     tmp.lay.pool_offset = 0; tmp.lay.pool_stride = 0; tmp.lay.s_cap = s_cap; tmp.lay.a_cap = a_cap; tmp.lay.real_bytes = rb;
-    tmp.lay.state_dim = S; tmp.lay.counters_offset = 0; tmp.lay.disc_offset = 0; tmp.lay.ln_offset = 0; tmp.lay.ln_count = 0; tmp.lay.disc_count = 0; tmp.lay.pw1_offset = 0; tmp.lay.pw2_offset = 0;
+    tmp.lay.state_dim = S; tmp.lay.counters_offset = 0; tmp.lay.disc_offset = 0; tmp.lay.ln_offset = 0; tmp.lay.ln_count = 0; tmp.lay.disc_count = 0; tmp.lay.pw1_offset = 0; tmp.lay.pw2_offset = 0; tmp.lay.hash_offset = 0; tmp.lay.hash_cap = 0;
     return make_params(&tmp).off[O_COUNT];
 }
 
@@ -801,6 +863,9 @@ int cta_fill_layout(const isla_config& cfg, isla_layout& lay) {
     lay.slots_per_tree = 0; lay.rec_offset = lay.rec_stride = lay.state_offset = lay.state_stride = lay.meta_offset = lay.path_offset = 0;
     int64_t off = 0;
     lay.pool_offset = off; lay.pool_stride = pool_bytes(cfg, lay.s_cap, lay.a_cap, S, rb); off = up(off + cfg.n_trees * lay.pool_stride);
+    lay.hash_cap = 0;
+    if (cfg.agent == ISLA_AGENT_APW || cfg.agent == ISLA_AGENT_DPW) { lay.hash_cap = 64; while (lay.hash_cap < 2 * lay.a_cap) lay.hash_cap <<= 1; }
+    lay.hash_offset = off; off = up(off + cfg.n_trees * lay.hash_cap * 16);
     lay.counters_offset = off; off = up(off + 64);
     add_table_layout(cfg, lay, off);
     lay.total_bytes = off;
@@ -810,6 +875,8 @@ int cta_fill_layout(const isla_config& cfg, isla_layout& lay) {
 int cta_set_roots(isla_engine* e, const double* roots_dev, cudaStream_t st) {
     CtaParams p = make_params(e);
     ISLA_CUDA_OK(cudaMemsetAsync(e->ws + e->lay.counters_offset, 0, 64, st));
+    if (e->lay.hash_cap > 0)  // empty hash sets: state field < 0
+        ISLA_CUDA_OK(cudaMemsetAsync(e->ws + e->lay.hash_offset, 0xFF, (size_t)(e->cfg.n_trees * e->lay.hash_cap * 16), st));
     const unsigned grid = (unsigned)((e->cfg.n_trees + 127) / 128);
     if (e->lay.real_bytes == 4) cta_set_roots_kernel<float><<<grid, 128, 0, st>>>(p, roots_dev, e->lay.state_dim);
     else cta_set_roots_kernel<double><<<grid, 128, 0, st>>>(p, roots_dev, e->lay.state_dim);

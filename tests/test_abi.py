@@ -31,7 +31,7 @@ def test_struct_sizes_match_header(lib):
     import ctypes as C
     from islamcts_b200 import _lib
     assert C.sizeof(_lib.IslaConfig) == 14 * 4 + 7 * 8 + 3 * 8
-    assert C.sizeof(_lib.IslaLayout) == 4 * 4 + 24 * 8
+    assert C.sizeof(_lib.IslaLayout) == 4 * 4 + 26 * 8
 
 
 def test_workspace_sizing_and_validation_without_gpu(lib):
