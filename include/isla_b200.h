@@ -141,7 +141,7 @@ int isla_engine_root_children(isla_engine* e, int64_t tree, int32_t cap, double*
                               double* total_dev, int32_t* count_dev, void* stream);
 /* CTA-per-tree engine: byte offsets of the SoA arrays inside one tree's pool, for host-side decoding
  * (order: s_total, s_term_reward, s_ns, s_flags, s_coff, s_ccap, s_ccnt, s_state, a_total, a_value, a_na,
- *  a_visits, a_child, ipool, path_s, path_a, path_r, path_flag, meta, end). */
+ *  a_visits, a_child, ipool, path_s, path_a, path_r, path_flag, meta, path_g, end). */
 int isla_engine_pool_offsets(const isla_engine* e, int64_t out[24]);
 
 /* Device counters int64[8]: [0] env steps executed, [1] rollout steps, [2] tree levels visited,

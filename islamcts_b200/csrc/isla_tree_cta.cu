@@ -44,7 +44,7 @@ struct Pool {
     // action nodes
     double* a_total; double* a_value; int* a_na; int* a_visits; int* a_child;
     // child index arrays, path
-    int* ipool; int* p_s; int* p_a; double* p_r; int* p_flag;
+    int* ipool; int* p_s; int* p_a; double* p_r; int* p_flag; double* p_g;
     int* meta;
 };
 
@@ -65,7 +65,7 @@ struct CtaParams {
 };
 
 enum : int { O_S_TOTAL = 0, O_S_TERMR, O_S_NS, O_S_FLAGS, O_S_COFF, O_S_CCAP, O_S_CCNT, O_S_STATE, O_A_TOTAL, O_A_VALUE,
-             O_A_NA, O_A_VISITS, O_A_CHILD, O_IPOOL, O_P_S, O_P_A, O_P_R, O_P_FLAG, O_META, O_COUNT };
+             O_A_NA, O_A_VISITS, O_A_CHILD, O_IPOOL, O_P_S, O_P_A, O_P_R, O_P_FLAG, O_META, O_P_G, O_COUNT };
 enum : int { CM_NS = 0, CM_NA = 1, CM_ITOP = 2, CM_SIMS = 3, CM_RNG = 4, CM_FAULT = 5, CM_TRACE_POS = 6, CM_WORDS = 8 };
 
 __device__ __forceinline__ Pool make_pool_at(const CtaParams& p, char* b) {
@@ -80,6 +80,7 @@ __device__ __forceinline__ Pool make_pool_at(const CtaParams& p, char* b) {
     q.p_s = (int*)(b + p.off[O_P_S]); q.p_a = (int*)(b + p.off[O_P_A]); q.p_r = (double*)(b + p.off[O_P_R]);
     q.p_flag = (int*)(b + p.off[O_P_FLAG]);
     q.meta = (int*)(b + p.off[O_META]);
+    q.p_g = (double*)(b + p.off[O_P_G]);
     return q;
 }
 __device__ __forceinline__ Pool make_pool(const CtaParams& p, long long tree) {
@@ -407,6 +408,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
     uint32_t sims_done = (uint32_t)ctx.q.meta[CM_SIMS];
     int s_done = 0;
     unsigned long long my_steps = 0;  // rollout env steps played by THIS thread
+    int prev_levels = 0;              // recorded path entries of the previous simulation (warp 0, replicated)
 
     for (int sim = 0; sim < p.n_sim; ++sim) {
         // ------------------------------------------------------------ warp 0: descent to the leaf
@@ -418,6 +420,42 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
         if (leader && !ctx.fault) {
             Pool& q = ctx.q;
             int s = 0;
+            if constexpr (!SCRIPTED) {
+                // Vanilla trees re-walk almost the same path every simulation.  The 32 lanes re-evaluate UCB1 on 32
+                // LEVELS of the previous path at once (the statistics are already backed up); the first level that
+                // has an unvisited action, an exact tie (needs a draw) or a different arg-max is where the serial
+                // descent resumes.  The old path's last level is always re-decided serially.
+                if (p.agent == ISLA_AGENT_VANILLA && prev_levels > 1) {
+                    const int Lv = prev_levels - 1;
+                    int event = Lv;
+                    for (int l0 = 0; l0 < Lv; l0 += 32) {
+                        const int l = l0 + lane;
+                        bool my_event = false;
+                        if (l < Lv) {
+                            const int sl = q.p_s[l], al = q.p_a[l];
+                            const int n = q.s_ccnt[sl], off = q.s_coff[sl];
+                            if (n < p.n_actions) my_event = true;
+                            else {
+                                const int ns = q.s_ns[sl];
+                                const double lg = ns < p.ln_count ? p.ln_table[ns] : ::log((double)ns);
+                                double best = -INFINITY; int arg = -1, ties = 0;
+                                for (int i = 0; i < n; ++i) {
+                                    const int a = q.ipool[off + i];
+                                    const double na = (double)q.a_na[a];
+                                    const double sc = __dadd_rn(__ddiv_rn(q.a_total[a], na), __dmul_rn(p.C, __dsqrt_rn(__ddiv_rn(lg, na))));
+                                    if (sc > best) { best = sc; arg = a; ties = 1; } else if (sc == best) ++ties;
+                                }
+                                my_event = (ties != 1) || (arg != al);
+                            }
+                        }
+                        const unsigned ev = __ballot_sync(kFull, my_event);
+                        if (ev) { event = l0 + __ffs(ev) - 1; break; }
+                    }
+                    level = event;
+                    s = q.p_s[event];
+                    ctx.c_levels += (unsigned long long)event;
+                }
+            }
             for (;;) {
                 ++ctx.c_levels;
                 // ---------------- state node: choose or create the action node
@@ -612,20 +650,28 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                 G = __dadd_rn(r_leaf, __dmul_rn(p.gamma, mean));
                 if (lane == 0) { q.a_na[leaf_a] += 1; q.s_ns[leaf_s] += 1; q.a_total[leaf_a] += G; q.s_total[leaf_s] += G; }
             }
-            // the deepest level's action node was updated above; unwind the recursion for the rest
+            // the deepest level's action node was updated above; unwind the recursion for the rest:
+            // the returns g_l = r_l + gamma * g_{l+1} are a serial chain (lane 0), the node updates are not
             if (lane == 0) {
                 double g = G;
-                for (int l = level - 1; l >= 0; --l) {
-                    const int s = q.p_s[l], a = q.p_a[l], fl = q.p_flag[l];
-                    if (l < level - 1) {
-                        g = __dadd_rn(q.p_r[l], __dmul_rn(p.gamma, g));       // r + gamma * build_tree_state(child)
-                        if (fl & 2) { q.a_total[a] += g; q.a_na[a] += 1; }
-                    }
-                    q.s_ns[s] += 1; q.a_visits[a] += 1; q.s_total[s] += g;      // mcts.py:63-66
+                q.p_g[level - 1] = g;
+                for (int l = level - 2; l >= 0; --l) {
+                    g = __dadd_rn(q.p_r[l], __dmul_rn(p.gamma, g));             // r + gamma * build_tree_state(child)
+                    q.p_g[l] = g;
                 }
             }
             __syncwarp();
+            for (int l = lane; l < level; l += 32) {
+                const int s = q.p_s[l], a = q.p_a[l], fl = q.p_flag[l];
+                const double g = q.p_g[l];
+                if (l < level - 1 && (fl & 2)) { q.a_total[a] += g; q.a_na[a] += 1; }
+                q.s_ns[s] += 1; q.a_visits[a] += 1; q.s_total[s] += g;          // mcts.py:63-66
+            }
+            __syncwarp();
             ++sims_done; ++s_done;
+            prev_levels = level;
+        } else {
+            prev_levels = 0;
         }
         __syncthreads();
     }
@@ -777,6 +823,7 @@ CtaParams make_params(const isla_engine* e) {
     take(O_A_CHILD, L.a_cap * 4); take(O_IPOOL, p.i_cap * 4);
     take(O_P_S, L.s_cap * 4); take(O_P_A, L.s_cap * 4); take(O_P_R, L.s_cap * 8); take(O_P_FLAG, L.s_cap * 4);
     take(O_META, CM_WORDS * 4);
+    take(O_P_G, L.s_cap * 8);
     p.off[O_COUNT] = off;
     p.counters = (unsigned long long*)(e->ws + L.counters_offset);
     p.trace_kinds = nullptr; p.trace_values = nullptr; p.trace_len = 0;

@@ -5,10 +5,10 @@ from __future__ import annotations
 import numpy as np
 
 _NAMES = ["s_total", "s_term_reward", "s_ns", "s_flags", "s_coff", "s_ccap", "s_ccnt", "s_state", "a_total", "a_value",
-          "a_na", "a_visits", "a_child", "ipool", "p_s", "p_a", "p_r", "p_flag", "meta", "end"]
+          "a_na", "a_visits", "a_child", "ipool", "p_s", "p_a", "p_r", "p_flag", "meta", "p_g", "end"]
 _DT = {"s_total": "<f8", "s_term_reward": "<f8", "s_ns": "<i4", "s_flags": "<i4", "s_coff": "<i4", "s_ccap": "<i4",
        "s_ccnt": "<i4", "a_total": "<f8", "a_value": "<f8", "a_na": "<i4", "a_visits": "<i4", "a_child": "<i4",
-       "ipool": "<i4", "p_s": "<i4", "p_a": "<i4", "p_r": "<f8", "p_flag": "<i4", "meta": "<i4"}
+       "ipool": "<i4", "p_s": "<i4", "p_a": "<i4", "p_r": "<f8", "p_flag": "<i4", "meta": "<i4", "p_g": "<f8"}
 
 
 def read_pool(engine, tree: int) -> dict:
