@@ -276,7 +276,7 @@ def run_isla(args):
                      "algorithmic_bytes": "levels*(12*A+36) + sims*16 (SURVEY 8d), A=2"},
         "e2e": {"value": e2e_value, "unit": "sims/s", "h2d_bytes_per_step": search.h2d_bytes(),
                 "d2h_bytes_per_step": search.d2h_bytes(), "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": 5 * args.steps,
+        "gpu_launches": 4 * args.steps,   # per step: tpt_set_roots, tpt_search, tpt_root_stats, merge_root_stats
         "clocks": clk,
     }
     if not args.no_extras and world == 1:

@@ -300,6 +300,44 @@ struct Search {
         return found;
     }
 
+    // genetic_policy2 (utils/action_selection_functions.py:104-136), one action dimension, float32 Box.  p is drawn
+    // first on every call; 0 / 1 / 2 existing actions get the centre / a random bound / the missing bound; later calls
+    // take default_policy with probability 1 - epsilon, else the mean of the two LOWEST-q actions (the list is sorted
+    // ascending by q and entries [0], [1] are used, :108-112; python's sort is stable, so ties keep insertion order).
+    __device__ double genetic2_expand(int s) {
+        const double pr = u01();
+        const int off = q.s_coff[s], n = q.s_ccnt[s];
+        float lof, hif; env_action_bounds(ENV, lof, hif);
+        if (n == 0) return (double)__fmul_rn(__fadd_rn(lof, hif), 0.5f);
+        if (n == 1) {
+            int idx;
+            if constexpr (SCRIPTED) idx = (int)tc.take(ISLA_K_CHOICES);
+            else idx = (1.0 > __dmul_rn(u32_to_d01(ts.next()), 2.0)) ? 0 : 1;   // random.choices([high, low])
+            return idx == 0 ? (double)hif : (double)lof;
+        }
+        if (n == 2) return find_action(s, (double)hif) >= 0 ? (double)lof : (double)hif;
+        if (pr < __dsub_rn(1.0, p.epsilon)) return tree_action();
+        auto qv = [&](int i) -> double { const int a = q.ipool[off + i]; return __ddiv_rn(q.a_total[a], (double)q.a_na[a]); };
+        int r0 = -1, r1 = -1;
+        for (int pass = 0; pass < 2; ++pass) {
+            double bq = INFINITY; int br = 0x7fffffff;
+            for (int i = lane; i < n; i += 32) {
+                if (pass == 1 && i == r0) continue;
+                const double v = qv(i);
+                if (v < bq) { bq = v; br = i; }          // ascending i per lane: the first minimum is kept
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double oq = __shfl_xor_sync(kFull, bq, o);
+                const int orank = __shfl_xor_sync(kFull, br, o);
+                if (oq < bq || (oq == bq && orank < br)) { bq = oq; br = orank; }
+            }
+            if (pass == 0) r0 = br; else r1 = br;
+        }
+        const float x = (float)q.a_value[q.ipool[off + r0]], y = (float)q.a_value[q.ipool[off + r1]];
+        return (double)__fmul_rn(__fadd_rn(x, y), 0.5f);   // np.mean([best, second], axis=0) in float32
+    }
+
     // voo (utils/action_selection_functions.py:139-205), one action dimension
     __device__ double voo_expand(int s) {
         const double pr = u01();
@@ -482,6 +520,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                     if (n_act == 0 || (double)n_act <= cap) {
                         double val;
                         if (p.agent == ISLA_AGENT_APW && p.expansion == ISLA_EXPAND_VOO) val = ctx.voo_expand(s);
+                        else if (p.agent == ISLA_AGENT_APW && p.expansion == ISLA_EXPAND_GENETIC2) val = ctx.genetic2_expand(s);
                         else val = ctx.tree_action();  // dpw ignores --ae (mcts_double_...:57)
                         const int old = ctx.find_action(s, val);
                         if (p.agent == ISLA_AGENT_APW) {
@@ -899,7 +938,8 @@ int cta_fill_layout(const isla_config& cfg, isla_layout& lay) {
                                                                            cfg.n_actions != env_n_actions(cfg.env_id))) {
         set_error("n_actions=%d does not match env (%d)", cfg.n_actions, env_n_actions(cfg.env_id)); return ISLA_ERR_INVALID;
     }
-    if (cfg.expansion == ISLA_EXPAND_VOO && cfg.agent != ISLA_AGENT_APW) { set_error("voo expansion is an APW option"); return ISLA_ERR_INVALID; }
+    if (cfg.expansion != ISLA_EXPAND_RANDOM && cfg.agent != ISLA_AGENT_APW) { set_error("voo / genetic2 expansion are APW options"); return ISLA_ERR_INVALID; }
+    if (cfg.expansion < ISLA_EXPAND_RANDOM || cfg.expansion > ISLA_EXPAND_GENETIC2) { set_error("unknown expansion %d", cfg.expansion); return ISLA_ERR_INVALID; }
     if (cfg.expansion == ISLA_EXPAND_VOO && (cfg.voo_n_samples < 1 || cfg.voo_n_samples > 8 || cfg.voo_max_try < 1)) {
         set_error("voo: n_samples must be in [1, 8] and max_try >= 1"); return ISLA_ERR_INVALID;
     }

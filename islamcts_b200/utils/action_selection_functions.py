@@ -51,6 +51,24 @@ def voo(epsilon, default_policy, n_samples, max_try=1000):
     return _Voo(epsilon, default_policy, n_samples, max_try)
 
 
+class _Genetic2:
+    """Product of ``genetic_policy2(epsilon, default_policy)`` (reference :104-136): a tag carrying epsilon."""
+
+    isla_kind = "genetic2"
+
+    def __init__(self, epsilon, default_policy):
+        if getattr(default_policy, "isla_kind", None) != "random":
+            raise NotImplementedError("genetic_policy2: only continuous_default_policy is supported as the default policy")
+        self.epsilon, self.default_policy = float(epsilon), default_policy
+
+    def __call__(self, node):
+        raise NotImplementedError("genetic_policy2 runs on the device inside fit(); it is not evaluated on the host")
+
+
+def genetic_policy2(epsilon, default_policy):
+    return _Genetic2(epsilon, default_policy)
+
+
 def _next_round(name):
     def factory(*args, **kwargs):
         raise NotImplementedError(f"{name}: not on the B200 hot path yet (SURVEY section 8f); no CPU fallback by design")
@@ -59,6 +77,5 @@ def _next_round(name):
 
 
 genetic_policy = _next_round("genetic_policy")
-genetic_policy2 = _next_round("genetic_policy2")
 grid_policy = _next_round("grid_policy")
 discrete_default_policy = _next_round("discrete_default_policy")

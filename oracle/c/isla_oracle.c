@@ -447,6 +447,33 @@ static double voo_expand(orc_tree* t, int sidx) {
     return out; /* NOTE: a float64 action; the reference keys it by its float64 bytes */
 }
 
+/* genetic_policy2: utils/action_selection_functions.py:104-136 (one action dimension, float32 Box).
+ * p is drawn first on every call; 0/1/2 existing actions get the centre / a random bound / the missing bound;
+ * later calls take default_policy with probability 1-epsilon, else the mean of the two LOWEST-q actions
+ * (the list is sorted ascending and [0], [1] are used, :108-112). */
+static double genetic2_expand(orc_tree* t, int sidx) {
+    snode* s = &t->S[sidx];
+    const double p = rnd_u01(t);
+    float lowf, highf; action_bounds(t->cfg.env_id, &lowf, &highf);
+    if (s->n_act == 0) { float m = (lowf + highf) / 2.0f; return (double)m; }          /* np.mean([low, high]) in float32 */
+    if (s->n_act == 1) {
+        double w[2] = {1.0, 1.0};
+        return rnd_choices(t, w, 2) == 0 ? (double)highf : (double)lowf;                /* random.choices([high, low]) */
+    }
+    if (s->n_act == 2) return find_action_bits(t, sidx, (double)highf) >= 0 ? (double)lowf : (double)highf;
+    if (p < 1 - t->cfg.epsilon) return rnd_action(t, &t->tree_stream);
+    /* stable ascending sort by q: the first two entries */
+    int b0 = -1, b1 = -1; double q0 = INFINITY, q1 = INFINITY;
+    for (int a = s->first_act; a >= 0; a = t->A[a].next_act) {
+        double q = t->A[a].total / (double)t->A[a].na;
+        if (q < q0) { b1 = b0; q1 = q0; b0 = a; q0 = q; }
+        else if (q < q1) { b1 = a; q1 = q; }
+    }
+    float x = (float)t->A[b0].value, y = (float)t->A[b1].value;
+    float m = (x + y) / 2.0f;                                                           /* np.mean([best, second], axis=0) */
+    return (double)m;
+}
+
 static double state_visit(orc_tree* t, int sidx, int level);
 
 /* build_tree_action.  `level` = tree depth of the parent state node (root = 0). */
@@ -561,6 +588,7 @@ static double state_visit(orc_tree* t, int sidx, int level) {
         if (s->n_act == 0 || (double)s->n_act <= cap) {
             double a;
             if (c->agent == ORC_AGENT_APW && c->expansion == ORC_EXPAND_VOO) a = voo_expand(t, sidx);
+            else if (c->agent == ORC_AGENT_APW && c->expansion == ORC_EXPAND_GENETIC2) a = genetic2_expand(t, sidx);
             else a = rnd_action(t, &t->tree_stream); /* dpw ignores --ae: always action_space.sample() */
             int old = find_action_bits(t, sidx, a);
             if (c->agent == ORC_AGENT_APW) {

@@ -50,6 +50,10 @@ SCENARIOS = {
     "apw_voo_pendulum": dict(agent="MctsApw", env="Pendulum-v1", n_sim=120, C=2.0, gamma=0.95, max_depth=200,
                              alpha=0.5, k=2, budget="zero", env_seed=2, rng_seed=8,
                              expansion="voo", epsilon=0.5, voo_n_samples=3, voo_max_try=50),
+    # APW with the genetic2 expansion (--ae genetic2): centre / bounds first, then epsilon-mix of random and the mean
+    # of the two lowest-q actions
+    "apw_genetic2_pendulum": dict(agent="MctsApw", env="Pendulum-v1", n_sim=160, C=2.0, gamma=0.95, max_depth=200,
+                                  alpha=0.6, k=2, budget="zero", env_seed=3, rng_seed=13, expansion="genetic2", epsilon=0.6),
     # SPW (with the state_variable shim) on CartPole: k=1 always re-expands; k=0.4 resamples and descends
     "spw_cartpole_k1": dict(agent="MctsSpw", env="CartPole-v1", n_sim=150, C=1.0, gamma=0.99, max_depth=500,
                             alpha=0.5, k=1, budget="zero", env_seed=0, rng_seed=9),
@@ -100,6 +104,8 @@ def run_scenario(name: str, sc: dict):
     elif agent_key == "MctsApw":
         if sc.get("expansion") == "voo":
             ae = R.voo(sc["epsilon"], R.continuous_default_policy, sc["voo_n_samples"], sc["voo_max_try"])
+        elif sc.get("expansion") == "genetic2":
+            ae = R.asf.genetic_policy2(sc["epsilon"], R.continuous_default_policy)
         else:
             ae = R.continuous_default_policy
         param = R.PwParameters(**common, alpha=sc["alpha"], k=sc["k"], action_expansion_function=ae)

@@ -107,7 +107,7 @@ def recording(trace: Trace, seed: int):
 
     def choices(population, weights=None, **kwargs):
         pop = list(population)
-        w = np.asarray(weights, dtype=np.float64)
+        w = np.ones(len(pop)) if weights is None else np.asarray(weights, dtype=np.float64)
         cum = np.cumsum(w)
         u = float(rng.random()) * cum[-1]
         idx = int(np.searchsorted(cum, u, side="right"))

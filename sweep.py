@@ -46,14 +46,16 @@ def argument_parser():
 
 
 def get_function(name, args):
-    from islamcts_b200.utils.action_selection_functions import continuous_default_policy, ucb1, voo
+    from islamcts_b200.utils.action_selection_functions import continuous_default_policy, genetic_policy2, ucb1, voo
     if name == "ucb":
         return ucb1
     if name == "random":
         return continuous_default_policy
     if name == "voo":
         return voo(epsilon=args["epsilon"], default_policy=get_function(args["genetic_default"], args), n_samples=args["n_sample"])
-    raise NotImplementedError(f"--{name}: not on the device yet (genetic / genetic2 are SURVEY 8f rows)")
+    if name == "genetic2":
+        return genetic_policy2(epsilon=args["epsilon"], default_policy=get_function(args["genetic_default"], args))
+    raise NotImplementedError(f"--{name}: not on the device yet (genetic is a SURVEY 8f row)")
 
 
 def create_agent(args, env, observation):

@@ -35,6 +35,8 @@ def engine_kwargs(cfg):
     if cfg.get("expansion") == "voo":
         kw.update(expansion=1, epsilon=cfg["epsilon"], voo_n_samples=cfg["voo_n_samples"],
                   voo_max_try=cfg["voo_max_try"])
+    if cfg.get("expansion") == "genetic2":
+        kw.update(expansion=2, epsilon=cfg["epsilon"])
     return kw
 
 

@@ -7,7 +7,7 @@ from islamcts_b200.agents.abstract_mcts import AbstractActionNode, AbstractState
 from islamcts_b200.agents.parameters.dpw_parameters import DpwParameters
 from islamcts_b200.agents.parameters.mcts_parameters import MctsParameters
 from islamcts_b200.agents.parameters.pw_parameters import PwParameters
-from islamcts_b200.utils.action_selection_functions import continuous_default_policy, genetic_policy2, ucb1, voo
+from islamcts_b200.utils.action_selection_functions import continuous_default_policy, genetic_policy, genetic_policy2, ucb1, voo
 from islamcts_b200.utils.agent_factory import get_agent
 
 
@@ -67,7 +67,9 @@ def test_unknown_callables_and_envs_fail_loudly():
     with pytest.raises(NotImplementedError):
         identify_env(type("Acrobot", (), {})())
     with pytest.raises(NotImplementedError):
-        genetic_policy2(0.7, continuous_default_policy)                     # SURVEY 8f "next" row
+        genetic_policy(0.7, continuous_default_policy, 5)                   # SURVEY 8f "next" row
+    g2 = genetic_policy2(0.7, continuous_default_policy)
+    assert (g2.isla_kind, g2.epsilon) == ("genetic2", 0.7)
     v = voo(0.7, continuous_default_policy, 5)
     assert (v.isla_kind, v.epsilon, v.n_samples, v.max_try) == ("voo", 0.7, 5, 1000)
 

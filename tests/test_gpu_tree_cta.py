@@ -46,6 +46,7 @@ FREE = {
     "apw_pendulum": dict(env_id=1, agent=1, max_depth=25, C=2.0, gamma=0.95, alpha1=0.45, k1=1.0),
     "apw_voo_pendulum": dict(env_id=1, agent=1, max_depth=15, C=2.0, gamma=0.95, alpha1=0.5, k1=2.0, expansion=1,
                              epsilon=0.4, voo_n_samples=3, voo_max_try=20),
+    "apw_genetic2_pendulum": dict(env_id=1, agent=1, max_depth=15, C=2.0, gamma=0.95, alpha1=0.6, k1=2.0, expansion=2, epsilon=0.6),
     "apw_mountaincar_c3like": dict(env_id=2, agent=1, max_depth=40, C=1.0, gamma=0.99, alpha1=0.8, k1=60.0),
     "spw_cartpole_descend": dict(env_id=0, agent=2, n_actions=2, max_depth=40, C=1.0, gamma=0.9, alpha1=0.3, k1=0.4),
     "spw_cartpole_k1": dict(env_id=0, agent=2, n_actions=2, max_depth=40, C=1.0, gamma=0.9, alpha1=0.5, k1=1.0),
