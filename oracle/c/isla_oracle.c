@@ -24,7 +24,8 @@
 #include <stdlib.h>
 #include <string.h>
 
-#define ORC_MAX_DISCRETE 16
+#define ORC_MAX_DISCRETE 128
+#define ORC_MAX_S 8
 
 /* ------------------------------------------------------------------ Philox4x32-10 */
 void orc_philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
@@ -79,24 +80,36 @@ static inline float box_sample_f32(uint32_t u, float low, float high) {
 /* Gymnasium definitions restated in oracle/pyenvs.py; float64. */
 int orc_state_dim(int env_id) {
     switch (env_id) { case ORC_ENV_CARTPOLE: return 4; case ORC_ENV_PENDULUM: return 2;
-                      case ORC_ENV_MOUNTAINCAR: return 2; case ORC_ENV_FROZENLAKE: return 1; }
+                      case ORC_ENV_MOUNTAINCAR: return 2; case ORC_ENV_FROZENLAKE: return 1; case ORC_ENV_CURVE: return 5; }
     return 0;
 }
-static int obs_dim(int env_id) { return env_id == ORC_ENV_PENDULUM ? 3 : orc_state_dim(env_id); }
+static int obs_dim(int env_id) { return env_id == ORC_ENV_PENDULUM ? 3 : env_id == ORC_ENV_CURVE ? 4 : orc_state_dim(env_id); }
+int orc_action_dim(int env_id) { return env_id == ORC_ENV_CURVE ? 2 : 1; }
 
 static const char LAKE[16] = {'S','F','F','F','F','H','F','H','F','F','F','H','H','F','F','G'};
 
-static void make_obs(int env_id, const double* s, float* obs) {
+/* the observation the reference keys its children dicts with (float32 values for the gym envs, the float64
+ * car.state for CurveEnv), held as doubles */
+static void make_obs(int env_id, const double* s, double* obs) {
     switch (env_id) {
-    case ORC_ENV_CARTPOLE: for (int i = 0; i < 4; ++i) obs[i] = (float)s[i]; break;
-    case ORC_ENV_PENDULUM: obs[0] = (float)cos(s[0]); obs[1] = (float)sin(s[0]); obs[2] = (float)s[1]; break;
-    case ORC_ENV_MOUNTAINCAR: obs[0] = (float)s[0]; obs[1] = (float)s[1]; break;
-    default: obs[0] = (float)s[0]; break;
+    case ORC_ENV_CARTPOLE: for (int i = 0; i < 4; ++i) obs[i] = (double)(float)s[i]; break;
+    case ORC_ENV_PENDULUM: obs[0] = (double)(float)cos(s[0]); obs[1] = (double)(float)sin(s[0]); obs[2] = (double)(float)s[1]; break;
+    case ORC_ENV_MOUNTAINCAR: obs[0] = (double)(float)s[0]; obs[1] = (double)(float)s[1]; break;
+    case ORC_ENV_CURVE: for (int i = 0; i < 4; ++i) obs[i] = s[i]; break;
+    default: obs[0] = (double)(float)s[0]; break;
     }
 }
 
-int orc_env_step(int env_id, const double* s, double action, double* ns, double* reward, int32_t* term,
-                 float* obs) {
+/* CurveEnv reward tables: islaMcts/environments/curve_env.py:61-72 */
+static double curve_gradient(int second, int idx) {
+    if (idx >= 27) return 50.0;
+    if (!second) return 1.80 * idx;
+    return 1.80 * (29 + (26 - idx));   /* idx 26 -> 1.8*29, 25 -> 1.8*30, ..., 20 -> 1.8*35 */
+}
+
+int orc_env_step(int env_id, const double* s, const double* act, double* ns, double* reward, int32_t* term,
+                 double* obs) {
+    const double action = act[0];
     switch (env_id) {
     case ORC_ENV_CARTPOLE: {
         const double gravity = 9.8, masscart = 1.0, masspole = 0.1, total_mass = masspole + masscart,
@@ -155,6 +168,43 @@ int orc_env_step(int env_id, const double* s, double action, double* ns, double*
         ns[0] = (double)cell; *reward = LAKE[cell] == 'G' ? 1.0 : 0.0; *term = (LAKE[cell] == 'G' || LAKE[cell] == 'H');
         break;
     }
+    case ORC_ENV_CURVE: {
+        /* islaMcts/environments/curve_env.py: Car.update :34-56, CurveEnv.step :120-174.  state = (x, y, velocity,
+         * angle, n_step); the step counter is hidden state of the env object (it scales the rewards). */
+        const double dt = 0.5;
+        double x = s[0], y = s[1], velocity = s[2], angle = s[3];
+        const double n_step = s[4] + 1.0;
+        const double last_x = x, last_y = y;
+        velocity += act[0] * dt;
+        if (velocity > 20.0) velocity = 20.0;
+        if (velocity < 0.0) velocity = 0.0;
+        angle += act[1];
+        angle = fmod(angle, 360.0);
+        if (angle < 0) angle += 360.0;                       /* python float % */
+        const double rad = angle * (M_PI / 180.0);           /* math.radians */
+        const double vel_x = cos(rad) * velocity * dt, vel_y = sin(rad) * velocity * dt;
+        x += vel_x; y += vel_y;
+        /* 100 points of np.linspace(last, new) must lie inside the corridor (:136-143) */
+        int inside = 1;
+        const double step_x = (x - last_x) / 99.0, step_y = (y - last_y) / 99.0;
+        for (int i = 0; i < 100 && inside; ++i) {
+            const double px = i == 99 ? x : (double)i * step_x + last_x;
+            const double py = i == 99 ? y : (double)i * step_y + last_y;
+            const double lower = -(1.0 / 50) * (3 * (px * px)) + 27.3;
+            const double higher = -(1.0 / 50) * (px * px) + 27.5;
+            if (!(py >= lower) || !(py <= higher)) inside = 0;
+        }
+        if (!inside) { *term = 1; *reward = -1000.0; }
+        else if (x >= 9 && 20 <= y && y <= 26) { *term = 1; *reward = 10000.0 / n_step; }
+        else {
+            *term = 0;
+            const int second = !(x < 0);
+            const int idx = y <= 21 ? 20 : (y >= 27 ? 27 : (int)y);
+            *reward = curve_gradient(second, idx) / n_step;
+        }
+        ns[0] = x; ns[1] = y; ns[2] = velocity; ns[3] = angle; ns[4] = n_step;
+        break;
+    }
     default: return -1;
     }
     if (obs) make_obs(env_id, ns, obs);
@@ -168,6 +218,7 @@ void orc_env_reset(int env_id, uint64_t seed, uint64_t index, double* state) {
     case ORC_ENV_CARTPOLE: for (int i = 0; i < 4; ++i) state[i] = -0.05 + 0.1 * u32_to_d01(r[i]); break;
     case ORC_ENV_PENDULUM: state[0] = -M_PI + 2 * M_PI * u32_to_d01(r[0]); state[1] = -1.0 + 2.0 * u32_to_d01(r[1]); break;
     case ORC_ENV_MOUNTAINCAR: state[0] = (double)(float)(-0.6 + 0.2 * u32_to_d01(r[0])); state[1] = 0.0; break;
+    case ORC_ENV_CURVE: state[0] = -11.0; state[1] = 21.0; state[2] = 10.0; state[3] = 90.0; state[4] = 0.0; break;  /* Car(-11, 21), curve_env.py:181 */
     default: state[0] = 0.0; break;
     }
 }
@@ -180,15 +231,14 @@ static int env_n_actions(int env_id) { return env_id == ORC_ENV_CARTPOLE ? 2 : e
 /* ------------------------------------------------------------------ the tree */
 typedef struct {
     int64_t ns; double total; int terminal; double terminal_reward;
-    float obs[4];          /* node.data: the observation (key of the parent's children dict) */
+    double obs[ORC_MAX_S]; /* node.data: the observation (key of the parent's children dict) */
     int first_act, last_act, n_act;   /* actions dict, insertion order */
     int next_sibling;      /* next entry of the parent's children dict */
-    int64_t visit_disc[ORC_MAX_DISCRETE]; /* vanilla/spw: visit_actions ndarray */
     int blk;               /* instrumentation only: order in which nodes were first descended into */
 } snode;
 
 typedef struct {
-    int64_t na; double total; double value; /* node.data */
+    int64_t na; double total; double value[2]; /* node.data (1 or 2 action dimensions) */
     int64_t visits;        /* apw/dpw: parent's visit_actions[key] */
     int first_child, last_child, n_child;   /* children dict, insertion order */
     int next_act;          /* next entry of the parent's actions dict */
@@ -196,10 +246,10 @@ typedef struct {
 
 struct orc_tree {
     orc_config cfg;
-    double root_state[4];
+    double root_state[ORC_MAX_S];
     snode* S; anode* A; int nS, nA, capS, capA;
     /* the live environment of the current simulation (param.env) */
-    double env[4];
+    double env[ORC_MAX_S];
     /* randomness */
     const uint8_t* tk; const double* tv; int64_t tlen, tpos; int fault;
     stream_t tree_stream, roll_stream;
@@ -209,17 +259,17 @@ struct orc_tree {
     int prev_path[4096], cur_path[4096], prev_len, cur_len; int64_t c_common, c_prevlen;
 };
 
-static int new_snode(orc_tree* t, const float* obs) {
+static int new_snode(orc_tree* t, const double* obs) {
     if (t->nS == t->capS) { t->capS = t->capS * 2 + 16; t->S = (snode*)realloc(t->S, sizeof(snode) * t->capS); }
     snode* s = &t->S[t->nS]; memset(s, 0, sizeof *s);
     s->first_act = s->last_act = -1; s->next_sibling = -1;
-    memcpy(s->obs, obs, sizeof(float) * 4);
+    memcpy(s->obs, obs, sizeof(double) * ORC_MAX_S);
     return t->nS++;
 }
-static int new_anode(orc_tree* t, double value) {
+static int new_anode(orc_tree* t, const double* value) {
     if (t->nA == t->capA) { t->capA = t->capA * 2 + 16; t->A = (anode*)realloc(t->A, sizeof(anode) * t->capA); }
     anode* a = &t->A[t->nA]; memset(a, 0, sizeof *a);
-    a->first_child = a->last_child = -1; a->next_act = -1; a->value = value;
+    a->first_child = a->last_child = -1; a->next_act = -1; a->value[0] = value[0]; a->value[1] = value[1];
     return t->nA++;
 }
 
@@ -242,23 +292,37 @@ static int rnd_choice(orc_tree* t, int n) {
     if (n <= 1) return 0; /* Philox mode: a single candidate consumes no draw */
     return (int)mulhi32(stream_u32(&t->tree_stream), (uint32_t)n);
 }
-/* env.action_space.sample() */
-static double rnd_action(orc_tree* t, stream_t* st) {
-    int nd = env_n_actions(t->cfg.env_id);
+/* number of discrete actions of the run (0 = continuous Box): DiscreteCurveEnv has grid0 x grid1 of them */
+static int n_discrete(const orc_tree* t) {
+    if (t->cfg.env_id == ORC_ENV_CURVE) return t->cfg.grid0 > 0 ? t->cfg.grid0 * t->cfg.grid1 : 0;
+    return env_n_actions(t->cfg.env_id);
+}
+/* env.action_space.sample(): out[0] (and out[1] for the 2-D CurveEnv box) */
+static void rnd_action(orc_tree* t, stream_t* st, double out[2]) {
+    int nd = n_discrete(t);
+    out[0] = 0; out[1] = 0;
     if (nd > 0) {
         if (scripted(t)) {
             int a = (int)trace_next(t, ORC_K_SAMPLE_D);
-            if (a < 0 || a >= nd) { if (!t->fault) t->fault = -3; return 0; }
-            return a;
+            if (a < 0 || a >= nd) { if (!t->fault) t->fault = -3; return; }
+            out[0] = a; return;
         }
         /* Discrete(2) / Discrete(4): 1 / 2 bits of a stream word, most significant first */
-        if (nd == 2) return (double)stream_bits(st, 1);
-        if (nd == 4) return (double)stream_bits(st, 2);
-        return (double)mulhi32(stream_u32(st), (uint32_t)nd);
+        if (nd == 2) out[0] = (double)stream_bits(st, 1);
+        else if (nd == 4) out[0] = (double)stream_bits(st, 2);
+        else out[0] = (double)mulhi32(stream_u32(st), (uint32_t)nd);
+        return;
     }
-    if (scripted(t)) return (double)(float)trace_next(t, ORC_K_SAMPLE_C);
+    if (t->cfg.env_id == ORC_ENV_CURVE) {
+        /* Box(low=[-5,-30], high=[5,30], dtype=float64): np_random.uniform per dimension */
+        if (scripted(t)) { out[0] = trace_next(t, ORC_K_SAMPLE_C); out[1] = trace_next(t, ORC_K_SAMPLE_C); return; }
+        out[0] = -5.0 + 10.0 * u32_to_d01(stream_u32(st));
+        out[1] = -30.0 + 60.0 * u32_to_d01(stream_u32(st));
+        return;
+    }
+    if (scripted(t)) { out[0] = (double)(float)trace_next(t, ORC_K_SAMPLE_C); return; }
     float low, high; action_bounds(t->cfg.env_id, &low, &high);
-    return (double)box_sample_f32(stream_u32(st), low, high);
+    out[0] = (double)box_sample_f32(stream_u32(st), low, high);
 }
 /* random.choices(population, weights)[0] -> index */
 static int rnd_choices(orc_tree* t, const double* w, int n) {
@@ -282,17 +346,29 @@ static double rnd_uniform(orc_tree* t, double low, double high) {
 }
 
 /* ---- env of the running simulation */
-static void env_step(orc_tree* t, double action, float* obs, double* r, int* term) {
-    double ns[4]; int32_t tm;
-    orc_env_step(t->cfg.env_id, t->env, action, ns, r, &tm, obs);
-    memcpy(t->env, ns, sizeof(double) * 4);
+/* np.linspace(lo, hi, n)[i] */
+static double linspace_at(double lo, double hi, int n, int i) {
+    if (n <= 1) return lo;
+    if (i == n - 1) return hi;
+    return (double)i * ((hi - lo) / (double)(n - 1)) + lo;
+}
+static void env_step(orc_tree* t, const double* action, double* obs, double* r, int* term) {
+    double ns[ORC_MAX_S], act[2] = {action[0], action[1]}; int32_t tm;
+    if (t->cfg.env_id == ORC_ENV_CURVE && t->cfg.grid0 > 0) {
+        /* DiscreteCurveEnv: itertools.product(linspace(acc), linspace(angle))[k]  (curve_env.py:187-201) */
+        const int k = (int)action[0];
+        act[0] = linspace_at(-5.0, 5.0, t->cfg.grid0, k / t->cfg.grid1);
+        act[1] = linspace_at(-30.0, 30.0, t->cfg.grid1, k % t->cfg.grid1);
+    }
+    orc_env_step(t->cfg.env_id, t->env, act, ns, r, &tm, obs);
+    memcpy(t->env, ns, sizeof(double) * ORC_MAX_S);
     *term = tm; t->c_env_steps++;
 }
 /* SPW/DPW poke the node's observation into the env (mcts_state_...:24-25,127;
  * mcts_double_...:25-26,68-69,131-132): valid when obs == state (float32 values). */
-static void env_set_from_obs(orc_tree* t, const float* obs) {
+static void env_set_from_obs(orc_tree* t, const double* obs) {
     int d = orc_state_dim(t->cfg.env_id);
-    for (int i = 0; i < d; ++i) t->env[i] = (double)obs[i];
+    for (int i = 0; i < d; ++i) t->env[i] = obs[i];
 }
 
 /* abstract_mcts.py:72-91.  `budget` = number of steps the loop condition
@@ -301,15 +377,15 @@ static void env_set_from_obs(orc_tree* t, const float* obs) {
 static double do_rollout(orc_tree* t, int budget) {
     const int R = t->cfg.rollouts_per_leaf > 0 ? t->cfg.rollouts_per_leaf : 1;
     int P = 1; while (P < R) P <<= 1;
-    double leaf[4]; memcpy(leaf, t->env, sizeof leaf);
+    double leaf[ORC_MAX_S]; memcpy(leaf, t->env, sizeof leaf);
     double* x = (double*)calloc((size_t)P, sizeof(double));
     for (int j = 0; j < R; ++j) {
         memcpy(t->env, leaf, sizeof leaf);
         if (!scripted(t)) stream_init(&t->roll_stream, t->cfg.seed, t->sim_index, (uint32_t)t->cfg.tree_id, (uint32_t)j);
         int done = 0, depth = 0; double reward = 0;
         while (!done && depth < budget) {
-            double a = rnd_action(t, &t->roll_stream);
-            float obs[4]; double r; int term;
+            double a[2]; rnd_action(t, &t->roll_stream, a);
+            double obs[ORC_MAX_S]; double r; int term;
             env_step(t, a, obs, &r, &term);
             reward += r * pow(t->cfg.gamma, depth);
             done = term; depth++; t->c_roll_steps++;
@@ -367,10 +443,10 @@ static void replace_action(orc_tree* t, int sidx, int old, int neu) {
     else { int p = s->first_act; while (t->A[p].next_act != old) p = t->A[p].next_act; t->A[p].next_act = neu; }
     if (s->last_act == old) s->last_act = neu;
 }
-static int find_child(const orc_tree* t, int aidx, const float* obs) {
+static int find_child(const orc_tree* t, int aidx, const double* obs) {
     int od = obs_dim(t->cfg.env_id);
     for (int c = t->A[aidx].first_child; c >= 0; c = t->S[c].next_sibling)
-        if (memcmp(t->S[c].obs, obs, sizeof(float) * od) == 0) return c;
+        if (memcmp(t->S[c].obs, obs, sizeof(double) * od) == 0) return c;
     return -1;
 }
 static void append_child(orc_tree* t, int aidx, int sidx) {
@@ -387,9 +463,10 @@ static void replace_child(orc_tree* t, int aidx, int old, int neu) {
 }
 /* actions dict lookup by action.tobytes(): float32 samples are stored widened to double, so
  * comparing the double bits is the same test (voo yields float64 actions directly) */
-static int find_action_bits(const orc_tree* t, int sidx, double value) {
+static int find_action_bits(const orc_tree* t, int sidx, const double* value) {
+    const int ad = orc_action_dim(t->cfg.env_id);
     for (int a = t->S[sidx].first_act; a >= 0; a = t->A[a].next_act)
-        if (memcmp(&value, &t->A[a].value, sizeof(double)) == 0) return a;
+        if (memcmp(value, t->A[a].value, sizeof(double) * ad) == 0) return a;
     return -1;
 }
 
@@ -397,13 +474,13 @@ static int find_action_bits(const orc_tree* t, int sidx, double value) {
 static double voo_expand(orc_tree* t, int sidx) {
     snode* s = &t->S[sidx];
     double p = rnd_u01(t);
-    if (p <= t->cfg.epsilon || s->n_act == 0) return rnd_action(t, &t->tree_stream);
+    if (p <= t->cfg.epsilon || s->n_act == 0) { double d[2]; rnd_action(t, &t->tree_stream, d); return d[0]; }
     int n = s->n_act;
     double* act = (double*)malloc(sizeof(double) * n);
     double* q = (double*)malloc(sizeof(double) * n);
     int i = 0; double qmax = -INFINITY;
     for (int a = s->first_act; a >= 0; a = t->A[a].next_act, ++i) {
-        act[i] = t->A[a].value; q[i] = t->A[a].total / (double)t->A[a].na; if (q[i] > qmax) qmax = q[i];
+        act[i] = t->A[a].value[0]; q[i] = t->A[a].total / (double)t->A[a].na; if (q[i] > qmax) qmax = q[i];
     }
     int ties = 0; for (i = 0; i < n; ++i) ties += (q[i] == qmax);
     int pos = rnd_choice(t, ties), best = 0;
@@ -460,8 +537,8 @@ static double genetic2_expand(orc_tree* t, int sidx) {
         double w[2] = {1.0, 1.0};
         return rnd_choices(t, w, 2) == 0 ? (double)highf : (double)lowf;                /* random.choices([high, low]) */
     }
-    if (s->n_act == 2) return find_action_bits(t, sidx, (double)highf) >= 0 ? (double)lowf : (double)highf;
-    if (p < 1 - t->cfg.epsilon) return rnd_action(t, &t->tree_stream);
+    if (s->n_act == 2) { double hv[2] = {(double)highf, 0.0}; return find_action_bits(t, sidx, hv) >= 0 ? (double)lowf : (double)highf; }
+    if (p < 1 - t->cfg.epsilon) { double d[2]; rnd_action(t, &t->tree_stream, d); return d[0]; }
     /* stable ascending sort by q: the first two entries */
     int b0 = -1, b1 = -1; double q0 = INFINITY, q1 = INFINITY;
     for (int a = s->first_act; a >= 0; a = t->A[a].next_act) {
@@ -469,7 +546,7 @@ static double genetic2_expand(orc_tree* t, int sidx) {
         if (q < q0) { b1 = b0; q1 = q0; b0 = a; q0 = q; }
         else if (q < q1) { b1 = a; q1 = q; }
     }
-    float x = (float)t->A[b0].value, y = (float)t->A[b1].value;
+    float x = (float)t->A[b0].value[0], y = (float)t->A[b1].value[0];
     float m = (x + y) / 2.0f;                                                           /* np.mean([best, second], axis=0) */
     return (double)m;
 }
@@ -479,7 +556,7 @@ static double state_visit(orc_tree* t, int sidx, int level);
 /* build_tree_action.  `level` = tree depth of the parent state node (root = 0). */
 static double action_visit(orc_tree* t, int aidx, int level, int* descended_without_backup) {
     const orc_config* c = &t->cfg;
-    float obs[4] = {0, 0, 0, 0}; double r; int term;
+    double obs[ORC_MAX_S] = {0}; double r; int term;
     env_step(t, t->A[aidx].value, obs, &r, &term);
     t->c_expand_steps++;
     *descended_without_backup = 0;
@@ -567,29 +644,32 @@ static double state_visit(orc_tree* t, int sidx, int level) {
     if (t->cur_len < 4096) t->cur_path[t->cur_len++] = sidx;
     if (c->agent == ORC_AGENT_VANILLA || c->agent == ORC_AGENT_SPW) {
         /* mcts.py:55-62 */
+        /* visit_actions[a] == 0  <=>  action a has no node yet (the count is bumped right after the node's first visit) */
+        unsigned char seen[ORC_MAX_DISCRETE] = {0};
+        for (int a = t->S[sidx].first_act; a >= 0; a = t->A[a].next_act) seen[(int)t->A[a].value[0]] = 1;
         int cand[ORC_MAX_DISCRETE], nc = 0;
-        for (int a = 0; a < c->n_actions; ++a) if (t->S[sidx].visit_disc[a] == 0) cand[nc++] = a;
+        for (int a = 0; a < c->n_actions; ++a) if (!seen[a]) cand[nc++] = a;
         if (nc > 0) {
             disc = cand[rnd_choice(t, nc)];
-            aidx = new_anode(t, (double)disc);
+            { double dv[2] = {(double)disc, 0.0}; aidx = new_anode(t, dv); }
             /* self.actions[action] = child: replaces an entry with the same key (cannot exist
              * in vanilla; SPW keeps visit_actions in step as well) */
             int old = -1;
-            for (int a = t->S[sidx].first_act; a >= 0; a = t->A[a].next_act) if ((int)t->A[a].value == disc) old = a;
+            for (int a = t->S[sidx].first_act; a >= 0; a = t->A[a].next_act) if ((int)t->A[a].value[0] == disc) old = a;
             if (old >= 0) replace_action(t, sidx, old, aidx); else append_action(t, sidx, aidx);
         } else {
             aidx = act_by_rank(t, sidx, ucb_pick(t, sidx));
-            disc = (int)t->A[aidx].value;
+            disc = (int)t->A[aidx].value[0];
         }
     } else {
         /* mcts_action_...:62-75 ; mcts_double_...:56-65 */
         const snode* s = &t->S[sidx];
         double cap = ceil(c->k1 * pow((double)s->ns, c->alpha1));
         if (s->n_act == 0 || (double)s->n_act <= cap) {
-            double a;
-            if (c->agent == ORC_AGENT_APW && c->expansion == ORC_EXPAND_VOO) a = voo_expand(t, sidx);
-            else if (c->agent == ORC_AGENT_APW && c->expansion == ORC_EXPAND_GENETIC2) a = genetic2_expand(t, sidx);
-            else a = rnd_action(t, &t->tree_stream); /* dpw ignores --ae: always action_space.sample() */
+            double a[2] = {0.0, 0.0};
+            if (c->agent == ORC_AGENT_APW && c->expansion == ORC_EXPAND_VOO) a[0] = voo_expand(t, sidx);
+            else if (c->agent == ORC_AGENT_APW && c->expansion == ORC_EXPAND_GENETIC2) a[0] = genetic2_expand(t, sidx);
+            else rnd_action(t, &t->tree_stream, a); /* dpw ignores --ae: always action_space.sample() */
             int old = find_action_bits(t, sidx, a);
             if (c->agent == ORC_AGENT_APW) {
                 if (old >= 0) aidx = old;
@@ -607,7 +687,7 @@ static double state_visit(orc_tree* t, int sidx, int level) {
     double reward = action_visit(t, aidx, level, &skip);
     snode* s = &t->S[sidx];
     s->ns += 1;
-    if (disc >= 0) s->visit_disc[disc] += 1; else t->A[aidx].visits += 1;
+    t->A[aidx].visits += 1;   /* visit_actions[action] += 1 */
     s->total += reward;
     (void)skip;
     return reward;
@@ -619,7 +699,7 @@ orc_tree* orc_tree_create(const orc_config* cfg, const double* root_state) {
     t->cfg = *cfg;
     int d = orc_state_dim(cfg->env_id);
     for (int i = 0; i < d; ++i) t->root_state[i] = root_state[i];
-    float obs[4] = {0, 0, 0, 0}; make_obs(cfg->env_id, t->root_state, obs);
+    double obs[ORC_MAX_S] = {0}; make_obs(cfg->env_id, t->root_state, obs);
     new_snode(t, obs);
     stream_init(&t->tree_stream, cfg->seed, 0, (uint32_t)cfg->tree_id, STREAM_TREE);
     t->tlen = -1;
@@ -649,7 +729,7 @@ static int key_less_bytes(double x, double y) {
     float fx = (float)x, fy = (float)y; return memcmp(&fx, &fy, 4) < 0;
 }
 
-int orc_tree_best(orc_tree* t, int32_t* child_rank, double* action) {
+int orc_tree_best(orc_tree* t, int32_t* child_rank, double* action /* [2] */) {
     /* mcts_hash.py:42-50 (insertion order).  spw/dpw first REORDER root.actions by key
      * (mcts_state_...:29, mcts_double_...:30: OrderedDict(sorted(items))), which persists. */
     snode* r = &t->S[0];
@@ -661,7 +741,7 @@ int orc_tree_best(orc_tree* t, int32_t* child_rank, double* action) {
         for (int x = 1; x < n; ++x) {               /* stable insertion sort, like sorted() */
             int cur = order[x], y = x;
             while (y > 0) {
-                double kv = t->A[cur].value, pv = t->A[order[y - 1]].value;
+                double kv = t->A[cur].value[0], pv = t->A[order[y - 1]].value[0];
                 int less = (t->cfg.agent == ORC_AGENT_SPW) ? (kv < pv) : key_less_bytes(kv, pv);
                 if (!less) break;
                 order[y] = order[y - 1]; --y;
@@ -678,21 +758,21 @@ int orc_tree_best(orc_tree* t, int32_t* child_rank, double* action) {
     int pos = rnd_choice(t, ties);
     for (i = 0; i < n; ++i) if (t->A[order[i]].total / (double)t->A[order[i]].na == qmax) { if (pos-- == 0) break; }
     if (i >= n) i = n - 1;
-    *child_rank = i; *action = t->A[order[i]].value;
+    *child_rank = i; action[0] = t->A[order[i]].value[0]; action[1] = t->A[order[i]].value[1];
     free(order);
     return t->fault;
 }
 
-int orc_tree_root_children(const orc_tree* t, int cap, double* action, int64_t* na, double* total) {
+int orc_tree_root_children(const orc_tree* t, int cap, double* action, int64_t* na, double* total, double* action2) {
     int i = 0;
     for (int a = t->S[0].first_act; a >= 0 && i < cap; a = t->A[a].next_act, ++i) {
-        action[i] = t->A[a].value; na[i] = t->A[a].na; total[i] = t->A[a].total;
+        action[i] = t->A[a].value[0]; if (action2) action2[i] = t->A[a].value[1]; na[i] = t->A[a].na; total[i] = t->A[a].total;
     }
     return t->S[0].n_act;
 }
 
 int64_t orc_tree_serialise(const orc_tree* t, int64_t cap, uint8_t* kind, int32_t* depth, int64_t* count,
-                           double* total, uint8_t* terminal, int32_t* fanout, double* action) {
+                           double* total, uint8_t* terminal, int32_t* fanout, double* action, double* action2) {
     /* explicit stack of (kind, index, depth); children pushed in reverse insertion order */
     int64_t n = 0, sp = 0, scap = 1024;
     int* st = (int*)malloc(sizeof(int) * 3 * scap);
@@ -703,9 +783,9 @@ int64_t orc_tree_serialise(const orc_tree* t, int64_t cap, uint8_t* kind, int32_
         if (n < cap) {
             kind[n] = (uint8_t)k; depth[n] = d;
             if (k == 0) { count[n] = t->S[idx].ns; total[n] = t->S[idx].total; terminal[n] = (uint8_t)t->S[idx].terminal;
-                          fanout[n] = t->S[idx].n_act; action[n] = 0.0; }
+                          fanout[n] = t->S[idx].n_act; action[n] = 0.0; if (action2) action2[n] = 0.0; }
             else { count[n] = t->A[idx].na; total[n] = t->A[idx].total; terminal[n] = 0; fanout[n] = t->A[idx].n_child;
-                   action[n] = t->A[idx].value; }
+                   action[n] = t->A[idx].value[0]; if (action2) action2[n] = t->A[idx].value[1]; }
         }
         ++n;
         int m = 0;
@@ -733,8 +813,8 @@ int orc_rollout(int env_id, const double* state, int budget, double gamma, uint6
     stream_init(&t.roll_stream, seed, sim, (uint32_t)tree, j);
     int done = 0, depth = 0; double reward = 0;
     while (!done && depth < budget) {
-        double a = rnd_action(&t, &t.roll_stream);
-        float obs[4]; double r; int term;
+        double a[2]; rnd_action(&t, &t.roll_stream, a);
+        double obs[ORC_MAX_S]; double r; int term;
         env_step(&t, a, obs, &r, &term);
         reward += r * pow(gamma, depth);
         done = term; depth++;
@@ -759,7 +839,7 @@ static void* many_worker(void* p) {
         orc_tree_run(t, j->n_sim, NULL, NULL, -1);
         for (int a = 0; a < A; ++a) { j->na[i * A + a] = 0; j->total[i * A + a] = 0; }
         for (int a = t->S[0].first_act; a >= 0; a = t->A[a].next_act) {
-            int k = (int)t->A[a].value; j->na[i * A + k] = t->A[a].na; j->total[i * A + k] = t->A[a].total;
+            int k = (int)t->A[a].value[0]; j->na[i * A + k] = t->A[a].na; j->total[i * A + k] = t->A[a].total;
         }
         int64_t cc[8]; orc_tree_counters(t, cc);
         for (int k = 0; k < 8; ++k) j->counters[k] += cc[k];

@@ -10,7 +10,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "c", "libisla_oracle.so")
 
-ENV_CARTPOLE, ENV_PENDULUM, ENV_MOUNTAINCAR, ENV_FROZENLAKE = 0, 1, 2, 3
+ENV_CARTPOLE, ENV_PENDULUM, ENV_MOUNTAINCAR, ENV_FROZENLAKE, ENV_CURVE = 0, 1, 2, 3, 4
 AGENT_VANILLA, AGENT_APW, AGENT_SPW, AGENT_DPW = 0, 1, 2, 3
 BUDGET_TO_MAX_DEPTH, BUDGET_ZERO = 0, 1
 EXPAND_RANDOM, EXPAND_VOO, EXPAND_GENETIC2 = 0, 1, 2
@@ -20,7 +20,8 @@ class Config(C.Structure):
     _fields_ = [
         ("env_id", C.c_int32), ("agent", C.c_int32), ("n_actions", C.c_int32), ("max_depth", C.c_int32),
         ("budget_mode", C.c_int32), ("rollouts_per_leaf", C.c_int32), ("expansion", C.c_int32),
-        ("voo_n_samples", C.c_int32), ("voo_max_try", C.c_int32), ("reserved", C.c_int32),
+        ("voo_n_samples", C.c_int32), ("voo_max_try", C.c_int32), ("grid0", C.c_int32), ("grid1", C.c_int32),
+        ("reserved", C.c_int32),
         ("C", C.c_double), ("gamma", C.c_double), ("alpha1", C.c_double), ("k1", C.c_double),
         ("alpha2", C.c_double), ("k2", C.c_double), ("epsilon", C.c_double),
         ("seed", C.c_uint64), ("tree_id", C.c_uint64),
@@ -55,9 +56,9 @@ def lib():
         L.orc_tree_best.restype = C.c_int
         L.orc_tree_best.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_tree_root_children.restype = C.c_int
-        L.orc_tree_root_children.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_tree_root_children.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_tree_serialise.restype = C.c_int64
-        L.orc_tree_serialise.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7
+        L.orc_tree_serialise.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 8
         L.orc_tree_counters.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_run_many.restype = C.c_int
         L.orc_run_many.argtypes = [C.POINTER(Config), C.c_void_p, C.c_int64, C.c_int, C.c_int,
@@ -65,7 +66,9 @@ def lib():
         L.orc_state_dim.restype = C.c_int
         L.orc_state_dim.argtypes = [C.c_int]
         L.orc_env_step.restype = C.c_int
-        L.orc_env_step.argtypes = [C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_env_step.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_action_dim.restype = C.c_int
+        L.orc_action_dim.argtypes = [C.c_int]
         L.orc_env_reset.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]
         L.orc_rollout.restype = C.c_int
         L.orc_rollout.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_uint64, C.c_uint64,
@@ -81,15 +84,15 @@ def _p(a):
 
 def make_config(env_id, agent=AGENT_VANILLA, n_actions=0, max_depth=500, budget_mode=BUDGET_TO_MAX_DEPTH,
                 rollouts_per_leaf=1, expansion=EXPAND_RANDOM, voo_n_samples=5, voo_max_try=1000, C_=1.0,
-                gamma=0.99, alpha1=0.0, k1=1.0, alpha2=0.0, k2=1.0, epsilon=0.7, seed=0, tree_id=0) -> Config:
+                gamma=0.99, alpha1=0.0, k1=1.0, alpha2=0.0, k2=1.0, epsilon=0.7, seed=0, tree_id=0, grid0=0, grid1=0) -> Config:
     return Config(env_id, agent, n_actions, max_depth, budget_mode, rollouts_per_leaf, expansion,
-                  voo_n_samples, voo_max_try, 0, C_, gamma, alpha1, k1, alpha2, k2, epsilon, seed, tree_id)
+                  voo_n_samples, voo_max_try, grid0, grid1, 0, C_, gamma, alpha1, k1, alpha2, k2, epsilon, seed, tree_id)
 
 
 class Tree:
     def __init__(self, cfg: Config, root_state):
         self.cfg = cfg
-        self._root = np.zeros(4, dtype=np.float64)
+        self._root = np.zeros(8, dtype=np.float64)
         rs = np.asarray(root_state, dtype=np.float64).reshape(-1)
         self._root[: rs.size] = rs
         self._h = lib().orc_tree_create(C.byref(cfg), _p(self._root))
@@ -119,16 +122,19 @@ class Tree:
 
     def best(self):
         rank = C.c_int32(0)
-        act = C.c_double(0)
-        rc = lib().orc_tree_best(self._h, C.byref(rank), C.byref(act))
-        return rc, rank.value, act.value
+        act = np.zeros(2, np.float64)
+        rc = lib().orc_tree_best(self._h, C.byref(rank), _p(act))
+        self.best_action2 = float(act[1])
+        return rc, rank.value, float(act[0])
 
     def root_children(self):
-        n = lib().orc_tree_root_children(self._h, 0, None, None, None)
+        n = lib().orc_tree_root_children(self._h, 0, None, None, None, None)
         a = np.zeros(n, np.float64)
+        a2 = np.zeros(n, np.float64)
         na = np.zeros(n, np.int64)
         tot = np.zeros(n, np.float64)
-        lib().orc_tree_root_children(self._h, n, _p(a), _p(na), _p(tot))
+        lib().orc_tree_root_children(self._h, n, _p(a), _p(na), _p(tot), _p(a2))
+        self.root_action2 = a2
         return a, na, tot
 
     def counters(self):
@@ -147,10 +153,11 @@ class Tree:
         term = np.zeros(cap, np.uint8)
         fan = np.zeros(cap, np.int32)
         act = np.zeros(cap, np.float64)
-        n = lib().orc_tree_serialise(self._h, cap, _p(kind), _p(depth), _p(count), _p(total), _p(term), _p(fan), _p(act))
+        act2 = np.zeros(cap, np.float64)
+        n = lib().orc_tree_serialise(self._h, cap, _p(kind), _p(depth), _p(count), _p(total), _p(term), _p(fan), _p(act), _p(act2))
         assert n <= cap
         return dict(kind=kind[:n], depth=depth[:n], count=count[:n], total=total[:n], terminal=term[:n],
-                    fanout=fan[:n], action=act[:n])
+                    fanout=fan[:n], action=act[:n], action2=act2[:n])
 
 
 def run_many(cfg: Config, roots, n_sim, n_threads=1):
@@ -171,26 +178,29 @@ def state_dim(env_id):
 
 
 def env_step(env_id, state, action):
-    s = np.zeros(4, np.float64)
+    s = np.zeros(8, np.float64)
     st = np.asarray(state, np.float64).reshape(-1)
     s[: st.size] = st
-    ns = np.zeros(4, np.float64)
+    a = np.zeros(2, np.float64)
+    av = np.asarray(action, np.float64).reshape(-1)
+    a[: av.size] = av
+    ns = np.zeros(8, np.float64)
     r = C.c_double(0)
     t = C.c_int32(0)
-    obs = np.zeros(4, np.float32)
-    lib().orc_env_step(env_id, _p(s), float(action), _p(ns), C.byref(r), C.byref(t), _p(obs))
+    obs = np.zeros(8, np.float64)
+    lib().orc_env_step(env_id, _p(s), _p(a), _p(ns), C.byref(r), C.byref(t), _p(obs))
     d = state_dim(env_id)
     return ns[:d].copy(), r.value, bool(t.value), obs
 
 
 def env_reset(env_id, seed, index):
-    s = np.zeros(4, np.float64)
+    s = np.zeros(8, np.float64)
     lib().orc_env_reset(env_id, seed, index, _p(s))
     return s[: state_dim(env_id)].copy()
 
 
 def rollout(env_id, state, budget, gamma, seed, tree, sim, j):
-    s = np.zeros(4, np.float64)
+    s = np.zeros(8, np.float64)
     st = np.asarray(state, np.float64).reshape(-1)
     s[: st.size] = st
     ret = C.c_double(0)

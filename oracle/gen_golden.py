@@ -54,6 +54,13 @@ SCENARIOS = {
     # of the two lowest-q actions
     "apw_genetic2_pendulum": dict(agent="MctsApw", env="Pendulum-v1", n_sim=160, C=2.0, gamma=0.95, max_depth=200,
                                   alpha=0.6, k=2, budget="zero", env_seed=3, rng_seed=13, expansion="genetic2", epsilon=0.6),
+    # CurveEnv is the reference's OWN environment (islaMcts/environments/curve_env.py) -- the env sweep.py runs.
+    # APW on the continuous 2-D action box, after two real steps so that the hidden step counter is > 0
+    "apw_curve": dict(agent="MctsApw", env="CurveEnv", n_sim=250, C=11.0, gamma=0.99, max_depth=50, alpha=0.5, k=3,
+                      budget="zero", env_seed=0, rng_seed=14, pre_steps=[[-5.0, -30.0], [-5.0, -30.0], [-4.0, -25.0]]),
+    # vanilla MctsHash on DiscreteCurveEnv([5 accelerations, 7 angles]) (sweep_vanilla.py:177), real rollouts
+    "hash_curve_discrete": dict(agent="MctsHash", env="DiscreteCurveEnv", n_sim=300, C=5.0, gamma=0.95, max_depth=12,
+                                budget="to_max_depth", env_seed=0, rng_seed=15, grid=[5, 7], pre_steps=[0, 0, 0]),
     # SPW (with the state_variable shim) on CartPole: k=1 always re-expands; k=0.4 resamples and descends
     "spw_cartpole_k1": dict(agent="MctsSpw", env="CartPole-v1", n_sim=150, C=1.0, gamma=0.99, max_depth=500,
                             alpha=0.5, k=1, budget="zero", env_seed=0, rng_seed=9),
@@ -82,14 +89,24 @@ def run_scenario(name: str, sc: dict):
     env_name = sc["env"]
     agent_key = sc["agent"]
     api = 5 if agent_key == "Mcts" else 4  # mcts.py:79-82 indexes vals[0..2]; the others unpack 4 (mcts_hash.py:93)
-    if env_name == "FrozenLake-v1" and agent_key == "MctsHash":
+    if env_name in ("CurveEnv", "DiscreteCurveEnv"):
+        env = R.CurveEnv() if env_name == "CurveEnv" else R.DiscreteCurveEnv(sc["grid"])
+        env.action_space.seed(sc["env_seed"])
+        obs = env.reset()
+        for a in sc.get("pre_steps", []):
+            obs, _, done, _ = env.step(np.asarray(a, dtype=np.float64) if env_name == "CurveEnv" else int(a))
+            assert not done, "pre_steps must keep the car on the track"
+        root_state = np.array([*env.car.state, float(env.n_step)], dtype=np.float64)
+    elif env_name == "FrozenLake-v1" and agent_key == "MctsHash":
         env = _LakeHashEnv(api=4, seed=sc["env_seed"])
+        obs = env.reset()
+        root_state = pyenvs.env_state_vector(env)
     else:
         env = pyenvs.make(env_name, api=api, seed=sc["env_seed"])
-    obs = env.reset()
-    if api == 5:
-        obs = obs[0]
-    root_state = pyenvs.env_state_vector(env)
+        obs = env.reset()
+        if api == 5:
+            obs = obs[0]
+        root_state = pyenvs.env_state_vector(env)
     tr = T.Trace()
     env.action_space = T.RecordingSpace(env.action_space, tr)
     n_actions = getattr(env.action_space, "n", None)
@@ -133,6 +150,7 @@ def run_scenario(name: str, sc: dict):
     ser = T.serialise_reference_tree(agent.root)
     ch = list(agent.root.actions.values())
     root_action = np.array([float(np.asarray(c.data, dtype=np.float64).reshape(-1)[0]) for c in ch])
+    root_action2 = np.array([float(np.asarray(c.data, dtype=np.float64).reshape(-1)[1]) if np.size(c.data) > 1 else 0.0 for c in ch])
     root_na = np.array([c.na for c in ch], dtype=np.int64)
     root_total = np.array([c.total for c in ch], dtype=np.float64)
     if action is None:
@@ -148,16 +166,53 @@ def run_scenario(name: str, sc: dict):
         root_state=root_state,
         trace_kind=kinds, trace_value=vals,
         q_values=np.asarray(agent.q_values, dtype=np.float64),
-        root_action=root_action, root_na=root_na, root_total=root_total,
+        root_action=root_action, root_action2=root_action2, root_na=root_na, root_total=root_total,
         fit_action=np.float64(action_val),
-        env_steps=np.int64(pyenvs.STEP_COUNTER[0] - steps0),
+        env_steps=np.int64(pyenvs.STEP_COUNTER[0] - steps0) if env_name not in ("CurveEnv", "DiscreteCurveEnv") else np.int64(-1),
         **{f"tree_{k}": v for k, v in ser.items()},
     )
     return out
 
 
+def curve_env_vectors(n_walks=400, seed=77):
+    """Step vectors of the reference's OWN CurveEnv (islaMcts/environments/curve_env.py:121-177):
+    random walks from reset() and from random on-track poses, recording (state+n_step, action) ->
+    (next state, reward, terminal).  Pins the env arithmetic of the oracle / device CurveEnv."""
+    R = ref_loader.load()
+    rng = np.random.default_rng(seed)
+    S, A, NS, RW, TM = [], [], [], [], []
+    for w in range(n_walks):
+        env = R.CurveEnv()
+        env.reset()
+        if w % 2:
+            x = rng.uniform(-11.0, 9.0)
+            lo, hi = env.lower_bound(x), env.higher_bound(x)
+            env.car.position[:] = (x, rng.uniform(lo, hi))
+            env.car.velocity = rng.uniform(0.0, 8.0)
+            env.car.angle = rng.uniform(-60.0, 100.0) % 360
+            env.car.state = np.array([*env.car.position, env.car.velocity, env.car.angle])
+            env.n_step = int(rng.integers(0, 30))
+        for _ in range(12):
+            s = np.array([*env.car.state, float(env.n_step)])
+            a = rng.uniform([-5.0, -30.0], [5.0, 30.0]) if w % 4 < 2 else rng.uniform([-5.0, -30.0], [0.0, 0.0])
+            ns, r, done, _ = env.step(a)
+            S.append(s); A.append(a); NS.append(np.array([*ns, float(env.n_step)])); RW.append(float(r)); TM.append(bool(done))
+            if done:
+                break
+    # DiscreteCurveEnv index -> (acceleration, angle) table (curve_env.py:180-195)
+    d = R.DiscreteCurveEnv([5, 7])
+    out = dict(state=np.array(S), action=np.array(A), next_state=np.array(NS), reward=np.array(RW),
+               terminal=np.array(TM), grid=np.array([5, 7]), grid_actions=np.array(d.actions, dtype=np.float64))
+    os.makedirs(os.path.join(GOLDEN_DIR, "env"), exist_ok=True)
+    path = os.path.join(GOLDEN_DIR, "env", "curve_env_steps.npz")
+    np.savez_compressed(path, **out)
+    print(f"curve_env_steps: {len(S)} steps, terminal {np.mean(TM):.2f}, wins {(np.array(RW) > 100).sum()} -> {path}")
+
+
 def main(names=None):
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    if not names or "curve_env_steps" in names:
+        curve_env_vectors()
     for name, sc in SCENARIOS.items():
         if names and name not in names:
             continue

@@ -55,7 +55,11 @@ def load():
         g = _mod("gym", Env=type("Env", (), {}))
         g.spaces = _mod("gym.spaces", Discrete=type("Discrete", (), {}), Box=type("Box", (), {}))
     if "gymnasium" not in sys.modules:
-        _mod("gymnasium", Env=type("Env", (), {}))
+        from oracle import pyenvs
+        gy = _mod("gymnasium", Env=type("Env", (), {"unwrapped": property(lambda self: self)}))
+        gy.spaces = _mod("gymnasium.spaces", Discrete=pyenvs.Discrete, Box=pyenvs.Box)
+        gy.envs = _mod("gymnasium.envs")
+        gy.envs.registration = _mod("gymnasium.envs.registration", register=lambda **kw: None)
     sys.path.insert(0, REFERENCE_ROOT)
     try:
         from islaMcts.agents.mcts import Mcts
@@ -68,6 +72,7 @@ def load():
         from islaMcts.agents.parameters.dpw_parameters import DpwParameters
         import islaMcts.utils.action_selection_functions as asf
         import islaMcts.agents.abstract_mcts as abstract_mcts
+        from islaMcts.environments.curve_env import CurveEnv, DiscreteCurveEnv
     finally:
         sys.path.remove(REFERENCE_ROOT)
     import islaMcts as _pkg
@@ -111,6 +116,8 @@ def load():
         voo=asf.voo,
         asf=asf,
         abstract_mcts=abstract_mcts,
+        CurveEnv=CurveEnv,
+        DiscreteCurveEnv=DiscreteCurveEnv,
     )
     _loaded = ns
     return ns

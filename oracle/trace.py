@@ -133,12 +133,12 @@ def recording(trace: Trace, seed: int):
 # ---------------------------------------------------------------------------------
 # DFS pre-order, children in INSERTION order (python dict order in the reference):
 #   state record : (kind=0, depth, ns,  total, terminal, n_actions,  0.0)
-#   action record: (kind=1, depth, na,  total, 0,        n_children, action_value)
+#   action record: (kind=1, depth, na,  total, 0,        n_children, action_value[, action_value2])
 # ``depth`` counts state levels (root = 0; an action node has its parent's depth).
 
 
 def serialise_reference_tree(root, action_to_float=None):
-    kinds, depths, counts, totals, flags, fanout, avals = [], [], [], [], [], [], []
+    kinds, depths, counts, totals, flags, fanout, avals, avals2 = [], [], [], [], [], [], [], []
     if action_to_float is None:
         def action_to_float(a):
             return float(np.asarray(a, dtype=np.float64).reshape(-1)[0])
@@ -154,6 +154,7 @@ def serialise_reference_tree(root, action_to_float=None):
             flags.append(int(bool(node.terminal)))
             fanout.append(len(node.actions))
             avals.append(0.0)
+            avals2.append(0.0)
             for act in reversed(list(node.actions.values())):
                 stack.append((1, act, depth))
         else:
@@ -164,6 +165,8 @@ def serialise_reference_tree(root, action_to_float=None):
             flags.append(0)
             fanout.append(len(node.children))
             avals.append(action_to_float(node.data))
+            flat = np.asarray(node.data, dtype=np.float64).reshape(-1)
+            avals2.append(float(flat[1]) if flat.size > 1 else 0.0)
             for st in reversed(list(node.children.values())):
                 stack.append((0, st, depth + 1))
     return {
@@ -174,4 +177,5 @@ def serialise_reference_tree(root, action_to_float=None):
         "terminal": np.asarray(flags, dtype=np.uint8),
         "fanout": np.asarray(fanout, dtype=np.int32),
         "action": np.asarray(avals, dtype=np.float64),
+        "action2": np.asarray(avals2, dtype=np.float64),   # second action dimension (CurveEnv), else 0
     }

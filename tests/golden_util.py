@@ -7,7 +7,8 @@ import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
-ENV_IDS = {"CartPole-v1": 0, "Pendulum-v1": 1, "MountainCarContinuous-v0": 2, "FrozenLake-v1": 3}
+ENV_IDS = {"CartPole-v1": 0, "Pendulum-v1": 1, "MountainCarContinuous-v0": 2, "FrozenLake-v1": 3,
+           "CurveEnv": 4, "DiscreteCurveEnv": 4}
 AGENTS = {"Mcts": 0, "MctsHash": 0, "MctsApw": 1, "MctsSpw": 2, "MctsDpw": 3}
 
 
@@ -32,6 +33,8 @@ def engine_kwargs(cfg):
         kw.update(alpha1=cfg["alpha"], k1=cfg["k"])
     if agent == 3:
         kw.update(alpha1=cfg["alpha1"], k1=cfg["k1"], alpha2=cfg["alpha2"], k2=cfg["k2"])
+    if cfg.get("grid"):
+        kw.update(grid0=cfg["grid"][0], grid1=cfg["grid"][1], n_actions=cfg["grid"][0] * cfg["grid"][1])
     if cfg.get("expansion") == "voo":
         kw.update(expansion=1, epsilon=cfg["epsilon"], voo_n_samples=cfg["voo_n_samples"],
                   voo_max_try=cfg["voo_max_try"])
@@ -49,3 +52,5 @@ def assert_tree_equal(got, g, rtol=1e-9, atol=1e-9, label=""):
         assert bad.size == 0, f"{label}{k} differs at records {bad[:8]}: {np.asarray(got[k])[bad[:8]]} vs {exp[bad[:8]]}"
     np.testing.assert_allclose(got["total"], g["tree_total"], rtol=rtol, atol=atol, err_msg=label + "total")
     np.testing.assert_allclose(got["action"], g["tree_action"], rtol=0, atol=1e-12, err_msg=label + "action")
+    if "tree_action2" in g and "action2" in got:
+        np.testing.assert_allclose(got["action2"], g["tree_action2"], rtol=0, atol=1e-12, err_msg=label + "action2")

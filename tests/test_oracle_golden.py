@@ -32,8 +32,12 @@ def test_oracle_replays_reference_trace(name):
     np.testing.assert_array_equal(na, g["root_na"])
     np.testing.assert_allclose(tot, g["root_total"], rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(a, g["root_action"], rtol=0, atol=1e-12)
-    # counted env.step calls of the reference run (tree-level replay + rollouts)
-    assert tree.counters()["env_steps"] == int(g["env_steps"])
+    if "root_action2" in g:
+        np.testing.assert_allclose(tree.root_action2, g["root_action2"], rtol=0, atol=1e-12)
+    # counted env.step calls of the reference run (tree-level replay + rollouts); the reference's own
+    # CurveEnv is not instrumented (-1)
+    if int(g["env_steps"]) >= 0:
+        assert tree.counters()["env_steps"] == int(g["env_steps"])
     # the invariants SURVEY.md 8(a) lists for the reference's trees
     assert tree.serialise()["count"][0] == cfg["n_sim"]          # root ns
     if cfg["agent"] in ("Mcts", "MctsHash", "MctsApw"):
@@ -62,3 +66,17 @@ def test_known_answer_values_of_reference_unit_tests():
     ser = tree.serialise()
     assert ser["total"].tolist() == [1.0, 1.0, 1.0]   # G = r + gamma*0
     assert tree.counters()["rollout_steps"] == 0
+
+
+def test_oracle_curve_env_matches_reference_step_vectors():
+    """The reference's own CurveEnv (environments/curve_env.py:121-177) stepped on 1090 random
+    (state, action) pairs; fixture tests/golden/env/curve_env_steps.npz (oracle/gen_golden.py).
+    State = (x, y, velocity, angle, n_step).  Terminal flags bit-exact, floats to 1e-12."""
+    import os
+    from tests.golden_util import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "env", "curve_env_steps.npz"))
+    for s, a, ns, r, t in zip(z["state"], z["action"], z["next_state"], z["reward"], z["terminal"]):
+        got_ns, got_r, got_t, _ = coracle.env_step(coracle.ENV_CURVE, s, a)
+        assert got_t == bool(t)
+        np.testing.assert_allclose(got_ns, ns, rtol=1e-12, atol=1e-12)
+        assert got_r == pytest.approx(float(r), rel=1e-12)
