@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ISLA_ABI_VERSION 1
+#define ISLA_ABI_VERSION 2
 
 typedef enum {
     ISLA_OK = 0,
@@ -35,8 +35,9 @@ typedef enum {
     ISLA_ERR_TRACE = -4         /* scripted run: trace exhausted / kind mismatch / value out of range */
 } isla_status;
 
-/* environments (gym ids the Python layer recognises) */
-enum { ISLA_ENV_CARTPOLE = 0, ISLA_ENV_PENDULUM = 1, ISLA_ENV_MOUNTAINCAR = 2, ISLA_ENV_FROZENLAKE = 3 };
+/* environments: the gym ids the Python layer recognises, and the reference's own CurveEnv / DiscreteCurveEnv
+ * (islaMcts/environments/curve_env.py:59-199; state = x, y, velocity, angle, n_step) */
+enum { ISLA_ENV_CARTPOLE = 0, ISLA_ENV_PENDULUM = 1, ISLA_ENV_MOUNTAINCAR = 2, ISLA_ENV_FROZENLAKE = 3, ISLA_ENV_CURVE = 4 };
 /* agents: islaMcts/agents/{mcts,mcts_hash}.py ; mcts_action_... ; mcts_state_... ; mcts_double_... */
 enum { ISLA_AGENT_VANILLA = 0, ISLA_AGENT_APW = 1, ISLA_AGENT_SPW = 2, ISLA_AGENT_DPW = 3 };
 /* rollout budget: MctsHash depth accounting (mcts_hash.py:34,116,126) or the zero-length rollouts the
@@ -65,6 +66,8 @@ typedef struct {
     int32_t block_threads;      /* CTA-per-tree kernel: threads per tree (multiple of 32); 0 = auto */
     int32_t sim_capacity;       /* max cumulative simulations per tree the workspace is sized for */
     int32_t tuning;             /* experiment flags for A/B timing; 0 = defaults */
+    int32_t action_grid0;       /* ISLA_ENV_CURVE: DiscreteCurveEnv([g0, g1]) = g0 accelerations x g1 steering angles */
+    int32_t action_grid1;       /*   (curve_env.py:184-199; n_actions = g0*g1 <= 128); both 0 = the continuous 2-D CurveEnv box */
     double C;                   /* param.C */
     double gamma;               /* param.gamma */
     double alpha1, k1;          /* PwParameters.alpha/k ; DpwParameters.alphaApw/kApw */
@@ -83,6 +86,8 @@ typedef struct {
     int32_t state_dim;
     int32_t real_bytes;         /* 4 or 8 */
     int32_t n_actions;
+    int32_t action_dim;         /* reals per stored action: 1, or 2 for the continuous CurveEnv box */
+    int32_t reserved0;
     int64_t slots_per_tree;     /* thread-per-tree: edge slots per tree = blocks * A; slot = block * A + action */
     int64_t rec_offset, rec_stride;         /* thread-per-tree: node blocks {double total[A]; int32 na[A]; uint32 link[A]} */
     int64_t state_offset, state_stride;     /* env states, state_dim reals per slot */
@@ -132,16 +137,16 @@ int isla_engine_run_scripted(isla_engine* e, int64_t tree, int32_t n_sim, const 
  * best_dev[n_trees] = chosen action index.  scripted_pos >= 0 replaces the tie-break draw. */
 int isla_engine_root_stats(isla_engine* e, int64_t* na_dev, double* total_dev, void* stream);
 /* best_rank_dev[n_trees]: position of the chosen child in root.actions (insertion order; spw/dpw: after the
- * persistent key-sorted re-ordering of mcts_state_...:29 / mcts_double_...:30); best_action_dev[n_trees]
+ * persistent key-sorted re-ordering of mcts_state_...:29 / mcts_double_...:30); best_action_dev[n_trees][action_dim]
  * (optional, may be NULL): its action value (discrete agents: the action index). */
 int isla_engine_best(isla_engine* e, int32_t scripted_pos, int32_t* best_rank_dev, double* best_action_dev, void* stream);
-/* Root children of one tree in root.actions order (continuous-action agents: apw/dpw): action value,
- * ActionNode.na, ActionNode.total; count_dev[0] = number of children (may exceed cap). */
+/* Root children of one tree in root.actions order (continuous-action agents: apw/dpw): action value
+ * (action_dev[cap][action_dim]), ActionNode.na, ActionNode.total; count_dev[0] = number of children (may exceed cap). */
 int isla_engine_root_children(isla_engine* e, int64_t tree, int32_t cap, double* action_dev, int64_t* na_dev,
                               double* total_dev, int32_t* count_dev, void* stream);
 /* CTA-per-tree engine: byte offsets of the SoA arrays inside one tree's pool, for host-side decoding
  * (order: s_total, s_term_reward, s_ns, s_flags, s_coff, s_ccap, s_ccnt, s_state, a_total, a_value, a_na,
- *  a_visits, a_child, ipool, path_s, path_a, path_r, path_flag, meta, path_g, end). */
+ *  a_visits, a_child, ipool, path_s, path_a, path_r, path_flag, meta, path_g, a_value2, end). */
 int isla_engine_pool_offsets(const isla_engine* e, int64_t out[24]);
 
 /* Device counters int64[8]: [0] env steps executed, [1] rollout steps, [2] tree levels visited,
@@ -155,17 +160,20 @@ int isla_merge_root_stats(const int64_t* na_dev, const double* total_dev, const 
                           int64_t n_trees, int32_t n_actions, int64_t n_roots, int64_t* na_out_dev,
                           double* total_out_dev, void* stream);
 
-/* gym env.step over a batch (parity of the dynamics): states [n][state_dim], actions [n] (discrete:
- * index as a real), precision selects float/double buffers for states/actions/rewards. */
+/* env.step over a batch (parity of the dynamics): states [n][state_dim], actions [n][action_dim] (discrete:
+ * index as a real; ISLA_ENV_CURVE: (acceleration, steering) -- DiscreteCurveEnv indices are decoded by the caller),
+ * precision selects float/double buffers for states/actions/rewards. */
 int isla_env_step(int32_t env_id, int32_t precision, const void* states_dev, const void* actions_dev, int64_t n,
                   void* next_states_dev, void* rewards_dev, uint8_t* terminated_dev, void* stream);
 
 /* AbstractStateNode.rollout (abstract_mcts.py:72-91) over a batch: trajectory i starts at
  * states[i] (or, if states_dev == NULL, at the gym reset distribution, Philox reset stream, index i),
  * plays uniformly random actions (stream (seed, tree=i, sim, j=0)) for at most `budget` steps,
- * returns sum r*gamma^t (double) and the steps taken. */
+ * returns sum r*gamma^t (double) and the steps taken.  action_grid0/1: the config fields of the same name; both 0
+ * unless ISLA_ENV_CURVE is to sample the DiscreteCurveEnv grid. */
 int isla_rollout(int32_t env_id, int32_t precision, const void* states_dev, int64_t n, int32_t budget, double gamma,
-                 uint64_t seed, uint32_t sim, double* returns_dev, int32_t* steps_dev, void* stream);
+                 uint64_t seed, uint32_t sim, int32_t action_grid0, int32_t action_grid1, double* returns_dev,
+                 int32_t* steps_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("ISLA_LIB_PATH") or os.path.join(_HERE, "lib", "libisl
 ISLA_OK = 0
 ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_TRACE = -1, -2, -3, -4
 
-ENV_CARTPOLE, ENV_PENDULUM, ENV_MOUNTAINCAR, ENV_FROZENLAKE = 0, 1, 2, 3
+ENV_CARTPOLE, ENV_PENDULUM, ENV_MOUNTAINCAR, ENV_FROZENLAKE, ENV_CURVE = 0, 1, 2, 3, 4
 AGENT_VANILLA, AGENT_APW, AGENT_SPW, AGENT_DPW = 0, 1, 2, 3
 BUDGET_TO_MAX_DEPTH, BUDGET_ZERO = 0, 1
 EXPAND_RANDOM, EXPAND_VOO, EXPAND_GENETIC2 = 0, 1, 2
@@ -35,6 +35,7 @@ class IslaConfig(C.Structure):
         ("budget_mode", C.c_int32), ("rollouts_per_leaf", C.c_int32), ("expansion", C.c_int32),
         ("voo_n_samples", C.c_int32), ("voo_max_try", C.c_int32), ("precision", C.c_int32),
         ("kernel", C.c_int32), ("block_threads", C.c_int32), ("sim_capacity", C.c_int32), ("tuning", C.c_int32),
+        ("action_grid0", C.c_int32), ("action_grid1", C.c_int32),
         ("C", C.c_double), ("gamma", C.c_double), ("alpha1", C.c_double), ("k1", C.c_double),
         ("alpha2", C.c_double), ("k2", C.c_double), ("epsilon", C.c_double),
         ("seed", C.c_uint64), ("tree_id_base", C.c_uint64), ("n_trees", C.c_int64),
@@ -44,6 +45,7 @@ class IslaConfig(C.Structure):
 class IslaLayout(C.Structure):
     _fields_ = [
         ("kernel", C.c_int32), ("state_dim", C.c_int32), ("real_bytes", C.c_int32), ("n_actions", C.c_int32),
+        ("action_dim", C.c_int32), ("reserved0", C.c_int32),
         ("slots_per_tree", C.c_int64), ("rec_offset", C.c_int64), ("rec_stride", C.c_int64),
         ("state_offset", C.c_int64), ("state_stride", C.c_int64), ("gfirst_offset", C.c_int64), ("gfirst_stride", C.c_int64),
         ("meta_offset", C.c_int64), ("path_offset", C.c_int64), ("pathg_offset", C.c_int64), ("pvown_offset", C.c_int64),
@@ -76,7 +78,7 @@ SYMBOLS = {
     "isla_merge_root_stats": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int64, _P, _P, _P]),
     "isla_env_step": (C.c_int, [C.c_int32, C.c_int32, _P, _P, C.c_int64, _P, _P, _P, _P]),
     "isla_rollout": (C.c_int, [C.c_int32, C.c_int32, _P, C.c_int64, C.c_int32, C.c_double, C.c_uint64, C.c_uint32,
-                               _P, _P, _P]),
+                               C.c_int32, C.c_int32, _P, _P, _P]),
 }
 
 _lib = None

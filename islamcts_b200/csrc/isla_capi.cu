@@ -80,7 +80,16 @@ static int validate(const isla_config& c) {
     if (c.sim_capacity < 1) { set_error("sim_capacity must be >= 1"); return ISLA_ERR_INVALID; }
     if (c.max_depth < 0) { set_error("max_depth must be >= 0"); return ISLA_ERR_INVALID; }
     if (c.precision != ISLA_PRECISION_F32 && c.precision != ISLA_PRECISION_F64) { set_error("bad precision"); return ISLA_ERR_INVALID; }
-    const int A = env_n_actions(c.env_id);
+    if (c.env_id == ISLA_ENV_CURVE) {
+        const bool grid = c.action_grid0 != 0 || c.action_grid1 != 0;
+        if (grid && (c.action_grid0 < 1 || c.action_grid1 < 1 || (int64_t)c.action_grid0 * c.action_grid1 > 128)) {
+            set_error("DiscreteCurveEnv grid %d x %d: need 1 <= g0*g1 <= 128", c.action_grid0, c.action_grid1); return ISLA_ERR_INVALID;
+        }
+        if (c.agent == ISLA_AGENT_SPW || c.agent == ISLA_AGENT_DPW) {
+            set_error("spw/dpw poke the observation into env.state; CurveEnv keeps its state in env.car"); return ISLA_ERR_INVALID;
+        }
+    }
+    const int A = c.env_id == ISLA_ENV_CURVE ? c.action_grid0 * c.action_grid1 : env_n_actions(c.env_id);
     if ((c.agent == ISLA_AGENT_VANILLA || c.agent == ISLA_AGENT_SPW) && A == 0) {
         set_error("agent %d needs a discrete action space; env %d is continuous", c.agent, c.env_id); return ISLA_ERR_INVALID;
     }

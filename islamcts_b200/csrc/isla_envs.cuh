@@ -1,8 +1,11 @@
-// On-device environment dynamics: CartPole-v1, Pendulum-v1, MountainCarContinuous-v0, FrozenLake-v1.
+// On-device environment dynamics: CartPole-v1, Pendulum-v1, MountainCarContinuous-v0, FrozenLake-v1 and the
+// reference's own CurveEnv / DiscreteCurveEnv.
 //
-// Replaces gym's env.step() on the hot path (reference call sites: islaMcts/agents/mcts.py:79,
-// mcts_hash.py:93, abstract_mcts.py:85).  The arithmetic is third-party Gymnasium, absent from
+// Replaces env.step() on the hot path (reference call sites: islaMcts/agents/mcts.py:79,
+// mcts_hash.py:93, abstract_mcts.py:85).  The gym arithmetic is third-party Gymnasium, absent from
 // /root/reference and unpinned by it; the definitions followed are the ones SURVEY.md section 8c restates.
+// CurveEnv is reference code (islaMcts/environments/curve_env.py) and is pinned by step vectors generated from it
+// (tests/golden/env/curve_env_steps.npz).
 //
 // Two arithmetic modes, chosen at compile time by the state type T:
 //   float  : the fast path (state in registers, FMA contraction allowed, fp32 trig).
@@ -18,7 +21,10 @@
 
 namespace isla {
 
-enum : int { ENV_CARTPOLE = 0, ENV_PENDULUM = 1, ENV_MOUNTAINCAR = 2, ENV_FROZENLAKE = 3, ENV_COUNT = 4 };
+enum : int { ENV_CARTPOLE = 0, ENV_PENDULUM = 1, ENV_MOUNTAINCAR = 2, ENV_FROZENLAKE = 3, ENV_CURVE = 4, ENV_COUNT = 5 };
+
+// DiscreteCurveEnv([g0, g1]) (curve_env.py:184-199): g0 accelerations x g1 steering angles; g0 == 0 = the continuous CurveEnv
+struct ActionGrid { int g0, g1; };
 
 template <typename T> struct Ar;
 template <> struct Ar<double> {
@@ -47,13 +53,18 @@ template <> struct Ar<float> {
 };
 
 template <int ENV> struct EnvTraits;
-template <> struct EnvTraits<ENV_CARTPOLE>    { static constexpr int S = 4, A = 2; static constexpr bool kContinuous = false; };
-template <> struct EnvTraits<ENV_PENDULUM>    { static constexpr int S = 2, A = 0; static constexpr bool kContinuous = true;  };
-template <> struct EnvTraits<ENV_MOUNTAINCAR> { static constexpr int S = 2, A = 0; static constexpr bool kContinuous = true;  };
-template <> struct EnvTraits<ENV_FROZENLAKE>  { static constexpr int S = 1, A = 4; static constexpr bool kContinuous = false; };
+// S: env state reals; A: discrete actions (0: Box, or decided at run time by the ActionGrid); AD: action dimensions
+template <> struct EnvTraits<ENV_CARTPOLE>    { static constexpr int S = 4, A = 2, AD = 1; static constexpr bool kContinuous = false; };
+template <> struct EnvTraits<ENV_PENDULUM>    { static constexpr int S = 2, A = 0, AD = 1; static constexpr bool kContinuous = true;  };
+template <> struct EnvTraits<ENV_MOUNTAINCAR> { static constexpr int S = 2, A = 0, AD = 1; static constexpr bool kContinuous = true;  };
+template <> struct EnvTraits<ENV_FROZENLAKE>  { static constexpr int S = 1, A = 4, AD = 1; static constexpr bool kContinuous = false; };
+// state = (x, y, velocity, angle [deg], n_step): the step counter is hidden state of the env object (it scales rewards)
+template <> struct EnvTraits<ENV_CURVE>       { static constexpr int S = 5, A = 0, AD = 2; static constexpr bool kContinuous = true;  };
 
-__host__ __device__ inline int env_state_dim(int env) { return env == ENV_CARTPOLE ? 4 : env == ENV_FROZENLAKE ? 1 : 2; }
+__host__ __device__ inline int env_state_dim(int env) { return env == ENV_CARTPOLE ? 4 : env == ENV_FROZENLAKE ? 1 : env == ENV_CURVE ? 5 : 2; }
+// fixed discrete action count of the gym envs (0: continuous, or CurveEnv whose count comes from the ActionGrid)
 __host__ __device__ inline int env_n_actions(int env) { return env == ENV_CARTPOLE ? 2 : env == ENV_FROZENLAKE ? 4 : 0; }
+__host__ __device__ inline int env_action_dim(int env) { return env == ENV_CURVE ? 2 : 1; }
 __host__ __device__ inline void env_action_bounds(int env, float& lo, float& hi) {
     if (env == ENV_PENDULUM) { lo = -2.0f; hi = 2.0f; } else { lo = -1.0f; hi = 1.0f; }
 }
@@ -219,6 +230,107 @@ template <typename T> struct Env<ENV_FROZENLAKE, T> {
     }
 };
 
+// ---------------------------------------------------------------- CurveEnv (islaMcts/environments/curve_env.py)
+// Car.update :34-56 and CurveEnv.step :121-177.  The car must stay between two parabolas; the reference tests
+// 100 points of np.linspace(last_pos, new_pos) against them (:136-143).
+//   upper(x) - y is CONCAVE along the segment, so its minimum over the 100 points is at an end point;
+//   y - lower(x) is a CONVEX quadratic in the point index, so its minimum over the integers 0..99 is next to the
+//   real-valued vertex.
+// Hence at most six points decide containment.  The double instantiation evaluates exactly the reference's
+// expressions at those points and falls back to the full 100-point loop whenever a decisive margin is within 1e-9 of
+// zero, so its verdict is always the one of the 100-point test; the float instantiation (rollout fast path) uses the
+// six points alone.
+template <typename T> struct Env<ENV_CURVE, T> {
+    using A_ = Ar<T>;
+    static __device__ __forceinline__ T lower(T x) { return A_::add(A_::mul(T(-(1.0 / 50)), A_::mul(T(3), A_::mul(x, x))), T(27.3)); }
+    static __device__ __forceinline__ T upper(T x) { return A_::add(A_::mul(T(-(1.0 / 50)), A_::mul(x, x)), T(27.5)); }
+    // np.linspace(a, b, 100)[i] with step = (b - a) / 99
+    static __device__ __forceinline__ T point(T a, T b, T step, int i) { return i == 99 ? b : A_::add(A_::mul(T(i), step), a); }
+    static __device__ __forceinline__ T gradient(bool second, int idx) {
+        // gradient_1 / gradient_2 of CurveEnv.__init__ (:62-74): 1.8*idx up to 26 (mirrored to 1.8*(55-idx) for x >= 0), 50 above
+        if (idx >= 27) return T(50);
+        if constexpr (sizeof(T) == 8) return __dmul_rn(1.80, (double)(second ? 55 - idx : idx));
+        else return 1.8f * (float)(second ? 55 - idx : idx);
+    }
+    static __device__ __forceinline__ bool step2(T (&s)[5], T acceleration, T steer, T& reward) {
+        constexpr T dt = T(0.5);
+        T x = s[0], y = s[1], velocity = s[2], angle = s[3];
+        const T n_step = A_::add(s[4], T(1));
+        const T last_x = x, last_y = y;
+        velocity = A_::add(velocity, A_::mul(acceleration, dt));
+        if (velocity > T(20)) velocity = T(20);
+        if (velocity < T(0)) velocity = T(0);
+        angle = A_::fmodulo(A_::add(angle, steer), T(360));
+        if (angle < T(0)) angle = A_::add(angle, T(360));                     // python float %
+        const T rad = A_::mul(angle, T(3.141592653589793 / 180.0));          // math.radians
+        T sn, cs;
+        A_::sincos(rad, sn, cs);
+        x = A_::add(x, A_::mul(A_::mul(cs, velocity), dt));
+        y = A_::add(y, A_::mul(A_::mul(sn, velocity), dt));
+        const T step_x = A_::div(A_::sub(x, last_x), T(99)), step_y = A_::div(A_::sub(y, last_y), T(99));
+        // candidate points: the two ends and the neighbourhood of the vertex of y - lower(x)
+        //   g(i) = 0.06*(lx + i*sx)^2 + ly + i*sy - 27.3  ->  i* = -(0.12*lx*sx + sy) / (0.12*sx^2)
+        int iv = 0;
+        {
+            const T den = T(0.12) * step_x * step_x;
+            if (den > T(0)) {
+                const T v = -(T(0.12) * last_x * step_x + step_y) / den;
+                iv = v <= T(0) ? 0 : v >= T(99) ? 99 : (int)v;
+            }
+        }
+        T margin = T(1e30);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const int i = k == 0 ? 0 : k == 1 ? 99 : min(max(iv + k - 3, 0), 99);   // iv-1 .. iv+2
+            const T px = point(last_x, x, step_x, i), py = point(last_y, y, step_y, i);
+            margin = A_::fmin_(margin, A_::fmin_(A_::sub(py, lower(px)), A_::sub(upper(px), py)));
+        }
+        bool inside = margin >= T(0);
+        if constexpr (sizeof(T) == 8) {
+            if (fabs(margin) < 1e-9) {
+                inside = true;
+                for (int i = 0; i < 100 && inside; ++i) {
+                    const T px = point(last_x, x, step_x, i), py = point(last_y, y, step_y, i);
+                    inside = (py >= lower(px)) && (py <= upper(px));
+                }
+            }
+        }
+        bool term;
+        if (!inside) { term = true; reward = T(-1000); }
+        else if (x >= T(9) && T(20) <= y && y <= T(26)) { term = true; reward = A_::div(T(10000), n_step); }
+        else {
+            term = false;
+            const int idx = y <= T(21) ? 20 : (y >= T(27) ? 27 : (int)y);
+            reward = A_::div(gradient(!(x < T(0)), idx), n_step);
+        }
+        s[0] = x; s[1] = y; s[2] = velocity; s[3] = angle; s[4] = n_step;
+        return term;
+    }
+};
+
+// np.linspace(lo, hi, n)[i] in float64
+__device__ __forceinline__ double linspace_at(double lo, double hi, int n, int i) {
+    if (n <= 1) return lo;
+    if (i == n - 1) return hi;
+    return __dadd_rn(__dmul_rn((double)i, __ddiv_rn(__dsub_rn(hi, lo), (double)(n - 1))), lo);
+}
+// DiscreteCurveEnv: itertools.product(linspace(-5, 5, g0), linspace(-30, 30, g1))[k]  (curve_env.py:190-199)
+__device__ __forceinline__ void curve_decode(ActionGrid g, int k, double& acceleration, double& steer) {
+    acceleration = linspace_at(-5.0, 5.0, g.g0, k / g.g1);
+    steer = linspace_at(-30.0, 30.0, g.g1, k % g.g1);
+}
+
+// env.step(action) with the action as stored in the tree: (a0) for the gym envs, the grid index or (a0, a1) for CurveEnv
+template <int ENV, typename T>
+__device__ __forceinline__ bool env_step_action(T (&s)[EnvTraits<ENV>::S], double a0, double a1, ActionGrid g, T& reward) {
+    if constexpr (ENV == ENV_CURVE) {
+        if (g.g0 > 0) curve_decode(g, (int)a0, a0, a1);
+        return Env<ENV_CURVE, T>::step2(s, T(a0), T(a1), reward);
+    } else {
+        return Env<ENV, T>::step(s, T(a0), reward);
+    }
+}
+
 // Reward structure.  Envs with kClosedForm pay a constant reward kInterior on every non-terminal step and 0/1 on the
 // terminal one; rollout_return() is then the value of `reward += r_t * pow(gamma, t)` (agents/abstract_mcts.py:87)
 // after n steps in closed form, bit-identical to the left-to-right float64 sum: CartPole pays 1 on every step
@@ -251,6 +363,8 @@ __device__ __forceinline__ void env_reset(uint64_t seed, uint32_t index, T (&s)[
     } else if constexpr (ENV == ENV_MOUNTAINCAR) {
         s[0] = T(float(__dadd_rn(-0.6, __dmul_rn(0.2, u32_to_d01(r[0])))));
         s[1] = T(0);
+    } else if constexpr (ENV == ENV_CURVE) {
+        s[0] = T(-11); s[1] = T(21); s[2] = T(10); s[3] = T(90); s[4] = T(0);   // Car(-11, 21), curve_env.py:25-31,181
     } else {
         s[0] = T(0);
     }
@@ -268,6 +382,26 @@ __device__ __forceinline__ T sample_action(Stream& st) {
         if constexpr (A == 2) return T(st.next_bits(1));
         else if constexpr (A == 4) return T(st.next_bits(2));
         else return T(mulhi_u32(st.next(), (uint32_t)A));
+    }
+}
+
+// One random-policy rollout step: action_space.sample() from the stream, then env.step
+// (agents/abstract_mcts.py:84-85).  CurveEnv samples Box([-5,-30],[5,30], float64) or Discrete(g0*g1).
+template <int ENV, typename T>
+__device__ __forceinline__ bool rollout_step(Stream& st, T (&s)[EnvTraits<ENV>::S], ActionGrid g, T& reward) {
+    if constexpr (ENV == ENV_CURVE) {
+        double a0, a1;
+        if (g.g0 > 0) {
+            const int nd = g.g0 * g.g1;
+            const int k = nd == 2 ? (int)st.next_bits(1) : nd == 4 ? (int)st.next_bits(2) : (int)mulhi_u32(st.next(), (uint32_t)nd);
+            curve_decode(g, k, a0, a1);
+        } else {
+            a0 = __dadd_rn(-5.0, __dmul_rn(10.0, u32_to_d01(st.next())));
+            a1 = __dadd_rn(-30.0, __dmul_rn(60.0, u32_to_d01(st.next())));
+        }
+        return Env<ENV_CURVE, T>::step2(s, T(a0), T(a1), reward);
+    } else {
+        return Env<ENV, T>::step(s, sample_action<ENV, T>(st), reward);
     }
 }
 

@@ -28,7 +28,9 @@ __global__ void env_step_kernel(const T* __restrict__ states, const T* __restric
 #pragma unroll
     for (int k = 0; k < S; ++k) s[k] = states[i * S + k];
     T r;
-    const bool t = Env<ENV, T>::step(s, actions[i], r);
+    bool t;
+    if constexpr (ENV == ENV_CURVE) t = Env<ENV, T>::step2(s, actions[2 * i], actions[2 * i + 1], r);
+    else t = Env<ENV, T>::step(s, actions[i], r);
 #pragma unroll
     for (int k = 0; k < S; ++k) next_states[i * S + k] = s[k];
     rewards[i] = r;
@@ -39,7 +41,7 @@ __global__ void env_step_kernel(const T* __restrict__ states, const T* __restric
 // budget (Pendulum, MountainCarContinuous) every lane runs the same number of steps and nothing is gained by refilling.
 template <int ENV, typename T>
 __global__ void __launch_bounds__(256) rollout_kernel_simple(const T* __restrict__ states, long long n, int budget,
-                                                             unsigned long long seed, unsigned sim,
+                                                             unsigned long long seed, unsigned sim, ActionGrid grid,
                                                              const double* __restrict__ disc_table, double* __restrict__ returns,
                                                              int32_t* __restrict__ steps) {
     constexpr int S = EnvTraits<ENV>::S;
@@ -58,9 +60,8 @@ __global__ void __launch_bounds__(256) rollout_kernel_simple(const T* __restrict
     bool done = false;
     int t = 0;
     while (!done && t < budget) {
-        const T a = sample_action<ENV, T>(rs);
         T r;
-        done = Env<ENV, T>::step(s, a, r);
+        done = rollout_step<ENV, T>(rs, s, grid, r);
         R = __dadd_rn(R, __dmul_rn((double)r, __ldg(disc_table + t)));  // r * pow(gamma, t), host libm pow
         ++t;
     }
@@ -143,6 +144,7 @@ int env_step_dispatch(int env, const void* s, const void* a, long long n, void* 
     case ENV_PENDULUM: env_step_kernel<ENV_PENDULUM, T><<<grid, 256, 0, st>>>((const T*)s, (const T*)a, n, (T*)ns, (T*)r, t); break;
     case ENV_MOUNTAINCAR: env_step_kernel<ENV_MOUNTAINCAR, T><<<grid, 256, 0, st>>>((const T*)s, (const T*)a, n, (T*)ns, (T*)r, t); break;
     case ENV_FROZENLAKE: env_step_kernel<ENV_FROZENLAKE, T><<<grid, 256, 0, st>>>((const T*)s, (const T*)a, n, (T*)ns, (T*)r, t); break;
+    case ENV_CURVE: env_step_kernel<ENV_CURVE, T><<<grid, 256, 0, st>>>((const T*)s, (const T*)a, n, (T*)ns, (T*)r, t); break;
     default: set_error("unknown env %d", env); return ISLA_ERR_INVALID;
     }
     ISLA_CUDA_OK(cudaGetLastError());
@@ -175,7 +177,7 @@ static int get_tables(double gamma, int budget, const double** disc, const doubl
 }
 
 template <int ENV, typename T>
-int rollout_launch(const void* s, long long n, int budget, double gamma, unsigned long long seed, unsigned sim,
+int rollout_launch(const void* s, long long n, int budget, double gamma, unsigned long long seed, unsigned sim, ActionGrid ag,
                    const double* disc, const double* cum, double* ret, int32_t* steps, int sms, cudaStream_t st) {
     if constexpr (Rewards<ENV>::kClosedForm) {
         // random episode lengths: persistent grid (SM count x 6 resident CTAs of 256 threads at 40 registers), lane refill
@@ -188,7 +190,7 @@ int rollout_launch(const void* s, long long n, int budget, double gamma, unsigne
         ISLA_CUDA_OK(cudaGetLastError());
         ISLA_CUDA_OK(cudaFreeAsync(next, st));
     } else {
-        rollout_kernel_simple<ENV, T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const T*)s, n, budget, seed, sim, disc, ret, steps);
+        rollout_kernel_simple<ENV, T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const T*)s, n, budget, seed, sim, ag, disc, ret, steps);
         ISLA_CUDA_OK(cudaGetLastError());
     }
     return 0;
@@ -196,7 +198,7 @@ int rollout_launch(const void* s, long long n, int budget, double gamma, unsigne
 
 template <typename T>
 int rollout_dispatch(int env, const void* s, long long n, int budget, double gamma, unsigned long long seed, unsigned sim,
-                     double* ret, int32_t* steps, cudaStream_t st) {
+                     ActionGrid ag, double* ret, int32_t* steps, cudaStream_t st) {
     int dev = 0, sms = 148;
     ISLA_CUDA_OK(cudaGetDevice(&dev));
     ISLA_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -204,10 +206,11 @@ int rollout_dispatch(int env, const void* s, long long n, int budget, double gam
     const int rc = get_tables(gamma, budget, &disc, &cum);
     if (rc) return rc;
     switch (env) {
-    case ENV_CARTPOLE: return rollout_launch<ENV_CARTPOLE, T>(s, n, budget, gamma, seed, sim, disc, cum, ret, steps, sms, st);
-    case ENV_PENDULUM: return rollout_launch<ENV_PENDULUM, T>(s, n, budget, gamma, seed, sim, disc, cum, ret, steps, sms, st);
-    case ENV_MOUNTAINCAR: return rollout_launch<ENV_MOUNTAINCAR, T>(s, n, budget, gamma, seed, sim, disc, cum, ret, steps, sms, st);
-    case ENV_FROZENLAKE: return rollout_launch<ENV_FROZENLAKE, T>(s, n, budget, gamma, seed, sim, disc, cum, ret, steps, sms, st);
+    case ENV_CARTPOLE: return rollout_launch<ENV_CARTPOLE, T>(s, n, budget, gamma, seed, sim, ag, disc, cum, ret, steps, sms, st);
+    case ENV_PENDULUM: return rollout_launch<ENV_PENDULUM, T>(s, n, budget, gamma, seed, sim, ag, disc, cum, ret, steps, sms, st);
+    case ENV_MOUNTAINCAR: return rollout_launch<ENV_MOUNTAINCAR, T>(s, n, budget, gamma, seed, sim, ag, disc, cum, ret, steps, sms, st);
+    case ENV_FROZENLAKE: return rollout_launch<ENV_FROZENLAKE, T>(s, n, budget, gamma, seed, sim, ag, disc, cum, ret, steps, sms, st);
+    case ENV_CURVE: return rollout_launch<ENV_CURVE, T>(s, n, budget, gamma, seed, sim, ag, disc, cum, ret, steps, sms, st);
     }
     set_error("unknown env %d", env);
     return ISLA_ERR_INVALID;
@@ -226,10 +229,18 @@ extern "C" int isla_env_step(int32_t env_id, int32_t precision, const void* stat
 }
 
 extern "C" int isla_rollout(int32_t env_id, int32_t precision, const void* states_dev, int64_t n, int32_t budget, double gamma,
-                            uint64_t seed, uint32_t sim, double* returns_dev, int32_t* steps_dev, void* stream) {
+                            uint64_t seed, uint32_t sim, int32_t action_grid0, int32_t action_grid1, double* returns_dev,
+                            int32_t* steps_dev, void* stream) {
     if (n <= 0) return ISLA_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    isla::ActionGrid ag{0, 0};
+    if (env_id == ISLA_ENV_CURVE && (action_grid0 != 0 || action_grid1 != 0)) {
+        if (action_grid0 < 1 || action_grid1 < 1 || (int64_t)action_grid0 * action_grid1 > 128) {
+            isla::set_error("DiscreteCurveEnv grid %d x %d: need 1 <= g0*g1 <= 128", action_grid0, action_grid1); return ISLA_ERR_INVALID;
+        }
+        ag = isla::ActionGrid{action_grid0, action_grid1};
+    }
     return precision == ISLA_PRECISION_F64
-               ? isla::rollout_dispatch<double>(env_id, states_dev, n, budget, gamma, seed, sim, returns_dev, steps_dev, st)
-               : isla::rollout_dispatch<float>(env_id, states_dev, n, budget, gamma, seed, sim, returns_dev, steps_dev, st);
+               ? isla::rollout_dispatch<double>(env_id, states_dev, n, budget, gamma, seed, sim, ag, returns_dev, steps_dev, st)
+               : isla::rollout_dispatch<float>(env_id, states_dev, n, budget, gamma, seed, sim, ag, returns_dev, steps_dev, st);
 }

@@ -42,7 +42,7 @@ struct Pool {
     double* s_total; double* s_term_reward; int* s_ns; int* s_flags; int* s_coff; int* s_ccap; int* s_ccnt;
     void* s_state;
     // action nodes
-    double* a_total; double* a_value; int* a_na; int* a_visits; int* a_child;
+    double* a_total; double* a_value; double* a_value2; int* a_na; int* a_visits; int* a_child;
     // child index arrays, path
     int* ipool; int* p_s; int* p_a; double* p_r; int* p_flag; double* p_g;
     int* meta;
@@ -62,10 +62,12 @@ struct CtaParams {
     int n_sim, max_depth, budget_mode, agent, n_actions, R, expansion, voo_n, voo_max_try, real_bytes;
     int pool_in_smem;  // the whole tree pool fits in shared memory: search there, copy back at the end
     char* hash_base; long long hash_cap;  // per-tree action hash set (apw/dpw): hash_cap int4 entries per tree, 0 = none
+    ActionGrid grid;                       // DiscreteCurveEnv action grid (g0 == 0: not a grid)
+    int action_dim;                        // 1, or 2 for the continuous CurveEnv box (second coordinate in a_value2)
 };
 
 enum : int { O_S_TOTAL = 0, O_S_TERMR, O_S_NS, O_S_FLAGS, O_S_COFF, O_S_CCAP, O_S_CCNT, O_S_STATE, O_A_TOTAL, O_A_VALUE,
-             O_A_NA, O_A_VISITS, O_A_CHILD, O_IPOOL, O_P_S, O_P_A, O_P_R, O_P_FLAG, O_META, O_P_G, O_COUNT };
+             O_A_NA, O_A_VISITS, O_A_CHILD, O_IPOOL, O_P_S, O_P_A, O_P_R, O_P_FLAG, O_META, O_P_G, O_A_VALUE2, O_COUNT };
 enum : int { CM_NS = 0, CM_NA = 1, CM_ITOP = 2, CM_SIMS = 3, CM_RNG = 4, CM_FAULT = 5, CM_TRACE_POS = 6, CM_WORDS = 8 };
 
 __device__ __forceinline__ Pool make_pool_at(const CtaParams& p, char* b) {
@@ -81,6 +83,7 @@ __device__ __forceinline__ Pool make_pool_at(const CtaParams& p, char* b) {
     q.p_flag = (int*)(b + p.off[O_P_FLAG]);
     q.meta = (int*)(b + p.off[O_META]);
     q.p_g = (double*)(b + p.off[O_P_G]);
+    q.a_value2 = (double*)(b + p.off[O_A_VALUE2]);
     return q;
 }
 __device__ __forceinline__ Pool make_pool(const CtaParams& p, long long tree) {
@@ -139,8 +142,25 @@ struct Search {
             return n > 1 ? (int)mulhi_u32(ts.next(), (uint32_t)n) : 0;
         }
     }
-    __device__ double tree_action() {  // env.action_space.sample() drawn from the tree stream
-        if constexpr (EnvTraits<ENV>::kContinuous) {
+    // env.action_space.sample() drawn from the tree stream; a1 = second coordinate (continuous CurveEnv), else 0
+    __device__ double tree_action(double& a1) {
+        a1 = 0.0;
+        if constexpr (ENV == ENV_CURVE) {
+            if (p.grid.g0 > 0) {
+                const int nd = p.grid.g0 * p.grid.g1;
+                if constexpr (SCRIPTED) {
+                    const int v = (int)tc.take(ISLA_K_SAMPLE_D);
+                    if (v < 0 || v >= nd) { if (!tc.fault) tc.fault = ISLA_ERR_TRACE; return 0.0; }
+                    return (double)v;
+                }
+                return (double)mulhi_u32(ts.next(), (uint32_t)nd);
+            }
+            // Box([-5, -30], [5, 30], dtype=float64): one uniform per dimension (curve_env.py:90-95)
+            if constexpr (SCRIPTED) { const double a0 = tc.take(ISLA_K_SAMPLE_C); a1 = tc.take(ISLA_K_SAMPLE_C); return a0; }
+            const double a0 = __dadd_rn(-5.0, __dmul_rn(10.0, u32_to_d01(ts.next())));
+            a1 = __dadd_rn(-30.0, __dmul_rn(60.0, u32_to_d01(ts.next())));
+            return a0;
+        } else if constexpr (EnvTraits<ENV>::kContinuous) {
             if constexpr (SCRIPTED) return (double)(float)tc.take(ISLA_K_SAMPLE_C);
             float lo, hi; env_action_bounds(ENV, lo, hi);
             return (double)box_sample_f32(ts.next(), lo, hi);
@@ -179,10 +199,13 @@ struct Search {
         ++c_nodes;
         return s;
     }
-    __device__ int new_action(double value) {
+    __device__ int new_action(double value, double value2 = 0.0) {
         if (nA >= p.a_cap) { fault = ISLA_ERR_CAPACITY; return 0; }
         const int a = nA++;
-        if (lane == 0) { q.a_total[a] = 0.0; q.a_value[a] = value; q.a_na[a] = 0; q.a_visits[a] = 0; q.a_child[a] = -1; }
+        if (lane == 0) {
+            q.a_total[a] = 0.0; q.a_value[a] = value; q.a_na[a] = 0; q.a_visits[a] = 0; q.a_child[a] = -1;
+            if (p.action_dim == 2) q.a_value2[a] = value2;
+        }
         return a;
     }
     // append an action node to a state's child index array (insertion order), growing it by doubling
@@ -263,37 +286,54 @@ struct Search {
         h ^= h >> 29;
         return h & (unsigned long long)(p.hash_cap - 1);
     }
-    __device__ int find_action(int s, double value) {
-        if (p.hash_cap == 0) return find_action_scan(s, value);
-        const long long want = __double_as_longlong(value);
+    // 2-D actions (CurveEnv box) do not fit the 64-bit key field: the entry then holds a 64-bit mix of both
+    // coordinates and a match is confirmed against the stored action node.
+    __device__ __forceinline__ long long key_bits(double value, double value2) const {
+        long long bits = __double_as_longlong(value);
+        if (p.action_dim == 2) {
+            unsigned long long m = (unsigned long long)__double_as_longlong(value2) * 0xD6E8FEB86659FD93ull;
+            bits ^= (long long)(m ^ (m >> 32));
+        }
+        return bits;
+    }
+    __device__ __forceinline__ bool confirm(int s, int rank, double value, double value2) const {
+        if (p.action_dim != 2) return true;
+        const int a = q.ipool[q.s_coff[s] + rank];
+        return __double_as_longlong(q.a_value[a]) == __double_as_longlong(value) &&
+               __double_as_longlong(q.a_value2[a]) == __double_as_longlong(value2);
+    }
+    __device__ int find_action(int s, double value, double value2 = 0.0) {
+        if (p.hash_cap == 0) return find_action_scan(s, value, value2);
+        const long long want = key_bits(value, value2);
         unsigned long long h = hash_slot(s, want);
         for (;;) {
             const int4 e = reinterpret_cast<const int4*>(hash)[h];   // {bits lo, bits hi, state, rank}
             if (e.z < 0) return -1;
-            if (e.z == s && e.x == (int)(unsigned)(want & 0xffffffffll) && e.y == (int)(want >> 32)) return e.w;
+            if (e.z == s && e.x == (int)(unsigned)(want & 0xffffffffll) && e.y == (int)(want >> 32) && confirm(s, e.w, value, value2)) return e.w;
             h = (h + 1) & (unsigned long long)(p.hash_cap - 1);
         }
     }
     // record (state, action bits) -> rank; an existing key is overwritten (dpw replaces the node under the same key)
-    __device__ void hash_put(int s, double value, int rank) {
+    __device__ void hash_put(int s, double value, int rank, double value2 = 0.0) {
         if (p.hash_cap == 0) return;
-        const long long bits = __double_as_longlong(value);
+        const long long bits = key_bits(value, value2);
         unsigned long long h = hash_slot(s, bits);
         for (;;) {
             const int4 e = reinterpret_cast<const int4*>(hash)[h];
-            if (e.z < 0 || (e.z == s && e.x == (int)(unsigned)(bits & 0xffffffffll) && e.y == (int)(bits >> 32))) break;
+            if (e.z < 0 || (e.z == s && e.x == (int)(unsigned)(bits & 0xffffffffll) && e.y == (int)(bits >> 32) && confirm(s, e.w, value, value2))) break;
             h = (h + 1) & (unsigned long long)(p.hash_cap - 1);
         }
         if (lane == 0) reinterpret_cast<int4*>(hash)[h] = make_int4((int)(unsigned)(bits & 0xffffffffll), (int)(bits >> 32), s, rank);
         __syncwarp();
     }
-    __device__ int find_action_scan(int s, double value) {
+    __device__ int find_action_scan(int s, double value, double value2 = 0.0) {
         const int off = q.s_coff[s], n = q.s_ccnt[s];
-        const long long want = __double_as_longlong(value);
+        const long long want = __double_as_longlong(value), want2 = __double_as_longlong(value2);
         int found = -1;
         for (int base = 0; base < n && found < 0; base += 32) {
             const int i = base + lane;
-            const bool hit = i < n && __double_as_longlong(q.a_value[q.ipool[off + i]]) == want;
+            bool hit = i < n && __double_as_longlong(q.a_value[q.ipool[off + i]]) == want;
+            if (hit && p.action_dim == 2) hit = __double_as_longlong(q.a_value2[q.ipool[off + i]]) == want2;
             const unsigned b = __ballot_sync(kFull, hit);
             if (b) found = base + __ffs(b) - 1;
         }
@@ -316,7 +356,7 @@ struct Search {
             return idx == 0 ? (double)hif : (double)lof;
         }
         if (n == 2) return find_action(s, (double)hif) >= 0 ? (double)lof : (double)hif;
-        if (pr < __dsub_rn(1.0, p.epsilon)) return tree_action();
+        if (pr < __dsub_rn(1.0, p.epsilon)) { double unused; return tree_action(unused); }
         auto qv = [&](int i) -> double { const int a = q.ipool[off + i]; return __ddiv_rn(q.a_total[a], (double)q.a_na[a]); };
         int r0 = -1, r1 = -1;
         for (int pass = 0; pass < 2; ++pass) {
@@ -342,7 +382,7 @@ struct Search {
     __device__ double voo_expand(int s) {
         const double pr = u01();
         const int off = q.s_coff[s], n = q.s_ccnt[s];
-        if (pr <= p.epsilon || n == 0) return tree_action();
+        if (pr <= p.epsilon || n == 0) { double unused; return tree_action(unused); }
         auto qv = [&](int i) -> double { const int a = q.ipool[off + i]; return __ddiv_rn(q.a_total[a], (double)q.a_na[a]); };
         double qmax = -INFINITY;
         for (int i = lane; i < n; i += 32) qmax = fmax(qmax, qv(i));
@@ -412,7 +452,7 @@ struct Search {
 };
 
 struct RollShared {
-    double leaf[4];
+    double leaf[8];
     int budget, need, exit_flag;
     unsigned sim;
     double result;
@@ -501,12 +541,13 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                 const int n_act = q.s_ccnt[s], off = q.s_coff[s];
                 if (p.agent == ISLA_AGENT_VANILLA || p.agent == ISLA_AGENT_SPW) {
                     // unvisited actions = those without a node (visit_actions[a] == 0), mcts.py:55-59
-                    unsigned have = 0;
-                    for (int i = 0; i < n_act; ++i) have |= 1u << (int)q.a_value[q.ipool[off + i]];
-                    const int nun = p.n_actions - __popc(have);
+                    // (up to 128 actions: DiscreteCurveEnv grids)
+                    const int nun = p.n_actions - n_act;
                     if (nun > 0) {
+                        unsigned have[4] = {0u, 0u, 0u, 0u};
+                        for (int i = 0; i < n_act; ++i) { const int k = (int)q.a_value[q.ipool[off + i]]; have[k >> 5] |= 1u << (k & 31); }
                         int pos = ctx.choice(nun), disc = 0;
-                        for (int k = 0; k < p.n_actions; ++k) if (!((have >> k) & 1u)) { if (pos == 0) disc = k; --pos; }
+                        for (int k = 0; k < p.n_actions; ++k) if (!((have[k >> 5] >> (k & 31)) & 1u)) { if (pos == 0) disc = k; --pos; }
                         a = ctx.new_action((double)disc);
                         ctx.append_action(s, a);
                     } else {
@@ -518,14 +559,14 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                     const int ns_now = q.s_ns[s];
                     const double cap = ns_now < p.ln_count ? p.pw1_table[ns_now] : ceil(__dmul_rn(p.k1, pow((double)ns_now, p.alpha1)));
                     if (n_act == 0 || (double)n_act <= cap) {
-                        double val;
+                        double val, val2 = 0.0;
                         if (p.agent == ISLA_AGENT_APW && p.expansion == ISLA_EXPAND_VOO) val = ctx.voo_expand(s);
                         else if (p.agent == ISLA_AGENT_APW && p.expansion == ISLA_EXPAND_GENETIC2) val = ctx.genetic2_expand(s);
-                        else val = ctx.tree_action();  // dpw ignores --ae (mcts_double_...:57)
-                        const int old = ctx.find_action(s, val);
+                        else val = ctx.tree_action(val2);  // dpw ignores --ae (mcts_double_...:57)
+                        const int old = ctx.find_action(s, val, val2);
                         if (p.agent == ISLA_AGENT_APW) {
                             if (old >= 0) a = q.ipool[q.s_coff[s] + old];                  // reuse (:66-70)
-                            else { a = ctx.new_action(val); ctx.append_action(s, a); ctx.hash_put(s, val, q.s_ccnt[s] - 1); }
+                            else { a = ctx.new_action(val, val2); ctx.append_action(s, a); ctx.hash_put(s, val, q.s_ccnt[s] - 1, val2); }
                         } else {
                             a = ctx.new_action(val);                                      // always a new node (:58-60)
                             if (old >= 0) { if (lane == 0) q.ipool[q.s_coff[s] + old] = a; __syncwarp(); }
@@ -544,7 +585,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                     for (int i = 0; i < S; ++i) cur[i] = sp[i];
                 }
                 T rT;
-                const bool term = Env<ENV, T>::step(cur, T(q.a_value[a]), rT);
+                const bool term = env_step_action<ENV, T>(cur, q.a_value[a], p.action_dim == 2 ? q.a_value2[a] : 0.0, p.grid, rT);
                 const double r = (double)rT;
                 ++ctx.c_env;
                 const int child = q.a_child[a];
@@ -638,10 +679,11 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                     for (int i = 0; i < S; ++i) st[i] = T(sh.leaf[i]);
                     double Rr = 0.0; int t = 0; bool done = false;
                     while (!done && t < budget && !ctx.tc.fault) {
-                        const T act = T(ctx.tree_action());
+                        double act2;
+                        const double act = ctx.tree_action(act2);
                         if (ctx.tc.fault) break;
                         T rr;
-                        done = Env<ENV, T>::step(st, act, rr);
+                        done = env_step_action<ENV, T>(st, act, act2, p.grid, rr);
                         Rr = __dadd_rn(Rr, __dmul_rn((double)rr, p.disc_table[t]));
                         ++t;
                     }
@@ -661,9 +703,8 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                             rs.init(p.seed, sh.sim, tree_id, (uint32_t)j);
                             int t = 0; bool done = false;
                             while (!done && t < budget) {
-                                const T act = sample_action<ENV, T>(rs);
                                 T rr;
-                                done = Env<ENV, T>::step(st, act, rr);
+                                done = rollout_step<ENV, T>(rs, st, p.grid, rr);
                                 Rr = __dadd_rn(Rr, __dmul_rn((double)rr, __ldg(p.disc_table + t)));
                                 ++t;
                             }
@@ -780,7 +821,8 @@ __global__ void cta_best_kernel(const CtaParams p, int scripted_pos, int32_t* be
     if (tree >= p.n_trees) return;
     Pool q = make_pool(p, tree);
     const int off = q.s_coff[0], n = q.s_ccnt[0];
-    if (n == 0) { best_rank_out[tree] = -1; if (best_action_out) best_action_out[tree] = 0.0; return; }
+    const int AD = p.action_dim;
+    if (n == 0) { best_rank_out[tree] = -1; if (best_action_out) for (int d = 0; d < AD; ++d) best_action_out[tree * AD + d] = 0.0; return; }
     if (p.agent == ISLA_AGENT_SPW || p.agent == ISLA_AGENT_DPW) {
         for (int x = 1; x < n; ++x) {  // stable insertion sort == sorted(items)
             const int cur = q.ipool[off + x];
@@ -835,7 +877,10 @@ __global__ void cta_best_kernel(const CtaParams p, int scripted_pos, int32_t* be
         if (__ddiv_rn(q.a_total[a], (double)q.a_na[a]) == qmax) { if (pos == 0) pick = i; --pos; }
     }
     best_rank_out[tree] = pick;
-    if (best_action_out) best_action_out[tree] = q.a_value[q.ipool[off + pick]];
+    if (best_action_out) {
+        best_action_out[tree * AD] = q.a_value[q.ipool[off + pick]];
+        if (AD == 2) best_action_out[tree * AD + 1] = q.a_value2[q.ipool[off + pick]];
+    }
 }
 
 __global__ void cta_root_children_kernel(const CtaParams p, long long tree, int cap, double* action, int64_t* na, double* total, int32_t* count) {
@@ -844,7 +889,8 @@ __global__ void cta_root_children_kernel(const CtaParams p, long long tree, int 
     if (threadIdx.x == 0 && blockIdx.x == 0) *count = n;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n && i < cap; i += gridDim.x * blockDim.x) {
         const int a = q.ipool[off + i];
-        action[i] = q.a_value[a]; na[i] = q.a_na[a]; total[i] = q.a_total[a];
+        if (p.action_dim == 2) { action[2 * i] = q.a_value[a]; action[2 * i + 1] = q.a_value2[a]; } else action[i] = q.a_value[a];
+        na[i] = q.a_na[a]; total[i] = q.a_total[a];
     }
 }
 
@@ -863,6 +909,9 @@ CtaParams make_params(const isla_engine* e) {
     take(O_P_S, L.s_cap * 4); take(O_P_A, L.s_cap * 4); take(O_P_R, L.s_cap * 8); take(O_P_FLAG, L.s_cap * 4);
     take(O_META, CM_WORDS * 4);
     take(O_P_G, L.s_cap * 8);
+    p.grid = ActionGrid{e->cfg.env_id == ISLA_ENV_CURVE ? e->cfg.action_grid0 : 0, e->cfg.env_id == ISLA_ENV_CURVE ? e->cfg.action_grid1 : 0};
+    p.action_dim = (e->cfg.env_id == ISLA_ENV_CURVE && p.grid.g0 == 0) ? 2 : 1;
+    take(O_A_VALUE2, p.action_dim == 2 ? L.a_cap * 8 : 0);
     p.off[O_COUNT] = off;
     p.counters = (unsigned long long*)(e->ws + L.counters_offset);
     p.trace_kinds = nullptr; p.trace_values = nullptr; p.trace_len = 0;
@@ -922,6 +971,7 @@ int launch_env(const isla_engine* e, const CtaParams& p, int nt, bool scripted, 
     case ISLA_ENV_PENDULUM: return launch<ENV_PENDULUM, T>(p, nt, scripted, st);
     case ISLA_ENV_MOUNTAINCAR: return launch<ENV_MOUNTAINCAR, T>(p, nt, scripted, st);
     case ISLA_ENV_FROZENLAKE: return launch<ENV_FROZENLAKE, T>(p, nt, scripted, st);
+    case ISLA_ENV_CURVE: return launch<ENV_CURVE, T>(p, nt, scripted, st);
     }
     set_error("unknown env %d", e->cfg.env_id);
     return ISLA_ERR_INVALID;
@@ -934,11 +984,13 @@ int cta_fill_layout(const isla_config& cfg, isla_layout& lay) {
     const int rb = cfg.precision == ISLA_PRECISION_F64 ? 8 : 4;
     const int R = cfg.rollouts_per_leaf > 0 ? cfg.rollouts_per_leaf : 1;
     if (R > kMaxRollSmem) { set_error("rollouts_per_leaf %d exceeds %d", R, kMaxRollSmem); return ISLA_ERR_INVALID; }
-    if ((cfg.agent == ISLA_AGENT_VANILLA || cfg.agent == ISLA_AGENT_SPW) && (cfg.n_actions < 1 || cfg.n_actions > 32 ||
-                                                                           cfg.n_actions != env_n_actions(cfg.env_id))) {
-        set_error("n_actions=%d does not match env (%d)", cfg.n_actions, env_n_actions(cfg.env_id)); return ISLA_ERR_INVALID;
+    const int env_actions = cfg.env_id == ISLA_ENV_CURVE ? cfg.action_grid0 * cfg.action_grid1 : env_n_actions(cfg.env_id);
+    if ((cfg.agent == ISLA_AGENT_VANILLA || cfg.agent == ISLA_AGENT_SPW) && (cfg.n_actions < 1 || cfg.n_actions > 128 ||
+                                                                           cfg.n_actions != env_actions)) {
+        set_error("n_actions=%d does not match env (%d)", cfg.n_actions, env_actions); return ISLA_ERR_INVALID;
     }
     if (cfg.expansion != ISLA_EXPAND_RANDOM && cfg.agent != ISLA_AGENT_APW) { set_error("voo / genetic2 expansion are APW options"); return ISLA_ERR_INVALID; }
+    if (cfg.expansion != ISLA_EXPAND_RANDOM && cfg.env_id == ISLA_ENV_CURVE) { set_error("voo / genetic2 expansion: one action dimension only (CurveEnv has two)"); return ISLA_ERR_INVALID; }
     if (cfg.expansion < ISLA_EXPAND_RANDOM || cfg.expansion > ISLA_EXPAND_GENETIC2) { set_error("unknown expansion %d", cfg.expansion); return ISLA_ERR_INVALID; }
     if (cfg.expansion == ISLA_EXPAND_VOO && (cfg.voo_n_samples < 1 || cfg.voo_n_samples > 8 || cfg.voo_max_try < 1)) {
         set_error("voo: n_samples must be in [1, 8] and max_try >= 1"); return ISLA_ERR_INVALID;
@@ -946,6 +998,7 @@ int cta_fill_layout(const isla_config& cfg, isla_layout& lay) {
     auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
     lay.kernel = ISLA_KERNEL_CTA_PER_TREE;
     lay.state_dim = S; lay.real_bytes = rb; lay.n_actions = cfg.n_actions;
+    lay.action_dim = (cfg.env_id == ISLA_ENV_CURVE && cfg.action_grid0 == 0) ? 2 : 1;
     lay.s_cap = (int64_t)cfg.sim_capacity + 2; lay.a_cap = (int64_t)cfg.sim_capacity + 2;
     lay.slots_per_tree = 0; lay.rec_offset = lay.rec_stride = lay.state_offset = lay.state_stride = lay.meta_offset = lay.path_offset = 0;
     int64_t off = 0;

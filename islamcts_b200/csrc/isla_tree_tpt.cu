@@ -665,7 +665,7 @@ int tpt_fill_layout(const isla_config& cfg, isla_layout& lay) {
     const int rb = cfg.precision == ISLA_PRECISION_F64 ? 8 : 4;
     auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
     lay.kernel = ISLA_KERNEL_THREAD_PER_TREE;
-    lay.state_dim = S; lay.real_bytes = rb; lay.n_actions = A;
+    lay.state_dim = S; lay.real_bytes = rb; lay.n_actions = A; lay.action_dim = 1;
     lay.slots_per_tree = blocks * A;
     int64_t off = 0;
     lay.rec_offset = off; lay.rec_stride = lay.slots_per_tree * 16; off = up(off + cfg.n_trees * lay.rec_stride);

@@ -18,9 +18,11 @@ ENV_NAMES = {
     "Pendulum-v1": _lib.ENV_PENDULUM,
     "MountainCarContinuous-v0": _lib.ENV_MOUNTAINCAR,
     "FrozenLake-v1": _lib.ENV_FROZENLAKE,
+    "CurveEnv": _lib.ENV_CURVE, "DiscreteCurveEnv": _lib.ENV_CURVE,
 }
-STATE_DIM = {_lib.ENV_CARTPOLE: 4, _lib.ENV_PENDULUM: 2, _lib.ENV_MOUNTAINCAR: 2, _lib.ENV_FROZENLAKE: 1}
-N_ACTIONS = {_lib.ENV_CARTPOLE: 2, _lib.ENV_PENDULUM: 0, _lib.ENV_MOUNTAINCAR: 0, _lib.ENV_FROZENLAKE: 4}
+STATE_DIM = {_lib.ENV_CARTPOLE: 4, _lib.ENV_PENDULUM: 2, _lib.ENV_MOUNTAINCAR: 2, _lib.ENV_FROZENLAKE: 1, _lib.ENV_CURVE: 5}
+N_ACTIONS = {_lib.ENV_CARTPOLE: 2, _lib.ENV_PENDULUM: 0, _lib.ENV_MOUNTAINCAR: 0, _lib.ENV_FROZENLAKE: 4, _lib.ENV_CURVE: 0}
+ACTION_DIM = {_lib.ENV_CURVE: 2}   # every other env: 1
 ACTION_BOUNDS = {_lib.ENV_PENDULUM: (-2.0, 2.0), _lib.ENV_MOUNTAINCAR: (-1.0, 1.0)}
 
 LINK_BLOCK_MASK, LINK_TERMINAL, LINK_REWARD_ONE, LINK_RANK_SHIFT = 0x0FFFFFFF, 1 << 28, 1 << 29, 30
@@ -54,17 +56,19 @@ class Engine:
                  expansion: int = _lib.EXPAND_RANDOM, epsilon: float = 0.7, voo_n_samples: int = 5,
                  voo_max_try: int = 1000, alpha1: float = 0.0, k1: float = 1.0, alpha2: float = 0.0, k2: float = 1.0,
                  precision: int = _lib.PRECISION_F32, kernel: int = _lib.KERNEL_AUTO, block_threads: int = 0,
-                 seed: int = 0, tree_id_base: int = 0, device="cuda:0", tuning: int | None = None):
+                 seed: int = 0, tree_id_base: int = 0, device="cuda:0", tuning: int | None = None,
+                 action_grid=None):
         import os
         if tuning is None:
             tuning = int(os.environ.get("ISLA_TUNING", "0"))
         self.device = _require_cuda(device)
         self.lib = _lib.load()
+        g0, g1 = (int(action_grid[0]), int(action_grid[1])) if action_grid else (0, 0)   # DiscreteCurveEnv([g0, g1])
         if n_actions is None:
-            n_actions = N_ACTIONS[env_id]
+            n_actions = g0 * g1 if env_id == _lib.ENV_CURVE else N_ACTIONS[env_id]
         self.cfg = IslaConfig(env_id, agent, int(n_actions or 0), int(max_depth), budget_mode, int(rollouts_per_leaf),
                               expansion, int(voo_n_samples), int(voo_max_try), precision, kernel, int(block_threads),
-                              int(sim_capacity), int(tuning), float(C_), float(gamma), float(alpha1), float(k1), float(alpha2),
+                              int(sim_capacity), int(tuning), g0, g1, float(C_), float(gamma), float(alpha1), float(k1), float(alpha2),
                               float(k2), float(epsilon), int(seed), int(tree_id_base), int(n_trees))
         nbytes = check(self.lib.isla_engine_workspace_bytes(C.byref(self.cfg)))
         with torch.cuda.device(self.device):
@@ -80,6 +84,7 @@ class Engine:
         self.state_dim = STATE_DIM[env_id]
         self.n_actions = int(n_actions or 0)
         self.env_id = env_id
+        self.action_dim = int(self.layout.action_dim)
         self._keep = []
 
     # ------------------------------------------------------------------ lifecycle
@@ -129,9 +134,11 @@ class Engine:
         return na, tot
 
     def best(self, scripted_pos: int = -1):
-        """End of fit(): (rank in root.actions, action value) per tree -- device tensors (int32, float64)."""
+        """End of fit(): (rank in root.actions, action value) per tree -- device tensors (int32, float64;
+        the action is [n_trees, 2] for the continuous CurveEnv box)."""
         rank = torch.empty((self.n_trees,), dtype=torch.int32, device=self.device)
-        act = torch.empty((self.n_trees,), dtype=torch.float64, device=self.device)
+        shape = (self.n_trees,) if self.action_dim == 1 else (self.n_trees, self.action_dim)
+        act = torch.empty(shape, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
             check(self.lib.isla_engine_best(self._h, int(scripted_pos), C.c_void_p(rank.data_ptr()),
                                             C.c_void_p(act.data_ptr()), C.c_void_p(_stream_ptr(self.device))))
@@ -141,7 +148,7 @@ class Engine:
         """(action, na, total) numpy arrays of one tree's root children in root.actions order (CTA engine)."""
         cnt = torch.zeros(1, dtype=torch.int32, device=self.device)
         cap = max(16, int(self.layout.a_cap))
-        a = torch.empty(cap, dtype=torch.float64, device=self.device)
+        a = torch.empty(cap if self.action_dim == 1 else (cap, self.action_dim), dtype=torch.float64, device=self.device)
         na = torch.empty(cap, dtype=torch.int64, device=self.device)
         tot = torch.empty(cap, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
@@ -260,6 +267,8 @@ def env_step(env_id: int, states, actions, precision: int = _lib.PRECISION_F32, 
     s = torch.as_tensor(states).to(dev, dt).reshape(-1, S).contiguous()
     a = torch.as_tensor(actions).to(dev, dt).reshape(-1).contiguous()
     n = s.shape[0]
+    if a.numel() != n * ACTION_DIM.get(env_id, 1):
+        raise _lib.IslaError(_lib.ERR_INVALID, f"env_step: {n} states need {n * ACTION_DIM.get(env_id, 1)} action reals, got {a.numel()}")
     ns = torch.empty_like(s)
     r = torch.empty(n, dtype=dt, device=dev)
     t = torch.empty(n, dtype=torch.uint8, device=dev)
@@ -271,8 +280,10 @@ def env_step(env_id: int, states, actions, precision: int = _lib.PRECISION_F32, 
 
 
 def rollout(env_id: int, states, n: int | None = None, budget: int = 500, gamma: float = 0.99, seed: int = 0,
-            sim: int = 0, precision: int = _lib.PRECISION_F32, device="cuda:0"):
-    """Random-policy rollouts (abstract_mcts.py:72-91).  states=None starts from the reset distribution."""
+            sim: int = 0, precision: int = _lib.PRECISION_F32, device="cuda:0", action_grid=None):
+    """Random-policy rollouts (abstract_mcts.py:72-91).  states=None starts from the reset distribution.
+    action_grid=[g0, g1] samples DiscreteCurveEnv's grid instead of CurveEnv's box."""
+    g0, g1 = (int(action_grid[0]), int(action_grid[1])) if action_grid else (0, 0)
     dev = _require_cuda(device)
     lib = _lib.load()
     dt = _real(precision)
@@ -285,7 +296,7 @@ def rollout(env_id: int, states, n: int | None = None, budget: int = 500, gamma:
     ret = torch.empty(n, dtype=torch.float64, device=dev)
     steps = torch.empty(n, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        check(lib.isla_rollout(env_id, precision, sp, int(n), int(budget), float(gamma), int(seed), int(sim),
+        check(lib.isla_rollout(env_id, precision, sp, int(n), int(budget), float(gamma), int(seed), int(sim), g0, g1,
                                C.c_void_p(ret.data_ptr()), C.c_void_p(steps.data_ptr()), C.c_void_p(_stream_ptr(dev))))
     return ret, steps
 

@@ -806,7 +806,12 @@ void orc_tree_counters(const orc_tree* t, int64_t out[8]) {
 
 int orc_rollout(int env_id, const double* state, int budget, double gamma, uint64_t seed, uint64_t tree,
                 uint32_t sim, uint32_t j, double* ret) {
+    return orc_rollout_grid(env_id, state, budget, gamma, seed, tree, sim, j, 0, 0, ret);
+}
+int orc_rollout_grid(int env_id, const double* state, int budget, double gamma, uint64_t seed, uint64_t tree,
+                     uint32_t sim, uint32_t j, int grid0, int grid1, double* ret) {
     orc_config cfg; memset(&cfg, 0, sizeof cfg);
+    cfg.grid0 = grid0; cfg.grid1 = grid1;
     cfg.env_id = env_id; cfg.gamma = gamma; cfg.seed = seed; cfg.tree_id = tree; cfg.rollouts_per_leaf = 1;
     orc_tree t; memset(&t, 0, sizeof t); t.cfg = cfg; t.tlen = -1;
     int d = orc_state_dim(env_id); for (int i = 0; i < d; ++i) t.env[i] = state[i];

@@ -73,6 +73,9 @@ def lib():
         L.orc_rollout.restype = C.c_int
         L.orc_rollout.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_uint64, C.c_uint64,
                                   C.c_uint32, C.c_uint32, C.c_void_p]
+        L.orc_rollout_grid.restype = C.c_int
+        L.orc_rollout_grid.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_uint64, C.c_uint64,
+                                       C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p]
         L.orc_philox4x32.argtypes = [C.c_uint32] * 6 + [C.c_void_p]
         _lib = L
     return _lib
@@ -199,12 +202,13 @@ def env_reset(env_id, seed, index):
     return s[: state_dim(env_id)].copy()
 
 
-def rollout(env_id, state, budget, gamma, seed, tree, sim, j):
+def rollout(env_id, state, budget, gamma, seed, tree, sim, j, grid=(0, 0)):
     s = np.zeros(8, np.float64)
     st = np.asarray(state, np.float64).reshape(-1)
     s[: st.size] = st
     ret = C.c_double(0)
-    steps = lib().orc_rollout(env_id, _p(s), int(budget), float(gamma), seed, tree, sim, j, C.byref(ret))
+    steps = lib().orc_rollout_grid(env_id, _p(s), int(budget), float(gamma), seed, tree, sim, j, int(grid[0]), int(grid[1]),
+                                   C.byref(ret))
     return ret.value, steps
 
 

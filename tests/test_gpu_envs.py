@@ -6,7 +6,13 @@ from oracle import coracle
 
 pytestmark = pytest.mark.gpu
 
-ENVS = [0, 1, 2, 3]
+ENVS = [0, 1, 2, 3, 4]
+
+
+def _curve_fixture():
+    import os
+    from tests.golden_util import GOLDEN_DIR
+    return np.load(os.path.join(GOLDEN_DIR, "env", "curve_env_steps.npz"))
 
 
 def _random_states(env_id, n, rng):
@@ -19,9 +25,15 @@ def _random_states(env_id, n, rng):
     elif env_id == 2:
         s = rng.uniform([-1.2, -0.07], [0.6, 0.07], size=(n, 2)).astype(np.float32).astype(np.float64)
         a = rng.uniform(-1.2, 1.2, n).astype(np.float32).astype(np.float64)
-    else:
+    elif env_id == 3:
         s = rng.integers(0, 16, size=(n, 1)).astype(np.float64)
         a = rng.integers(0, 4, n).astype(np.float64)
+    else:
+        # CurveEnv: poses the reference's own env visited (fixture), fresh actions (half of them braking right turns)
+        fix = _curve_fixture()["state"]
+        s = fix[rng.integers(0, len(fix), n)].copy()
+        a = rng.uniform([-5.0, -30.0], [5.0, 30.0], size=(n, 2))
+        a[::2] = rng.uniform([-5.0, -30.0], [0.0, 0.0], size=(len(a[::2]), 2))
     return s, a
 
 
@@ -71,7 +83,7 @@ def test_scripted_trajectories_short_horizon(env_id):
     n, T = 512, 25
     s0 = np.stack([coracle.env_reset(env_id, 7, i) for i in range(n)])
     _, acts = _random_states(env_id, n * T, rng)
-    acts = acts.reshape(T, n)
+    acts = acts.reshape(T, n, -1).squeeze(-1) if acts.ndim == 1 else acts.reshape(T, n, -1)
     dev_s = torch.as_tensor(s0, dtype=torch.float32)
     cpu_s = s0.astype(np.float32).astype(np.float64)
     alive = np.ones(n, bool)
@@ -88,15 +100,22 @@ def test_scripted_trajectories_short_horizon(env_id):
                 alive[i] = False
 
 
-@pytest.mark.parametrize("env_id,budget,gamma", [(0, 500, 0.99), (1, 200, 0.99), (2, 500, 0.99), (3, 1000, 1.0), (0, 7, 0.9)])
-def test_rollout_f64_matches_oracle_streams(env_id, budget, gamma):
+@pytest.mark.parametrize("env_id,budget,gamma,grid", [(0, 500, 0.99, None), (1, 200, 0.99, None), (2, 500, 0.99, None),
+                                                      (3, 1000, 1.0, None), (0, 7, 0.9, None), (4, 40, 0.95, None),
+                                                      (4, 40, 0.95, (5, 7)), (4, 12, 0.9, (2, 2)), (4, 12, 0.9, (1, 2))])
+def test_rollout_f64_matches_oracle_streams(env_id, budget, gamma, grid):
     from islamcts_b200 import engine as E
     n = 1500
-    s0 = np.stack([coracle.env_reset(env_id, 3, i) for i in range(n)])
-    ret, steps = E.rollout(env_id, s0, budget=budget, gamma=gamma, seed=99, sim=5, precision=1)
+    if env_id == 4:
+        s0 = _random_states(4, n, np.random.default_rng(4))[0]
+    else:
+        s0 = np.stack([coracle.env_reset(env_id, 3, i) for i in range(n)])
+    ret, steps = E.rollout(env_id, s0, budget=budget, gamma=gamma, seed=99, sim=5, precision=1, action_grid=grid)
     ret, steps = ret.cpu().numpy(), steps.cpu().numpy()
+    if env_id == 4 and budget == 40:
+        assert steps.max() > 3 and (steps < budget).mean() > 0.5   # the car does leave the track in most rollouts
     for i in range(n):
-        eret, esteps = coracle.rollout(env_id, s0[i], budget, gamma, 99, i, 5, 0)
+        eret, esteps = coracle.rollout(env_id, s0[i], budget, gamma, 99, i, 5, 0, grid=grid or (0, 0))
         assert steps[i] == esteps, (i, steps[i], esteps)
         assert ret[i] == pytest.approx(eret, rel=1e-11, abs=1e-11)
 
@@ -113,3 +132,43 @@ def test_rollout_reset_distribution_and_f32_agreement():
         assert st64[i] == esteps
     assert (st64 != st32).mean() < 2e-3
     assert 15 < st64.mean() < 30   # random CartPole episodes last ~22 steps
+
+
+@pytest.mark.parametrize("precision", [1, 0])
+def test_curve_env_matches_reference_step_vectors(precision):
+    """CurveEnv is reference code (environments/curve_env.py:121-177): the device env against step vectors recorded
+    from the reference's own class (tests/golden/env/curve_env_steps.npz).  float64: terminal flags bit-exact, reals to
+    1e-12; float32: 1e-5 relative, and a containment test decided differently needs a pose within ~1e-5 of the edge."""
+    from islamcts_b200 import engine as E
+    z = _curve_fixture()
+    ns, r, t = E.env_step(4, z["state"], z["action"], precision=precision)
+    ns, r, t = ns.cpu().numpy().astype(np.float64), r.cpu().numpy().astype(np.float64), t.cpu().numpy().astype(bool)
+    if precision == 1:
+        np.testing.assert_array_equal(t, z["terminal"])
+        np.testing.assert_allclose(ns, z["next_state"], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(r, z["reward"], rtol=1e-12)
+    else:
+        same = t == z["terminal"]
+        assert (~same).sum() <= 2
+        np.testing.assert_allclose(ns, z["next_state"], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(r[same], z["reward"][same], rtol=1e-5)
+
+
+def test_curve_containment_shortcut_equals_100_point_test():
+    """The device decides containment from <= 6 of the reference's 100 linspace points (+ full loop when a margin is
+    within 1e-9); on 200k random moves its verdict must equal the oracle's plain 100-point loop."""
+    from islamcts_b200 import engine as E
+    rng = np.random.default_rng(123)
+    n = 200_000
+    x = rng.uniform(-12.0, 10.0, n)
+    lo, hi = -(1 / 50) * (3 * x ** 2) + 27.3, -(1 / 50) * x ** 2 + 27.5
+    y = rng.uniform(lo - 0.2, hi + 0.2)
+    s = np.stack([x, y, rng.uniform(0, 20, n), rng.uniform(0, 360, n), rng.integers(0, 40, n).astype(np.float64)], 1)
+    a = rng.uniform([-5.0, -30.0], [5.0, 30.0], size=(n, 2))
+    ns, r, t = E.env_step(4, s, a, precision=1)
+    r, t = r.cpu().numpy(), t.cpu().numpy().astype(bool)
+    sub = rng.choice(n, 20000, replace=False)
+    for i in sub:
+        _, er, et, _ = coracle.env_step(4, s[i], a[i])
+        assert bool(t[i]) == et and r[i] == pytest.approx(er, rel=1e-12), (i, s[i], a[i])
+    assert 0.05 < t.mean() < 0.95

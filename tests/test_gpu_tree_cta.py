@@ -12,6 +12,9 @@ pytestmark = pytest.mark.gpu
 def _engine(kw, n_trees, sim_capacity, precision, **extra):
     from islamcts_b200.engine import Engine
     kw = dict(kw)
+    g0, g1 = kw.pop("grid0", 0), kw.pop("grid1", 0)
+    if g0:
+        extra["action_grid"] = (g0, g1)
     return Engine(kw.pop("env_id"), agent=kw.pop("agent"), n_trees=n_trees, sim_capacity=sim_capacity,
                   C_=kw.pop("C"), precision=precision, kernel=2, **kw, **extra)
 
@@ -32,10 +35,13 @@ def test_scripted_trace_rebuilds_reference_tree_cta(name, precision):
     rank, act = eng.best(scripted_pos=int(vals[-1]))           # also applies the spw/dpw root re-ordering
     # float32 env: rewards of Pendulum/MountainCar differ in the 7th digit -> totals to 2e-5; counts stay exact
     tol = 1e-9 if precision == 1 else 2e-5
-    assert float(act.cpu()[0]) == pytest.approx(float(g["fit_action"]), abs=1e-12)
+    assert float(act.cpu().reshape(-1)[0]) == pytest.approx(float(g["fit_action"]), abs=1e-12)
     assert_tree_equal(eng.export_tree(0), g, rtol=tol, atol=tol, label=f"{name}/p{precision}: ")
     a, na, tot = eng.root_children(0)
     np.testing.assert_array_equal(na, g["root_na"])
+    if a.ndim == 2:   # the continuous CurveEnv box: (acceleration, steering)
+        np.testing.assert_allclose(a[:, 1], g["root_action2"], rtol=0, atol=1e-12)
+        a = a[:, 0]
     np.testing.assert_allclose(a, g["root_action"], rtol=0, atol=1e-12)
     np.testing.assert_allclose(tot, g["root_total"], rtol=tol, atol=tol)
 
@@ -52,7 +58,17 @@ FREE = {
     "spw_cartpole_k1": dict(env_id=0, agent=2, n_actions=2, max_depth=40, C=1.0, gamma=0.9, alpha1=0.5, k1=1.0),
     "dpw_mountaincar_c4like": dict(env_id=2, agent=3, max_depth=50, C=1.0, gamma=0.99, alpha1=0.5, k1=1.0, alpha2=0.5, k2=1.0),
     "dpw_mountaincar_descend": dict(env_id=2, agent=3, max_depth=50, C=0.5, gamma=0.95, alpha1=0.4, k1=1.0, alpha2=0.2, k2=0.5),
+    # the reference's own env: MctsHash on DiscreteCurveEnv([5, 7]) (sweep_vanilla.py) and APW on CurveEnv's 2-D box (sweep.py)
+    "vanilla_curve_grid": dict(env_id=4, agent=0, n_actions=35, grid0=5, grid1=7, max_depth=15, C=5.0, gamma=0.95),
+    "apw_curve": dict(env_id=4, agent=1, max_depth=15, C=11.0, gamma=0.95, alpha1=0.5, k1=2.0),
 }
+
+
+def _roots(env_id, n_trees, seed):
+    if env_id == 4:  # on-track poses after three braking right turns (the reset pose leaves the track at once)
+        base = np.array([-5.70993649, 25.49759526, 2.5, 0.0, 3.0])
+        return np.stack([base + np.array([0.01 * i, 0.0, 0.05 * i, 0.0, 0.0]) for i in range(n_trees)])
+    return np.stack([coracle.env_reset(env_id, seed, i) for i in range(n_trees)])
 
 
 @pytest.mark.parametrize("name", sorted(FREE))
@@ -62,7 +78,7 @@ def test_free_running_f64_equals_oracle(name, R):
     the CUDA engine and the C oracle share the Philox streams, so whole trees must agree node for node."""
     kw = FREE[name]
     n_trees, n_sim = 24, 160
-    roots = np.stack([coracle.env_reset(kw["env_id"], 5, i) for i in range(n_trees)])
+    roots = _roots(kw["env_id"], n_trees, 5)
     eng = _engine(kw, n_trees, n_sim, 1, rollouts_per_leaf=R, seed=2024, tree_id_base=70)
     eng.set_roots(roots).run(n_sim)
     assert eng.counters()["faults"] == 0
@@ -83,7 +99,10 @@ def test_free_running_f64_equals_oracle(name, R):
     rank, act = rank.cpu().numpy(), act.cpu().numpy()
     for i, t in enumerate(trees):
         rc, erank, eact = t.best()
-        assert rank[i] == erank and act[i] == eact
+        if act.ndim == 2:
+            assert rank[i] == erank and act[i, 0] == eact and act[i, 1] == t.best_action2
+        else:
+            assert rank[i] == erank and act[i] == eact
     exp = {"tree_" + k: v for k, v in trees[5].serialise().items()}
     assert_tree_equal(eng.export_tree(5), exp, rtol=1e-9, atol=1e-9, label=f"{name}/tree5 after best: ")
 
