@@ -31,6 +31,8 @@ def identify_env(env) -> int:
         return _lib.ENV_PENDULUM
     if "mountaincar" in low and ("continuous" in low or hasattr(getattr(u, "action_space", None), "low")):
         return _lib.ENV_MOUNTAINCAR
+    if "curve" in low and hasattr(u, "car"):
+        return _lib.ENV_CURVE                          # the reference's own islaMcts/environments/curve_env.py
     if "frozenlake" in low:
         desc = getattr(u, "desc", None)
         if desc is not None:
@@ -44,10 +46,33 @@ def identify_env(env) -> int:
     raise NotImplementedError(f"environment {name!r} has no device implementation (supported: {sorted(ENV_NAMES)})")
 
 
+def env_action_info(env, env_id: int):
+    """(number of discrete actions or 0, DiscreteCurveEnv grid or None) of the env object."""
+    if env_id != _lib.ENV_CURVE:
+        return N_ACTIONS[env_id], None
+    u = getattr(env, "unwrapped", env)
+    n = getattr(getattr(u, "action_space", None), "n", None)
+    if n is None:
+        return 0, None
+    table = np.asarray(getattr(u, "actions", ()), dtype=np.float64).reshape(-1, 2)
+    if len(table) != int(n) or n < 1:
+        raise NotImplementedError("discrete CurveEnv without the env.actions table of DiscreteCurveEnv")
+    g1 = int(np.sum(table[:, 0] == table[0, 0])) if len(np.unique(table[:, 0])) > 1 else len(table)
+    g0 = len(table) // g1
+    want = np.array([(a, b) for a in np.linspace(-5.0, 5.0, g0) for b in np.linspace(-30.0, 30.0, g1)]).reshape(-1, 2)
+    if g0 * g1 != len(table) or not np.array_equal(table, want):
+        raise NotImplementedError("env.actions is not linspace(-5, 5, g0) x linspace(-30, 30, g1) (curve_env.py:190-198)")
+    if len(table) > 128:
+        raise NotImplementedError(f"DiscreteCurveEnv with {len(table)} actions: the device engine holds at most 128")
+    return len(table), (g0, g1)
+
+
 def env_root_state(env, env_id: int) -> np.ndarray:
     u = getattr(env, "unwrapped", env)
     if env_id == _lib.ENV_FROZENLAKE:
         return np.array([float(int(u.s))], dtype=np.float64)
+    if env_id == _lib.ENV_CURVE:
+        return np.array([*np.asarray(u.car.state, dtype=np.float64).reshape(-1)[:4], float(u.n_step)], dtype=np.float64)
     st = getattr(u, "state", None)
     if st is None:
         raise ValueError("env.unwrapped.state is None: call env.reset() before fit()")
@@ -162,14 +187,16 @@ class AbstractMcts:
                   budget_mode=_lib.BUDGET_ZERO if zero else _lib.BUDGET_TO_MAX_DEPTH,
                   rollouts_per_leaf=int(p.rollouts_per_leaf),
                   precision=_lib.PRECISION_F64 if p.precision == "f64" else _lib.PRECISION_F32, device=p.device)
+        n, grid = env_action_info(p.env, env_id)
+        if grid:
+            kw["action_grid"] = grid
         if self.DISCRETE:
-            n = N_ACTIONS[env_id]
             if n == 0:
                 raise NotImplementedError(f"{type(self).__name__} needs a discrete action space")
             if p.n_actions is not None and int(p.n_actions) != n:
                 raise ValueError(f"n_actions={p.n_actions} but the environment has {n} actions")
             kw["n_actions"] = n
-        elif N_ACTIONS[env_id] != 0:
+        elif n != 0:
             raise NotImplementedError(f"{type(self).__name__} samples a continuous Box action space")
         self._agent_kwargs(kw)
         return kw
@@ -214,7 +241,7 @@ class AbstractMcts:
         rank, act = eng.best()
         if int(self.param.n_trees) > 1:
             return self._finish_ensemble(eng)
-        rank0, act0 = int(rank[0].item()), float(act[0].item())
+        rank0, act0 = int(rank[0].item()), act[0].cpu().numpy().reshape(-1)
         self._fill_q_values(eng)
         return self._format_action(rank0, act0)
 
@@ -245,7 +272,7 @@ class AbstractMcts:
         return np.int64(np.random.choice(best))
 
     def _format_action(self, rank, action_value):
-        return np.int64(int(action_value))
+        return np.int64(int(action_value[0]))
 
     # ------------------------------------------------------------------ proxies
     def _make_state(self, data):
@@ -255,6 +282,7 @@ class AbstractMcts:
         ser = self._engine.export_tree(0)
         kind, depth, count, total = ser["kind"], ser["depth"], ser["count"], ser["total"]
         term, action = ser["terminal"], ser["action"]
+        action2 = ser.get("action2") if getattr(self._engine, "action_dim", 1) == 2 else None
         root = self._make_state(self._root_stub.data)
         root.ns, root.total = int(count[0]), float(total[0])
         stack = [(root, 0)]              # (node object, depth) of the open state nodes
@@ -268,6 +296,9 @@ class AbstractMcts:
                 parent = stack[-1][0]
                 if self.DISCRETE:
                     data = int(action[i]); key = data
+                elif action2 is not None:          # CurveEnv: float64 (acceleration, steering) keyed like action.tobytes()
+                    data = np.array([action[i], action2[i]], dtype=np.float64)
+                    key = data.tobytes()
                 else:
                     data = np.array([action[i]], dtype=np.float64 if action[i] != np.float32(action[i]) else dtype)
                     key = data.tobytes()

@@ -25,4 +25,4 @@ class MctsActionProgressiveWideningHash(AbstractMcts):
 
     def _format_action(self, rank, action_value):
         space = getattr(self.param.env, "action_space", None)
-        return np.array([action_value], dtype=getattr(space, "dtype", np.float32))   # policy.data (:44)
+        return np.array(action_value, dtype=getattr(space, "dtype", np.float32)).reshape(-1)   # policy.data (:44)

@@ -18,4 +18,4 @@ class MctsDoubleProgressiveWideningHash(AbstractMcts):
         # spaces that line raises at HEAD.  Here the action comes back in the space's own dtype, so that
         # ``agent.root.actions[action.tobytes()]`` (sweep.py:196) finds the node.
         space = getattr(self.param.env, "action_space", None)
-        return np.array([action_value], dtype=getattr(space, "dtype", np.float64))
+        return np.array(action_value, dtype=getattr(space, "dtype", np.float64)).reshape(-1)

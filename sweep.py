@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """CLI mirror of the reference's sweep.py: same flag names, types and defaults (sweep.py:22-47 of the reference;
---n_angles/--n_accelerations of sweep_vanilla.py:45-48 are accepted and ignored until DiscreteCurveEnv is on the
-device).  --environment is effective here (the reference parses and ignores it, sweep.py:173).  wandb / plotting
-are out of scope; results are printed as JSON lines."""
+--n_angles/--n_accelerations of sweep_vanilla.py:45-48 size DiscreteCurveEnv like sweep_vanilla.py:177).
+--environment is effective here (the reference parses and ignores it and always builds CurveEnv, sweep.py:173-175):
+a gym id, "CurveEnv" or "DiscreteCurveEnv".  wandb / plotting are out of scope; results are printed as JSON lines."""
 from __future__ import annotations
 
 import argparse
@@ -58,7 +58,7 @@ def get_function(name, args):
     raise NotImplementedError(f"--{name}: not on the device yet (genetic is a SURVEY 8f row)")
 
 
-def create_agent(args, env, observation):
+def create_agent(args, env, observation, seed=None):
     from islamcts_b200.agents import Mcts, MctsApw, MctsDpw, MctsHash, MctsSpw
     from islamcts_b200.agents.parameters.dpw_parameters import DpwParameters
     from islamcts_b200.agents.parameters.mcts_parameters import MctsParameters
@@ -67,7 +67,7 @@ def create_agent(args, env, observation):
     common = dict(root_data=observation, env=env, n_sim=args["nsim"], C=args["c"], action_selection_fn=get_function(args["as"], args),
                   gamma=args["gamma"], rollout_selection_fn=get_function(args["rollout"], args), max_depth=args["max_depth"],
                   n_actions=n_act, x_values=None, y_values=None, depths=None, n_trees=args["n_trees"],
-                  rollouts_per_leaf=args["rollouts_per_leaf"], seed=args["seed"], depth_mode=args["depth_mode"],
+                  rollouts_per_leaf=args["rollouts_per_leaf"], seed=seed, depth_mode=args["depth_mode"],
                   precision=args["precision"])
     algo = args["algorithm"]
     if algo == "vanilla":
@@ -87,11 +87,20 @@ def main(argv=None):
     from islamcts_b200 import envs
     rewards = []
     for ep in range(args["n_episodes"]):
-        env = envs.make(args["environment"], api=4, seed=None if args["seed"] is None else args["seed"] + ep)
+        ep_seed = None if args["seed"] is None else args["seed"] + ep
+        if args["environment"] == "CurveEnv":
+            from islamcts_b200.environments import CurveEnv
+            env = CurveEnv(seed=ep_seed)                                                    # sweep.py:175
+        elif args["environment"] == "DiscreteCurveEnv":
+            from islamcts_b200.environments import DiscreteCurveEnv
+            env = DiscreteCurveEnv([args["n_accelerations"], args["n_angles"]], seed=ep_seed)   # sweep_vanilla.py:177
+        else:
+            env = envs.make(args["environment"], api=4, seed=ep_seed)
         observation = env.reset()
         done, total_reward, n_steps, t0 = False, 0.0, 0, time.time()
         while not done and n_steps < args["max_steps"]:
-            agent = create_agent(args, env.unwrapped, observation)      # a new agent (tree) every real step, sweep.py:186
+            step_seed = None if args["seed"] is None else args["seed"] + 100003 * ep + n_steps
+            agent = create_agent(args, env.unwrapped, observation, step_seed)   # a new agent (tree) every real step, sweep.py:186
             agent.root.data = observation
             action = agent.fit()
             observation, reward, done, _ = env.step(action)

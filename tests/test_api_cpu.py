@@ -93,3 +93,27 @@ def test_compat_package_paths():
     from islaMcts.utils.action_selection_functions import ucb1 as u2
     import islamcts_b200.agents.mcts_hash as real
     assert MctsHash is real.MctsHash and P2 is MctsParameters and u2 is ucb1
+
+
+def test_curve_env_host_mirror_without_gpu():
+    """islaMcts.environments.curve_env import path, spaces, action table and env identification (no device call)."""
+    import itertools
+    from islaMcts.environments.curve_env import CurveEnv, DiscreteCurveEnv
+    from islamcts_b200 import _lib
+    from islamcts_b200.agents.abstract_mcts import env_action_info, env_root_state, identify_env
+    env = CurveEnv()
+    assert env.action_space.shape == (2,) and env.action_space.dtype == np.float64
+    np.testing.assert_array_equal(env.action_space.low, [-5.0, -30.0])
+    np.testing.assert_array_equal(env.reset(), [-11.0, 21.0, 10.0, 90.0])
+    assert identify_env(env) == _lib.ENV_CURVE and env_action_info(env, _lib.ENV_CURVE) == (0, None)
+    np.testing.assert_array_equal(env_root_state(env, _lib.ENV_CURVE), [-11.0, 21.0, 10.0, 90.0, 0.0])
+    assert env.lower_bound(0.0) == 27.3 and env.higher_bound(0.0) == 27.5
+    d = DiscreteCurveEnv([5, 19])
+    assert d.action_space.n == 95 and len(d.actions) == 95
+    assert d.actions == list(itertools.product(np.linspace(-5, 5, 5), np.linspace(-30, 30, 19)))
+    assert env_action_info(d, _lib.ENV_CURVE) == (95, (5, 19))
+    assert env_action_info(DiscreteCurveEnv([1, 4]), _lib.ENV_CURVE) == (4, (1, 4))
+    assert env_action_info(DiscreteCurveEnv([4, 1]), _lib.ENV_CURVE) == (4, (4, 1))
+    big = DiscreteCurveEnv([10, 20])
+    with pytest.raises(NotImplementedError):
+        env_action_info(big, _lib.ENV_CURVE)

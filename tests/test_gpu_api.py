@@ -137,3 +137,104 @@ def test_ensemble_fit_merges_root_statistics():
     ag = MctsHash(p)
     a = ag.fit()
     assert a in (0, 1) and ag.root_statistics["na"].sum() == 2048 * 100
+
+
+def test_curve_env_sweep_flow_apw_and_vanilla():
+    """sweep.py:174-199 / sweep_vanilla.py:176-200 of the reference on its own CurveEnv: a fresh agent per real step,
+    ``agent.root.actions[action.tobytes()]`` / ``agent.root.actions[action]`` look-ups, depth metrics, env.step."""
+    from islamcts_b200.agents import MctsApw, MctsHash
+    from islamcts_b200.agents.parameters.mcts_parameters import MctsParameters
+    from islamcts_b200.agents.parameters.pw_parameters import PwParameters
+    from islamcts_b200.environments import CurveEnv, DiscreteCurveEnv
+    from islamcts_b200.utils.action_selection_functions import continuous_default_policy, ucb1
+    common = dict(n_sim=300, C=11, action_selection_fn=ucb1, gamma=0.95, rollout_selection_fn=continuous_default_policy,
+                  max_depth=30, seed=21, precision="f64")
+    # --- APW on the continuous box
+    env = CurveEnv()
+    obs = env.reset()
+    for step in range(3):
+        p = PwParameters(root_data=obs, env=env.unwrapped, n_actions=None, alpha=0.5, k=3,
+                         action_expansion_function=continuous_default_policy, **common)
+        agent = MctsApw(p)
+        agent.root.data = obs
+        action = agent.fit()
+        assert action.dtype == np.float64 and action.shape == (2,)
+        assert -5 <= action[0] <= 5 and -30 <= action[1] <= 30
+        node = agent.root.actions[action.tobytes()]
+        assert node.q_value == pytest.approx(agent.q_values.max())
+        assert node.get_depth_max(0) >= 0 and len(agent.root.actions) == len(agent.q_values)
+        # same Philox key -> the oracle builds the same root (float64 env arithmetic on both sides)
+        t = coracle.Tree(coracle.make_config(4, agent=1, max_depth=30, C_=11.0, gamma=0.95, alpha1=0.5, k1=3.0, seed=21),
+                         [*env.car.state, env.n_step])
+        t.run(300)
+        ea, ena, etot = t.root_children()
+        np.testing.assert_array_equal(agent.root_statistics["na"], ena)
+        np.testing.assert_array_equal(agent.root_statistics["action"][:, 0], ea)
+        np.testing.assert_array_equal(agent.root_statistics["action"][:, 1], t.root_action2)
+        np.testing.assert_allclose(agent.root_statistics["total"], etot, rtol=1e-9)
+        n_before = env.n_step
+        obs, reward, done, extra = env.step(np.array([-5.0, -30.0]))   # brake + turn right keeps the car on the track
+        assert extra is None and env.n_step == n_before + 1 and not done
+        eobs, er, _, _ = coracle.env_step(4, [*p.root_data, n_before], [-5.0, -30.0])
+        np.testing.assert_allclose(obs, eobs[:4], rtol=1e-13)
+        assert reward == pytest.approx(er, rel=1e-13)
+    env.reset()
+    assert env.n_step == 3                    # reset() re-creates the car but keeps the step counter (curve_env.py:179-182)
+    # --- vanilla MctsHash on the discrete grid (sweep_vanilla.py:177 uses [n_accelerations, n_angles])
+    denv = DiscreteCurveEnv([5, 7])
+    obs = denv.reset()
+    for a in (0, 0, 0):
+        obs, _, done, _ = denv.step(a)
+    assert not done and denv.actions[0] == (-5.0, -30.0) and denv.action_space.n == 35
+    p = MctsParameters(root_data=obs, env=denv.unwrapped, n_actions=denv.action_space.n, **common)
+    agent = MctsHash(p)
+    agent.root.data = obs
+    action = agent.fit()
+    assert isinstance(action, np.int64) and 0 <= action < 35
+    node = agent.root.actions[action]
+    assert node.q_value == pytest.approx(agent.q_values.max())
+    assert agent.root.ns == 300 and len(agent.root.actions) == 35
+    t = coracle.Tree(coracle.make_config(4, agent=0, n_actions=35, grid0=5, grid1=7, max_depth=30, C_=11.0, gamma=0.95, seed=21),
+                     [*denv.car.state, denv.n_step])
+    t.run(300)
+    ea, ena, etot = t.root_children()
+    np.testing.assert_array_equal(agent.root_statistics["na"], ena)
+    np.testing.assert_array_equal(agent.root_statistics["action"], ea)
+    obs2, reward, done, _ = denv.step(action)
+    assert obs2.shape == (4,)
+    # root-parallel ensemble over the 35 grid actions
+    p8 = MctsParameters(root_data=obs, env=denv.unwrapped, n_actions=35, n_trees=8, **common)
+    a8 = MctsHash(p8).fit()
+    assert isinstance(a8, np.int64) and 0 <= a8 < 35
+
+
+def test_reference_curve_env_objects_are_recognised():
+    """A maintainer passes the REFERENCE's env object as param.env; only attributes are read (car.state, n_step,
+    action_space, actions).  Stand-ins with exactly those attributes are used here (the reference is not on the GPU box)."""
+    import itertools
+    import types
+    from islamcts_b200.agents import MctsHash
+    from islamcts_b200.agents.parameters.mcts_parameters import MctsParameters
+    from islamcts_b200.utils.action_selection_functions import continuous_default_policy, ucb1
+    class DiscreteCurveEnv:     # same class name as the reference's
+        pass
+    env = DiscreteCurveEnv()
+    env.car = types.SimpleNamespace(state=np.array([-5.70993649, 25.49759526, 2.5, 0.0]))
+    env.n_step = 3
+    env.actions = list(itertools.product(np.linspace(-5.0, 5.0, 3), np.linspace(-30.0, 30.0, 4)))
+    env.action_space = types.SimpleNamespace(n=12)
+    p = MctsParameters(root_data=env.car.state, env=env, n_sim=200, C=5, action_selection_fn=ucb1, gamma=0.9,
+                       rollout_selection_fn=continuous_default_policy, max_depth=20, n_actions=12, seed=2, precision="f64")
+    agent = MctsHash(p)
+    a = agent.fit()
+    t = coracle.Tree(coracle.make_config(4, agent=0, n_actions=12, grid0=3, grid1=4, max_depth=20, C_=5.0, gamma=0.9, seed=2),
+                     [*env.car.state, 3.0])
+    t.run(200)
+    ea, ena, etot = t.root_children()
+    np.testing.assert_array_equal(agent.root_statistics["na"], ena)
+    rc, rank, eact = t.best()
+    # the final arg-max draw continues the tree stream on both sides
+    assert int(a) == int(eact)
+    env.actions[5] = (0.123, 4.0)                   # not the linspace grid any more -> refuse, never guess
+    with pytest.raises(NotImplementedError):
+        MctsHash(p).fit()
