@@ -104,12 +104,6 @@ __device__ __forceinline__ double warp_max(double x) {
     for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(kFull, x, o));
     return x;
 }
-__device__ __forceinline__ double warp_min(double x) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x = fmin(x, __shfl_xor_sync(kFull, x, o));
-    return x;
-}
-
 template <int ENV, typename T, bool SCRIPTED>
 struct Search {
     static constexpr int S = EnvTraits<ENV>::S;
@@ -340,23 +334,50 @@ struct Search {
         return found;
     }
 
-    // genetic_policy2 (utils/action_selection_functions.py:104-136), one action dimension, float32 Box.  p is drawn
+    // Box bounds per action dimension widened to double; gym boxes are float32, CurveEnv's box is float64
+    __device__ __forceinline__ bool box_bounds(double (&lo)[2], double (&hi)[2]) const {
+        if constexpr (ENV == ENV_CURVE) { lo[0] = -5.0; hi[0] = 5.0; lo[1] = -30.0; hi[1] = 30.0; return false; }
+        float lof, hif; env_action_bounds(ENV, lof, hif);
+        lo[0] = (double)lof; hi[0] = (double)hif; lo[1] = hi[1] = 0.0;
+        return true;
+    }
+    __device__ __forceinline__ double act2(int a) const { return p.action_dim == 2 ? q.a_value2[a] : 0.0; }
+    // scipy cdist(..., 'euclidean') on float64 rows: sqrt(sum (u_i - v_i)^2); one dimension: |d|
+    __device__ __forceinline__ double euclid(double x0, double x1, double y0, double y1) const {
+        const double d0 = __dsub_rn(x0, y0);
+        if (p.action_dim != 2) return fabs(d0);
+        const double d1 = __dsub_rn(x1, y1);
+        return __dsqrt_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)));
+    }
+
+    // genetic_policy2 (utils/action_selection_functions.py:104-136), one or two action dimensions.  p is drawn
     // first on every call; 0 / 1 / 2 existing actions get the centre / a random bound / the missing bound; later calls
     // take default_policy with probability 1 - epsilon, else the mean of the two LOWEST-q actions (the list is sorted
     // ascending by q and entries [0], [1] are used, :108-112; python's sort is stable, so ties keep insertion order).
-    __device__ double genetic2_expand(int s) {
+    // float32 gym boxes average in float32, CurveEnv's float64 box in float64 (np.mean(..., axis=0)).
+    __device__ double genetic2_expand(int s, double& out2) {
         const double pr = u01();
         const int off = q.s_coff[s], n = q.s_ccnt[s];
-        float lof, hif; env_action_bounds(ENV, lof, hif);
-        if (n == 0) return (double)__fmul_rn(__fadd_rn(lof, hif), 0.5f);
+        double lo[2], hi[2];
+        const bool f32 = box_bounds(lo, hi);
+        auto mean2 = [&](double x, double y) -> double {
+            return f32 ? (double)__fmul_rn(__fadd_rn((float)x, (float)y), 0.5f) : __dmul_rn(__dadd_rn(x, y), 0.5);
+        };
+        out2 = 0.0;
+        if (n == 0) { out2 = mean2(lo[1], hi[1]); return mean2(lo[0], hi[0]); }
         if (n == 1) {
             int idx;
             if constexpr (SCRIPTED) idx = (int)tc.take(ISLA_K_CHOICES);
             else idx = (1.0 > __dmul_rn(u32_to_d01(ts.next()), 2.0)) ? 0 : 1;   // random.choices([high, low])
-            return idx == 0 ? (double)hif : (double)lof;
+            out2 = idx == 0 ? hi[1] : lo[1];
+            return idx == 0 ? hi[0] : lo[0];
         }
-        if (n == 2) return find_action(s, (double)hif) >= 0 ? (double)lof : (double)hif;
-        if (pr < __dsub_rn(1.0, p.epsilon)) { double unused; return tree_action(unused); }
+        if (n == 2) {
+            const bool has_high = find_action(s, hi[0], hi[1]) >= 0;
+            out2 = has_high ? lo[1] : hi[1];
+            return has_high ? lo[0] : hi[0];
+        }
+        if (pr < __dsub_rn(1.0, p.epsilon)) return tree_action(out2);
         auto qv = [&](int i) -> double { const int a = q.ipool[off + i]; return __ddiv_rn(q.a_total[a], (double)q.a_na[a]); };
         int r0 = -1, r1 = -1;
         for (int pass = 0; pass < 2; ++pass) {
@@ -374,15 +395,19 @@ struct Search {
             }
             if (pass == 0) r0 = br; else r1 = br;
         }
-        const float x = (float)q.a_value[q.ipool[off + r0]], y = (float)q.a_value[q.ipool[off + r1]];
-        return (double)__fmul_rn(__fadd_rn(x, y), 0.5f);   // np.mean([best, second], axis=0) in float32
+        const int a0 = q.ipool[off + r0], a1 = q.ipool[off + r1];
+        out2 = p.action_dim == 2 ? mean2(q.a_value2[a0], q.a_value2[a1]) : 0.0;
+        return mean2(q.a_value[a0], q.a_value[a1]);   // np.mean([best, second], axis=0)
     }
 
-    // voo (utils/action_selection_functions.py:139-205), one action dimension
-    __device__ double voo_expand(int s) {
+    // voo (utils/action_selection_functions.py:139-205), one or two action dimensions.  `scratch` (the CTA's rollout
+    // reduction buffer, idle during the descent) holds the accepted samples: 3 doubles each.
+    __device__ double voo_expand(int s, double& out2, double* scratch) {
         const double pr = u01();
         const int off = q.s_coff[s], n = q.s_ccnt[s];
-        if (pr <= p.epsilon || n == 0) { double unused; return tree_action(unused); }
+        out2 = 0.0;
+        if (pr <= p.epsilon || n == 0) return tree_action(out2);
+        const bool two = p.action_dim == 2;
         auto qv = [&](int i) -> double { const int a = q.ipool[off + i]; return __ddiv_rn(q.a_total[a], (double)q.a_na[a]); };
         double qmax = -INFINITY;
         for (int i = lane; i < n; i += 32) qmax = fmax(qmax, qv(i));
@@ -400,53 +425,67 @@ struct Search {
             if (pos < seen + c) { unsigned bb = b; for (int k = 0; k < pos - seen; ++k) bb &= bb - 1; best = base + __ffs(bb) - 1; break; }
             seen += c;
         }
-        const double abest = q.a_value[q.ipool[off + best]];
-        float lof, hif; env_action_bounds(ENV, lof, hif);
-        double out = abest, out_d = INFINITY;
-        int n_acc = 0, out_ties = 0;
-        // the accepted samples are reduced on the fly: keep the minimum distance, count its ties, and
-        // re-draw among them at the end exactly like np.random.choice(np.where(d == d.min())[0])
-        double acc_x[8], acc_d[8];
-        const int n_samples = p.voo_n < 8 ? p.voo_n : 8;
+        const int abest_node = q.ipool[off + best];
+        const double abest = q.a_value[abest_node], abest2 = act2(abest_node);
+        double lo[2], hi[2];
+        box_bounds(lo, hi);
+        int n_acc = 0;
+        const int n_samples = p.voo_n;
         for (int k = 0; k < n_samples && !tc.fault; ++k) {
             int n_try = 0;
             double tmin = INFINITY; int tmin_ties = 0;  // closest tried sample (max_try fallback)
             // the fallback needs the pos-th closest-tried sample: replay it from a saved stream position
             Stream saved = ts; const long long saved_pos = tc.pos;
             for (;;) {
-                const double x = uniform((double)lof, (double)hif);
-                const double db = fabs(__dsub_rn(x, abest));
+                const double x = uniform(lo[0], hi[0]);
+                const double x2 = two ? uniform(lo[1], hi[1]) : 0.0;
+                const double db = euclid(x, x2, abest, abest2);
                 if (db < tmin) { tmin = db; tmin_ties = 1; } else if (db == tmin) { ++tmin_ties; }
                 if (db == 0.0) break;  // :177-178 leaves the loop WITHOUT appending
                 bool ok = true;
                 for (int base = 0; base < n; base += 32) {
                     const int i = base + lane;
-                    const bool bad = i < n && i != best && !(db <= fabs(__dsub_rn(x, q.a_value[q.ipool[off + i]])));
+                    bool bad = false;
+                    if (i < n && i != best) { const int a = q.ipool[off + i]; bad = !(db <= euclid(x, x2, q.a_value[a], act2(a))); }
                     if (__any_sync(kFull, bad)) { ok = false; break; }
                 }
-                if (ok) { acc_x[n_acc] = x; acc_d[n_acc] = db; ++n_acc; break; }
-                ++n_try;
-                if (n_try >= p.voo_max_try) {
-                    int pp = choice(tmin_ties);
-                    // replay the tried samples to find the pp-th one at distance tmin
-                    Stream after = ts; const long long after_pos = tc.pos;
-                    ts = saved; tc.pos = saved_pos;
-                    double pick = x;
-                    for (int j = 0; j < n_try; ++j) {
-                        const double xj = uniform((double)lof, (double)hif);
-                        if (fabs(__dsub_rn(xj, abest)) == tmin) { if (pp == 0) { pick = xj; } --pp; }
+                double acc_x = x, acc_x2 = x2, acc_d = db;
+                bool accept = ok;
+                if (!ok) {
+                    ++n_try;
+                    if (n_try >= p.voo_max_try) {
+                        int pp = choice(tmin_ties);
+                        // replay the tried samples to find the pp-th one at distance tmin
+                        Stream after = ts; const long long after_pos = tc.pos;
+                        ts = saved; tc.pos = saved_pos;
+                        for (int j = 0; j < n_try; ++j) {
+                            const double xj = uniform(lo[0], hi[0]);
+                            const double xj2 = two ? uniform(lo[1], hi[1]) : 0.0;
+                            if (euclid(xj, xj2, abest, abest2) == tmin) { if (pp == 0) { acc_x = xj; acc_x2 = xj2; } --pp; }
+                        }
+                        ts = after; tc.pos = after_pos;
+                        acc_d = tmin;
+                        accept = true;
                     }
-                    ts = after; tc.pos = after_pos;
-                    acc_x[n_acc] = pick; acc_d[n_acc] = tmin; ++n_acc;
+                }
+                if (accept) {
+                    if (lane == 0) { scratch[3 * n_acc] = acc_x; scratch[3 * n_acc + 1] = acc_x2; scratch[3 * n_acc + 2] = acc_d; }
+                    ++n_acc;
                     break;
                 }
             }
         }
-        for (int i = 0; i < n_acc; ++i) { if (acc_d[i] < out_d) { out_d = acc_d[i]; out_ties = 1; } else if (acc_d[i] == out_d) ++out_ties; }
+        __syncwarp();
+        // np.random.choice(np.where(d == d.min())[0]) over the accepted samples
+        double out = abest, out_d = INFINITY;
+        out2 = abest2;
+        int out_ties = 0;
+        for (int i = 0; i < n_acc; ++i) { const double d = scratch[3 * i + 2]; if (d < out_d) { out_d = d; out_ties = 1; } else if (d == out_d) ++out_ties; }
         if (n_acc > 0) {
             int pp = choice(out_ties);
-            for (int i = 0; i < n_acc; ++i) if (acc_d[i] == out_d) { if (pp == 0) out = acc_x[i]; --pp; }
+            for (int i = 0; i < n_acc; ++i) if (scratch[3 * i + 2] == out_d) { if (pp == 0) { out = scratch[3 * i]; out2 = scratch[3 * i + 1]; } --pp; }
         }
+        __syncwarp();
         return out;
     }
 };
@@ -560,8 +599,8 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                     const double cap = ns_now < p.ln_count ? p.pw1_table[ns_now] : ceil(__dmul_rn(p.k1, pow((double)ns_now, p.alpha1)));
                     if (n_act == 0 || (double)n_act <= cap) {
                         double val, val2 = 0.0;
-                        if (p.agent == ISLA_AGENT_APW && p.expansion == ISLA_EXPAND_VOO) val = ctx.voo_expand(s);
-                        else if (p.agent == ISLA_AGENT_APW && p.expansion == ISLA_EXPAND_GENETIC2) val = ctx.genetic2_expand(s);
+                        if (p.agent == ISLA_AGENT_APW && p.expansion == ISLA_EXPAND_VOO) val = ctx.voo_expand(s, val2, red);
+                        else if (p.agent == ISLA_AGENT_APW && p.expansion == ISLA_EXPAND_GENETIC2) val = ctx.genetic2_expand(s, val2);
                         else val = ctx.tree_action(val2);  // dpw ignores --ae (mcts_double_...:57)
                         const int old = ctx.find_action(s, val, val2);
                         if (p.agent == ISLA_AGENT_APW) {
@@ -990,10 +1029,9 @@ int cta_fill_layout(const isla_config& cfg, isla_layout& lay) {
         set_error("n_actions=%d does not match env (%d)", cfg.n_actions, env_actions); return ISLA_ERR_INVALID;
     }
     if (cfg.expansion != ISLA_EXPAND_RANDOM && cfg.agent != ISLA_AGENT_APW) { set_error("voo / genetic2 expansion are APW options"); return ISLA_ERR_INVALID; }
-    if (cfg.expansion != ISLA_EXPAND_RANDOM && cfg.env_id == ISLA_ENV_CURVE) { set_error("voo / genetic2 expansion: one action dimension only (CurveEnv has two)"); return ISLA_ERR_INVALID; }
     if (cfg.expansion < ISLA_EXPAND_RANDOM || cfg.expansion > ISLA_EXPAND_GENETIC2) { set_error("unknown expansion %d", cfg.expansion); return ISLA_ERR_INVALID; }
-    if (cfg.expansion == ISLA_EXPAND_VOO && (cfg.voo_n_samples < 1 || cfg.voo_n_samples > 8 || cfg.voo_max_try < 1)) {
-        set_error("voo: n_samples must be in [1, 8] and max_try >= 1"); return ISLA_ERR_INVALID;
+    if (cfg.expansion == ISLA_EXPAND_VOO && (cfg.voo_n_samples < 1 || cfg.voo_n_samples > kMaxRollSmem / 3 || cfg.voo_max_try < 1)) {
+        set_error("voo: n_samples must be in [1, %d] and max_try >= 1", kMaxRollSmem / 3); return ISLA_ERR_INVALID;
     }
     auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
     lay.kernel = ISLA_KERNEL_CTA_PER_TREE;

@@ -470,75 +470,105 @@ static int find_action_bits(const orc_tree* t, int sidx, const double* value) {
     return -1;
 }
 
-/* voo: utils/action_selection_functions.py:139-205 (1-D action spaces) */
-static double voo_expand(orc_tree* t, int sidx) {
+/* Box bounds of the env's action space widened to double, per dimension; gym boxes are float32, CurveEnv's is float64 */
+static int box_bounds(const orc_tree* t, double lo[2], double hi[2]) {
+    if (t->cfg.env_id == ORC_ENV_CURVE) { lo[0] = -5.0; hi[0] = 5.0; lo[1] = -30.0; hi[1] = 30.0; return 0; }
+    float lowf, highf; action_bounds(t->cfg.env_id, &lowf, &highf);
+    lo[0] = (double)lowf; hi[0] = (double)highf; lo[1] = hi[1] = 0.0;
+    return 1; /* float32 box */
+}
+/* scipy cdist(..., 'euclidean') on float64 rows: sqrt(sum (u_i - v_i)^2); one dimension: sqrt(d*d) == |d| */
+static double euclid(const double* u, const double* v, int D) {
+    if (D == 1) return fabs(u[0] - v[0]);
+    const double d0 = u[0] - v[0], d1 = u[1] - v[1];
+    return sqrt(d0 * d0 + d1 * d1);
+}
+
+/* voo: utils/action_selection_functions.py:139-205 (one or two action dimensions) */
+static void voo_expand(orc_tree* t, int sidx, double out[2]) {
     snode* s = &t->S[sidx];
+    const int D = orc_action_dim(t->cfg.env_id);
+    out[0] = out[1] = 0.0;
     double p = rnd_u01(t);
-    if (p <= t->cfg.epsilon || s->n_act == 0) { double d[2]; rnd_action(t, &t->tree_stream, d); return d[0]; }
+    if (p <= t->cfg.epsilon || s->n_act == 0) { rnd_action(t, &t->tree_stream, out); return; }
     int n = s->n_act;
-    double* act = (double*)malloc(sizeof(double) * n);
+    double* act = (double*)malloc(sizeof(double) * 2 * n);
     double* q = (double*)malloc(sizeof(double) * n);
     int i = 0; double qmax = -INFINITY;
     for (int a = s->first_act; a >= 0; a = t->A[a].next_act, ++i) {
-        act[i] = t->A[a].value[0]; q[i] = t->A[a].total / (double)t->A[a].na; if (q[i] > qmax) qmax = q[i];
+        act[2 * i] = t->A[a].value[0]; act[2 * i + 1] = t->A[a].value[1];
+        q[i] = t->A[a].total / (double)t->A[a].na; if (q[i] > qmax) qmax = q[i];
     }
     int ties = 0; for (i = 0; i < n; ++i) ties += (q[i] == qmax);
     int pos = rnd_choice(t, ties), best = 0;
     for (i = 0; i < n; ++i) if (q[i] == qmax) { if (pos-- == 0) { best = i; break; } }
-    float lowf, highf; action_bounds(t->cfg.env_id, &lowf, &highf);
+    double lo[2], hi[2]; box_bounds(t, lo, hi);
     const int ns_ = t->cfg.voo_n_samples, max_try = t->cfg.voo_max_try;
-    double* samp = (double*)malloc(sizeof(double) * (ns_ > 0 ? ns_ : 1));
+    double* samp = (double*)malloc(sizeof(double) * 2 * (ns_ > 0 ? ns_ : 1));
     double* sdist = (double*)malloc(sizeof(double) * (ns_ > 0 ? ns_ : 1));
-    double* tried = (double*)malloc(sizeof(double) * (max_try + 1));
+    double* tried = (double*)malloc(sizeof(double) * 2 * (max_try + 1));
     double* dtried = (double*)malloc(sizeof(double) * (max_try + 1));
     int n_acc = 0;
     for (int k = 0; k < ns_; ++k) {
         int n_try = 0;
         for (;;) {
-            double x = rnd_uniform(t, (double)lowf, (double)highf);
-            double db = fabs(x - act[best]);
-            tried[n_try] = x; dtried[n_try] = db;
+            double x[2] = {0.0, 0.0};
+            for (int d = 0; d < D; ++d) x[d] = rnd_uniform(t, lo[d], hi[d]);   /* np.random.uniform(low, high, shape) */
+            double db = euclid(x, act + 2 * best, D);
+            tried[2 * n_try] = x[0]; tried[2 * n_try + 1] = x[1]; dtried[n_try] = db;
             if (db == 0) break; /* :177-178 exits WITHOUT appending */
-            int ok = 1; for (i = 0; i < n; ++i) if (i != best && !(db <= fabs(x - act[i]))) { ok = 0; break; }
-            if (ok) { samp[n_acc] = x; sdist[n_acc] = db; n_acc++; break; }
+            int ok = 1; for (i = 0; i < n; ++i) if (i != best && !(db <= euclid(x, act + 2 * i, D))) { ok = 0; break; }
+            if (ok) { samp[2 * n_acc] = x[0]; samp[2 * n_acc + 1] = x[1]; sdist[n_acc] = db; n_acc++; break; }
             n_try++;
             if (n_try >= max_try) {
                 double dm = INFINITY; for (i = 0; i < max_try; ++i) if (dtried[i] < dm) dm = dtried[i];
                 int tt = 0; for (i = 0; i < max_try; ++i) tt += (dtried[i] == dm);
                 int pp = rnd_choice(t, tt), pick = 0;
                 for (i = 0; i < max_try; ++i) if (dtried[i] == dm) { if (pp-- == 0) { pick = i; break; } }
-                samp[n_acc] = tried[pick]; sdist[n_acc] = dtried[pick]; n_acc++;
+                samp[2 * n_acc] = tried[2 * pick]; samp[2 * n_acc + 1] = tried[2 * pick + 1]; sdist[n_acc] = dtried[pick]; n_acc++;
                 break;
             }
         }
         if (t->fault) break;
     }
-    double out = act[best];
+    out[0] = act[2 * best]; out[1] = act[2 * best + 1];
     if (n_acc > 0) {
         double dm = INFINITY; for (i = 0; i < n_acc; ++i) if (sdist[i] < dm) dm = sdist[i];
         int tt = 0; for (i = 0; i < n_acc; ++i) tt += (sdist[i] == dm);
         int pp = rnd_choice(t, tt);
-        for (i = 0; i < n_acc; ++i) if (sdist[i] == dm) { if (pp-- == 0) { out = samp[i]; break; } }
+        for (i = 0; i < n_acc; ++i) if (sdist[i] == dm) { if (pp-- == 0) { out[0] = samp[2 * i]; out[1] = samp[2 * i + 1]; break; } }
     }
     free(act); free(q); free(samp); free(sdist); free(tried); free(dtried);
-    return out; /* NOTE: a float64 action; the reference keys it by its float64 bytes */
+    /* NOTE: a float64 action; the reference keys it by its float64 bytes */
 }
 
-/* genetic_policy2: utils/action_selection_functions.py:104-136 (one action dimension, float32 Box).
- * p is drawn first on every call; 0/1/2 existing actions get the centre / a random bound / the missing bound;
- * later calls take default_policy with probability 1-epsilon, else the mean of the two LOWEST-q actions
- * (the list is sorted ascending and [0], [1] are used, :108-112). */
-static double genetic2_expand(orc_tree* t, int sidx) {
+/* genetic_policy2: utils/action_selection_functions.py:104-136 (one or two action dimensions; float32 gym boxes,
+ * float64 CurveEnv box).  p is drawn first on every call; 0/1/2 existing actions get the centre / a random bound /
+ * the missing bound; later calls take default_policy with probability 1-epsilon, else the mean of the two LOWEST-q
+ * actions (the list is sorted ascending and [0], [1] are used, :108-112). */
+static void genetic2_expand(orc_tree* t, int sidx, double out[2]) {
     snode* s = &t->S[sidx];
+    const int D = orc_action_dim(t->cfg.env_id);
     const double p = rnd_u01(t);
-    float lowf, highf; action_bounds(t->cfg.env_id, &lowf, &highf);
-    if (s->n_act == 0) { float m = (lowf + highf) / 2.0f; return (double)m; }          /* np.mean([low, high]) in float32 */
+    double lo[2], hi[2];
+    const int f32 = box_bounds(t, lo, hi);
+    out[0] = out[1] = 0.0;
+    if (s->n_act == 0) {                                                               /* np.mean([low, high], axis=0) */
+        for (int d = 0; d < D; ++d) out[d] = f32 ? (double)(((float)lo[d] + (float)hi[d]) / 2.0f) : (lo[d] + hi[d]) / 2.0;
+        return;
+    }
     if (s->n_act == 1) {
         double w[2] = {1.0, 1.0};
-        return rnd_choices(t, w, 2) == 0 ? (double)highf : (double)lowf;                /* random.choices([high, low]) */
+        const int pick_high = rnd_choices(t, w, 2) == 0;                               /* random.choices([high, low]) */
+        for (int d = 0; d < D; ++d) out[d] = pick_high ? hi[d] : lo[d];
+        return;
     }
-    if (s->n_act == 2) { double hv[2] = {(double)highf, 0.0}; return find_action_bits(t, sidx, hv) >= 0 ? (double)lowf : (double)highf; }
-    if (p < 1 - t->cfg.epsilon) { double d[2]; rnd_action(t, &t->tree_stream, d); return d[0]; }
+    if (s->n_act == 2) {
+        const int has_high = find_action_bits(t, sidx, hi) >= 0;
+        for (int d = 0; d < D; ++d) out[d] = has_high ? lo[d] : hi[d];
+        return;
+    }
+    if (p < 1 - t->cfg.epsilon) { rnd_action(t, &t->tree_stream, out); return; }
     /* stable ascending sort by q: the first two entries */
     int b0 = -1, b1 = -1; double q0 = INFINITY, q1 = INFINITY;
     for (int a = s->first_act; a >= 0; a = t->A[a].next_act) {
@@ -546,9 +576,10 @@ static double genetic2_expand(orc_tree* t, int sidx) {
         if (q < q0) { b1 = b0; q1 = q0; b0 = a; q0 = q; }
         else if (q < q1) { b1 = a; q1 = q; }
     }
-    float x = (float)t->A[b0].value[0], y = (float)t->A[b1].value[0];
-    float m = (x + y) / 2.0f;                                                           /* np.mean([best, second], axis=0) */
-    return (double)m;
+    for (int d = 0; d < D; ++d) {                                                      /* np.mean([best, second], axis=0) */
+        if (f32) { float x = (float)t->A[b0].value[d], y = (float)t->A[b1].value[d]; out[d] = (double)((x + y) / 2.0f); }
+        else out[d] = (t->A[b0].value[d] + t->A[b1].value[d]) / 2.0;
+    }
 }
 
 static double state_visit(orc_tree* t, int sidx, int level);
@@ -667,8 +698,8 @@ static double state_visit(orc_tree* t, int sidx, int level) {
         double cap = ceil(c->k1 * pow((double)s->ns, c->alpha1));
         if (s->n_act == 0 || (double)s->n_act <= cap) {
             double a[2] = {0.0, 0.0};
-            if (c->agent == ORC_AGENT_APW && c->expansion == ORC_EXPAND_VOO) a[0] = voo_expand(t, sidx);
-            else if (c->agent == ORC_AGENT_APW && c->expansion == ORC_EXPAND_GENETIC2) a[0] = genetic2_expand(t, sidx);
+            if (c->agent == ORC_AGENT_APW && c->expansion == ORC_EXPAND_VOO) voo_expand(t, sidx, a);
+            else if (c->agent == ORC_AGENT_APW && c->expansion == ORC_EXPAND_GENETIC2) genetic2_expand(t, sidx, a);
             else rnd_action(t, &t->tree_stream, a); /* dpw ignores --ae: always action_space.sample() */
             int old = find_action_bits(t, sidx, a);
             if (c->agent == ORC_AGENT_APW) {

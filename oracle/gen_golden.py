@@ -58,6 +58,13 @@ SCENARIOS = {
     # APW on the continuous 2-D action box, after two real steps so that the hidden step counter is > 0
     "apw_curve": dict(agent="MctsApw", env="CurveEnv", n_sim=250, C=11.0, gamma=0.99, max_depth=50, alpha=0.5, k=3,
                       budget="zero", env_seed=0, rng_seed=14, pre_steps=[[-5.0, -30.0], [-5.0, -30.0], [-4.0, -25.0]]),
+    # examples/example_curve.py:32-45 runs APW + voo on CurveEnv (C=11.837, gamma=0.4, 100 voo samples): 2-D Voronoi sampling
+    "apw_voo_curve": dict(agent="MctsApw", env="CurveEnv", n_sim=200, C=11.837, gamma=0.4, max_depth=50, alpha=0.3, k=4,
+                          budget="zero", env_seed=0, rng_seed=16, pre_steps=[[-5.0, -30.0], [-5.0, -30.0], [-4.0, -25.0]],
+                          expansion="voo", epsilon=0.5, voo_n_samples=12, voo_max_try=40),
+    "apw_genetic2_curve": dict(agent="MctsApw", env="CurveEnv", n_sim=220, C=11.0, gamma=0.9, max_depth=50, alpha=0.45, k=3,
+                               budget="zero", env_seed=0, rng_seed=17, pre_steps=[[-5.0, -30.0], [-5.0, -30.0], [-4.0, -25.0]],
+                               expansion="genetic2", epsilon=0.5),
     # vanilla MctsHash on DiscreteCurveEnv([5 accelerations, 7 angles]) (sweep_vanilla.py:177), real rollouts
     "hash_curve_discrete": dict(agent="MctsHash", env="DiscreteCurveEnv", n_sim=300, C=5.0, gamma=0.95, max_depth=12,
                                 budget="to_max_depth", env_seed=0, rng_seed=15, grid=[5, 7], pre_steps=[0, 0, 0]),
