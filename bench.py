@@ -357,6 +357,37 @@ def other_configs(dev):
     t = timeit(lambda: eng.set_roots(roots).run(10000), reps=2)
     c = eng.counters()
     out["c4_dpw_mountaincar_1tree"] = {"sims_per_s": 10000 / t, "env_steps_per_s": c["env_steps"] / t, "ms": t * 1e3}
+    # CurveEnv (the env sweep.py / sweep_vanilla.py / examples/example_curve.py of the reference actually run), from an
+    # on-track pose (three braking right turns after reset): APW random expansion, APW + voo as in example_curve.py:32-45,
+    # vanilla MctsHash on DiscreteCurveEnv([5, 19]) (sweep_vanilla.py:177 defaults) as one tree and as 4096 trees
+    pose = torch.tensor([[-5.70993649, 25.49759526, 2.5, 0.0, 3.0]], dtype=torch.float64)
+    eng = Engine(_lib.ENV_CURVE, agent=_lib.AGENT_APW, n_trees=1, sim_capacity=1000, max_depth=500, C_=11.0, gamma=0.95, alpha1=0.5,
+                 k1=3.0, kernel=_lib.KERNEL_CTA_PER_TREE, rollouts_per_leaf=32, seed=1, device=dev)
+    t = timeit(lambda: eng.set_roots(pose).run(1000))
+    c = eng.counters()
+    out["curve_apw_1tree_32rollouts"] = {"sims_per_s": 1000 / t, "env_steps_per_s": c["env_steps"] / t, "ms": t * 1e3}
+    eng = Engine(_lib.ENV_CURVE, agent=_lib.AGENT_APW, n_trees=1, sim_capacity=100, max_depth=500, C_=11.837, gamma=0.4, alpha1=0.0,
+                 k1=95.0, expansion=_lib.EXPAND_VOO, epsilon=0.5, voo_n_samples=100, voo_max_try=1000,
+                 kernel=_lib.KERNEL_CTA_PER_TREE, seed=1, device=dev)
+    t = timeit(lambda: eng.set_roots(pose).run(100))
+    out["curve_apw_voo_example_curve_py"] = {"sims_per_s": 100 / t, "ms": t * 1e3}
+    for name, nt in (("curve_vanilla_5x19_1tree", 1), ("curve_vanilla_5x19_4096trees", 4096)):
+        eng = Engine(_lib.ENV_CURVE, agent=_lib.AGENT_VANILLA, n_trees=nt, sim_capacity=1000, max_depth=500, C_=11.0, gamma=0.95,
+                     action_grid=(5, 19), kernel=_lib.KERNEL_CTA_PER_TREE, seed=1, device=dev)
+        roots = pose.repeat(nt, 1)
+        t = timeit(lambda: eng.set_roots(roots).run(1000), reps=2)
+        c = eng.counters()
+        out[name] = {"sims_per_s": nt * 1000 / t, "env_steps_per_s": c["env_steps"] / t, "ms": t * 1e3}
+    n = 1 << 21
+    poses = pose.repeat(n, 1)
+    for name, grid in (("rollout_curve_box", None), ("rollout_curve_grid_5x19", (5, 19))):
+        steps = []
+        def run_curve():
+            ret, st = E.rollout(_lib.ENV_CURVE, poses, budget=500, gamma=0.95, seed=1234, sim=0, device=dev, action_grid=grid)
+            steps.append(st)
+        t = timeit(run_curve, reps=3)
+        total = int(steps[-1].sum().item())
+        out[name] = {"trajectories": n, "env_steps_per_s": total / t, "mean_len": total / n, "ms": t * 1e3}
     # R: rollout micro-benchmark, 2^24 trajectories from the reset distribution, random policy, budget = max_depth
     flop = {0: 36, 1: 27, 2: 27, 3: 6}
     peak_fp32 = 148 * 128 * 2 * 1.965e9

@@ -104,6 +104,116 @@ __device__ __forceinline__ double warp_max(double x) {
     for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(kFull, x, o));
     return x;
 }
+// ---------------------------------------------------------------- CTA-wide evaluation of voo's rejection tries
+// voo draws uniform samples until one falls into the Voronoi cell of the best action (up to max_try tries, O(children)
+// each).  The tries of one sample are independent given their position in the counter-based tree stream, so in
+// free-running mode every thread of the CTA evaluates one try and the FIRST try (in stream order) that ends the
+// reference's loop wins -- the result and the stream position afterwards are exactly the serial ones.
+struct VooWork {
+    int cmd;            // VOO_EVAL: evaluate a batch of tries; VOO_FIND: locate the closest tried sample; VOO_EXIT: descent over
+    int s, best, base, first;
+    unsigned c0;        // tree-stream words consumed before try 0 of this sample
+    int ties;           // VOO_FIND: number of tries at distance tmin
+    double abest, abest2;
+    unsigned long long tmin_bits;   // smallest distance to the best action over the tries so far (bits of a double >= 0)
+};
+enum : int { VOO_EVAL = 0, VOO_EXIT = 1, VOO_FIND = 2 };
+
+struct RollShared {
+    double leaf[8];
+    int budget, need, exit_flag;
+    unsigned sim;
+    double result;
+    VooWork vw;
+};
+
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Box bounds per action dimension widened to double; gym boxes are float32 (returns true), CurveEnv's box is float64
+template <int ENV>
+__device__ __forceinline__ bool env_box_bounds(double (&lo)[2], double (&hi)[2]) {
+    if constexpr (ENV == ENV_CURVE) { lo[0] = -5.0; hi[0] = 5.0; lo[1] = -30.0; hi[1] = 30.0; return false; }
+    float lof, hif; env_action_bounds(ENV, lof, hif);
+    lo[0] = (double)lof; hi[0] = (double)hif; lo[1] = hi[1] = 0.0;
+    return true;
+}
+
+// word w of a tree stream (random access: the stream is counter based)
+__device__ __forceinline__ uint32_t tree_stream_word(unsigned long long seed, uint32_t tree_id, uint32_t w) {
+    uint32_t buf[4];
+    philox4x32_10(w >> 2, 0u, tree_id, kStreamTree, (uint32_t)seed, (uint32_t)(seed >> 32), buf);
+    const uint32_t r = w & 3u;
+    return r == 0 ? buf[0] : r == 1 ? buf[1] : r == 2 ? buf[2] : buf[3];
+}
+// np.random.uniform(low, high, shape) of try j of the sample whose tries start at stream word c0
+template <int ENV>
+__device__ __forceinline__ void voo_sample_at(const CtaParams& p, uint32_t tree_id, unsigned c0, int j, double& x, double& x2) {
+    double lo[2], hi[2];
+    env_box_bounds<ENV>(lo, hi);
+    const uint32_t w = c0 + (uint32_t)j * (uint32_t)p.action_dim;
+    x = __dadd_rn(lo[0], __dmul_rn(__dsub_rn(hi[0], lo[0]), u32_to_d01(tree_stream_word(p.seed, tree_id, w))));
+    x2 = p.action_dim == 2 ? __dadd_rn(lo[1], __dmul_rn(__dsub_rn(hi[1], lo[1]), u32_to_d01(tree_stream_word(p.seed, tree_id, w + 1)))) : 0.0;
+}
+// try j = w.base + tid: does it end the loop of :160-190 (coincides with the best action, or is at least as close to
+// it as to every other action)?  Distances like scipy's cdist: |d| in one dimension, sqrt(d0^2 + d1^2) in two -- the
+// square roots are only taken when the squared distances are too close to order them safely.
+template <int ENV>
+__device__ __forceinline__ void voo_eval_tries(const CtaParams& p, const Pool& q, VooWork& w, uint32_t tree_id, int tid) {
+    const int j = w.base + tid;
+    const bool live = j < p.voo_max_try;
+    double x = 0.0, x2 = 0.0;
+    if (live) voo_sample_at<ENV>(p, tree_id, w.c0, j, x, x2);
+    {   // closest tried sample so far (needed only if all max_try tries fail): one shared atomic per warp
+        const double d0 = __dsub_rn(x, w.abest), d1 = __dsub_rn(x2, w.abest2);
+        double db = p.action_dim != 2 ? fabs(d0) : __dsqrt_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)));
+        if (!live) db = INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) db = fmin(db, __shfl_xor_sync(kFull, db, o));
+        if ((tid & 31) == 0) atomicMin(&w.tmin_bits, (unsigned long long)__double_as_longlong(db));
+    }
+    if (!live || j > *(volatile int*)&w.first) return;
+    const int off = q.s_coff[w.s], n = q.s_ccnt[w.s];
+    bool stop = true;
+    if (p.action_dim != 2) {
+        const double db = fabs(__dsub_rn(x, w.abest));
+        if (db != 0.0) {
+            for (int i = 0; i < n; ++i) {
+                if (i == w.best) continue;
+                if (!(db <= fabs(__dsub_rn(x, q.a_value[q.ipool[off + i]])))) { stop = false; break; }
+            }
+        }
+    } else {
+        const double d0 = __dsub_rn(x, w.abest), d1 = __dsub_rn(x2, w.abest2);
+        const double sb = __dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1));
+        if (sb != 0.0) {
+            const double db = __dsqrt_rn(sb);
+            for (int i = 0; i < n; ++i) {
+                if (i == w.best) continue;
+                const int a = q.ipool[off + i];
+                const double e0 = __dsub_rn(x, q.a_value[a]), e1 = __dsub_rn(x2, q.a_value2[a]);
+                const double si = __dadd_rn(__dmul_rn(e0, e0), __dmul_rn(e1, e1));
+                if (sb <= si) continue;                                   // sqrt is monotone: db <= d_i
+                if (sb > si * (1.0 + 1e-15) || !(db <= __dsqrt_rn(si))) { stop = false; break; }
+            }
+        }
+    }
+    if (stop) atomicMin(&w.first, j);
+}
+// all max_try tries failed: which tries lie at distance tmin from the best action (thread tid looks at tries tid, tid+nt, ..)
+template <int ENV>
+__device__ __forceinline__ void voo_find_closest(const CtaParams& p, VooWork& w, uint32_t tree_id, int tid, int nt) {
+    const double tmin = __longlong_as_double((long long)w.tmin_bits);
+    for (int j = tid; j < p.voo_max_try; j += nt) {
+        double x, x2;
+        voo_sample_at<ENV>(p, tree_id, w.c0, j, x, x2);
+        const double d0 = __dsub_rn(x, w.abest), d1 = __dsub_rn(x2, w.abest2);
+        const double db = p.action_dim != 2 ? fabs(d0) : __dsqrt_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)));
+        if (db == tmin) { atomicAdd(&w.ties, 1); atomicMin(&w.first, j); }
+    }
+}
+
 template <int ENV, typename T, bool SCRIPTED>
 struct Search {
     static constexpr int S = EnvTraits<ENV>::S;
@@ -335,12 +445,7 @@ struct Search {
     }
 
     // Box bounds per action dimension widened to double; gym boxes are float32, CurveEnv's box is float64
-    __device__ __forceinline__ bool box_bounds(double (&lo)[2], double (&hi)[2]) const {
-        if constexpr (ENV == ENV_CURVE) { lo[0] = -5.0; hi[0] = 5.0; lo[1] = -30.0; hi[1] = 30.0; return false; }
-        float lof, hif; env_action_bounds(ENV, lof, hif);
-        lo[0] = (double)lof; hi[0] = (double)hif; lo[1] = hi[1] = 0.0;
-        return true;
-    }
+    __device__ __forceinline__ bool box_bounds(double (&lo)[2], double (&hi)[2]) const { return env_box_bounds<ENV>(lo, hi); }
     __device__ __forceinline__ double act2(int a) const { return p.action_dim == 2 ? q.a_value2[a] : 0.0; }
     // scipy cdist(..., 'euclidean') on float64 rows: sqrt(sum (u_i - v_i)^2); one dimension: |d|
     __device__ __forceinline__ double euclid(double x0, double x1, double y0, double y1) const {
@@ -402,7 +507,7 @@ struct Search {
 
     // voo (utils/action_selection_functions.py:139-205), one or two action dimensions.  `scratch` (the CTA's rollout
     // reduction buffer, idle during the descent) holds the accepted samples: 3 doubles each.
-    __device__ double voo_expand(int s, double& out2, double* scratch) {
+    __device__ double voo_expand(int s, double& out2, double* scratch, RollShared* sh, int nt) {
         const double pr = u01();
         const int off = q.s_coff[s], n = q.s_ccnt[s];
         out2 = 0.0;
@@ -431,7 +536,63 @@ struct Search {
         box_bounds(lo, hi);
         int n_acc = 0;
         const int n_samples = p.voo_n;
-        for (int k = 0; k < n_samples && !tc.fault; ++k) {
+        if constexpr (!SCRIPTED) {
+            const int D = p.action_dim;
+            for (int k = 0; k < n_samples; ++k) {
+                const unsigned c0 = ts.consumed();
+                int first = 0x7fffffff;
+                for (int base = 0; base < p.voo_max_try && first == 0x7fffffff; base += nt) {
+                    if (lane == 0) {
+                        VooWork& w = sh->vw;
+                        w.cmd = VOO_EVAL; w.s = s; w.best = best; w.base = base; w.first = 0x7fffffff; w.c0 = c0;
+                        w.abest = abest; w.abest2 = abest2;
+                        if (base == 0) w.tmin_bits = 0x7ff0000000000000ull;   // +inf
+                    }
+                    __syncwarp();
+                    bar_sync(1, nt);                                  // the helper warps wait here during the descent
+                    voo_eval_tries<ENV>(p, q, sh->vw, tree_id, lane);
+                    bar_sync(2, nt);
+                    first = *(volatile int*)&sh->vw.first;
+                }
+                double x, x2, d;
+                if (first != 0x7fffffff) {
+                    voo_sample_at<ENV>(p, tree_id, c0, first, x, x2);
+                    d = euclid(x, x2, abest, abest2);
+                    ts.resume(p.seed, 0u, tree_id, kStreamTree, c0 + (unsigned)(first + 1) * (unsigned)D);
+                    if (d == 0.0) continue;                           // :177-178 leaves the loop WITHOUT appending
+                } else {
+                    // max_try tries failed (:186-190): the closest tried sample, ties broken by a draw
+                    ts.resume(p.seed, 0u, tree_id, kStreamTree, c0 + (unsigned)p.voo_max_try * (unsigned)D);
+                    auto dist_of = [&](int j) -> double {
+                        if (j >= p.voo_max_try) return INFINITY;
+                        double y, y2; voo_sample_at<ENV>(p, tree_id, c0, j, y, y2);
+                        return euclid(y, y2, abest, abest2);
+                    };
+                    if (lane == 0) { sh->vw.cmd = VOO_FIND; sh->vw.first = 0x7fffffff; sh->vw.ties = 0; }
+                    __syncwarp();
+                    bar_sync(1, nt);
+                    voo_find_closest<ENV>(p, sh->vw, tree_id, lane, nt);
+                    bar_sync(2, nt);
+                    const double tmin = __longlong_as_double((long long)sh->vw.tmin_bits);
+                    const int tt = *(volatile int*)&sh->vw.ties;
+                    int pp = choice(tt), pick = *(volatile int*)&sh->vw.first;
+                    if (pp > 0) {   // several tries at exactly the same distance: the pp-th in stream order
+                        int seen2 = 0;
+                        for (int b0 = 0; b0 < p.voo_max_try; b0 += 32) {
+                            const unsigned bm = __ballot_sync(kFull, dist_of(b0 + lane) == tmin);
+                            const int c = __popc(bm);
+                            if (pp < seen2 + c) { unsigned bb = bm; for (int z = 0; z < pp - seen2; ++z) bb &= bb - 1; pick = b0 + __ffs(bb) - 1; break; }
+                            seen2 += c;
+                        }
+                    }
+                    voo_sample_at<ENV>(p, tree_id, c0, pick, x, x2);
+                    d = tmin;
+                }
+                if (lane == 0) { scratch[3 * n_acc] = x; scratch[3 * n_acc + 1] = x2; scratch[3 * n_acc + 2] = d; }
+                ++n_acc;
+            }
+        }
+        for (int k = 0; SCRIPTED && k < n_samples && !tc.fault; ++k) {
             int n_try = 0;
             double tmin = INFINITY; int tmin_ties = 0;  // closest tried sample (max_try fallback)
             // the fallback needs the pos-th closest-tried sample: replay it from a saved stream position
@@ -488,13 +649,6 @@ struct Search {
         __syncwarp();
         return out;
     }
-};
-
-struct RollShared {
-    double leaf[8];
-    int budget, need, exit_flag;
-    unsigned sim;
-    double result;
 };
 
 template <int ENV, typename T, bool SCRIPTED>
@@ -599,7 +753,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                     const double cap = ns_now < p.ln_count ? p.pw1_table[ns_now] : ceil(__dmul_rn(p.k1, pow((double)ns_now, p.alpha1)));
                     if (n_act == 0 || (double)n_act <= cap) {
                         double val, val2 = 0.0;
-                        if (p.agent == ISLA_AGENT_APW && p.expansion == ISLA_EXPAND_VOO) val = ctx.voo_expand(s, val2, red);
+                        if (p.agent == ISLA_AGENT_APW && p.expansion == ISLA_EXPAND_VOO) val = ctx.voo_expand(s, val2, red, &sh, nt);
                         else if (p.agent == ISLA_AGENT_APW && p.expansion == ISLA_EXPAND_GENETIC2) val = ctx.genetic2_expand(s, val2);
                         else val = ctx.tree_action(val2);  // dpw ignores --ae (mcts_double_...:57)
                         const int old = ctx.find_action(s, val, val2);
@@ -705,7 +859,21 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
         } else if (leader && lane == 0) {
             sh.need = 0;
         }
-        __syncthreads();
+        // end of the descent.  Until then the other warps serve voo's try batches (barrier 1 = work posted or descent
+        // over, barrier 2 = batch evaluated); the last barrier-1 also publishes sh.need / sh.leaf / sh.budget.
+        if (leader) {
+            if (lane == 0) sh.vw.cmd = VOO_EXIT;
+            __syncwarp();
+            bar_sync(1, nt);
+        } else {
+            for (;;) {
+                bar_sync(1, nt);
+                if (sh.vw.cmd == VOO_EXIT) break;
+                if (sh.vw.cmd == VOO_FIND) voo_find_closest<ENV>(p, sh.vw, tree_id, tid, nt);
+                else voo_eval_tries<ENV>(p, ctx.q, sh.vw, tree_id, tid);
+                bar_sync(2, nt);
+            }
+        }
 
         // ------------------------------------------------------------ all threads: R rollouts from the leaf
         if (sh.need) {
@@ -984,6 +1152,7 @@ int pick_threads(const isla_config& cfg) {
         const int R = cfg.rollouts_per_leaf > 0 ? cfg.rollouts_per_leaf : 1;
         nt = 32;
         while (nt < R && nt < 512) nt <<= 1;
+        if (cfg.expansion == ISLA_EXPAND_VOO) nt = 512;   // voo's rejection tries are evaluated CTA-wide
     }
     nt = (nt + 31) / 32 * 32;
     return nt > 512 ? 512 : nt;

@@ -136,6 +136,27 @@ def test_result_independent_of_cta_size_and_equal_to_thread_per_tree():
     assert_tree_equal(a.export_tree(7), {"tree_" + k: v for k, v in b.export_tree(7).items()}, rtol=1e-12, atol=1e-12)
 
 
+def test_voo_tries_evaluated_cta_wide_do_not_depend_on_cta_size():
+    """voo's rejection tries run one per thread; the first one in stream order wins, so 32 / 256 / 512 threads per tree
+    (and max_try small enough to hit the closest-tried fallback) must build identical trees."""
+    from islamcts_b200.engine import Engine
+    for env_id, root in ((1, coracle.env_reset(1, 5, 0)), (4, np.array([-5.70993649, 25.49759526, 2.5, 0.0, 3.0]))):
+        out = []
+        for nt in (32, 256, 512):
+            e = Engine(env_id, agent=1, n_trees=3, sim_capacity=150, max_depth=12, C_=3.0, gamma=0.9, alpha1=0.4, k1=3.0,
+                       expansion=1, epsilon=0.3, voo_n_samples=9, voo_max_try=7, precision=1, kernel=2, block_threads=nt, seed=8)
+            e.set_roots(np.tile(root[None, :], (3, 1))).run(150)
+            assert e.counters()["faults"] == 0
+            out.append(e.export_tree(2))
+        for o in out[1:]:
+            for k in out[0]:
+                np.testing.assert_array_equal(o[k], out[0][k])
+        t = coracle.Tree(coracle.make_config(env_id, agent=1, max_depth=12, C_=3.0, gamma=0.9, alpha1=0.4, k1=3.0, expansion=1,
+                                             epsilon=0.3, voo_n_samples=9, voo_max_try=7, seed=8, tree_id=2), root)
+        t.run(150)
+        assert_tree_equal(out[0], {"tree_" + k: v for k, v in t.serialise().items()}, rtol=1e-9, atol=1e-9)
+
+
 def test_c2_shape_leaf_parallel_4096_matches_oracle():
     """BASELINE C2: one CartPole tree, nsim=1000, max_depth=500, gamma=0.99, 4096 rollouts per leaf."""
     from islamcts_b200.engine import Engine
