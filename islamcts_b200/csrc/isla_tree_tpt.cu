@@ -89,6 +89,23 @@ template <int A> __device__ __forceinline__ uint32_t* link_ptr(char* base, int b
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void cp_async16(void* smem, const void* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// shared-memory ring of the cooperative phase, per warp: kSlots slots of {own 32 x 16 B | siblings 32 x sizeof(PvSib) |
+// pending return 32 x 8 B}; the producer runs kAhead = kSlots - 1 tasks in front of the consumer
+template <int A> struct CoopRing {
+    static constexpr int kSlots = A == 2 ? 6 : 3;
+    static constexpr int kAhead = kSlots - 1;
+    static constexpr int kSlotBytes = 32 * 16 + 32 * (A * 12 - 8) + 32 * 8;   // sizeof(PvSib<A>) = 12 A - 8
+    static constexpr int kWarpBytes = kSlots * kSlotBytes;
+};
 
 enum : int { MODE_DESCEND = 0, MODE_EXPAND = 1, MODE_RETURN = 2, MODE_IDLE = 3 };
 constexpr int kCoopMin = 16;  // deepest cached path in the warp below which phase 1a is skipped
@@ -164,6 +181,8 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
     }
     const double* const ln_table = p.ln_in_smem ? ln_smem : p.ln_table;
     const int lane = threadIdx.x & 31;
+    constexpr int kSlots = CoopRing<A>::kSlots, kAhead = CoopRing<A>::kAhead, kSlotBytes = CoopRing<A>::kSlotBytes;
+    char* const coop_ring = reinterpret_cast<char*>(ln_smem) + (p.ln_in_smem ? ((p.ln_count * 8 + 15) & ~15) : 0);
 
     // scripted (parity) mode drives ONE tree from lane 0 of a single warp; the other lanes are dummies
     const long long tree = SCRIPTED ? (threadIdx.x == 0 ? p.scripted_tree : p.n_trees)
@@ -283,97 +302,154 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
         if (SCRIPTED || warp_max_plen < kCoopMin) {
             if (live && plen > 0) write_back(0);
         } else {
+            // The rounds of all 32 trees form ONE sequence of tasks (tree j, levels l0..l0+31).  A producer cursor runs
+            // kAhead tasks in front of the consumer and copies each lane's entries (own 16 B, siblings, pending return)
+            // into a per-warp shared-memory ring with cp.async: the L2/HBM latency of a round is overlapped with the
+            // evaluation of the kAhead rounds before it, across tree boundaries.  Every lane reads back only what it
+            // copied itself, so cp.async.wait_group is the only synchronisation.
             const int my_plen = (live && pend) ? plen : 0;
-            for (int j = 0; j < 32; ++j) {
+            const unsigned work = __ballot_sync(kFull, my_plen > 0);
+            char* const ring = coop_ring + (threadIdx.x >> 5) * (kSlots * kSlotBytes);
+            int pj = work ? __ffs(work) - 1 : 32, pl0 = 0;
+            int pL = pj < 32 ? __shfl_sync(kFull, my_plen, pj & 31) : 0;
+            int issued = 0, consumed = 0;
+            auto issue_one = [&]() {
+                if (pj < 32) {
+                    const int l = pl0 + lane;
+                    if (l < pL && issued >= consumed) {   // tasks dropped after an event are stepped over, not copied
+                        const long long row = (warp_tree0 + pj) * path_cap + l;
+                        char* const slot = ring + (issued % kSlots) * kSlotBytes;
+                        cp_async16(slot + lane * 16, p.pv_own + row * 16);
+#pragma unroll
+                        for (int q = 0; q < (int)(kSibBytes / 16); ++q)
+                            cp_async16(slot + 512 + lane * kSibBytes + q * 16, p.pv_sib + row * kSibBytes + q * 16);
+                        cp_async8(slot + 512 + 32 * kSibBytes + lane * 8, p.path_g + row);
+                    }
+                    pl0 += 32;
+                    if (pl0 >= pL) {
+                        const unsigned rest = pj >= 31 ? 0u : (work & (kFull << (pj + 1)));
+                        pj = rest ? __ffs(rest) - 1 : 32;
+                        pl0 = 0;
+                        pL = pj < 32 ? __shfl_sync(kFull, my_plen, pj & 31) : 0;
+                    }
+                }
+                cp_async_commit();   // one group per task (an empty one once the sequence is exhausted)
+                ++issued;
+            };
+            for (unsigned todo = work; todo; todo &= todo - 1) {
+                const int j = __ffs(todo) - 1;
                 const int Lj = __shfl_sync(kFull, my_plen, j);
-                const int Ln = __shfl_sync(kFull, my_plen, (j + 1) & 31) * (j < 31);
                 const long long tj = warp_tree0 + j;
-                if (Ln > 0 && !(p.tuning & 8)) {
-                    // the next tree's rows (consecutive bytes) are requested while this tree is verified
-                    const char* on = p.pv_own + (tj + 1) * path_cap * 16;
-                    const char* sn = p.pv_sib + (tj + 1) * path_cap * kSibBytes;
-                    const double* gn = p.path_g + (tj + 1) * path_cap;
-                    for (int l = lane * 8; l < Ln; l += 256) {  // one 128-byte line of each row per lane and pass
-                        prefetch_l2(on + (long long)l * 16);
-                        prefetch_l2(sn + (long long)l * kSibBytes);
-                        if (kSibBytes > 16) { prefetch_l2(sn + (long long)l * kSibBytes + 128); prefetch_l2(sn + (long long)l * kSibBytes + 256); }
-                        if ((lane & 1) == 0) prefetch_l2(gn + l);
+                {
+                    const unsigned nxt = todo & (todo - 1);
+                    if (nxt && !(p.tuning & 8)) {
+                        // the next tree's rows (consecutive bytes) are requested from HBM while this tree is verified
+                        const int jn = __ffs(nxt) - 1;
+                        const int Ln = __shfl_sync(kFull, my_plen, jn);
+                        const char* on = p.pv_own + (warp_tree0 + jn) * path_cap * 16;
+                        const char* sn = p.pv_sib + (warp_tree0 + jn) * path_cap * kSibBytes;
+                        const double* gn = p.path_g + (warp_tree0 + jn) * path_cap;
+                        for (int l = lane * 8; l < Ln; l += 256) {  // one 128-byte line of each row per lane and pass
+                            prefetch_l2(on + (long long)l * 16);
+                            prefetch_l2(sn + (long long)l * kSibBytes);
+                            if (kSibBytes > 16) { prefetch_l2(sn + (long long)l * kSibBytes + 128); prefetch_l2(sn + (long long)l * kSibBytes + 256); }
+                            if ((lane & 1) == 0) prefetch_l2(gn + l);
+                        }
                     }
                 }
-                if (Lj > 0) {
-                    char* const bj = p.blocks + tj * p.slots_per_tree * 16;
-                    char* const oj = p.pv_own + tj * path_cap * 16;
-                    const char* sj = p.pv_sib + tj * path_cap * kSibBytes;
-                    const double* gj = p.path_g + tj * path_cap;
-                    int event = -1, done_upto = 0;
-                    double new_total = 0.0; int new_na = 0; uint32_t edge = 0u;
-                    // rounds are double-buffered: the entries of round r+1 are in flight while round r is evaluated
-                    PvOwn o_nx; PvSib<A> s_nx; double g_nx = 0.0;
-                    o_nx.total = 0.0; o_nx.na = 0; s_nx.edge = 0u;
-#pragma unroll
-                    for (int q = 0; q < A - 1; ++q) { s_nx.na[q] = 0; s_nx.total[q] = 0.0; }
-                    if (lane < Lj) { o_nx = load_own(oj, lane); s_nx = load_sib<A>(sj, lane); g_nx = __ldcg(gj + lane); }
-                    for (int l0 = 0; l0 < Lj && event < 0; l0 += 32) {
-                        const int l = l0 + lane;
-                        const bool act = l < Lj;
-                        const PvOwn o = o_nx; const PvSib<A> sb = s_nx; const double pg = g_nx;
-                        if (l + 32 < Lj) { o_nx = load_own(oj, l + 32); s_nx = load_sib<A>(sj, l + 32); g_nx = __ldcg(gj + l + 32); }
-                        bool my_event = false;
-                        if (act) {
-                            edge = sb.edge;
-                            const int pa = (int)(edge & 3u);
-                            new_total = __dadd_rn(o.total, pg);   // lazy backup: the return of the previous simulation
-                            new_na = o.na + 1;
-                            NodeBlock<A> c;
-                            int k = 0;
-#pragma unroll
-                            for (int a = 0; a < A; ++a) {
-                                c.link[a] = 0u;
-                                if (a == pa) { c.total[a] = new_total; c.na[a] = new_na; }
-                                else {
-                                    // siblings are stored in ascending action order
-                                    double st_ = sb.total[0]; int sn_ = sb.na[0];
-#pragma unroll
-                                    for (int q = 1; q < A - 1; ++q) if (q == k) { st_ = sb.total[q]; sn_ = sb.na[q]; }
-                                    c.total[a] = st_; c.na[a] = sn_; ++k;
-                                }
+                char* const bj = p.blocks + tj * p.slots_per_tree * 16;
+                char* const oj = p.pv_own + tj * path_cap * 16;
+                const char* sj = p.pv_sib + tj * path_cap * kSibBytes;
+                const double* gj = p.path_g + tj * path_cap;
+                int event = -1, done_upto = 0;
+                double new_total = 0.0; int new_na = 0; uint32_t edge = 0u;
+                const int rounds = (Lj + 31) >> 5;
+                int rnd = 0;
+                for (int l0 = 0; l0 < Lj && event < 0; l0 += 32, ++rnd) {
+                    const int l = l0 + lane;
+                    const bool act = l < Lj;
+                    while (issued < consumed + kAhead) issue_one();
+                    cp_async_wait<kAhead - 1>();
+                    const char* const slot = ring + (consumed % kSlots) * kSlotBytes;
+                    ++consumed;
+                    bool my_event = false;
+                    if (act) {
+                        PvOwn o; PvSib<A> sb;
+                        {
+                            const int4 v = *reinterpret_cast<const int4*>(slot + lane * 16);
+                            o.total = __hiloint2double(v.y, v.x); o.na = v.z;
+                            const int4* sp = reinterpret_cast<const int4*>(slot + 512 + lane * kSibBytes);
+                            if constexpr (A == 2) {
+                                const int4 w = sp[0];
+                                sb.edge = (uint32_t)w.x; sb.na[0] = w.y; sb.total[0] = __hiloint2double(w.w, w.z);
+                            } else {
+                                const int4 v0 = sp[0], v1 = sp[1], v2 = sp[2];
+                                sb.edge = (uint32_t)v0.x; sb.na[0] = v0.y; sb.na[1] = v0.z; sb.na[2] = v0.w;
+                                sb.total[0] = __hiloint2double(v1.y, v1.x); sb.total[1] = __hiloint2double(v1.w, v1.z);
+                                sb.total[2] = __hiloint2double(v2.y, v2.x);
                             }
-                            int nun = 0;
-#pragma unroll
-                            for (int a = 0; a < A; ++a) nun += (c.na[a] == 0);
-                            int a_sel = -1;
-                            double sc[A], best;
-                            const int ties = nun > 0 ? 2 : ucb(c, l > 0, a_sel, sc, best);
-                            my_event = (ties != 1) || (a_sel != pa);
                         }
-                        const unsigned ev = __ballot_sync(kFull, my_event);
-                        if (ev) event = l0 + __ffs(ev) - 1;
-                        if (act) {
-                            // levels before the event stay cached (with the return added); the event level and
-                            // everything deeper leave the cache: their statistics go back to the node blocks.
-                            // Without an event the LAST level is handed over too (phase 1b re-decides it on its block).
-                            const bool leaves = (event >= 0 && l >= event) || (event < 0 && l == Lj - 1);
-                            if (!leaves) store_own(oj, l, new_total, new_na);
+                        const double pg = *reinterpret_cast<const double*>(slot + 512 + 32 * kSibBytes + lane * 8);
+                        edge = sb.edge;
+                        const int pa = (int)(edge & 3u);
+                        new_total = __dadd_rn(o.total, pg);   // lazy backup: the return of the previous simulation
+                        new_na = o.na + 1;
+                        NodeBlock<A> c;
+                        int k = 0;
+#pragma unroll
+                        for (int a = 0; a < A; ++a) {
+                            c.link[a] = 0u;
+                            if (a == pa) { c.total[a] = new_total; c.na[a] = new_na; }
                             else {
-                                __stcg(total_ptr<A>(bj, (int)(edge >> 2), (int)(edge & 3u)), new_total);
-                                __stcg(na_ptr<A>(bj, (int)(edge >> 2), (int)(edge & 3u)), new_na);
+                                // siblings are stored in ascending action order
+                                double st_ = sb.total[0]; int sn_ = sb.na[0];
+#pragma unroll
+                                for (int q = 1; q < A - 1; ++q) if (q == k) { st_ = sb.total[q]; sn_ = sb.na[q]; }
+                                c.total[a] = st_; c.na[a] = sn_; ++k;
                             }
                         }
-                        done_upto = min(l0 + 32, Lj);
+                        int nun = 0;
+#pragma unroll
+                        for (int a = 0; a < A; ++a) nun += (c.na[a] == 0);
+                        int a_sel = -1;
+                        double sc[A], best;
+                        const int ties = nun > 0 ? 2 : ucb(c, l > 0, a_sel, sc, best);
+                        my_event = (ties != 1) || (a_sel != pa);
                     }
-                    const int r = event >= 0 ? event : Lj - 1;
-                    // levels the verification did not reach leave the cache as well
-                    for (int l = done_upto + lane; l < Lj; l += 32) {
-                        const PvOwn o = load_own(oj, l);
-                        const uint32_t e = load_edge<A>(sj, l);
-                        const double pg = __ldcg(gj + l);
-                        __stcg(total_ptr<A>(bj, (int)(e >> 2), (int)(e & 3u)), __dadd_rn(o.total, pg));
-                        __stcg(na_ptr<A>(bj, (int)(e >> 2), (int)(e & 3u)), o.na + 1);
+                    const unsigned ev = __ballot_sync(kFull, my_event);
+                    if (ev) event = l0 + __ffs(ev) - 1;
+                    if (act) {
+                        // levels before the event stay cached (with the return added); the event level and
+                        // everything deeper leave the cache: their statistics go back to the node blocks.
+                        // Without an event the LAST level is handed over too (phase 1b re-decides it on its block).
+                        const bool leaves = (event >= 0 && l >= event) || (event < 0 && l == Lj - 1);
+                        if (!leaves) store_own(oj, l, new_total, new_na);
+                        else {
+                            __stcg(total_ptr<A>(bj, (int)(edge >> 2), (int)(edge & 3u)), new_total);
+                            __stcg(na_ptr<A>(bj, (int)(edge >> 2), (int)(edge & 3u)), new_na);
+                        }
                     }
-                    __syncwarp();
-                    if (lane == j) { level = r; plen = r; pend = false; }
+                    done_upto = min(l0 + 32, Lj);
                 }
+                if (rnd < rounds) {
+                    // rounds skipped after an event: their tasks are dropped.  Copies already in flight for them are
+                    // drained first, so that no slot ever has two copies outstanding.
+                    cp_async_wait<0>();
+                    consumed += rounds - rnd;
+                }
+                const int r = event >= 0 ? event : Lj - 1;
+                // levels the verification did not reach leave the cache as well
+                for (int l = done_upto + lane; l < Lj; l += 32) {
+                    const PvOwn o = load_own(oj, l);
+                    const uint32_t e = load_edge<A>(sj, l);
+                    const double pg = __ldcg(gj + l);
+                    __stcg(total_ptr<A>(bj, (int)(e >> 2), (int)(e & 3u)), __dadd_rn(o.total, pg));
+                    __stcg(na_ptr<A>(bj, (int)(e >> 2), (int)(e & 3u)), o.na + 1);
+                }
+                __syncwarp();
+                if (lane == j) { level = r; plen = r; pend = false; }
             }
+            cp_async_wait<0>();
         }
 
         // ------------------------------------------------------------------ phase 1b: serial continuation
@@ -642,7 +718,9 @@ __global__ void tpt_best_kernel(const char* blocks, int32_t* meta, long long n_t
 
 template <int ENV, typename T>
 int launch_search(const TptParams& p, bool scripted, cudaStream_t st) {
-    const size_t smem = p.ln_in_smem ? (size_t)p.ln_count * sizeof(double) : 0;
+    constexpr int A = EnvTraits<ENV>::A;
+    const size_t smem = (p.ln_in_smem ? (((size_t)p.ln_count * sizeof(double) + 15) & ~(size_t)15) : 0) +
+                        (size_t)(kTptBlock / 32) * CoopRing<A>::kWarpBytes;
     if (scripted) {
         tpt_search_kernel<ENV, T, true><<<1, 32, smem, st>>>(p);
     } else {
