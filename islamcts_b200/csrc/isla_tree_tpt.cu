@@ -25,7 +25,7 @@
 //   * Visit counts and totals are exact: int32 counts, float64 totals, UCB decisions are the float64 ones (fp32
 //     screening settles only unambiguous arg-maxes), ln(n) and gamma^t come from host libm tables.  Env state and
 //     rollouts live in registers; Philox4x32-10 replaces numpy/gym RNGs.
-// tuning bits (A/B timing only): 1 = no fp32 screening, 8 = no L2 prefetch of the next tree's rows.
+// tuning bits (A/B timing only): 1 = no fp32 screening.
 #include <cmath>
 #include <cstring>
 
@@ -88,20 +88,26 @@ template <int A> __device__ __forceinline__ uint32_t* link_ptr(char* base, int b
     return reinterpret_cast<uint32_t*>(base + (long long)blk * (A * 16) + A * 12) + a;
 }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void cp_async16(void* smem, const void* g) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+// cp.async with the destination given as a 32-bit shared-window address
+__device__ __forceinline__ void cp_async16(unsigned smem, const void* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(g) : "memory");
 }
-__device__ __forceinline__ void cp_async8(void* smem, const void* g) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+__device__ __forceinline__ void cp_async8(unsigned smem, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem), "l"(g) : "memory");
 }
+// MUFU approximations (relative error ~2^-22) for the fp32 screening pass of UCB1; exact float64 decides near-ties
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // shared-memory ring of the cooperative phase, per warp: kSlots slots of {own 32 x 16 B | siblings 32 x sizeof(PvSib) |
 // pending return 32 x 8 B}; the producer runs kAhead = kSlots - 1 tasks in front of the consumer
+#ifndef ISLA_COOP_SLOTS
+#define ISLA_COOP_SLOTS 6
+#endif
 template <int A> struct CoopRing {
-    static constexpr int kSlots = A == 2 ? 6 : 3;
+    static constexpr int kSlots = A == 2 ? ISLA_COOP_SLOTS : 3;
     static constexpr int kAhead = kSlots - 1;
     static constexpr int kSlotBytes = 32 * 16 + 32 * (A * 12 - 8) + 32 * 8;   // sizeof(PvSib<A>) = 12 A - 8
     static constexpr int kWarpBytes = kSlots * kSlotBytes;
@@ -174,15 +180,18 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
     constexpr int A = EnvTraits<ENV>::A;
     constexpr int S = EnvTraits<ENV>::S;
     constexpr double kInterior = Rewards<ENV>::kInterior;
-    extern __shared__ double ln_smem[];  // copy of the host-computed ln(n) table when it fits
+    // dynamic shared memory: [ln(n) rounded to float, for the fp32 screening pass (when it fits)] | cooperative ring.
+    // The float64 table (host libm values) stays in global memory: only near-ties read it.
+    extern __shared__ float lnf_smem[];
+    const int ln_slots = p.ln_in_smem ? ((p.ln_count + 3) & ~3) : 0;
     if (p.ln_in_smem) {
-        for (int i = threadIdx.x; i < p.ln_count; i += blockDim.x) ln_smem[i] = p.ln_table[i];
+        for (int i = threadIdx.x; i < p.ln_count; i += blockDim.x) lnf_smem[i] = (float)p.ln_table[i];
         __syncthreads();
     }
-    const double* const ln_table = p.ln_in_smem ? ln_smem : p.ln_table;
+    const double* const ln_table = p.ln_table;
     const int lane = threadIdx.x & 31;
     constexpr int kSlots = CoopRing<A>::kSlots, kAhead = CoopRing<A>::kAhead, kSlotBytes = CoopRing<A>::kSlotBytes;
-    char* const coop_ring = reinterpret_cast<char*>(ln_smem) + (p.ln_in_smem ? ((p.ln_count * 8 + 15) & ~15) : 0);
+    char* const coop_ring = reinterpret_cast<char*>(lnf_smem) + ln_slots * 4;
 
     // scripted (parity) mode drives ONE tree from lane 0 of a single warp; the other lanes are dummies
     const long long tree = SCRIPTED ? (threadIdx.x == 0 ? p.scripted_tree : p.n_trees)
@@ -233,15 +242,14 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
         int ns = nonroot ? 1 : 0;
 #pragma unroll
         for (int a = 0; a < A; ++a) ns += c.na[a];
-        const double lg = ns < p.ln_count ? ln_table[ns] : ::log((double)ns);
         if (!(p.tuning & 1)) {
-            const float lgf = (float)lg;
+            const float lgf = ns < p.ln_count ? (p.ln_in_smem ? lnf_smem[ns] : (float)ln_table[ns]) : (float)::log((double)ns);
             float sf[A], m1 = -INFINITY, scale = 0.f;
 #pragma unroll
             for (int a = 0; a < A; ++a) {
-                const float naf = (float)c.na[a];
-                const float qf = __fdividef((float)c.total[a], naf);
-                const float ef = Cf * sqrtf(__fdividef(lgf, naf));
+                const float rn = rcp_approx((float)c.na[a]);
+                const float qf = (float)c.total[a] * rn;
+                const float ef = Cf * sqrt_approx(lgf * rn);
                 sf[a] = qf + ef;
                 m1 = fmaxf(m1, sf[a]);
                 scale = fmaxf(scale, fabsf(qf) + fabsf(ef));
@@ -252,6 +260,7 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
             for (int a = 0; a < A; ++a) { if (sf[a] >= thr) { ++ncand; a_sel = a; } }
             if (ncand == 1) return 1;
         }
+        const double lg = ns < p.ln_count ? ln_table[ns] : ::log((double)ns);
         best = -INFINITY;
 #pragma unroll
         for (int a = 0; a < A; ++a) {
@@ -310,53 +319,47 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
             const int my_plen = (live && pend) ? plen : 0;
             const unsigned work = __ballot_sync(kFull, my_plen > 0);
             char* const ring = coop_ring + (threadIdx.x >> 5) * (kSlots * kSlotBytes);
-            int pj = work ? __ffs(work) - 1 : 32, pl0 = 0;
+            // this lane's three entries inside slot 0, as shared-window addresses
+            const unsigned ring_own = (unsigned)__cvta_generic_to_shared(ring) + lane * 16;
+            const unsigned ring_sib = ring_own - lane * 16 + 512 + lane * (unsigned)kSibBytes;
+            const unsigned ring_g = ring_own - lane * 16 + 512 + 32 * (unsigned)kSibBytes + lane * 8;
+            int pj = work ? __ffs(work) - 1 : 32;
             int pL = pj < 32 ? __shfl_sync(kFull, my_plen, pj & 31) : 0;
+            int pl = lane;                      // this lane's level of the next task of tree pj
+            // this lane's entries of that level in the three rows of tree pj
+            const char* p_own = p.pv_own + ((warp_tree0 + (pj & 31)) * path_cap + lane) * 16;
+            const char* p_sib = p.pv_sib + ((warp_tree0 + (pj & 31)) * path_cap + lane) * kSibBytes;
+            const double* p_g = p.path_g + (warp_tree0 + (pj & 31)) * path_cap + lane;
             int issued = 0, consumed = 0;
+            unsigned pslot = 0;                 // byte offset of the producer's slot in the ring
             auto issue_one = [&]() {
                 if (pj < 32) {
-                    const int l = pl0 + lane;
-                    if (l < pL && issued >= consumed) {   // tasks dropped after an event are stepped over, not copied
-                        const long long row = (warp_tree0 + pj) * path_cap + l;
-                        char* const slot = ring + (issued % kSlots) * kSlotBytes;
-                        cp_async16(slot + lane * 16, p.pv_own + row * 16);
+                    if (pl < pL && issued >= consumed) {   // tasks dropped after an event are stepped over, not copied
+                        cp_async16(ring_own + pslot, p_own);
 #pragma unroll
-                        for (int q = 0; q < (int)(kSibBytes / 16); ++q)
-                            cp_async16(slot + 512 + lane * kSibBytes + q * 16, p.pv_sib + row * kSibBytes + q * 16);
-                        cp_async8(slot + 512 + 32 * kSibBytes + lane * 8, p.path_g + row);
+                        for (int q = 0; q < (int)(kSibBytes / 16); ++q) cp_async16(ring_sib + pslot + q * 16, p_sib + q * 16);
+                        cp_async8(ring_g + pslot, p_g);
                     }
-                    pl0 += 32;
-                    if (pl0 >= pL) {
+                    pl += 32; p_own += 32 * 16; p_sib += 32 * kSibBytes; p_g += 32;
+                    if (pl - lane >= pL) {
                         const unsigned rest = pj >= 31 ? 0u : (work & (kFull << (pj + 1)));
                         pj = rest ? __ffs(rest) - 1 : 32;
-                        pl0 = 0;
                         pL = pj < 32 ? __shfl_sync(kFull, my_plen, pj & 31) : 0;
+                        pl = lane;
+                        p_own = p.pv_own + ((warp_tree0 + (pj & 31)) * path_cap + lane) * 16;
+                        p_sib = p.pv_sib + ((warp_tree0 + (pj & 31)) * path_cap + lane) * kSibBytes;
+                        p_g = p.path_g + (warp_tree0 + (pj & 31)) * path_cap + lane;
                     }
                 }
                 cp_async_commit();   // one group per task (an empty one once the sequence is exhausted)
                 ++issued;
+                pslot = pslot + kSlotBytes == kSlots * kSlotBytes ? 0u : pslot + kSlotBytes;
             };
+            unsigned cslot = 0;                 // byte offset of the consumer's slot
             for (unsigned todo = work; todo; todo &= todo - 1) {
                 const int j = __ffs(todo) - 1;
                 const int Lj = __shfl_sync(kFull, my_plen, j);
                 const long long tj = warp_tree0 + j;
-                {
-                    const unsigned nxt = todo & (todo - 1);
-                    if (nxt && !(p.tuning & 8)) {
-                        // the next tree's rows (consecutive bytes) are requested from HBM while this tree is verified
-                        const int jn = __ffs(nxt) - 1;
-                        const int Ln = __shfl_sync(kFull, my_plen, jn);
-                        const char* on = p.pv_own + (warp_tree0 + jn) * path_cap * 16;
-                        const char* sn = p.pv_sib + (warp_tree0 + jn) * path_cap * kSibBytes;
-                        const double* gn = p.path_g + (warp_tree0 + jn) * path_cap;
-                        for (int l = lane * 8; l < Ln; l += 256) {  // one 128-byte line of each row per lane and pass
-                            prefetch_l2(on + (long long)l * 16);
-                            prefetch_l2(sn + (long long)l * kSibBytes);
-                            if (kSibBytes > 16) { prefetch_l2(sn + (long long)l * kSibBytes + 128); prefetch_l2(sn + (long long)l * kSibBytes + 256); }
-                            if ((lane & 1) == 0) prefetch_l2(gn + l);
-                        }
-                    }
-                }
                 char* const bj = p.blocks + tj * p.slots_per_tree * 16;
                 char* const oj = p.pv_own + tj * path_cap * 16;
                 const char* sj = p.pv_sib + tj * path_cap * kSibBytes;
@@ -370,8 +373,9 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
                     const bool act = l < Lj;
                     while (issued < consumed + kAhead) issue_one();
                     cp_async_wait<kAhead - 1>();
-                    const char* const slot = ring + (consumed % kSlots) * kSlotBytes;
+                    const char* const slot = ring + cslot;
                     ++consumed;
+                    cslot = cslot + kSlotBytes == kSlots * kSlotBytes ? 0u : cslot + kSlotBytes;
                     bool my_event = false;
                     if (act) {
                         PvOwn o; PvSib<A> sb;
@@ -394,6 +398,31 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
                         const int pa = (int)(edge & 3u);
                         new_total = __dadd_rn(o.total, pg);   // lazy backup: the return of the previous simulation
                         new_na = o.na + 1;
+                        if constexpr (A == 2) {
+                            // two actions: the old decision stands iff the path edge's score is the UNIQUE maximum
+                            const int sna = sb.na[0];
+                            if (sna == 0) my_event = true;   // unvisited sibling: phase 1b expands it
+                            else {
+                                const int ns = new_na + sna + (l > 0 ? 1 : 0);
+                                int verdict = 0;   // +1 stands, -1 changes, 0 undecided by the fp32 screening
+                                if (!(p.tuning & 1)) {
+                                    const float lgf = ns < p.ln_count ? (p.ln_in_smem ? lnf_smem[ns] : (float)ln_table[ns]) : (float)::log((double)ns);
+                                    const float ro = rcp_approx((float)new_na), rs = rcp_approx((float)sna);
+                                    const float qo = (float)new_total * ro, qs = (float)sb.total[0] * rs;
+                                    const float eo = Cf * sqrt_approx(lgf * ro), es = Cf * sqrt_approx(lgf * rs);
+                                    const float d = (qo + eo) - (qs + es);
+                                    const float tol = 1e-5f * fmaxf(fabsf(qo) + fabsf(eo), fabsf(qs) + fabsf(es)) + 1e-30f;
+                                    verdict = d > tol ? 1 : (d < -tol ? -1 : 0);
+                                }
+                                if (verdict == 0) {
+                                    const double lg = ns < p.ln_count ? ln_table[ns] : ::log((double)ns);
+                                    const double so = __dadd_rn(__ddiv_rn(new_total, (double)new_na), __dmul_rn(Cexp, __dsqrt_rn(__ddiv_rn(lg, (double)new_na))));
+                                    const double ss = __dadd_rn(__ddiv_rn(sb.total[0], (double)sna), __dmul_rn(Cexp, __dsqrt_rn(__ddiv_rn(lg, (double)sna))));
+                                    verdict = so > ss ? 1 : -1;   // a tie needs a draw: phase 1b
+                                }
+                                my_event = verdict < 0;
+                            }
+                        } else {
                         NodeBlock<A> c;
                         int k = 0;
 #pragma unroll
@@ -415,6 +444,7 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
                         double sc[A], best;
                         const int ties = nun > 0 ? 2 : ucb(c, l > 0, a_sel, sc, best);
                         my_event = (ties != 1) || (a_sel != pa);
+                        }
                     }
                     const unsigned ev = __ballot_sync(kFull, my_event);
                     if (ev) event = l0 + __ffs(ev) - 1;
@@ -436,6 +466,7 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
                     // drained first, so that no slot ever has two copies outstanding.
                     cp_async_wait<0>();
                     consumed += rounds - rnd;
+                    cslot = (unsigned)(consumed % kSlots) * kSlotBytes;
                 }
                 const int r = event >= 0 ? event : Lj - 1;
                 // levels the verification did not reach leave the cache as well
@@ -719,8 +750,7 @@ __global__ void tpt_best_kernel(const char* blocks, int32_t* meta, long long n_t
 template <int ENV, typename T>
 int launch_search(const TptParams& p, bool scripted, cudaStream_t st) {
     constexpr int A = EnvTraits<ENV>::A;
-    const size_t smem = (p.ln_in_smem ? (((size_t)p.ln_count * sizeof(double) + 15) & ~(size_t)15) : 0) +
-                        (size_t)(kTptBlock / 32) * CoopRing<A>::kWarpBytes;
+    const size_t smem = (p.ln_in_smem ? (size_t)((p.ln_count + 3) & ~3) * 4 : 0) + (size_t)(kTptBlock / 32) * CoopRing<A>::kWarpBytes;
     if (scripted) {
         tpt_search_kernel<ENV, T, true><<<1, 32, smem, st>>>(p);
     } else {
@@ -798,7 +828,7 @@ int tpt_run(isla_engine* e, int n_sim, long long scripted_tree, const uint8_t* k
     p.disc_table = (const double*)(e->ws + L.disc_offset);
     p.cum_table = (const double*)(e->ws + L.cumdisc_offset);
     p.ln_count = (int)L.ln_count; p.disc_count = (int)L.disc_count;
-    p.ln_in_smem = (L.ln_count * 8 <= 32 * 1024) ? 1 : 0;
+    p.ln_in_smem = (L.ln_count * 4 <= 8 * 1024) ? 1 : 0;   // float copy of ln(n) next to the cooperative ring
     p.tuning = e->cfg.tuning;
     const bool scripted = scripted_tree >= 0;
     const bool f64 = e->cfg.precision == ISLA_PRECISION_F64;
