@@ -365,64 +365,60 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
                 const char* sj = p.pv_sib + tj * path_cap * kSibBytes;
                 const double* gj = p.path_g + tj * path_cap;
                 int event = -1, done_upto = 0;
-                double new_total = 0.0; int new_na = 0; uint32_t edge = 0u;
                 const int rounds = (Lj + 31) >> 5;
                 int rnd = 0;
-                for (int l0 = 0; l0 < Lj && event < 0; l0 += 32, ++rnd) {
-                    const int l = l0 + lane;
-                    const bool act = l < Lj;
-                    while (issued < consumed + kAhead) issue_one();
-                    cp_async_wait<kAhead - 1>();
-                    const char* const slot = ring + cslot;
-                    ++consumed;
-                    cslot = cslot + kSlotBytes == kSlots * kSlotBytes ? 0u : cslot + kSlotBytes;
-                    bool my_event = false;
-                    if (act) {
-                        PvOwn o; PvSib<A> sb;
-                        {
-                            const int4 v = *reinterpret_cast<const int4*>(slot + lane * 16);
-                            o.total = __hiloint2double(v.y, v.x); o.na = v.z;
-                            const int4* sp = reinterpret_cast<const int4*>(slot + 512 + lane * kSibBytes);
-                            if constexpr (A == 2) {
-                                const int4 w = sp[0];
-                                sb.edge = (uint32_t)w.x; sb.na[0] = w.y; sb.total[0] = __hiloint2double(w.w, w.z);
-                            } else {
-                                const int4 v0 = sp[0], v1 = sp[1], v2 = sp[2];
-                                sb.edge = (uint32_t)v0.x; sb.na[0] = v0.y; sb.na[1] = v0.z; sb.na[2] = v0.w;
-                                sb.total[0] = __hiloint2double(v1.y, v1.x); sb.total[1] = __hiloint2double(v1.w, v1.z);
-                                sb.total[2] = __hiloint2double(v2.y, v2.x);
-                            }
-                        }
-                        const double pg = *reinterpret_cast<const double*>(slot + 512 + 32 * kSibBytes + lane * 8);
-                        edge = sb.edge;
-                        const int pa = (int)(edge & 3u);
-                        new_total = __dadd_rn(o.total, pg);   // lazy backup: the return of the previous simulation
-                        new_na = o.na + 1;
+                // one level of the cached path, from this lane's entries in ring slot `slot`: adds the pending return
+                // (lazy backup) and decides whether the old decision stands
+                struct Lev { double total; int na; uint32_t edge; bool event; };
+                auto eval_level = [&](const char* slot, int l) -> Lev {
+                    Lev out;
+                    PvOwn o; PvSib<A> sb;
+                    {
+                        const int4 v = *reinterpret_cast<const int4*>(slot + lane * 16);
+                        o.total = __hiloint2double(v.y, v.x); o.na = v.z;
+                        const int4* sp = reinterpret_cast<const int4*>(slot + 512 + lane * kSibBytes);
                         if constexpr (A == 2) {
-                            // two actions: the old decision stands iff the path edge's score is the UNIQUE maximum
-                            const int sna = sb.na[0];
-                            if (sna == 0) my_event = true;   // unvisited sibling: phase 1b expands it
-                            else {
-                                const int ns = new_na + sna + (l > 0 ? 1 : 0);
-                                int verdict = 0;   // +1 stands, -1 changes, 0 undecided by the fp32 screening
-                                if (!(p.tuning & 1)) {
-                                    const float lgf = ns < p.ln_count ? (p.ln_in_smem ? lnf_smem[ns] : (float)ln_table[ns]) : (float)::log((double)ns);
-                                    const float ro = rcp_approx((float)new_na), rs = rcp_approx((float)sna);
-                                    const float qo = (float)new_total * ro, qs = (float)sb.total[0] * rs;
-                                    const float eo = Cf * sqrt_approx(lgf * ro), es = Cf * sqrt_approx(lgf * rs);
-                                    const float d = (qo + eo) - (qs + es);
-                                    const float tol = 1e-5f * fmaxf(fabsf(qo) + fabsf(eo), fabsf(qs) + fabsf(es)) + 1e-30f;
-                                    verdict = d > tol ? 1 : (d < -tol ? -1 : 0);
-                                }
-                                if (verdict == 0) {
-                                    const double lg = ns < p.ln_count ? ln_table[ns] : ::log((double)ns);
-                                    const double so = __dadd_rn(__ddiv_rn(new_total, (double)new_na), __dmul_rn(Cexp, __dsqrt_rn(__ddiv_rn(lg, (double)new_na))));
-                                    const double ss = __dadd_rn(__ddiv_rn(sb.total[0], (double)sna), __dmul_rn(Cexp, __dsqrt_rn(__ddiv_rn(lg, (double)sna))));
-                                    verdict = so > ss ? 1 : -1;   // a tie needs a draw: phase 1b
-                                }
-                                my_event = verdict < 0;
-                            }
+                            const int4 w = sp[0];
+                            sb.edge = (uint32_t)w.x; sb.na[0] = w.y; sb.total[0] = __hiloint2double(w.w, w.z);
                         } else {
+                            const int4 v0 = sp[0], v1 = sp[1], v2 = sp[2];
+                            sb.edge = (uint32_t)v0.x; sb.na[0] = v0.y; sb.na[1] = v0.z; sb.na[2] = v0.w;
+                            sb.total[0] = __hiloint2double(v1.y, v1.x); sb.total[1] = __hiloint2double(v1.w, v1.z);
+                            sb.total[2] = __hiloint2double(v2.y, v2.x);
+                        }
+                    }
+                    const double pg = *reinterpret_cast<const double*>(slot + 512 + 32 * kSibBytes + lane * 8);
+                    out.edge = sb.edge;
+                    const int pa = (int)(sb.edge & 3u);
+                    const double new_total = __dadd_rn(o.total, pg);   // lazy backup: the return of the previous simulation
+                    const int new_na = o.na + 1;
+                    out.total = new_total; out.na = new_na;
+                    bool my_event;
+                    if constexpr (A == 2) {
+                        // two actions: the old decision stands iff the path edge's score is the UNIQUE maximum
+                        const int sna = sb.na[0];
+                        if (sna == 0) my_event = true;   // unvisited sibling: phase 1b expands it
+                        else {
+                            const int ns = new_na + sna + (l > 0 ? 1 : 0);
+                            int verdict = 0;   // +1 stands, -1 changes, 0 undecided by the fp32 screening
+                            if (!(p.tuning & 1)) {
+                                const float lgf = ns < p.ln_count ? (p.ln_in_smem ? lnf_smem[ns] : (float)ln_table[ns]) : (float)::log((double)ns);
+                                const float ro = rcp_approx((float)new_na), rs = rcp_approx((float)sna);
+                                const float qo = (float)new_total * ro, qs = (float)sb.total[0] * rs;
+                                const float eo = Cf * sqrt_approx(lgf * ro), es = Cf * sqrt_approx(lgf * rs);
+                                const float d = (qo + eo) - (qs + es);
+                                const float tol = 1e-5f * fmaxf(fabsf(qo) + fabsf(eo), fabsf(qs) + fabsf(es)) + 1e-30f;
+                                verdict = d > tol ? 1 : (d < -tol ? -1 : 0);
+                            }
+                            if (verdict == 0) {
+                                const double lg = ns < p.ln_count ? ln_table[ns] : ::log((double)ns);
+                                const double so = __dadd_rn(__ddiv_rn(new_total, (double)new_na), __dmul_rn(Cexp, __dsqrt_rn(__ddiv_rn(lg, (double)new_na))));
+                                const double ss = __dadd_rn(__ddiv_rn(sb.total[0], (double)sna), __dmul_rn(Cexp, __dsqrt_rn(__ddiv_rn(lg, (double)sna))));
+                                verdict = so > ss ? 1 : -1;   // a tie needs a draw: phase 1b
+                            }
+                            my_event = verdict < 0;
+                        }
+                    } else {
                         NodeBlock<A> c;
                         int k = 0;
 #pragma unroll
@@ -444,22 +440,43 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
                         double sc[A], best;
                         const int ties = nun > 0 ? 2 : ucb(c, l > 0, a_sel, sc, best);
                         my_event = (ties != 1) || (a_sel != pa);
-                        }
                     }
-                    const unsigned ev = __ballot_sync(kFull, my_event);
-                    if (ev) event = l0 + __ffs(ev) - 1;
-                    if (act) {
-                        // levels before the event stay cached (with the return added); the event level and
-                        // everything deeper leave the cache: their statistics go back to the node blocks.
-                        // Without an event the LAST level is handed over too (phase 1b re-decides it on its block).
-                        const bool leaves = (event >= 0 && l >= event) || (event < 0 && l == Lj - 1);
-                        if (!leaves) store_own(oj, l, new_total, new_na);
-                        else {
-                            __stcg(total_ptr<A>(bj, (int)(edge >> 2), (int)(edge & 3u)), new_total);
-                            __stcg(na_ptr<A>(bj, (int)(edge >> 2), (int)(edge & 3u)), new_na);
-                        }
+                    out.event = my_event;
+                    return out;
+                };
+                // levels before the event stay cached (with the return added); the event level and everything deeper
+                // leave the cache: their statistics go back to the node blocks.  Without an event the LAST level is
+                // handed over too (phase 1b re-decides it on its block).
+                auto settle_level = [&](const Lev& v, int l) {
+                    const bool leaves = (event >= 0 && l >= event) || (event < 0 && l == Lj - 1);
+                    if (!leaves) store_own(oj, l, v.total, v.na);
+                    else {
+                        __stcg(total_ptr<A>(bj, (int)(v.edge >> 2), (int)(v.edge & 3u)), v.total);
+                        __stcg(na_ptr<A>(bj, (int)(v.edge >> 2), (int)(v.edge & 3u)), v.na);
                     }
-                    done_upto = min(l0 + 32, Lj);
+                };
+                // two rounds (64 levels) per iteration: their evaluations are independent instruction streams
+                for (int l0 = 0; l0 < Lj && event < 0;) {
+                    const bool two = l0 + 32 < Lj;
+                    const int la = l0 + lane, lb = l0 + 32 + lane;
+                    while (issued < consumed + kAhead) issue_one();
+                    cp_async_wait<kAhead - 2>();
+                    const char* const slot_a = ring + cslot;
+                    cslot = cslot + kSlotBytes == kSlots * kSlotBytes ? 0u : cslot + kSlotBytes;
+                    const char* const slot_b = ring + cslot;
+                    Lev va, vb;
+                    va.event = false; vb.event = false;
+                    if (la < Lj) va = eval_level(slot_a, la);
+                    if (two && lb < Lj) vb = eval_level(slot_b, lb);
+                    const unsigned ea = __ballot_sync(kFull, la < Lj && va.event);
+                    const unsigned eb = two ? __ballot_sync(kFull, lb < Lj && vb.event) : 0u;
+                    if (ea) event = l0 + __ffs(ea) - 1;
+                    else if (eb) event = l0 + 32 + __ffs(eb) - 1;
+                    if (la < Lj) settle_level(va, la);
+                    if (two && lb < Lj) settle_level(vb, lb);
+                    if (two) { cslot = cslot + kSlotBytes == kSlots * kSlotBytes ? 0u : cslot + kSlotBytes; consumed += 2; rnd += 2; l0 += 64; }
+                    else { ++consumed; ++rnd; l0 += 32; }
+                    done_upto = min(l0, Lj);
                 }
                 if (rnd < rounds) {
                     // rounds skipped after an event: their tasks are dropped.  Copies already in flight for them are
