@@ -38,6 +38,16 @@ namespace isla {
 namespace {
 
 constexpr int kTptBlock = 64;
+// trees owned by one warp (its first kTreesPerWarp lanes).  With fewer than 32, the phases that run one lane per tree
+// use part of the warp, but the same trees give more warps per SM to hide the dependent-instruction latency of the
+// cooperative phase.
+#ifndef ISLA_TPW
+#define ISLA_TPW 32
+#endif
+#ifndef ISLA_TPT_MINBLOCKS
+#define ISLA_TPT_MINBLOCKS 7
+#endif
+constexpr int kTreesPerWarp = ISLA_TPW;
 constexpr unsigned kFull = 0xffffffffu;
 
 struct TraceCursor {
@@ -176,7 +186,7 @@ template <int A> __device__ __forceinline__ void store_sib(char* row, int l, con
 // The decisions are those of the sequential algorithm: a level's UCB sees exactly the statistics an eager backup
 // would have produced; draws happen only in 1b, in path order.
 template <int ENV, typename T, bool SCRIPTED>
-__global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParams p) {
+__global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kernel(const TptParams p) {
     constexpr int A = EnvTraits<ENV>::A;
     constexpr int S = EnvTraits<ENV>::S;
     constexpr double kInterior = Rewards<ENV>::kInterior;
@@ -194,11 +204,11 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
     char* const coop_ring = reinterpret_cast<char*>(lnf_smem) + ln_slots * 4;
 
     // scripted (parity) mode drives ONE tree from lane 0 of a single warp; the other lanes are dummies
+    const long long warp_tree0 = ((long long)blockIdx.x * (kTptBlock / 32) + (threadIdx.x >> 5)) * kTreesPerWarp;  // tree of lane 0 (free-running)
     const long long tree = SCRIPTED ? (threadIdx.x == 0 ? p.scripted_tree : p.n_trees)
-                                    : (long long)blockIdx.x * blockDim.x + threadIdx.x;
+                                    : (lane < kTreesPerWarp ? warp_tree0 + lane : p.n_trees);
     const bool valid = tree < p.n_trees;
     const long long tix = valid ? tree : 0;
-    const long long warp_tree0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31);  // tree of lane 0 (free-running)
     const long long path_cap = p.block_cap;
     constexpr long long kSibBytes = sizeof(PvSib<A>);
 
@@ -297,7 +307,22 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
     };
 
     int s_done = 0;
+    // -DISLA_PHASE_TIMING: cycles per phase of a few sample warps, printed at the end (development aid)
+#ifdef ISLA_PHASE_TIMING
+    long long t_1a = 0, t_1b = 0, t_2 = 0, t_3 = 0, t_mark;
+    long long u_issue = 0, u_wait = 0, u_eval = 0, u_settle = 0, u_tree = 0, u_mark = 0;
+#define SUB_MARK() u_mark = clock64()
+#define SUB_ADD(acc) do { const long long now_ = clock64(); acc += now_ - u_mark; u_mark = now_; } while (0)
+#define PHASE_MARK() t_mark = clock64()
+#define PHASE_ADD(acc) do { const long long now_ = clock64(); acc += now_ - t_mark; t_mark = now_; } while (0)
+#else
+#define PHASE_MARK()
+#define PHASE_ADD(acc)
+#define SUB_MARK()
+#define SUB_ADD(acc)
+#endif
     for (int sim = 0; sim < p.n_sim; ++sim) {
+        PHASE_MARK();
         const bool live = valid && !fault;
         int mode = live ? MODE_DESCEND : MODE_IDLE;
         int level = 0;  // hand-over level of phase 1a = first level phase 1b decides
@@ -356,6 +381,7 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
                 pslot = pslot + kSlotBytes == kSlots * kSlotBytes ? 0u : pslot + kSlotBytes;
             };
             unsigned cslot = 0;                 // byte offset of the consumer's slot
+            SUB_MARK();
             for (unsigned todo = work; todo; todo &= todo - 1) {
                 const int j = __ffs(todo) - 1;
                 const int Lj = __shfl_sync(kFull, my_plen, j);
@@ -455,28 +481,85 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
                         __stcg(na_ptr<A>(bj, (int)(v.edge >> 2), (int)(v.edge & 3u)), v.na);
                     }
                 };
-                // two rounds (64 levels) per iteration: their evaluations are independent instruction streams
+                // two rounds (64 levels) per iteration.  For two actions both levels of a lane are evaluated in ONE
+                // straight-line block (loads, lazy backup, fp32 screening), so that the two dependent chains overlap in
+                // the in-order issue; only undecided near-ties branch to the exact float64 comparison.
                 for (int l0 = 0; l0 < Lj && event < 0;) {
                     const bool two = l0 + 32 < Lj;
                     const int la = l0 + lane, lb = l0 + 32 + lane;
+                    SUB_ADD(u_tree);
                     while (issued < consumed + kAhead) issue_one();
+                    SUB_ADD(u_issue);
                     cp_async_wait<kAhead - 2>();
+                    SUB_ADD(u_wait);
                     const char* const slot_a = ring + cslot;
                     cslot = cslot + kSlotBytes == kSlots * kSlotBytes ? 0u : cslot + kSlotBytes;
                     const char* const slot_b = ring + cslot;
                     Lev va, vb;
                     va.event = false; vb.event = false;
-                    if (la < Lj) va = eval_level(slot_a, la);
-                    if (two && lb < Lj) vb = eval_level(slot_b, lb);
-                    const unsigned ea = __ballot_sync(kFull, la < Lj && va.event);
-                    const unsigned eb = two ? __ballot_sync(kFull, lb < Lj && vb.event) : 0u;
+                    const bool act_a = la < Lj, act_b = two && lb < Lj;
+                    if constexpr (A == 2) {
+                        const int4 oa = *reinterpret_cast<const int4*>(slot_a + lane * 16);
+                        const int4 ob = *reinterpret_cast<const int4*>(slot_b + lane * 16);
+                        const int4 sa = *reinterpret_cast<const int4*>(slot_a + 512 + lane * 16);
+                        const int4 sb = *reinterpret_cast<const int4*>(slot_b + 512 + lane * 16);
+                        const double ga = *reinterpret_cast<const double*>(slot_a + 1024 + lane * 8);
+                        const double gb = *reinterpret_cast<const double*>(slot_b + 1024 + lane * 8);
+                        va.total = __dadd_rn(__hiloint2double(oa.y, oa.x), ga);   // lazy backup: the return of the previous simulation
+                        vb.total = __dadd_rn(__hiloint2double(ob.y, ob.x), gb);
+                        va.na = oa.z + 1; vb.na = ob.z + 1;
+                        va.edge = (uint32_t)sa.x; vb.edge = (uint32_t)sb.x;
+                        const int sna_a = sa.y, sna_b = sb.y;
+                        const double st_a = __hiloint2double(sa.w, sa.z), st_b = __hiloint2double(sb.w, sb.z);
+                        const int ns_a = va.na + sna_a + (la > 0 ? 1 : 0), ns_b = vb.na + sna_b + 1;
+                        // verdict: +1 the old decision stands, -1 it changes (or the sibling is unvisited), 0 undecided
+                        int ver_a = 0, ver_b = 0;
+                        if (!(p.tuning & 1)) {
+                            const int ia = min(max(ns_a, 0), p.ln_count - 1), ib = min(max(ns_b, 0), p.ln_count - 1);
+                            const float lga = p.ln_in_smem ? lnf_smem[ia] : (float)__ldg(ln_table + ia);
+                            const float lgb = p.ln_in_smem ? lnf_smem[ib] : (float)__ldg(ln_table + ib);
+                            const float roa = rcp_approx((float)va.na), rsa = rcp_approx((float)sna_a);
+                            const float rob = rcp_approx((float)vb.na), rsb = rcp_approx((float)sna_b);
+                            const float qoa = (float)va.total * roa, qsa = (float)st_a * rsa;
+                            const float qob = (float)vb.total * rob, qsb = (float)st_b * rsb;
+                            const float eoa = Cf * sqrt_approx(lga * roa), esa = Cf * sqrt_approx(lga * rsa);
+                            const float eob = Cf * sqrt_approx(lgb * rob), esb = Cf * sqrt_approx(lgb * rsb);
+                            const float da = (qoa + eoa) - (qsa + esa), db = (qob + eob) - (qsb + esb);
+                            const float ta = 1e-5f * fmaxf(fabsf(qoa) + fabsf(eoa), fabsf(qsa) + fabsf(esa)) + 1e-30f;
+                            const float tb = 1e-5f * fmaxf(fabsf(qob) + fabsf(eob), fabsf(qsb) + fabsf(esb)) + 1e-30f;
+                            ver_a = da > ta ? 1 : (da < -ta ? -1 : 0);
+                            ver_b = db > tb ? 1 : (db < -tb ? -1 : 0);
+                            if (ns_a >= p.ln_count) ver_a = 0;
+                            if (ns_b >= p.ln_count) ver_b = 0;
+                        }
+                        if (sna_a == 0) ver_a = -1;   // unvisited sibling: phase 1b expands it
+                        if (sna_b == 0) ver_b = -1;
+                        if ((act_a && ver_a == 0) || (act_b && ver_b == 0)) {
+                            auto exact = [&](double ot, int ona, double st, int sna, int ns) -> int {
+                                const double lg = ns < p.ln_count ? ln_table[ns] : ::log((double)ns);
+                                const double so = __dadd_rn(__ddiv_rn(ot, (double)ona), __dmul_rn(Cexp, __dsqrt_rn(__ddiv_rn(lg, (double)ona))));
+                                const double ss = __dadd_rn(__ddiv_rn(st, (double)sna), __dmul_rn(Cexp, __dsqrt_rn(__ddiv_rn(lg, (double)sna))));
+                                return so > ss ? 1 : -1;   // a tie needs a draw: phase 1b
+                            };
+                            if (act_a && ver_a == 0) ver_a = exact(va.total, va.na, st_a, sna_a, ns_a);
+                            if (act_b && ver_b == 0) ver_b = exact(vb.total, vb.na, st_b, sna_b, ns_b);
+                        }
+                        va.event = ver_a < 0; vb.event = ver_b < 0;
+                    } else {
+                        if (act_a) va = eval_level(slot_a, la);
+                        if (act_b) vb = eval_level(slot_b, lb);
+                    }
+                    SUB_ADD(u_eval);
+                    const unsigned ea = __ballot_sync(kFull, act_a && va.event);
+                    const unsigned eb = two ? __ballot_sync(kFull, act_b && vb.event) : 0u;
                     if (ea) event = l0 + __ffs(ea) - 1;
                     else if (eb) event = l0 + 32 + __ffs(eb) - 1;
-                    if (la < Lj) settle_level(va, la);
-                    if (two && lb < Lj) settle_level(vb, lb);
+                    if (act_a) settle_level(va, la);
+                    if (act_b) settle_level(vb, lb);
                     if (two) { cslot = cslot + kSlotBytes == kSlots * kSlotBytes ? 0u : cslot + kSlotBytes; consumed += 2; rnd += 2; l0 += 64; }
                     else { ++consumed; ++rnd; l0 += 32; }
                     done_upto = min(l0, Lj);
+                    SUB_ADD(u_settle);
                 }
                 if (rnd < rounds) {
                     // rounds skipped after an event: their tasks are dropped.  Copies already in flight for them are
@@ -500,6 +583,7 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
             cp_async_wait<0>();
         }
 
+        PHASE_ADD(t_1a);
         // ------------------------------------------------------------------ phase 1b: serial continuation
         int node_slot = 0, blk = 1, exp_a = 0, exp_rank = 0;
         bool fresh = false;  // block just allocated: all children unvisited, nothing to load
@@ -592,6 +676,7 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
             }
         }
 
+        PHASE_ADD(t_1b);
         // ------------------------------------------------------------------ phase 2: expansion + rollout
         T st[S];
         T r_exp = T(0);
@@ -669,6 +754,7 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
         if constexpr (SCRIPTED) { if (tc.fault && !fault) fault = tc.fault; }
         if (fault) mode = MODE_IDLE;
 
+        PHASE_ADD(t_2);
         // ------------------------------------------------------------------ phase 3: return pass
         // G_l = r + gamma * G_{l+1} up the recorded path (mcts_hash.py:126-131, 79-81).  The returns are only
         // WRITTEN to the tree's pending-return row; the next simulation's phase 1a adds them.
@@ -682,7 +768,13 @@ __global__ void __launch_bounds__(kTptBlock, 7) tpt_search_kernel(const TptParam
             ++sims_done; ++s_done;
         }
         __syncwarp();
+        PHASE_ADD(t_3);
     }
+#ifdef ISLA_PHASE_TIMING
+    if ((blockIdx.x % 197) == 0 && threadIdx.x == 0)
+        printf("block %d cycles 1a %lld 1b %lld 2 %lld 3 %lld | 1a: tree %lld issue %lld wait %lld eval %lld settle %lld\n", blockIdx.x, t_1a, t_1b, t_2, t_3,
+               u_tree, u_issue, u_wait, u_eval, u_settle);
+#endif
 
     if (valid) {
         // leave the tree consistent for the host / the next launch: the cached levels go back to their blocks
@@ -771,7 +863,8 @@ int launch_search(const TptParams& p, bool scripted, cudaStream_t st) {
     if (scripted) {
         tpt_search_kernel<ENV, T, true><<<1, 32, smem, st>>>(p);
     } else {
-        const unsigned grid = (unsigned)((p.n_trees + kTptBlock - 1) / kTptBlock);
+        constexpr int kTreesPerBlock = (kTptBlock / 32) * kTreesPerWarp;
+        const unsigned grid = (unsigned)((p.n_trees + kTreesPerBlock - 1) / kTreesPerBlock);
         tpt_search_kernel<ENV, T, false><<<grid, kTptBlock, smem, st>>>(p);
     }
     const cudaError_t err = cudaGetLastError();
