@@ -351,6 +351,12 @@ def other_configs(dev):
     t = timeit(lambda: eng.set_roots(roots).run(10000), reps=2)
     c = eng.counters()
     out["c3_apw_pendulum_1tree"] = {"sims_per_s": 10000 / t, "env_steps_per_s": c["env_steps"] / t, "ms": t * 1e3}
+    # post-fit analytics of the sweep loop (sweep.py:199-200) on that 10 000-child tree: device kernel vs decoding the whole tree
+    import time as _time
+    eng.depth_stats(0); torch.cuda.synchronize(dev)
+    t0 = _time.perf_counter(); eng.depth_stats(0); t_dev = _time.perf_counter() - t0
+    t0 = _time.perf_counter(); eng.export_tree(0); t_host = _time.perf_counter() - t0
+    out["analytics_c3_tree"] = {"depth_stats_device_ms": t_dev * 1e3, "full_tree_decode_host_ms": t_host * 1e3}
     eng = Engine(_lib.ENV_MOUNTAINCAR, agent=_lib.AGENT_DPW, n_trees=1, sim_capacity=10000, max_depth=500, C_=1.0, gamma=0.99,
                  alpha1=0.5, k1=1.0, alpha2=0.5, k2=1.0, kernel=_lib.KERNEL_CTA_PER_TREE, seed=1, device=dev)
     roots = torch.tensor([[-0.5, 0.0]], dtype=torch.float64)

@@ -144,6 +144,13 @@ int isla_engine_best(isla_engine* e, int32_t scripted_pos, int32_t* best_rank_de
  * (action_dev[cap][action_dim]), ActionNode.na, ActionNode.total; count_dev[0] = number of children (may exceed cap). */
 int isla_engine_root_children(isla_engine* e, int64_t tree, int32_t cap, double* action_dev, int64_t* na_dev,
                               double* total_dev, int32_t* count_dev, void* stream);
+/* Post-fit tree analytics of the sweep loop (sweep.py:199-200): for every root action node of one tree, in root.actions
+ * order, AbstractActionNode.get_depth_max(0) (agents/abstract_mcts.py:190-200) and get_depth_mean(0, True) (:202-209):
+ * the deepest state level below it and the mean level of its leaf states.  depth_max_dev int32[cap], depth_mean_dev
+ * double[cap], count_dev[0] = number of root children (may exceed cap).  Uses per-tree scratch of the workspace: do not
+ * run it concurrently with a search on the same engine. */
+int isla_engine_depth_stats(isla_engine* e, int64_t tree, int32_t cap, int32_t* depth_max_dev, double* depth_mean_dev,
+                            int32_t* count_dev, void* stream);
 /* CTA-per-tree engine: byte offsets of the SoA arrays inside one tree's pool, for host-side decoding
  * (order: s_total, s_term_reward, s_ns, s_flags, s_coff, s_ccap, s_ccnt, s_state, a_total, a_value, a_na,
  *  a_visits, a_child, ipool, path_s, path_a, path_r, path_flag, meta, path_g, a_value2, end). */

@@ -73,6 +73,7 @@ SYMBOLS = {
     "isla_engine_root_stats": (C.c_int, [_P, _P, _P, _P]),
     "isla_engine_best": (C.c_int, [_P, C.c_int32, _P, _P, _P]),
     "isla_engine_root_children": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, _P, _P]),
+    "isla_engine_depth_stats": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, _P]),
     "isla_engine_pool_offsets": (C.c_int, [_P, _P]),
     "isla_engine_counters": (C.c_int, [_P, _P, _P]),
     "isla_merge_root_stats": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int64, _P, _P, _P]),

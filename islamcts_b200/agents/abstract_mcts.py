@@ -140,6 +140,48 @@ class AbstractActionNode:
         return depths
 
 
+class _RootActionProxy(AbstractActionNode):
+    """Root action node served from two small device arrays (root_children + depth_stats): what the sweep loop reads
+    every real step (sweep.py:191-200) -- na, total, q_value, get_depth_max(0), get_depth_mean(0, True) -- needs no
+    copy of the whole tree.  ``children`` (and the list form of get_depth_mean) decode the full tree on first use."""
+    __slots__ = ("_agent", "_key", "_dmax", "_dmean")
+
+    def __init__(self, data, param, agent, key, na, total, dmax, dmean):
+        self.data, self.param = data, param
+        self.total, self.na = float(total), int(na)
+        self._agent, self._key, self._dmax, self._dmean = agent, key, int(dmax), float(dmean)
+
+    @property
+    def children(self):
+        return self._agent._full_root().actions[self._key].children
+
+    def get_depth_max(self, depth):
+        return depth + self._dmax                      # agents/abstract_mcts.py:190-200: levels below are relative
+
+    def get_depth_mean(self, depth=0, root=False):
+        if root:
+            return depth + self._dmean if self._dmax > 0 else depth     # :202-209
+        return self._agent._full_root().actions[self._key].get_depth_mean(depth)
+
+
+class _RootProxy(AbstractStateNode):
+    """Root state node: ``actions`` from the device's root arrays; ns / total decode the tree on first use."""
+    __slots__ = ("_agent",)
+
+    def __init__(self, data, param, agent, actions):
+        self.data, self.param, self._agent = data, param, agent
+        self.terminal, self.actions = False, actions
+        self.terminal_reward, self.visit_actions = None, None
+
+    @property
+    def ns(self):
+        return self._agent._full_root().ns
+
+    @property
+    def total(self):
+        return self._agent._full_root().total
+
+
 class AbstractMcts:
     """Common driver.  Subclasses set AGENT (engine enum), HEAD_BUDGET (what the class does at reference HEAD)."""
 
@@ -157,6 +199,7 @@ class AbstractMcts:
         self._engine: Engine | None = None
         self._engine_key = None
         self._root_proxy = None
+        self._full_proxy = None
         self._root_stub = AbstractStateNode(param.root_data, param)
         self.root_statistics = None
 
@@ -166,7 +209,7 @@ class AbstractMcts:
         if self._engine is None:
             return self._root_stub
         if self._root_proxy is None:
-            self._root_proxy = self._build_proxy()
+            self._root_proxy = self._build_root_proxy()
         return self._root_proxy
 
     @root.setter
@@ -232,6 +275,7 @@ class AbstractMcts:
         eng.run(int(p.n_sim))
         self._sims_done += int(p.n_sim)
         self._root_proxy = None
+        self._full_proxy = None
         cnt = eng.counters()
         if cnt["faults"]:
             raise _lib.IslaError(_lib.ERR_CAPACITY, f"device search reported faults: {cnt}")
@@ -277,6 +321,41 @@ class AbstractMcts:
     # ------------------------------------------------------------------ proxies
     def _make_state(self, data):
         return AbstractStateNode(data, self.param)
+
+    def _action_key(self, a_row):
+        """(data, dict key) of a root action as the reference stores it (int for discrete agents, ndarray.tobytes())."""
+        a_row = np.atleast_1d(a_row)
+        if self.DISCRETE:
+            return int(a_row[0]), int(a_row[0])
+        if a_row.size == 2:                            # CurveEnv: float64 (acceleration, steering)
+            data = np.array(a_row, dtype=np.float64)
+            return data, data.tobytes()
+        space = getattr(self.param.env, "action_space", None)
+        dtype = getattr(space, "dtype", np.float32)
+        data = np.array([a_row[0]], dtype=np.float64 if a_row[0] != np.float32(a_row[0]) else dtype)
+        return data, data.tobytes()
+
+    def _build_root_proxy(self):
+        eng = self._engine
+        if eng.layout.kernel == _lib.KERNEL_CTA_PER_TREE:
+            a, na, tot = eng.root_children(0)
+        else:
+            na_t, tot_t = eng.root_stats()
+            order = eng.root_order(0)
+            a = np.array(order, dtype=np.float64)
+            na = np.array([int(na_t[0, k]) for k in order])
+            tot = np.array([float(tot_t[0, k]) for k in order])
+        dmax, dmean = eng.depth_stats(0)
+        actions = {}
+        for i in range(len(na)):
+            data, key = self._action_key(a[i])
+            actions[key] = _RootActionProxy(data, self.param, self, key, na[i], tot[i], dmax[i], dmean[i])
+        return _RootProxy(self._root_stub.data, self.param, self, actions)
+
+    def _full_root(self):
+        if self._full_proxy is None:
+            self._full_proxy = self._build_proxy()
+        return self._full_proxy
 
     def _build_proxy(self):
         ser = self._engine.export_tree(0)

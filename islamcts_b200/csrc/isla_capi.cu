@@ -220,6 +220,16 @@ int isla_engine_root_children(isla_engine* e, int64_t tree, int32_t cap, double*
     return cta_root_children(e, tree, cap, action_dev, na_dev, total_dev, count_dev, (cudaStream_t)stream);
 }
 
+int isla_engine_depth_stats(isla_engine* e, int64_t tree, int32_t cap, int32_t* depth_max_dev, double* depth_mean_dev,
+                            int32_t* count_dev, void* stream) {
+    if (!e || !count_dev || cap < 0 || (cap > 0 && (!depth_max_dev || !depth_mean_dev))) { set_error("bad argument"); return ISLA_ERR_INVALID; }
+    if (tree < 0 || tree >= e->cfg.n_trees) { set_error("tree index out of range"); return ISLA_ERR_INVALID; }
+    if (!e->roots_set) { set_error("isla_engine_set_roots must be called first"); return ISLA_ERR_INVALID; }
+    return e->kernel == ISLA_KERNEL_THREAD_PER_TREE
+               ? tpt_depth_stats(e, tree, cap, depth_max_dev, depth_mean_dev, count_dev, (cudaStream_t)stream)
+               : cta_depth_stats(e, tree, cap, depth_max_dev, depth_mean_dev, count_dev, (cudaStream_t)stream);
+}
+
 int isla_engine_pool_offsets(const isla_engine* e, int64_t out[24]) {
     if (!e || !out) { set_error("null argument"); return ISLA_ERR_INVALID; }
     if (e->kernel != ISLA_KERNEL_CTA_PER_TREE) { set_error("pool_offsets: CTA-per-tree engine only"); return ISLA_ERR_INVALID; }

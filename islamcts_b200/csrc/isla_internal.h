@@ -94,4 +94,6 @@ int cta_best(isla_engine* e, int scripted_pos, int32_t* best_dev, double* best_a
 int cta_root_children(isla_engine* e, long long tree, int cap, double* action, int64_t* na, double* total, int32_t* count,
                       cudaStream_t st);
 void cta_pool_offsets(const isla_engine* e, long long out[24]);
+int cta_depth_stats(isla_engine* e, long long tree, int cap, int32_t* dmax, double* dmean, int32_t* count, cudaStream_t st);
+int tpt_depth_stats(isla_engine* e, long long tree, int cap, int32_t* dmax, double* dmean, int32_t* count, cudaStream_t st);
 }  // namespace isla

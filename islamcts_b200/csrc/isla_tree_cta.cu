@@ -1101,6 +1101,51 @@ __global__ void cta_root_children_kernel(const CtaParams p, long long tree, int 
     }
 }
 
+// Post-fit depth analytics (agents/abstract_mcts.py:120-142,190-209; sweep.py:199-200) of one tree, level-synchronous:
+// state node levels are propagated from the root, every state is tagged with the root child it hangs under, and the
+// leaves (state nodes none of whose action nodes has a child) feed max / sum / count per root child.  The path arrays of
+// the pool (p_s, p_a, p_flag: only meaningful during a search launch) serve as scratch.
+__global__ void __launch_bounds__(256) cta_depth_stats_kernel(const CtaParams p, long long tree, int cap, int32_t* dmax,
+                                                              double* dmean, int32_t* count) {
+    Pool q = make_pool(p, tree);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int nS = q.meta[CM_NS], n_root = q.s_ccnt[0], root_off = q.s_coff[0];
+    int* const lvl = q.p_s; int* const own = q.p_a; int* const leaves = q.p_flag;
+    __shared__ int changed;
+    for (int s = tid; s < nS; s += nt) lvl[s] = -1;
+    for (int i = tid; i < n_root && i < cap; i += nt) { dmax[i] = 0; dmean[i] = 0.0; leaves[i] = 0; }
+    if (tid == 0) *count = n_root;
+    __syncthreads();
+    // the root's children (up to 10^4 under progressive widening) are spread over the CTA
+    for (int i = tid; i < n_root; i += nt) {
+        const int c = q.a_child[q.ipool[root_off + i]];
+        if (c >= 0) { lvl[c] = 1; own[c] = i; }
+    }
+    __syncthreads();
+    for (int cur = 1;; ++cur) {
+        if (tid == 0) changed = 0;
+        __syncthreads();
+        for (int s = tid; s < nS; s += nt) {
+            if (lvl[s] != cur) continue;
+            const int n = q.s_ccnt[s], off = q.s_coff[s], o = own[s];
+            int pushed = 0;
+            for (int i = 0; i < n; ++i) {
+                const int c = q.a_child[q.ipool[off + i]];
+                if (c >= 0) { lvl[c] = cur + 1; own[c] = o; ++pushed; }
+            }
+            if (pushed) changed = 1;
+            if (o < cap) {
+                atomicMax(dmax + o, cur);
+                if (!pushed) { atomicAdd(leaves + o, 1); atomicAdd(dmean + o, (double)cur); }   // integer-valued sums: order-free
+            }
+        }
+        __syncthreads();
+        if (!changed) break;
+        __syncthreads();
+    }
+    for (int i = tid; i < n_root && i < cap; i += nt) dmean[i] = leaves[i] ? __ddiv_rn(dmean[i], (double)leaves[i]) : 0.0;
+}
+
 CtaParams make_params(const isla_engine* e) {
     CtaParams p;
     const isla_layout& L = e->lay;
@@ -1260,6 +1305,13 @@ int cta_root_children(isla_engine* e, long long tree, int cap, double* action, i
                       cudaStream_t st) {
     CtaParams p = make_params(e);
     cta_root_children_kernel<<<8, 256, 0, st>>>(p, tree, cap, action, na, total, count);
+    ISLA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int cta_depth_stats(isla_engine* e, long long tree, int cap, int32_t* dmax, double* dmean, int32_t* count, cudaStream_t st) {
+    CtaParams p = make_params(e);
+    cta_depth_stats_kernel<<<1, 256, 0, st>>>(p, tree, cap, dmax, dmean, count);
     ISLA_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -856,6 +856,52 @@ __global__ void tpt_best_kernel(const char* blocks, int32_t* meta, long long n_t
     if (best_action_out) best_action_out[tree] = (double)sel;
 }
 
+// Post-fit depth analytics of one tree (agents/abstract_mcts.py:120-142,190-209; sweep.py:199-200) on the node blocks,
+// level-synchronous like the CTA engine's.  A visited edge whose child has no block yet, or is terminal, is a leaf state
+// one level below its block.  Scratch: the tree's edge-id row of the PV cache (free between launches), as {level, owner}.
+__global__ void __launch_bounds__(256) tpt_depth_stats_kernel(const char* blocks_all, const int32_t* meta_all, char* scratch_all,
+                                                              long long slots_per_tree, long long path_cap, int A, long long tree,
+                                                              int cap, int32_t* dmax, double* dmean, int32_t* count) {
+    const char* blocks = blocks_all + tree * slots_per_tree * 16;
+    const int alloc = meta_all[tree * META_WORDS + META_ALLOC];
+    int2* const tag = reinterpret_cast<int2*>(scratch_all + tree * path_cap * 16);   // {level, root-child rank} per block
+    const int tid = threadIdx.x, nt = blockDim.x;
+    __shared__ int changed, n_root;
+    __shared__ int leaves[4];
+    for (int b = tid; b < alloc; b += nt) tag[b] = make_int2(-1, -1);
+    if (tid < 4) leaves[tid] = 0;
+    if (tid == 0) {
+        int n = 0;
+        for (int a = 0; a < A; ++a) n += reinterpret_cast<const int32_t*>(blocks + (long long)A * 16 + A * 8)[a] > 0;
+        n_root = n; *count = n;
+        for (int i = 0; i < n && i < cap; ++i) { dmax[i] = 0; dmean[i] = 0.0; }
+    }
+    __syncthreads();
+    if (tid == 0 && alloc > 1) tag[1] = make_int2(0, -1);
+    __syncthreads();
+    for (int cur = 0;; ++cur) {
+        if (tid == 0) changed = 0;
+        __syncthreads();
+        for (int b = 1 + tid; b < alloc; b += nt) {
+            if (tag[b].x != cur) continue;
+            const char* blk = blocks + (long long)b * (A * 16);
+            for (int a = 0; a < A; ++a) {
+                if (reinterpret_cast<const int32_t*>(blk + A * 8)[a] <= 0) continue;
+                const uint32_t lk = reinterpret_cast<const uint32_t*>(blk + A * 12)[a];
+                const int o = b == 1 ? (int)(lk >> kLinkRankShift) : tag[b].y;
+                const int nb = (int)(lk & kLinkBlockMask);
+                if (o < cap) atomicMax(dmax + o, cur + 1);
+                if (nb != 0 && !(lk & kLinkTerminal)) { tag[nb] = make_int2(cur + 1, o); changed = 1; }
+                else if (o < cap) { atomicAdd(leaves + o, 1); atomicAdd(dmean + o, (double)(cur + 1)); }
+            }
+        }
+        __syncthreads();
+        if (!changed) break;
+        __syncthreads();
+    }
+    if (tid < n_root && tid < cap) dmean[tid] = leaves[tid] ? __ddiv_rn(dmean[tid], (double)leaves[tid]) : 0.0;
+}
+
 template <int ENV, typename T>
 int launch_search(const TptParams& p, bool scripted, cudaStream_t st) {
     constexpr int A = EnvTraits<ENV>::A;
@@ -958,6 +1004,14 @@ int tpt_root_stats(isla_engine* e, int64_t* na_dev, double* total_dev, cudaStrea
     const long long n = e->cfg.n_trees * L.n_actions;
     tpt_root_stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e->ws + L.rec_offset, e->cfg.n_trees,
                                                                        L.slots_per_tree, L.n_actions, na_dev, total_dev);
+    ISLA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int tpt_depth_stats(isla_engine* e, long long tree, int cap, int32_t* dmax, double* dmean, int32_t* count, cudaStream_t st) {
+    const isla_layout& L = e->lay;
+    tpt_depth_stats_kernel<<<1, 256, 0, st>>>(e->ws + L.rec_offset, (const int32_t*)(e->ws + L.meta_offset), e->ws + L.pvown_offset,
+                                            L.slots_per_tree, L.slots_per_tree / L.n_actions, L.n_actions, tree, cap, dmax, dmean, count);
     ISLA_CUDA_OK(cudaGetLastError());
     return 0;
 }

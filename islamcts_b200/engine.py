@@ -158,6 +158,20 @@ class Engine:
         n = int(cnt.item())
         return a[:n].cpu().numpy(), na[:n].cpu().numpy(), tot[:n].cpu().numpy()
 
+    def depth_stats(self, tree: int = 0):
+        """(get_depth_max(0) int32, get_depth_mean(0, True) float64) of one tree's root action nodes, root.actions order
+        (reference: agents/abstract_mcts.py:190-209; the metrics sweep.py:199-200 logs every real step)."""
+        cnt = torch.zeros(1, dtype=torch.int32, device=self.device)
+        cap = max(16, int(self.layout.a_cap), self.n_actions)
+        dmax = torch.empty(cap, dtype=torch.int32, device=self.device)
+        dmean = torch.empty(cap, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.isla_engine_depth_stats(self._h, int(tree), cap, C.c_void_p(dmax.data_ptr()),
+                                                   C.c_void_p(dmean.data_ptr()), C.c_void_p(cnt.data_ptr()),
+                                                   C.c_void_p(_stream_ptr(self.device))))
+        n = int(cnt.item())
+        return dmax[:n].cpu().numpy(), dmean[:n].cpu().numpy()
+
     def counters(self) -> dict:
         out = (C.c_int64 * 8)()
         with torch.cuda.device(self.device):

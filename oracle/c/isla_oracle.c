@@ -802,6 +802,36 @@ int orc_tree_root_children(const orc_tree* t, int cap, double* action, int64_t* 
     return t->S[0].n_act;
 }
 
+/* agents/abstract_mcts.py:120-142 (state node) and :190-209 (action node), iterative: the subtree below root action
+ * node `a0` is walked with an explicit stack of (state index, level); the direct child state has level 1.
+ *   get_depth_max(0)        = deepest level reached (0 when the action node has no child)
+ *   get_depth_mean(0, True) = mean level of the leaves: state nodes without actions, or whose actions all lack children */
+static void action_depth_stats(const orc_tree* t, int a0, int32_t* dmax, double* dmean) {
+    int cap = 256, sp = 0;
+    int* st = (int*)malloc(sizeof(int) * 2 * cap);
+    for (int c = t->A[a0].first_child; c >= 0; c = t->S[c].next_sibling) { st[2 * sp] = c; st[2 * sp + 1] = 1; ++sp; }
+    int best = 0; double sum = 0; int64_t leaves = 0;
+    while (sp > 0) {
+        --sp; const int s = st[2 * sp], lvl = st[2 * sp + 1];
+        if (lvl > best) best = lvl;
+        int pushed = 0;
+        for (int a = t->S[s].first_act; a >= 0; a = t->A[a].next_act)
+            for (int c = t->A[a].first_child; c >= 0; c = t->S[c].next_sibling) {
+                if (sp + 1 >= cap) { cap *= 2; st = (int*)realloc(st, sizeof(int) * 2 * cap); }
+                st[2 * sp] = c; st[2 * sp + 1] = lvl + 1; ++sp; ++pushed;
+            }
+        if (!pushed) { sum += lvl; ++leaves; }
+    }
+    free(st);
+    *dmax = best;
+    *dmean = leaves ? sum / (double)leaves : 0.0;
+}
+int orc_tree_depth_stats(const orc_tree* t, int cap, int32_t* depth_max, double* depth_mean) {
+    int i = 0;
+    for (int a = t->S[0].first_act; a >= 0 && i < cap; a = t->A[a].next_act, ++i) action_depth_stats(t, a, depth_max + i, depth_mean + i);
+    return t->S[0].n_act;
+}
+
 int64_t orc_tree_serialise(const orc_tree* t, int64_t cap, uint8_t* kind, int32_t* depth, int64_t* count,
                            double* total, uint8_t* terminal, int32_t* fanout, double* action, double* action2) {
     /* explicit stack of (kind, index, depth); children pushed in reverse insertion order */

@@ -57,6 +57,8 @@ def lib():
         L.orc_tree_best.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_tree_root_children.restype = C.c_int
         L.orc_tree_root_children.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_tree_depth_stats.restype = C.c_int
+        L.orc_tree_depth_stats.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_tree_serialise.restype = C.c_int64
         L.orc_tree_serialise.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 8
         L.orc_tree_counters.argtypes = [C.c_void_p, C.c_void_p]
@@ -139,6 +141,14 @@ class Tree:
         lib().orc_tree_root_children(self._h, n, _p(a), _p(na), _p(tot), _p(a2))
         self.root_action2 = a2
         return a, na, tot
+
+    def depth_stats(self):
+        """(get_depth_max(0), get_depth_mean(0, True)) of every root action node, root.actions order."""
+        n = lib().orc_tree_root_children(self._h, 0, None, None, None, None)
+        dmax = np.zeros(n, np.int32)
+        dmean = np.zeros(n, np.float64)
+        lib().orc_tree_depth_stats(self._h, n, _p(dmax), _p(dmean))
+        return dmax, dmean
 
     def counters(self):
         out = np.zeros(8, np.int64)

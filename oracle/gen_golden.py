@@ -168,12 +168,17 @@ def run_scenario(name: str, sc: dict):
         action_val = float(root_action[int(action)])  # fit returns an INDEX into the sorted actions (:38)
     else:
         action_val = float(np.asarray(action, dtype=np.float64).reshape(-1)[0])
+    # the sweep loop's per-step metrics (sweep.py:199-200): the reference's own get_depth_max / get_depth_mean
+    # (agents/abstract_mcts.py:120-142,190-209) on every root action node
+    root_depth_max = np.array([c.get_depth_max(0) for c in ch], dtype=np.int32)
+    root_depth_mean = np.array([float(c.get_depth_mean(0, True)) for c in ch], dtype=np.float64)
     out = dict(
         config=np.array(json.dumps(dict(sc, name=name, n_actions=n_actions, fit_error=fit_error))),
         root_state=root_state,
         trace_kind=kinds, trace_value=vals,
         q_values=np.asarray(agent.q_values, dtype=np.float64),
         root_action=root_action, root_action2=root_action2, root_na=root_na, root_total=root_total,
+        root_depth_max=root_depth_max, root_depth_mean=root_depth_mean,
         fit_action=np.float64(action_val),
         env_steps=np.int64(pyenvs.STEP_COUNTER[0] - steps0) if env_name not in ("CurveEnv", "DiscreteCurveEnv") else np.int64(-1),
         **{f"tree_{k}": v for k, v in ser.items()},

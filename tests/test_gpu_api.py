@@ -238,3 +238,40 @@ def test_reference_curve_env_objects_are_recognised():
     env.actions[5] = (0.123, 4.0)                   # not the linspace grid any more -> refuse, never guess
     with pytest.raises(NotImplementedError):
         MctsHash(p).fit()
+
+
+def test_root_proxies_serve_sweep_metrics_from_device_analytics():
+    """sweep.py:191-200 reads len(root.actions), root.actions[action] and its depth metrics every real step: those come
+    from two small device arrays; the full tree is decoded only when something deeper is touched, and agrees."""
+    from islamcts_b200 import envs
+    from islamcts_b200.agents import MctsApw, MctsHash
+    from islamcts_b200.agents.abstract_mcts import _RootActionProxy
+    from islamcts_b200.agents.parameters.mcts_parameters import MctsParameters
+    from islamcts_b200.agents.parameters.pw_parameters import PwParameters
+    from islamcts_b200.utils.action_selection_functions import continuous_default_policy, ucb1
+    common = dict(n_sim=500, C=1, action_selection_fn=ucb1, gamma=0.95, rollout_selection_fn=continuous_default_policy,
+                  max_depth=60, seed=4)
+    cases = []
+    env = envs.make("CartPole-v1", api=4, seed=1); obs = env.reset()
+    cases.append(MctsHash(MctsParameters(root_data=obs, env=env, n_actions=2, **common)))
+    env = envs.make("Pendulum-v1", api=4, seed=1); obs = env.reset()
+    cases.append(MctsApw(PwParameters(root_data=obs, env=env, n_actions=None, alpha=0.4, k=2,
+                                      action_expansion_function=continuous_default_policy, **common)))
+    for agent in cases:
+        action = agent.fit()
+        root = agent.root
+        assert agent._full_proxy is None                       # nothing decoded yet
+        key = action.tobytes() if isinstance(action, np.ndarray) else action
+        node = root.actions[key]
+        assert isinstance(node, _RootActionProxy)
+        dmax, dmean, q = node.get_depth_max(0), node.get_depth_mean(0, True), node.q_value
+        assert agent._full_proxy is None and len(root.actions) == len(agent.q_values)
+        assert q == pytest.approx(agent.q_values.max())
+        full = agent._full_root()                              # the reference's recursion on the decoded tree
+        for k, n in root.actions.items():
+            assert n.get_depth_max(0) == full.actions[k].get_depth_max(0)
+            assert n.get_depth_mean(0, True) == pytest.approx(full.actions[k].get_depth_mean(0, True), rel=1e-12)
+            assert n.get_depth_max(3) == full.actions[k].get_depth_max(3)
+            assert n.na == full.actions[k].na and n.total == full.actions[k].total
+            assert sorted(n.get_depth_mean(0)) == sorted(full.actions[k].get_depth_mean(0))
+        assert root.ns == 500 and dmax >= 1 and dmean >= 1

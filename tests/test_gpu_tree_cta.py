@@ -44,6 +44,10 @@ def test_scripted_trace_rebuilds_reference_tree_cta(name, precision):
         a = a[:, 0]
     np.testing.assert_allclose(a, g["root_action"], rtol=0, atol=1e-12)
     np.testing.assert_allclose(tot, g["root_total"], rtol=tol, atol=tol)
+    # the sweep loop's depth metrics, as the reference's own get_depth_max / get_depth_mean computed them
+    dmax, dmean = eng.depth_stats(0)
+    np.testing.assert_array_equal(dmax, g["root_depth_max"])
+    np.testing.assert_allclose(dmean, g["root_depth_mean"], rtol=1e-12)
 
 
 FREE = {
@@ -99,6 +103,11 @@ def test_free_running_f64_equals_oracle(name, R):
         assert_tree_equal(eng.export_tree(i), exp, rtol=1e-9, atol=1e-9, label=f"{name}/tree{i}: ")
         levels += t.counters()["levels"]
         trees.append(t)
+        if i % 6 == 0:
+            dmax, dmean = eng.depth_stats(i)
+            edmax, edmean = t.depth_stats()
+            np.testing.assert_array_equal(dmax, edmax)
+            np.testing.assert_allclose(dmean, edmean, rtol=1e-12)
     assert eng.counters()["levels"] == levels
     # end of fit() for every tree (spw/dpw: also the persistent key-sorted re-ordering of root.actions)
     rank, act = eng.best()

@@ -42,6 +42,10 @@ def test_scripted_trace_rebuilds_reference_tree_tpt(name, precision):
     for a, n_, t_ in zip(g["root_action"].astype(int), g["root_na"], g["root_total"]):
         assert na[a] == n_
         assert tot[a] == pytest.approx(t_, rel=tol, abs=tol)
+    # the sweep loop's depth metrics (reference get_depth_max / get_depth_mean on every root action node)
+    dmax, dmean = eng.depth_stats(0)
+    np.testing.assert_array_equal(dmax, g["root_depth_max"])
+    np.testing.assert_allclose(dmean, g["root_depth_mean"], rtol=1e-12)
 
 
 @pytest.mark.parametrize("env_id,n_sim,max_depth,C,gamma", [(0, 300, 500, 1.0, 0.99), (0, 200, 12, 4.0, 0.9),
@@ -74,6 +78,10 @@ def test_free_running_f64_equals_oracle_bit_for_bit(env_id, n_sim, max_depth, C,
     best_rank, best_act = eng.best()
     _, rank, act = t5.best()
     assert int(best_act.cpu()[5]) == int(act) and int(best_rank.cpu()[5]) == rank
+    dmax, dmean = eng.depth_stats(5)
+    edmax, edmean = t5.depth_stats()
+    np.testing.assert_array_equal(dmax, edmax)
+    np.testing.assert_allclose(dmean, edmean, rtol=1e-12)
 
 
 def test_free_running_f32_env_agrees_with_f64_oracle_statistically():

@@ -34,6 +34,10 @@ def test_oracle_replays_reference_trace(name):
     np.testing.assert_allclose(a, g["root_action"], rtol=0, atol=1e-12)
     if "root_action2" in g:
         np.testing.assert_allclose(tree.root_action2, g["root_action2"], rtol=0, atol=1e-12)
+    # the sweep loop's depth metrics, computed by the reference's own get_depth_max / get_depth_mean
+    dmax, dmean = tree.depth_stats()
+    np.testing.assert_array_equal(dmax, g["root_depth_max"])
+    np.testing.assert_allclose(dmean, g["root_depth_mean"], rtol=1e-12)
     # counted env.step calls of the reference run (tree-level replay + rollouts); the reference's own
     # CurveEnv is not instrumented (-1)
     if int(g["env_steps"]) >= 0:
