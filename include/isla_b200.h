@@ -43,7 +43,7 @@ enum { ISLA_AGENT_VANILLA = 0, ISLA_AGENT_APW = 1, ISLA_AGENT_SPW = 2, ISLA_AGEN
 /* rollout budget: MctsHash depth accounting (mcts_hash.py:34,116,126) or the zero-length rollouts the
  * other four agents perform at HEAD (mcts.py:27 + abstract_mcts.py:83) */
 enum { ISLA_BUDGET_TO_MAX_DEPTH = 0, ISLA_BUDGET_ZERO = 1 };
-enum { ISLA_EXPAND_RANDOM = 0, ISLA_EXPAND_VOO = 1, ISLA_EXPAND_GENETIC2 = 2 };   /* utils/action_selection_functions.py:46, :139, :104 */
+enum { ISLA_EXPAND_RANDOM = 0, ISLA_EXPAND_VOO = 1, ISLA_EXPAND_GENETIC2 = 2, ISLA_EXPAND_GENETIC = 3 };   /* utils/action_selection_functions.py:46, :139, :104, :50 */
 enum { ISLA_PRECISION_F32 = 0, ISLA_PRECISION_F64 = 1 };   /* env arithmetic; tree statistics are always f64 */
 enum { ISLA_KERNEL_AUTO = 0, ISLA_KERNEL_THREAD_PER_TREE = 1, ISLA_KERNEL_CTA_PER_TREE = 2 };
 /* decision-trace kinds of the scripted (parity) mode */
@@ -59,7 +59,7 @@ typedef struct {
     int32_t budget_mode;        /* ISLA_BUDGET_* */
     int32_t rollouts_per_leaf;  /* build extension: mean of R rollouts backed up as ONE visit */
     int32_t expansion;          /* ISLA_EXPAND_*  (param.action_expansion_function) */
-    int32_t voo_n_samples;
+    int32_t voo_n_samples;      /* voo: samples per expansion; genetic_policy: n_samples */
     int32_t voo_max_try;
     int32_t precision;          /* ISLA_PRECISION_* */
     int32_t kernel;             /* ISLA_KERNEL_* */

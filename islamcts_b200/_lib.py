@@ -18,7 +18,7 @@ ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_TRACE = -1, -2, -3, -4
 ENV_CARTPOLE, ENV_PENDULUM, ENV_MOUNTAINCAR, ENV_FROZENLAKE, ENV_CURVE = 0, 1, 2, 3, 4
 AGENT_VANILLA, AGENT_APW, AGENT_SPW, AGENT_DPW = 0, 1, 2, 3
 BUDGET_TO_MAX_DEPTH, BUDGET_ZERO = 0, 1
-EXPAND_RANDOM, EXPAND_VOO, EXPAND_GENETIC2 = 0, 1, 2
+EXPAND_RANDOM, EXPAND_VOO, EXPAND_GENETIC2, EXPAND_GENETIC = 0, 1, 2, 3
 PRECISION_F32, PRECISION_F64 = 0, 1
 KERNEL_AUTO, KERNEL_THREAD_PER_TREE, KERNEL_CTA_PER_TREE = 0, 1, 2
 

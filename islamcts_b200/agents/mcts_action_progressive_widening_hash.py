@@ -20,6 +20,8 @@ class MctsActionProgressiveWideningHash(AbstractMcts):
             kw.update(expansion=_lib.EXPAND_VOO, epsilon=fn.epsilon, voo_n_samples=fn.n_samples, voo_max_try=fn.max_try)
         elif kind == "genetic2":
             kw.update(expansion=_lib.EXPAND_GENETIC2, epsilon=fn.epsilon)
+        elif kind == "genetic":
+            kw.update(expansion=_lib.EXPAND_GENETIC, epsilon=fn.epsilon, voo_n_samples=fn.n_samples)
         else:
             raise NotImplementedError(f"action_expansion_function kind {kind!r} is not on the device yet")
 

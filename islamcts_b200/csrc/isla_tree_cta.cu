@@ -505,6 +505,70 @@ struct Search {
         return mean2(q.a_value[a0], q.a_value[a1]);   // np.mean([best, second], axis=0)
     }
 
+    // genetic_policy (utils/action_selection_functions.py:50-102), one or two action dimensions.  0 / 1 / 2 existing
+    // actions get the centre / a random bound / the missing bound without drawing p; later calls draw p and, if
+    // p < epsilon, sample n_samples points uniformly in the box spanned by the two LOWEST-q actions (:56-59; which one is
+    // the box's `low` follows from their distance to action_space.low, :61-69, measured in the box's dtype) and return the
+    // sample closest to the first of them (np.argmin: the first minimum).
+    __device__ double genetic_expand(int s, double& out2) {
+        const int off = q.s_coff[s], n = q.s_ccnt[s];
+        double lo[2], hi[2];
+        const bool f32 = box_bounds(lo, hi);
+        const bool two = p.action_dim == 2;
+        out2 = 0.0;
+        auto mean2 = [&](double x, double y) -> double {
+            return f32 ? (double)__fmul_rn(__fadd_rn((float)x, (float)y), 0.5f) : __dmul_rn(__dadd_rn(x, y), 0.5);
+        };
+        if (n == 0) { out2 = mean2(hi[1], lo[1]); return mean2(hi[0], lo[0]); }
+        if (n == 1) {
+            int idx;
+            if constexpr (SCRIPTED) idx = (int)tc.take(ISLA_K_CHOICES);
+            else idx = (1.0 > __dmul_rn(u32_to_d01(ts.next()), 2.0)) ? 0 : 1;   // random.choices([high, low])
+            out2 = idx == 0 ? hi[1] : lo[1];
+            return idx == 0 ? hi[0] : lo[0];
+        }
+        if (n == 2) {
+            const bool has_high = find_action(s, hi[0], hi[1]) >= 0;
+            out2 = has_high ? lo[1] : hi[1];
+            return has_high ? lo[0] : hi[0];
+        }
+        const double pr = u01();
+        if (!(pr < p.epsilon)) return tree_action(out2);
+        auto qv = [&](int i) -> double { const int a = q.ipool[off + i]; return __ddiv_rn(q.a_total[a], (double)q.a_na[a]); };
+        int r0 = -1, r1 = -1;
+        for (int pass = 0; pass < 2; ++pass) {
+            double bq = INFINITY; int br = 0x7fffffff;
+            for (int i = lane; i < n; i += 32) {
+                if (pass == 1 && i == r0) continue;
+                const double v = qv(i);
+                if (v < bq) { bq = v; br = i; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double oq = __shfl_xor_sync(kFull, bq, o);
+                const int orank = __shfl_xor_sync(kFull, br, o);
+                if (oq < bq || (oq == bq && orank < br)) { bq = oq; br = orank; }
+            }
+            if (pass == 0) r0 = br; else r1 = br;
+        }
+        const int a0 = q.ipool[off + r0], a1 = q.ipool[off + r1];
+        const double b0 = q.a_value[a0], b1 = act2(a0), s0 = q.a_value[a1], s1 = act2(a1);   // "best", "second best"
+        double db, ds;
+        if (f32) { db = (double)fabsf(__fsub_rn((float)lo[0], (float)b0)); ds = (double)fabsf(__fsub_rn((float)lo[0], (float)s0)); }
+        else { db = euclid(lo[0], lo[1], b0, b1); ds = euclid(lo[0], lo[1], s0, s1); }
+        const bool best_is_high = db >= ds;
+        const double l0 = best_is_high ? s0 : b0, l1 = best_is_high ? s1 : b1, h0 = best_is_high ? b0 : s0, h1 = best_is_high ? b1 : s1;
+        double dmin = INFINITY, pick = b0, pick2 = b1;
+        for (int k = 0; k < p.voo_n && !tc.fault; ++k) {      // np.random.uniform(low, high, [n_samples, D])
+            const double x = uniform(l0, h0);
+            const double x2 = two ? uniform(l1, h1) : 0.0;
+            const double d = euclid(b0, b1, x, x2);
+            if (d < dmin) { dmin = d; pick = x; pick2 = x2; }
+        }
+        out2 = pick2;
+        return pick;
+    }
+
     // voo (utils/action_selection_functions.py:139-205), one or two action dimensions.  `scratch` (the CTA's rollout
     // reduction buffer, idle during the descent) holds the accepted samples: 3 doubles each.
     __device__ double voo_expand(int s, double& out2, double* scratch, RollShared* sh, int nt) {
@@ -755,6 +819,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                         double val, val2 = 0.0;
                         if (p.agent == ISLA_AGENT_APW && p.expansion == ISLA_EXPAND_VOO) val = ctx.voo_expand(s, val2, red, &sh, nt);
                         else if (p.agent == ISLA_AGENT_APW && p.expansion == ISLA_EXPAND_GENETIC2) val = ctx.genetic2_expand(s, val2);
+                        else if (p.agent == ISLA_AGENT_APW && p.expansion == ISLA_EXPAND_GENETIC) val = ctx.genetic_expand(s, val2);
                         else val = ctx.tree_action(val2);  // dpw ignores --ae (mcts_double_...:57)
                         const int old = ctx.find_action(s, val, val2);
                         if (p.agent == ISLA_AGENT_APW) {
@@ -1243,7 +1308,8 @@ int cta_fill_layout(const isla_config& cfg, isla_layout& lay) {
         set_error("n_actions=%d does not match env (%d)", cfg.n_actions, env_actions); return ISLA_ERR_INVALID;
     }
     if (cfg.expansion != ISLA_EXPAND_RANDOM && cfg.agent != ISLA_AGENT_APW) { set_error("voo / genetic2 expansion are APW options"); return ISLA_ERR_INVALID; }
-    if (cfg.expansion < ISLA_EXPAND_RANDOM || cfg.expansion > ISLA_EXPAND_GENETIC2) { set_error("unknown expansion %d", cfg.expansion); return ISLA_ERR_INVALID; }
+    if (cfg.expansion < ISLA_EXPAND_RANDOM || cfg.expansion > ISLA_EXPAND_GENETIC) { set_error("unknown expansion %d", cfg.expansion); return ISLA_ERR_INVALID; }
+    if (cfg.expansion == ISLA_EXPAND_GENETIC && cfg.voo_n_samples < 1) { set_error("genetic_policy: n_samples must be >= 1"); return ISLA_ERR_INVALID; }
     if (cfg.expansion == ISLA_EXPAND_VOO && (cfg.voo_n_samples < 1 || cfg.voo_n_samples > kMaxRollSmem / 3 || cfg.voo_max_try < 1)) {
         set_error("voo: n_samples must be in [1, %d] and max_try >= 1", kMaxRollSmem / 3); return ISLA_ERR_INVALID;
     }

@@ -76,6 +76,22 @@ def _next_round(name):
     return factory
 
 
-genetic_policy = _next_round("genetic_policy")
+class _Genetic:
+    """Product of ``genetic_policy(epsilon, default_policy, n_samples)`` (reference :50-102): a tag."""
+
+    isla_kind = "genetic"
+
+    def __init__(self, epsilon, default_policy, n_samples):
+        if getattr(default_policy, "isla_kind", None) != "random":
+            raise NotImplementedError("genetic_policy: only continuous_default_policy is supported as the default policy")
+        self.epsilon, self.default_policy, self.n_samples = float(epsilon), default_policy, int(n_samples)
+
+    def __call__(self, node):
+        raise NotImplementedError("genetic_policy runs on the device inside fit(); it is not evaluated on the host")
+
+
+def genetic_policy(epsilon, default_policy, n_samples):
+    return _Genetic(epsilon, default_policy, n_samples)
+
 grid_policy = _next_round("grid_policy")
 discrete_default_policy = _next_round("discrete_default_policy")

@@ -582,6 +582,60 @@ static void genetic2_expand(orc_tree* t, int sidx, double out[2]) {
     }
 }
 
+/* genetic_policy: utils/action_selection_functions.py:50-102 (one or two action dimensions).  0 / 1 / 2 existing
+ * actions get the centre / a random bound / the missing bound (no draw of p); later calls draw p and, if p < epsilon,
+ * sample n_samples points uniformly in the box spanned by the two LOWEST-q actions (sorted ascending, [0] and [1],
+ * :56-59; which of them is the box's `low` is decided by their distance from action_space.low, :61-69) and return the
+ * sample closest to the first of them. */
+static void genetic_expand(orc_tree* t, int sidx, double out[2]) {
+    snode* s = &t->S[sidx];
+    const int D = orc_action_dim(t->cfg.env_id);
+    double lo[2], hi[2];
+    const int f32 = box_bounds(t, lo, hi);
+    out[0] = out[1] = 0.0;
+    if (s->n_act == 0) {     /* np.median([high[i], low[i]]) of two values = their mean, in the box's dtype */
+        for (int d = 0; d < D; ++d) out[d] = f32 ? (double)(((float)hi[d] + (float)lo[d]) / 2.0f) : (hi[d] + lo[d]) / 2.0;
+        return;
+    }
+    if (s->n_act == 1) {
+        double w[2] = {1.0, 1.0};
+        const int pick_high = rnd_choices(t, w, 2) == 0;
+        for (int d = 0; d < D; ++d) out[d] = pick_high ? hi[d] : lo[d];
+        return;
+    }
+    if (s->n_act == 2) {
+        const int has_high = find_action_bits(t, sidx, hi) >= 0;
+        for (int d = 0; d < D; ++d) out[d] = has_high ? lo[d] : hi[d];
+        return;
+    }
+    const double p = rnd_u01(t);
+    if (!(p < t->cfg.epsilon)) { rnd_action(t, &t->tree_stream, out); return; }
+    int b0 = -1, b1 = -1; double q0 = INFINITY, q1 = INFINITY;
+    for (int a = s->first_act; a >= 0; a = t->A[a].next_act) {
+        double q = t->A[a].total / (double)t->A[a].na;
+        if (q < q0) { b1 = b0; q1 = q0; b0 = a; q0 = q; }
+        else if (q < q1) { b1 = a; q1 = q; }
+    }
+    const double* best = t->A[b0].value; const double* second = t->A[b1].value;
+    /* scipy distance.euclidean(action_space.low, x) = norm(low - x): in the arrays' dtype */
+    double db, ds;
+    if (f32) {
+        const float e0 = (float)lo[0] - (float)best[0], e1 = (float)lo[0] - (float)second[0];
+        db = (double)fabsf(e0); ds = (double)fabsf(e1);
+    } else { db = euclid(lo, best, D); ds = euclid(lo, second, D); }
+    const double* bl; const double* bh;
+    if (db >= ds) { bh = best; bl = second; } else { bh = second; bl = best; }
+    int arg = -1; double dmin = INFINITY, pick[2] = {0.0, 0.0};
+    for (int k = 0; k < t->cfg.voo_n_samples; ++k) {        /* np.random.uniform(low, high, [n_samples, D]) */
+        double x[2] = {0.0, 0.0};
+        for (int d = 0; d < D; ++d) x[d] = rnd_uniform(t, bl[d], bh[d]);
+        const double dist = euclid(best, x, D);             /* cdist([best_action], samples) in float64 */
+        if (dist < dmin) { dmin = dist; arg = k; pick[0] = x[0]; pick[1] = x[1]; }   /* np.argmin: first minimum */
+    }
+    (void)arg;
+    out[0] = pick[0]; out[1] = pick[1];
+}
+
 static double state_visit(orc_tree* t, int sidx, int level);
 
 /* build_tree_action.  `level` = tree depth of the parent state node (root = 0). */
@@ -700,6 +754,7 @@ static double state_visit(orc_tree* t, int sidx, int level) {
             double a[2] = {0.0, 0.0};
             if (c->agent == ORC_AGENT_APW && c->expansion == ORC_EXPAND_VOO) voo_expand(t, sidx, a);
             else if (c->agent == ORC_AGENT_APW && c->expansion == ORC_EXPAND_GENETIC2) genetic2_expand(t, sidx, a);
+            else if (c->agent == ORC_AGENT_APW && c->expansion == ORC_EXPAND_GENETIC) genetic_expand(t, sidx, a);
             else rnd_action(t, &t->tree_stream, a); /* dpw ignores --ae: always action_space.sample() */
             int old = find_action_bits(t, sidx, a);
             if (c->agent == ORC_AGENT_APW) {

@@ -13,7 +13,7 @@ _SO = os.path.join(_HERE, "c", "libisla_oracle.so")
 ENV_CARTPOLE, ENV_PENDULUM, ENV_MOUNTAINCAR, ENV_FROZENLAKE, ENV_CURVE = 0, 1, 2, 3, 4
 AGENT_VANILLA, AGENT_APW, AGENT_SPW, AGENT_DPW = 0, 1, 2, 3
 BUDGET_TO_MAX_DEPTH, BUDGET_ZERO = 0, 1
-EXPAND_RANDOM, EXPAND_VOO, EXPAND_GENETIC2 = 0, 1, 2
+EXPAND_RANDOM, EXPAND_VOO, EXPAND_GENETIC2, EXPAND_GENETIC = 0, 1, 2, 3
 
 
 class Config(C.Structure):

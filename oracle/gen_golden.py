@@ -54,6 +54,13 @@ SCENARIOS = {
     # of the two lowest-q actions
     "apw_genetic2_pendulum": dict(agent="MctsApw", env="Pendulum-v1", n_sim=160, C=2.0, gamma=0.95, max_depth=200,
                                   alpha=0.6, k=2, budget="zero", env_seed=3, rng_seed=13, expansion="genetic2", epsilon=0.6),
+    # APW with the first genetic expansion (--ae genetic, n_sample points between the two lowest-q actions)
+    "apw_genetic_pendulum": dict(agent="MctsApw", env="Pendulum-v1", n_sim=170, C=2.0, gamma=0.95, max_depth=200,
+                                 alpha=0.6, k=2, budget="zero", env_seed=4, rng_seed=18, expansion="genetic", epsilon=0.6,
+                                 voo_n_samples=5),
+    "apw_genetic_curve": dict(agent="MctsApw", env="CurveEnv", n_sim=200, C=11.0, gamma=0.9, max_depth=50, alpha=0.45, k=3,
+                              budget="zero", env_seed=0, rng_seed=19, pre_steps=[[-5.0, -30.0], [-5.0, -30.0], [-4.0, -25.0]],
+                              expansion="genetic", epsilon=0.5, voo_n_samples=4),
     # CurveEnv is the reference's OWN environment (islaMcts/environments/curve_env.py) -- the env sweep.py runs.
     # APW on the continuous 2-D action box, after two real steps so that the hidden step counter is > 0
     "apw_curve": dict(agent="MctsApw", env="CurveEnv", n_sim=250, C=11.0, gamma=0.99, max_depth=50, alpha=0.5, k=3,
@@ -130,6 +137,8 @@ def run_scenario(name: str, sc: dict):
             ae = R.voo(sc["epsilon"], R.continuous_default_policy, sc["voo_n_samples"], sc["voo_max_try"])
         elif sc.get("expansion") == "genetic2":
             ae = R.asf.genetic_policy2(sc["epsilon"], R.continuous_default_policy)
+        elif sc.get("expansion") == "genetic":
+            ae = R.asf.genetic_policy(sc["epsilon"], R.continuous_default_policy, sc["voo_n_samples"])
         else:
             ae = R.continuous_default_policy
         param = R.PwParameters(**common, alpha=sc["alpha"], k=sc["k"], action_expansion_function=ae)

@@ -100,7 +100,10 @@ def recording(trace: Trace, seed: int):
         return v
 
     def uniform(low=0.0, high=1.0, size=None):
-        v = rng.uniform(low, high, size)
+        # legacy np.random.uniform = low + (high - low) * random_sample(size); it accepts high < low (genetic_policy
+        # passes the two lowest-q actions in either order), which Generator.uniform rejects
+        lo, hi = np.asarray(low, dtype=np.float64), np.asarray(high, dtype=np.float64)
+        v = lo + (hi - lo) * rng.random(size)
         for x in np.asarray(v, dtype=np.float64).reshape(-1):
             trace.add(K_UNIFORM, float(x))
         return v

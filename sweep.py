@@ -46,16 +46,20 @@ def argument_parser():
 
 
 def get_function(name, args):
-    from islamcts_b200.utils.action_selection_functions import continuous_default_policy, genetic_policy2, ucb1, voo
+    from islamcts_b200.utils.action_selection_functions import (continuous_default_policy, genetic_policy, genetic_policy2,
+                                                                ucb1, voo)
     if name == "ucb":
         return ucb1
     if name == "random":
         return continuous_default_policy
     if name == "voo":
         return voo(epsilon=args["epsilon"], default_policy=get_function(args["genetic_default"], args), n_samples=args["n_sample"])
+    if name == "genetic":
+        return genetic_policy(epsilon=args["epsilon"], default_policy=get_function(args["genetic_default"], args),
+                              n_samples=args["n_sample"])
     if name == "genetic2":
         return genetic_policy2(epsilon=args["epsilon"], default_policy=get_function(args["genetic_default"], args))
-    raise NotImplementedError(f"--{name}: not on the device yet (genetic is a SURVEY 8f row)")
+    raise NotImplementedError(f"--{name}: unknown function name")
 
 
 def create_agent(args, env, observation, seed=None):

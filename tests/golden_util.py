@@ -40,6 +40,8 @@ def engine_kwargs(cfg):
                   voo_max_try=cfg["voo_max_try"])
     if cfg.get("expansion") == "genetic2":
         kw.update(expansion=2, epsilon=cfg["epsilon"])
+    if cfg.get("expansion") == "genetic":
+        kw.update(expansion=3, epsilon=cfg["epsilon"], voo_n_samples=cfg["voo_n_samples"])
     return kw
 
 

@@ -66,8 +66,10 @@ def test_unknown_callables_and_envs_fail_loudly():
         ag.fit()                                                            # a Python callable cannot run on the device
     with pytest.raises(NotImplementedError):
         identify_env(type("Acrobot", (), {})())
+    g1 = genetic_policy(0.7, continuous_default_policy, 5)
+    assert (g1.isla_kind, g1.epsilon, g1.n_samples) == ("genetic", 0.7, 5)
     with pytest.raises(NotImplementedError):
-        genetic_policy(0.7, continuous_default_policy, 5)                   # SURVEY 8f "next" row
+        genetic_policy(0.7, lambda node: 0, 5)                              # only the reference's default policy
     g2 = genetic_policy2(0.7, continuous_default_policy)
     assert (g2.isla_kind, g2.epsilon) == ("genetic2", 0.7)
     v = voo(0.7, continuous_default_policy, 5)

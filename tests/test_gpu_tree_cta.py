@@ -69,6 +69,10 @@ FREE = {
     "apw_voo_curve": dict(env_id=4, agent=1, max_depth=15, C=11.837, gamma=0.4, alpha1=0.3, k1=4.0, expansion=1, epsilon=0.5,
                           voo_n_samples=20, voo_max_try=15),
     "apw_genetic2_curve": dict(env_id=4, agent=1, max_depth=15, C=11.0, gamma=0.9, alpha1=0.45, k1=3.0, expansion=2, epsilon=0.5),
+    "apw_genetic_pendulum": dict(env_id=1, agent=1, max_depth=15, C=2.0, gamma=0.95, alpha1=0.6, k1=2.0, expansion=3, epsilon=0.6,
+                                 voo_n_samples=5),
+    "apw_genetic_curve": dict(env_id=4, agent=1, max_depth=15, C=11.0, gamma=0.9, alpha1=0.45, k1=3.0, expansion=3, epsilon=0.5,
+                              voo_n_samples=4),
     "apw_voo_pendulum_100samples": dict(env_id=1, agent=1, max_depth=10, C=2.0, gamma=0.95, alpha1=0.4, k1=2.0, expansion=1,
                                         epsilon=0.3, voo_n_samples=100, voo_max_try=1000),
 }
