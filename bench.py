@@ -394,6 +394,16 @@ def other_configs(dev):
         t = timeit(run_curve, reps=3)
         total = int(steps[-1].sum().item())
         out[name] = {"trajectories": n, "env_steps_per_s": total / t, "mean_len": total / n, "ms": t * 1e3}
+    # whole episodes in lock-step (sweep.py's loop for --n_episodes 100 at once): CartPole, vanilla, nsim=1000, 100 real steps
+    from islamcts_b200.episodes import EpisodeBatch
+    eb = EpisodeBatch("CartPole-v1", n_episodes=100, n_sim=1000, max_steps=100, seed=1, max_depth=500, C_=1.0, gamma=0.99, device=dev)
+    st0 = (torch.rand((100, 4), generator=g, dtype=torch.float64) - 0.5) * 0.1
+    eb.run(st0)
+    torch.cuda.synchronize(dev)
+    import time as _t
+    t0 = _t.perf_counter(); res = eb.run(st0); dt = _t.perf_counter() - t0
+    out["episodes_cartpole_100_lockstep"] = {"real_steps": res["real_steps"], "seconds": dt, "real_steps_per_s": res["real_steps"] / dt,
+                                             "sims_per_s": res["real_steps"] * 1000 / dt, "mean_steps": float(res["n_steps"].mean())}
     # R: rollout micro-benchmark, 2^24 trajectories from the reset distribution, random policy, budget = max_depth
     flop = {0: 36, 1: 27, 2: 27, 3: 6}
     peak_fp32 = 148 * 128 * 2 * 1.965e9

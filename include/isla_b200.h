@@ -156,6 +156,19 @@ int isla_engine_depth_stats(isla_engine* e, int64_t tree, int32_t cap, int32_t* 
  *  a_visits, a_child, ipool, path_s, path_a, path_r, path_flag, meta, path_g, a_value2, end). */
 int isla_engine_pool_offsets(const isla_engine* e, int64_t out[24]);
 
+/* New Philox key / tree-id base for the searches that follow (takes effect at the next isla_engine_set_roots): the
+ * episode loop builds a fresh tree per real step (sweep.py:186) and gives every step its own streams without
+ * re-creating the engine. */
+int isla_engine_reseed(isla_engine* e, uint64_t seed, uint64_t tree_id_base);
+
+/* Real-step half of the episode loop (sweep.py:190,202-213) for n episodes at once, no host round trip: applies
+ * actions_dev[n][action_dim] (ISLA_ENV_CURVE with a grid: the DiscreteCurveEnv index) to states_dev[n][state_dim] in
+ * float64 for every episode with alive_dev[i] != 0, adds the reward to total_reward_dev[i], counts the step in
+ * n_steps_dev[i] and clears alive_dev[i] when the env terminates or max_steps is reached; finished episodes are frozen. */
+int isla_episode_step(int32_t env_id, int32_t action_grid0, int32_t action_grid1, double* states_dev,
+                      const double* actions_dev, int64_t n, int32_t max_steps, uint8_t* alive_dev,
+                      double* total_reward_dev, int32_t* n_steps_dev, void* stream);
+
 /* Device counters int64[8]: [0] env steps executed, [1] rollout steps, [2] tree levels visited,
  * [3] simulations, [4] nodes created, [5] faults.  SYNCHRONISES the stream. */
 int isla_engine_counters(isla_engine* e, int64_t out_host[8], void* stream);

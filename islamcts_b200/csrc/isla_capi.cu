@@ -239,6 +239,12 @@ int isla_engine_pool_offsets(const isla_engine* e, int64_t out[24]) {
     return ISLA_OK;
 }
 
+int isla_engine_reseed(isla_engine* e, uint64_t seed, uint64_t tree_id_base) {
+    if (!e) { set_error("null engine"); return ISLA_ERR_INVALID; }
+    e->cfg.seed = seed; e->cfg.tree_id_base = tree_id_base; e->roots_set = false;
+    return ISLA_OK;
+}
+
 int isla_engine_counters(isla_engine* e, int64_t out_host[8], void* stream) {
     if (!e || !out_host) { set_error("null argument"); return ISLA_ERR_INVALID; }
     ISLA_CUDA_OK(cudaMemcpyAsync(out_host, e->ws + e->lay.counters_offset, 64, cudaMemcpyDeviceToHost, (cudaStream_t)stream));

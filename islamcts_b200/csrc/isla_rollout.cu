@@ -136,6 +136,28 @@ __global__ void __launch_bounds__(256) rollout_kernel(const T* __restrict__ stat
     }
 }
 
+// real-step half of the episode loop: env.step(best action) for every live episode, float64, in place
+template <int ENV>
+__global__ void episode_step_kernel(double* __restrict__ states, const double* __restrict__ actions, long long n, ActionGrid grid,
+                                    int max_steps, uint8_t* __restrict__ alive, double* __restrict__ total_reward,
+                                    int32_t* __restrict__ n_steps) {
+    constexpr int S = EnvTraits<ENV>::S;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !alive[i]) return;
+    double s[S];
+#pragma unroll
+    for (int k = 0; k < S; ++k) s[k] = states[i * S + k];
+    const int AD = (ENV == ENV_CURVE && grid.g0 == 0) ? 2 : 1;
+    double r;
+    const bool term = env_step_action<ENV, double>(s, actions[i * AD], AD == 2 ? actions[i * AD + 1] : 0.0, grid, r);
+#pragma unroll
+    for (int k = 0; k < S; ++k) states[i * S + k] = s[k];
+    total_reward[i] = __dadd_rn(total_reward[i], r);
+    const int steps = n_steps[i] + 1;
+    n_steps[i] = steps;
+    if (term || steps >= max_steps) alive[i] = 0;
+}
+
 template <typename T>
 int env_step_dispatch(int env, const void* s, const void* a, long long n, void* ns, void* r, uint8_t* t, cudaStream_t st) {
     const unsigned grid = (unsigned)((n + 255) / 256);
@@ -226,6 +248,33 @@ extern "C" int isla_env_step(int32_t env_id, int32_t precision, const void* stat
     return precision == ISLA_PRECISION_F64
                ? isla::env_step_dispatch<double>(env_id, states_dev, actions_dev, n, next_states_dev, rewards_dev, terminated_dev, st)
                : isla::env_step_dispatch<float>(env_id, states_dev, actions_dev, n, next_states_dev, rewards_dev, terminated_dev, st);
+}
+
+extern "C" int isla_episode_step(int32_t env_id, int32_t action_grid0, int32_t action_grid1, double* states_dev,
+                                 const double* actions_dev, int64_t n, int32_t max_steps, uint8_t* alive_dev,
+                                 double* total_reward_dev, int32_t* n_steps_dev, void* stream) {
+    using namespace isla;
+    if (n <= 0) return ISLA_OK;
+    if (!states_dev || !actions_dev || !alive_dev || !total_reward_dev || !n_steps_dev) { set_error("null argument"); return ISLA_ERR_INVALID; }
+    ActionGrid ag{0, 0};
+    if (env_id == ISLA_ENV_CURVE && (action_grid0 != 0 || action_grid1 != 0)) {
+        if (action_grid0 < 1 || action_grid1 < 1 || (int64_t)action_grid0 * action_grid1 > 128) {
+            set_error("DiscreteCurveEnv grid %d x %d: need 1 <= g0*g1 <= 128", action_grid0, action_grid1); return ISLA_ERR_INVALID;
+        }
+        ag = ActionGrid{action_grid0, action_grid1};
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    switch (env_id) {
+    case ENV_CARTPOLE: episode_step_kernel<ENV_CARTPOLE><<<grid, 128, 0, st>>>(states_dev, actions_dev, n, ag, max_steps, alive_dev, total_reward_dev, n_steps_dev); break;
+    case ENV_PENDULUM: episode_step_kernel<ENV_PENDULUM><<<grid, 128, 0, st>>>(states_dev, actions_dev, n, ag, max_steps, alive_dev, total_reward_dev, n_steps_dev); break;
+    case ENV_MOUNTAINCAR: episode_step_kernel<ENV_MOUNTAINCAR><<<grid, 128, 0, st>>>(states_dev, actions_dev, n, ag, max_steps, alive_dev, total_reward_dev, n_steps_dev); break;
+    case ENV_FROZENLAKE: episode_step_kernel<ENV_FROZENLAKE><<<grid, 128, 0, st>>>(states_dev, actions_dev, n, ag, max_steps, alive_dev, total_reward_dev, n_steps_dev); break;
+    case ENV_CURVE: episode_step_kernel<ENV_CURVE><<<grid, 128, 0, st>>>(states_dev, actions_dev, n, ag, max_steps, alive_dev, total_reward_dev, n_steps_dev); break;
+    default: set_error("unknown env %d", env_id); return ISLA_ERR_INVALID;
+    }
+    ISLA_CUDA_OK(cudaGetLastError());
+    return ISLA_OK;
 }
 
 extern "C" int isla_rollout(int32_t env_id, int32_t precision, const void* states_dev, int64_t n, int32_t budget, double gamma,

@@ -109,6 +109,11 @@ class Engine:
         self._roots = t
         return self
 
+    def reseed(self, seed: int, tree_id_base: int = 0):
+        """New Philox key for the searches after the next set_roots() (a fresh tree per real step, sweep.py:186)."""
+        check(self.lib.isla_engine_reseed(self._h, int(seed), int(tree_id_base)))
+        return self
+
     def run(self, n_sim: int):
         with torch.cuda.device(self.device):
             check(self.lib.isla_engine_run(self._h, int(n_sim), C.c_void_p(_stream_ptr(self.device))))

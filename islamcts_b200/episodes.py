@@ -1,0 +1,59 @@
+"""Whole episodes on the device: fit -> real step -> new root, for many episodes in lock-step, without host round trips.
+
+Mirrors the episode loop of the reference's CLIs (sweep.py:166-227, sweep_vanilla.py, README.md:99-121): every real step
+builds a FRESH tree per episode (``agent = create_agent()`` inside the loop, sweep.py:186), takes ``agent.fit()``'s action
+and applies it to the real env.  Here the E episodes of an experiment (the reference runs ``--n_episodes`` of them one
+after the other) advance together: one search launch for the E trees, one ``best`` epilogue, one env-step kernel that
+applies the chosen actions, accumulates rewards and freezes finished episodes.  The host only enqueues launches; it
+looks at the ``alive`` flags every few steps to stop early.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import engine as E
+from ._lib import check
+
+
+class EpisodeBatch:
+    def __init__(self, env: str | int, agent: int = _lib.AGENT_VANILLA, n_episodes: int = 100, n_sim: int = 1000,
+                 max_steps: int = 100, seed: int = 0, device="cuda:0", action_grid=None, **engine_kwargs):
+        self.env_id = E.ENV_NAMES[env] if isinstance(env, str) else int(env)
+        self.device = torch.device(device)
+        self.n, self.n_sim, self.max_steps, self.seed = int(n_episodes), int(n_sim), int(max_steps), int(seed)
+        self.grid = tuple(int(x) for x in action_grid) if action_grid else (0, 0)
+        self.engine = E.Engine(self.env_id, agent=agent, n_trees=self.n, sim_capacity=self.n_sim, seed=seed, device=device,
+                               action_grid=action_grid, **engine_kwargs)
+        self.S = E.STATE_DIM[self.env_id]
+
+    def run(self, initial_states, check_every: int = 8) -> dict:
+        """initial_states: [n_episodes, state_dim] float64 env states.  Returns host arrays: total_reward, n_steps, final
+        states, and the per-step actions (rank of the chosen root child is not kept)."""
+        dev, eng, lib = self.device, self.engine, _lib.load()
+        states = torch.as_tensor(initial_states, dtype=torch.float64).reshape(self.n, self.S).to(dev).clone()
+        alive = torch.ones(self.n, dtype=torch.uint8, device=dev)
+        total = torch.zeros(self.n, dtype=torch.float64, device=dev)
+        steps = torch.zeros(self.n, dtype=torch.int32, device=dev)
+        actions = []
+        for k in range(self.max_steps):
+            eng.reseed(self.seed + k, 0)                       # every real step searches with its own streams
+            eng.set_roots(states)
+            eng.run(self.n_sim)
+            _, act = eng.best()
+            actions.append(act)
+            with torch.cuda.device(dev):
+                check(lib.isla_episode_step(self.env_id, self.grid[0], self.grid[1], C.c_void_p(states.data_ptr()),
+                                            C.c_void_p(act.data_ptr()), self.n, self.max_steps, C.c_void_p(alive.data_ptr()),
+                                            C.c_void_p(total.data_ptr()), C.c_void_p(steps.data_ptr()),
+                                            C.c_void_p(E._stream_ptr(dev))))
+            if (k + 1) % check_every == 0 and not bool(alive.any().item()):
+                break
+        cnt = eng.counters()
+        if cnt["faults"]:
+            raise _lib.IslaError(_lib.ERR_CAPACITY, f"device search reported faults: {cnt}")
+        return dict(total_reward=total.cpu().numpy(), n_steps=steps.cpu().numpy(), states=states.cpu().numpy(),
+                    actions=torch.stack(actions).cpu().numpy(), real_steps=int(steps.sum().item()))

@@ -42,6 +42,8 @@ def argument_parser():
     p.add_argument('--depth_mode', default="budgeted", choices=["budgeted", "reference_head"])
     p.add_argument('--precision', default="f32", choices=["f32", "f64"])
     p.add_argument('--max_steps', default=100, type=int, help='real steps per episode (the reference stops at 100, sweep.py:206)')
+    p.add_argument('--lockstep', action='store_true',
+                   help='advance all --n_episodes episodes together on the device (islamcts_b200.episodes.EpisodeBatch)')
     return p
 
 
@@ -86,8 +88,58 @@ def create_agent(args, env, observation, seed=None):
     raise NotImplementedError(algo)
 
 
+def run_lockstep(args):
+    """All episodes at once: one search launch per real step for the whole experiment, no host round trip in the loop."""
+    from islamcts_b200 import _lib
+    from islamcts_b200 import engine as E
+    from islamcts_b200.episodes import EpisodeBatch
+    name, algo = args["environment"], args["algorithm"]
+    env_id = E.ENV_NAMES[name]
+    n = args["n_episodes"]
+    kw = dict(max_depth=args["max_depth"], C_=args["c"], gamma=args["gamma"], rollouts_per_leaf=args["rollouts_per_leaf"],
+              precision=_lib.PRECISION_F64 if args["precision"] == "f64" else _lib.PRECISION_F32)
+    grid = None
+    if algo == "vanilla":
+        agent = _lib.AGENT_VANILLA
+        if name == "DiscreteCurveEnv":
+            grid = (args["n_accelerations"], args["n_angles"])
+        # MctsHash budgets its rollouts; Mcts (integer observations) plays zero-length rollouts at HEAD
+        if env_id == _lib.ENV_FROZENLAKE and args["depth_mode"] == "reference_head":
+            kw["budget_mode"] = _lib.BUDGET_ZERO
+    elif algo == "apw":
+        agent = _lib.AGENT_APW
+        kw.update(alpha1=args["alpha1"], k1=args["k1"], epsilon=args["epsilon"], voo_n_samples=args["n_sample"],
+                  expansion={"random": 0, "voo": 1, "genetic2": 2, "genetic": 3}[args["ae"]])
+        if args["depth_mode"] == "reference_head":
+            kw["budget_mode"] = _lib.BUDGET_ZERO
+    else:
+        raise NotImplementedError("--lockstep: vanilla and apw")
+    seed = 0 if args["seed"] is None else args["seed"]
+    if env_id == _lib.ENV_CURVE:
+        states = np.tile(np.array([-11.0, 21.0, 10.0, 90.0, 0.0]), (n, 1))             # CurveEnv.reset(), curve_env.py:181
+    elif env_id == _lib.ENV_FROZENLAKE:
+        states = np.zeros((n, 1))
+    else:
+        from islamcts_b200 import envs
+        rows = []
+        for i in range(n):
+            e = envs.make(name, api=4, seed=seed + i)
+            e.reset()
+            rows.append(np.asarray(e.state, dtype=np.float64))
+        states = np.stack(rows)
+    t0 = time.time()
+    out = EpisodeBatch(env_id, agent=agent, n_episodes=n, n_sim=args["nsim"], max_steps=args["max_steps"], seed=seed,
+                       action_grid=grid, **kw).run(states)
+    dt = time.time() - t0
+    print(json.dumps({"episodes": n, "real_steps": out["real_steps"], "seconds": dt, "real_steps_per_s": out["real_steps"] / dt,
+                      "mean_reward": float(out["total_reward"].mean()), "max_reward": float(out["total_reward"].max()),
+                      "min_reward": float(out["total_reward"].min()), "mean_steps": float(out["n_steps"].mean())}), flush=True)
+
+
 def main(argv=None):
     args = argument_parser().parse_args(argv).__dict__
+    if args["lockstep"]:
+        return run_lockstep(args)
     from islamcts_b200 import envs
     rewards = []
     for ep in range(args["n_episodes"]):
