@@ -68,6 +68,9 @@ typedef struct {
     int32_t tuning;             /* experiment flags for A/B timing; 0 = defaults */
     int32_t action_grid0;       /* ISLA_ENV_CURVE: DiscreteCurveEnv([g0, g1]) = g0 accelerations x g1 steering angles */
     int32_t action_grid1;       /*   (curve_env.py:184-199; n_actions = g0*g1 <= 128); both 0 = the continuous 2-D CurveEnv box */
+    int32_t cluster_ctas;       /* CTA-per-tree kernel: thread blocks (one thread-block cluster) that share one tree's leaf-parallel
+                                 * rollouts; 0 = auto (up to 8 when rollouts_per_leaf > 512), else 1, 2, 4 or 8 */
+    int32_t reserved1;
     double C;                   /* param.C */
     double gamma;               /* param.gamma */
     double alpha1, k1;          /* PwParameters.alpha/k ; DpwParameters.alphaApw/kApw */

@@ -26,6 +26,7 @@
 // Envs on the device are deterministic, hence an action node has at most ONE child state;
 // the dict-overwrite quirks of spw/dpw (a13, a14) are reproduced on that single slot.
 #include <cmath>
+#include <cooperative_groups.h>
 
 #include "isla_envs.cuh"
 #include "isla_internal.h"
@@ -57,13 +58,14 @@ struct CtaParams {
     long long n_trees, scripted_tree;
     unsigned long long seed, tree_id_base;
     double C, gamma, alpha1, k1, alpha2, k2, epsilon;
-    const double* disc_table; const double* ln_table; const double* pw1_table; const double* pw2_table;
+    const double* disc_table; const double* cum_table; const double* ln_table; const double* pw1_table; const double* pw2_table;
     int ln_count, disc_count;
     int n_sim, max_depth, budget_mode, agent, n_actions, R, expansion, voo_n, voo_max_try, real_bytes;
     int pool_in_smem;  // the whole tree pool fits in shared memory: search there, copy back at the end
     char* hash_base; long long hash_cap;  // per-tree action hash set (apw/dpw): hash_cap int4 entries per tree, 0 = none
     ActionGrid grid;                       // DiscreteCurveEnv action grid (g0 == 0: not a grid)
     int action_dim;                        // 1, or 2 for the continuous CurveEnv box (second coordinate in a_value2)
+    int cluster;                           // CTAs (one thread-block cluster) sharing one tree's leaf-parallel rollouts
 };
 
 enum : int { O_S_TOTAL = 0, O_S_TERMR, O_S_NS, O_S_FLAGS, O_S_COFF, O_S_CCAP, O_S_CCNT, O_S_STATE, O_A_TOTAL, O_A_VALUE,
@@ -720,9 +722,19 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
     constexpr int S = EnvTraits<ENV>::S;
     __shared__ RollShared sh;
     __shared__ double red[kMaxRollSmem];
-    const long long tree = SCRIPTED ? p.scripted_tree : (long long)blockIdx.x;
+    __shared__ double partials[8];   // rank 0: the rollout sums of the cluster's CTAs
+    // A tree whose leaves are evaluated by thousands of rollouts is served by a thread-block CLUSTER: rank 0 owns the
+    // tree (descent, expansion, backup), every rank plays an interleaved power-of-two slice of the rollouts from the leaf
+    // state it reads out of rank 0's shared memory (DSMEM), reduces it with the fixed pairwise tree and stores its sum
+    // into rank 0's `partials`; rank 0 finishes the same tree over the ranks -- the mean is bit-identical for any
+    // cluster and CTA size.  Two cluster barriers per simulation.
+    namespace cg = cooperative_groups;
+    const int CS = SCRIPTED ? 1 : p.cluster;
+    const unsigned crank = CS > 1 ? cg::this_cluster().block_rank() : 0u;
+    const bool owner = crank == 0;
+    const long long tree = SCRIPTED ? p.scripted_tree : (long long)(blockIdx.x / (unsigned)CS);
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
-    const bool leader = tid < 32;  // warp 0
+    const bool leader = owner && tid < 32;  // warp 0 of the owning CTA
     const uint32_t tree_id = (uint32_t)(p.tree_id_base + (unsigned long long)tree);
     const int R = p.R;
     int P = 1;
@@ -733,13 +745,14 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
     // the end.  Larger pools stay in HBM/L2.
     extern __shared__ int4 pool_smem[];
     char* const pool_global = p.pool_base + tree * p.pool_stride;
-    if (p.pool_in_smem) {
+    if (p.pool_in_smem && owner) {
         const int n16 = (int)(p.pool_stride >> 4);
         const int4* src = reinterpret_cast<const int4*>(pool_global);
         for (int i = tid; i < n16; i += nt) pool_smem[i] = src[i];
         __syncthreads();
     }
-    Search<ENV, T, SCRIPTED> ctx(p, tree, p.pool_in_smem ? reinterpret_cast<char*>(pool_smem) : pool_global);
+    Search<ENV, T, SCRIPTED> ctx(p, tree, (p.pool_in_smem && owner) ? reinterpret_cast<char*>(pool_smem) : pool_global);
+    const RollShared* const sh0 = CS > 1 ? cg::this_cluster().map_shared_rank(&sh, 0) : &sh;   // the owner's leaf record
     uint32_t sims_done = (uint32_t)ctx.q.meta[CM_SIMS];
     int s_done = 0;
     unsigned long long my_steps = 0;  // rollout env steps played by THIS thread
@@ -924,6 +937,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
         } else if (leader && lane == 0) {
             sh.need = 0;
         }
+        if (owner) {
         // end of the descent.  Until then the other warps serve voo's try batches (barrier 1 = work posted or descent
         // over, barrier 2 = batch evaluated); the last barrier-1 also publishes sh.need / sh.leaf / sh.budget.
         if (leader) {
@@ -939,10 +953,13 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                 bar_sync(2, nt);
             }
         }
+        }
+        if (CS > 1) cg::this_cluster().sync();   // the owner's leaf record is final
 
         // ------------------------------------------------------------ all threads: R rollouts from the leaf
-        if (sh.need) {
-            const int budget = sh.budget;
+        const bool need = sh0->need != 0;
+        if (need) {
+            const int budget = sh0->budget;
             if constexpr (SCRIPTED) {
                 // the trace scripts ONE rollout (R == 1), replayed by every lane of warp 0
                 if (leader) {
@@ -963,35 +980,56 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                 }
                 __syncthreads();
             } else {
-                for (int j0 = 0; j0 < P; j0 += nt) {
-                    const int j = j0 + tid;
-                    if (j < P) {
+                // this CTA plays the rollouts j = jl * CS + rank (jl < slice): the single-CTA reduction tree (strides
+                // P/2 ... 1) first combines indices with equal low bits, i.e. exactly the elements of one rank, and
+                // ends with the CS per-rank sums
+                const int slice = P / CS;
+                const unsigned sim_id = sh0->sim;
+                double leaf[S];
+#pragma unroll
+                for (int i = 0; i < S; ++i) leaf[i] = sh0->leaf[i];
+                for (int j0 = 0; j0 < slice; j0 += nt) {
+                    const int jl = j0 + tid, j = jl * CS + (int)crank;
+                    if (jl < slice) {
                         double Rr = 0.0;
                         if (j < R) {
                             T st[S];
 #pragma unroll
-                            for (int i = 0; i < S; ++i) st[i] = T(sh.leaf[i]);
+                            for (int i = 0; i < S; ++i) st[i] = T(leaf[i]);
                             Stream rs;
-                            rs.init(p.seed, sh.sim, tree_id, (uint32_t)j);
+                            rs.init(p.seed, sim_id, tree_id, (uint32_t)j);
                             int t = 0; bool done = false;
+                            T rr = T(0);
                             while (!done && t < budget) {
-                                T rr;
                                 done = rollout_step<ENV, T>(rs, st, p.grid, rr);
-                                Rr = __dadd_rn(Rr, __dmul_rn((double)rr, __ldg(p.disc_table + t)));
+                                // r * pow(gamma, t) summed left to right (abstract_mcts.py:87); envs with a constant
+                                // interior reward take the bit-identical closed form from the host prefix table below
+                                if constexpr (!Rewards<ENV>::kClosedForm) Rr = __dadd_rn(Rr, __dmul_rn((double)rr, __ldg(p.disc_table + t)));
                                 ++t;
                             }
+                            if constexpr (Rewards<ENV>::kClosedForm) Rr = Rewards<ENV>::rollout_return(t, (double)rr, p.disc_table, p.cum_table);
                             my_steps += t;
                         }
-                        red[j] = Rr;
+                        red[jl] = Rr;
                     }
                 }
                 __syncthreads();
-                // fixed power-of-two tree: the sum does not depend on the CTA size
-                for (int stride = P >> 1; stride > 0; stride >>= 1) {
+                // fixed power-of-two tree: the sum does not depend on the CTA size nor on the cluster size
+                for (int stride = slice >> 1; stride > 0; stride >>= 1) {
                     for (int i = tid; i < stride; i += nt) red[i] = __dadd_rn(red[i], red[i + stride]);
                     __syncthreads();
                 }
+                if (CS > 1 && tid == 0) cg::this_cluster().map_shared_rank(partials, 0)[crank] = red[0];
             }
+        }
+        if (CS > 1) {
+            cg::this_cluster().sync();   // every rank's sum has landed in the owner's `partials`
+            if (owner && need && tid == 0) {
+                for (int stride = CS >> 1; stride > 0; stride >>= 1)
+                    for (int i = 0; i < stride; ++i) partials[i] = __dadd_rn(partials[i], partials[i + stride]);
+                red[0] = partials[0];
+            }
+            __syncthreads();
         }
 
         // ------------------------------------------------------------ warp 0: leaf update + backup
@@ -1029,7 +1067,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
     }
 
     if (my_steps) { atomicAdd(p.counters + CNT_ROLLOUT_STEPS, my_steps); atomicAdd(p.counters + CNT_ENV_STEPS, my_steps); }
-    bool copy_back = p.pool_in_smem;
+    bool copy_back = p.pool_in_smem && owner;
     if (leader) {
         int flt = ctx.fault ? ctx.fault : ctx.tc.fault;
         if (lane == 0) {
@@ -1237,6 +1275,7 @@ CtaParams make_params(const isla_engine* e) {
     p.C = e->cfg.C; p.gamma = e->cfg.gamma; p.alpha1 = e->cfg.alpha1; p.k1 = e->cfg.k1; p.alpha2 = e->cfg.alpha2; p.k2 = e->cfg.k2;
     p.epsilon = e->cfg.epsilon;
     p.disc_table = (const double*)(e->ws + L.disc_offset); p.ln_table = (const double*)(e->ws + L.ln_offset);
+    p.cum_table = (const double*)(e->ws + L.cumdisc_offset);
     p.pw1_table = (const double*)(e->ws + L.pw1_offset); p.pw2_table = (const double*)(e->ws + L.pw2_offset);
     p.ln_count = (int)L.ln_count; p.disc_count = (int)L.disc_count;
     p.n_sim = 0; p.max_depth = e->cfg.max_depth; p.budget_mode = e->cfg.budget_mode; p.agent = e->cfg.agent;
@@ -1246,9 +1285,16 @@ CtaParams make_params(const isla_engine* e) {
     // the descent then costs ~30 cycles per access instead of an L2 round trip.  That pays while ALL trees are resident
     // at once; with more trees than that, shared-memory pools cap the CTAs per SM and pools in HBM/L2 with up to 32 CTAs
     // per SM are 3-4x faster (measured: 4096 DiscreteCurveEnv trees 4.8 -> 17.2 M sims/s).
+    // leaf-parallel batches beyond one CTA's 512 threads are spread over a thread-block cluster (portable size <= 8)
+    int cs = e->cfg.cluster_ctas;
+    if (cs <= 0) { cs = 1; while (cs < 8 && p.R > 512 * cs) cs <<= 1; }
+    int Pw = 1; while (Pw < p.R) Pw <<= 1;
+    while (cs > 1 && (Pw / cs) < 1) cs >>= 1;
+    p.cluster = cs;
     const long long fit_per_sm = off > 0 ? (190 * 1024) / off : 0;
     const long long sms = e->sm_count > 0 ? e->sm_count : 148;
-    p.pool_in_smem = (fit_per_sm >= 1 && e->cfg.n_trees <= sms * fit_per_sm && !(e->cfg.tuning & 16)) ? 1 : 0;
+    // (every CTA of a launch reserves the dynamic shared memory, the cluster's helper CTAs included)
+    p.pool_in_smem = (fit_per_sm >= 1 && e->cfg.n_trees * cs <= sms * fit_per_sm && !(e->cfg.tuning & 16)) ? 1 : 0;
     p.hash_base = e->ws ? e->ws + L.hash_offset : nullptr; p.hash_cap = L.hash_cap;
     return p;
 }
@@ -1257,7 +1303,7 @@ long long pool_bytes(const isla_config& cfg, long long s_cap, long long a_cap, i
     isla_engine tmp;
     tmp.cfg = cfg; tmp.ws = nullptr; tmp.sm_count = 0;
     tmp.lay.pool_offset = 0; tmp.lay.pool_stride = 0; tmp.lay.s_cap = s_cap; tmp.lay.a_cap = a_cap; tmp.lay.real_bytes = rb;
-    tmp.lay.state_dim = S; tmp.lay.counters_offset = 0; tmp.lay.disc_offset = 0; tmp.lay.ln_offset = 0; tmp.lay.ln_count = 0; tmp.lay.disc_count = 0; tmp.lay.pw1_offset = 0; tmp.lay.pw2_offset = 0; tmp.lay.hash_offset = 0; tmp.lay.hash_cap = 0;
+    tmp.lay.state_dim = S; tmp.lay.counters_offset = 0; tmp.lay.disc_offset = 0; tmp.lay.ln_offset = 0; tmp.lay.ln_count = 0; tmp.lay.disc_count = 0; tmp.lay.pw1_offset = 0; tmp.lay.pw2_offset = 0; tmp.lay.cumdisc_offset = 0; tmp.lay.hash_offset = 0; tmp.lay.hash_cap = 0;
     return make_params(&tmp).off[O_COUNT];
 }
 
@@ -1281,7 +1327,19 @@ int launch(const CtaParams& p, int nt, bool scripted, cudaStream_t st) {
         cta_search_kernel<ENV, T, true><<<1, nt, smem, st>>>(p);
     } else {
         if (smem) cudaFuncSetAttribute(cta_search_kernel<ENV, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cta_search_kernel<ENV, T, false><<<(unsigned)p.n_trees, nt, smem, st>>>(p);
+        if (p.cluster > 1) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(p.n_trees * p.cluster)); cfg.blockDim = dim3((unsigned)nt);
+            cfg.dynamicSmemBytes = smem; cfg.stream = st;
+            cudaLaunchAttribute attr;
+            attr.id = cudaLaunchAttributeClusterDimension;
+            attr.val.clusterDim.x = (unsigned)p.cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+            cfg.attrs = &attr; cfg.numAttrs = 1;
+            const cudaError_t le = cudaLaunchKernelEx(&cfg, cta_search_kernel<ENV, T, false>, p);
+            if (le != cudaSuccess) return cuda_fail(le, "cta_search_kernel cluster launch");
+        } else {
+            cta_search_kernel<ENV, T, false><<<(unsigned)p.n_trees, nt, smem, st>>>(p);
+        }
     }
     const cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? 0 : cuda_fail(err, "cta_search_kernel launch");
@@ -1313,6 +1371,9 @@ int cta_fill_layout(const isla_config& cfg, isla_layout& lay) {
         set_error("n_actions=%d does not match env (%d)", cfg.n_actions, env_actions); return ISLA_ERR_INVALID;
     }
     if (cfg.expansion != ISLA_EXPAND_RANDOM && cfg.agent != ISLA_AGENT_APW) { set_error("voo / genetic2 expansion are APW options"); return ISLA_ERR_INVALID; }
+    if (cfg.cluster_ctas != 0 && cfg.cluster_ctas != 1 && cfg.cluster_ctas != 2 && cfg.cluster_ctas != 4 && cfg.cluster_ctas != 8) {
+        set_error("cluster_ctas must be 0 (auto), 1, 2, 4 or 8"); return ISLA_ERR_INVALID;
+    }
     if (cfg.expansion < ISLA_EXPAND_RANDOM || cfg.expansion > ISLA_EXPAND_GENETIC) { set_error("unknown expansion %d", cfg.expansion); return ISLA_ERR_INVALID; }
     if (cfg.expansion == ISLA_EXPAND_GENETIC && cfg.voo_n_samples < 1) { set_error("genetic_policy: n_samples must be >= 1"); return ISLA_ERR_INVALID; }
     if (cfg.expansion == ISLA_EXPAND_VOO && (cfg.voo_n_samples < 1 || cfg.voo_n_samples > kMaxRollSmem / 3 || cfg.voo_max_try < 1)) {

@@ -30,23 +30,23 @@ def test_every_declared_symbol_is_exported(lib):
 def test_struct_sizes_match_header(lib):
     import ctypes as C
     from islamcts_b200 import _lib
-    assert C.sizeof(_lib.IslaConfig) == 16 * 4 + 7 * 8 + 3 * 8
+    assert C.sizeof(_lib.IslaConfig) == 18 * 4 + 7 * 8 + 3 * 8
     assert C.sizeof(_lib.IslaLayout) == 6 * 4 + 26 * 8
 
 
 def test_workspace_sizing_and_validation_without_gpu(lib):
     import ctypes as C
     from islamcts_b200 import _lib
-    cfg = _lib.IslaConfig(0, 0, 2, 500, 0, 1, 0, 5, 1000, 0, 1, 0, 1000, 0, 0, 0, 1.0, 0.99, 0, 1, 0, 1, 0.7, 0, 0, 65536)
+    cfg = _lib.IslaConfig(0, 0, 2, 500, 0, 1, 0, 5, 1000, 0, 1, 0, 1000, 0, 0, 0, 0, 0, 1.0, 0.99, 0, 1, 0, 1, 0.7, 0, 0, 65536)
     nbytes = lib.isla_engine_workspace_bytes(C.byref(cfg))
     # 65536 trees x 2004 slots x (32 B record + 16 B state) + path + meta
     assert 6.0e9 < nbytes < 8.0e9
-    bad = _lib.IslaConfig(1, 0, 2, 500, 0, 1, 0, 5, 1000, 0, 1, 0, 1000, 0, 0, 0, 1.0, 0.99, 0, 1, 0, 1, 0.7, 0, 0, 16)
+    bad = _lib.IslaConfig(1, 0, 2, 500, 0, 1, 0, 5, 1000, 0, 1, 0, 1000, 0, 0, 0, 0, 0, 1.0, 0.99, 0, 1, 0, 1, 0.7, 0, 0, 16)
     assert lib.isla_engine_workspace_bytes(C.byref(bad)) == _lib.ERR_INVALID   # vanilla on continuous Pendulum
     assert b"discrete" in lib.isla_last_error()
     # CurveEnv: APW on the 2-D box and vanilla on a DiscreteCurveEnv grid size fine; spw/dpw and oversized grids do not
     def curve(agent, n_actions, g0, g1):
-        return _lib.IslaConfig(4, agent, n_actions, 50, 0, 1, 0, 5, 1000, 0, 2, 0, 1000, 0, g0, g1, 1.0, 0.99, 0.5, 2, 0, 1, 0.7, 0, 0, 8)
+        return _lib.IslaConfig(4, agent, n_actions, 50, 0, 1, 0, 5, 1000, 0, 2, 0, 1000, 0, g0, g1, 0, 0, 1.0, 0.99, 0.5, 2, 0, 1, 0.7, 0, 0, 8)
     assert lib.isla_engine_workspace_bytes(C.byref(curve(1, 0, 0, 0))) > 0
     assert lib.isla_engine_workspace_bytes(C.byref(curve(0, 35, 5, 7))) > 0
     assert lib.isla_engine_workspace_bytes(C.byref(curve(0, 34, 5, 7))) == _lib.ERR_INVALID

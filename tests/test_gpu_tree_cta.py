@@ -170,6 +170,32 @@ def test_voo_tries_evaluated_cta_wide_do_not_depend_on_cta_size():
         assert_tree_equal(out[0], {"tree_" + k: v for k, v in t.serialise().items()}, rtol=1e-9, atol=1e-9)
 
 
+def test_cluster_of_ctas_shares_the_rollouts_bit_identically():
+    """Thread-block clusters (1, 2, 4, 8 CTAs per tree) play slices of the leaf's rollouts; the fixed reduction tree makes
+    the backed-up means -- hence whole trees -- bit-identical, also for partial batches (R not a power of two)."""
+    from islamcts_b200.engine import Engine
+    n_trees, n_sim = 5, 120
+    roots = np.stack([coracle.env_reset(0, 9, i) for i in range(n_trees)])
+    for R in (2048, 1500):
+        out = []
+        for cs, nt in ((1, 512), (2, 512), (4, 256), (8, 512), (0, 0)):
+            e = Engine(0, n_trees=n_trees, sim_capacity=n_sim, max_depth=60, gamma=0.97, precision=1, kernel=2,
+                       rollouts_per_leaf=R, block_threads=nt, cluster_ctas=cs, seed=5)
+            e.set_roots(roots).run(n_sim)
+            assert e.counters()["faults"] == 0
+            na, tot = e.root_stats()
+            out.append((na.cpu().numpy(), tot.cpu().numpy(), e.export_tree(3), e.counters()["rollout_steps"]))
+        for na, tot, tree, steps in out[1:]:
+            np.testing.assert_array_equal(na, out[0][0])
+            np.testing.assert_array_equal(tot, out[0][1])
+            assert steps == out[0][3]
+            for k in tree:
+                np.testing.assert_array_equal(tree[k], out[0][2][k])
+    t = coracle.Tree(coracle.make_config(0, n_actions=2, max_depth=60, C_=1.0, gamma=0.97, rollouts_per_leaf=1500, seed=5, tree_id=3), roots[3])
+    t.run(n_sim)
+    assert_tree_equal(out[0][2], {"tree_" + k: v for k, v in t.serialise().items()}, rtol=1e-9, atol=1e-9)
+
+
 def test_c2_shape_leaf_parallel_4096_matches_oracle():
     """BASELINE C2: one CartPole tree, nsim=1000, max_depth=500, gamma=0.99, 4096 rollouts per leaf."""
     from islamcts_b200.engine import Engine
