@@ -1286,8 +1286,11 @@ CtaParams make_params(const isla_engine* e) {
     // at once; with more trees than that, shared-memory pools cap the CTAs per SM and pools in HBM/L2 with up to 32 CTAs
     // per SM are 3-4x faster (measured: 4096 DiscreteCurveEnv trees 4.8 -> 17.2 M sims/s).
     // leaf-parallel batches beyond one CTA's 512 threads are spread over a thread-block cluster (portable size <= 8)
+    // -- while the clusters of all trees still fit on the SMs at once; batches of many trees are throughput-bound and
+    // run best with one CTA per tree (296 trees x 4096 rollouts: 1.48 M sims/s without clusters, 0.29 M with)
+    const long long sms_ = e->sm_count > 0 ? e->sm_count : 148;
     int cs = e->cfg.cluster_ctas;
-    if (cs <= 0) { cs = 1; while (cs < 8 && p.R > 512 * cs) cs <<= 1; }
+    if (cs <= 0) { cs = 1; while (cs < 8 && p.R > 512 * cs && e->cfg.n_trees * cs * 2 <= sms_) cs <<= 1; }
     int Pw = 1; while (Pw < p.R) Pw <<= 1;
     while (cs > 1 && (Pw / cs) < 1) cs >>= 1;
     p.cluster = cs;
