@@ -72,6 +72,7 @@ struct isla_engine {
     int kernel;
     int sm_count;
     bool roots_set;
+    long long sims_run = 0;   // simulations requested since the last set_roots (bounds the nodes a tree can hold)
 };
 
 namespace isla {

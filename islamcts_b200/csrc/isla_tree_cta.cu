@@ -61,7 +61,9 @@ struct CtaParams {
     const double* disc_table; const double* cum_table; const double* ln_table; const double* pw1_table; const double* pw2_table;
     int ln_count, disc_count;
     int n_sim, max_depth, budget_mode, agent, n_actions, R, expansion, voo_n, voo_max_try, real_bytes;
-    int pool_in_smem;  // the whole tree pool fits in shared memory: search there, copy back at the end
+    int pool_in_smem;  // the tree pool (a compact view sized for this launch) fits in shared memory: search there, copy back at the end
+    long long off_s[24]; long long stride_s;   // array offsets / bytes of that compact view (capacity cap_s nodes)
+    int state_bytes;   // bytes of one env state in the pool
     char* hash_base; long long hash_cap;  // per-tree action hash set (apw/dpw): hash_cap int4 entries per tree, 0 = none
     ActionGrid grid;                       // DiscreteCurveEnv action grid (g0 == 0: not a grid)
     int action_dim;                        // 1, or 2 for the continuous CurveEnv box (second coordinate in a_value2)
@@ -72,21 +74,40 @@ enum : int { O_S_TOTAL = 0, O_S_TERMR, O_S_NS, O_S_FLAGS, O_S_COFF, O_S_CCAP, O_
              O_A_NA, O_A_VISITS, O_A_CHILD, O_IPOOL, O_P_S, O_P_A, O_P_R, O_P_FLAG, O_META, O_P_G, O_A_VALUE2, O_COUNT };
 enum : int { CM_NS = 0, CM_NA = 1, CM_ITOP = 2, CM_SIMS = 3, CM_RNG = 4, CM_FAULT = 5, CM_TRACE_POS = 6, CM_WORDS = 8 };
 
-__device__ __forceinline__ Pool make_pool_at(const CtaParams& p, char* b) {
+__device__ __forceinline__ Pool make_pool_off(const long long* off, char* b) {
     Pool q;
-    q.s_total = (double*)(b + p.off[O_S_TOTAL]); q.s_term_reward = (double*)(b + p.off[O_S_TERMR]);
-    q.s_ns = (int*)(b + p.off[O_S_NS]); q.s_flags = (int*)(b + p.off[O_S_FLAGS]);
-    q.s_coff = (int*)(b + p.off[O_S_COFF]); q.s_ccap = (int*)(b + p.off[O_S_CCAP]); q.s_ccnt = (int*)(b + p.off[O_S_CCNT]);
-    q.s_state = (void*)(b + p.off[O_S_STATE]);
-    q.a_total = (double*)(b + p.off[O_A_TOTAL]); q.a_value = (double*)(b + p.off[O_A_VALUE]);
-    q.a_na = (int*)(b + p.off[O_A_NA]); q.a_visits = (int*)(b + p.off[O_A_VISITS]); q.a_child = (int*)(b + p.off[O_A_CHILD]);
-    q.ipool = (int*)(b + p.off[O_IPOOL]);
-    q.p_s = (int*)(b + p.off[O_P_S]); q.p_a = (int*)(b + p.off[O_P_A]); q.p_r = (double*)(b + p.off[O_P_R]);
-    q.p_flag = (int*)(b + p.off[O_P_FLAG]);
-    q.meta = (int*)(b + p.off[O_META]);
-    q.p_g = (double*)(b + p.off[O_P_G]);
-    q.a_value2 = (double*)(b + p.off[O_A_VALUE2]);
+    q.s_total = (double*)(b + off[O_S_TOTAL]); q.s_term_reward = (double*)(b + off[O_S_TERMR]);
+    q.s_ns = (int*)(b + off[O_S_NS]); q.s_flags = (int*)(b + off[O_S_FLAGS]);
+    q.s_coff = (int*)(b + off[O_S_COFF]); q.s_ccap = (int*)(b + off[O_S_CCAP]); q.s_ccnt = (int*)(b + off[O_S_CCNT]);
+    q.s_state = (void*)(b + off[O_S_STATE]);
+    q.a_total = (double*)(b + off[O_A_TOTAL]); q.a_value = (double*)(b + off[O_A_VALUE]);
+    q.a_na = (int*)(b + off[O_A_NA]); q.a_visits = (int*)(b + off[O_A_VISITS]); q.a_child = (int*)(b + off[O_A_CHILD]);
+    q.ipool = (int*)(b + off[O_IPOOL]);
+    q.p_s = (int*)(b + off[O_P_S]); q.p_a = (int*)(b + off[O_P_A]); q.p_r = (double*)(b + off[O_P_R]);
+    q.p_flag = (int*)(b + off[O_P_FLAG]);
+    q.meta = (int*)(b + off[O_META]);
+    q.p_g = (double*)(b + off[O_P_G]);
+    q.a_value2 = (double*)(b + off[O_A_VALUE2]);
     return q;
+}
+__device__ __forceinline__ Pool make_pool_at(const CtaParams& p, char* b) { return make_pool_off(p.off, b); }
+// Copies the USED part of one tree's pool between its HBM layout (capacity s_cap) and the compact shared-memory view
+// (capacity of this launch): nS state entries, nA action entries, itop child indices and the meta words.  The path
+// arrays are scratch of a launch and are not copied.
+__device__ __forceinline__ void copy_pool(const CtaParams& p, char* dst, const long long* doff, const char* src, const long long* soff,
+                                          int nS, int nA, int itop, int tid, int nt) {
+    auto cp = [&](int idx, long long bytes) {
+        const int4* s4 = reinterpret_cast<const int4*>(src + soff[idx]);
+        int4* d4 = reinterpret_cast<int4*>(dst + doff[idx]);
+        const int n16 = (int)((bytes + 15) >> 4);           // arrays start 256-byte aligned and are padded to 256
+        for (int i = tid; i < n16; i += nt) d4[i] = s4[i];
+    };
+    cp(O_S_TOTAL, nS * 8ll); cp(O_S_TERMR, nS * 8ll); cp(O_S_NS, nS * 4ll); cp(O_S_FLAGS, nS * 4ll);
+    cp(O_S_COFF, nS * 4ll); cp(O_S_CCAP, nS * 4ll); cp(O_S_CCNT, nS * 4ll); cp(O_S_STATE, (long long)nS * p.state_bytes);
+    cp(O_A_TOTAL, nA * 8ll); cp(O_A_VALUE, nA * 8ll); cp(O_A_NA, nA * 4ll); cp(O_A_VISITS, nA * 4ll); cp(O_A_CHILD, nA * 4ll);
+    if (p.action_dim == 2) cp(O_A_VALUE2, nA * 8ll);
+    cp(O_IPOOL, itop * 4ll);
+    cp(O_META, CM_WORDS * 4ll);
 }
 __device__ __forceinline__ Pool make_pool(const CtaParams& p, long long tree) {
     return make_pool_at(p, p.pool_base + tree * p.pool_stride);
@@ -229,7 +250,7 @@ struct Search {
     char* hash;  // this tree's action hash set (apw/dpw), HBM
     unsigned long long c_env = 0, c_roll = 0, c_levels = 0, c_nodes = 0;
 
-    __device__ Search(const CtaParams& p_, long long tree, char* pool_bytes) : p(p_), q(make_pool_at(p_, pool_bytes)) {
+    __device__ Search(const CtaParams& p_, long long tree, char* pool_bytes, bool compact) : p(p_), q(make_pool_off(compact ? p_.off_s : p_.off, pool_bytes)) {
         hash = p.hash_base + tree * p.hash_cap * 16;
         lane = threadIdx.x & 31;
         nS = q.meta[CM_NS]; nA = q.meta[CM_NA]; itop = q.meta[CM_ITOP]; fault = q.meta[CM_FAULT];
@@ -746,12 +767,12 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
     extern __shared__ int4 pool_smem[];
     char* const pool_global = p.pool_base + tree * p.pool_stride;
     if (p.pool_in_smem && owner) {
-        const int n16 = (int)(p.pool_stride >> 4);
-        const int4* src = reinterpret_cast<const int4*>(pool_global);
-        for (int i = tid; i < n16; i += nt) pool_smem[i] = src[i];
+        const int* gm = reinterpret_cast<const int*>(pool_global + p.off[O_META]);
+        copy_pool(p, reinterpret_cast<char*>(pool_smem), p.off_s, pool_global, p.off, gm[CM_NS], gm[CM_NA], gm[CM_ITOP], tid, nt);
         __syncthreads();
     }
-    Search<ENV, T, SCRIPTED> ctx(p, tree, (p.pool_in_smem && owner) ? reinterpret_cast<char*>(pool_smem) : pool_global);
+    Search<ENV, T, SCRIPTED> ctx(p, tree, (p.pool_in_smem && owner) ? reinterpret_cast<char*>(pool_smem) : pool_global,
+                                 p.pool_in_smem && owner);
     const RollShared* const sh0 = CS > 1 ? cg::this_cluster().map_shared_rank(&sh, 0) : &sh;   // the owner's leaf record
     uint32_t sims_done = (uint32_t)ctx.q.meta[CM_SIMS];
     int s_done = 0;
@@ -1085,9 +1106,8 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
     }
     if (copy_back) {
         __syncthreads();
-        const int n16 = (int)(p.pool_stride >> 4);
-        int4* dst = reinterpret_cast<int4*>(pool_global);
-        for (int i = tid; i < n16; i += nt) dst[i] = pool_smem[i];
+        const int* sm = reinterpret_cast<const int*>(reinterpret_cast<char*>(pool_smem) + p.off_s[O_META]);
+        copy_pool(p, pool_global, p.off, reinterpret_cast<const char*>(pool_smem), p.off_s, sm[CM_NS], sm[CM_NA], sm[CM_ITOP], tid, nt);
     }
 }
 
@@ -1249,25 +1269,40 @@ __global__ void __launch_bounds__(256) cta_depth_stats_kernel(const CtaParams p,
     for (int i = tid; i < n_root && i < cap; i += nt) dmean[i] = leaves[i] ? __ddiv_rn(dmean[i], (double)leaves[i]) : 0.0;
 }
 
-CtaParams make_params(const isla_engine* e) {
+// byte offsets of the SoA arrays of one tree's pool for a capacity of `cap` state / action nodes; returns the pool size
+static long long pool_layout(long long cap, int state_dim, int rb, int action_dim, long long* o) {
+    long long off = 0;
+    const long long i_cap = 2 * cap + 4 * cap + 64;
+    auto take = [&](int idx, long long bytes) { o[idx] = off; off = (off + bytes + 255) / 256 * 256; };
+    take(O_S_TOTAL, cap * 8); take(O_S_TERMR, cap * 8); take(O_S_NS, cap * 4); take(O_S_FLAGS, cap * 4);
+    take(O_S_COFF, cap * 4); take(O_S_CCAP, cap * 4); take(O_S_CCNT, cap * 4); take(O_S_STATE, cap * state_dim * rb);
+    take(O_A_TOTAL, cap * 8); take(O_A_VALUE, cap * 8); take(O_A_NA, cap * 4); take(O_A_VISITS, cap * 4);
+    take(O_A_CHILD, cap * 4); take(O_IPOOL, i_cap * 4);
+    take(O_P_S, cap * 4); take(O_P_A, cap * 4); take(O_P_R, cap * 8); take(O_P_FLAG, cap * 4);
+    take(O_META, CM_WORDS * 4);
+    take(O_P_G, cap * 8);
+    take(O_A_VALUE2, action_dim == 2 ? cap * 8 : 0);
+    o[O_COUNT] = off;
+    return off;
+}
+
+// n_sim_launch: simulations of the launch being prepared (0: not a search launch).  The shared-memory view of a pool is
+// sized for the nodes that can exist at the END of that launch (<= 2 + simulations run since set_roots + n_sim_launch),
+// not for the engine's capacity, so a tree keeps living in shared memory while it is small even if the engine was
+// sized for many more simulations.
+CtaParams make_params(const isla_engine* e, int n_sim_launch = 0) {
     CtaParams p;
     const isla_layout& L = e->lay;
     p.pool_base = e->ws + L.pool_offset; p.pool_stride = L.pool_stride;
     p.s_cap = L.s_cap; p.a_cap = L.a_cap; p.i_cap = 2 * L.a_cap + 4 * L.s_cap + 64;
     const int rb = L.real_bytes;
-    long long off = 0;
-    auto take = [&](int idx, long long bytes) { p.off[idx] = off; off = (off + bytes + 255) / 256 * 256; };
-    take(O_S_TOTAL, L.s_cap * 8); take(O_S_TERMR, L.s_cap * 8); take(O_S_NS, L.s_cap * 4); take(O_S_FLAGS, L.s_cap * 4);
-    take(O_S_COFF, L.s_cap * 4); take(O_S_CCAP, L.s_cap * 4); take(O_S_CCNT, L.s_cap * 4); take(O_S_STATE, L.s_cap * L.state_dim * rb);
-    take(O_A_TOTAL, L.a_cap * 8); take(O_A_VALUE, L.a_cap * 8); take(O_A_NA, L.a_cap * 4); take(O_A_VISITS, L.a_cap * 4);
-    take(O_A_CHILD, L.a_cap * 4); take(O_IPOOL, p.i_cap * 4);
-    take(O_P_S, L.s_cap * 4); take(O_P_A, L.s_cap * 4); take(O_P_R, L.s_cap * 8); take(O_P_FLAG, L.s_cap * 4);
-    take(O_META, CM_WORDS * 4);
-    take(O_P_G, L.s_cap * 8);
     p.grid = ActionGrid{e->cfg.env_id == ISLA_ENV_CURVE ? e->cfg.action_grid0 : 0, e->cfg.env_id == ISLA_ENV_CURVE ? e->cfg.action_grid1 : 0};
     p.action_dim = (e->cfg.env_id == ISLA_ENV_CURVE && p.grid.g0 == 0) ? 2 : 1;
-    take(O_A_VALUE2, p.action_dim == 2 ? L.a_cap * 8 : 0);
-    p.off[O_COUNT] = off;
+    p.state_bytes = L.state_dim * rb;
+    long long off = pool_layout(L.s_cap, L.state_dim, rb, p.action_dim, p.off);
+    long long cap_s = e->sims_run + (long long)n_sim_launch + 2;
+    if (cap_s > L.s_cap) cap_s = L.s_cap;
+    p.stride_s = pool_layout(cap_s, L.state_dim, rb, p.action_dim, p.off_s);
     p.counters = (unsigned long long*)(e->ws + L.counters_offset);
     p.trace_kinds = nullptr; p.trace_values = nullptr; p.trace_len = 0;
     p.n_trees = e->cfg.n_trees; p.scripted_tree = -1;
@@ -1294,7 +1329,8 @@ CtaParams make_params(const isla_engine* e) {
     int Pw = 1; while (Pw < p.R) Pw <<= 1;
     while (cs > 1 && (Pw / cs) < 1) cs >>= 1;
     p.cluster = cs;
-    const long long fit_per_sm = off > 0 ? (190 * 1024) / off : 0;
+    (void)off;
+    const long long fit_per_sm = p.stride_s > 0 ? (190 * 1024) / p.stride_s : 0;
     const long long sms = e->sm_count > 0 ? e->sm_count : 148;
     // (every CTA of a launch reserves the dynamic shared memory, the cluster's helper CTAs included)
     p.pool_in_smem = (fit_per_sm >= 1 && e->cfg.n_trees * cs <= sms * fit_per_sm && !(e->cfg.tuning & 16)) ? 1 : 0;
@@ -1324,7 +1360,7 @@ int pick_threads(const isla_config& cfg) {
 
 template <int ENV, typename T>
 int launch(const CtaParams& p, int nt, bool scripted, cudaStream_t st) {
-    const size_t smem = p.pool_in_smem ? (size_t)p.pool_stride : 0;
+    const size_t smem = p.pool_in_smem ? (size_t)p.stride_s : 0;
     if (scripted) {
         if (smem) cudaFuncSetAttribute(cta_search_kernel<ENV, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cta_search_kernel<ENV, T, true><<<1, nt, smem, st>>>(p);
@@ -1400,6 +1436,7 @@ int cta_fill_layout(const isla_config& cfg, isla_layout& lay) {
 }
 
 int cta_set_roots(isla_engine* e, const double* roots_dev, cudaStream_t st) {
+    e->sims_run = 0;
     CtaParams p = make_params(e);
     ISLA_CUDA_OK(cudaMemsetAsync(e->ws + e->lay.counters_offset, 0, 64, st));
     if (e->lay.hash_cap > 0)  // empty hash sets: state field < 0
@@ -1413,7 +1450,8 @@ int cta_set_roots(isla_engine* e, const double* roots_dev, cudaStream_t st) {
 
 int cta_run(isla_engine* e, int n_sim, long long scripted_tree, const uint8_t* kinds, const double* values,
             long long trace_len, cudaStream_t st) {
-    CtaParams p = make_params(e);
+    CtaParams p = make_params(e, n_sim);
+    e->sims_run += n_sim;
     p.n_sim = n_sim; p.scripted_tree = scripted_tree; p.trace_kinds = kinds; p.trace_values = values; p.trace_len = trace_len;
     const bool scripted = scripted_tree >= 0;
     if (scripted && p.R != 1) { set_error("scripted runs need rollouts_per_leaf == 1"); return ISLA_ERR_INVALID; }
