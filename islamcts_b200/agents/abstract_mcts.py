@@ -302,7 +302,19 @@ class AbstractMcts:
         self.q_values = tot / na
 
     def _finish_ensemble(self, eng):
-        """Root-parallel ensemble (n_trees > 1, discrete agents): root statistics summed over the trees."""
+        """Root-parallel ensemble (n_trees > 1): root statistics summed over the trees (discrete agents), or the union of
+        the trees' root children (continuous agents: every tree sampled its own actions)."""
+        if not self.DISCRETE:
+            from .. import sharding
+            rows = [eng.root_children(i) for i in range(eng.n_trees)]
+            a = torch.as_tensor(np.concatenate([np.asarray(r[0]).reshape(len(r[1]), -1) for r in rows]))
+            na = torch.as_tensor(np.concatenate([r[1] for r in rows]))
+            tot = torch.as_tensor(np.concatenate([r[2] for r in rows]))
+            ma, mna, mtot = sharding.merge_root_children(a, na, tot)
+            self.root_statistics = dict(action=ma.numpy(), na=mna.numpy(), total=mtot.numpy())
+            self.q_values = self.root_statistics["total"] / self.root_statistics["na"]
+            i, row = sharding.pick_continuous(ma, mna, mtot)
+            return self._format_action(i, row.numpy())
         from ..engine import merge_root_stats
         na, tot = eng.root_stats()
         group = torch.zeros(eng.n_trees, dtype=torch.int32, device=na.device)   # every tree shares the one root

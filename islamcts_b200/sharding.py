@@ -46,3 +46,53 @@ def pick(mna: torch.Tensor, mtot: torch.Tensor) -> torch.Tensor:
     """q = total/na per root and its arg-max (end of fit(), mcts_hash.py:42-50) on the merged statistics."""
     q = torch.where(mna > 0, mtot / mna.clamp(min=1).to(torch.float64), torch.full_like(mtot, -float("inf")))
     return q.argmax(dim=1).to(torch.int32)
+
+
+# ---------------------------------------------------------------- continuous-action agents (apw / dpw)
+# Every tree samples its own root actions, so the root children of the trees of one root are LISTS that differ per
+# tree: the merge is a union (SURVEY 8e), not a dense sum -- locally over a rank's trees, then one all-gather.
+
+def merge_root_children(actions: torch.Tensor, na: torch.Tensor, total: torch.Tensor):
+    """Union of root-children lists: rows of `actions` [n, action_dim] that are bit-equal (the centre / bounds genetic
+    expansions add to every tree, duplicates of a sample) are summed; order = first appearance.  Returns the merged
+    (actions, na:int64, total:float64)."""
+    actions = actions.reshape(len(na), -1).to(torch.float64)
+    if len(na) == 0:
+        return actions, na.to(torch.int64), total.to(torch.float64)
+    uniq, inverse = torch.unique(actions, dim=0, return_inverse=True)
+    first = torch.full((len(uniq),), len(na), dtype=torch.int64, device=actions.device)
+    first = first.scatter_reduce(0, inverse, torch.arange(len(na), device=actions.device), reduce="amin")
+    order = torch.argsort(first)
+    mna = torch.zeros(len(uniq), dtype=torch.int64, device=actions.device).index_add_(0, inverse, na.to(torch.int64))
+    mtot = torch.zeros(len(uniq), dtype=torch.float64, device=actions.device).index_add_(0, inverse, total.to(torch.float64))
+    return uniq[order], mna[order], mtot[order]
+
+
+def all_gather_root_children(actions: torch.Tensor, na: torch.Tensor, total: torch.Tensor, group=None):
+    """The exchange step for continuous-action agents: every rank contributes its (already locally merged) root children
+    (actions [n_r, action_dim], na [n_r], total [n_r]); all ranks receive the union in rank order, merged again."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    actions = actions.reshape(len(na), -1).to(torch.float64)
+    ad = actions.shape[1]
+    cnt = torch.tensor([len(na), ad], dtype=torch.int64, device=actions.device)
+    cnts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(cnts, cnt, group=group)
+    ad = int(max(int(c[1]) for c in cnts))              # a rank without children still needs the row width
+    m = int(max(int(c[0]) for c in cnts))
+    packed = torch.zeros((max(m, 1), ad + 2), dtype=torch.float64, device=actions.device)
+    if len(na):
+        packed[: len(na), :ad] = actions
+        packed[: len(na), ad] = na.to(torch.float64)    # exact: visit counts are far below 2**53
+        packed[: len(na), ad + 1] = total.to(torch.float64)
+    parts = [torch.zeros_like(packed) for _ in range(world)]
+    dist.all_gather(parts, packed, group=group)
+    rows = torch.cat([parts[r][: int(cnts[r][0])] for r in range(world)], dim=0)
+    return merge_root_children(rows[:, :ad], rows[:, ad].to(torch.int64), rows[:, ad + 1])
+
+
+def pick_continuous(actions: torch.Tensor, na: torch.Tensor, total: torch.Tensor):
+    """arg-max q over the merged children (first maximum); returns (index, action row)."""
+    q = total / na.clamp(min=1).to(torch.float64)
+    i = int(torch.argmax(q).item())
+    return i, actions[i]

@@ -69,3 +69,55 @@ def test_plan_arithmetic():
     assert (np.bincount(p.group) == 256).all()
     with pytest.raises(ValueError):
         sharding.plan(0, 2, 10, 3)
+
+
+def _worker_children(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from islamcts_b200 import sharding
+    from oracle import coracle
+    # two APW trees per rank on the same Pendulum root (the oracle stands in for the device search); genetic2 adds the
+    # same centre / bound actions to every tree, so the union has rows to sum
+    root = coracle.env_reset(1, 3, 0)
+    acts, nas, tots = [], [], []
+    for t in range(2):
+        tree = coracle.Tree(coracle.make_config(1, agent=1, max_depth=20, C_=2.0, gamma=0.95, alpha1=0.5, k1=2.0, expansion=2,
+                                                epsilon=0.5, seed=4, tree_id=rank * 2 + t), root)
+        tree.run(60 if rank == 0 else 25)      # ranks end up with different numbers of children
+        a, na, tot = tree.root_children()
+        acts.append(a); nas.append(na); tots.append(tot)
+    la, lna, ltot = sharding.merge_root_children(torch.as_tensor(np.concatenate(acts))[:, None], torch.as_tensor(np.concatenate(nas)),
+                                                 torch.as_tensor(np.concatenate(tots)))
+    ga, gna, gtot = sharding.all_gather_root_children(la, lna, ltot, dist.group.WORLD)
+    q.put((rank, np.concatenate(acts), np.concatenate(nas), np.concatenate(tots), ga.numpy(), gna.numpy(), gtot.numpy()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_union_of_continuous_root_children():
+    world, port = 2, 29731 + os.getpid() % 200
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_children, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted((q.get(timeout=120) for _ in range(world)), key=lambda o: o[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # expected union: python dict keyed by the action's bytes, rank order then tree order then insertion order
+    exp = {}
+    for o in out:
+        for a, n, t in zip(o[1], o[2], o[3]):
+            k = np.float64(a).tobytes()
+            if k not in exp:
+                exp[k] = [float(a), 0, 0.0]
+            exp[k][1] += int(n); exp[k][2] += float(t)
+    ea = np.array([v[0] for v in exp.values()]); en = np.array([v[1] for v in exp.values()]); et = np.array([v[2] for v in exp.values()])
+    assert len(ea) < sum(len(o[1]) for o in out)        # some actions were shared between trees
+    for o in out:                                        # every rank holds the same union
+        np.testing.assert_array_equal(o[4][:, 0], ea)
+        np.testing.assert_array_equal(o[5], en)
+        np.testing.assert_allclose(o[6], et, rtol=1e-12)
+    assert en.sum() == 2 * 60 + 2 * 25

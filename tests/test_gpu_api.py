@@ -275,3 +275,25 @@ def test_root_proxies_serve_sweep_metrics_from_device_analytics():
             assert n.na == full.actions[k].na and n.total == full.actions[k].total
             assert sorted(n.get_depth_mean(0)) == sorted(full.actions[k].get_depth_mean(0))
         assert root.ns == 500 and dmax >= 1 and dmean >= 1
+
+
+def test_apw_ensemble_unions_the_trees_root_children():
+    """n_trees > 1 for a continuous-action agent: every tree samples its own root actions; fit() returns the arg-max over
+    the union of the trees' root children (equal actions summed)."""
+    from islamcts_b200 import envs
+    from islamcts_b200.agents import MctsApw
+    from islamcts_b200.agents.parameters.pw_parameters import PwParameters
+    from islamcts_b200.utils.action_selection_functions import continuous_default_policy, genetic_policy2, ucb1
+    env = envs.make("Pendulum-v1", api=4, seed=2); obs = env.reset()
+    p = PwParameters(root_data=obs, env=env, n_sim=200, C=2, action_selection_fn=ucb1, gamma=0.95, max_depth=30,
+                     rollout_selection_fn=continuous_default_policy, n_actions=None, alpha=0.5, k=2,
+                     action_expansion_function=genetic_policy2(0.5, continuous_default_policy), n_trees=6, seed=9)
+    agent = MctsApw(p)
+    a = agent.fit()
+    st = agent.root_statistics
+    assert a.shape == (1,) and st["na"].sum() == 6 * 200
+    assert len(np.unique(st["action"])) == len(st["action"])           # merged: no duplicates left
+    per_tree = sum(len(agent._engine.root_children(i)[1]) for i in range(6))
+    assert len(st["action"]) <= per_tree - 3 * 5                       # centre and both bounds exist in all 6 trees: summed
+    best = int(np.argmax(st["total"] / st["na"]))
+    assert float(a[0]) == float(st["action"][best, 0])
