@@ -807,14 +807,36 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                             else {
                                 const int ns = q.s_ns[sl];
                                 const double lg = ns < p.ln_count ? p.ln_table[ns] : ::log((double)ns);
-                                double best = -INFINITY; int arg = -1, ties = 0;
-                                for (int i = 0; i < n; ++i) {
-                                    const int a = q.ipool[off + i];
-                                    const double na = (double)q.a_na[a];
-                                    const double sc = __dadd_rn(__ddiv_rn(q.a_total[a], na), __dmul_rn(p.C, __dsqrt_rn(__ddiv_rn(lg, na))));
-                                    if (sc > best) { best = sc; arg = a; ties = 1; } else if (sc == best) ++ties;
+                                // fp32 screening (MUFU approximations, error ~1e-6 of the score magnitude): a gap above
+                                // 1e-5 of that magnitude between the two largest scores settles the arg-max; only
+                                // near-ties pay for the float64 scores, so the decision is always the float64 one
+                                bool decided = false;
+                                {
+                                    const float lgf = (float)lg, Cf = (float)p.C;
+                                    float top = -INFINITY, second = -INFINITY, scale = 0.f; int argf = -1;
+                                    for (int i = 0; i < n; ++i) {
+                                        const int a = q.ipool[off + i];
+                                        float rn, ef;
+                                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rn) : "f"((float)q.a_na[a]));
+                                        const float qf = (float)q.a_total[a] * rn;
+                                        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(ef) : "f"(lgf * rn));
+                                        ef *= Cf;
+                                        const float sc = qf + ef;
+                                        scale = fmaxf(scale, fabsf(qf) + fabsf(ef));
+                                        if (sc > top) { second = top; top = sc; argf = a; } else second = fmaxf(second, sc);
+                                    }
+                                    if (top - second > 1e-5f * scale + 1e-30f) { decided = true; my_event = argf != al; }
                                 }
-                                my_event = (ties != 1) || (arg != al);
+                                if (!decided) {
+                                    double best = -INFINITY; int arg = -1, ties = 0;
+                                    for (int i = 0; i < n; ++i) {
+                                        const int a = q.ipool[off + i];
+                                        const double na = (double)q.a_na[a];
+                                        const double sc = __dadd_rn(__ddiv_rn(q.a_total[a], na), __dmul_rn(p.C, __dsqrt_rn(__ddiv_rn(lg, na))));
+                                        if (sc > best) { best = sc; arg = a; ties = 1; } else if (sc == best) ++ties;
+                                    }
+                                    my_event = (ties != 1) || (arg != al);
+                                }
                             }
                         }
                         const unsigned ev = __ballot_sync(kFull, my_event);
