@@ -374,6 +374,34 @@ struct Search {
             for (int k = 0; k < pos; ++k) bb &= bb - 1;
             return __ffs(bb) - 1;
         }
+        {   // wide node: fp32 screening first (MUFU approximations, error ~1e-6 of the score magnitude).  A gap above 1e-5
+            // of that magnitude between the two largest scores settles the arg-max without the float64 passes.
+            const float lgf = (float)lg, Cf = (float)p.C;
+            float top = -INFINITY, second = -INFINITY, scale = 0.f; int arg = -1;
+            for (int i = lane; i < n; i += 32) {
+                const int a = q.ipool[off + i];
+                float rn, ef;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rn) : "f"((float)q.a_na[a]));
+                const float qf = (float)q.a_total[a] * rn;
+                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(ef) : "f"(lgf * rn));
+                ef *= Cf;
+                const float sc = qf + ef;
+                scale = fmaxf(scale, fabsf(qf) + fabsf(ef));
+                if (sc > top) { second = top; top = sc; arg = i; } else second = fmaxf(second, sc);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ot = __shfl_xor_sync(kFull, top, o), os = __shfl_xor_sync(kFull, second, o);
+                const int oa = __shfl_xor_sync(kFull, arg, o);
+                scale = fmaxf(scale, __shfl_xor_sync(kFull, scale, o));
+                if (ot > top) { second = fmaxf(top, os); top = ot; arg = oa; }
+                else { second = fmaxf(second, ot); }      // ot <= top: an equal top leaves the gap at 0 (undecided)
+            }
+            if (top - second > 1e-5f * scale + 1e-30f) {
+                if constexpr (SCRIPTED) (void)choice(1);   // the reference still draws among its single candidate
+                return arg;
+            }
+        }
         double best = -INFINITY;
         for (int i = lane; i < n; i += 32) best = fmax(best, score(i));
         best = warp_max(best);
