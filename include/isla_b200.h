@@ -127,6 +127,11 @@ int isla_engine_layout(const isla_engine* e, isla_layout* out);
  * sweep.py:186-189). */
 int isla_engine_set_roots(isla_engine* e, const double* roots_dev, void* stream);
 
+/* param.rollout_selection_fn = grid_policy(prior_knowledge, n_actions) (utils/action_selection_functions.py:258-282;
+ * examples/example_lake.py:56-66): rollouts on ISLA_ENV_FROZENLAKE take an arg-min of table_host[cell][action] (HOST
+ * doubles, [16][4], lower = better), ties broken uniformly.  NULL restores env.action_space.sample().  Synchronous. */
+int isla_engine_set_rollout_heuristic(isla_engine* e, const double* table_host, int32_t n_states, int32_t n_actions);
+
 /* fit(): the `for s in range(n_sim)` loop (mcts.py:24-27, mcts_hash.py:30-34, mcts_action_...:25-30,
  * mcts_state_...:23-26, mcts_double_...:24-27) for all trees.  Calling it again continues the trees. */
 int isla_engine_run(isla_engine* e, int32_t n_sim, void* stream);

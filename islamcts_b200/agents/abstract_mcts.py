@@ -221,8 +221,12 @@ class AbstractMcts:
         p = self.param
         if _kind(p.action_selection_fn, "action_selection_fn") != "ucb1":
             raise NotImplementedError("action_selection_fn must be ucb1")
-        if _kind(p.rollout_selection_fn, "rollout_selection_fn") != "random":
-            raise NotImplementedError("rollout_selection_fn must be continuous_default_policy (env.action_space.sample())")
+        rk = _kind(p.rollout_selection_fn, "rollout_selection_fn")
+        if rk == "grid" and env_id != _lib.ENV_FROZENLAKE:
+            raise NotImplementedError("grid_policy reads env.s: FrozenLake only (utils/action_selection_functions.py:271-272)")
+        if rk not in ("random", "grid"):
+            raise NotImplementedError("rollout_selection_fn must be continuous_default_policy (env.action_space.sample()) "
+                                      "or grid_policy(...)")
         if p.depth_mode not in ("budgeted", "reference_head"):
             raise ValueError("depth_mode must be 'budgeted' or 'reference_head'")
         zero = p.depth_mode == "reference_head" and self.HEAD_ZERO_ROLLOUTS
@@ -258,6 +262,8 @@ class AbstractMcts:
         seed = p.seed if p.seed is not None else int(np.random.randint(0, 2**31 - 1))
         self._capacity = max(4 * int(p.n_sim), 64)
         self._engine = Engine(env_id, sim_capacity=self._capacity, seed=seed, **kw)
+        if _kind(p.rollout_selection_fn, "rollout_selection_fn") == "grid":
+            self._engine.set_rollout_heuristic(p.rollout_selection_fn.table)
         self._engine.set_roots(np.tile(root_state[None, :], (int(p.n_trees), 1)))
         self._engine_key = key
         self._sims_done = 0

@@ -164,7 +164,25 @@ int isla_engine_create(const isla_config* cfg, void* workspace_dev, int64_t work
     return ISLA_OK;
 }
 
-int isla_engine_destroy(isla_engine* e) { delete e; return ISLA_OK; }
+int isla_engine_destroy(isla_engine* e) {
+    if (e && e->heur_dev) cudaFree(e->heur_dev);
+    delete e;
+    return ISLA_OK;
+}
+
+int isla_engine_set_rollout_heuristic(isla_engine* e, const double* table_host, int32_t n_states, int32_t n_actions) {
+    if (!e) { set_error("null engine"); return ISLA_ERR_INVALID; }
+    if (!table_host) {
+        if (e->heur_dev) { ISLA_CUDA_OK(cudaDeviceSynchronize()); cudaFree(e->heur_dev); e->heur_dev = nullptr; }
+        return ISLA_OK;
+    }
+    if (e->cfg.env_id != ISLA_ENV_FROZENLAKE || n_states != 16 || n_actions != 4) {
+        set_error("grid_policy: only FrozenLake (16 states x 4 actions) has a heuristic rollout on the device"); return ISLA_ERR_INVALID;
+    }
+    if (!e->heur_dev) ISLA_CUDA_OK(cudaMalloc((void**)&e->heur_dev, 16 * 4 * sizeof(double)));
+    ISLA_CUDA_OK(cudaMemcpy(e->heur_dev, table_host, 16 * 4 * sizeof(double), cudaMemcpyHostToDevice));
+    return ISLA_OK;
+}
 
 int isla_engine_layout(const isla_engine* e, isla_layout* out) {
     if (!e || !out) { set_error("null argument"); return ISLA_ERR_INVALID; }

@@ -385,10 +385,34 @@ __device__ __forceinline__ T sample_action(Stream& st) {
     }
 }
 
+// grid_policy (utils/action_selection_functions.py:258-282): an arg-min of the prior knowledge of the current cell;
+// `pos_of(ties)` picks among the tied minima (np.random.choice)
+template <typename PosFn>
+__device__ __forceinline__ int lake_heuristic_action(const double* __restrict__ table, int cell, PosFn pos_of) {
+    double ks[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) ks[a] = __ldg(table + cell * 4 + a);
+    const double m = fmin(fmin(ks[0], ks[1]), fmin(ks[2], ks[3]));
+    int ties = 0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) ties += (ks[a] == m);
+    int pos = pos_of(ties), pick = 0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) if (ks[a] == m) { if (pos == 0) pick = a; --pos; }
+    return pick;
+}
+
 // One random-policy rollout step: action_space.sample() from the stream, then env.step
 // (agents/abstract_mcts.py:84-85).  CurveEnv samples Box([-5,-30],[5,30], float64) or Discrete(g0*g1).
 template <int ENV, typename T>
-__device__ __forceinline__ bool rollout_step(Stream& st, T (&s)[EnvTraits<ENV>::S], ActionGrid g, T& reward) {
+__device__ __forceinline__ bool rollout_step(Stream& st, T (&s)[EnvTraits<ENV>::S], ActionGrid g, T& reward,
+                                             const double* heur = nullptr) {
+    if constexpr (ENV == ENV_FROZENLAKE) {
+        if (heur) {   // rollout_selection_fn = grid_policy: one stream word only when several actions tie
+            const int a = lake_heuristic_action(heur, (int)s[0], [&](int ties) { return ties > 1 ? (int)mulhi_u32(st.next(), (uint32_t)ties) : 0; });
+            return Env<ENV, T>::step(s, T(a), reward);
+        }
+    }
     if constexpr (ENV == ENV_CURVE) {
         double a0, a1;
         if (g.g0 > 0) {

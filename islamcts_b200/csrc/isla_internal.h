@@ -61,6 +61,7 @@ struct TptParams {
     const double* disc_table;  // host-computed gamma**t
     const double* cum_table;   // host-computed sum_{t<n} gamma**t (left-to-right)
     int n_sim, max_depth, budget_mode, block_cap, ln_count, disc_count, ln_in_smem, tuning;
+    const double* heur;        // grid_policy table (FrozenLake), nullptr = random rollouts
 };
 
 }  // namespace isla
@@ -73,6 +74,7 @@ struct isla_engine {
     int sm_count;
     bool roots_set;
     long long sims_run = 0;   // simulations requested since the last set_roots (bounds the nodes a tree can hold)
+    double* heur_dev = nullptr;   // grid_policy prior knowledge [16][4] (engine-owned), nullptr = random rollouts
 };
 
 namespace isla {

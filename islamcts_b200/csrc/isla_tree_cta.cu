@@ -68,6 +68,7 @@ struct CtaParams {
     ActionGrid grid;                       // DiscreteCurveEnv action grid (g0 == 0: not a grid)
     int action_dim;                        // 1, or 2 for the continuous CurveEnv box (second coordinate in a_value2)
     int cluster;                           // CTAs (one thread-block cluster) sharing one tree's leaf-parallel rollouts
+    const double* heur;                    // grid_policy table (FrozenLake rollouts), nullptr = random rollouts
 };
 
 enum : int { O_S_TOTAL = 0, O_S_TERMR, O_S_NS, O_S_FLAGS, O_S_COFF, O_S_CCAP, O_S_CCNT, O_S_STATE, O_A_TOTAL, O_A_VALUE,
@@ -1039,8 +1040,11 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                     for (int i = 0; i < S; ++i) st[i] = T(sh.leaf[i]);
                     double Rr = 0.0; int t = 0; bool done = false;
                     while (!done && t < budget && !ctx.tc.fault) {
-                        double act2;
-                        const double act = ctx.tree_action(act2);
+                        double act2 = 0.0, act;
+                        bool heuristic = false;
+                        if constexpr (ENV == ENV_FROZENLAKE) heuristic = p.heur != nullptr;
+                        if (heuristic) act = (double)lake_heuristic_action(p.heur, (int)st[0], [&](int ties) { return ctx.choice(ties); });
+                        else act = ctx.tree_action(act2);
                         if (ctx.tc.fault) break;
                         T rr;
                         done = env_step_action<ENV, T>(st, act, act2, p.grid, rr);
@@ -1072,7 +1076,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                             int t = 0; bool done = false;
                             T rr = T(0);
                             while (!done && t < budget) {
-                                done = rollout_step<ENV, T>(rs, st, p.grid, rr);
+                                done = rollout_step<ENV, T>(rs, st, p.grid, rr, p.heur);
                                 // r * pow(gamma, t) summed left to right (abstract_mcts.py:87); envs with a constant
                                 // interior reward take the bit-identical closed form from the host prefix table below
                                 if constexpr (!Rewards<ENV>::kClosedForm) Rr = __dadd_rn(Rr, __dmul_rn((double)rr, __ldg(p.disc_table + t)));
@@ -1385,6 +1389,7 @@ CtaParams make_params(const isla_engine* e, int n_sim_launch = 0) {
     // (every CTA of a launch reserves the dynamic shared memory, the cluster's helper CTAs included)
     p.pool_in_smem = (fit_per_sm >= 1 && e->cfg.n_trees * cs <= sms * fit_per_sm && !(e->cfg.tuning & 16)) ? 1 : 0;
     p.hash_base = e->ws ? e->ws + L.hash_offset : nullptr; p.hash_cap = L.hash_cap;
+    p.heur = e->heur_dev;
     return p;
 }
 

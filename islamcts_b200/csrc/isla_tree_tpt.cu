@@ -721,7 +721,19 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
             while (__any_sync(kFull, go)) {
                 if (go) {
                     T act;
-                    if constexpr (SCRIPTED) {
+                    bool heuristic = false;
+                    if constexpr (ENV == ENV_FROZENLAKE) heuristic = p.heur != nullptr;
+                    if (heuristic) {   // rollout_selection_fn = grid_policy (utils/action_selection_functions.py:258-282)
+                        act = T(lake_heuristic_action(p.heur, (int)st[0], [&](int ties) -> int {
+                            if constexpr (SCRIPTED) {
+                                const int v = (int)tc.take(ISLA_K_CHOICE);
+                                if (v < 0 || v >= ties) { if (!tc.fault) tc.fault = ISLA_ERR_TRACE; return 0; }
+                                return v;
+                            } else {
+                                return ties > 1 ? (int)mulhi_u32(rs.next(), (uint32_t)ties) : 0;
+                            }
+                        }));
+                    } else if constexpr (SCRIPTED) {
                         const int v = (int)tc.take(ISLA_K_SAMPLE_D);
                         if (v < 0 || v >= A) { if (!tc.fault) tc.fault = ISLA_ERR_TRACE; }
                         act = T(tc.fault ? 0 : v);
@@ -984,7 +996,8 @@ int tpt_run(isla_engine* e, int n_sim, long long scripted_tree, const uint8_t* k
     p.disc_table = (const double*)(e->ws + L.disc_offset);
     p.cum_table = (const double*)(e->ws + L.cumdisc_offset);
     p.ln_count = (int)L.ln_count; p.disc_count = (int)L.disc_count;
-    p.ln_in_smem = (L.ln_count * 4 <= 8 * 1024) ? 1 : 0;   // float copy of ln(n) next to the cooperative ring
+    p.ln_in_smem = (L.ln_count * 4 <= 8 * 1024) ? 1 : 0;
+    p.heur = e->heur_dev;   // float copy of ln(n) next to the cooperative ring
     p.tuning = e->cfg.tuning;
     const bool scripted = scripted_tree >= 0;
     const bool f64 = e->cfg.precision == ISLA_PRECISION_F64;

@@ -109,6 +109,16 @@ class Engine:
         self._roots = t
         return self
 
+    def set_rollout_heuristic(self, table):
+        """grid_policy prior knowledge [16, 4] (lower = better) for FrozenLake rollouts; None = random rollouts."""
+        if table is None:
+            check(self.lib.isla_engine_set_rollout_heuristic(self._h, None, 0, 0))
+            return self
+        tb = np.ascontiguousarray(table, dtype=np.float64)
+        with torch.cuda.device(self.device):
+            check(self.lib.isla_engine_set_rollout_heuristic(self._h, tb.ctypes.data_as(C.c_void_p), tb.shape[0], tb.shape[1]))
+        return self
+
     def reseed(self, seed: int, tree_id_base: int = 0):
         """New Philox key for the searches after the next set_roots() (a fresh tree per real step, sweep.py:186)."""
         check(self.lib.isla_engine_reseed(self._h, int(seed), int(tree_id_base)))

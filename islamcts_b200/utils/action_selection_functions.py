@@ -93,5 +93,26 @@ class _Genetic:
 def genetic_policy(epsilon, default_policy, n_samples):
     return _Genetic(epsilon, default_policy, n_samples)
 
-grid_policy = _next_round("grid_policy")
+class _GridPolicy:
+    """Product of ``grid_policy(prior_knowledge, n_actions)`` (reference :258-282): a rollout policy for FrozenLake that
+    takes an arg-min of ``prior_knowledge[state]`` (ties uniformly).  A tag carrying the table; it runs on the device."""
+
+    isla_kind = "grid"
+
+    def __init__(self, prior_knowledge, n_actions):
+        import numpy as np
+        self.n_actions = int(n_actions)
+        states = sorted(prior_knowledge)
+        if states != list(range(len(states))):
+            raise ValueError("grid_policy: prior_knowledge must be keyed by the states 0 .. n-1")
+        self.table = np.array([list(prior_knowledge[s]) for s in states], dtype=np.float64)
+        if self.table.shape[1] != self.n_actions:
+            raise ValueError("grid_policy: every state needs one value per action")
+
+    def __call__(self, node):
+        raise NotImplementedError("grid_policy runs on the device inside fit(); it is not evaluated on the host")
+
+
+def grid_policy(prior_knowledge, n_actions):
+    return _GridPolicy(prior_knowledge, n_actions)
 discrete_default_policy = _next_round("discrete_default_policy")

@@ -254,6 +254,7 @@ struct orc_tree {
     const uint8_t* tk; const double* tv; int64_t tlen, tpos; int fault;
     stream_t tree_stream, roll_stream;
     uint32_t sim_index; /* cumulative over run() calls */
+    double* heur; int heur_states, heur_actions;   /* grid_policy prior knowledge [state][action], NULL = random rollouts */
     int64_t c_env_steps, c_roll_steps, c_levels, c_sims, c_expand_steps, c_seq; int next_blk, cur_parent_blk;
     /* instrumentation only: common prefix of consecutive simulation paths */
     int prev_path[4096], cur_path[4096], prev_len, cur_len; int64_t c_common, c_prevlen;
@@ -374,6 +375,23 @@ static void env_set_from_obs(orc_tree* t, const double* obs) {
 /* abstract_mcts.py:72-91.  `budget` = number of steps the loop condition
  * `curr_depth + starting_depth < max_depth` admits.  R rollouts (build extension,
  * SURVEY 8a) share the leaf state; rollout j draws from stream (seed, tree, sim, j). */
+/* grid_policy (utils/action_selection_functions.py:258-282): the rollout action is an arg-min of the prior knowledge of
+ * the env's current cell, ties broken by np.random.choice over the tied actions (K_CHOICE; Philox: one tree-independent
+ * rollout-stream word when there are several candidates). */
+static double heuristic_action(orc_tree* t, stream_t* st) {
+    const int cell = (int)t->env[0], A = t->heur_actions;
+    const double* ks = t->heur + (size_t)cell * A;
+    double m = INFINITY; for (int a = 0; a < A; ++a) if (ks[a] < m) m = ks[a];
+    int ties = 0; for (int a = 0; a < A; ++a) ties += (ks[a] == m);
+    int pos;
+    if (scripted(t)) {
+        pos = (int)trace_next(t, ORC_K_CHOICE);
+        if (pos < 0 || pos >= ties) { if (!t->fault) t->fault = -3; pos = 0; }
+    } else pos = ties > 1 ? (int)mulhi32(stream_u32(st), (uint32_t)ties) : 0;
+    for (int a = 0; a < A; ++a) if (ks[a] == m) { if (pos-- == 0) return (double)a; }
+    return 0.0;
+}
+
 static double do_rollout(orc_tree* t, int budget) {
     const int R = t->cfg.rollouts_per_leaf > 0 ? t->cfg.rollouts_per_leaf : 1;
     int P = 1; while (P < R) P <<= 1;
@@ -384,7 +402,8 @@ static double do_rollout(orc_tree* t, int budget) {
         if (!scripted(t)) stream_init(&t->roll_stream, t->cfg.seed, t->sim_index, (uint32_t)t->cfg.tree_id, (uint32_t)j);
         int done = 0, depth = 0; double reward = 0;
         while (!done && depth < budget) {
-            double a[2]; rnd_action(t, &t->roll_stream, a);
+            double a[2] = {0.0, 0.0};
+            if (t->heur) a[0] = heuristic_action(t, &t->roll_stream); else rnd_action(t, &t->roll_stream, a);
             double obs[ORC_MAX_S]; double r; int term;
             env_step(t, a, obs, &r, &term);
             reward += r * pow(t->cfg.gamma, depth);
@@ -791,7 +810,17 @@ orc_tree* orc_tree_create(const orc_config* cfg, const double* root_state) {
     t->tlen = -1;
     return t;
 }
-void orc_tree_destroy(orc_tree* t) { if (t) { free(t->S); free(t->A); free(t); } }
+int orc_tree_set_heuristic(orc_tree* t, const double* table, int n_states, int n_actions) {
+    free(t->heur); t->heur = NULL;
+    if (!table) return 0;
+    if (t->cfg.env_id != ORC_ENV_FROZENLAKE || n_states != 16 || n_actions != 4) return -1;
+    t->heur = (double*)malloc(sizeof(double) * n_states * n_actions);
+    memcpy(t->heur, table, sizeof(double) * n_states * n_actions);
+    t->heur_states = n_states; t->heur_actions = n_actions;
+    return 0;
+}
+
+void orc_tree_destroy(orc_tree* t) { if (t) { free(t->S); free(t->A); free(t->heur); free(t); } }
 
 int orc_tree_run(orc_tree* t, int n_sim, const uint8_t* kinds, const double* values, int64_t trace_len) {
     t->tk = kinds; t->tv = values; t->tlen = trace_len; t->tpos = 0; t->fault = 0;

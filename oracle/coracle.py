@@ -49,6 +49,8 @@ def lib():
         L.orc_tree_create.restype = C.c_void_p
         L.orc_tree_create.argtypes = [C.POINTER(Config), C.c_void_p]
         L.orc_tree_destroy.argtypes = [C.c_void_p]
+        L.orc_tree_set_heuristic.restype = C.c_int
+        L.orc_tree_set_heuristic.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.orc_tree_run.restype = C.c_int
         L.orc_tree_run.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
         L.orc_tree_trace_pos.restype = C.c_int64
@@ -112,6 +114,13 @@ class Tree:
             self.close()
         except Exception:
             pass
+
+    def set_heuristic(self, table):
+        """grid_policy prior knowledge [16, 4] (lower = better) for FrozenLake rollouts; None = random rollouts."""
+        if table is None:
+            return lib().orc_tree_set_heuristic(self._h, None, 0, 0)
+        tb = np.ascontiguousarray(table, dtype=np.float64)
+        return lib().orc_tree_set_heuristic(self._h, _p(tb), tb.shape[0], tb.shape[1])
 
     def run(self, n_sim, trace=None) -> int:
         if trace is None:

@@ -75,6 +75,10 @@ SCENARIOS = {
     # vanilla MctsHash on DiscreteCurveEnv([5 accelerations, 7 angles]) (sweep_vanilla.py:177), real rollouts
     "hash_curve_discrete": dict(agent="MctsHash", env="DiscreteCurveEnv", n_sim=300, C=5.0, gamma=0.95, max_depth=12,
                                 budget="to_max_depth", env_seed=0, rng_seed=15, grid=[5, 7], pre_steps=[0, 0, 0]),
+    # MctsHash on FrozenLake with the heuristic rollout policy of examples/example_lake.py:22-66: grid_policy over the
+    # Manhattan distance of the cell each action leads to (ties broken by np.random.choice)
+    "hash_lake_grid_policy": dict(agent="MctsHash", env="FrozenLake-v1", n_sim=220, C=0.5, gamma=0.95, max_depth=14,
+                                  budget="to_max_depth", env_seed=5, rng_seed=20, rollout="grid"),
     # SPW (with the state_variable shim) on CartPole: k=1 always re-expands; k=0.4 resamples and descends
     "spw_cartpole_k1": dict(agent="MctsSpw", env="CartPole-v1", n_sim=150, C=1.0, gamma=0.99, max_depth=500,
                             alpha=0.5, k=1, budget="zero", env_seed=0, rng_seed=9),
@@ -88,6 +92,17 @@ SCENARIOS = {
                                     max_depth=500, alpha1=0.4, k1=1, alpha2=0.2, k2=0.5, budget="zero",
                                     env_seed=5, rng_seed=12),
 }
+
+
+def lake_manhattan_knowledge():
+    """The prior knowledge of examples/example_lake.py:22-66: for every cell and action, the Manhattan distance to the goal
+    (3, 3) of the cell the action leads to (moves off the grid stay put).  key = row * 4 + col."""
+    def dist(r, c, a):
+        nr, nc = (r, c - 1) if a == 0 else (r + 1, c) if a == 1 else (r, c + 1) if a == 2 else (r - 1, c)
+        if nc < 0 or nc > 3 or nr < 0 or nr > 3:
+            nr, nc = r, c
+        return abs(3 - nc) + abs(3 - nr)
+    return {r * 4 + c: [dist(r, c, a) for a in range(4)] for c in range(4) for r in range(4)}
 
 
 class _LakeHashEnv(pyenvs.FrozenLakeEnv):
@@ -127,8 +142,11 @@ def run_scenario(name: str, sc: dict):
     root_data = obs
     if env_name == "FrozenLake-v1" and agent_key == "MctsHash":
         root_data = np.array([0, 0])  # fit() indexes root_data[0], root_data[1] (mcts_hash.py:37-38)
+    rollout_fn = R.continuous_default_policy
+    if sc.get("rollout") == "grid":
+        rollout_fn = R.asf.grid_policy(lake_manhattan_knowledge(), 4)
     common = dict(root_data=root_data, env=env, n_sim=sc["n_sim"], C=sc["C"], action_selection_fn=R.ucb1,
-                  gamma=sc["gamma"], rollout_selection_fn=R.continuous_default_policy, max_depth=sc["max_depth"],
+                  gamma=sc["gamma"], rollout_selection_fn=rollout_fn, max_depth=sc["max_depth"],
                   n_actions=n_actions, x_values=[], y_values=[], depths=[])
     if agent_key in ("Mcts", "MctsHash"):
         param = R.MctsParameters(**common)

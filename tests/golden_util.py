@@ -45,6 +45,16 @@ def engine_kwargs(cfg):
     return kw
 
 
+def lake_manhattan_table():
+    """[16, 4] prior knowledge of examples/example_lake.py:22-66 (Manhattan distance to the goal after the move)."""
+    def dist(r, c, a):
+        nr, nc = (r, c - 1) if a == 0 else (r + 1, c) if a == 1 else (r, c + 1) if a == 2 else (r - 1, c)
+        if nc < 0 or nc > 3 or nr < 0 or nr > 3:
+            nr, nc = r, c
+        return abs(3 - nc) + abs(3 - nr)
+    return np.array([[dist(s // 4, s % 4, a) for a in range(4)] for s in range(16)], dtype=np.float64)
+
+
 def assert_tree_equal(got, g, rtol=1e-9, atol=1e-9, label=""):
     """Canonical DFS serialisations: integers bit-exact, totals/actions to tolerance."""
     for k in ("kind", "depth", "count", "terminal", "fanout"):

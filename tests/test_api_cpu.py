@@ -74,6 +74,11 @@ def test_unknown_callables_and_envs_fail_loudly():
     assert (g2.isla_kind, g2.epsilon) == ("genetic2", 0.7)
     v = voo(0.7, continuous_default_policy, 5)
     assert (v.isla_kind, v.epsilon, v.n_samples, v.max_try) == ("voo", 0.7, 5, 1000)
+    from islamcts_b200.utils.action_selection_functions import grid_policy
+    gp = grid_policy({s: [s % 3, 1, 2, 0] for s in range(16)}, 4)
+    assert gp.isla_kind == "grid" and gp.table.shape == (16, 4) and gp.table[5, 0] == 2.0
+    with pytest.raises(ValueError):
+        grid_policy({0: [1, 2, 3, 4], 2: [1, 2, 3, 4]}, 4)
 
 
 def test_depth_statistics_of_proxies():

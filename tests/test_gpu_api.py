@@ -297,3 +297,31 @@ def test_apw_ensemble_unions_the_trees_root_children():
     assert len(st["action"]) <= per_tree - 3 * 5                       # centre and both bounds exist in all 6 trees: summed
     best = int(np.argmax(st["total"] / st["na"]))
     assert float(a[0]) == float(st["action"][best, 0])
+
+
+def test_example_lake_with_grid_policy_rollouts():
+    """examples/example_lake.py:56-97: grid_policy over the Manhattan-distance table as rollout_selection_fn.  Mcts at HEAD
+    never rolls out (depth_mode='reference_head'); in the budgeted mode the heuristic guides the rollouts."""
+    from islamcts_b200 import envs
+    from islamcts_b200.agents.mcts import Mcts
+    from islamcts_b200.agents.parameters.mcts_parameters import MctsParameters
+    from islamcts_b200.utils.action_selection_functions import grid_policy, ucb1
+    from tests.golden_util import lake_manhattan_table
+    distances = {s: list(lake_manhattan_table()[s]) for s in range(16)}
+    rollout_fn = grid_policy(distances, 4)
+    real_env = envs.make("FrozenLake-v1").unwrapped
+    observation, _ = real_env.reset()
+    done, steps, reward = False, 0, 0.0
+    while not done and steps < 20:
+        p = MctsParameters(C=0.5, n_sim=100, root_data=observation, env=real_env, action_selection_fn=ucb1, max_depth=1000,
+                           gamma=1, rollout_selection_fn=rollout_fn, n_actions=4, depth_mode="budgeted", seed=steps)
+        agent = Mcts(param=p)
+        action = agent.fit()
+        observation, reward, done, _, _ = real_env.step(action)
+        steps += 1
+    assert done and reward == 1.0 and steps == 6            # the shortest path to the goal
+    from islamcts_b200.agents.mcts_hash import MctsHash
+    cart = envs.make("CartPole-v1", api=4, seed=1); obs = cart.reset()
+    with pytest.raises(NotImplementedError):
+        MctsHash(MctsParameters(C=1, n_sim=10, root_data=obs, env=cart, action_selection_fn=ucb1, max_depth=10, gamma=0.9,
+                                rollout_selection_fn=rollout_fn, n_actions=2)).fit()

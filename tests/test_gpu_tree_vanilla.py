@@ -7,15 +7,19 @@ from tests.golden_util import assert_tree_equal, engine_kwargs, load_golden
 
 pytestmark = pytest.mark.gpu
 
-VANILLA_GOLDENS = ["hash_cartpole", "hash_cartpole_shallow", "mcts_lake", "mcts_lake_long", "hash_lake"]
+VANILLA_GOLDENS = ["hash_cartpole", "hash_cartpole_shallow", "mcts_lake", "mcts_lake_long", "hash_lake", "hash_lake_grid_policy"]
 
 
 def _engine_from_golden(g, precision, kernel, n_trees=1):
     from islamcts_b200.engine import Engine
     kw = engine_kwargs(g["config"])
-    return Engine(kw["env_id"], agent=kw["agent"], n_trees=n_trees, sim_capacity=g["config"]["n_sim"] + 8,
-                  max_depth=kw["max_depth"], C_=kw["C"], gamma=kw["gamma"], n_actions=kw["n_actions"],
-                  budget_mode=kw["budget_mode"], precision=precision, kernel=kernel)
+    eng = Engine(kw["env_id"], agent=kw["agent"], n_trees=n_trees, sim_capacity=g["config"]["n_sim"] + 8,
+                 max_depth=kw["max_depth"], C_=kw["C"], gamma=kw["gamma"], n_actions=kw["n_actions"],
+                 budget_mode=kw["budget_mode"], precision=precision, kernel=kernel)
+    if g["config"].get("rollout") == "grid":      # rollout_selection_fn = grid_policy(...) of examples/example_lake.py
+        from tests.golden_util import lake_manhattan_table
+        eng.set_rollout_heuristic(lake_manhattan_table())
+    return eng
 
 
 @pytest.mark.parametrize("name", VANILLA_GOLDENS)
@@ -181,3 +185,29 @@ def test_edge_cases_partial_warps_tiny_runs_and_trace_faults():
     eng.set_roots(g["root_state"][None, :])
     eng.run_scripted(0, g["config"]["n_sim"], g["trace_kind"][:500], g["trace_value"][:500])
     assert eng.tree_meta(0)["fault"] == -4 and eng.counters()["faults"] == 1
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_grid_policy_rollouts_free_running_equal_oracle(kernel):
+    """Heuristic rollouts (grid_policy over the Manhattan table of examples/example_lake.py) on both engines vs the
+    oracle with the same Philox streams: identical trees; and the heuristic finds the goal far more often than random."""
+    from islamcts_b200.engine import Engine
+    from tests.golden_util import lake_manhattan_table
+    n_trees, n_sim = 40, 150
+    roots = np.zeros((n_trees, 1))
+    eng = Engine(3, n_trees=n_trees, sim_capacity=n_sim, max_depth=30, C_=0.5, gamma=0.95, precision=1, kernel=kernel, seed=21,
+                 tree_id_base=300)
+    eng.set_rollout_heuristic(lake_manhattan_table())
+    eng.set_roots(roots).run(n_sim)
+    assert eng.counters()["faults"] == 0
+    na, tot = eng.root_stats()
+    na, tot = na.cpu().numpy(), tot.cpu().numpy()
+    for i in (0, 7, 39):
+        t = coracle.Tree(coracle.make_config(3, n_actions=4, max_depth=30, C_=0.5, gamma=0.95, seed=21, tree_id=300 + i), roots[i])
+        assert t.set_heuristic(lake_manhattan_table()) == 0
+        assert t.run(n_sim) == 0
+        assert_tree_equal(eng.export_tree(i), {"tree_" + k: v for k, v in t.serialise().items()})
+    heur_total = tot.sum()
+    eng.set_rollout_heuristic(None)                      # back to env.action_space.sample()
+    eng.set_roots(roots).run(n_sim)
+    assert eng.root_stats()[1].sum().item() < 0.7 * heur_total

@@ -18,6 +18,9 @@ def test_oracle_replays_reference_trace(name):
     kw = engine_kwargs(cfg)
     conf = coracle.make_config(kw.pop("env_id"), C_=kw.pop("C"), **kw)
     tree = coracle.Tree(conf, g["root_state"])
+    if cfg.get("rollout") == "grid":
+        from tests.golden_util import lake_manhattan_table
+        assert tree.set_heuristic(lake_manhattan_table()) == 0
     kinds, vals = g["trace_kind"], g["trace_value"]
     rc = tree.run(cfg["n_sim"], (kinds, vals))
     assert rc == 0, f"trace fault {rc} at {tree.trace_pos()}/{len(kinds)}"
