@@ -255,6 +255,10 @@ struct orc_tree {
     stream_t tree_stream, roll_stream;
     uint32_t sim_index; /* cumulative over run() calls */
     double* heur; int heur_states, heur_actions;   /* grid_policy prior knowledge [state][action], NULL = random rollouts */
+    /* FrozenLake is_slippery=True: every simulation runs on a pickled clone of the env INCLUDING its generator state
+     * (utils/mcts_utils.py:8-16), so inside one fit() the k-th env.step of every simulation draws the same number:
+     * noise[k], k = env.step calls so far in the simulation.  NULL = deterministic env. */
+    double* noise; int noise_n, sim_step;
     int64_t c_env_steps, c_roll_steps, c_levels, c_sims, c_expand_steps, c_seq; int next_blk, cur_parent_blk;
     /* instrumentation only: common prefix of consecutive simulation paths */
     int prev_path[4096], cur_path[4096], prev_len, cur_len; int64_t c_common, c_prevlen;
@@ -361,6 +365,16 @@ static void env_step(orc_tree* t, const double* action, double* obs, double* r, 
         act[0] = linspace_at(-5.0, 5.0, t->cfg.grid0, k / t->cfg.grid1);
         act[1] = linspace_at(-30.0, 30.0, t->cfg.grid1, k % t->cfg.grid1);
     }
+    if (t->noise && t->cfg.env_id == ORC_ENV_FROZENLAKE) {
+        if (t->sim_step >= t->noise_n) { if (!t->fault) t->fault = -3; }
+        else {
+            /* gym categorical_sample: argmax(cumsum([1/3, 1/3, 1/3]) > u); carried-out action = (a - 1 + i) mod 4 */
+            const double u = t->noise[t->sim_step], c0 = 1.0 / 3.0, c1 = c0 + 1.0 / 3.0;
+            const int i = c0 > u ? 0 : (c1 > u ? 1 : 2);
+            act[0] = (double)(((int)action[0] - 1 + i + 4) % 4);
+        }
+        t->sim_step++;
+    }
     orc_env_step(t->cfg.env_id, t->env, act, ns, r, &tm, obs);
     memcpy(t->env, ns, sizeof(double) * ORC_MAX_S);
     *term = tm; t->c_env_steps++;
@@ -397,8 +411,10 @@ static double do_rollout(orc_tree* t, int budget) {
     int P = 1; while (P < R) P <<= 1;
     double leaf[ORC_MAX_S]; memcpy(leaf, t->env, sizeof leaf);
     double* x = (double*)calloc((size_t)P, sizeof(double));
+    const int leaf_step = t->sim_step;
     for (int j = 0; j < R; ++j) {
         memcpy(t->env, leaf, sizeof leaf);
+        t->sim_step = leaf_step;   /* every rollout of a leaf batch continues the clone's noise from the leaf */
         if (!scripted(t)) stream_init(&t->roll_stream, t->cfg.seed, t->sim_index, (uint32_t)t->cfg.tree_id, (uint32_t)j);
         int done = 0, depth = 0; double reward = 0;
         while (!done && depth < budget) {
@@ -810,6 +826,16 @@ orc_tree* orc_tree_create(const orc_config* cfg, const double* root_state) {
     t->tlen = -1;
     return t;
 }
+int orc_tree_set_noise(orc_tree* t, const double* u, int n) {
+    free(t->noise); t->noise = NULL; t->noise_n = 0;
+    if (!u) return 0;
+    if (t->cfg.env_id != ORC_ENV_FROZENLAKE || n < 1) return -1;
+    t->noise = (double*)malloc(sizeof(double) * n);
+    memcpy(t->noise, u, sizeof(double) * n);
+    t->noise_n = n;
+    return 0;
+}
+
 int orc_tree_set_heuristic(orc_tree* t, const double* table, int n_states, int n_actions) {
     free(t->heur); t->heur = NULL;
     if (!table) return 0;
@@ -820,13 +846,14 @@ int orc_tree_set_heuristic(orc_tree* t, const double* table, int n_states, int n
     return 0;
 }
 
-void orc_tree_destroy(orc_tree* t) { if (t) { free(t->S); free(t->A); free(t->heur); free(t); } }
+void orc_tree_destroy(orc_tree* t) { if (t) { free(t->S); free(t->A); free(t->heur); free(t->noise); free(t); } }
 
 int orc_tree_run(orc_tree* t, int n_sim, const uint8_t* kinds, const double* values, int64_t trace_len) {
     t->tk = kinds; t->tv = values; t->tlen = trace_len; t->tpos = 0; t->fault = 0;
     for (int s = 0; s < n_sim && !t->fault; ++s) {
         /* fit(): param.env = my_deepcopy(initial_env, ...) -- mcts_hash.py:31 ; spw/dpw poke root_data */
         memcpy(t->env, t->root_state, sizeof t->env);
+        t->sim_step = 0;
         if (t->cfg.agent == ORC_AGENT_SPW || t->cfg.agent == ORC_AGENT_DPW) env_set_from_obs(t, t->S[0].obs);
         t->cur_len = 0;
         state_visit(t, 0, 0);

@@ -51,6 +51,8 @@ def lib():
         L.orc_tree_destroy.argtypes = [C.c_void_p]
         L.orc_tree_set_heuristic.restype = C.c_int
         L.orc_tree_set_heuristic.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.orc_tree_set_noise.restype = C.c_int
+        L.orc_tree_set_noise.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.orc_tree_run.restype = C.c_int
         L.orc_tree_run.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
         L.orc_tree_trace_pos.restype = C.c_int64
@@ -121,6 +123,13 @@ class Tree:
             return lib().orc_tree_set_heuristic(self._h, None, 0, 0)
         tb = np.ascontiguousarray(table, dtype=np.float64)
         return lib().orc_tree_set_heuristic(self._h, _p(tb), tb.shape[0], tb.shape[1])
+
+    def set_noise(self, u):
+        """Per-step transition noise of a slippery FrozenLake fit (same for every simulation); None = deterministic."""
+        if u is None:
+            return lib().orc_tree_set_noise(self._h, None, 0)
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        return lib().orc_tree_set_noise(self._h, _p(u), len(u))
 
     def run(self, n_sim, trace=None) -> int:
         if trace is None:

@@ -79,6 +79,13 @@ SCENARIOS = {
     # Manhattan distance of the cell each action leads to (ties broken by np.random.choice)
     "hash_lake_grid_policy": dict(agent="MctsHash", env="FrozenLake-v1", n_sim=220, C=0.5, gamma=0.95, max_depth=14,
                                   budget="to_max_depth", env_seed=5, rng_seed=20, rollout="grid"),
+    # FrozenLake is_slippery=True: my_deepcopy clones the env WITH its generator for every simulation
+    # (utils/mcts_utils.py:8-16), so the k-th step of every simulation draws the same noise; Mcts (zero rollouts at HEAD)
+    # and MctsHash (budgeted rollouts)
+    "mcts_lake_slippery": dict(agent="Mcts", env="FrozenLake-v1", n_sim=250, C=0.5, gamma=0.95, max_depth=30, budget="zero",
+                               env_seed=7, rng_seed=22, slippery=True),
+    "hash_lake_slippery": dict(agent="MctsHash", env="FrozenLake-v1", n_sim=220, C=0.5, gamma=0.95, max_depth=16,
+                               budget="to_max_depth", env_seed=8, rng_seed=23, slippery=True),
     # SPW (with the state_variable shim) on CartPole: k=1 always re-expands; k=0.4 resamples and descends
     "spw_cartpole_k1": dict(agent="MctsSpw", env="CartPole-v1", n_sim=150, C=1.0, gamma=0.99, max_depth=500,
                             alpha=0.5, k=1, budget="zero", env_seed=0, rng_seed=9),
@@ -127,8 +134,12 @@ def run_scenario(name: str, sc: dict):
             assert not done, "pre_steps must keep the car on the track"
         root_state = np.array([*env.car.state, float(env.n_step)], dtype=np.float64)
     elif env_name == "FrozenLake-v1" and agent_key == "MctsHash":
-        env = _LakeHashEnv(api=4, seed=sc["env_seed"])
+        env = _LakeHashEnv(api=4, seed=sc["env_seed"], is_slippery=sc.get("slippery", False))
         obs = env.reset()
+        root_state = pyenvs.env_state_vector(env)
+    elif env_name == "FrozenLake-v1" and sc.get("slippery"):
+        env = pyenvs.FrozenLakeEnv(api=api, seed=sc["env_seed"], is_slippery=True)
+        obs = env.reset()[0]
         root_state = pyenvs.env_state_vector(env)
     else:
         env = pyenvs.make(env_name, api=api, seed=sc["env_seed"])
@@ -170,6 +181,11 @@ def run_scenario(name: str, sc: dict):
     else:
         raise KeyError(agent_key)
     agent = getattr(R, agent_key)(param)
+    # what every simulation's cloned env will draw, step by step (slippery FrozenLake)
+    noise = None
+    if sc.get("slippery"):
+        import copy
+        noise = copy.deepcopy(env.np_random).random(sc["max_depth"] + 4)
     fit_error = ""
     steps0 = pyenvs.STEP_COUNTER[0]
     with T.recording(tr, sc["rng_seed"]):
@@ -206,6 +222,7 @@ def run_scenario(name: str, sc: dict):
         q_values=np.asarray(agent.q_values, dtype=np.float64),
         root_action=root_action, root_action2=root_action2, root_na=root_na, root_total=root_total,
         root_depth_max=root_depth_max, root_depth_mean=root_depth_mean,
+        **({"noise": noise} if noise is not None else {}),
         fit_action=np.float64(action_val),
         env_steps=np.int64(pyenvs.STEP_COUNTER[0] - steps0) if env_name not in ("CurveEnv", "DiscreteCurveEnv") else np.int64(-1),
         **{f"tree_{k}": v for k, v in ser.items()},

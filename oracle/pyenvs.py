@@ -239,17 +239,21 @@ class MountainCarContinuousEnv(_Env):
 
 
 class FrozenLakeEnv(_Env):
-    """FrozenLake-v1 4x4, is_slippery=False.  0 LEFT, 1 DOWN, 2 RIGHT, 3 UP."""
+    """FrozenLake-v1 4x4.  0 LEFT, 1 DOWN, 2 RIGHT, 3 UP.  is_slippery=True: the action carried out is a-1, a or a+1
+    (mod 4), each with probability 1/3, chosen like gym's categorical_sample: argmax(cumsum(p) > np_random.random()),
+    one draw of the env's own generator per step (terminal cells included)."""
 
     env_id = ENV_FROZENLAKE
     spec_id = "FrozenLake-v1"
     MAP = ("SFFF", "FHFH", "FFFH", "HFFG")
 
-    def __init__(self, api: int = 5, seed=None):
+    def __init__(self, api: int = 5, seed=None, is_slippery: bool = False):
         super().__init__(api)
         self.desc = np.asarray([list(r) for r in self.MAP], dtype="U1")
         self.nrow, self.ncol = self.desc.shape
         self.action_space = Discrete(4, seed)
+        self.is_slippery = bool(is_slippery)
+        self.np_random = np.random.default_rng(seed)
         self.s = 0
 
     @property
@@ -262,10 +266,14 @@ class FrozenLakeEnv(_Env):
 
     def step(self, a):
         row, col = divmod(int(self.s), self.ncol)
+        u = self.np_random.random() if self.is_slippery else 0.0
         if self.desc[row, col] in "GH":
             # stepping from a terminal cell: stays put, reward 0, terminated
             return self._ret(int(self.s), 0.0, True)
         a = int(a)
+        if self.is_slippery:
+            i = int(np.argmax(np.cumsum([1.0 / 3.0] * 3) > u))
+            a = (a - 1 + i) % 4
         if a == 0:
             col = max(col - 1, 0)
         elif a == 1:

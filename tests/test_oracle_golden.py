@@ -21,6 +21,8 @@ def test_oracle_replays_reference_trace(name):
     if cfg.get("rollout") == "grid":
         from tests.golden_util import lake_manhattan_table
         assert tree.set_heuristic(lake_manhattan_table()) == 0
+    if "noise" in g:                                    # slippery FrozenLake: the cloned env's per-step draws
+        assert tree.set_noise(g["noise"]) == 0
     kinds, vals = g["trace_kind"], g["trace_value"]
     rc = tree.run(cfg["n_sim"], (kinds, vals))
     assert rc == 0, f"trace fault {rc} at {tree.trace_pos()}/{len(kinds)}"
