@@ -132,6 +132,13 @@ int isla_engine_set_roots(isla_engine* e, const double* roots_dev, void* stream)
  * doubles, [16][4], lower = better), ties broken uniformly.  NULL restores env.action_space.sample().  Synchronous. */
 int isla_engine_set_rollout_heuristic(isla_engine* e, const double* table_host, int32_t n_states, int32_t n_actions);
 
+/* FrozenLake-v1 with is_slippery=True as the reference runs it: every simulation steps a pickled clone of param.env
+ * INCLUDING the env's generator state (utils/mcts_utils.py:8-16), so inside one fit() the k-th env.step of every
+ * simulation draws the same number.  u_host[k] (HOST doubles, n >= the deepest step index a simulation can reach) is
+ * that sequence, e.g. copy.deepcopy(env.np_random).random(n); the action carried out at step k is (a - 1 + i) mod 4
+ * with i = argmax(cumsum([1/3, 1/3, 1/3]) > u[k]) (gym's categorical_sample).  NULL = deterministic.  Synchronous. */
+int isla_engine_set_transition_noise(isla_engine* e, const double* u_host, int32_t n);
+
 /* fit(): the `for s in range(n_sim)` loop (mcts.py:24-27, mcts_hash.py:30-34, mcts_action_...:25-30,
  * mcts_state_...:23-26, mcts_double_...:24-27) for all trees.  Calling it again continues the trees. */
 int isla_engine_run(isla_engine* e, int32_t n_sim, void* stream);

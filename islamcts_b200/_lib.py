@@ -69,6 +69,7 @@ SYMBOLS = {
     "isla_engine_layout": (C.c_int, [_P, C.POINTER(IslaLayout)]),
     "isla_engine_set_roots": (C.c_int, [_P, _P, _P]),
     "isla_engine_set_rollout_heuristic": (C.c_int, [_P, _P, C.c_int32, C.c_int32]),
+    "isla_engine_set_transition_noise": (C.c_int, [_P, _P, C.c_int32]),
     "isla_engine_run": (C.c_int, [_P, C.c_int32, _P]),
     "isla_engine_run_scripted": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, C.c_int64, _P]),
     "isla_engine_root_stats": (C.c_int, [_P, _P, _P, _P]),

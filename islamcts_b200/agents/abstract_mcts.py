@@ -39,11 +39,26 @@ def identify_env(env) -> int:
             rows = tuple("".join(c.decode() if isinstance(c, bytes) else str(c) for c in r) for r in np.asarray(desc))
             if rows != _LAKE_MAP:
                 raise NotImplementedError(f"FrozenLake map {rows} is not on the device (only the default 4x4 map)")
-        P = getattr(u, "P", None)
-        if P is not None and len(P[0][0]) != 1:
-            raise NotImplementedError("FrozenLake is_slippery=True is not on the device yet (SURVEY 8f)")
         return _lib.ENV_FROZENLAKE
     raise NotImplementedError(f"environment {name!r} has no device implementation (supported: {sorted(ENV_NAMES)})")
+
+
+def lake_transition_noise(env, n: int):
+    """FrozenLake is_slippery=True: what the next n env.step calls of a CLONE of the env would draw.  The reference
+    steps a pickled clone (generator state included) in every simulation (utils/mcts_utils.py:8-16), so all simulations
+    of one fit() see this same sequence.  None for the deterministic lake."""
+    import copy
+    u = getattr(env, "unwrapped", env)
+    slippery = getattr(u, "is_slippery", None)
+    if slippery is None:
+        P = getattr(u, "P", None)
+        slippery = P is not None and len(P[0][0]) != 1
+    if not slippery:
+        return None
+    rng = getattr(u, "np_random", None)
+    if rng is None or not hasattr(rng, "random"):
+        raise NotImplementedError("slippery FrozenLake without a numpy Generator in env.np_random")
+    return np.asarray(copy.deepcopy(rng).random(int(n)), dtype=np.float64)
 
 
 def env_action_info(env, env_id: int):
@@ -278,6 +293,8 @@ class AbstractMcts:
         root_state = env_root_state(p.env, env_id)
         self._ensure_engine(env_id, root_state)
         eng = self._engine
+        if env_id == _lib.ENV_FROZENLAKE:   # slippery lake: the clone's per-step draws, as of this fit()
+            eng.set_transition_noise(lake_transition_noise(p.env, max(int(p.max_depth), self._capacity) + 4))
         eng.run(int(p.n_sim))
         self._sims_done += int(p.n_sim)
         self._root_proxy = None

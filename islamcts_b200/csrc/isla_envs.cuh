@@ -385,6 +385,14 @@ __device__ __forceinline__ T sample_action(Stream& st) {
     }
 }
 
+// FrozenLake is_slippery=True: the action carried out is a-1, a or a+1 (mod 4), chosen like gym's categorical_sample,
+// argmax(cumsum([1/3, 1/3, 1/3]) > u)
+__device__ __forceinline__ int lake_slip(int a, double u) {
+    constexpr double c0 = 1.0 / 3.0, c1 = 1.0 / 3.0 + 1.0 / 3.0;
+    const int i = c0 > u ? 0 : (c1 > u ? 1 : 2);
+    return (a - 1 + i + 4) & 3;
+}
+
 // grid_policy (utils/action_selection_functions.py:258-282): an arg-min of the prior knowledge of the current cell;
 // `pos_of(ties)` picks among the tied minima (np.random.choice)
 template <typename PosFn>
@@ -406,10 +414,13 @@ __device__ __forceinline__ int lake_heuristic_action(const double* __restrict__ 
 // (agents/abstract_mcts.py:84-85).  CurveEnv samples Box([-5,-30],[5,30], float64) or Discrete(g0*g1).
 template <int ENV, typename T>
 __device__ __forceinline__ bool rollout_step(Stream& st, T (&s)[EnvTraits<ENV>::S], ActionGrid g, T& reward,
-                                             const double* heur = nullptr) {
+                                             const double* heur = nullptr, const double* noise = nullptr, int step_index = 0) {
     if constexpr (ENV == ENV_FROZENLAKE) {
-        if (heur) {   // rollout_selection_fn = grid_policy: one stream word only when several actions tie
-            const int a = lake_heuristic_action(heur, (int)s[0], [&](int ties) { return ties > 1 ? (int)mulhi_u32(st.next(), (uint32_t)ties) : 0; });
+        if (heur || noise) {
+            int a;   // rollout_selection_fn = grid_policy: one stream word only when several actions tie
+            if (heur) a = lake_heuristic_action(heur, (int)s[0], [&](int ties) { return ties > 1 ? (int)mulhi_u32(st.next(), (uint32_t)ties) : 0; });
+            else a = (int)st.next_bits(2);
+            if (noise) a = lake_slip(a, __ldg(noise + step_index));
             return Env<ENV, T>::step(s, T(a), reward);
         }
     }

@@ -62,6 +62,8 @@ struct TptParams {
     const double* cum_table;   // host-computed sum_{t<n} gamma**t (left-to-right)
     int n_sim, max_depth, budget_mode, block_cap, ln_count, disc_count, ln_in_smem, tuning;
     const double* heur;        // grid_policy table (FrozenLake), nullptr = random rollouts
+    const double* noise;       // slippery FrozenLake: noise[k] of the k-th env.step of a simulation, nullptr = deterministic
+    int noise_n;
 };
 
 }  // namespace isla
@@ -75,6 +77,8 @@ struct isla_engine {
     bool roots_set;
     long long sims_run = 0;   // simulations requested since the last set_roots (bounds the nodes a tree can hold)
     double* heur_dev = nullptr;   // grid_policy prior knowledge [16][4] (engine-owned), nullptr = random rollouts
+    double* noise_dev = nullptr;  // slippery FrozenLake: per-step transition noise of a fit (engine-owned)
+    int noise_n = 0;
 };
 
 namespace isla {

@@ -69,6 +69,7 @@ struct CtaParams {
     int action_dim;                        // 1, or 2 for the continuous CurveEnv box (second coordinate in a_value2)
     int cluster;                           // CTAs (one thread-block cluster) sharing one tree's leaf-parallel rollouts
     const double* heur;                    // grid_policy table (FrozenLake rollouts), nullptr = random rollouts
+    const double* noise; int noise_n;      // slippery FrozenLake: noise[k] of the k-th env.step of a simulation
 };
 
 enum : int { O_S_TOTAL = 0, O_S_TERMR, O_S_NS, O_S_FLAGS, O_S_COFF, O_S_CCAP, O_S_CCNT, O_S_STATE, O_A_TOTAL, O_A_VALUE,
@@ -146,6 +147,7 @@ enum : int { VOO_EVAL = 0, VOO_EXIT = 1, VOO_FIND = 2 };
 struct RollShared {
     double leaf[8];
     int budget, need, exit_flag;
+    int depth;          // env.step calls of the simulation before the leaf's rollouts (slippery FrozenLake noise index)
     unsigned sim;
     double result;
     VooWork vw;
@@ -928,7 +930,14 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                     for (int i = 0; i < S; ++i) cur[i] = sp[i];
                 }
                 T rT;
-                const bool term = env_step_action<ENV, T>(cur, q.a_value[a], p.action_dim == 2 ? q.a_value2[a] : 0.0, p.grid, rT);
+                double step_a = q.a_value[a];
+                if constexpr (ENV == ENV_FROZENLAKE) {
+                    if (p.noise) {   // is_slippery=True: this is step `level` of the simulation
+                        if (level >= p.noise_n) { ctx.fault = ISLA_ERR_INVALID; break; }
+                        step_a = (double)lake_slip((int)step_a, __ldg(p.noise + level));
+                    }
+                }
+                const bool term = env_step_action<ENV, T>(cur, step_a, p.action_dim == 2 ? q.a_value2[a] : 0.0, p.grid, rT);
                 const double r = (double)rT;
                 ++ctx.c_env;
                 const int child = q.a_child[a];
@@ -999,10 +1008,15 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                 if (!descend) break;
                 s = child;
             }
+            if constexpr (ENV == ENV_FROZENLAKE) {   // the noise table must cover every step the rollouts can take
+                const int b_ = p.budget_mode == ISLA_BUDGET_ZERO ? 0 : max(0, min(p.max_depth - level, p.disc_count));
+                if (p.noise && need_roll && level + b_ > p.noise_n) ctx.fault = ISLA_ERR_INVALID;
+            }
             if (lane == 0) {
 #pragma unroll
                 for (int i = 0; i < S; ++i) sh.leaf[i] = (double)cur[i];
                 sh.budget = p.budget_mode == ISLA_BUDGET_ZERO ? 0 : max(0, min(p.max_depth - level, p.disc_count));
+                sh.depth = level;
                 sh.need = (need_roll && !ctx.fault && !ctx.tc.fault) ? 1 : 0;
                 sh.sim = sims_done;
             }
@@ -1046,6 +1060,12 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                         if (heuristic) act = (double)lake_heuristic_action(p.heur, (int)st[0], [&](int ties) { return ctx.choice(ties); });
                         else act = ctx.tree_action(act2);
                         if (ctx.tc.fault) break;
+                        if constexpr (ENV == ENV_FROZENLAKE) {
+                            if (p.noise) {
+                                if (sh.depth + t >= p.noise_n) { ctx.fault = ISLA_ERR_INVALID; break; }
+                                act = (double)lake_slip((int)act, __ldg(p.noise + sh.depth + t));
+                            }
+                        }
                         T rr;
                         done = env_step_action<ENV, T>(st, act, act2, p.grid, rr);
                         Rr = __dadd_rn(Rr, __dmul_rn((double)rr, p.disc_table[t]));
@@ -1060,6 +1080,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                 // ends with the CS per-rank sums
                 const int slice = P / CS;
                 const unsigned sim_id = sh0->sim;
+                const int leaf_depth = sh0->depth;
                 double leaf[S];
 #pragma unroll
                 for (int i = 0; i < S; ++i) leaf[i] = sh0->leaf[i];
@@ -1076,7 +1097,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                             int t = 0; bool done = false;
                             T rr = T(0);
                             while (!done && t < budget) {
-                                done = rollout_step<ENV, T>(rs, st, p.grid, rr, p.heur);
+                                done = rollout_step<ENV, T>(rs, st, p.grid, rr, p.heur, p.noise, min(leaf_depth + t, p.noise_n - 1));
                                 // r * pow(gamma, t) summed left to right (abstract_mcts.py:87); envs with a constant
                                 // interior reward take the bit-identical closed form from the host prefix table below
                                 if constexpr (!Rewards<ENV>::kClosedForm) Rr = __dadd_rn(Rr, __dmul_rn((double)rr, __ldg(p.disc_table + t)));
@@ -1390,6 +1411,7 @@ CtaParams make_params(const isla_engine* e, int n_sim_launch = 0) {
     p.pool_in_smem = (fit_per_sm >= 1 && e->cfg.n_trees * cs <= sms * fit_per_sm && !(e->cfg.tuning & 16)) ? 1 : 0;
     p.hash_base = e->ws ? e->ws + L.hash_offset : nullptr; p.hash_cap = L.hash_cap;
     p.heur = e->heur_dev;
+    p.noise = e->noise_dev; p.noise_n = e->noise_n;
     return p;
 }
 

@@ -690,7 +690,13 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
 #pragma unroll
                 for (int i = 0; i < S; ++i) st[i] = __ldcg(states + (long long)node_slot * S + i);
             }
-            const bool term = Env<ENV, T>::step(st, T(exp_a), r_exp);
+            int step_a = exp_a;
+            if constexpr (ENV == ENV_FROZENLAKE) {
+                if (p.noise) {   // is_slippery=True: step `level` of the simulation
+                    if (level >= p.noise_n) fault = ISLA_ERR_INVALID; else step_a = lake_slip(exp_a, __ldg(p.noise + level));
+                }
+            }
+            const bool term = Env<ENV, T>::step(st, T(step_a), r_exp);
             ++c_env;
             if (term) {
                 G = (double)r_exp;  // terminal child: total += r, na += 1, child.ns += 1 (mcts_hash.py:96-107)
@@ -739,6 +745,12 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                         act = T(tc.fault ? 0 : v);
                     } else {
                         act = sample_action<ENV, T>(rs);
+                    }
+                    if constexpr (ENV == ENV_FROZENLAKE) {
+                        if (p.noise) {   // rollout step t is step level + 1 + t of the simulation
+                            const int k = level + 1 + t;
+                            if (k >= p.noise_n) fault = ISLA_ERR_INVALID; else act = T(lake_slip((int)act, __ldg(p.noise + k)));
+                        }
                     }
                     const bool done = Env<ENV, T>::step(st, act, last_r);
                     ++t;
@@ -997,7 +1009,8 @@ int tpt_run(isla_engine* e, int n_sim, long long scripted_tree, const uint8_t* k
     p.cum_table = (const double*)(e->ws + L.cumdisc_offset);
     p.ln_count = (int)L.ln_count; p.disc_count = (int)L.disc_count;
     p.ln_in_smem = (L.ln_count * 4 <= 8 * 1024) ? 1 : 0;
-    p.heur = e->heur_dev;   // float copy of ln(n) next to the cooperative ring
+    p.heur = e->heur_dev;
+    p.noise = e->noise_dev; p.noise_n = e->noise_n;   // float copy of ln(n) next to the cooperative ring
     p.tuning = e->cfg.tuning;
     const bool scripted = scripted_tree >= 0;
     const bool f64 = e->cfg.precision == ISLA_PRECISION_F64;

@@ -119,6 +119,17 @@ class Engine:
             check(self.lib.isla_engine_set_rollout_heuristic(self._h, tb.ctypes.data_as(C.c_void_p), tb.shape[0], tb.shape[1]))
         return self
 
+    def set_transition_noise(self, u):
+        """Slippery FrozenLake: u[k] = what the k-th env.step of every simulation of this fit draws (the reference clones
+        the env's generator per simulation, utils/mcts_utils.py:8-16); None = deterministic env."""
+        if u is None:
+            check(self.lib.isla_engine_set_transition_noise(self._h, None, 0))
+            return self
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        with torch.cuda.device(self.device):
+            check(self.lib.isla_engine_set_transition_noise(self._h, u.ctypes.data_as(C.c_void_p), len(u)))
+        return self
+
     def reseed(self, seed: int, tree_id_base: int = 0):
         """New Philox key for the searches after the next set_roots() (a fresh tree per real step, sweep.py:186)."""
         check(self.lib.isla_engine_reseed(self._h, int(seed), int(tree_id_base)))

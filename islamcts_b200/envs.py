@@ -34,8 +34,9 @@ class Box:
 class DeviceEnv:
     """new_step_api: ``step`` returns (obs, reward, terminated, truncated, info); ``api=4`` gives the old 4-tuple."""
 
-    def __init__(self, name: str, api: int = 5, seed=None, device="cuda:0"):
+    def __init__(self, name: str, api: int = 5, seed=None, device="cuda:0", is_slippery: bool = False):
         self.spec_id = name
+        self.is_slippery = bool(is_slippery)   # FrozenLake-v1 only: gym.make("FrozenLake-v1", is_slippery=True)
         self.env_id = E.ENV_NAMES[name]
         self.api, self.device = api, device
         self.np_random = np.random.default_rng(seed)
@@ -79,6 +80,10 @@ class DeviceEnv:
 
     def step(self, action):
         a = float(np.asarray(action, dtype=np.float64).reshape(-1)[0])
+        if self.env_id == _lib.ENV_FROZENLAKE and self.is_slippery:
+            # gym's categorical_sample over the three outcomes a-1, a, a+1 (one draw of the env's generator per step)
+            i = int(np.argmax(np.cumsum([1.0 / 3.0] * 3) > self.np_random.random()))
+            a = float((int(a) - 1 + i) % 4)
         cur = np.array([float(self.s)]) if self.env_id == _lib.ENV_FROZENLAKE else np.asarray(self.state, np.float64)
         ns, r, t = E.env_step(self.env_id, cur[None, :], [a], precision=_lib.PRECISION_F64, device=self.device)
         self.state = ns[0].cpu().numpy()
@@ -90,5 +95,5 @@ class DeviceEnv:
         return self._obs(), reward, term, False, {}
 
 
-def make(name: str, api: int = 5, seed=None, device="cuda:0") -> DeviceEnv:
-    return DeviceEnv(name, api=api, seed=seed, device=device)
+def make(name: str, api: int = 5, seed=None, device="cuda:0", is_slippery: bool = False) -> DeviceEnv:
+    return DeviceEnv(name, api=api, seed=seed, device=device, is_slippery=is_slippery)

@@ -325,3 +325,34 @@ def test_example_lake_with_grid_policy_rollouts():
     with pytest.raises(NotImplementedError):
         MctsHash(MctsParameters(C=1, n_sim=10, root_data=obs, env=cart, action_selection_fn=ucb1, max_depth=10, gamma=0.9,
                                 rollout_selection_fn=rollout_fn, n_actions=2)).fit()
+
+
+def test_slippery_frozenlake_through_the_agent_api():
+    """gym.make("FrozenLake-v1", is_slippery=True): fit() clones the env generator's next draws (every simulation of the
+    reference steps a pickled clone) and the search equals the oracle fed with the same draws."""
+    import copy
+    from islamcts_b200 import envs
+    from islamcts_b200.agents.mcts_hash import MctsHash
+    from islamcts_b200.agents.parameters.mcts_parameters import MctsParameters
+    from islamcts_b200.utils.action_selection_functions import continuous_default_policy, ucb1
+    env = envs.make("FrozenLake-v1", api=4, seed=12, is_slippery=True)
+    obs = env.reset()
+    total_slips = 0
+    for step in range(4):
+        p = MctsParameters(C=0.5, n_sim=150, root_data=obs, env=env, action_selection_fn=ucb1, max_depth=25, gamma=0.95,
+                           rollout_selection_fn=continuous_default_policy, n_actions=4, seed=40 + step, precision="f64")
+        noise = copy.deepcopy(env.np_random).random(700)
+        agent = MctsHash(p)
+        a = agent.fit()
+        t = coracle.Tree(coracle.make_config(3, n_actions=4, max_depth=25, C_=0.5, gamma=0.95, seed=40 + step), [float(env.s)])
+        assert t.set_noise(noise) == 0 and t.run(150) == 0
+        ea, ena, etot = t.root_children()
+        np.testing.assert_array_equal(agent.root_statistics["na"], ena)
+        np.testing.assert_allclose(agent.root_statistics["total"], etot, rtol=1e-12)
+        before = env.s
+        obs, r, done, _ = env.step(a)
+        det = envs.make("FrozenLake-v1", api=4); det.reset(); det.s = before
+        total_slips += int(det.step(a)[0] != obs)
+        if done:
+            break
+    assert 0 <= total_slips <= 4

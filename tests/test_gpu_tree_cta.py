@@ -29,6 +29,8 @@ def test_scripted_trace_rebuilds_reference_tree_cta(name, precision):
     if cfg.get("rollout") == "grid":                    # rollout_selection_fn = grid_policy(...) of examples/example_lake.py
         from tests.golden_util import lake_manhattan_table
         eng.set_rollout_heuristic(lake_manhattan_table())
+    if "noise" in g:                                    # slippery FrozenLake: the cloned env's per-step draws
+        eng.set_transition_noise(g["noise"])
     eng.set_roots(g["root_state"][None, :])
     kinds, vals = g["trace_kind"], g["trace_value"]
     eng.run_scripted(0, cfg["n_sim"], kinds, vals)

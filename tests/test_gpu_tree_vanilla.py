@@ -7,7 +7,8 @@ from tests.golden_util import assert_tree_equal, engine_kwargs, load_golden
 
 pytestmark = pytest.mark.gpu
 
-VANILLA_GOLDENS = ["hash_cartpole", "hash_cartpole_shallow", "mcts_lake", "mcts_lake_long", "hash_lake", "hash_lake_grid_policy"]
+VANILLA_GOLDENS = ["hash_cartpole", "hash_cartpole_shallow", "mcts_lake", "mcts_lake_long", "hash_lake", "hash_lake_grid_policy",
+                   "mcts_lake_slippery", "hash_lake_slippery"]
 
 
 def _engine_from_golden(g, precision, kernel, n_trees=1):
@@ -19,6 +20,8 @@ def _engine_from_golden(g, precision, kernel, n_trees=1):
     if g["config"].get("rollout") == "grid":      # rollout_selection_fn = grid_policy(...) of examples/example_lake.py
         from tests.golden_util import lake_manhattan_table
         eng.set_rollout_heuristic(lake_manhattan_table())
+    if "noise" in g:                               # slippery FrozenLake: the cloned env's per-step draws
+        eng.set_transition_noise(g["noise"])
     return eng
 
 
@@ -211,3 +214,27 @@ def test_grid_policy_rollouts_free_running_equal_oracle(kernel):
     eng.set_rollout_heuristic(None)                      # back to env.action_space.sample()
     eng.set_roots(roots).run(n_sim)
     assert eng.root_stats()[1].sum().item() < 0.7 * heur_total
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_slippery_lake_free_running_equals_oracle(kernel):
+    """FrozenLake is_slippery=True the way the reference runs it (the same per-step noise in every simulation of a fit):
+    both engines vs the oracle, with random and with heuristic rollouts."""
+    from islamcts_b200.engine import Engine
+    from tests.golden_util import lake_manhattan_table
+    n_trees, n_sim = 36, 140
+    noise = np.random.default_rng(5).random(80)
+    for heur in (None, lake_manhattan_table()):
+        eng = Engine(3, n_trees=n_trees, sim_capacity=n_sim, max_depth=40, C_=0.5, gamma=0.95, precision=1, kernel=kernel, seed=31,
+                     tree_id_base=50)
+        eng.set_transition_noise(noise).set_rollout_heuristic(heur)
+        eng.set_roots(np.zeros((n_trees, 1))).run(n_sim)
+        assert eng.counters()["faults"] == 0
+        for i in (0, 11, 35):
+            t = coracle.Tree(coracle.make_config(3, n_actions=4, max_depth=40, C_=0.5, gamma=0.95, seed=31, tree_id=50 + i), [0.0])
+            assert t.set_noise(noise) == 0 and t.set_heuristic(heur) == 0
+            assert t.run(n_sim) == 0
+            assert_tree_equal(eng.export_tree(i), {"tree_" + k: v for k, v in t.serialise().items()})
+    short = Engine(3, n_trees=2, sim_capacity=50, max_depth=40, precision=1, kernel=kernel, seed=1)
+    short.set_transition_noise(noise[:3]).set_roots(np.zeros((2, 1))).run(50)
+    assert short.counters()["faults"] > 0          # a noise table shorter than the simulation is a loud fault
