@@ -69,8 +69,9 @@ int upload_tables(isla_engine* e) {
 static int resolve_kernel(const isla_config& c) {
     if (c.kernel == ISLA_KERNEL_THREAD_PER_TREE || c.kernel == ISLA_KERNEL_CTA_PER_TREE) return c.kernel;
     const bool tpt_ok = c.agent == ISLA_AGENT_VANILLA && env_n_actions(c.env_id) > 0 && c.rollouts_per_leaf <= 1;
-    // many independent narrow trees -> one thread each; few / wide / leaf-parallel trees -> one CTA each
-    return (tpt_ok && c.n_trees >= 1024) ? ISLA_KERNEL_THREAD_PER_TREE : ISLA_KERNEL_CTA_PER_TREE;
+    // independent narrow trees -> one thread each (the kernel spreads a small batch over many warps, see kTreesPerWarp: it
+    // is ahead of the CTA engine from a few dozen trees on); few / wide / leaf-parallel trees -> one CTA each
+    return (tpt_ok && c.n_trees >= 64) ? ISLA_KERNEL_THREAD_PER_TREE : ISLA_KERNEL_CTA_PER_TREE;
 }
 
 static int validate(const isla_config& c) {

@@ -64,6 +64,7 @@ struct TptParams {
     const double* heur;        // grid_policy table (FrozenLake), nullptr = random rollouts
     const double* noise;       // slippery FrozenLake: noise[k] of the k-th env.step of a simulation, nullptr = deterministic
     int noise_n;
+    int tpw;                   // trees owned by one warp (its first tpw lanes)
 };
 
 }  // namespace isla

@@ -38,16 +38,18 @@ namespace isla {
 namespace {
 
 constexpr int kTptBlock = 64;
-// trees owned by one warp (its first kTreesPerWarp lanes).  With fewer than 32, the phases that run one lane per tree
-// use part of the warp, but the same trees give more warps per SM to hide the dependent-instruction latency of the
-// cooperative phase.
+// Trees owned by one warp (its first tpw lanes), chosen per launch.  A launch of this kernel is bound by the serial
+// instruction stream of a warp, most of it the cooperative phase, whose length is proportional to the warp's trees.  A
+// batch that does not fill the GPU's resident warps (148 SMs x 14) with 32 trees each is therefore spread over more
+// warps with fewer trees each: the phases that run one lane per tree then use part of the warp, which costs nothing
+// while latency-bound (4096 CartPole trees: 44.6 -> 206 M sims/s).  ISLA_TPW pins it (experiments).
 #ifndef ISLA_TPW
-#define ISLA_TPW 32
+#define ISLA_TPW 0
 #endif
 #ifndef ISLA_TPT_MINBLOCKS
 #define ISLA_TPT_MINBLOCKS 7
 #endif
-constexpr int kTreesPerWarp = ISLA_TPW;
+constexpr int kTreesPerWarpFixed = ISLA_TPW;
 constexpr unsigned kFull = 0xffffffffu;
 
 struct TraceCursor {
@@ -204,9 +206,9 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
     char* const coop_ring = reinterpret_cast<char*>(lnf_smem) + ln_slots * 4;
 
     // scripted (parity) mode drives ONE tree from lane 0 of a single warp; the other lanes are dummies
-    const long long warp_tree0 = ((long long)blockIdx.x * (kTptBlock / 32) + (threadIdx.x >> 5)) * kTreesPerWarp;  // tree of lane 0 (free-running)
+    const long long warp_tree0 = ((long long)blockIdx.x * (kTptBlock / 32) + (threadIdx.x >> 5)) * p.tpw;  // tree of lane 0 (free-running)
     const long long tree = SCRIPTED ? (threadIdx.x == 0 ? p.scripted_tree : p.n_trees)
-                                    : (lane < kTreesPerWarp ? warp_tree0 + lane : p.n_trees);
+                                    : (lane < p.tpw ? warp_tree0 + lane : p.n_trees);
     const bool valid = tree < p.n_trees;
     const long long tix = valid ? tree : 0;
     const long long path_cap = p.block_cap;
@@ -933,7 +935,7 @@ int launch_search(const TptParams& p, bool scripted, cudaStream_t st) {
     if (scripted) {
         tpt_search_kernel<ENV, T, true><<<1, 32, smem, st>>>(p);
     } else {
-        constexpr int kTreesPerBlock = (kTptBlock / 32) * kTreesPerWarp;
+        const int kTreesPerBlock = (kTptBlock / 32) * p.tpw;
         const unsigned grid = (unsigned)((p.n_trees + kTreesPerBlock - 1) / kTreesPerBlock);
         tpt_search_kernel<ENV, T, false><<<grid, kTptBlock, smem, st>>>(p);
     }
@@ -1010,7 +1012,21 @@ int tpt_run(isla_engine* e, int n_sim, long long scripted_tree, const uint8_t* k
     p.ln_count = (int)L.ln_count; p.disc_count = (int)L.disc_count;
     p.ln_in_smem = (L.ln_count * 4 <= 8 * 1024) ? 1 : 0;
     p.heur = e->heur_dev;
-    p.noise = e->noise_dev; p.noise_n = e->noise_n;   // float copy of ln(n) next to the cooperative ring
+    p.noise = e->noise_dev; p.noise_n = e->noise_n;
+    // trees per warp: the fewest (power of two) with which all warps are still resident at once
+    {
+        const long long resident_warps = (long long)(e->sm_count > 0 ? e->sm_count : 148) * ISLA_TPT_MINBLOCKS * (kTptBlock / 32);
+        int tpw = kTreesPerWarpFixed > 0 ? kTreesPerWarpFixed : 1;
+        // ... up to 16: beyond that (65 536 trees and more) two or more waves of 16-tree warps are faster than one wave of
+        // 32-tree warps (measured: 383 vs 371 M sims/s at 65 536 trees, 386 vs 367 M at 131 072)
+        // (deep CartPole paths, where the cooperative phase dominates; FrozenLake's shallow trees skip that phase and are
+        // fastest in one wave: 65 536 trees x 100 sims 2.75 G sims/s with 32 trees per warp, 1.81 G with 16)
+        const int tpw_cap = e->cfg.env_id == ISLA_ENV_CARTPOLE ? 16 : 32;
+        if (kTreesPerWarpFixed <= 0) while (tpw < tpw_cap && (e->cfg.n_trees + tpw - 1) / tpw > resident_warps) tpw <<= 1;
+        const int forced = (e->cfg.tuning >> 8) & 63;   // tuning bits 8..13: trees per warp (A/B timing only)
+        if (forced >= 1 && forced <= 32) tpw = forced;
+        p.tpw = tpw;
+    }   // float copy of ln(n) next to the cooperative ring
     p.tuning = e->cfg.tuning;
     const bool scripted = scripted_tree >= 0;
     const bool f64 = e->cfg.precision == ISLA_PRECISION_F64;

@@ -1,0 +1,19 @@
+import sys, torch
+sys.path.insert(0, ".")
+from islamcts_b200.engine import Engine
+g = torch.Generator().manual_seed(7)
+for env_id, S, md, gam in ((0, 4, 500, 0.99), (3, 1, 1000, 1.0)):
+    for nt in (16, 64, 128, 256, 16384, 32768):
+        roots = (torch.rand((nt, S), generator=g, dtype=torch.float64) - 0.5) * 0.1 if env_id == 0 else torch.zeros((nt, 1), dtype=torch.float64)
+        res = []
+        for kern in (1, 2):
+            nsim = 1000 if env_id == 0 else 100
+            eng = Engine(env_id, n_trees=nt, sim_capacity=nsim, max_depth=md, gamma=gam, C_=1.0 if env_id == 0 else 0.5, kernel=kern, seed=1)
+            eng.set_roots(roots).run(nsim); torch.cuda.synchronize()
+            best = 1e9
+            for _ in range(2):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); eng.set_roots(roots).run(nsim); e1.record(); torch.cuda.synchronize(); best = min(best, e0.elapsed_time(e1))
+            res.append(nt * nsim / best / 1e3)
+            del eng
+        print("env", env_id, "trees", nt, "TPT %.1fM  CTA %.1fM sims/s" % tuple(res), flush=True)
