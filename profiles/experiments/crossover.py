@@ -3,7 +3,7 @@ sys.path.insert(0, ".")
 from islamcts_b200.engine import Engine
 g = torch.Generator().manual_seed(7)
 for env_id, S, md, gam in ((0, 4, 500, 0.99), (3, 1, 1000, 1.0)):
-    for nt in (16, 64, 128, 256, 16384, 32768):
+    for nt in (1, 2, 4, 8, 32):
         roots = (torch.rand((nt, S), generator=g, dtype=torch.float64) - 0.5) * 0.1 if env_id == 0 else torch.zeros((nt, 1), dtype=torch.float64)
         res = []
         for kern in (1, 2):
