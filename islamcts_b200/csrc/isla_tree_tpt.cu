@@ -228,11 +228,12 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
     int plen = 0;        // cached levels [0, plen): PvOwn authoritative, node blocks stale for those edges
     bool pend = false;   // the returns G_l of those levels are still to be added
     const uint32_t tree_id = (uint32_t)(p.tree_id_base + (unsigned long long)tix);
-    Stream ts;
-    ts.resume(p.seed, 0u, tree_id, kStreamTree, valid ? (uint32_t)meta[META_RNG] : 0u);
+    // the tree stream is rarely drawn from (expansion picks, exact UCB ties): only its position is kept in a register and
+    // the Philox state is rebuilt per draw
+    uint32_t rng_used = valid ? (uint32_t)meta[META_RNG] : 0u;
     TraceCursor tc{p.trace_kinds, p.trace_values, p.trace_len, 0, 0};
 
-    unsigned long long c_env = 0, c_roll = 0, c_levels = 0, c_nodes = 0, c_flushed = 0;
+    unsigned int c_env = 0, c_roll = 0, c_levels = 0, c_nodes = 0, c_flushed = 0;   // per thread and launch: 32 bits suffice
     const double gamma = p.gamma, Cexp = p.C;
     const float Cf = (float)p.C;
 
@@ -242,7 +243,12 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
             if (v < 0 || v >= n) { if (!tc.fault) tc.fault = ISLA_ERR_TRACE; return 0; }
             return v;
         } else {
-            return n > 1 ? (int)mulhi_u32(ts.next(), (uint32_t)n) : 0;
+            if (n <= 1) return 0;
+            Stream ts;
+            ts.resume(p.seed, 0u, tree_id, kStreamTree, rng_used);
+            const uint32_t w = ts.next();
+            ++rng_used;
+            return (int)mulhi_u32(w, (uint32_t)n);
         }
     };
     // UCB1 over the A visited children (action_selection_functions.py:9-25).  The reference evaluates the scores
@@ -785,7 +791,7 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
         // G_l = r + gamma * G_{l+1} up the recorded path (mcts_hash.py:126-131, 79-81).  The returns are only
         // WRITTEN to the tree's pending-return row; the next simulation's phase 1a adds them.
         if (mode == MODE_RETURN) {
-            c_levels += (unsigned long long)level + 1ull;
+            c_levels += (unsigned)level + 1u;
             for (int l = level - 1; l >= 0; --l) {
                 G = __dadd_rn(kInterior, __dmul_rn(gamma, G));
                 path_g[l] = G;
@@ -807,18 +813,18 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
         if (plen > 0) write_back(0);
         meta[META_ALLOC] = alloc;
         meta[META_SIMS] = (int32_t)sims_done;
-        meta[META_RNG] = (int32_t)ts.consumed();
+        meta[META_RNG] = (int32_t)rng_used;
         meta[META_FAULT] = fault;
         meta[META_PENDING] = 0;
         if constexpr (SCRIPTED) meta[META_TRACE_POS] = (int32_t)tc.pos;
         // counters (once per thread at kernel end)
-        atomicAdd(p.counters + CNT_ENV_STEPS, c_env);
-        atomicAdd(p.counters + CNT_ROLLOUT_STEPS, c_roll);
-        atomicAdd(p.counters + CNT_LEVELS, c_levels);
+        atomicAdd(p.counters + CNT_ENV_STEPS, (unsigned long long)c_env);
+        atomicAdd(p.counters + CNT_ROLLOUT_STEPS, (unsigned long long)c_roll);
+        atomicAdd(p.counters + CNT_LEVELS, (unsigned long long)c_levels);
         atomicAdd(p.counters + CNT_SIMS, (unsigned long long)s_done);
-        atomicAdd(p.counters + CNT_NODES, c_nodes);
+        atomicAdd(p.counters + CNT_NODES, (unsigned long long)c_nodes);
         if (fault) atomicAdd(p.counters + CNT_FAULTS, 1ull);
-        atomicAdd(p.counters + 6, c_flushed);
+        atomicAdd(p.counters + 6, (unsigned long long)c_flushed);
     }
 }
 
