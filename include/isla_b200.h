@@ -62,7 +62,7 @@ typedef struct {
     int32_t voo_n_samples;      /* voo: samples per expansion; genetic_policy: n_samples */
     int32_t voo_max_try;
     int32_t precision;          /* ISLA_PRECISION_* */
-    int32_t kernel;             /* ISLA_KERNEL_*; AUTO = thread-per-tree for >= 64 vanilla trees on CartPole / FrozenLake with
+    int32_t kernel;             /* ISLA_KERNEL_*; AUTO = thread-per-tree for vanilla trees on CartPole / FrozenLake with
                                  * rollouts_per_leaf <= 1, CTA-per-tree otherwise */
     int32_t block_threads;      /* CTA-per-tree kernel: threads per tree (multiple of 32); 0 = auto */
     int32_t sim_capacity;       /* max cumulative simulations per tree the workspace is sized for */
