@@ -238,3 +238,22 @@ def test_slippery_lake_free_running_equals_oracle(kernel):
     short = Engine(3, n_trees=2, sim_capacity=50, max_depth=40, precision=1, kernel=kernel, seed=1)
     short.set_transition_noise(noise[:3]).set_roots(np.zeros((2, 1))).run(50)
     assert short.counters()["faults"] > 0          # a noise table shorter than the simulation is a loud fault
+
+
+@pytest.mark.parametrize("tpw", [1, 3, 16, 32])
+def test_trees_per_warp_does_not_change_results(tpw):
+    """The launch picks how many trees a warp owns (tuning bits 8..13 pin it for the test): ragged tree counts, partial
+    last warps and every trees-per-warp value build the same trees as the oracle."""
+    from islamcts_b200.engine import Engine
+    n_trees, n_sim = 77, 180
+    roots = np.stack([coracle.env_reset(0, 13, i) for i in range(n_trees)])
+    eng = Engine(0, n_trees=n_trees, sim_capacity=n_sim, max_depth=120, C_=1.0, gamma=0.98, precision=1, kernel=1, seed=77,
+                 tree_id_base=5, tuning=tpw << 8)
+    eng.set_roots(roots).run(n_sim)
+    na, tot = eng.root_stats()
+    cfg = coracle.make_config(0, n_actions=2, max_depth=120, C_=1.0, gamma=0.98, seed=77, tree_id=5)
+    ena, etot, ecnt = coracle.run_many(cfg, roots, n_sim, n_threads=8)
+    np.testing.assert_array_equal(na.cpu().numpy(), ena)
+    np.testing.assert_allclose(tot.cpu().numpy(), etot, rtol=1e-9, atol=1e-9)
+    c = eng.counters()
+    assert c["faults"] == 0 and c["levels"] == ecnt["levels"] and c["rollout_steps"] == ecnt["rollout_steps"]
