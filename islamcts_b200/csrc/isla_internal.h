@@ -44,8 +44,9 @@ struct TptParams {
     void* states;
     double* gfirst;
     int32_t* meta;
-    char* pv_sib;          // [tree][level]  PV cache, static half: edge id (block << 2 | action) + the siblings' statistics
-    char* pv_own;          // [tree][level]  PV cache, dynamic half: {double total; int32 na; int32 pad} of the edge taken
+    char* pv_sta;          // [tree][level]  PV cache, static entry: the siblings' statistics + own_base (see isla_tree_tpt.cu)
+    double* pv_tot;        // [tree][level]  PV cache, dynamic entry: total of the edge taken (its visit count is implicit)
+    uint32_t* pv_edge;     // [tree][level]  PV cache, cold entry: edge id (block << 2 | action), read when a level leaves the cache
     double* path_g;        // [tree][level]  return G backed up through that edge (pending until the next simulation)
     unsigned long long* counters;
     const uint8_t* trace_kinds;

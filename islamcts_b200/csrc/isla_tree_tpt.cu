@@ -113,15 +113,15 @@ __device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.appro
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// shared-memory ring of the cooperative phase, per warp: kSlots slots of {own 32 x 16 B | siblings 32 x sizeof(PvSib) |
-// pending return 32 x 8 B}; the producer runs kAhead = kSlots - 1 tasks in front of the consumer
+// shared-memory ring of the cooperative phase, per warp: kSlots slots of {static entries 32 x sizeof(PvSta) | totals
+// 32 x 8 B | pending returns 32 x 8 B}; the producer runs kAhead = kSlots - 1 tasks in front of the consumer
 #ifndef ISLA_COOP_SLOTS
 #define ISLA_COOP_SLOTS 6
 #endif
 template <int A> struct CoopRing {
     static constexpr int kSlots = A == 2 ? ISLA_COOP_SLOTS : 3;
     static constexpr int kAhead = kSlots - 1;
-    static constexpr int kSlotBytes = 32 * 16 + 32 * (A * 12 - 8) + 32 * 8;   // sizeof(PvSib<A>) = 12 A - 8
+    static constexpr int kSlotBytes = 32 * (A == 2 ? 16 : 48) + 32 * 8 + 32 * 8;
     static constexpr int kWarpBytes = kSlots * kSlotBytes;
 };
 
@@ -129,48 +129,44 @@ enum : int { MODE_DESCEND = 0, MODE_EXPAND = 1, MODE_RETURN = 2, MODE_IDLE = 3 }
 constexpr int kCoopMin = 16;  // deepest cached path in the warp below which phase 1a is skipped
 
 // PV cache (per tree, per level of the last simulation's path; tree-major rows in HBM):
-//   PvOwn  16 B  {double total; int32 na; int32 pad}      statistics of the edge the path takes  (changes every simulation)
-//   PvSib  16 B (A=2) / 48 B (A=4)  {uint32 edge = block<<2|action; int32 na[A-1]; double total[A-1]}
-//                                                         the sibling edges                       (static while on the path)
-//   G       8 B  the return backed up through the edge, pending until the next simulation
-// While a level is cached, PvOwn is the AUTHORITATIVE copy of that edge's statistics; its node block in HBM is stale
-// for that one edge and is written back when the level leaves the path (or at the end of the launch).
-struct __align__(16) PvOwn { double total; int32_t na; int32_t pad; };
-template <int A> struct __align__(16) PvSib { uint32_t edge; int32_t na[A - 1]; double total[A - 1]; };
-static_assert(sizeof(PvOwn) == 16 && sizeof(PvSib<2>) == 16 && sizeof(PvSib<4>) == 48, "PV cache entry sizes");
+//   tot    8 B  double total of the edge the path takes -- the AUTHORITATIVE copy while the level is cached (changes
+//               every simulation: the pending return of the previous simulation is added when the level is re-evaluated)
+//   sta   16 B (A=2) / 48 B (A=4)  {int32 sib_na[A-1]; int32 own_base; double sib_total[A-1]}   static while cached:
+//               the sibling edges' statistics, and own_base = (path edge's na) - (tree's completed simulations) at
+//               caching time.  Every simulation passes through a cached level exactly once, so the path edge's visit
+//               count is own_base + simulations_completed: it is never stored again.
+//   g      8 B  the return backed up through the edge, pending until the next simulation
+//   edge   4 B  block << 2 | action of the path edge: cold, read only where a level leaves the cache
+// While a level is cached its node block in HBM is stale for that one edge; it is written back when the level leaves
+// the path (or at the end of the launch).  Per level and simulation: 32 bytes read, 8 + 8 bytes written.
+template <int A> struct __align__(16) PvSta { int32_t sib_na[A - 1]; int32_t own_base; double sib_total[A - 1]; };
+static_assert(sizeof(PvSta<2>) == 16 && sizeof(PvSta<4>) == 48, "PV cache entry sizes");
 
-__device__ __forceinline__ PvOwn load_own(const char* row, int l) {
-    const int4 v = __ldcg(reinterpret_cast<const int4*>(row) + l);
-    PvOwn o; o.total = __hiloint2double(v.y, v.x); o.na = v.z; o.pad = 0; return o;
-}
-__device__ __forceinline__ void store_own(char* row, int l, double total, int na) {
-    __stcg(reinterpret_cast<int4*>(row) + l, make_int4(__double2loint(total), __double2hiint(total), na, 0));
-}
-template <int A> __device__ __forceinline__ PvSib<A> load_sib(const char* row, int l) {
-    PvSib<A> s;
-    const int4* p = reinterpret_cast<const int4*>(row + (long long)l * sizeof(PvSib<A>));
+template <int A> __device__ __forceinline__ PvSta<A> decode_sta(const int4* p) {
+    PvSta<A> s;
     if constexpr (A == 2) {
-        const int4 v = __ldcg(p);
-        s.edge = (uint32_t)v.x; s.na[0] = v.y; s.total[0] = __hiloint2double(v.w, v.z);
+        const int4 v = p[0];
+        s.sib_na[0] = v.x; s.own_base = v.y; s.sib_total[0] = __hiloint2double(v.w, v.z);
     } else {
-        const int4 v0 = __ldcg(p), v1 = __ldcg(p + 1), v2 = __ldcg(p + 2);
-        s.edge = (uint32_t)v0.x; s.na[0] = v0.y; s.na[1] = v0.z; s.na[2] = v0.w;
-        s.total[0] = __hiloint2double(v1.y, v1.x); s.total[1] = __hiloint2double(v1.w, v1.z); s.total[2] = __hiloint2double(v2.y, v2.x);
+        const int4 v0 = p[0], v1 = p[1], v2 = p[2];
+        s.sib_na[0] = v0.x; s.sib_na[1] = v0.y; s.sib_na[2] = v0.z; s.own_base = v0.w;
+        s.sib_total[0] = __hiloint2double(v1.y, v1.x); s.sib_total[1] = __hiloint2double(v1.w, v1.z);
+        s.sib_total[2] = __hiloint2double(v2.y, v2.x);
     }
     return s;
 }
-template <int A> __device__ __forceinline__ uint32_t load_edge(const char* row, int l) {
-    return __ldcg(reinterpret_cast<const uint32_t*>(row + (long long)l * sizeof(PvSib<A>)));
-}
-template <int A> __device__ __forceinline__ void store_sib(char* row, int l, const PvSib<A>& s) {
-    int4* p = reinterpret_cast<int4*>(row + (long long)l * sizeof(PvSib<A>));
+template <int A> __device__ __forceinline__ void store_sta(char* row, int l, const PvSta<A>& s) {
+    int4* p = reinterpret_cast<int4*>(row + (long long)l * sizeof(PvSta<A>));
     if constexpr (A == 2) {
-        __stcg(p, make_int4((int)s.edge, s.na[0], __double2loint(s.total[0]), __double2hiint(s.total[0])));
+        __stcg(p, make_int4(s.sib_na[0], s.own_base, __double2loint(s.sib_total[0]), __double2hiint(s.sib_total[0])));
     } else {
-        __stcg(p, make_int4((int)s.edge, s.na[0], s.na[1], s.na[2]));
-        __stcg(p + 1, make_int4(__double2loint(s.total[0]), __double2hiint(s.total[0]), __double2loint(s.total[1]), __double2hiint(s.total[1])));
-        __stcg(p + 2, make_int4(__double2loint(s.total[2]), __double2hiint(s.total[2]), 0, 0));
+        __stcg(p, make_int4(s.sib_na[0], s.sib_na[1], s.sib_na[2], s.own_base));
+        __stcg(p + 1, make_int4(__double2loint(s.sib_total[0]), __double2hiint(s.sib_total[0]), __double2loint(s.sib_total[1]), __double2hiint(s.sib_total[1])));
+        __stcg(p + 2, make_int4(__double2loint(s.sib_total[2]), __double2hiint(s.sib_total[2]), 0, 0));
     }
+}
+template <int A> __device__ __forceinline__ int load_own_base(const char* row, int l) {
+    return __ldcg(reinterpret_cast<const int32_t*>(row + (long long)l * sizeof(PvSta<A>)) + (A - 1));
 }
 
 // One simulation of the 32 trees of a warp = four phases.
@@ -212,20 +208,21 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
     const bool valid = tree < p.n_trees;
     const long long tix = valid ? tree : 0;
     const long long path_cap = p.block_cap;
-    constexpr long long kSibBytes = sizeof(PvSib<A>);
+    constexpr long long kStaBytes = sizeof(PvSta<A>);
 
     char* const blocks = p.blocks + tix * p.slots_per_tree * 16;
     T* const states = reinterpret_cast<T*>(p.states) + tix * p.slots_per_tree * S;
     double* const gfirst = p.gfirst + tix * p.slots_per_tree;
     int32_t* const meta = p.meta + tix * META_WORDS;
-    char* const pv_sib = p.pv_sib + tix * path_cap * kSibBytes;  // tree-major rows: [tree][level]
-    char* const pv_own = p.pv_own + tix * path_cap * 16;
+    char* const pv_sta = p.pv_sta + tix * path_cap * kStaBytes;  // tree-major rows: [tree][level]
+    double* const pv_tot = p.pv_tot + tix * path_cap;
+    uint32_t* const pv_edge = p.pv_edge + tix * path_cap;
     double* const path_g = p.path_g + tix * path_cap;
 
     int alloc = valid ? meta[META_ALLOC] : 0;
     uint32_t sims_done = valid ? (uint32_t)meta[META_SIMS] : 0u;
     int fault = valid ? meta[META_FAULT] : 0;
-    int plen = 0;        // cached levels [0, plen): PvOwn authoritative, node blocks stale for those edges
+    int plen = 0;        // cached levels [0, plen): pv_tot authoritative, node blocks stale for those edges
     bool pend = false;   // the returns G_l of those levels are still to be added
     const uint32_t tree_id = (uint32_t)(p.tree_id_base + (unsigned long long)tix);
     // the tree stream is rarely drawn from (expansion picks, exact UCB ties): only its position is kept in a register and
@@ -303,11 +300,12 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
     // pending return if there is one): those levels leave the cache
     auto write_back = [&](int from) {
         for (int l = from; l < plen; ++l) {
-            const PvOwn o = load_own(pv_own, l);
-            const uint32_t e = load_edge<A>(pv_sib, l);
+            const double t_ = __ldcg(pv_tot + l);
+            const uint32_t e = __ldcg(pv_edge + l);
             const double g = pend ? __ldcg(path_g + l) : 0.0;
-            __stcg(total_ptr<A>(blocks, (int)(e >> 2), (int)(e & 3u)), pend ? __dadd_rn(o.total, g) : o.total);
-            __stcg(na_ptr<A>(blocks, (int)(e >> 2), (int)(e & 3u)), o.na + (pend ? 1 : 0));
+            __stcg(total_ptr<A>(blocks, (int)(e >> 2), (int)(e & 3u)), pend ? __dadd_rn(t_, g) : t_);
+            // with a pending return the stored count is one behind: own_base + sims_done either way
+            __stcg(na_ptr<A>(blocks, (int)(e >> 2), (int)(e & 3u)), load_own_base<A>(pv_sta, l) + (int)sims_done);
             ++c_flushed;
         }
         plen = from;
@@ -353,34 +351,34 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
             const unsigned work = __ballot_sync(kFull, my_plen > 0);
             char* const ring = coop_ring + (threadIdx.x >> 5) * (kSlots * kSlotBytes);
             // this lane's three entries inside slot 0, as shared-window addresses
-            const unsigned ring_own = (unsigned)__cvta_generic_to_shared(ring) + lane * 16;
-            const unsigned ring_sib = ring_own - lane * 16 + 512 + lane * (unsigned)kSibBytes;
-            const unsigned ring_g = ring_own - lane * 16 + 512 + 32 * (unsigned)kSibBytes + lane * 8;
+            const unsigned ring_sta = (unsigned)__cvta_generic_to_shared(ring) + lane * (unsigned)kStaBytes;
+            const unsigned ring_tot = (unsigned)__cvta_generic_to_shared(ring) + 32 * (unsigned)kStaBytes + lane * 8;
+            const unsigned ring_g = ring_tot + 256;
             int pj = work ? __ffs(work) - 1 : 32;
             int pL = pj < 32 ? __shfl_sync(kFull, my_plen, pj & 31) : 0;
             int pl = lane;                      // this lane's level of the next task of tree pj
             // this lane's entries of that level in the three rows of tree pj
-            const char* p_own = p.pv_own + ((warp_tree0 + (pj & 31)) * path_cap + lane) * 16;
-            const char* p_sib = p.pv_sib + ((warp_tree0 + (pj & 31)) * path_cap + lane) * kSibBytes;
+            const char* p_sta = p.pv_sta + ((warp_tree0 + (pj & 31)) * path_cap + lane) * kStaBytes;
+            const double* p_tot = p.pv_tot + (warp_tree0 + (pj & 31)) * path_cap + lane;
             const double* p_g = p.path_g + (warp_tree0 + (pj & 31)) * path_cap + lane;
             int issued = 0, consumed = 0;
             unsigned pslot = 0;                 // byte offset of the producer's slot in the ring
             auto issue_one = [&]() {
                 if (pj < 32) {
                     if (pl < pL && issued >= consumed) {   // tasks dropped after an event are stepped over, not copied
-                        cp_async16(ring_own + pslot, p_own);
 #pragma unroll
-                        for (int q = 0; q < (int)(kSibBytes / 16); ++q) cp_async16(ring_sib + pslot + q * 16, p_sib + q * 16);
+                        for (int q = 0; q < (int)(kStaBytes / 16); ++q) cp_async16(ring_sta + pslot + q * 16, p_sta + q * 16);
+                        cp_async8(ring_tot + pslot, p_tot);
                         cp_async8(ring_g + pslot, p_g);
                     }
-                    pl += 32; p_own += 32 * 16; p_sib += 32 * kSibBytes; p_g += 32;
+                    pl += 32; p_sta += 32 * kStaBytes; p_tot += 32; p_g += 32;
                     if (pl - lane >= pL) {
                         const unsigned rest = pj >= 31 ? 0u : (work & (kFull << (pj + 1)));
                         pj = rest ? __ffs(rest) - 1 : 32;
                         pL = pj < 32 ? __shfl_sync(kFull, my_plen, pj & 31) : 0;
                         pl = lane;
-                        p_own = p.pv_own + ((warp_tree0 + (pj & 31)) * path_cap + lane) * 16;
-                        p_sib = p.pv_sib + ((warp_tree0 + (pj & 31)) * path_cap + lane) * kSibBytes;
+                        p_sta = p.pv_sta + ((warp_tree0 + (pj & 31)) * path_cap + lane) * kStaBytes;
+                        p_tot = p.pv_tot + (warp_tree0 + (pj & 31)) * path_cap + lane;
                         p_g = p.path_g + (warp_tree0 + (pj & 31)) * path_cap + lane;
                     }
                 }
@@ -395,42 +393,34 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                 const int Lj = __shfl_sync(kFull, my_plen, j);
                 const long long tj = warp_tree0 + j;
                 char* const bj = p.blocks + tj * p.slots_per_tree * 16;
-                char* const oj = p.pv_own + tj * path_cap * 16;
-                const char* sj = p.pv_sib + tj * path_cap * kSibBytes;
+                double* const oj = p.pv_tot + tj * path_cap;
+                const char* sj = p.pv_sta + tj * path_cap * kStaBytes;
+                const uint32_t* const ej = p.pv_edge + tj * path_cap;
                 const double* gj = p.path_g + tj * path_cap;
+                const int sims_j = (int)__shfl_sync(kFull, sims_done, j);   // the path edge's na (return added) = own_base + sims_j
+                // the edge of the last cached level: it leaves the cache in every simulation (phase 1b re-decides it), so
+                // its id is requested now and has arrived when the rounds are done
+                const uint32_t e_last = __ldcg(ej + (Lj - 1));
                 int event = -1, done_upto = 0;
                 const int rounds = (Lj + 31) >> 5;
                 int rnd = 0;
                 // one level of the cached path, from this lane's entries in ring slot `slot`: adds the pending return
                 // (lazy backup) and decides whether the old decision stands
-                struct Lev { double total; int na; uint32_t edge; bool event; };
+                struct Lev { double total; int na; bool event; };
                 auto eval_level = [&](const char* slot, int l) -> Lev {
                     Lev out;
-                    PvOwn o; PvSib<A> sb;
-                    {
-                        const int4 v = *reinterpret_cast<const int4*>(slot + lane * 16);
-                        o.total = __hiloint2double(v.y, v.x); o.na = v.z;
-                        const int4* sp = reinterpret_cast<const int4*>(slot + 512 + lane * kSibBytes);
-                        if constexpr (A == 2) {
-                            const int4 w = sp[0];
-                            sb.edge = (uint32_t)w.x; sb.na[0] = w.y; sb.total[0] = __hiloint2double(w.w, w.z);
-                        } else {
-                            const int4 v0 = sp[0], v1 = sp[1], v2 = sp[2];
-                            sb.edge = (uint32_t)v0.x; sb.na[0] = v0.y; sb.na[1] = v0.z; sb.na[2] = v0.w;
-                            sb.total[0] = __hiloint2double(v1.y, v1.x); sb.total[1] = __hiloint2double(v1.w, v1.z);
-                            sb.total[2] = __hiloint2double(v2.y, v2.x);
-                        }
-                    }
-                    const double pg = *reinterpret_cast<const double*>(slot + 512 + 32 * kSibBytes + lane * 8);
-                    out.edge = sb.edge;
-                    const int pa = (int)(sb.edge & 3u);
-                    const double new_total = __dadd_rn(o.total, pg);   // lazy backup: the return of the previous simulation
-                    const int new_na = o.na + 1;
+                    const PvSta<A> sb = decode_sta<A>(reinterpret_cast<const int4*>(slot + lane * kStaBytes));
+                    const double own_t = *reinterpret_cast<const double*>(slot + 32 * kStaBytes + lane * 8);
+                    const double pg = *reinterpret_cast<const double*>(slot + 32 * kStaBytes + 256 + lane * 8);
+                    const double new_total = __dadd_rn(own_t, pg);   // lazy backup: the return of the previous simulation
+                    const int new_na = sb.own_base + sims_j;
                     out.total = new_total; out.na = new_na;
+                    const int pa = A == 2 ? 0 : (int)(__ldcg(ej + l) & 3u);
                     bool my_event;
                     if constexpr (A == 2) {
                         // two actions: the old decision stands iff the path edge's score is the UNIQUE maximum
-                        const int sna = sb.na[0];
+                        const int sna = sb.sib_na[0];
+                        (void)pa;
                         if (sna == 0) my_event = true;   // unvisited sibling: phase 1b expands it
                         else {
                             const int ns = new_na + sna + (l > 0 ? 1 : 0);
@@ -438,7 +428,7 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                             if (!(p.tuning & 1)) {
                                 const float lgf = ns < p.ln_count ? (p.ln_in_smem ? lnf_smem[ns] : (float)ln_table[ns]) : (float)::log((double)ns);
                                 const float ro = rcp_approx((float)new_na), rs = rcp_approx((float)sna);
-                                const float qo = (float)new_total * ro, qs = (float)sb.total[0] * rs;
+                                const float qo = (float)new_total * ro, qs = (float)sb.sib_total[0] * rs;
                                 const float eo = Cf * sqrt_approx(lgf * ro), es = Cf * sqrt_approx(lgf * rs);
                                 const float d = (qo + eo) - (qs + es);
                                 const float tol = 1e-5f * fmaxf(fabsf(qo) + fabsf(eo), fabsf(qs) + fabsf(es)) + 1e-30f;
@@ -447,7 +437,7 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                             if (verdict == 0) {
                                 const double lg = ns < p.ln_count ? ln_table[ns] : ::log((double)ns);
                                 const double so = __dadd_rn(__ddiv_rn(new_total, (double)new_na), __dmul_rn(Cexp, __dsqrt_rn(__ddiv_rn(lg, (double)new_na))));
-                                const double ss = __dadd_rn(__ddiv_rn(sb.total[0], (double)sna), __dmul_rn(Cexp, __dsqrt_rn(__ddiv_rn(lg, (double)sna))));
+                                const double ss = __dadd_rn(__ddiv_rn(sb.sib_total[0], (double)sna), __dmul_rn(Cexp, __dsqrt_rn(__ddiv_rn(lg, (double)sna))));
                                 verdict = so > ss ? 1 : -1;   // a tie needs a draw: phase 1b
                             }
                             my_event = verdict < 0;
@@ -461,9 +451,9 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                             if (a == pa) { c.total[a] = new_total; c.na[a] = new_na; }
                             else {
                                 // siblings are stored in ascending action order
-                                double st_ = sb.total[0]; int sn_ = sb.na[0];
+                                double st_ = sb.sib_total[0]; int sn_ = sb.sib_na[0];
 #pragma unroll
-                                for (int q = 1; q < A - 1; ++q) if (q == k) { st_ = sb.total[q]; sn_ = sb.na[q]; }
+                                for (int q = 1; q < A - 1; ++q) if (q == k) { st_ = sb.sib_total[q]; sn_ = sb.sib_na[q]; }
                                 c.total[a] = st_; c.na[a] = sn_; ++k;
                             }
                         }
@@ -483,10 +473,11 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                 // handed over too (phase 1b re-decides it on its block).
                 auto settle_level = [&](const Lev& v, int l) {
                     const bool leaves = (event >= 0 && l >= event) || (event < 0 && l == Lj - 1);
-                    if (!leaves) store_own(oj, l, v.total, v.na);
+                    if (!leaves) __stcg(oj + l, v.total);   // 8 bytes: the visit count is implicit (own_base + sims_done)
                     else {
-                        __stcg(total_ptr<A>(bj, (int)(v.edge >> 2), (int)(v.edge & 3u)), v.total);
-                        __stcg(na_ptr<A>(bj, (int)(v.edge >> 2), (int)(v.edge & 3u)), v.na);
+                        const uint32_t e = (event < 0) ? e_last : __ldcg(ej + l);
+                        __stcg(total_ptr<A>(bj, (int)(e >> 2), (int)(e & 3u)), v.total);
+                        __stcg(na_ptr<A>(bj, (int)(e >> 2), (int)(e & 3u)), v.na);
                     }
                 };
                 // two rounds (64 levels) per iteration.  For two actions both levels of a lane are evaluated in ONE
@@ -507,17 +498,17 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                     va.event = false; vb.event = false;
                     const bool act_a = la < Lj, act_b = two && lb < Lj;
                     if constexpr (A == 2) {
-                        const int4 oa = *reinterpret_cast<const int4*>(slot_a + lane * 16);
-                        const int4 ob = *reinterpret_cast<const int4*>(slot_b + lane * 16);
-                        const int4 sa = *reinterpret_cast<const int4*>(slot_a + 512 + lane * 16);
-                        const int4 sb = *reinterpret_cast<const int4*>(slot_b + 512 + lane * 16);
-                        const double ga = *reinterpret_cast<const double*>(slot_a + 1024 + lane * 8);
-                        const double gb = *reinterpret_cast<const double*>(slot_b + 1024 + lane * 8);
-                        va.total = __dadd_rn(__hiloint2double(oa.y, oa.x), ga);   // lazy backup: the return of the previous simulation
-                        vb.total = __dadd_rn(__hiloint2double(ob.y, ob.x), gb);
-                        va.na = oa.z + 1; vb.na = ob.z + 1;
-                        va.edge = (uint32_t)sa.x; vb.edge = (uint32_t)sb.x;
-                        const int sna_a = sa.y, sna_b = sb.y;
+                        // slot = {static 32 x 16 B | totals 32 x 8 B | pending returns 32 x 8 B}
+                        const int4 sa = *reinterpret_cast<const int4*>(slot_a + lane * 16);
+                        const int4 sb = *reinterpret_cast<const int4*>(slot_b + lane * 16);
+                        const double oa = *reinterpret_cast<const double*>(slot_a + 512 + lane * 8);
+                        const double ob = *reinterpret_cast<const double*>(slot_b + 512 + lane * 8);
+                        const double ga = *reinterpret_cast<const double*>(slot_a + 768 + lane * 8);
+                        const double gb = *reinterpret_cast<const double*>(slot_b + 768 + lane * 8);
+                        va.total = __dadd_rn(oa, ga);   // lazy backup: the return of the previous simulation
+                        vb.total = __dadd_rn(ob, gb);
+                        va.na = sa.y + sims_j; vb.na = sb.y + sims_j;   // own_base + simulations done
+                        const int sna_a = sa.x, sna_b = sb.x;
                         const double st_a = __hiloint2double(sa.w, sa.z), st_b = __hiloint2double(sb.w, sb.z);
                         const int ns_a = va.na + sna_a + (la > 0 ? 1 : 0), ns_b = vb.na + sna_b + 1;
                         // verdict: +1 the old decision stands, -1 it changes (or the sibling is unvisited), 0 undecided
@@ -579,11 +570,11 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                 const int r = event >= 0 ? event : Lj - 1;
                 // levels the verification did not reach leave the cache as well
                 for (int l = done_upto + lane; l < Lj; l += 32) {
-                    const PvOwn o = load_own(oj, l);
-                    const uint32_t e = load_edge<A>(sj, l);
+                    const double ot = __ldcg(oj + l);
+                    const uint32_t e = __ldcg(ej + l);
                     const double pg = __ldcg(gj + l);
-                    __stcg(total_ptr<A>(bj, (int)(e >> 2), (int)(e & 3u)), __dadd_rn(o.total, pg));
-                    __stcg(na_ptr<A>(bj, (int)(e >> 2), (int)(e & 3u)), o.na + 1);
+                    __stcg(total_ptr<A>(bj, (int)(e >> 2), (int)(e & 3u)), __dadd_rn(ot, pg));
+                    __stcg(na_ptr<A>(bj, (int)(e >> 2), (int)(e & 3u)), load_own_base<A>(sj, l) + sims_j);
                 }
                 __syncwarp();
                 if (lane == j) { level = r; plen = r; pend = false; }
@@ -597,7 +588,7 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
         bool fresh = false;  // block just allocated: all children unvisited, nothing to load
         double G = 0.0;
         if (mode == MODE_DESCEND && level > 0) {
-            const uint32_t prev = load_edge<A>(pv_sib, level - 1), here = load_edge<A>(pv_sib, level);
+            const uint32_t prev = __ldcg(pv_edge + level - 1), here = __ldcg(pv_edge + level);
             node_slot = (int)(prev >> 2) * A + (int)(prev & 3u);
             blk = (int)(here >> 2);
         }
@@ -653,8 +644,7 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                     } else {
                         // this level joins the PV cache: own statistics + the siblings', as they are before the backup
                         {
-                            PvSib<A> sb;
-                            sb.edge = ((uint32_t)blk << 2) | (uint32_t)a_sel;
+                            PvSta<A> sb;
                             double ot = c.total[0]; int on_ = c.na[0];
                             int k = 0;
 #pragma unroll
@@ -662,12 +652,14 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                                 if (a == a_sel) { ot = c.total[a]; on_ = c.na[a]; }
                                 else {
 #pragma unroll
-                                    for (int q = 0; q < A - 1; ++q) if (q == k) { sb.total[q] = c.total[a]; sb.na[q] = c.na[a]; }
+                                    for (int q = 0; q < A - 1; ++q) if (q == k) { sb.sib_total[q] = c.total[a]; sb.sib_na[q] = c.na[a]; }
                                     ++k;
                                 }
                             }
-                            store_sib<A>(pv_sib, level, sb);
-                            store_own(pv_own, level, ot, on_);
+                            sb.own_base = on_ - (int)sims_done;   // na with the pending return added = own_base + sims_done
+                            store_sta<A>(pv_sta, level, sb);
+                            __stcg(pv_tot + level, ot);
+                            __stcg(pv_edge + level, ((uint32_t)blk << 2) | (uint32_t)a_sel);
                         }
                         ++level;
                         plen = level;
@@ -968,9 +960,9 @@ int tpt_fill_layout(const isla_config& cfg, isla_layout& lay) {
     lay.state_offset = off; lay.state_stride = lay.slots_per_tree * S * rb; off = up(off + cfg.n_trees * lay.state_stride);
     lay.gfirst_offset = off; lay.gfirst_stride = lay.slots_per_tree * 8; off = up(off + cfg.n_trees * lay.gfirst_stride);
     lay.meta_offset = off; off = up(off + cfg.n_trees * META_WORDS * 4);
-    lay.path_offset = off; off = up(off + cfg.n_trees * blocks * (A == 2 ? 16 : 48));   // PV cache, sibling half
+    lay.path_offset = off; off = up(off + cfg.n_trees * blocks * (A == 2 ? 16 : 48));   // PV cache, static entries
     lay.pathg_offset = off; off = up(off + cfg.n_trees * blocks * 8);                   // pending returns
-    lay.pvown_offset = off; off = up(off + cfg.n_trees * blocks * 16);                  // PV cache, own half
+    lay.pvown_offset = off; off = up(off + cfg.n_trees * blocks * 16);                  // PV cache: own totals + edge ids
     lay.counters_offset = off; off = up(off + 8 * 8);
     add_table_layout(cfg, lay, off);
     lay.s_cap = lay.a_cap = 0; lay.pool_offset = lay.pool_stride = 0;
@@ -1002,8 +994,9 @@ int tpt_run(isla_engine* e, int n_sim, long long scripted_tree, const uint8_t* k
     p.states = e->ws + L.state_offset;
     p.gfirst = (double*)(e->ws + L.gfirst_offset);
     p.meta = (int32_t*)(e->ws + L.meta_offset);
-    p.pv_sib = e->ws + L.path_offset;
-    p.pv_own = e->ws + L.pvown_offset;
+    p.pv_sta = e->ws + L.path_offset;
+    p.pv_tot = (double*)(e->ws + L.pvown_offset);   // the own region holds the total rows (8 B/level), then the edge-id rows (4 B/level)
+    p.pv_edge = (uint32_t*)(e->ws + L.pvown_offset + e->cfg.n_trees * (long long)(e->cfg.sim_capacity + 2) * 8);
     p.path_g = (double*)(e->ws + L.pathg_offset);
     p.counters = (unsigned long long*)(e->ws + L.counters_offset);
     p.trace_kinds = kinds; p.trace_values = values; p.trace_len = trace_len;
