@@ -110,18 +110,21 @@ __device__ __forceinline__ void cp_async8(unsigned smem, const void* g) {
 // MUFU approximations (relative error ~2^-22) for the fp32 screening pass of UCB1; exact float64 decides near-ties
 __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void cp_async4(unsigned smem, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem), "l"(g) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // shared-memory ring of the cooperative phase, per warp: kSlots slots of {static entries 32 x sizeof(PvSta) | totals
 // 32 x 8 B | pending returns 32 x 8 B}; the producer runs kAhead = kSlots - 1 tasks in front of the consumer
 #ifndef ISLA_COOP_SLOTS
-#define ISLA_COOP_SLOTS 6
+#define ISLA_COOP_SLOTS 8
 #endif
 template <int A> struct CoopRing {
     static constexpr int kSlots = A == 2 ? ISLA_COOP_SLOTS : 3;
     static constexpr int kAhead = kSlots - 1;
-    static constexpr int kSlotBytes = 32 * (A == 2 ? 16 : 48) + 32 * 8 + 32 * 8;
+    static constexpr int kSlotBytes = 32 * (A == 2 ? 16 : 48) + 32 * 8 + 32 * 8 + 32 * 4;
     static constexpr int kWarpBytes = kSlots * kSlotBytes;
 };
 
@@ -354,6 +357,7 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
             const unsigned ring_sta = (unsigned)__cvta_generic_to_shared(ring) + lane * (unsigned)kStaBytes;
             const unsigned ring_tot = (unsigned)__cvta_generic_to_shared(ring) + 32 * (unsigned)kStaBytes + lane * 8;
             const unsigned ring_g = ring_tot + 256;
+            const unsigned ring_edge = (unsigned)__cvta_generic_to_shared(ring) + 32 * (unsigned)kStaBytes + 512 + lane * 4;
             int pj = work ? __ffs(work) - 1 : 32;
             int pL = pj < 32 ? __shfl_sync(kFull, my_plen, pj & 31) : 0;
             int pl = lane;                      // this lane's level of the next task of tree pj
@@ -361,17 +365,19 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
             const char* p_sta = p.pv_sta + ((warp_tree0 + (pj & 31)) * path_cap + lane) * kStaBytes;
             const double* p_tot = p.pv_tot + (warp_tree0 + (pj & 31)) * path_cap + lane;
             const double* p_g = p.path_g + (warp_tree0 + (pj & 31)) * path_cap + lane;
+            const uint32_t* p_edge = p.pv_edge + (warp_tree0 + (pj & 31)) * path_cap + lane;
             int issued = 0, consumed = 0;
             unsigned pslot = 0;                 // byte offset of the producer's slot in the ring
             auto issue_one = [&]() {
                 if (pj < 32) {
-                    if (pl < pL && issued >= consumed) {   // tasks dropped after an event are stepped over, not copied
+                    if (pl < pL) {
 #pragma unroll
                         for (int q = 0; q < (int)(kStaBytes / 16); ++q) cp_async16(ring_sta + pslot + q * 16, p_sta + q * 16);
                         cp_async8(ring_tot + pslot, p_tot);
                         cp_async8(ring_g + pslot, p_g);
+                        cp_async4(ring_edge + pslot, p_edge);
                     }
-                    pl += 32; p_sta += 32 * kStaBytes; p_tot += 32; p_g += 32;
+                    pl += 32; p_sta += 32 * kStaBytes; p_tot += 32; p_g += 32; p_edge += 32;
                     if (pl - lane >= pL) {
                         const unsigned rest = pj >= 31 ? 0u : (work & (kFull << (pj + 1)));
                         pj = rest ? __ffs(rest) - 1 : 32;
@@ -380,6 +386,7 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                         p_sta = p.pv_sta + ((warp_tree0 + (pj & 31)) * path_cap + lane) * kStaBytes;
                         p_tot = p.pv_tot + (warp_tree0 + (pj & 31)) * path_cap + lane;
                         p_g = p.path_g + (warp_tree0 + (pj & 31)) * path_cap + lane;
+                        p_edge = p.pv_edge + (warp_tree0 + (pj & 31)) * path_cap + lane;
                     }
                 }
                 cp_async_commit();   // one group per task (an empty one once the sequence is exhausted)
@@ -394,20 +401,12 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                 const long long tj = warp_tree0 + j;
                 char* const bj = p.blocks + tj * p.slots_per_tree * 16;
                 double* const oj = p.pv_tot + tj * path_cap;
-                const char* sj = p.pv_sta + tj * path_cap * kStaBytes;
-                const uint32_t* const ej = p.pv_edge + tj * path_cap;
-                const double* gj = p.path_g + tj * path_cap;
                 const int sims_j = (int)__shfl_sync(kFull, sims_done, j);   // the path edge's na (return added) = own_base + sims_j
-                // the edge of the last cached level: it leaves the cache in every simulation (phase 1b re-decides it), so
-                // its id is requested now and has arrived when the rounds are done
-                const uint32_t e_last = __ldcg(ej + (Lj - 1));
-                int event = -1, done_upto = 0;
-                const int rounds = (Lj + 31) >> 5;
-                int rnd = 0;
+                int event = -1;
                 // one level of the cached path, from this lane's entries in ring slot `slot`: adds the pending return
                 // (lazy backup) and decides whether the old decision stands
-                struct Lev { double total; int na; bool event; };
-                auto eval_level = [&](const char* slot, int l) -> Lev {
+                struct Lev { double total; int na; uint32_t edge; bool event; };
+                auto eval_level = [&](const char* slot, int l, bool decide) -> Lev {
                     Lev out;
                     const PvSta<A> sb = decode_sta<A>(reinterpret_cast<const int4*>(slot + lane * kStaBytes));
                     const double own_t = *reinterpret_cast<const double*>(slot + 32 * kStaBytes + lane * 8);
@@ -415,7 +414,10 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                     const double new_total = __dadd_rn(own_t, pg);   // lazy backup: the return of the previous simulation
                     const int new_na = sb.own_base + sims_j;
                     out.total = new_total; out.na = new_na;
-                    const int pa = A == 2 ? 0 : (int)(__ldcg(ej + l) & 3u);
+                    out.edge = *reinterpret_cast<const uint32_t*>(slot + 32 * kStaBytes + 512 + lane * 4);
+                    out.event = false;
+                    if (!decide) return out;
+                    const int pa = (int)(out.edge & 3u);
                     bool my_event;
                     if constexpr (A == 2) {
                         // two actions: the old decision stands iff the path edge's score is the UNIQUE maximum
@@ -475,7 +477,7 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                     const bool leaves = (event >= 0 && l >= event) || (event < 0 && l == Lj - 1);
                     if (!leaves) __stcg(oj + l, v.total);   // 8 bytes: the visit count is implicit (own_base + sims_done)
                     else {
-                        const uint32_t e = (event < 0) ? e_last : __ldcg(ej + l);
+                        const uint32_t e = v.edge;
                         __stcg(total_ptr<A>(bj, (int)(e >> 2), (int)(e & 3u)), v.total);
                         __stcg(na_ptr<A>(bj, (int)(e >> 2), (int)(e & 3u)), v.na);
                     }
@@ -483,7 +485,10 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                 // two rounds (64 levels) per iteration.  For two actions both levels of a lane are evaluated in ONE
                 // straight-line block (loads, lazy backup, fp32 screening), so that the two dependent chains overlap in
                 // the in-order issue; only undecided near-ties branch to the exact float64 comparison.
-                for (int l0 = 0; l0 < Lj && event < 0;) {
+                // After an event the remaining rounds only flush: the levels leave the cache from the ring entries the
+                // producer has already copied (no evaluation, no second read).
+                for (int l0 = 0; l0 < Lj;) {
+                    const bool decide = event < 0;   // warp-uniform
                     const bool two = l0 + 32 < Lj;
                     const int la = l0 + lane, lb = l0 + 32 + lane;
                     SUB_ADD(u_tree);
@@ -498,7 +503,7 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                     va.event = false; vb.event = false;
                     const bool act_a = la < Lj, act_b = two && lb < Lj;
                     if constexpr (A == 2) {
-                        // slot = {static 32 x 16 B | totals 32 x 8 B | pending returns 32 x 8 B}
+                        // slot = {static 32 x 16 B | totals 32 x 8 B | pending returns 32 x 8 B | edge ids 32 x 4 B}
                         const int4 sa = *reinterpret_cast<const int4*>(slot_a + lane * 16);
                         const int4 sb = *reinterpret_cast<const int4*>(slot_b + lane * 16);
                         const double oa = *reinterpret_cast<const double*>(slot_a + 512 + lane * 8);
@@ -508,6 +513,9 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                         va.total = __dadd_rn(oa, ga);   // lazy backup: the return of the previous simulation
                         vb.total = __dadd_rn(ob, gb);
                         va.na = sa.y + sims_j; vb.na = sb.y + sims_j;   // own_base + simulations done
+                        va.edge = *reinterpret_cast<const uint32_t*>(slot_a + 1024 + lane * 4);
+                        vb.edge = *reinterpret_cast<const uint32_t*>(slot_b + 1024 + lane * 4);
+                        if (decide) {
                         const int sna_a = sa.x, sna_b = sb.x;
                         const double st_a = __hiloint2double(sa.w, sa.z), st_b = __hiloint2double(sb.w, sb.z);
                         const int ns_a = va.na + sna_a + (la > 0 ? 1 : 0), ns_b = vb.na + sna_b + 1;
@@ -544,38 +552,25 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                             if (act_b && ver_b == 0) ver_b = exact(vb.total, vb.na, st_b, sna_b, ns_b);
                         }
                         va.event = ver_a < 0; vb.event = ver_b < 0;
+                        }
                     } else {
-                        if (act_a) va = eval_level(slot_a, la);
-                        if (act_b) vb = eval_level(slot_b, lb);
+                        if (act_a) va = eval_level(slot_a, la, decide);
+                        if (act_b) vb = eval_level(slot_b, lb, decide);
                     }
                     SUB_ADD(u_eval);
-                    const unsigned ea = __ballot_sync(kFull, act_a && va.event);
-                    const unsigned eb = two ? __ballot_sync(kFull, act_b && vb.event) : 0u;
-                    if (ea) event = l0 + __ffs(ea) - 1;
-                    else if (eb) event = l0 + 32 + __ffs(eb) - 1;
+                    if (decide) {
+                        const unsigned ea = __ballot_sync(kFull, act_a && va.event);
+                        const unsigned eb = two ? __ballot_sync(kFull, act_b && vb.event) : 0u;
+                        if (ea) event = l0 + __ffs(ea) - 1;
+                        else if (eb) event = l0 + 32 + __ffs(eb) - 1;
+                    }
                     if (act_a) settle_level(va, la);
                     if (act_b) settle_level(vb, lb);
-                    if (two) { cslot = cslot + kSlotBytes == kSlots * kSlotBytes ? 0u : cslot + kSlotBytes; consumed += 2; rnd += 2; l0 += 64; }
-                    else { ++consumed; ++rnd; l0 += 32; }
-                    done_upto = min(l0, Lj);
+                    if (two) { cslot = cslot + kSlotBytes == kSlots * kSlotBytes ? 0u : cslot + kSlotBytes; consumed += 2; l0 += 64; }
+                    else { ++consumed; l0 += 32; }
                     SUB_ADD(u_settle);
                 }
-                if (rnd < rounds) {
-                    // rounds skipped after an event: their tasks are dropped.  Copies already in flight for them are
-                    // drained first, so that no slot ever has two copies outstanding.
-                    cp_async_wait<0>();
-                    consumed += rounds - rnd;
-                    cslot = (unsigned)(consumed % kSlots) * kSlotBytes;
-                }
                 const int r = event >= 0 ? event : Lj - 1;
-                // levels the verification did not reach leave the cache as well
-                for (int l = done_upto + lane; l < Lj; l += 32) {
-                    const double ot = __ldcg(oj + l);
-                    const uint32_t e = __ldcg(ej + l);
-                    const double pg = __ldcg(gj + l);
-                    __stcg(total_ptr<A>(bj, (int)(e >> 2), (int)(e & 3u)), __dadd_rn(ot, pg));
-                    __stcg(na_ptr<A>(bj, (int)(e >> 2), (int)(e & 3u)), load_own_base<A>(sj, l) + sims_j);
-                }
                 __syncwarp();
                 if (lane == j) { level = r; plen = r; pend = false; }
             }
