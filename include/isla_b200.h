@@ -97,8 +97,8 @@ typedef struct {
     int64_t state_offset, state_stride;     /* env states, state_dim reals per slot */
     int64_t gfirst_offset, gfirst_stride;   /* double per slot: return backed up when the child state was created */
     int64_t meta_offset;                    /* per-tree int32[8]: alloc, sims, rng words consumed, fault, trace pos, pending */
-    int64_t path_offset, pathg_offset;      /* per tree, per level: PV-cache sibling entry (edge id + sibling statistics) and pending return G */
-    int64_t pvown_offset;                   /* per tree, per level: PV-cache own entry {double total; int32 na; int32 pad} */
+    int64_t path_offset, pathg_offset;      /* PV cache: per tree, chunks of 32 path levels {sibling statistics | own totals | pending returns G | edge ids} */
+    int64_t pvown_offset;                   /* (pathg_offset and pvown_offset equal path_offset: those rows live inside the chunks) */
     int64_t counters_offset;                /* int64[8] device counters */
     int64_t ln_offset, ln_count;            /* double ln(n), n < ln_count  (host libm log, like numpy)  */
     int64_t disc_offset, disc_count;        /* double gamma**t, t < disc_count (host libm pow, like CPython) */

@@ -44,10 +44,8 @@ struct TptParams {
     void* states;
     double* gfirst;
     int32_t* meta;
-    char* pv_sta;          // [tree][level]  PV cache, static entry: the siblings' statistics + own_base (see isla_tree_tpt.cu)
-    double* pv_tot;        // [tree][level]  PV cache, dynamic entry: total of the edge taken (its visit count is implicit)
-    uint32_t* pv_edge;     // [tree][level]  PV cache, cold entry: edge id (block << 2 | action), read when a level leaves the cache
-    double* path_g;        // [tree][level]  return G backed up through that edge (pending until the next simulation)
+    char* pv;              // PV cache: per tree, chunks of 32 levels (layout: PvChunk in isla_tree_tpt.cu)
+    long long pv_stride;   // bytes of one tree's chunks
     unsigned long long* counters;
     const uint8_t* trace_kinds;
     const double* trace_values;

@@ -124,7 +124,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 template <int A> struct CoopRing {
     static constexpr int kSlots = A == 2 ? ISLA_COOP_SLOTS : 3;
     static constexpr int kAhead = kSlots - 1;
-    static constexpr int kSlotBytes = 32 * (A == 2 ? 16 : 48) + 32 * 8 + 32 * 8 + 32 * 4;
+    static constexpr int kSlotBytes = 32 * (A == 2 ? 16 : 48) + 32 * 8 + 32 * 8 + 32 * 4;   // = one PV chunk
     static constexpr int kWarpBytes = kSlots * kSlotBytes;
 };
 
@@ -158,8 +158,8 @@ template <int A> __device__ __forceinline__ PvSta<A> decode_sta(const int4* p) {
     }
     return s;
 }
-template <int A> __device__ __forceinline__ void store_sta(char* row, int l, const PvSta<A>& s) {
-    int4* p = reinterpret_cast<int4*>(row + (long long)l * sizeof(PvSta<A>));
+template <int A> __device__ __forceinline__ void store_sta(char* entry, const PvSta<A>& s) {
+    int4* p = reinterpret_cast<int4*>(entry);
     if constexpr (A == 2) {
         __stcg(p, make_int4(s.sib_na[0], s.own_base, __double2loint(s.sib_total[0]), __double2hiint(s.sib_total[0])));
     } else {
@@ -168,9 +168,27 @@ template <int A> __device__ __forceinline__ void store_sta(char* row, int l, con
         __stcg(p + 2, make_int4(__double2loint(s.sib_total[2]), __double2hiint(s.sib_total[2]), 0, 0));
     }
 }
-template <int A> __device__ __forceinline__ int load_own_base(const char* row, int l) {
-    return __ldcg(reinterpret_cast<const int32_t*>(row + (long long)l * sizeof(PvSta<A>)) + (A - 1));
-}
+// HBM layout of the PV cache: per tree, CHUNKS of 32 consecutive levels, each chunk laid out exactly like a ring slot
+//   {static entries 32 x sizeof(PvSta) | totals 32 x 8 B | pending returns 32 x 8 B | edge ids 32 x 4 B}
+// so that a round of the cooperative phase is ONE contiguous copy (1152 B for A = 2) through a single pointer.
+template <int A> struct PvChunk {
+    static constexpr int kSta = (int)sizeof(PvSta<A>);
+    static constexpr int kTot = 32 * kSta, kG = kTot + 256, kEdge = kG + 256, kBytes = kEdge + 128;
+    static constexpr int kPieces = kBytes / 16;              // 16-byte pieces of a chunk (72 / 136)
+    static constexpr int kCopies = (kPieces + 31) / 32;      // cp.async16 per lane and chunk (3 / 5)
+    // first level (within the chunk) a 16-byte piece holds data of
+    __host__ __device__ static constexpr int piece_level(int piece) {
+        return piece * 16 < kTot ? piece * 16 / kSta : (piece * 16 < kG ? (piece * 16 - kTot) / 8
+               : (piece * 16 < kEdge ? (piece * 16 - kG) / 8 : (piece * 16 - kEdge) / 4));
+    }
+    __device__ __forceinline__ static char* chunk(char* pv, int l) { return pv + (long long)(l >> 5) * kBytes; }
+    __device__ __forceinline__ static char* sta(char* pv, int l) { return chunk(pv, l) + (l & 31) * kSta; }
+    __device__ __forceinline__ static double* tot(char* pv, int l) { return reinterpret_cast<double*>(chunk(pv, l) + kTot) + (l & 31); }
+    __device__ __forceinline__ static double* g(char* pv, int l) { return reinterpret_cast<double*>(chunk(pv, l) + kG) + (l & 31); }
+    __device__ __forceinline__ static uint32_t* edge(char* pv, int l) { return reinterpret_cast<uint32_t*>(chunk(pv, l) + kEdge) + (l & 31); }
+    __device__ __forceinline__ static int own_base(char* pv, int l) { return __ldcg(reinterpret_cast<const int32_t*>(sta(pv, l)) + (A - 1)); }
+};
+static_assert(PvChunk<2>::kBytes == 1152 && PvChunk<4>::kBytes == 2176, "PV chunk sizes");
 
 // One simulation of the 32 trees of a warp = four phases.
 //   1a  cooperative verification   for each tree in turn, the 32 lanes take 32 consecutive LEVELS of its cached
@@ -210,17 +228,15 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                                     : (lane < p.tpw ? warp_tree0 + lane : p.n_trees);
     const bool valid = tree < p.n_trees;
     const long long tix = valid ? tree : 0;
-    const long long path_cap = p.block_cap;
     constexpr long long kStaBytes = sizeof(PvSta<A>);
+    using PC = PvChunk<A>;
+    static_assert(PC::kBytes == kSlotBytes, "a ring slot mirrors a PV chunk");
 
     char* const blocks = p.blocks + tix * p.slots_per_tree * 16;
     T* const states = reinterpret_cast<T*>(p.states) + tix * p.slots_per_tree * S;
     double* const gfirst = p.gfirst + tix * p.slots_per_tree;
     int32_t* const meta = p.meta + tix * META_WORDS;
-    char* const pv_sta = p.pv_sta + tix * path_cap * kStaBytes;  // tree-major rows: [tree][level]
-    double* const pv_tot = p.pv_tot + tix * path_cap;
-    uint32_t* const pv_edge = p.pv_edge + tix * path_cap;
-    double* const path_g = p.path_g + tix * path_cap;
+    char* const pv = p.pv + tix * p.pv_stride;  // this tree's PV chunks
 
     int alloc = valid ? meta[META_ALLOC] : 0;
     uint32_t sims_done = valid ? (uint32_t)meta[META_SIMS] : 0u;
@@ -303,12 +319,12 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
     // pending return if there is one): those levels leave the cache
     auto write_back = [&](int from) {
         for (int l = from; l < plen; ++l) {
-            const double t_ = __ldcg(pv_tot + l);
-            const uint32_t e = __ldcg(pv_edge + l);
-            const double g = pend ? __ldcg(path_g + l) : 0.0;
+            const double t_ = __ldcg(PC::tot(pv, l));
+            const uint32_t e = __ldcg(PC::edge(pv, l));
+            const double g = pend ? __ldcg(PC::g(pv, l)) : 0.0;
             __stcg(total_ptr<A>(blocks, (int)(e >> 2), (int)(e & 3u)), pend ? __dadd_rn(t_, g) : t_);
             // with a pending return the stored count is one behind: own_base + sims_done either way
-            __stcg(na_ptr<A>(blocks, (int)(e >> 2), (int)(e & 3u)), load_own_base<A>(pv_sta, l) + (int)sims_done);
+            __stcg(na_ptr<A>(blocks, (int)(e >> 2), (int)(e & 3u)), PC::own_base(pv, l) + (int)sims_done);
             ++c_flushed;
         }
         plen = from;
@@ -346,47 +362,36 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
             if (live && plen > 0) write_back(0);
         } else {
             // The rounds of all 32 trees form ONE sequence of tasks (tree j, levels l0..l0+31).  A producer cursor runs
-            // kAhead tasks in front of the consumer and copies each lane's entries (own 16 B, siblings, pending return)
-            // into a per-warp shared-memory ring with cp.async: the L2/HBM latency of a round is overlapped with the
-            // evaluation of the kAhead rounds before it, across tree boundaries.  Every lane reads back only what it
-            // copied itself, so cp.async.wait_group is the only synchronisation.
+            // kAhead tasks in front of the consumer and copies the task's PV chunk (one contiguous piece of HBM, 16 bytes
+            // per lane and cp.async) into a per-warp shared-memory ring: the L2/HBM latency of a round is overlapped with
+            // the evaluation of the kAhead rounds before it, across tree boundaries.  Lanes read entries other lanes
+            // copied: cp.async.wait_group + __syncwarp publish a slot, a second __syncwarp frees it for the producer.
             const int my_plen = (live && pend) ? plen : 0;
             const unsigned work = __ballot_sync(kFull, my_plen > 0);
             char* const ring = coop_ring + (threadIdx.x >> 5) * (kSlots * kSlotBytes);
-            // this lane's three entries inside slot 0, as shared-window addresses
-            const unsigned ring_sta = (unsigned)__cvta_generic_to_shared(ring) + lane * (unsigned)kStaBytes;
-            const unsigned ring_tot = (unsigned)__cvta_generic_to_shared(ring) + 32 * (unsigned)kStaBytes + lane * 8;
-            const unsigned ring_g = ring_tot + 256;
-            const unsigned ring_edge = (unsigned)__cvta_generic_to_shared(ring) + 32 * (unsigned)kStaBytes + 512 + lane * 4;
+            // this lane's 16-byte pieces of a chunk: piece q = lane + 32 q, at the same offset in the ring slot
+            const unsigned ring_dst = (unsigned)__cvta_generic_to_shared(ring) + lane * 16;
+            int plv[PC::kCopies];               // first level (within the chunk) piece q holds data of
+#pragma unroll
+            for (int q = 0; q < PC::kCopies; ++q) plv[q] = lane + 32 * q < PC::kPieces ? PC::piece_level(lane + 32 * q) : (1 << 30);
             int pj = work ? __ffs(work) - 1 : 32;
             int pL = pj < 32 ? __shfl_sync(kFull, my_plen, pj & 31) : 0;
-            int pl = lane;                      // this lane's level of the next task of tree pj
-            // this lane's entries of that level in the three rows of tree pj
-            const char* p_sta = p.pv_sta + ((warp_tree0 + (pj & 31)) * path_cap + lane) * kStaBytes;
-            const double* p_tot = p.pv_tot + (warp_tree0 + (pj & 31)) * path_cap + lane;
-            const double* p_g = p.path_g + (warp_tree0 + (pj & 31)) * path_cap + lane;
-            const uint32_t* p_edge = p.pv_edge + (warp_tree0 + (pj & 31)) * path_cap + lane;
+            int pl = 0;                         // first level of the next task of tree pj
+            const char* p_src = p.pv + (warp_tree0 + (pj & 31)) * p.pv_stride + lane * 16;
             int issued = 0, consumed = 0;
             unsigned pslot = 0;                 // byte offset of the producer's slot in the ring
             auto issue_one = [&]() {
                 if (pj < 32) {
-                    if (pl < pL) {
 #pragma unroll
-                        for (int q = 0; q < (int)(kStaBytes / 16); ++q) cp_async16(ring_sta + pslot + q * 16, p_sta + q * 16);
-                        cp_async8(ring_tot + pslot, p_tot);
-                        cp_async8(ring_g + pslot, p_g);
-                        cp_async4(ring_edge + pslot, p_edge);
-                    }
-                    pl += 32; p_sta += 32 * kStaBytes; p_tot += 32; p_g += 32; p_edge += 32;
-                    if (pl - lane >= pL) {
+                    for (int q = 0; q < PC::kCopies; ++q)   // pieces that only hold levels beyond the path are not copied
+                        if (pl + plv[q] < pL) cp_async16(ring_dst + pslot + q * 512, p_src + q * 512);
+                    pl += 32; p_src += PC::kBytes;
+                    if (pl >= pL) {
                         const unsigned rest = pj >= 31 ? 0u : (work & (kFull << (pj + 1)));
                         pj = rest ? __ffs(rest) - 1 : 32;
                         pL = pj < 32 ? __shfl_sync(kFull, my_plen, pj & 31) : 0;
-                        pl = lane;
-                        p_sta = p.pv_sta + ((warp_tree0 + (pj & 31)) * path_cap + lane) * kStaBytes;
-                        p_tot = p.pv_tot + (warp_tree0 + (pj & 31)) * path_cap + lane;
-                        p_g = p.path_g + (warp_tree0 + (pj & 31)) * path_cap + lane;
-                        p_edge = p.pv_edge + (warp_tree0 + (pj & 31)) * path_cap + lane;
+                        pl = 0;
+                        p_src = p.pv + (warp_tree0 + (pj & 31)) * p.pv_stride + lane * 16;
                     }
                 }
                 cp_async_commit();   // one group per task (an empty one once the sequence is exhausted)
@@ -400,7 +405,7 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                 const int Lj = __shfl_sync(kFull, my_plen, j);
                 const long long tj = warp_tree0 + j;
                 char* const bj = p.blocks + tj * p.slots_per_tree * 16;
-                double* const oj = p.pv_tot + tj * path_cap;
+                char* const wr_tot = p.pv + tj * p.pv_stride + PC::kTot + lane * 8;   // this lane's total in chunk 0
                 const int sims_j = (int)__shfl_sync(kFull, sims_done, j);   // the path edge's na (return added) = own_base + sims_j
                 int event = -1;
                 // one level of the cached path, from this lane's entries in ring slot `slot`: adds the pending return
@@ -475,7 +480,8 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                 // handed over too (phase 1b re-decides it on its block).
                 auto settle_level = [&](const Lev& v, int l) {
                     const bool leaves = (event >= 0 && l >= event) || (event < 0 && l == Lj - 1);
-                    if (!leaves) __stcg(oj + l, v.total);   // 8 bytes: the visit count is implicit (own_base + sims_done)
+                    // 8 bytes: the visit count is implicit (own_base + sims_done)
+                    if (!leaves) __stcg(reinterpret_cast<double*>(wr_tot + (long long)(l >> 5) * PC::kBytes), v.total);
                     else {
                         const uint32_t e = v.edge;
                         __stcg(total_ptr<A>(bj, (int)(e >> 2), (int)(e & 3u)), v.total);
@@ -495,6 +501,7 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                     while (issued < consumed + kAhead) issue_one();
                     SUB_ADD(u_issue);
                     cp_async_wait<kAhead - 2>();
+                    __syncwarp();
                     SUB_ADD(u_wait);
                     const char* const slot_a = ring + cslot;
                     cslot = cslot + kSlotBytes == kSlots * kSlotBytes ? 0u : cslot + kSlotBytes;
@@ -568,6 +575,7 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                     if (act_b) settle_level(vb, lb);
                     if (two) { cslot = cslot + kSlotBytes == kSlots * kSlotBytes ? 0u : cslot + kSlotBytes; consumed += 2; l0 += 64; }
                     else { ++consumed; l0 += 32; }
+                    __syncwarp();   // the slots just read may be overwritten by the next issue
                     SUB_ADD(u_settle);
                 }
                 const int r = event >= 0 ? event : Lj - 1;
@@ -583,7 +591,7 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
         bool fresh = false;  // block just allocated: all children unvisited, nothing to load
         double G = 0.0;
         if (mode == MODE_DESCEND && level > 0) {
-            const uint32_t prev = __ldcg(pv_edge + level - 1), here = __ldcg(pv_edge + level);
+            const uint32_t prev = __ldcg(PC::edge(pv, level - 1)), here = __ldcg(PC::edge(pv, level));
             node_slot = (int)(prev >> 2) * A + (int)(prev & 3u);
             blk = (int)(here >> 2);
         }
@@ -652,9 +660,9 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                                 }
                             }
                             sb.own_base = on_ - (int)sims_done;   // na with the pending return added = own_base + sims_done
-                            store_sta<A>(pv_sta, level, sb);
-                            __stcg(pv_tot + level, ot);
-                            __stcg(pv_edge + level, ((uint32_t)blk << 2) | (uint32_t)a_sel);
+                            store_sta<A>(PC::sta(pv, level), sb);
+                            __stcg(PC::tot(pv, level), ot);
+                            __stcg(PC::edge(pv, level), ((uint32_t)blk << 2) | (uint32_t)a_sel);
                         }
                         ++level;
                         plen = level;
@@ -781,7 +789,7 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
             c_levels += (unsigned)level + 1u;
             for (int l = level - 1; l >= 0; --l) {
                 G = __dadd_rn(kInterior, __dmul_rn(gamma, G));
-                path_g[l] = G;
+                *PC::g(pv, l) = G;
             }
             pend = level > 0;
             ++sims_done; ++s_done;
@@ -879,11 +887,11 @@ __global__ void tpt_best_kernel(const char* blocks, int32_t* meta, long long n_t
 // level-synchronous like the CTA engine's.  A visited edge whose child has no block yet, or is terminal, is a leaf state
 // one level below its block.  Scratch: the tree's edge-id row of the PV cache (free between launches), as {level, owner}.
 __global__ void __launch_bounds__(256) tpt_depth_stats_kernel(const char* blocks_all, const int32_t* meta_all, char* scratch_all,
-                                                              long long slots_per_tree, long long path_cap, int A, long long tree,
+                                                              long long slots_per_tree, long long scratch_stride, int A, long long tree,
                                                               int cap, int32_t* dmax, double* dmean, int32_t* count) {
     const char* blocks = blocks_all + tree * slots_per_tree * 16;
     const int alloc = meta_all[tree * META_WORDS + META_ALLOC];
-    int2* const tag = reinterpret_cast<int2*>(scratch_all + tree * path_cap * 16);   // {level, root-child rank} per block
+    int2* const tag = reinterpret_cast<int2*>(scratch_all + tree * scratch_stride);   // {level, root-child rank} per block
     const int tid = threadIdx.x, nt = blockDim.x;
     __shared__ int changed, n_root;
     __shared__ int leaves[4];
@@ -938,6 +946,11 @@ int launch_search(const TptParams& p, bool scripted, cudaStream_t st) {
 
 }  // namespace
 
+// bytes of one tree's PV chunks
+static long long tpt_pv_stride(long long blocks, int A) {
+    return (blocks + 31) / 32 * (A == 2 ? PvChunk<2>::kBytes : PvChunk<4>::kBytes);
+}
+
 int tpt_fill_layout(const isla_config& cfg, isla_layout& lay) {
     const int A = env_n_actions(cfg.env_id), S = env_state_dim(cfg.env_id);
     if (A == 0 || cfg.agent != ISLA_AGENT_VANILLA) { set_error("thread-per-tree kernel: vanilla agent on a discrete env only"); return ISLA_ERR_INVALID; }
@@ -955,9 +968,9 @@ int tpt_fill_layout(const isla_config& cfg, isla_layout& lay) {
     lay.state_offset = off; lay.state_stride = lay.slots_per_tree * S * rb; off = up(off + cfg.n_trees * lay.state_stride);
     lay.gfirst_offset = off; lay.gfirst_stride = lay.slots_per_tree * 8; off = up(off + cfg.n_trees * lay.gfirst_stride);
     lay.meta_offset = off; off = up(off + cfg.n_trees * META_WORDS * 4);
-    lay.path_offset = off; off = up(off + cfg.n_trees * blocks * (A == 2 ? 16 : 48));   // PV cache, static entries
-    lay.pathg_offset = off; off = up(off + cfg.n_trees * blocks * 8);                   // pending returns
-    lay.pvown_offset = off; off = up(off + cfg.n_trees * blocks * 16);                  // PV cache: own totals + edge ids
+    // PV cache: per tree ceil(blocks / 32) chunks of 32 levels (static entries, totals, pending returns, edge ids)
+    lay.path_offset = off; off = up(off + cfg.n_trees * tpt_pv_stride(blocks, A));
+    lay.pathg_offset = lay.pvown_offset = lay.path_offset;   // pending returns and own totals live inside the chunks
     lay.counters_offset = off; off = up(off + 8 * 8);
     add_table_layout(cfg, lay, off);
     lay.s_cap = lay.a_cap = 0; lay.pool_offset = lay.pool_stride = 0;
@@ -989,10 +1002,8 @@ int tpt_run(isla_engine* e, int n_sim, long long scripted_tree, const uint8_t* k
     p.states = e->ws + L.state_offset;
     p.gfirst = (double*)(e->ws + L.gfirst_offset);
     p.meta = (int32_t*)(e->ws + L.meta_offset);
-    p.pv_sta = e->ws + L.path_offset;
-    p.pv_tot = (double*)(e->ws + L.pvown_offset);   // the own region holds the total rows (8 B/level), then the edge-id rows (4 B/level)
-    p.pv_edge = (uint32_t*)(e->ws + L.pvown_offset + e->cfg.n_trees * (long long)(e->cfg.sim_capacity + 2) * 8);
-    p.path_g = (double*)(e->ws + L.pathg_offset);
+    p.pv = e->ws + L.path_offset;
+    p.pv_stride = tpt_pv_stride((long long)e->cfg.sim_capacity + 2, L.n_actions);
     p.counters = (unsigned long long*)(e->ws + L.counters_offset);
     p.trace_kinds = kinds; p.trace_values = values; p.trace_len = trace_len;
     p.n_trees = e->cfg.n_trees; p.slots_per_tree = L.slots_per_tree; p.scripted_tree = scripted_tree;
@@ -1046,8 +1057,8 @@ int tpt_root_stats(isla_engine* e, int64_t* na_dev, double* total_dev, cudaStrea
 
 int tpt_depth_stats(isla_engine* e, long long tree, int cap, int32_t* dmax, double* dmean, int32_t* count, cudaStream_t st) {
     const isla_layout& L = e->lay;
-    tpt_depth_stats_kernel<<<1, 256, 0, st>>>(e->ws + L.rec_offset, (const int32_t*)(e->ws + L.meta_offset), e->ws + L.pvown_offset,
-                                            L.slots_per_tree, L.slots_per_tree / L.n_actions, L.n_actions, tree, cap, dmax, dmean, count);
+    tpt_depth_stats_kernel<<<1, 256, 0, st>>>(e->ws + L.rec_offset, (const int32_t*)(e->ws + L.meta_offset), e->ws + L.path_offset,
+                                            L.slots_per_tree, tpt_pv_stride(L.slots_per_tree / L.n_actions, L.n_actions), L.n_actions, tree, cap, dmax, dmean, count);
     ISLA_CUDA_OK(cudaGetLastError());
     return 0;
 }
