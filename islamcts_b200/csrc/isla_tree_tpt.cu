@@ -787,9 +787,18 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
         // WRITTEN to the tree's pending-return row; the next simulation's phase 1a adds them.
         if (mode == MODE_RETURN) {
             c_levels += (unsigned)level + 1u;
-            for (int l = level - 1; l >= 0; --l) {
+            int l = level - 1;
+            for (; l >= 0 && (l & 3) != 3; --l) {
                 G = __dadd_rn(kInterior, __dmul_rn(gamma, G));
                 *PC::g(pv, l) = G;
+            }
+            for (; l >= 3; l -= 4) {   // four levels of one chunk per address computation
+                double* const q = PC::g(pv, l - 3);
+#pragma unroll
+                for (int i = 3; i >= 0; --i) {
+                    G = __dadd_rn(kInterior, __dmul_rn(gamma, G));
+                    q[i] = G;
+                }
             }
             pend = level > 0;
             ++sims_done; ++s_done;
