@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
         int warp_max_plen = (live && pend) ? plen : 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) warp_max_plen = max(warp_max_plen, __shfl_xor_sync(kFull, warp_max_plen, o));
-        if (SCRIPTED || warp_max_plen < kCoopMin) {
+        if (SCRIPTED || warp_max_plen < ((p.tuning & 2) ? 1 : kCoopMin)) {   // tuning bit 1: verify cooperatively at any depth (tests)
             if (live && plen > 0) write_back(0);
         } else {
             // The rounds of all 32 trees form ONE sequence of tasks (tree j, levels l0..l0+31).  A producer cursor runs

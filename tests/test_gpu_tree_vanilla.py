@@ -257,3 +257,28 @@ def test_trees_per_warp_does_not_change_results(tpw):
     np.testing.assert_allclose(tot.cpu().numpy(), etot, rtol=1e-9, atol=1e-9)
     c = eng.counters()
     assert c["faults"] == 0 and c["levels"] == ecnt["levels"] and c["rollout_steps"] == ecnt["rollout_steps"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env_id,n_sim,max_depth,C,gamma", [(3, 400, 60, 0.3, 0.97), (0, 250, 500, 1.0, 0.99)])
+def test_cooperative_verification_at_any_depth_equals_oracle(env_id, n_sim, max_depth, C, gamma):
+    """FrozenLake's trees are too shallow to reach the cooperative verification (phase 1a starts at 16 cached levels),
+    so its four-action variant (48-byte static entries, 2176-byte chunks) would go untested: tuning bit 1 lowers the
+    threshold to one level.  Results must not change: same Philox streams as the C oracle, bit-equal counts."""
+    from islamcts_b200.engine import Engine
+    n_trees, A = 96, (2 if env_id == 0 else 4)
+    roots = np.stack([coracle.env_reset(env_id, 5, i) for i in range(n_trees)])
+    eng = Engine(env_id, n_trees=n_trees, sim_capacity=n_sim, max_depth=max_depth, C_=C, gamma=gamma, precision=1,
+                 kernel=1, seed=77, tree_id_base=300, tuning=2)
+    eng.set_roots(roots).run(n_sim)
+    na, tot = eng.root_stats()
+    cfg = coracle.make_config(env_id, n_actions=A, max_depth=max_depth, C_=C, gamma=gamma, seed=77, tree_id=300)
+    ena, etot, ecnt = coracle.run_many(cfg, roots, n_sim, n_threads=8)
+    np.testing.assert_array_equal(na.cpu().numpy(), ena)
+    np.testing.assert_allclose(tot.cpu().numpy(), etot, rtol=1e-9, atol=1e-9)
+    cnt = eng.counters()
+    assert cnt["faults"] == 0 and cnt["levels"] == ecnt["levels"] and cnt["rollout_steps"] == ecnt["rollout_steps"]
+    c3 = coracle.make_config(env_id, n_actions=A, max_depth=max_depth, C_=C, gamma=gamma, seed=77, tree_id=303)
+    t3 = coracle.Tree(c3, roots[3])
+    t3.run(n_sim)
+    assert_tree_equal(eng.export_tree(3), {"tree_" + k: v for k, v in t3.serialise().items()})
