@@ -66,7 +66,7 @@ typedef struct {
                                  * rollouts_per_leaf <= 1, CTA-per-tree otherwise */
     int32_t block_threads;      /* CTA-per-tree kernel: threads per tree (multiple of 32); 0 = auto */
     int32_t sim_capacity;       /* max cumulative simulations per tree the workspace is sized for */
-    int32_t tuning;             /* experiment flags for A/B timing; 0 = defaults */
+    int32_t tuning;             /* experiment flags for A/B timing and tests; 0 = defaults */
     int32_t action_grid0;       /* ISLA_ENV_CURVE: DiscreteCurveEnv([g0, g1]) = g0 accelerations x g1 steering angles */
     int32_t action_grid1;       /*   (curve_env.py:184-199; n_actions = g0*g1 <= 128); both 0 = the continuous 2-D CurveEnv box */
     int32_t cluster_ctas;       /* CTA-per-tree kernel: thread blocks (one thread-block cluster) that share one tree's leaf-parallel

@@ -121,6 +121,9 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 #ifndef ISLA_COOP_SLOTS
 #define ISLA_COOP_SLOTS 8
 #endif
+#ifndef ISLA_COOP_NR
+#define ISLA_COOP_NR 2
+#endif
 template <int A> struct CoopRing {
     static constexpr int kSlots = A == 2 ? ISLA_COOP_SLOTS : 3;
     static constexpr int kAhead = kSlots - 1;
@@ -408,6 +411,8 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                 char* const wr_tot = p.pv + tj * p.pv_stride + PC::kTot + lane * 8;   // this lane's total in chunk 0
                 const int sims_j = (int)__shfl_sync(kFull, sims_done, j);   // the path edge's na (return added) = own_base + sims_j
                 int event = -1;
+                constexpr int NR = A == 2 ? ISLA_COOP_NR : 2;   // rounds (levels per lane) evaluated together
+                static_assert(NR >= 1 && NR <= kAhead, "rounds per iteration");
                 // one level of the cached path, from this lane's entries in ring slot `slot`: adds the pending return
                 // (lazy backup) and decides whether the old decision stands
                 struct Lev { double total; int na; uint32_t edge; bool event; };
@@ -495,86 +500,111 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                 // producer has already copied (no evaluation, no second read).
                 for (int l0 = 0; l0 < Lj;) {
                     const bool decide = event < 0;   // warp-uniform
-                    const bool two = l0 + 32 < Lj;
-                    const int la = l0 + lane, lb = l0 + 32 + lane;
+                    const int nr = min(NR, (Lj - l0 + 31) >> 5);   // rounds of this iteration
                     SUB_ADD(u_tree);
                     while (issued < consumed + kAhead) issue_one();
                     SUB_ADD(u_issue);
-                    cp_async_wait<kAhead - 2>();
+                    cp_async_wait<kAhead - NR>();
                     __syncwarp();
                     SUB_ADD(u_wait);
-                    const char* const slot_a = ring + cslot;
-                    cslot = cslot + kSlotBytes == kSlots * kSlotBytes ? 0u : cslot + kSlotBytes;
-                    const char* const slot_b = ring + cslot;
-                    Lev va, vb;
-                    va.event = false; vb.event = false;
-                    const bool act_a = la < Lj, act_b = two && lb < Lj;
+                    const char* slot[NR];
+                    bool act[NR];
+                    Lev v[NR];
+                    {
+                        unsigned cs = cslot;
+#pragma unroll
+                        for (int r = 0; r < NR; ++r) {
+                            slot[r] = ring + cs;
+                            cs = cs + kSlotBytes == kSlots * kSlotBytes ? 0u : cs + kSlotBytes;
+                            act[r] = r < nr && l0 + 32 * r + lane < Lj;
+                            v[r].event = false;
+                        }
+                    }
                     if constexpr (A == 2) {
                         // slot = {static 32 x 16 B | totals 32 x 8 B | pending returns 32 x 8 B | edge ids 32 x 4 B}
-                        const int4 sa = *reinterpret_cast<const int4*>(slot_a + lane * 16);
-                        const int4 sb = *reinterpret_cast<const int4*>(slot_b + lane * 16);
-                        const double oa = *reinterpret_cast<const double*>(slot_a + 512 + lane * 8);
-                        const double ob = *reinterpret_cast<const double*>(slot_b + 512 + lane * 8);
-                        const double ga = *reinterpret_cast<const double*>(slot_a + 768 + lane * 8);
-                        const double gb = *reinterpret_cast<const double*>(slot_b + 768 + lane * 8);
-                        va.total = __dadd_rn(oa, ga);   // lazy backup: the return of the previous simulation
-                        vb.total = __dadd_rn(ob, gb);
-                        va.na = sa.y + sims_j; vb.na = sb.y + sims_j;   // own_base + simulations done
-                        va.edge = *reinterpret_cast<const uint32_t*>(slot_a + 1024 + lane * 4);
-                        vb.edge = *reinterpret_cast<const uint32_t*>(slot_b + 1024 + lane * 4);
+                        // (slots beyond nr hold other trees' rounds or copies in flight: read, never used)
+                        int4 sv[NR];
+                        double ov[NR], gv[NR];
+#pragma unroll
+                        for (int r = 0; r < NR; ++r) sv[r] = *reinterpret_cast<const int4*>(slot[r] + lane * 16);
+#pragma unroll
+                        for (int r = 0; r < NR; ++r) ov[r] = *reinterpret_cast<const double*>(slot[r] + 512 + lane * 8);
+#pragma unroll
+                        for (int r = 0; r < NR; ++r) gv[r] = *reinterpret_cast<const double*>(slot[r] + 768 + lane * 8);
+#pragma unroll
+                        for (int r = 0; r < NR; ++r) {
+                            v[r].total = __dadd_rn(ov[r], gv[r]);   // lazy backup: the return of the previous simulation
+                            v[r].na = sv[r].y + sims_j;             // own_base + simulations done
+                            v[r].edge = *reinterpret_cast<const uint32_t*>(slot[r] + 1024 + lane * 4);
+                        }
                         if (decide) {
-                        const int sna_a = sa.x, sna_b = sb.x;
-                        const double st_a = __hiloint2double(sa.w, sa.z), st_b = __hiloint2double(sb.w, sb.z);
-                        const int ns_a = va.na + sna_a + (la > 0 ? 1 : 0), ns_b = vb.na + sna_b + 1;
-                        // verdict: +1 the old decision stands, -1 it changes (or the sibling is unvisited), 0 undecided
-                        int ver_a = 0, ver_b = 0;
-                        if (!(p.tuning & 1)) {
-                            const int ia = min(max(ns_a, 0), p.ln_count - 1), ib = min(max(ns_b, 0), p.ln_count - 1);
-                            const float lga = p.ln_in_smem ? lnf_smem[ia] : (float)__ldg(ln_table + ia);
-                            const float lgb = p.ln_in_smem ? lnf_smem[ib] : (float)__ldg(ln_table + ib);
-                            const float roa = rcp_approx((float)va.na), rsa = rcp_approx((float)sna_a);
-                            const float rob = rcp_approx((float)vb.na), rsb = rcp_approx((float)sna_b);
-                            const float qoa = (float)va.total * roa, qsa = (float)st_a * rsa;
-                            const float qob = (float)vb.total * rob, qsb = (float)st_b * rsb;
-                            const float eoa = Cf * sqrt_approx(lga * roa), esa = Cf * sqrt_approx(lga * rsa);
-                            const float eob = Cf * sqrt_approx(lgb * rob), esb = Cf * sqrt_approx(lgb * rsb);
-                            const float da = (qoa + eoa) - (qsa + esa), db = (qob + eob) - (qsb + esb);
-                            const float ta = 1e-5f * fmaxf(fabsf(qoa) + fabsf(eoa), fabsf(qsa) + fabsf(esa)) + 1e-30f;
-                            const float tb = 1e-5f * fmaxf(fabsf(qob) + fabsf(eob), fabsf(qsb) + fabsf(esb)) + 1e-30f;
-                            ver_a = da > ta ? 1 : (da < -ta ? -1 : 0);
-                            ver_b = db > tb ? 1 : (db < -tb ? -1 : 0);
-                            if (ns_a >= p.ln_count) ver_a = 0;
-                            if (ns_b >= p.ln_count) ver_b = 0;
-                        }
-                        if (sna_a == 0) ver_a = -1;   // unvisited sibling: phase 1b expands it
-                        if (sna_b == 0) ver_b = -1;
-                        if ((act_a && ver_a == 0) || (act_b && ver_b == 0)) {
-                            auto exact = [&](double ot, int ona, double st, int sna, int ns) -> int {
-                                const double lg = ns < p.ln_count ? ln_table[ns] : ::log((double)ns);
-                                const double so = __dadd_rn(__ddiv_rn(ot, (double)ona), __dmul_rn(Cexp, __dsqrt_rn(__ddiv_rn(lg, (double)ona))));
-                                const double ss = __dadd_rn(__ddiv_rn(st, (double)sna), __dmul_rn(Cexp, __dsqrt_rn(__ddiv_rn(lg, (double)sna))));
-                                return so > ss ? 1 : -1;   // a tie needs a draw: phase 1b
-                            };
-                            if (act_a && ver_a == 0) ver_a = exact(va.total, va.na, st_a, sna_a, ns_a);
-                            if (act_b && ver_b == 0) ver_b = exact(vb.total, vb.na, st_b, sna_b, ns_b);
-                        }
-                        va.event = ver_a < 0; vb.event = ver_b < 0;
+                            int sna[NR], ns[NR], ver[NR];
+                            double st[NR];
+#pragma unroll
+                            for (int r = 0; r < NR; ++r) {
+                                sna[r] = sv[r].x;
+                                st[r] = __hiloint2double(sv[r].w, sv[r].z);
+                                ns[r] = v[r].na + sna[r] + ((r > 0 || l0 + lane > 0) ? 1 : 0);
+                                ver[r] = 0;   // +1 the old decision stands, -1 it changes (or the sibling is unvisited), 0 undecided
+                            }
+                            if (!(p.tuning & 1)) {
+                                float lg[NR], ro[NR], rs[NR], qo[NR], qs[NR], eo[NR], es[NR];
+#pragma unroll
+                                for (int r = 0; r < NR; ++r) {
+                                    const int i = min(max(ns[r], 0), p.ln_count - 1);
+                                    lg[r] = p.ln_in_smem ? lnf_smem[i] : (float)__ldg(ln_table + i);
+                                }
+#pragma unroll
+                                for (int r = 0; r < NR; ++r) { ro[r] = rcp_approx((float)v[r].na); rs[r] = rcp_approx((float)sna[r]); }
+#pragma unroll
+                                for (int r = 0; r < NR; ++r) { qo[r] = (float)v[r].total * ro[r]; qs[r] = (float)st[r] * rs[r]; }
+#pragma unroll
+                                for (int r = 0; r < NR; ++r) { eo[r] = Cf * sqrt_approx(lg[r] * ro[r]); es[r] = Cf * sqrt_approx(lg[r] * rs[r]); }
+#pragma unroll
+                                for (int r = 0; r < NR; ++r) {
+                                    const float d = (qo[r] + eo[r]) - (qs[r] + es[r]);
+                                    const float t = 1e-5f * fmaxf(fabsf(qo[r]) + fabsf(eo[r]), fabsf(qs[r]) + fabsf(es[r])) + 1e-30f;
+                                    ver[r] = d > t ? 1 : (d < -t ? -1 : 0);
+                                    if (ns[r] >= p.ln_count) ver[r] = 0;
+                                }
+                            }
+                            bool undecided = false;
+#pragma unroll
+                            for (int r = 0; r < NR; ++r) {
+                                if (sna[r] == 0) ver[r] = -1;   // unvisited sibling: phase 1b expands it
+                                undecided |= act[r] && ver[r] == 0;
+                            }
+                            if (undecided) {
+                                auto exact = [&](double ot, int ona, double st_, int sna_, int ns_) -> int {
+                                    const double lg = ns_ < p.ln_count ? ln_table[ns_] : ::log((double)ns_);
+                                    const double so = __dadd_rn(__ddiv_rn(ot, (double)ona), __dmul_rn(Cexp, __dsqrt_rn(__ddiv_rn(lg, (double)ona))));
+                                    const double ss = __dadd_rn(__ddiv_rn(st_, (double)sna_), __dmul_rn(Cexp, __dsqrt_rn(__ddiv_rn(lg, (double)sna_))));
+                                    return so > ss ? 1 : -1;   // a tie needs a draw: phase 1b
+                                };
+#pragma unroll
+                                for (int r = 0; r < NR; ++r)
+                                    if (act[r] && ver[r] == 0) ver[r] = exact(v[r].total, v[r].na, st[r], sna[r], ns[r]);
+                            }
+#pragma unroll
+                            for (int r = 0; r < NR; ++r) v[r].event = ver[r] < 0;
                         }
                     } else {
-                        if (act_a) va = eval_level(slot_a, la, decide);
-                        if (act_b) vb = eval_level(slot_b, lb, decide);
+#pragma unroll
+                        for (int r = 0; r < NR; ++r) if (act[r]) v[r] = eval_level(slot[r], l0 + 32 * r + lane, decide);
                     }
                     SUB_ADD(u_eval);
                     if (decide) {
-                        const unsigned ea = __ballot_sync(kFull, act_a && va.event);
-                        const unsigned eb = two ? __ballot_sync(kFull, act_b && vb.event) : 0u;
-                        if (ea) event = l0 + __ffs(ea) - 1;
-                        else if (eb) event = l0 + 32 + __ffs(eb) - 1;
+#pragma unroll
+                        for (int r = NR - 1; r >= 0; --r) {   // the first event from the top wins
+                            const unsigned e = __ballot_sync(kFull, act[r] && v[r].event);
+                            if (e) event = l0 + 32 * r + __ffs(e) - 1;
+                        }
                     }
-                    if (act_a) settle_level(va, la);
-                    if (act_b) settle_level(vb, lb);
-                    if (two) { cslot = cslot + kSlotBytes == kSlots * kSlotBytes ? 0u : cslot + kSlotBytes; consumed += 2; l0 += 64; }
-                    else { ++consumed; l0 += 32; }
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) if (act[r]) settle_level(v[r], l0 + 32 * r + lane);
+                    cslot += (unsigned)nr * kSlotBytes;
+                    if (cslot >= (unsigned)(kSlots * kSlotBytes)) cslot -= (unsigned)(kSlots * kSlotBytes);
+                    consumed += nr; l0 += 32 * nr;
                     __syncwarp();   // the slots just read may be overwritten by the next issue
                     SUB_ADD(u_settle);
                 }
