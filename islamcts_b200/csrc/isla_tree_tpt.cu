@@ -14,18 +14,20 @@
 //     (A=2) / 64 bytes (A=4); an edge's link word carries the block of the child.  States and creation returns
 //     are cold side arrays.
 //   * PV cache + lazy backup.  Consecutive simulations share 99.7 % of their path (measured, CartPole C5).  The
-//     statistics of the path's edges therefore live in sequential per-tree rows (own 16 B + siblings 16 B + pending
-//     return 8 B per level); the returns G_l of simulation s are added by simulation s+1 when it re-evaluates the
-//     level, and the node blocks are only touched where the path changes.  Every level sees exactly the statistics
-//     an eager backup would have produced, so the decisions are those of the sequential algorithm.
-//   * Cooperative verification.  A warp owns 32 trees; for each tree in turn its 32 lanes re-evaluate UCB1 on 32
+//     statistics of the path's edges therefore live in per-tree chunks of 32 consecutive levels (per level: sibling
+//     statistics 16 B, own total 8 B, pending return 8 B, edge id 4 B; the own visit count is implicit); the returns
+//     G_l of simulation s are added by simulation s+1 when it re-evaluates the level, and the node blocks are only
+//     touched where the path changes.  Every level sees exactly the statistics an eager backup would have produced,
+//     so the decisions are those of the sequential algorithm.
+//   * Cooperative verification.  A warp owns up to 32 trees; for each tree in turn its 32 lanes re-evaluate UCB1 on 32
 //     consecutive LEVELS of the cached path and ballot whether the decisions stand -- a dependent pointer chase of
 //     ~180 levels becomes ~6 coalesced rounds.  Only the tail (first changed decision, tie-break draws, expansion)
 //     is walked serially on the node blocks, lock-step across the warp's trees.
 //   * Visit counts and totals are exact: int32 counts, float64 totals, UCB decisions are the float64 ones (fp32
 //     screening settles only unambiguous arg-maxes), ln(n) and gamma^t come from host libm tables.  Env state and
 //     rollouts live in registers; Philox4x32-10 replaces numpy/gym RNGs.
-// tuning bits (A/B timing only): 1 = no fp32 screening.
+// tuning bits: 1 = no fp32 screening (A/B timing), 2 = cooperative verification at any path depth (tests),
+// bits 8..13 = trees per warp (A/B timing).
 #include <cmath>
 #include <cstring>
 
@@ -104,15 +106,9 @@ template <int A> __device__ __forceinline__ uint32_t* link_ptr(char* base, int b
 __device__ __forceinline__ void cp_async16(unsigned smem, const void* g) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(g) : "memory");
 }
-__device__ __forceinline__ void cp_async8(unsigned smem, const void* g) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem), "l"(g) : "memory");
-}
 // MUFU approximations (relative error ~2^-22) for the fp32 screening pass of UCB1; exact float64 decides near-ties
 __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ void cp_async4(unsigned smem, const void* g) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem), "l"(g) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
