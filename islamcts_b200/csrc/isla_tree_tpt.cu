@@ -39,7 +39,10 @@ namespace isla {
 
 namespace {
 
-constexpr int kTptBlock = 64;
+#ifndef ISLA_TPT_BLOCK
+#define ISLA_TPT_BLOCK 64
+#endif
+constexpr int kTptBlock = ISLA_TPT_BLOCK;   // threads per CTA (32 / 128 with matching ISLA_TPT_MINBLOCKS: no faster, profiles/README.md)
 // Trees owned by one warp (its first tpw lanes), chosen per launch.  A launch of this kernel is bound by the serial
 // instruction stream of a warp, most of it the cooperative phase, whose length is proportional to the warp's trees.  A
 // batch that does not fill the GPU's resident warps (148 SMs x 14) with 32 trees each is therefore spread over more
