@@ -39,6 +39,9 @@ namespace isla {
 
 namespace {
 
+#ifndef ISLA_G_STORE
+#define ISLA_G_STORE 32   // bytes per store of the return pass: one 256-bit store per sector (16: two 128-bit stores)
+#endif
 #ifndef ISLA_TPT_BLOCK
 #define ISLA_TPT_BLOCK 64
 #endif
@@ -822,12 +825,19 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                 *PC::g(pv, l) = G;
             }
             for (; l >= 3; l -= 4) {   // four levels of one chunk per address computation
-                double* const q = PC::g(pv, l - 3);
+                double* const q = PC::g(pv, l - 3);   // 32-byte aligned: one sector
+                double gq[4];
 #pragma unroll
                 for (int i = 3; i >= 0; --i) {
                     G = __dadd_rn(kInterior, __dmul_rn(gamma, G));
-                    q[i] = G;
+                    gq[i] = G;
                 }
+#if ISLA_G_STORE == 32
+                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(q), "d"(gq[0]), "d"(gq[1]), "d"(gq[2]), "d"(gq[3]) : "memory");
+#else
+                *reinterpret_cast<double2*>(q) = make_double2(gq[0], gq[1]);
+                *reinterpret_cast<double2*>(q + 2) = make_double2(gq[2], gq[3]);
+#endif
             }
             pend = level > 0;
             ++sims_done; ++s_done;
