@@ -38,6 +38,47 @@ void add_table_layout(const isla_config& cfg, isla_layout& lay, int64_t& off) {
     lay.pw2_offset = off; off = up(off + lay.ln_count * 8);
     lay.cumdisc_offset = off; off = up(off + lay.disc_count * 8);
 }
+// Return table of the thread-per-tree engine.  Its envs pay a constant reward r on every non-terminal step (CartPole 1,
+// FrozenLake 0), so the value a simulation backs up l levels above its leaf is h^l(G_leaf), h(x) = r + gamma * x evaluated
+// exactly like the recursion unwind `reward + gamma * child.build_tree_state(...)` (mcts_hash.py:126-127: one multiply,
+// one add, both rounded), and G_leaf is one of max_depth + 3 values (Rewards<ENV>::leaf_row_*): a terminal reward, or
+// r + gamma * rollout(t) with the t-step rollout return accumulated as in abstract_mcts.py:87.  The kernel therefore
+// writes nothing per level on the way up: the next simulation reads ret[row][levels above the leaf].
+// `volatile` keeps every product and sum a separately rounded double (no contraction), as in CPython.
+static int build_return_table(isla_engine* e, const std::vector<double>& disc, const std::vector<double>& cum) {
+    const int rows = e->cfg.max_depth + 3;
+    // a path has at most sim_capacity + 1 levels; deeper columns than the table holds are continued on the device
+    long long K = (long long)e->cfg.sim_capacity + 2;
+    const long long cap_entries = (64ll << 20) / 8;
+    if (K > 4096) K = 4096;
+    while (K > 64 && K * rows > cap_entries) K /= 2;
+    const bool lake = e->cfg.env_id == ISLA_ENV_FROZENLAKE;
+    const double r = lake ? 0.0 : 1.0, gamma = e->cfg.gamma;
+    std::vector<double> tab((size_t)rows * (size_t)K);
+    for (int j = 0; j < rows; ++j) {
+        volatile double g;
+        if (lake) {
+            if (j == 0) g = 0.0;
+            else if (j == 1) g = 1.0;
+            else { volatile double R = 1.0 * disc[(size_t)j - 2]; volatile double m = gamma * R; g = 0.0 + m; }
+        } else {
+            if (j == rows - 1) g = 0.0;
+            else { volatile double m = gamma * cum[(size_t)j]; g = 1.0 + m; }
+        }
+        double* row = tab.data() + (size_t)j * (size_t)K;
+        for (long long k = 0; k < K; ++k) {
+            row[k] = g;
+            volatile double m = gamma * g;
+            g = r + m;
+        }
+    }
+    if (e->ret_dev) { cudaFree(e->ret_dev); e->ret_dev = nullptr; }
+    ISLA_CUDA_OK(cudaMalloc((void**)&e->ret_dev, tab.size() * 8));
+    ISLA_CUDA_OK(cudaMemcpy(e->ret_dev, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice));
+    e->ret_rows = rows; e->ret_K = (int)K;
+    return 0;
+}
+
 int upload_tables(isla_engine* e) {
     std::vector<double> ln((size_t)e->lay.ln_count), disc((size_t)e->lay.disc_count);
     ln[0] = 0.0;
@@ -62,6 +103,10 @@ int upload_tables(isla_engine* e) {
     }
     ISLA_CUDA_OK(cudaMemcpy(e->ws + e->lay.pw1_offset, pw1.data(), pw1.size() * 8, cudaMemcpyHostToDevice));
     ISLA_CUDA_OK(cudaMemcpy(e->ws + e->lay.pw2_offset, pw2.data(), pw2.size() * 8, cudaMemcpyHostToDevice));
+    if (e->kernel == ISLA_KERNEL_THREAD_PER_TREE) {
+        const int rc = build_return_table(e, disc, cum);
+        if (rc) return rc;
+    }
     ISLA_CUDA_OK(cudaDeviceSynchronize());
     return 0;
 }
@@ -169,6 +214,7 @@ int isla_engine_create(const isla_config* cfg, void* workspace_dev, int64_t work
 int isla_engine_destroy(isla_engine* e) {
     if (e && e->heur_dev) cudaFree(e->heur_dev);
     if (e && e->noise_dev) cudaFree(e->noise_dev);
+    if (e && e->ret_dev) cudaFree(e->ret_dev);
     delete e;
     return ISLA_OK;
 }

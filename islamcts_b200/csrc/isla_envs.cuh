@@ -336,10 +336,16 @@ __device__ __forceinline__ bool env_step_action(T (&s)[EnvTraits<ENV>::S], doubl
 // after n steps in closed form, bit-identical to the left-to-right float64 sum: CartPole pays 1 on every step
 // (host-accumulated prefix table `cum`), FrozenLake pays 0 until the last step (0.0 + ... + r * gamma**(n-1) is exact).
 template <int ENV> struct Rewards { static constexpr bool kClosedForm = false; };
+// Rows of the thread-per-tree engine's return table (isla_capi.cu: build_return_table): the value a simulation backs up
+// from its leaf is one of max_depth + 3 numbers, indexed by leaf_row_*().
 template <> struct Rewards<ENV_CARTPOLE> {
     static constexpr bool kClosedForm = true;
     static constexpr double kInterior = 1.0;
     static __device__ __forceinline__ double rollout_return(int n, double, const double*, const double* cum) { return __ldg(cum + n); }
+    // row t (0..max_depth+1): 1 + gamma * cum[t], a leaf created with a t-step rollout; a terminal step pays 1 = row 0
+    // (cum[0] = 0); row max_depth + 2: 0 (unused by CartPole)
+    static __host__ __device__ __forceinline__ int leaf_row_rollout(int t, double) { return t; }
+    static __host__ __device__ __forceinline__ int leaf_row_terminal(bool reward_one, int max_depth) { return reward_one ? 0 : max_depth + 2; }
 };
 template <> struct Rewards<ENV_FROZENLAKE> {
     static constexpr bool kClosedForm = true;
@@ -347,6 +353,10 @@ template <> struct Rewards<ENV_FROZENLAKE> {
     static __device__ __forceinline__ double rollout_return(int n, double last_r, const double* disc, const double*) {
         return n > 0 ? __dmul_rn(last_r, __ldg(disc + (n - 1))) : 0.0;
     }
+    // row 0: 0 (hole / budget exhausted / zero-step rollout); row 1: 1 (the terminal step reaches the goal);
+    // row 1 + t (t = 1..max_depth): 0 + gamma * (1 * gamma**(t-1)), a t-step rollout that ends on the goal
+    static __host__ __device__ __forceinline__ int leaf_row_rollout(int t, double last_r) { return (t > 0 && last_r != 0.0) ? 1 + t : 0; }
+    static __host__ __device__ __forceinline__ int leaf_row_terminal(bool reward_one, int) { return reward_one ? 1 : 0; }
 };
 
 // gym reset distributions driven by the Philox reset stream (synthetic roots; bench + tests)

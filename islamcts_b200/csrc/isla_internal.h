@@ -59,6 +59,8 @@ struct TptParams {
     const double* ln_table;    // host-computed ln(n)
     const double* disc_table;  // host-computed gamma**t
     const double* cum_table;   // host-computed sum_{t<n} gamma**t (left-to-right)
+    const double* ret_table;   // host-computed returns: [max_depth + 3 leaf values][ret_K levels above the leaf] (isla_capi.cu)
+    int ret_K;
     int n_sim, max_depth, budget_mode, block_cap, ln_count, disc_count, ln_in_smem, tuning;
     const double* heur;        // grid_policy table (FrozenLake), nullptr = random rollouts
     const double* noise;       // slippery FrozenLake: noise[k] of the k-th env.step of a simulation, nullptr = deterministic
@@ -79,6 +81,8 @@ struct isla_engine {
     double* heur_dev = nullptr;   // grid_policy prior knowledge [16][4] (engine-owned), nullptr = random rollouts
     double* noise_dev = nullptr;  // slippery FrozenLake: per-step transition noise of a fit (engine-owned)
     int noise_n = 0;
+    double* ret_dev = nullptr;    // thread-per-tree engine: return table (engine-owned), ret_rows x ret_K
+    int ret_rows = 0, ret_K = 0;
 };
 
 namespace isla {

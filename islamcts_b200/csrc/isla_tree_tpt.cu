@@ -39,9 +39,6 @@ namespace isla {
 
 namespace {
 
-#ifndef ISLA_G_STORE
-#define ISLA_G_STORE 32   // bytes per store of the return pass: one 256-bit store per sector (16: two 128-bit stores)
-#endif
 #ifndef ISLA_TPT_BLOCK
 #define ISLA_TPT_BLOCK 64
 #endif
@@ -112,6 +109,9 @@ template <int A> __device__ __forceinline__ uint32_t* link_ptr(char* base, int b
 __device__ __forceinline__ void cp_async16(unsigned smem, const void* g) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(g) : "memory");
 }
+__device__ __forceinline__ void cp_async8(unsigned smem, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem), "l"(g) : "memory");
+}
 // MUFU approximations (relative error ~2^-22) for the fp32 screening pass of UCB1; exact float64 decides near-ties
 __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -129,7 +129,8 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 template <int A> struct CoopRing {
     static constexpr int kSlots = A == 2 ? ISLA_COOP_SLOTS : 3;
     static constexpr int kAhead = kSlots - 1;
-    static constexpr int kSlotBytes = 32 * (A == 2 ? 16 : 48) + 32 * 8 + 32 * 8 + 32 * 4;   // = one PV chunk
+    static constexpr int kChunkBytes = 32 * (A == 2 ? 16 : 48) + 32 * 8 + 32 * 4;   // = one PV chunk (HBM)
+    static constexpr int kSlotBytes = kChunkBytes + 32 * 8;                          // + the 32 pending returns (from the return table)
     static constexpr int kWarpBytes = kSlots * kSlotBytes;
 };
 
@@ -178,22 +179,20 @@ template <int A> __device__ __forceinline__ void store_sta(char* entry, const Pv
 // so that a round of the cooperative phase is ONE contiguous copy (1152 B for A = 2) through a single pointer.
 template <int A> struct PvChunk {
     static constexpr int kSta = (int)sizeof(PvSta<A>);
-    static constexpr int kTot = 32 * kSta, kG = kTot + 256, kEdge = kG + 256, kBytes = kEdge + 128;
-    static constexpr int kPieces = kBytes / 16;              // 16-byte pieces of a chunk (72 / 136)
-    static constexpr int kCopies = (kPieces + 31) / 32;      // cp.async16 per lane and chunk (3 / 5)
+    static constexpr int kTot = 32 * kSta, kEdge = kTot + 256, kBytes = kEdge + 128;
+    static constexpr int kPieces = kBytes / 16;              // 16-byte pieces of a chunk (56 / 120)
+    static constexpr int kCopies = (kPieces + 31) / 32;      // cp.async16 per lane and chunk (2 / 4)
     // first level (within the chunk) a 16-byte piece holds data of
     __host__ __device__ static constexpr int piece_level(int piece) {
-        return piece * 16 < kTot ? piece * 16 / kSta : (piece * 16 < kG ? (piece * 16 - kTot) / 8
-               : (piece * 16 < kEdge ? (piece * 16 - kG) / 8 : (piece * 16 - kEdge) / 4));
+        return piece * 16 < kTot ? piece * 16 / kSta : (piece * 16 < kEdge ? (piece * 16 - kTot) / 8 : (piece * 16 - kEdge) / 4);
     }
     __device__ __forceinline__ static char* chunk(char* pv, int l) { return pv + (long long)(l >> 5) * kBytes; }
     __device__ __forceinline__ static char* sta(char* pv, int l) { return chunk(pv, l) + (l & 31) * kSta; }
     __device__ __forceinline__ static double* tot(char* pv, int l) { return reinterpret_cast<double*>(chunk(pv, l) + kTot) + (l & 31); }
-    __device__ __forceinline__ static double* g(char* pv, int l) { return reinterpret_cast<double*>(chunk(pv, l) + kG) + (l & 31); }
     __device__ __forceinline__ static uint32_t* edge(char* pv, int l) { return reinterpret_cast<uint32_t*>(chunk(pv, l) + kEdge) + (l & 31); }
     __device__ __forceinline__ static int own_base(char* pv, int l) { return __ldcg(reinterpret_cast<const int32_t*>(sta(pv, l)) + (A - 1)); }
 };
-static_assert(PvChunk<2>::kBytes == 1152 && PvChunk<4>::kBytes == 2176, "PV chunk sizes");
+static_assert(PvChunk<2>::kBytes == 896 && PvChunk<4>::kBytes == 1920, "PV chunk sizes");
 
 // One simulation of the 32 trees of a warp = four phases.
 //   1a  cooperative verification   for each tree in turn, the 32 lanes take 32 consecutive LEVELS of its cached
@@ -235,7 +234,7 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
     const long long tix = valid ? tree : 0;
     constexpr long long kStaBytes = sizeof(PvSta<A>);
     using PC = PvChunk<A>;
-    static_assert(PC::kBytes == kSlotBytes, "a ring slot mirrors a PV chunk");
+    static_assert(PC::kBytes == CoopRing<A>::kChunkBytes, "a ring slot starts with a copy of a PV chunk");
 
     char* const blocks = p.blocks + tix * p.slots_per_tree * 16;
     T* const states = reinterpret_cast<T*>(p.states) + tix * p.slots_per_tree * S;
@@ -247,7 +246,8 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
     uint32_t sims_done = valid ? (uint32_t)meta[META_SIMS] : 0u;
     int fault = valid ? meta[META_FAULT] : 0;
     int plen = 0;        // cached levels [0, plen): pv_tot authoritative, node blocks stale for those edges
-    bool pend = false;   // the returns G_l of those levels are still to be added
+    bool pend = false;   // the returns G_l of those levels are still to be added:
+    int ret_j = 0;       //   G_l = ret_table[ret_j][plen - l] (row = the leaf value of the last simulation)
     const uint32_t tree_id = (uint32_t)(p.tree_id_base + (unsigned long long)tix);
     // the tree stream is rarely drawn from (expansion picks, exact UCB ties): only its position is kept in a register and
     // the Philox state is rebuilt per draw
@@ -320,13 +320,25 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
         }
         return ties;
     };
+    // Return table (host libm arithmetic, isla_capi.cu): row j = a leaf value G_leaf, column k = the return k levels
+    // above it, G = r + gamma * G' applied k times (mcts_hash.py:126-131, 79-81) with this kernel's constant interior
+    // reward.  The backup of a simulation is therefore two integers per tree (leaf level, row); nothing is written per
+    // level.  Columns beyond the table (paths deeper than ret_K levels) continue the recurrence from its last column.
+    auto ret_value = [&](int j, int k) -> double {
+        const double* row = p.ret_table + (long long)j * p.ret_K;
+        if (k < p.ret_K) return __ldg(row + k);
+        double g = __ldg(row + p.ret_K - 1);
+        for (int i = p.ret_K - 1; i < k; ++i) g = __dadd_rn(kInterior, __dmul_rn(gamma, g));
+        return g;
+    };
     // write the cached statistics of the own tree's levels [from, plen) back to their node blocks (adding the
     // pending return if there is one): those levels leave the cache
     auto write_back = [&](int from) {
+        const int top = plen;   // the pending returns count from the leaf level of the last simulation (= plen then)
         for (int l = from; l < plen; ++l) {
             const double t_ = __ldcg(PC::tot(pv, l));
             const uint32_t e = __ldcg(PC::edge(pv, l));
-            const double g = pend ? __ldcg(PC::g(pv, l)) : 0.0;
+            const double g = pend ? ret_value(ret_j, top - l) : 0.0;
             __stcg(total_ptr<A>(blocks, (int)(e >> 2), (int)(e & 3u)), pend ? __dadd_rn(t_, g) : t_);
             // with a pending return the stored count is one behind: own_base + sims_done either way
             __stcg(na_ptr<A>(blocks, (int)(e >> 2), (int)(e & 3u)), PC::own_base(pv, l) + (int)sims_done);
@@ -360,6 +372,7 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
         // ------------------------------------------------------------------ phase 1a: cooperative verification
         // (shallow trees -- FrozenLake, the first simulations -- have nothing to verify in parallel: their cache is
         //  written back at once and the descent starts at the root)
+        if (live && pend && plen >= p.ret_K) write_back(0);   // deeper than the return table: no cooperative pass (rare)
         int warp_max_plen = (live && pend) ? plen : 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) warp_max_plen = max(warp_max_plen, __shfl_xor_sync(kFull, warp_max_plen, o));
@@ -376,6 +389,9 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
             char* const ring = coop_ring + (threadIdx.x >> 5) * (kSlots * kSlotBytes);
             // this lane's 16-byte pieces of a chunk: piece q = lane + 32 q, at the same offset in the ring slot
             const unsigned ring_dst = (unsigned)__cvta_generic_to_shared(ring) + lane * 16;
+            const unsigned ring_dst_g = (unsigned)__cvta_generic_to_shared(ring) + PC::kBytes + lane * 8;   // pending returns
+            // the own tree's pending returns: G_l = ret_table[my_ridx - l] (row ret_j, column plen - l)
+            const int my_ridx = ret_j * p.ret_K + my_plen;
             int plv[PC::kCopies];               // first level (within the chunk) piece q holds data of
 #pragma unroll
             for (int q = 0; q < PC::kCopies; ++q) plv[q] = lane + 32 * q < PC::kPieces ? PC::piece_level(lane + 32 * q) : (1 << 30);
@@ -383,6 +399,10 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
             int pL = pj < 32 ? __shfl_sync(kFull, my_plen, pj & 31) : 0;
             int pl = 0;                         // first level of the next task of tree pj
             const char* p_src = p.pv + (warp_tree0 + (pj & 31)) * p.pv_stride + lane * 16;
+            auto ret_src = [&](int owner) -> const double* {   // this lane's entry of the first round of tree `owner`
+                return p.ret_table + (__shfl_sync(kFull, my_ridx, owner & 31) - lane);
+            };
+            const double* p_ret = ret_src(pj);
             int issued = 0, consumed = 0;
             unsigned pslot = 0;                 // byte offset of the producer's slot in the ring
             auto issue_one = [&]() {
@@ -390,13 +410,15 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
 #pragma unroll
                     for (int q = 0; q < PC::kCopies; ++q)   // pieces that only hold levels beyond the path are not copied
                         if (pl + plv[q] < pL) cp_async16(ring_dst + pslot + q * 512, p_src + q * 512);
-                    pl += 32; p_src += PC::kBytes;
+                    if (pl + lane < pL) cp_async8(ring_dst_g + pslot, p_ret);   // G_l of 32 levels: 256 contiguous bytes of one row
+                    pl += 32; p_src += PC::kBytes; p_ret -= 32;
                     if (pl >= pL) {
                         const unsigned rest = pj >= 31 ? 0u : (work & (kFull << (pj + 1)));
                         pj = rest ? __ffs(rest) - 1 : 32;
                         pL = pj < 32 ? __shfl_sync(kFull, my_plen, pj & 31) : 0;
                         pl = 0;
                         p_src = p.pv + (warp_tree0 + (pj & 31)) * p.pv_stride + lane * 16;
+                        p_ret = ret_src(pj);
                     }
                 }
                 cp_async_commit();   // one group per task (an empty one once the sequence is exhausted)
@@ -421,12 +443,12 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                 auto eval_level = [&](const char* slot, int l, bool decide) -> Lev {
                     Lev out;
                     const PvSta<A> sb = decode_sta<A>(reinterpret_cast<const int4*>(slot + lane * kStaBytes));
-                    const double own_t = *reinterpret_cast<const double*>(slot + 32 * kStaBytes + lane * 8);
-                    const double pg = *reinterpret_cast<const double*>(slot + 32 * kStaBytes + 256 + lane * 8);
+                    const double own_t = *reinterpret_cast<const double*>(slot + PC::kTot + lane * 8);
+                    const double pg = *reinterpret_cast<const double*>(slot + PC::kBytes + lane * 8);
                     const double new_total = __dadd_rn(own_t, pg);   // lazy backup: the return of the previous simulation
                     const int new_na = sb.own_base + sims_j;
                     out.total = new_total; out.na = new_na;
-                    out.edge = *reinterpret_cast<const uint32_t*>(slot + 32 * kStaBytes + 512 + lane * 4);
+                    out.edge = *reinterpret_cast<const uint32_t*>(slot + PC::kEdge + lane * 4);
                     out.event = false;
                     if (!decide) return out;
                     const int pa = (int)(out.edge & 3u);
@@ -523,7 +545,7 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                         }
                     }
                     if constexpr (A == 2) {
-                        // slot = {static 32 x 16 B | totals 32 x 8 B | pending returns 32 x 8 B | edge ids 32 x 4 B}
+                        // slot = {static 32 x 16 B | totals 32 x 8 B | edge ids 32 x 4 B | pending returns 32 x 8 B}
                         // (slots beyond nr hold other trees' rounds or copies in flight: read, never used)
                         int4 sv[NR];
                         double ov[NR], gv[NR];
@@ -532,12 +554,12 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
 #pragma unroll
                         for (int r = 0; r < NR; ++r) ov[r] = *reinterpret_cast<const double*>(slot[r] + 512 + lane * 8);
 #pragma unroll
-                        for (int r = 0; r < NR; ++r) gv[r] = *reinterpret_cast<const double*>(slot[r] + 768 + lane * 8);
+                        for (int r = 0; r < NR; ++r) gv[r] = *reinterpret_cast<const double*>(slot[r] + 896 + lane * 8);
 #pragma unroll
                         for (int r = 0; r < NR; ++r) {
                             v[r].total = __dadd_rn(ov[r], gv[r]);   // lazy backup: the return of the previous simulation
                             v[r].na = sv[r].y + sims_j;             // own_base + simulations done
-                            v[r].edge = *reinterpret_cast<const uint32_t*>(slot[r] + 1024 + lane * 4);
+                            v[r].edge = *reinterpret_cast<const uint32_t*>(slot[r] + 768 + lane * 4);
                         }
                         if (decide) {
                             int sna[NR], ns[NR], ver[NR];
@@ -670,6 +692,7 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                     if (lk & kLinkTerminal) {
                         // terminal child re-visited: total += r, na += 1 (mcts_hash.py:96-107); the block is in hand
                         G = (lk & kLinkRewardOne) ? 1.0 : 0.0;
+                        ret_j = Rewards<ENV>::leaf_row_terminal(G != 0.0, p.max_depth);
 #pragma unroll
                         for (int a = 0; a < A; ++a) if (a == a_sel) {
                             __stcg(total_ptr<A>(blocks, blk, a), __dadd_rn(c.total[a], G));
@@ -736,6 +759,7 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
             if (term) {
                 G = (double)r_exp;  // terminal child: total += r, na += 1, child.ns += 1 (mcts_hash.py:96-107)
                 if (G != 0.0 && G != 1.0) fault = ISLA_ERR_INVALID;
+                ret_j = Rewards<ENV>::leaf_row_terminal(G != 0.0, p.max_depth);
             } else {
                 if ((double)r_exp != kInterior) fault = ISLA_ERR_INVALID;  // reward model of this kernel (isla_internal.h)
                 const int child = blk * A + exp_a;
@@ -797,6 +821,7 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
             if (rolling) {
                 const double R = Rewards<ENV>::rollout_return(t, (double)last_r, p.disc_table, p.cum_table);
                 G = __dadd_rn((double)r_exp, __dmul_rn(gamma, R));
+                ret_j = Rewards<ENV>::leaf_row_rollout(t, (double)last_r);
             }
         }
         if (mode == MODE_EXPAND) {
@@ -814,31 +839,13 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
         if (fault) mode = MODE_IDLE;
 
         PHASE_ADD(t_2);
-        // ------------------------------------------------------------------ phase 3: return pass
-        // G_l = r + gamma * G_{l+1} up the recorded path (mcts_hash.py:126-131, 79-81).  The returns are only
-        // WRITTEN to the tree's pending-return row; the next simulation's phase 1a adds them.
+        // ------------------------------------------------------------------ phase 3: backup
+        // G_l = r + gamma * G_{l+1} up the recorded path (mcts_hash.py:126-131, 79-81) is a function of (leaf value,
+        // levels above the leaf) only, because the interior reward is constant: the returns are NOT computed or stored
+        // here -- the next simulation's phase 1a reads them from the return table (row ret_j, column plen - l) when it
+        // adds them to the cached statistics (lazy backup).
         if (mode == MODE_RETURN) {
             c_levels += (unsigned)level + 1u;
-            int l = level - 1;
-            for (; l >= 0 && (l & 3) != 3; --l) {
-                G = __dadd_rn(kInterior, __dmul_rn(gamma, G));
-                *PC::g(pv, l) = G;
-            }
-            for (; l >= 3; l -= 4) {   // four levels of one chunk per address computation
-                double* const q = PC::g(pv, l - 3);   // 32-byte aligned: one sector
-                double gq[4];
-#pragma unroll
-                for (int i = 3; i >= 0; --i) {
-                    G = __dadd_rn(kInterior, __dmul_rn(gamma, G));
-                    gq[i] = G;
-                }
-#if ISLA_G_STORE == 32
-                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(q), "d"(gq[0]), "d"(gq[1]), "d"(gq[2]), "d"(gq[3]) : "memory");
-#else
-                *reinterpret_cast<double2*>(q) = make_double2(gq[0], gq[1]);
-                *reinterpret_cast<double2*>(q + 2) = make_double2(gq[2], gq[3]);
-#endif
-            }
             pend = level > 0;
             ++sims_done; ++s_done;
         }
@@ -1063,6 +1070,7 @@ int tpt_run(isla_engine* e, int n_sim, long long scripted_tree, const uint8_t* k
     p.disc_table = (const double*)(e->ws + L.disc_offset);
     p.cum_table = (const double*)(e->ws + L.cumdisc_offset);
     p.ln_count = (int)L.ln_count; p.disc_count = (int)L.disc_count;
+    p.ret_table = e->ret_dev; p.ret_K = e->ret_K;
     p.ln_in_smem = (L.ln_count * 4 <= 8 * 1024) ? 1 : 0;
     p.heur = e->heur_dev;
     p.noise = e->noise_dev; p.noise_n = e->noise_n;
