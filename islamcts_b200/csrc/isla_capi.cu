@@ -73,8 +73,10 @@ static int build_return_table(isla_engine* e, const std::vector<double>& disc, c
         }
     }
     if (e->ret_dev) { cudaFree(e->ret_dev); e->ret_dev = nullptr; }
-    ISLA_CUDA_OK(cudaMalloc((void**)&e->ret_dev, tab.size() * 8));
-    ISLA_CUDA_OK(cudaMemcpy(e->ret_dev, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice));
+    // kRetTablePad zero entries on both sides: a bulk-copied window of a round may start before row 0 / end past the last row
+    ISLA_CUDA_OK(cudaMalloc((void**)&e->ret_dev, (tab.size() + 2 * kRetTablePad) * 8));
+    ISLA_CUDA_OK(cudaMemset(e->ret_dev, 0, (tab.size() + 2 * kRetTablePad) * 8));
+    ISLA_CUDA_OK(cudaMemcpy(e->ret_dev + kRetTablePad, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice));
     e->ret_rows = rows; e->ret_K = (int)K;
     return 0;
 }

@@ -33,6 +33,7 @@ constexpr uint32_t kLinkBlockMask = 0x0fffffffu;
 constexpr uint32_t kLinkTerminal = 1u << 28;
 constexpr uint32_t kLinkRewardOne = 1u << 29;
 constexpr int kLinkRankShift = 30;
+constexpr int kRetTablePad = 64;   // zero doubles before and after the return table (isla_capi.cu: build_return_table)
 
 // per-tree meta words
 enum : int { META_ALLOC = 0, META_SIMS = 1, META_RNG = 2, META_FAULT = 3, META_TRACE_POS = 4, META_PENDING = 5, META_WORDS = 8 };

@@ -26,7 +26,7 @@
 //   * Visit counts and totals are exact: int32 counts, float64 totals, UCB decisions are the float64 ones (fp32
 //     screening settles only unambiguous arg-maxes), ln(n) and gamma^t come from host libm tables.  Env state and
 //     rollouts live in registers; Philox4x32-10 replaces numpy/gym RNGs.
-// tuning bits: 1 = no fp32 screening (A/B timing), 2 = cooperative verification at any path depth (tests),
+// tuning bits: 2 = cooperative verification at any path depth (tests); -DISLA_NO_SCREEN builds without the fp32 screening (A/B timing),
 // bits 8..13 = trees per warp (A/B timing).
 #include <cmath>
 #include <cstring>
@@ -126,12 +126,32 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 #ifndef ISLA_COOP_NR
 #define ISLA_COOP_NR 2
 #endif
+// -DISLA_BULK=1: the producer of the cooperative phase is ONE lane issuing cp.async.bulk copies that complete on an
+// mbarrier per ring slot, instead of 32 lanes x 3 cp.async (A/B: profiles/README.md)
+#ifndef ISLA_BULK
+#define ISLA_BULK 0
+#endif
+constexpr int kRetWin = ISLA_BULK ? 272 : 256;   // bytes of pending returns per slot (bulk: 16-byte aligned window of 34)
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+    asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}"
+                 ::"r"(mbar), "r"(parity) : "memory");
+}
 template <int A> struct CoopRing {
     static constexpr int kSlots = A == 2 ? ISLA_COOP_SLOTS : 3;
     static constexpr int kAhead = kSlots - 1;
     static constexpr int kChunkBytes = 32 * (A == 2 ? 16 : 48) + 32 * 8 + 32 * 4;   // = one PV chunk (HBM)
-    static constexpr int kSlotBytes = kChunkBytes + 32 * 8;                          // + the 32 pending returns (from the return table)
-    static constexpr int kWarpBytes = kSlots * kSlotBytes;
+    static constexpr int kSlotBytes = kChunkBytes + kRetWin;                         // + the 32 pending returns (from the return table)
+    static constexpr int kWarpBytes = kSlots * kSlotBytes + (ISLA_BULK ? kSlots * 8 : 0);   // + one mbarrier per slot
 };
 
 enum : int { MODE_DESCEND = 0, MODE_EXPAND = 1, MODE_RETURN = 2, MODE_IDLE = 3 };
@@ -225,6 +245,16 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
     const int lane = threadIdx.x & 31;
     constexpr int kSlots = CoopRing<A>::kSlots, kAhead = CoopRing<A>::kAhead, kSlotBytes = CoopRing<A>::kSlotBytes;
     char* const coop_ring = reinterpret_cast<char*>(lnf_smem) + ln_slots * 4;
+#if ISLA_BULK
+    // mbarriers of this warp's ring slots (behind all rings); par_bits = phase parity the consumer waits for, per slot
+    const unsigned mbar0 = (unsigned)__cvta_generic_to_shared(coop_ring + (kTptBlock / 32) * (kSlots * kSlotBytes)) + (threadIdx.x >> 5) * (kSlots * 8);
+    unsigned par_bits = 0u;
+    if (lane == 0) {
+        for (int i = 0; i < kSlots; ++i) mbar_init(mbar0 + i * 8, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+#endif
 
     // scripted (parity) mode drives ONE tree from lane 0 of a single warp; the other lanes are dummies
     const long long warp_tree0 = ((long long)blockIdx.x * (kTptBlock / 32) + (threadIdx.x >> 5)) * p.tpw;  // tree of lane 0 (free-running)
@@ -281,7 +311,8 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
         int ns = nonroot ? 1 : 0;
 #pragma unroll
         for (int a = 0; a < A; ++a) ns += c.na[a];
-        if (!(p.tuning & 1)) {
+#ifndef ISLA_NO_SCREEN
+        {
             const float lgf = ns < p.ln_count ? (p.ln_in_smem ? lnf_smem[ns] : (float)ln_table[ns]) : (float)::log((double)ns);
             float sf[A], m1 = -INFINITY, scale = 0.f;
 #pragma unroll
@@ -299,6 +330,7 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
             for (int a = 0; a < A; ++a) { if (sf[a] >= thr) { ++ncand; a_sel = a; } }
             if (ncand == 1) return 1;
         }
+#endif
         const double lg = ns < p.ln_count ? ln_table[ns] : ::log((double)ns);
         best = -INFINITY;
 #pragma unroll
@@ -389,130 +421,127 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
             char* const ring = coop_ring + (threadIdx.x >> 5) * (kSlots * kSlotBytes);
             // this lane's 16-byte pieces of a chunk: piece q = lane + 32 q, at the same offset in the ring slot
             const unsigned ring_dst = (unsigned)__cvta_generic_to_shared(ring) + lane * 16;
-            const unsigned ring_dst_g = (unsigned)__cvta_generic_to_shared(ring) + PC::kBytes + lane * 8;   // pending returns
+            const unsigned g_adj = PC::kBytes - lane * 8;   // from this lane's first piece of a slot to its pending return
+            const char* const pv_warp = p.pv + warp_tree0 * p.pv_stride + lane * 16;
             // the own tree's pending returns: G_l = ret_table[my_ridx - l] (row ret_j, column plen - l)
             const int my_ridx = ret_j * p.ret_K + my_plen;
             int plv[PC::kCopies];               // first level (within the chunk) piece q holds data of
 #pragma unroll
             for (int q = 0; q < PC::kCopies; ++q) plv[q] = lane + 32 * q < PC::kPieces ? PC::piece_level(lane + 32 * q) : (1 << 30);
-            int pj = work ? __ffs(work) - 1 : 32;
-            int pL = pj < 32 ? __shfl_sync(kFull, my_plen, pj & 31) : 0;
-            int pl = 0;                         // first level of the next task of tree pj
-            const char* p_src = p.pv + (warp_tree0 + (pj & 31)) * p.pv_stride + lane * 16;
-            auto ret_src = [&](int owner) -> const double* {   // this lane's entry of the first round of tree `owner`
-                return p.ret_table + (__shfl_sync(kFull, my_ridx, owner & 31) - lane);
+            // producer cursor: tree by tree in lane order, `rem` = levels of the current tree not yet issued
+            unsigned pwork = work;
+            int rem = 0;
+            const char* p_src = nullptr;     // this lane's first piece of the next chunk
+#if ISLA_BULK
+            int p_ridx = 0;                  // ret_table index of the LAST level (lowest index) of the next round
+#else
+            const double* p_ret = nullptr;   // this lane's pending return of the next round
+#endif
+            auto next_tree = [&]() {
+                const int pj = __ffs(pwork) - 1;
+                pwork &= pwork - 1;
+                rem = __shfl_sync(kFull, my_plen, pj);
+                p_src = pv_warp + (long long)pj * p.pv_stride;
+#if ISLA_BULK
+                p_ridx = __shfl_sync(kFull, my_ridx, pj) - 31;
+#else
+                p_ret = p.ret_table + (__shfl_sync(kFull, my_ridx, pj) - lane);
+#endif
             };
-            const double* p_ret = ret_src(pj);
-            int issued = 0, consumed = 0;
-            unsigned pslot = 0;                 // byte offset of the producer's slot in the ring
+            unsigned pdst = ring_dst;           // this lane's first piece in the producer's slot
+            const unsigned ring_end = ring_dst + kSlots * kSlotBytes;
+            // one task = one round of the current tree: its PV chunk (pieces that only hold levels beyond the path are
+            // not copied) + the 32 pending returns, 256 contiguous bytes of one row of the return table
             auto issue_one = [&]() {
-                if (pj < 32) {
-#pragma unroll
-                    for (int q = 0; q < PC::kCopies; ++q)   // pieces that only hold levels beyond the path are not copied
-                        if (pl + plv[q] < pL) cp_async16(ring_dst + pslot + q * 512, p_src + q * 512);
-                    if (pl + lane < pL) cp_async8(ring_dst_g + pslot, p_ret);   // G_l of 32 levels: 256 contiguous bytes of one row
-                    pl += 32; p_src += PC::kBytes; p_ret -= 32;
-                    if (pl >= pL) {
-                        const unsigned rest = pj >= 31 ? 0u : (work & (kFull << (pj + 1)));
-                        pj = rest ? __ffs(rest) - 1 : 32;
-                        pL = pj < 32 ? __shfl_sync(kFull, my_plen, pj & 31) : 0;
-                        pl = 0;
-                        p_src = p.pv + (warp_tree0 + (pj & 31)) * p.pv_stride + lane * 16;
-                        p_ret = ret_src(pj);
-                    }
+#if ISLA_BULK
+                // one lane: a bulk copy of the whole chunk and one of the (16-byte aligned) window of the return table
+                // that holds the round's 32 entries, both completing on the slot's mbarrier
+                if (rem > 0 && lane == 0) {
+                    const unsigned slot0 = pdst;    // lane 0: pdst = start of the slot
+                    const unsigned mb = mbar0 + ((pdst - ring_dst) / kSlotBytes) * 8;
+                    mbar_expect_tx(mb, PC::kBytes + kRetWin);
+                    bulk_g2s(slot0, p_src, PC::kBytes, mb);
+                    bulk_g2s(slot0 + PC::kBytes, p.ret_table + (p_ridx & ~1), kRetWin, mb);
                 }
+                rem -= 32; p_src += PC::kBytes; p_ridx -= 32;
+#else
+#pragma unroll
+                for (int q = 0; q < PC::kCopies; ++q)
+                    if (plv[q] < rem) cp_async16(pdst + q * 512, p_src + q * 512);
+                if (lane < rem) cp_async8(pdst + g_adj, p_ret);
+                rem -= 32; p_src += PC::kBytes; p_ret -= 32;
                 cp_async_commit();   // one group per task (an empty one once the sequence is exhausted)
-                ++issued;
-                pslot = pslot + kSlotBytes == kSlots * kSlotBytes ? 0u : pslot + kSlotBytes;
+#endif
+                pdst = pdst + kSlotBytes == ring_end ? ring_dst : pdst + kSlotBytes;
+                if (rem <= 0 && pwork) next_tree();   // warp-uniform
             };
+            next_tree();
+#pragma unroll
+            for (int i = 0; i < kAhead; ++i) issue_one();
             unsigned cslot = 0;                 // byte offset of the consumer's slot
             SUB_MARK();
             for (unsigned todo = work; todo; todo &= todo - 1) {
                 const int j = __ffs(todo) - 1;
                 const int Lj = __shfl_sync(kFull, my_plen, j);
-                const long long tj = warp_tree0 + j;
-                char* const bj = p.blocks + tj * p.slots_per_tree * 16;
-                char* const wr_tot = p.pv + tj * p.pv_stride + PC::kTot + lane * 8;   // this lane's total in chunk 0
                 const int sims_j = (int)__shfl_sync(kFull, sims_done, j);   // the path edge's na (return added) = own_base + sims_j
+                // this lane's total in the chunk of the iteration's first round (advances with the iterations)
+                char* wr_tot = p.pv + (warp_tree0 + j) * p.pv_stride + PC::kTot + lane * 8;
+#if ISLA_BULK
+                // the slot holds the aligned window of the return table in table order: level l0 + i is entry 31 - i (+ parity)
+                const int g_off = PC::kBytes + (31 - lane + ((__shfl_sync(kFull, my_ridx, j) + 1) & 1)) * 8;
+#else
+                const int g_off = PC::kBytes + lane * 8;
+#endif
                 int event = -1;
                 constexpr int NR = A == 2 ? ISLA_COOP_NR : 2;   // rounds (levels per lane) evaluated together
                 static_assert(NR >= 1 && NR <= kAhead, "rounds per iteration");
                 // one level of the cached path, from this lane's entries in ring slot `slot`: adds the pending return
                 // (lazy backup) and decides whether the old decision stands
-                struct Lev { double total; int na; uint32_t edge; bool event; };
+                struct Lev { double total; int na; bool event; };
                 auto eval_level = [&](const char* slot, int l, bool decide) -> Lev {
                     Lev out;
                     const PvSta<A> sb = decode_sta<A>(reinterpret_cast<const int4*>(slot + lane * kStaBytes));
                     const double own_t = *reinterpret_cast<const double*>(slot + PC::kTot + lane * 8);
-                    const double pg = *reinterpret_cast<const double*>(slot + PC::kBytes + lane * 8);
+                    const double pg = *reinterpret_cast<const double*>(slot + g_off);
                     const double new_total = __dadd_rn(own_t, pg);   // lazy backup: the return of the previous simulation
                     const int new_na = sb.own_base + sims_j;
                     out.total = new_total; out.na = new_na;
-                    out.edge = *reinterpret_cast<const uint32_t*>(slot + PC::kEdge + lane * 4);
                     out.event = false;
                     if (!decide) return out;
-                    const int pa = (int)(out.edge & 3u);
-                    bool my_event;
-                    if constexpr (A == 2) {
-                        // two actions: the old decision stands iff the path edge's score is the UNIQUE maximum
-                        const int sna = sb.sib_na[0];
-                        (void)pa;
-                        if (sna == 0) my_event = true;   // unvisited sibling: phase 1b expands it
+                    const int pa = (int)(*reinterpret_cast<const uint32_t*>(slot + PC::kEdge + lane * 4) & 3u);
+                    NodeBlock<A> c;
+                    int k = 0;
+#pragma unroll
+                    for (int a = 0; a < A; ++a) {
+                        c.link[a] = 0u;
+                        if (a == pa) { c.total[a] = new_total; c.na[a] = new_na; }
                         else {
-                            const int ns = new_na + sna + (l > 0 ? 1 : 0);
-                            int verdict = 0;   // +1 stands, -1 changes, 0 undecided by the fp32 screening
-                            if (!(p.tuning & 1)) {
-                                const float lgf = ns < p.ln_count ? (p.ln_in_smem ? lnf_smem[ns] : (float)ln_table[ns]) : (float)::log((double)ns);
-                                const float ro = rcp_approx((float)new_na), rs = rcp_approx((float)sna);
-                                const float qo = (float)new_total * ro, qs = (float)sb.sib_total[0] * rs;
-                                const float eo = Cf * sqrt_approx(lgf * ro), es = Cf * sqrt_approx(lgf * rs);
-                                const float d = (qo + eo) - (qs + es);
-                                const float tol = 1e-5f * fmaxf(fabsf(qo) + fabsf(eo), fabsf(qs) + fabsf(es)) + 1e-30f;
-                                verdict = d > tol ? 1 : (d < -tol ? -1 : 0);
-                            }
-                            if (verdict == 0) {
-                                const double lg = ns < p.ln_count ? ln_table[ns] : ::log((double)ns);
-                                const double so = __dadd_rn(__ddiv_rn(new_total, (double)new_na), __dmul_rn(Cexp, __dsqrt_rn(__ddiv_rn(lg, (double)new_na))));
-                                const double ss = __dadd_rn(__ddiv_rn(sb.sib_total[0], (double)sna), __dmul_rn(Cexp, __dsqrt_rn(__ddiv_rn(lg, (double)sna))));
-                                verdict = so > ss ? 1 : -1;   // a tie needs a draw: phase 1b
-                            }
-                            my_event = verdict < 0;
+                            // siblings are stored in ascending action order
+                            double st_ = sb.sib_total[0]; int sn_ = sb.sib_na[0];
+#pragma unroll
+                            for (int q = 1; q < A - 1; ++q) if (q == k) { st_ = sb.sib_total[q]; sn_ = sb.sib_na[q]; }
+                            c.total[a] = st_; c.na[a] = sn_; ++k;
                         }
-                    } else {
-                        NodeBlock<A> c;
-                        int k = 0;
-#pragma unroll
-                        for (int a = 0; a < A; ++a) {
-                            c.link[a] = 0u;
-                            if (a == pa) { c.total[a] = new_total; c.na[a] = new_na; }
-                            else {
-                                // siblings are stored in ascending action order
-                                double st_ = sb.sib_total[0]; int sn_ = sb.sib_na[0];
-#pragma unroll
-                                for (int q = 1; q < A - 1; ++q) if (q == k) { st_ = sb.sib_total[q]; sn_ = sb.sib_na[q]; }
-                                c.total[a] = st_; c.na[a] = sn_; ++k;
-                            }
-                        }
-                        int nun = 0;
-#pragma unroll
-                        for (int a = 0; a < A; ++a) nun += (c.na[a] == 0);
-                        int a_sel = -1;
-                        double sc[A], best;
-                        const int ties = nun > 0 ? 2 : ucb(c, l > 0, a_sel, sc, best);
-                        my_event = (ties != 1) || (a_sel != pa);
                     }
-                    out.event = my_event;
+                    int nun = 0;
+#pragma unroll
+                    for (int a = 0; a < A; ++a) nun += (c.na[a] == 0);
+                    int a_sel = -1;
+                    double sc[A], best;
+                    const int ties = nun > 0 ? 2 : ucb(c, l > 0, a_sel, sc, best);
+                    out.event = (ties != 1) || (a_sel != pa);
                     return out;
                 };
                 // levels before the event stay cached (with the return added); the event level and everything deeper
                 // leave the cache: their statistics go back to the node blocks.  Without an event the LAST level is
                 // handed over too (phase 1b re-decides it on its block).
-                auto settle_level = [&](const Lev& v, int l) {
+                auto settle_level = [&](const Lev& v, int l, const char* slot, char* wr) {
                     const bool leaves = (event >= 0 && l >= event) || (event < 0 && l == Lj - 1);
                     // 8 bytes: the visit count is implicit (own_base + sims_done)
-                    if (!leaves) __stcg(reinterpret_cast<double*>(wr_tot + (long long)(l >> 5) * PC::kBytes), v.total);
+                    if (!leaves) __stcg(reinterpret_cast<double*>(wr), v.total);
                     else {
-                        const uint32_t e = v.edge;
+                        const uint32_t e = *reinterpret_cast<const uint32_t*>(slot + PC::kEdge + lane * 4);
+                        char* const bj = p.blocks + (warp_tree0 + j) * p.slots_per_tree * 16;
                         __stcg(total_ptr<A>(bj, (int)(e >> 2), (int)(e & 3u)), v.total);
                         __stcg(na_ptr<A>(bj, (int)(e >> 2), (int)(e & 3u)), v.na);
                     }
@@ -526,21 +555,31 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                     const bool decide = event < 0;   // warp-uniform
                     const int nr = min(NR, (Lj - l0 + 31) >> 5);   // rounds of this iteration
                     SUB_ADD(u_tree);
-                    while (issued < consumed + kAhead) issue_one();
-                    SUB_ADD(u_issue);
+#if ISLA_BULK
+                    {
+                        unsigned cs = cslot;
+#pragma unroll
+                        for (int r = 0; r < NR; ++r) {
+                            if (r < nr) { mbar_wait(mbar0 + (cs / kSlotBytes) * 8, (par_bits >> (cs / kSlotBytes)) & 1u); par_bits ^= 1u << (cs / kSlotBytes); }
+                            cs = cs + kSlotBytes == kSlots * kSlotBytes ? 0u : cs + kSlotBytes;
+                        }
+                    }
+#else
                     cp_async_wait<kAhead - NR>();
                     __syncwarp();
+#endif
                     SUB_ADD(u_wait);
                     const char* slot[NR];
                     bool act[NR];
                     Lev v[NR];
                     {
                         unsigned cs = cslot;
+                        const int lim = Lj - l0 - lane;   // levels of the path from this lane's first one on
 #pragma unroll
                         for (int r = 0; r < NR; ++r) {
                             slot[r] = ring + cs;
                             cs = cs + kSlotBytes == kSlots * kSlotBytes ? 0u : cs + kSlotBytes;
-                            act[r] = r < nr && l0 + 32 * r + lane < Lj;
+                            act[r] = lim > 32 * r;        // (rounds beyond nr start past the path)
                             v[r].event = false;
                         }
                     }
@@ -554,14 +593,14 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
 #pragma unroll
                         for (int r = 0; r < NR; ++r) ov[r] = *reinterpret_cast<const double*>(slot[r] + 512 + lane * 8);
 #pragma unroll
-                        for (int r = 0; r < NR; ++r) gv[r] = *reinterpret_cast<const double*>(slot[r] + 896 + lane * 8);
+                        for (int r = 0; r < NR; ++r) gv[r] = *reinterpret_cast<const double*>(slot[r] + g_off);
 #pragma unroll
                         for (int r = 0; r < NR; ++r) {
                             v[r].total = __dadd_rn(ov[r], gv[r]);   // lazy backup: the return of the previous simulation
                             v[r].na = sv[r].y + sims_j;             // own_base + simulations done
-                            v[r].edge = *reinterpret_cast<const uint32_t*>(slot[r] + 768 + lane * 4);
                         }
                         if (decide) {
+                            // a cached level was decided by UCB1, so its sibling has been visited: sna >= 1
                             int sna[NR], ns[NR], ver[NR];
                             double st[NR];
 #pragma unroll
@@ -569,13 +608,15 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                                 sna[r] = sv[r].x;
                                 st[r] = __hiloint2double(sv[r].w, sv[r].z);
                                 ns[r] = v[r].na + sna[r] + ((r > 0 || l0 + lane > 0) ? 1 : 0);
-                                ver[r] = 0;   // +1 the old decision stands, -1 it changes (or the sibling is unvisited), 0 undecided
+                                ver[r] = 0;   // +1 the old decision stands, -1 it changes, 0 undecided
                             }
-                            if (!(p.tuning & 1)) {
+#ifndef ISLA_NO_SCREEN
+                            {
                                 float lg[NR], ro[NR], rs[NR], qo[NR], qs[NR], eo[NR], es[NR];
 #pragma unroll
                                 for (int r = 0; r < NR; ++r) {
-                                    const int i = min(max(ns[r], 0), p.ln_count - 1);
+                                    // ns <= simulations done + 1 < ln_count on a live level; idle lanes read entry 0
+                                    const int i = act[r] ? ns[r] : 0;
                                     lg[r] = p.ln_in_smem ? lnf_smem[i] : (float)__ldg(ln_table + i);
                                 }
 #pragma unroll
@@ -589,15 +630,12 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                                     const float d = (qo[r] + eo[r]) - (qs[r] + es[r]);
                                     const float t = 1e-5f * fmaxf(fabsf(qo[r]) + fabsf(eo[r]), fabsf(qs[r]) + fabsf(es[r])) + 1e-30f;
                                     ver[r] = d > t ? 1 : (d < -t ? -1 : 0);
-                                    if (ns[r] >= p.ln_count) ver[r] = 0;
                                 }
                             }
+#endif
                             bool undecided = false;
 #pragma unroll
-                            for (int r = 0; r < NR; ++r) {
-                                if (sna[r] == 0) ver[r] = -1;   // unvisited sibling: phase 1b expands it
-                                undecided |= act[r] && ver[r] == 0;
-                            }
+                            for (int r = 0; r < NR; ++r) undecided |= act[r] && ver[r] == 0;
                             if (undecided) {
                                 auto exact = [&](double ot, int ona, double st_, int sna_, int ns_) -> int {
                                     const double lg = ns_ < p.ln_count ? ln_table[ns_] : ::log((double)ns_);
@@ -610,7 +648,7 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                                     if (act[r] && ver[r] == 0) ver[r] = exact(v[r].total, v[r].na, st[r], sna[r], ns[r]);
                             }
 #pragma unroll
-                            for (int r = 0; r < NR; ++r) v[r].event = ver[r] < 0;
+                            for (int r = 0; r < NR; ++r) v[r].event = act[r] && ver[r] < 0;
                         }
                     } else {
 #pragma unroll
@@ -618,25 +656,43 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                     }
                     SUB_ADD(u_eval);
                     if (decide) {
+                        bool any = false;
 #pragma unroll
-                        for (int r = NR - 1; r >= 0; --r) {   // the first event from the top wins
-                            const unsigned e = __ballot_sync(kFull, act[r] && v[r].event);
-                            if (e) event = l0 + 32 * r + __ffs(e) - 1;
+                        for (int r = 0; r < NR; ++r) any |= v[r].event;
+                        if (__any_sync(kFull, any)) {
+#pragma unroll
+                            for (int r = NR - 1; r >= 0; --r) {   // the first event from the top wins
+                                const unsigned e = __ballot_sync(kFull, v[r].event);
+                                if (e) event = l0 + 32 * r + __ffs(e) - 1;
+                            }
                         }
                     }
+                    if (event < 0 && l0 + 32 * nr < Lj) {
+                        // the common case: every level of the iteration stays cached with the return added
 #pragma unroll
-                    for (int r = 0; r < NR; ++r) if (act[r]) settle_level(v[r], l0 + 32 * r + lane);
+                        for (int r = 0; r < NR; ++r) if (act[r]) __stcg(reinterpret_cast<double*>(wr_tot + r * PC::kBytes), v[r].total);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < NR; ++r) if (act[r]) settle_level(v[r], l0 + 32 * r + lane, slot[r], wr_tot + r * PC::kBytes);
+                    }
+                    wr_tot += nr * PC::kBytes;
                     cslot += (unsigned)nr * kSlotBytes;
                     if (cslot >= (unsigned)(kSlots * kSlotBytes)) cslot -= (unsigned)(kSlots * kSlotBytes);
-                    consumed += nr; l0 += 32 * nr;
+                    l0 += 32 * nr;
                     __syncwarp();   // the slots just read may be overwritten by the next issue
                     SUB_ADD(u_settle);
+                    issue_one();
+                    if (nr > 1) issue_one();
+                    if constexpr (NR > 2) { for (int i = 2; i < nr; ++i) issue_one(); }
+                    SUB_ADD(u_issue);
                 }
                 const int r = event >= 0 ? event : Lj - 1;
                 __syncwarp();
                 if (lane == j) { level = r; plen = r; pend = false; }
             }
+#if !ISLA_BULK
             cp_async_wait<0>();
+#endif
         }
 
         PHASE_ADD(t_1a);
@@ -985,12 +1041,29 @@ __global__ void __launch_bounds__(256) tpt_depth_stats_kernel(const char* blocks
 }
 
 template <int ENV, typename T>
-int launch_search(const TptParams& p, bool scripted, cudaStream_t st) {
+int launch_search(TptParams& p, bool scripted, int sm_count, int tpw_forced, cudaStream_t st) {
     constexpr int A = EnvTraits<ENV>::A;
     const size_t smem = (p.ln_in_smem ? (size_t)((p.ln_count + 3) & ~3) * 4 : 0) + (size_t)(kTptBlock / 32) * CoopRing<A>::kWarpBytes;
     if (scripted) {
+        p.tpw = 1;
         tpt_search_kernel<ENV, T, true><<<1, 32, smem, st>>>(p);
     } else {
+        // Trees per warp.  A launch is bound by the serial instruction stream of a warp, and the phases that run one
+        // lane per tree (serial continuation, expansion, rollout) cost the same for 1 or 32 busy lanes: so as many
+        // warps as the GPU keeps resident at once, each with as few trees as that allows -- n_trees / resident warps,
+        // rounded up (8192 trees: 4, 16 384: 7, 65 536: 28 on a B200 at 8 CTAs per SM); batches beyond 32 trees per
+        // resident warp run in equal waves.  Measured: profiles/README.md (round 2).
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tpt_search_kernel<ENV, T, false>, kTptBlock, smem) != cudaSuccess || occ < 1) {
+            cudaGetLastError();
+            occ = ISLA_TPT_MINBLOCKS;
+        }
+        const long long resident = (long long)(sm_count > 0 ? sm_count : 148) * occ * (kTptBlock / 32);
+        const long long waves = (p.n_trees + 32 * resident - 1) / (32 * resident);
+        long long tpw = (p.n_trees + waves * resident - 1) / (waves * resident);
+        if (kTreesPerWarpFixed > 0) tpw = kTreesPerWarpFixed;
+        if (tpw_forced >= 1 && tpw_forced <= 32) tpw = tpw_forced;   // tuning bits 8..13 (A/B timing, tests)
+        p.tpw = (int)(tpw < 1 ? 1 : (tpw > 32 ? 32 : tpw));
         const int kTreesPerBlock = (kTptBlock / 32) * p.tpw;
         const unsigned grid = (unsigned)((p.n_trees + kTreesPerBlock - 1) / kTreesPerBlock);
         tpt_search_kernel<ENV, T, false><<<grid, kTptBlock, smem, st>>>(p);
@@ -1070,32 +1143,22 @@ int tpt_run(isla_engine* e, int n_sim, long long scripted_tree, const uint8_t* k
     p.disc_table = (const double*)(e->ws + L.disc_offset);
     p.cum_table = (const double*)(e->ws + L.cumdisc_offset);
     p.ln_count = (int)L.ln_count; p.disc_count = (int)L.disc_count;
-    p.ret_table = e->ret_dev; p.ret_K = e->ret_K;
+    p.ret_table = e->ret_dev + kRetTablePad; p.ret_K = e->ret_K;
     p.ln_in_smem = (L.ln_count * 4 <= 8 * 1024) ? 1 : 0;
     p.heur = e->heur_dev;
     p.noise = e->noise_dev; p.noise_n = e->noise_n;
-    // trees per warp: the fewest (power of two) with which all warps are still resident at once
-    {
-        const long long resident_warps = (long long)(e->sm_count > 0 ? e->sm_count : 148) * ISLA_TPT_MINBLOCKS * (kTptBlock / 32);
-        int tpw = kTreesPerWarpFixed > 0 ? kTreesPerWarpFixed : 1;
-        // ... up to 16: beyond that (65 536 trees and more) two or more waves of 16-tree warps are faster than one wave of
-        // 32-tree warps (measured: 383 vs 371 M sims/s at 65 536 trees, 386 vs 367 M at 131 072)
-        // (deep CartPole paths, where the cooperative phase dominates; FrozenLake's shallow trees skip that phase and are
-        // fastest in one wave: 65 536 trees x 100 sims 2.75 G sims/s with 32 trees per warp, 1.81 G with 16)
-        const int tpw_cap = e->cfg.env_id == ISLA_ENV_CARTPOLE ? 16 : 32;
-        if (kTreesPerWarpFixed <= 0) while (tpw < tpw_cap && (e->cfg.n_trees + tpw - 1) / tpw > resident_warps) tpw <<= 1;
-        const int forced = (e->cfg.tuning >> 8) & 63;   // tuning bits 8..13: trees per warp (A/B timing only)
-        if (forced >= 1 && forced <= 32) tpw = forced;
-        p.tpw = tpw;
-    }   // float copy of ln(n) next to the cooperative ring
+    const int tpw_forced = (e->cfg.tuning >> 8) & 63;   // tuning bits 8..13: trees per warp (A/B timing, tests)
+    p.tpw = 1;
     p.tuning = e->cfg.tuning;
     const bool scripted = scripted_tree >= 0;
     const bool f64 = e->cfg.precision == ISLA_PRECISION_F64;
     switch (e->cfg.env_id) {
     case ISLA_ENV_CARTPOLE:
-        return f64 ? launch_search<ENV_CARTPOLE, double>(p, scripted, st) : launch_search<ENV_CARTPOLE, float>(p, scripted, st);
+        return f64 ? launch_search<ENV_CARTPOLE, double>(p, scripted, e->sm_count, tpw_forced, st)
+                   : launch_search<ENV_CARTPOLE, float>(p, scripted, e->sm_count, tpw_forced, st);
     case ISLA_ENV_FROZENLAKE:
-        return f64 ? launch_search<ENV_FROZENLAKE, double>(p, scripted, st) : launch_search<ENV_FROZENLAKE, float>(p, scripted, st);
+        return f64 ? launch_search<ENV_FROZENLAKE, double>(p, scripted, e->sm_count, tpw_forced, st)
+                   : launch_search<ENV_FROZENLAKE, float>(p, scripted, e->sm_count, tpw_forced, st);
     default:
         set_error("thread-per-tree kernel: env %d unsupported", e->cfg.env_id);
         return ISLA_ERR_INVALID;
