@@ -2,14 +2,17 @@
 """bench.py -- MCTS simulations/s (and executed env-steps/s) of the root-parallel hot path on B200.
 
 Workload (BASELINE.json config C5, the configuration the metric "at 1/2/4/8 B200" is quoted on):
-vanilla MCTS on CartPole-v1, 65 536 independent trees PER GPU x nsim=1000, C=1, gamma=0.99,
-max_depth=500, one random rollout per leaf, 256 distinct roots per GPU-group (each root searched by
-trees/256 trees on every rank; root statistics merged by a per-rank segmented sum + one NCCL all-reduce).
-One "step" = one full pass: reset trees -> 1000 simulations per tree -> root statistics -> merge -> arg-max.
+vanilla MCTS on CartPole-v1, 65 536 independent trees IN TOTAL x nsim=1000, C=1, gamma=0.99, max_depth=500,
+one random rollout per leaf, sharded over the N GPUs (65 536 / N trees per GPU: STRONG scaling), 256 distinct
+roots x 256 trees (root statistics merged by one fixed-order kernel per rank + ONE NCCL all-reduce of the packed
+[256, 2, 2] float64 array).  One "step" = one full pass: reset trees -> 1000 simulations per tree -> per-root
+merge -> all-reduce -> arg-max.  Extras: the other two root layouts of SURVEY 8(e) (1 shared root, 65 536 distinct
+roots) with their message sizes, the weak-scaling figure (65 536 trees PER GPU), configs C1-C4 with the reference's
+CPU speed beside them, the rollout micro-benchmarks.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA engine
-    python bench.py --impl reference [--gpus N] ...                # the reference's CPU path (Python port, all cores)
-    torchrun ... bench.py --gpus N ...                             # N ranks, one per GPU (weak scaling)
+    python bench.py --impl reference [--gpus N] ...                # the reference's own CPU classes, all host cores
+    torchrun ... bench.py --gpus N ...                             # N ranks, one per GPU
 
 Prints ONE JSON line (rank 0).
 """
@@ -26,7 +29,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "C5: vanilla MCTS CartPole-v1, 65536 trees/GPU x nsim=1000, C=1, gamma=0.99, max_depth=500, 1 rollout/leaf"
+WORKLOAD = "C5: vanilla MCTS CartPole-v1, 65536 trees x nsim=1000 sharded over the GPUs, C=1, gamma=0.99, max_depth=500, 1 rollout/leaf"
 FLOP_PER_STEP_CARTPOLE = 36
 BYTES_PER_LEVEL_A2 = 12 * 2 + 36     # B_level = 12*A + 36
 STATE_BYTES = 16
@@ -38,7 +41,8 @@ def parse():
     p.add_argument("--steps", type=int, default=5)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="isla", choices=["isla", "reference"])
-    p.add_argument("--trees", type=int, default=65536, help="trees per GPU")
+    p.add_argument("--trees", type=int, default=65536, help="trees of the whole job (sharded over the GPUs)")
+    p.add_argument("--weak", action="store_true", help="headline = weak scaling (--trees per GPU) instead of strong")
     p.add_argument("--nsim", type=int, default=1000)
     p.add_argument("--roots", type=int, default=256, help="distinct roots (root groups)")
     p.add_argument("--max_depth", type=int, default=500)
@@ -107,8 +111,8 @@ def _cpu_fit_worker(args):
     return dt, sims, steps
 
 
-def cpu_baseline_python(args, cores, trees):
-    """The reference's CPU path (pure-Python port, oracle/py_port.py), `cores` processes, `trees` fits."""
+def cpu_baseline_port(args, cores, trees):
+    """Fallback CPU arm: the pure-Python port of MctsHash.fit (oracle/py_port.py), `cores` processes, `trees` fits."""
     import multiprocessing as mp
     jobs = [(args.nsim, args.c, args.gamma, args.max_depth, s) for s in range(trees)]
     t0 = time.perf_counter()
@@ -118,9 +122,19 @@ def cpu_baseline_python(args, cores, trees):
         with mp.get_context("fork").Pool(cores) as pool:
             res = pool.map(_cpu_fit_worker, jobs, chunksize=1)
     wall = time.perf_counter() - t0
-    sims = sum(r[1] for r in res)
-    steps = sum(r[2] for r in res)
-    return wall, sims, steps
+    return wall, sum(r[1] for r in res), sum(r[2] for r in res)
+
+
+def cpu_baseline(args, cores, trees):
+    """The reference's CPU path for the headline config: its OWN MctsHash.fit (unmodified files staged under
+    baseline/_ref, imported through oracle/ref_loader.py) when present -> kind "reference"; else the port."""
+    from oracle import ref_bench
+    default_cfg = (args.nsim, args.c, args.gamma, args.max_depth) == (1000, 1.0, 0.99, 500)
+    if ref_bench.reference_root() is not None and default_cfg:
+        w, s, st = ref_bench.time_many("c5", trees, cores)
+        return w, s, st, "reference", "the reference's own MctsHash.fit (islaMcts/agents/mcts_hash.py, staged unmodified in baseline/_ref) on the float64 env restatement"
+    w, s, st = cpu_baseline_port(args, cores, trees)
+    return w, s, st, "port", "oracle/py_port.py, pure-Python port of MctsHash.fit (same per-node work as the reference)"
 
 
 def cpu_baseline_native(args, threads, trees):
@@ -142,22 +156,22 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     trees = args.cpu_trees or cores
     for _ in range(min(args.warmup, 1)):
-        cpu_baseline_python(args, cores, max(1, cores // 4))
+        cpu_baseline(args, cores, max(1, cores // 4))
     walls, sims, steps = [], 0, 0
+    kind = note = None
     for _ in range(args.steps):
-        w, s, st = cpu_baseline_python(args, cores, trees)
+        w, s, st, kind, note = cpu_baseline(args, cores, trees)
         walls.append(w); sims += s; steps += st
     total = sum(walls)
     value = sims / total
     line = {
         "metric": "mcts_simulations_per_second", "value": value, "unit": "sims/s", "impl": "reference",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": f"{trees} trees x nsim={args.nsim} per step"},
         "env_steps_per_s": steps / total,
-        "cpu_baseline": {"value": value, "unit": "sims/s", "cores": cores, "kind": "port",
-                         "sample": f"{trees} independent CartPole fits x nsim={args.nsim} per step on {cores} processes "
-                                   f"(oracle/py_port.py: pure-Python port of MctsHash.fit, same per-node work as the reference)"},
+        "cpu_baseline": {"value": value, "unit": "sims/s", "cores": cores, "kind": kind,
+                         "sample": f"{trees} independent CartPole fits x nsim={args.nsim} per step on {cores} processes ({note})"},
         "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -171,6 +185,7 @@ def run_isla(args):
     import torch.distributed as dist
 
     from islamcts_b200 import _lib
+    from islamcts_b200 import engine as E
     from islamcts_b200.batch import RootParallelSearch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -186,13 +201,17 @@ def run_isla(args):
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
     prec = _lib.PRECISION_F64 if args.precision == "f64" else _lib.PRECISION_F32
-    search = RootParallelSearch("CartPole-v1", trees_per_rank=args.trees, n_sim=args.nsim, C=args.c, gamma=args.gamma,
-                                max_depth=args.max_depth, n_roots=args.roots, seed=0, precision=prec, device=dev,
-                                process_group=pg, rank=rank, world_size=world)
-    # synthetic roots: CartPole reset distribution U(-0.05,0.05)^4, seed = root id (same on every rank)
-    g = torch.Generator().manual_seed(1234)
-    roots_host = ((torch.rand((args.roots, 4), generator=g, dtype=torch.float64) - 0.5) * 0.1).pin_memory()
-    tree_roots = search.expand_roots(roots_host)
+
+    def make_search(n_roots, weak=False, trees=None):
+        kw = dict(trees_per_rank=trees or args.trees) if weak else dict(total_trees=trees or args.trees)
+        return RootParallelSearch("CartPole-v1", n_sim=args.nsim, C=args.c, gamma=args.gamma, max_depth=args.max_depth,
+                                  n_roots=n_roots, seed=0, precision=prec, device=dev, process_group=pg, rank=rank,
+                                  world_size=world, **kw)
+
+    def synthetic_roots(n_roots):
+        # CartPole reset distribution U(-0.05,0.05)^4, same on every rank
+        g = torch.Generator().manual_seed(1234)
+        return ((torch.rand((n_roots, 4), generator=g, dtype=torch.float64) - 0.5) * 0.1).pin_memory()
 
     def barrier():
         if world > 1:
@@ -212,19 +231,22 @@ def run_isla(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    search = make_search(args.roots, weak=args.weak)
+    roots_host = synthetic_roots(args.roots)
+    tree_roots = search.expand_roots(roots_host)
+    trees_job = search.trees * world
+
     # ---- device-resident pass
     for _ in range(args.warmup):
         search.search_device(tree_roots)
-    cnt0 = search.engine.counters()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    l0 = E.kernel_launches()
     ms = timed(lambda: search.search_device(tree_roots), args.steps)
+    launches = (E.kernel_launches() - l0) * world          # counted by the library; every rank launches the same kernels
     clk = clocks.stop() if rank == 0 else None
-    cnt1 = search.engine.counters()
-    # counters are reset by set_roots each pass: cnt1 is the last pass only
-    sims_per_pass = args.trees * args.nsim
-    total_sims = sims_per_pass * world * args.steps
+    total_sims = trees_job * args.nsim * args.steps
     value = total_sims / (ms * 1e-3)
 
     # ---- kernel-only timing of the dominant kernel (the search kernel), same stream, CUDA events
@@ -255,47 +277,89 @@ def run_isla(args):
     e2e_ms = timed(lambda: search.fit(roots_host), args.steps)
     e2e_value = total_sims / (e2e_ms * 1e-3)
 
+    # ---- the other root layouts of SURVEY 8(e) and the other scaling mode (same kernel; short runs)
+    layouts = {}
+    msg_main = search.merge_message_bytes()
+    arena_gb = eng.layout.total_bytes / 1e9
+    del search, eng, tree_roots
+    torch.cuda.empty_cache()
+    if not args.no_extras:
+        steps_x = max(2, min(args.steps, 3))
+        for name, n_roots in (("one_shared_root", 1), ("all_distinct_roots", args.trees)):
+            try:
+                sx = make_search(n_roots)
+            except ValueError:
+                continue
+            rx = sx.expand_roots(synthetic_roots(n_roots))
+            sx.search_device(rx)
+            mx = timed(lambda: sx.search_device(rx), steps_x)
+            layouts[name] = {"roots": n_roots, "sims_per_s": sx.trees * world * args.nsim * steps_x / (mx * 1e-3),
+                             "ms_per_step": mx / steps_x, "allreduce_message_bytes": sx.merge_message_bytes()}
+            del sx, rx
+            torch.cuda.empty_cache()
+        if world > 1 and not args.weak:
+            sx = make_search(args.roots, weak=True)
+            rx = sx.expand_roots(synthetic_roots(args.roots))
+            sx.search_device(rx)
+            mx = timed(lambda: sx.search_device(rx), steps_x)
+            layouts["weak_scaling"] = {"trees_per_gpu": sx.trees, "roots": args.roots,
+                                       "sims_per_s": sx.trees * world * args.nsim * steps_x / (mx * 1e-3),
+                                       "ms_per_step": mx / steps_x, "allreduce_message_bytes": sx.merge_message_bytes()}
+            del sx, rx
+            torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
+    # MUFU (SFU) rate of the search kernel: 4 per re-evaluated level (two reciprocals, two square roots of the fp32 UCB
+    # screening) + 1 per env step (the fast division of the float32 CartPole step) against SMs x 16 lanes x clock
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    mufu_per_s = (cnt["levels"] * 4 + cnt["env_steps"]) / (kern_ms * 1e-3)
     line = {
         "metric": "mcts_simulations_per_second", "value": value, "unit": "sims/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64 tree statistics / " + args.precision + " env", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "trees_per_gpu": args.trees, "nsim": args.nsim, "roots": args.roots,
-                   "C": args.c, "gamma": args.gamma, "max_depth": args.max_depth,
+        "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
+        "dtype": "f64 tree statistics / " + args.precision + " env", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "trees_total": trees_job, "trees_per_gpu": trees_job // world, "nsim": args.nsim,
+                   "roots": args.roots, "C": args.c, "gamma": args.gamma, "max_depth": args.max_depth,
+                   "allreduce_message_bytes": msg_main,
                    "l2": "working set (tree arena %.1f GB/GPU) larger than L2; trees are rebuilt every step"
-                         % (eng.layout.total_bytes / 1e9)},
+                         % arena_gb},
         "env_steps_per_s": cnt["env_steps"] * world / (kern_ms * 1e-3),
         "levels_per_sim": levels_per_sim, "rollout_steps_per_sim": cnt["rollout_steps"] / max(1, cnt["sims"]),
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peak, "unit": "GB/s", "frac": achieved_gbs / peak,
                      "traffic": None, "kernel": "tpt_search_kernel<CartPole,%s>" % args.precision,
                      "kernel_ms": kern_ms, "peak_source": peak_src,
-                     "algorithmic_bytes": "levels*(12*A+36) + sims*16 (SURVEY 8d), A=2"},
-        "e2e": {"value": e2e_value, "unit": "sims/s", "h2d_bytes_per_step": search.h2d_bytes(),
-                "d2h_bytes_per_step": search.d2h_bytes(), "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": 4 * args.steps,   # per step: tpt_set_roots, tpt_search, tpt_root_stats, merge_root_stats
+                     "algorithmic_bytes": "levels*(12*A+36) + sims*16 (SURVEY 8d), A=2",
+                     "note": "SURVEY's byte model counts 60 B per visited level; the kernel moves 36 (implicit visit counts, "
+                             "returns read from a table instead of a stored row), so `frac` can exceed the share of DRAM time: see dram_frac",
+                     "mufu_per_s": mufu_per_s, "mufu_frac": mufu_per_s / (sm_count * 16 * 1.965e9)},
+        "e2e": {"value": e2e_value, "unit": "sims/s", "h2d_bytes_per_step": args.roots * 4 * 8,
+                "d2h_bytes_per_step": args.roots * (4 + 2 * 16), "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches,
         "clocks": clk,
     }
-    if not args.no_extras and world == 1:
-        line["extras"] = other_configs(dev)
+    if layouts:
+        line["root_layouts"] = layouts
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tr = json.load(f)
-        if tr.get("nsim") == args.nsim and tr.get("trees") == args.trees:
+        if tr.get("nsim") == args.nsim and tr.get("trees") == trees_job // world:
             line["roofline"]["traffic"] = tr["dram_bytes_per_launch"]
             line["roofline"]["traffic_source"] = tr["source"]
+            line["roofline"]["dram_frac"] = tr["dram_bytes_per_launch"] / (kern_ms * 1e-3) / 1e9 / peak
     except Exception:
         pass
+    if not args.no_extras and world == 1:
+        line["extras"] = other_configs(dev)
     if not args.no_cpu_baseline and world == 1:
         cores_avail = os.cpu_count() or 1
-        w, s, st = cpu_baseline_python(args, 1, args.cpu_trees or 3)
-        line["cpu_baseline"] = {"value": s / w, "unit": "sims/s", "cores": 1, "kind": "port",
-                                "env_steps_per_s": st / w,
-                                "sample": f"{args.cpu_trees or 3} CartPole fits x nsim={args.nsim}, 1 core "
-                                          f"(oracle/py_port.py, pure-Python port of MctsHash.fit)"}
+        n_fit = args.cpu_trees or 3
+        w, s, st, kind, note = cpu_baseline(args, 1, n_fit)
+        line["cpu_baseline"] = {"value": s / w, "unit": "sims/s", "cores": 1, "kind": kind, "env_steps_per_s": st / w,
+                                "sample": f"{n_fit} CartPole fits x nsim={args.nsim}, 1 core ({note})"}
         nt = min(cores_avail, 64)
         w2, s2, st2 = cpu_baseline_native(args, nt, nt * 8)
         line["cpu_baseline_native_c"] = {"value": s2 / w2, "unit": "sims/s", "cores": nt, "kind": "port",
@@ -322,6 +386,20 @@ def other_configs(dev):
             best = min(best, e0.elapsed_time(e1))
         return best * 1e-3
 
+    def ref_cpu(config, fits=1, n_sim=None):
+        """The reference's own class for that config on ONE host core (oracle/ref_bench.py; HEAD semantics)."""
+        try:
+            from oracle import ref_bench
+            if ref_bench.reference_root() is None:
+                return {"unavailable": "baseline/_ref not staged"}
+            w, s_, st = ref_bench.time_many(config, fits, 1, n_sim)
+            sc = ref_bench.CONFIGS[config]
+            return {"sims_per_s": s_ / w, "env_steps_per_s": st / w, "cores": 1, "kind": "reference",
+                    "sample": "%d x %s.fit(), nsim=%d (reference HEAD: %s)" % (fits, sc["agent"], n_sim or sc["n_sim"],
+                              "budgeted rollouts" if sc["agent"] == "MctsHash" else "zero-length rollouts")}
+        except Exception as e:   # the baseline is reported, never required
+            return {"unavailable": repr(e)[:200]}
+
     out = {}
     g = torch.Generator().manual_seed(7)
     # C1: vanilla FrozenLake nsim=100 C=0.5 gamma=1 max_depth=1000: one tree, and 65 536 trees (thread-per-tree)
@@ -330,13 +408,20 @@ def other_configs(dev):
         roots = torch.zeros((nt, 1), dtype=torch.float64, device=dev)
         t = timeit(lambda: eng.set_roots(roots).run(100))
         out[name] = {"sims_per_s": nt * 100 / t, "ms": t * 1e3}
+    # the reference's Mcts.fit passes max_depth as the depth (zero-length rollouts): the same semantics on the device
+    eng = Engine(_lib.ENV_FROZENLAKE, n_trees=1, sim_capacity=100, max_depth=1000, C_=0.5, gamma=1.0, budget_mode=_lib.BUDGET_ZERO,
+                 kernel=_lib.KERNEL_THREAD_PER_TREE, seed=1, device=dev)
+    roots = torch.zeros((1, 1), dtype=torch.float64, device=dev)
+    t = timeit(lambda: eng.set_roots(roots).run(100))
+    out["c1_frozenlake_1tree_reference_head"] = {"sims_per_s": 100 / t, "ms": t * 1e3, "cpu_reference": ref_cpu("c1", fits=20)}
     # C2: one CartPole tree, nsim=1000, 4096 rollouts per leaf
     eng = Engine(_lib.ENV_CARTPOLE, n_trees=1, sim_capacity=1000, max_depth=500, C_=1.0, gamma=0.99, kernel=_lib.KERNEL_CTA_PER_TREE,
                  rollouts_per_leaf=4096, seed=1, device=dev)
     roots = (torch.rand((1, 4), generator=g, dtype=torch.float64) - 0.5) * 0.1
     t = timeit(lambda: eng.set_roots(roots).run(1000))
     c = eng.counters()
-    out["c2_cartpole_1tree_4096rollouts"] = {"sims_per_s": 1000 / t, "env_steps_per_s": c["env_steps"] / t, "ms": t * 1e3}
+    out["c2_cartpole_1tree_4096rollouts"] = {"sims_per_s": 1000 / t, "env_steps_per_s": c["env_steps"] / t, "ms": t * 1e3,
+                                             "cpu_reference": ref_cpu("c2", fits=1)}
     # the same shape as a batch of 296 trees (2 CTAs per SM): what the GPU does with C2 when it is not alone
     eng = Engine(_lib.ENV_CARTPOLE, n_trees=296, sim_capacity=1000, max_depth=500, C_=1.0, gamma=0.99, kernel=_lib.KERNEL_CTA_PER_TREE,
                  rollouts_per_leaf=4096, seed=1, device=dev)
@@ -351,6 +436,11 @@ def other_configs(dev):
     t = timeit(lambda: eng.set_roots(roots).run(10000), reps=2)
     c = eng.counters()
     out["c3_apw_pendulum_1tree"] = {"sims_per_s": 10000 / t, "env_steps_per_s": c["env_steps"] / t, "ms": t * 1e3}
+    engz = Engine(_lib.ENV_PENDULUM, agent=_lib.AGENT_APW, n_trees=1, sim_capacity=10000, max_depth=200, C_=1.0, gamma=0.99, alpha1=0.8,
+                  k1=60.0, kernel=_lib.KERNEL_CTA_PER_TREE, rollouts_per_leaf=1, budget_mode=_lib.BUDGET_ZERO, seed=1, device=dev)
+    tz = timeit(lambda: engz.set_roots(roots).run(10000), reps=2)
+    out["c3_apw_pendulum_1tree_reference_head"] = {"sims_per_s": 10000 / tz, "ms": tz * 1e3, "cpu_reference": ref_cpu("c3")}
+    del engz
     # post-fit analytics of the sweep loop (sweep.py:199-200) on that 10 000-child tree: device kernel vs decoding the whole tree
     import time as _time
     eng.depth_stats(0); torch.cuda.synchronize(dev)
@@ -363,6 +453,11 @@ def other_configs(dev):
     t = timeit(lambda: eng.set_roots(roots).run(10000), reps=2)
     c = eng.counters()
     out["c4_dpw_mountaincar_1tree"] = {"sims_per_s": 10000 / t, "env_steps_per_s": c["env_steps"] / t, "ms": t * 1e3}
+    engz = Engine(_lib.ENV_MOUNTAINCAR, agent=_lib.AGENT_DPW, n_trees=1, sim_capacity=10000, max_depth=500, C_=1.0, gamma=0.99,
+                  alpha1=0.5, k1=1.0, alpha2=0.5, k2=1.0, kernel=_lib.KERNEL_CTA_PER_TREE, budget_mode=_lib.BUDGET_ZERO, seed=1, device=dev)
+    tz = timeit(lambda: engz.set_roots(roots).run(10000), reps=2)
+    out["c4_dpw_mountaincar_1tree_reference_head"] = {"sims_per_s": 10000 / tz, "ms": tz * 1e3, "cpu_reference": ref_cpu("c4")}
+    del engz
     # CurveEnv (the env sweep.py / sweep_vanilla.py / examples/example_curve.py of the reference actually run), from an
     # on-track pose (three braking right turns after reset): APW random expansion, APW + voo as in example_curve.py:32-45,
     # vanilla MctsHash on DiscreteCurveEnv([5, 19]) (sweep_vanilla.py:177 defaults) as one tree and as 4096 trees
@@ -406,7 +501,9 @@ def other_configs(dev):
                                              "sims_per_s": res["real_steps"] * 1000 / dt, "mean_steps": float(res["n_steps"].mean())}
     # R: rollout micro-benchmark, 2^24 trajectories from the reset distribution, random policy, budget = max_depth
     flop = {0: 36, 1: 27, 2: 27, 3: 6}
+    mufu = {0: 4, 1: 2, 2: 1, 3: 0}     # CartPole 1 sin + 1 cos + 2 div, Pendulum 1 sin + 1 mod, MountainCar 1 cos
     peak_fp32 = 148 * 128 * 2 * 1.965e9
+    peak_sfu = 148 * 16 * 1.965e9
     for env_id, name, budget, gamma in ((0, "cartpole", 500, 0.99), (1, "pendulum", 200, 0.99), (2, "mountaincar", 500, 0.99), (3, "frozenlake", 1000, 1.0)):
         n = 1 << 24 if env_id in (0, 3) else 1 << 21
         steps = []
@@ -416,7 +513,10 @@ def other_configs(dev):
         t = timeit(run, reps=5)
         total = int(steps[-1].sum().item())
         out["rollout_" + name] = {"trajectories": n, "env_steps_per_s": total / t, "mean_len": total / n, "ms": t * 1e3,
-                                  "fp32_roofline_frac": total / t * flop[env_id] / peak_fp32}
+                                  "fp32_roofline_frac": total / t * flop[env_id] / peak_fp32,
+                                  "roofline": {"bound": "fp32 issue", "achieved": total / t * flop[env_id] / 1e12, "peak": peak_fp32 / 1e12,
+                                               "unit": "TFLOP/s", "frac": total / t * flop[env_id] / peak_fp32,
+                                               "mufu_frac": total / t * mufu[env_id] / peak_sfu}}
     return out
 
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ISLA_ABI_VERSION 2
+#define ISLA_ABI_VERSION 3
 
 typedef enum {
     ISLA_OK = 0,
@@ -189,12 +189,21 @@ int isla_episode_step(int32_t env_id, int32_t action_grid0, int32_t action_grid1
  * [3] simulations, [4] nodes created, [5] faults.  SYNCHRONISES the stream. */
 int isla_engine_counters(isla_engine* e, int64_t out_host[8], void* stream);
 
-/* Root-parallel merge (north_star (4)): per-root sums over the trees that share a root.
- * group_dev[n_trees] = root id in [0, n_roots); outputs [n_roots][n_actions], zero-filled first.
- * The caller then all-reduces the two arrays over NCCL. */
+/* Root-parallel merge (north_star (4); replaces the reference's only parallel construct, joblib over whole
+ * experiments, islaMcts/experiment_runner.py:305-306): per-root sums over the trees that share a root, in a FIXED
+ * order (bit-reproducible totals).  group_dev[n_trees] = root id in [0, n_roots), ASCENDING (the trees of a root are
+ * contiguous); NULL = tree i is root i.  Outputs [n_roots][n_actions].  The caller then all-reduces over NCCL. */
 int isla_merge_root_stats(const int64_t* na_dev, const double* total_dev, const int32_t* group_dev,
                           int64_t n_trees, int32_t n_actions, int64_t n_roots, int64_t* na_out_dev,
                           double* total_out_dev, void* stream);
+
+/* root_stats + merge in ONE launch for the thread-per-tree engine, packed for ONE all-reduce: tree i belongs to root
+ * i / (n_trees / n_roots); packed_out_dev[n_roots][n_actions][2] = {na as float64 (exact: counts << 2**53), total}.
+ * q = total / na and the arg-max follow on every rank (mcts_hash.py:42-50). */
+int isla_engine_root_merge(isla_engine* e, int64_t n_roots, double* packed_out_dev, void* stream);
+
+/* Kernels this library has launched in this process (bench.py's gpu_launches is a difference of two readings). */
+int64_t isla_kernel_launches(void);
 
 /* env.step over a batch (parity of the dynamics): states [n][state_dim], actions [n][action_dim] (discrete:
  * index as a real; ISLA_ENV_CURVE: (acceleration, steering) -- DiscreteCurveEnv indices are decoded by the caller),

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstring>
 #include <new>
+#include <atomic>
 #include <vector>
 
 #include "isla_envs.cuh"
@@ -158,16 +159,63 @@ static int fill_layout(const isla_config& cfg, isla_layout& lay) {
     return resolve_kernel(cfg) == ISLA_KERNEL_THREAD_PER_TREE ? tpt_fill_layout(cfg, lay) : cta_fill_layout(cfg, lay);
 }
 
-__global__ void merge_root_stats_kernel(const int64_t* na, const double* total, const int32_t* group, long long n_trees,
-                                        int A, unsigned long long* na_out, double* total_out) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_trees * A) return;
-    const long long tree = i / A;
-    const int a = (int)(i % A);
-    const long long g = group ? group[tree] : tree;
-    atomicAdd(na_out + g * A + a, (unsigned long long)na[i]);
-    atomicAdd(total_out + g * A + a, total[i]);
+// Per-root sums in a FIXED order (bit-reproducible totals, unlike float atomics): the trees of a root are summed by one
+// CTA -- every thread adds the root's trees first + tid, first + tid + T, ... in ascending order, then a pairwise tree over
+// the T partial sums in shared memory.  `group` (root of each tree) must be ASCENDING, i.e. the trees of a root are
+// contiguous (what sharding.plan() lays out); the CTA finds its range by binary search.  group == nullptr: tree i = root i.
+__global__ void __launch_bounds__(256) merge_root_stats_kernel(const int64_t* na, const double* total, const int32_t* group, long long n_trees,
+                                                               int A, long long* na_out, double* total_out) {
+    extern __shared__ double red[];   // [blockDim.x] totals | [blockDim.x] counts (as int64)
+    long long* const redn = reinterpret_cast<long long*>(red + blockDim.x);
+    const long long root = blockIdx.x;
+    long long first = root, last = root + 1;
+    if (group) {
+        auto lower = [&](long long key) { long long lo = 0, hi = n_trees; while (lo < hi) { const long long mid = (lo + hi) >> 1; if (group[mid] < key) lo = mid + 1; else hi = mid; } return lo; };
+        first = lower(root); last = lower(root + 1);
+    }
+    if (last > n_trees) last = n_trees;
+    for (int a = 0; a < A; ++a) {
+        double t = 0.0; long long n = 0;
+        for (long long tree = first + threadIdx.x; tree < last; tree += blockDim.x) { t = __dadd_rn(t, total[tree * A + a]); n += na[tree * A + a]; }
+        red[threadIdx.x] = t; redn[threadIdx.x] = n;
+        __syncthreads();
+        for (int s_ = blockDim.x >> 1; s_ > 0; s_ >>= 1) {
+            if ((int)threadIdx.x < s_) { red[threadIdx.x] = __dadd_rn(red[threadIdx.x], red[threadIdx.x + s_]); redn[threadIdx.x] += redn[threadIdx.x + s_]; }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) { total_out[root * A + a] = red[0]; na_out[root * A + a] = redn[0]; }
+        __syncthreads();
+    }
 }
+
+// The same sums straight from the thread-per-tree engine's root blocks, for CONTIGUOUS equal groups (tree i belongs to
+// root i / per_root, what sharding.plan() lays out), packed for ONE all-reduce: out[root][a] = {na as double, total}.
+// Visit counts are far below 2**53, so the float64 sum of counts is exact.
+__global__ void __launch_bounds__(256) tpt_root_merge_kernel(const char* blocks, long long slots_per_tree, int A, long long per_root,
+                                                             double* out) {
+    extern __shared__ double red[];   // [blockDim.x] totals | [blockDim.x] counts
+    double* const redn = red + blockDim.x;
+    const long long root = blockIdx.x;
+    for (int a = 0; a < A; ++a) {
+        double t = 0.0, n = 0.0;
+        for (long long i = threadIdx.x; i < per_root; i += blockDim.x) {
+            const char* b = blocks + (root * per_root + i) * slots_per_tree * 16 + (long long)A * 16;   // block 1 = the root's edges
+            t = __dadd_rn(t, reinterpret_cast<const double*>(b)[a]);
+            n += (double)reinterpret_cast<const int32_t*>(b + A * 8)[a];
+        }
+        red[threadIdx.x] = t; redn[threadIdx.x] = n;
+        __syncthreads();
+        for (int s_ = blockDim.x >> 1; s_ > 0; s_ >>= 1) {
+            if ((int)threadIdx.x < s_) { red[threadIdx.x] = __dadd_rn(red[threadIdx.x], red[threadIdx.x + s_]); redn[threadIdx.x] += redn[threadIdx.x + s_]; }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) { out[(root * A + a) * 2] = redn[0]; out[(root * A + a) * 2 + 1] = red[0]; }
+        __syncthreads();
+    }
+}
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 }  // namespace isla
 
@@ -258,6 +306,7 @@ int isla_engine_set_roots(isla_engine* e, const double* roots_dev, void* stream)
     const int rc = e->kernel == ISLA_KERNEL_THREAD_PER_TREE ? tpt_set_roots(e, roots_dev, (cudaStream_t)stream)
                                                             : cta_set_roots(e, roots_dev, (cudaStream_t)stream);
     if (rc == 0) e->roots_set = true;
+    if (rc == 0) count_launch(1);
     return rc;
 }
 
@@ -266,8 +315,10 @@ int isla_engine_run(isla_engine* e, int32_t n_sim, void* stream) {
     if (!e->roots_set) { set_error("isla_engine_set_roots must be called before run"); return ISLA_ERR_INVALID; }
     if (n_sim < 0) { set_error("n_sim < 0"); return ISLA_ERR_INVALID; }
     if (n_sim == 0) return ISLA_OK;
-    return e->kernel == ISLA_KERNEL_THREAD_PER_TREE ? tpt_run(e, n_sim, -1, nullptr, nullptr, 0, (cudaStream_t)stream)
+    const int rc_ = e->kernel == ISLA_KERNEL_THREAD_PER_TREE ? tpt_run(e, n_sim, -1, nullptr, nullptr, 0, (cudaStream_t)stream)
                                                     : cta_run(e, n_sim, -1, nullptr, nullptr, 0, (cudaStream_t)stream);
+    if (rc_ == 0) count_launch(1);
+    return rc_;
 }
 
 int isla_engine_run_scripted(isla_engine* e, int64_t tree, int32_t n_sim, const uint8_t* kinds_dev, const double* values_dev,
@@ -277,20 +328,26 @@ int isla_engine_run_scripted(isla_engine* e, int64_t tree, int32_t n_sim, const 
     if (tree < 0 || tree >= e->cfg.n_trees) { set_error("tree index out of range"); return ISLA_ERR_INVALID; }
     if (trace_len > 0 && (!kinds_dev || !values_dev)) { set_error("null trace"); return ISLA_ERR_INVALID; }
     if (n_sim <= 0) return ISLA_OK;
-    return e->kernel == ISLA_KERNEL_THREAD_PER_TREE ? tpt_run(e, n_sim, tree, kinds_dev, values_dev, trace_len, (cudaStream_t)stream)
+    const int rc_ = e->kernel == ISLA_KERNEL_THREAD_PER_TREE ? tpt_run(e, n_sim, tree, kinds_dev, values_dev, trace_len, (cudaStream_t)stream)
                                                     : cta_run(e, n_sim, tree, kinds_dev, values_dev, trace_len, (cudaStream_t)stream);
+    if (rc_ == 0) count_launch(1);
+    return rc_;
 }
 
 int isla_engine_root_stats(isla_engine* e, int64_t* na_dev, double* total_dev, void* stream) {
     if (!e || !na_dev || !total_dev) { set_error("null argument"); return ISLA_ERR_INVALID; }
-    return e->kernel == ISLA_KERNEL_THREAD_PER_TREE ? tpt_root_stats(e, na_dev, total_dev, (cudaStream_t)stream)
+    const int rc_ = e->kernel == ISLA_KERNEL_THREAD_PER_TREE ? tpt_root_stats(e, na_dev, total_dev, (cudaStream_t)stream)
                                                     : cta_root_stats(e, na_dev, total_dev, (cudaStream_t)stream);
+    if (rc_ == 0) count_launch(1);
+    return rc_;
 }
 
 int isla_engine_best(isla_engine* e, int32_t scripted_pos, int32_t* best_dev, double* best_action_dev, void* stream) {
     if (!e || !best_dev) { set_error("null argument"); return ISLA_ERR_INVALID; }
-    return e->kernel == ISLA_KERNEL_THREAD_PER_TREE ? tpt_best(e, scripted_pos, best_dev, best_action_dev, (cudaStream_t)stream)
+    const int rc_ = e->kernel == ISLA_KERNEL_THREAD_PER_TREE ? tpt_best(e, scripted_pos, best_dev, best_action_dev, (cudaStream_t)stream)
                                                     : cta_best(e, scripted_pos, best_dev, best_action_dev, (cudaStream_t)stream);
+    if (rc_ == 0) count_launch(1);
+    return rc_;
 }
 
 int isla_engine_root_children(isla_engine* e, int64_t tree, int32_t cap, double* action_dev, int64_t* na_dev, double* total_dev,
@@ -298,7 +355,9 @@ int isla_engine_root_children(isla_engine* e, int64_t tree, int32_t cap, double*
     if (!e || !count_dev || (cap > 0 && (!action_dev || !na_dev || !total_dev))) { set_error("null argument"); return ISLA_ERR_INVALID; }
     if (tree < 0 || tree >= e->cfg.n_trees) { set_error("tree index out of range"); return ISLA_ERR_INVALID; }
     if (e->kernel != ISLA_KERNEL_CTA_PER_TREE) { set_error("root_children: CTA-per-tree engine only (use root_stats)"); return ISLA_ERR_INVALID; }
-    return cta_root_children(e, tree, cap, action_dev, na_dev, total_dev, count_dev, (cudaStream_t)stream);
+    const int rc_ = cta_root_children(e, tree, cap, action_dev, na_dev, total_dev, count_dev, (cudaStream_t)stream);
+    if (rc_ == 0) count_launch(1);
+    return rc_;
 }
 
 int isla_engine_depth_stats(isla_engine* e, int64_t tree, int32_t cap, int32_t* depth_max_dev, double* depth_mean_dev,
@@ -306,9 +365,11 @@ int isla_engine_depth_stats(isla_engine* e, int64_t tree, int32_t cap, int32_t* 
     if (!e || !count_dev || cap < 0 || (cap > 0 && (!depth_max_dev || !depth_mean_dev))) { set_error("bad argument"); return ISLA_ERR_INVALID; }
     if (tree < 0 || tree >= e->cfg.n_trees) { set_error("tree index out of range"); return ISLA_ERR_INVALID; }
     if (!e->roots_set) { set_error("isla_engine_set_roots must be called first"); return ISLA_ERR_INVALID; }
-    return e->kernel == ISLA_KERNEL_THREAD_PER_TREE
+    const int rc_ = e->kernel == ISLA_KERNEL_THREAD_PER_TREE
                ? tpt_depth_stats(e, tree, cap, depth_max_dev, depth_mean_dev, count_dev, (cudaStream_t)stream)
                : cta_depth_stats(e, tree, cap, depth_max_dev, depth_mean_dev, count_dev, (cudaStream_t)stream);
+    if (rc_ == 0) count_launch(1);
+    return rc_;
 }
 
 int isla_engine_pool_offsets(const isla_engine* e, int64_t out[24]) {
@@ -339,14 +400,31 @@ int isla_merge_root_stats(const int64_t* na_dev, const double* total_dev, const 
         set_error("bad argument"); return ISLA_ERR_INVALID;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    ISLA_CUDA_OK(cudaMemsetAsync(na_out_dev, 0, (size_t)(n_roots * n_actions) * 8, st));
-    ISLA_CUDA_OK(cudaMemsetAsync(total_out_dev, 0, (size_t)(n_roots * n_actions) * 8, st));
-    const long long n = n_trees * n_actions;
-    if (n == 0) return ISLA_OK;
-    merge_root_stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(na_dev, total_dev, group_dev, n_trees, n_actions,
-                                                                         (unsigned long long*)na_out_dev, total_out_dev);
+    // one CTA per root; threads = trees per root rounded up to a power of two (32..256)
+    long long per = n_roots > 0 ? (n_trees + n_roots - 1) / n_roots : 1;
+    int threads = 32;
+    while (threads < 256 && threads < per) threads <<= 1;
+    merge_root_stats_kernel<<<(unsigned)n_roots, threads, (size_t)threads * 16, st>>>(na_dev, total_dev, group_dev, n_trees, n_actions,
+                                                                                     (long long*)na_out_dev, total_out_dev);
     ISLA_CUDA_OK(cudaGetLastError());
+    count_launch(1);
     return ISLA_OK;
 }
+
+int isla_engine_root_merge(isla_engine* e, int64_t n_roots, double* packed_out_dev, void* stream) {
+    if (!e || !packed_out_dev || n_roots < 1) { set_error("bad argument"); return ISLA_ERR_INVALID; }
+    if (e->kernel != ISLA_KERNEL_THREAD_PER_TREE) { set_error("root_merge: thread-per-tree engine only (use root_stats + isla_merge_root_stats)"); return ISLA_ERR_INVALID; }
+    if (e->cfg.n_trees % n_roots) { set_error("root_merge: n_trees must be a multiple of n_roots (contiguous equal groups)"); return ISLA_ERR_INVALID; }
+    const long long per = e->cfg.n_trees / n_roots;
+    int threads = 32;
+    while (threads < 256 && threads < per) threads <<= 1;
+    tpt_root_merge_kernel<<<(unsigned)n_roots, threads, (size_t)threads * 16, (cudaStream_t)stream>>>(
+        e->ws + e->lay.rec_offset, e->lay.slots_per_tree, e->lay.n_actions, per, packed_out_dev);
+    ISLA_CUDA_OK(cudaGetLastError());
+    count_launch(1);
+    return ISLA_OK;
+}
+
+int64_t isla_kernel_launches(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 }  // extern "C"

@@ -10,6 +10,7 @@ namespace isla {
 
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
+void count_launch(int n);   // kernels launched by this library, process-wide (isla_kernel_launches)
 
 #define ISLA_CUDA_OK(expr)                                                   \
     do {                                                                     \

@@ -245,9 +245,11 @@ extern "C" int isla_env_step(int32_t env_id, int32_t precision, const void* stat
                              void* next_states_dev, void* rewards_dev, uint8_t* terminated_dev, void* stream) {
     if (n <= 0) return ISLA_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    return precision == ISLA_PRECISION_F64
+    const int rc = precision == ISLA_PRECISION_F64
                ? isla::env_step_dispatch<double>(env_id, states_dev, actions_dev, n, next_states_dev, rewards_dev, terminated_dev, st)
                : isla::env_step_dispatch<float>(env_id, states_dev, actions_dev, n, next_states_dev, rewards_dev, terminated_dev, st);
+    if (rc == 0) isla::count_launch(1);
+    return rc;
 }
 
 extern "C" int isla_episode_step(int32_t env_id, int32_t action_grid0, int32_t action_grid1, double* states_dev,
@@ -274,6 +276,7 @@ extern "C" int isla_episode_step(int32_t env_id, int32_t action_grid0, int32_t a
     default: set_error("unknown env %d", env_id); return ISLA_ERR_INVALID;
     }
     ISLA_CUDA_OK(cudaGetLastError());
+    count_launch(1);
     return ISLA_OK;
 }
 
@@ -289,7 +292,9 @@ extern "C" int isla_rollout(int32_t env_id, int32_t precision, const void* state
         }
         ag = isla::ActionGrid{action_grid0, action_grid1};
     }
-    return precision == ISLA_PRECISION_F64
+    const int rc = precision == ISLA_PRECISION_F64
                ? isla::rollout_dispatch<double>(env_id, states_dev, n, budget, gamma, seed, sim, ag, returns_dev, steps_dev, st)
                : isla::rollout_dispatch<float>(env_id, states_dev, n, budget, gamma, seed, sim, ag, returns_dev, steps_dev, st);
+    if (rc == 0) isla::count_launch(1);
+    return rc;
 }

@@ -159,6 +159,16 @@ class Engine:
                                                   C.c_void_p(_stream_ptr(self.device))))
         return na, tot
 
+    def root_merge(self, n_roots: int, out: torch.Tensor | None = None):
+        """root_stats + per-root sum in one launch (thread-per-tree engine; tree i belongs to root i // (n_trees // n_roots)):
+        packed float64 [n_roots, A, 2] = (na, total), ready for ONE all-reduce."""
+        if out is None:
+            out = torch.empty((int(n_roots), self.n_actions, 2), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.isla_engine_root_merge(self._h, int(n_roots), C.c_void_p(out.data_ptr()),
+                                                  C.c_void_p(_stream_ptr(self.device))))
+        return out
+
     def best(self, scripted_pos: int = -1):
         """End of fit(): (rank in root.actions, action value) per tree -- device tensors (int32, float64;
         the action is [n_trees, 2] for the continuous CurveEnv box)."""
@@ -341,8 +351,14 @@ def rollout(env_id: int, states, n: int | None = None, budget: int = 500, gamma:
     return ret, steps
 
 
+def kernel_launches() -> int:
+    """Kernels libisla_b200 has launched in this process."""
+    return int(_lib.load().isla_kernel_launches())
+
+
 def merge_root_stats(na, total, group, n_roots: int):
-    """Per-root sums over trees sharing a root (the local half of the root-parallel merge)."""
+    """Per-root sums over trees sharing a root (the local half of the root-parallel merge), in a fixed order.
+    `group` must be ascending (the trees of a root contiguous), as sharding.plan() lays them out."""
     lib = _lib.load()
     dev = na.device
     n_trees, A = na.shape

@@ -14,17 +14,38 @@ class Plan:
     rank: int
     world: int
     trees_per_rank: int
-    n_roots: int
+    n_roots: int               # distinct roots of the WHOLE job
     tree_id_base: int          # global id of this rank's tree 0 (also its Philox stream offset)
-    group: np.ndarray          # int32 [trees_per_rank]: root id of every local tree
+    group: np.ndarray          # int32 [trees_per_rank]: LOCAL root index of every local tree (ascending)
+    local_roots: int = 0       # roots this rank holds trees of
+    root_offset: int = 0       # global id of local root 0
+    scaling: str = "weak"
 
 
 def plan(rank: int, world: int, trees_per_rank: int, n_roots: int) -> Plan:
+    """Weak scaling: every rank searches trees_per_rank trees of its own, trees_per_rank / n_roots for each of the
+    job's n_roots roots (every rank holds every root)."""
     if trees_per_rank % n_roots:
         raise ValueError("trees_per_rank must be a multiple of n_roots")
     per = trees_per_rank // n_roots
     group = (np.arange(trees_per_rank) // per).astype(np.int32)
-    return Plan(rank, world, trees_per_rank, n_roots, rank * trees_per_rank, group)
+    return Plan(rank, world, trees_per_rank, n_roots, rank * trees_per_rank, group, n_roots, 0, "weak")
+
+
+def plan_total(rank: int, world: int, total_trees: int, n_roots: int) -> Plan:
+    """Strong scaling (BASELINE config 5: "65 536 trees sharded across 1/2/4/8"): the job has total_trees trees, tree i
+    belongs to root i // (total_trees / n_roots) and to rank i // (total_trees / world).  A rank therefore holds either
+    n_roots / world whole roots or a 1 / (world / n_roots) share of one root."""
+    if total_trees % world or total_trees % n_roots:
+        raise ValueError("total_trees must be a multiple of the world size and of n_roots")
+    tpr, per = total_trees // world, total_trees // n_roots
+    if tpr % per and per % tpr:
+        raise ValueError("a rank must hold whole roots or a whole fraction of one root")
+    first = rank * tpr
+    gl = (np.arange(first, first + tpr) // per)
+    root_offset = int(gl[0])
+    group = (gl - root_offset).astype(np.int32)
+    return Plan(rank, world, tpr, n_roots, first, group, int(group[-1]) + 1, root_offset, "strong")
 
 
 def segmented_sum(na: torch.Tensor, total: torch.Tensor, group: torch.Tensor, n_roots: int):
@@ -42,10 +63,25 @@ def all_reduce_root_stats(mna: torch.Tensor, mtot: torch.Tensor, group=None) -> 
     dist.all_reduce(mtot, op=dist.ReduceOp.SUM, group=group)
 
 
-def pick(mna: torch.Tensor, mtot: torch.Tensor) -> torch.Tensor:
-    """q = total/na per root and its arg-max (end of fit(), mcts_hash.py:42-50) on the merged statistics."""
+def all_reduce_packed(packed: torch.Tensor, group=None) -> None:
+    """The single exchange step of the packed form: float64 [n_roots, A, 2] = (na, total) summed over ranks, in place
+    (ranks contribute zeros for roots they hold no tree of, so the same call is merge and gather)."""
+    import torch.distributed as dist
+    dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+
+
+def pick(mna: torch.Tensor, mtot: torch.Tensor, seed: int = 0) -> torch.Tensor:
+    """q = total/na per root and a UNIFORMLY RANDOM arg-max among exact ties (end of fit(), mcts_hash.py:42-50:
+    `np.random.choice(max_children)`) on the merged statistics.  The draw comes from a generator seeded with `seed` on
+    the tensors' device, so every rank of a job (same seed, same merged statistics) picks the same action."""
     q = torch.where(mna > 0, mtot / mna.clamp(min=1).to(torch.float64), torch.full_like(mtot, -float("inf")))
-    return q.argmax(dim=1).to(torch.int32)
+    ties = q == q.max(dim=1, keepdim=True).values
+    count = ties.sum(dim=1)
+    g = torch.Generator(device=q.device).manual_seed(int(seed))
+    u = torch.rand(q.shape[0], generator=g, device=q.device, dtype=torch.float64)
+    k = torch.minimum((u * count).floor().to(torch.int64), count - 1)          # position among the tied maxima
+    hit = ties & (ties.cumsum(dim=1) == (k + 1).unsqueeze(1))
+    return hit.to(torch.int8).argmax(dim=1).to(torch.int32)
 
 
 # ---------------------------------------------------------------- continuous-action agents (apw / dpw)
@@ -91,8 +127,10 @@ def all_gather_root_children(actions: torch.Tensor, na: torch.Tensor, total: tor
     return merge_root_children(rows[:, :ad], rows[:, ad].to(torch.int64), rows[:, ad + 1])
 
 
-def pick_continuous(actions: torch.Tensor, na: torch.Tensor, total: torch.Tensor):
-    """arg-max q over the merged children (first maximum); returns (index, action row)."""
+def pick_continuous(actions: torch.Tensor, na: torch.Tensor, total: torch.Tensor, seed: int = 0):
+    """arg-max q over the merged children, exact ties broken uniformly (mcts_action_...:38-44); returns (index, action row)."""
     q = total / na.clamp(min=1).to(torch.float64)
-    i = int(torch.argmax(q).item())
+    tied = torch.nonzero(q == q.max()).reshape(-1)
+    g = torch.Generator(device=q.device).manual_seed(int(seed))
+    i = int(tied[int(torch.randint(len(tied), (1,), generator=g, device=q.device).item())].item()) if len(tied) > 1 else int(tied[0].item())
     return i, actions[i]

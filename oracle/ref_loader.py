@@ -21,7 +21,9 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("ISLA_REFERENCE_ROOT", "/root/reference")
+# /root/reference in the build container; on the GPU box the copy staged by oracle/ref_bench.py (baseline/_ref, git-ignored)
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+REFERENCE_ROOT = os.environ.get("ISLA_REFERENCE_ROOT") or ("/root/reference" if os.path.isdir("/root/reference/islaMcts") else _STAGED)
 
 
 def available() -> bool:

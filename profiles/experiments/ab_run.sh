@@ -1,2 +1,1 @@
-python -m pytest tests/test_gpu_tree_vanilla.py -x -q -m gpu 2>&1 | tail -3
-python profiles/experiments/r2_sweep.py 4096:0 8192:0 16384:0 32768:0 65536:0,28 131072:0
+python -m pytest tests -q -m gpu -s -k "f32_vs_f64 or c5_full or merge or strong_scaling_shard or c3_c4_full" 2>&1 | tail -25

@@ -24,7 +24,7 @@ def test_every_declared_symbol_is_exported(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/isla_b200.h but not exported"
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
-    assert lib.isla_abi_version() == 2
+    assert lib.isla_abi_version() == 3
 
 
 def test_struct_sizes_match_header(lib):

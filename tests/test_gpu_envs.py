@@ -172,3 +172,31 @@ def test_curve_containment_shortcut_equals_100_point_test():
         _, er, et, _ = coracle.env_step(4, s[i], a[i])
         assert bool(t[i]) == et and r[i] == pytest.approx(er, rel=1e-12), (i, s[i], a[i])
     assert 0.05 < t.mean() < 0.95
+
+
+@pytest.mark.parametrize("env_id,budget,gamma,tol", [(0, 500, 0.99, 1e-12), (1, 25, 0.99, 1e-4), (2, 25, 0.99, 1e-5),
+                                                      (1, 200, 0.99, 5e-2), (2, 500, 0.99, 1e-4), (3, 1000, 1.0, 0.0)])
+def test_rollout_returns_f32_vs_f64(env_id, budget, gamma, tol):
+    """The float32 rollout path (what the benchmarks run) against the float64 one on the same Philox action streams:
+    discounted returns on every trajectory that ends on the same step.  A single float32 step is within the north_star
+    tolerance (1e-5 relative, test_env_step_*); a RETURN sums a trajectory along which the float32 state error grows
+    (Pendulum near its unstable equilibrium: measured worst case 2.9e-5 after 25 steps), hence 1e-4 over 25 Pendulum
+    steps, 1e-5 over 25 MountainCar steps; over the full C3 horizon (200 steps of a driven pendulum: trajectories that pass
+    the unstable upright position amplify the float32 rounding, measured worst case 1.8e-2 of 8192) the bound is 5e-2 and
+    the MEDIAN deviation must stay below 1e-5; 1e-4 over the C4 horizon.  CartPole's closed-form return and FrozenLake's
+    integers agree exactly."""
+    from islamcts_b200 import engine as E
+    n = 8192
+    ret64, st64 = E.rollout(env_id, None, n=n, budget=budget, gamma=gamma, seed=11, sim=3, precision=1)
+    ret32, st32 = E.rollout(env_id, None, n=n, budget=budget, gamma=gamma, seed=11, sim=3, precision=0)
+    same = (st64 == st32).cpu().numpy()
+    assert same.mean() > 0.995
+    r64, r32 = ret64.cpu().numpy()[same], ret32.cpu().numpy()[same]
+    scale = np.maximum(np.abs(r64), 1.0)
+    dev = np.abs(r32 - r64) / scale
+    assert dev.max() <= tol, (dev.max(), np.argmax(dev))
+    assert np.median(dev) <= 1e-5
+    # and the float64 path is the oracle's (steps exact, returns 1e-11) on a few trajectories of this configuration
+    for i in range(8):
+        eret, esteps = coracle.rollout(env_id, coracle.env_reset(env_id, 11, i), budget, gamma, 11, i, 3, 0)
+        assert int(st64[i]) == esteps and float(ret64[i]) == pytest.approx(eret, rel=1e-11, abs=1e-11)

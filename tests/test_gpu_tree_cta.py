@@ -233,3 +233,35 @@ def test_c3_c4_shapes_run_at_full_size():
     assert len(a) == 101 and na.sum() == 10000       # the root reaches 101 children, 9 899 UCB picks
     ser = e4.export_tree(0)
     assert ser["count"][0] == 10000 and ser["depth"].max() == 1
+
+
+@pytest.mark.parametrize("name,kw,rpl", [
+    ("c3", dict(env_id=1, agent=1, max_depth=200, C=1.0, gamma=0.99, alpha1=0.8, k1=60.0), 1),
+    ("c4", dict(env_id=2, agent=3, max_depth=500, C=1.0, gamma=0.99, alpha1=0.5, k1=1.0, alpha2=0.5, k2=1.0), 1),
+    ("c3_zero", dict(env_id=1, agent=1, max_depth=200, C=1.0, gamma=0.99, alpha1=0.8, k1=60.0, budget_mode=1), 1),
+])
+def test_c3_c4_full_size_free_running_equals_oracle(name, kw, rpl):
+    """BASELINE C3 (APW Pendulum k=60 alpha=0.8) and C4 (DPW MountainCarContinuous alpha=0.5) at nsim = 10 000 as
+    benchmarked: the 10 000-child root (child-array doubling, the action hash set near capacity) / the 101-child root with
+    9 899 UCB picks, node for node against the C oracle on the same Philox streams (float64 env)."""
+    n_sim = 10000
+    root = coracle.env_reset(kw["env_id"], 0, 0)
+    eng = _engine(dict(kw), 1, n_sim, 1, rollouts_per_leaf=rpl, seed=17, tree_id_base=3)
+    eng.set_roots(root[None, :]).run(n_sim)
+    assert eng.counters()["faults"] == 0
+    okw = dict(kw)
+    conf = coracle.make_config(okw.pop("env_id"), C_=okw.pop("C"), rollouts_per_leaf=rpl, seed=17, tree_id=3, **okw)
+    t = coracle.Tree(conf, root)
+    assert t.run(n_sim) == 0
+    assert_tree_equal(eng.export_tree(0), {"tree_" + k: v for k, v in t.serialise().items()}, rtol=1e-9, atol=1e-9)
+    a, na, tot = eng.root_children(0)
+    oa, ona, otot = t.root_children()
+    np.testing.assert_array_equal(na, ona)
+    np.testing.assert_array_equal(a, oa)
+    np.testing.assert_allclose(tot, otot, rtol=1e-9, atol=1e-9)
+    c, oc = eng.counters(), t.counters()
+    assert c["rollout_steps"] == oc["rollout_steps"] and c["env_steps"] == oc["env_steps"]
+    if name == "c4":
+        assert len(a) == 101
+    else:
+        assert len(a) >= 9990
