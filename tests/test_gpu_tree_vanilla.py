@@ -241,15 +241,19 @@ def test_slippery_lake_free_running_equals_oracle(kernel):
     assert short.counters()["faults"] > 0          # a noise table shorter than the simulation is a loud fault
 
 
-@pytest.mark.parametrize("tpw", [1, 3, 16, 32])
-def test_trees_per_warp_does_not_change_results(tpw):
-    """The launch picks how many trees a warp owns (tuning bits 8..13 pin it for the test): ragged tree counts, partial
-    last warps and every trees-per-warp value build the same trees as the oracle."""
+@pytest.mark.parametrize("tuning", [1 << 8, 3 << 8, 16 << 8, 32 << 8,
+                                    4 | (1 << 8) | (1 << 16), 4 | (5 << 8) | (7 << 16), 4 | (13 << 8) | (2 << 16),
+                                    4 | (28 << 8) | (7 << 16), 4 | (32 << 8) | (3 << 16), 4, 4 | 2 | (9 << 8) | (4 << 16)])
+def test_launch_shape_does_not_change_results(tuning):
+    """The launch picks how many trees a warp owns (tuning bits 8..13 pin it for the test) or, with tuning bit 4, runs the
+    worker / owner kernel (isla_tree_flow.cu; bits 8..13 = trees per CTA, bits 16..19 = worker warps, bit 2 = cooperative
+    phase at any depth): ragged tree counts, partial last warps / CTAs, workers without trees and every shape build the
+    same trees as the oracle."""
     from islamcts_b200.engine import Engine
     n_trees, n_sim = 77, 180
     roots = np.stack([coracle.env_reset(0, 13, i) for i in range(n_trees)])
-    eng = Engine(0, n_trees=n_trees, sim_capacity=n_sim, max_depth=120, C_=1.0, gamma=0.98, precision=1, kernel=1, seed=77,
-                 tree_id_base=5, tuning=tpw << 8)
+    eng = Engine(0, n_trees=n_trees, sim_capacity=2 * n_sim, max_depth=120, C_=1.0, gamma=0.98, precision=1, kernel=1, seed=77,
+                 tree_id_base=5, tuning=tuning)
     eng.set_roots(roots).run(n_sim)
     na, tot = eng.root_stats()
     cfg = coracle.make_config(0, n_actions=2, max_depth=120, C_=1.0, gamma=0.98, seed=77, tree_id=5)
@@ -258,6 +262,15 @@ def test_trees_per_warp_does_not_change_results(tpw):
     np.testing.assert_allclose(tot.cpu().numpy(), etot, rtol=1e-9, atol=1e-9)
     c = eng.counters()
     assert c["faults"] == 0 and c["levels"] == ecnt["levels"] and c["rollout_steps"] == ecnt["rollout_steps"]
+    for i in (0, 76):
+        t = coracle.Tree(coracle.make_config(0, n_actions=2, max_depth=120, C_=1.0, gamma=0.98, seed=77, tree_id=5 + i), roots[i])
+        assert t.run(n_sim) == 0
+        assert_tree_equal(eng.export_tree(i), {"tree_" + k: v for k, v in t.serialise().items()})
+    # a second launch continues the same trees (fit() twice): the statistics of 2 x n_sim simulations
+    eng.run(n_sim)
+    na2, _ = eng.root_stats()
+    ena2, _, _ = coracle.run_many(cfg, roots, 2 * n_sim, n_threads=8)
+    np.testing.assert_array_equal(na2.cpu().numpy(), ena2)
 
 
 @pytest.mark.gpu
