@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libisla_b200.so")
-SOURCES = ["isla_capi.cu", "isla_tree_tpt.cu", "isla_tree_flow.cu", "isla_tree_cta.cu", "isla_rollout.cu"]
+SOURCES = ["isla_capi.cu", "isla_tree_tpt.cu", "isla_tree_cta.cu", "isla_rollout.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

@@ -68,7 +68,6 @@ struct TptParams {
     const double* noise;       // slippery FrozenLake: noise[k] of the k-th env.step of a simulation, nullptr = deterministic
     int noise_n;
     int tpw;                   // trees owned by one warp (its first tpw lanes)
-    int tpc;                   // worker / owner kernel (isla_tree_flow.cu): trees owned by one CTA
 };
 
 }  // namespace isla
@@ -109,6 +108,5 @@ int cta_root_children(isla_engine* e, long long tree, int cap, double* action, i
                       cudaStream_t st);
 void cta_pool_offsets(const isla_engine* e, long long out[24]);
 int cta_depth_stats(isla_engine* e, long long tree, int cap, int32_t* dmax, double* dmean, int32_t* count, cudaStream_t st);
-int tpt_flow_launch(TptParams& p, bool f64, int sm_count, int tuning, cudaStream_t st);   // isla_tree_flow.cu
 int tpt_depth_stats(isla_engine* e, long long tree, int cap, int32_t* dmax, double* dmean, int32_t* count, cudaStream_t st);
 }  // namespace isla

@@ -16,9 +16,9 @@ for item in spec:
         if sh == "auto":
             tuning = 0
         else:
-            flow = sh.startswith("f")
+            flow = False
             tpc, _, w = sh.lstrip("f").partition("x")
-            tuning = (4 if flow else 8) | (int(tpc or 0) << 8) | (int(w or 0) << 16)
+            tuning = (int(tpc or 0) << 8) | (int(w or 0) << 16)
         eng = Engine(0, n_trees=nt, sim_capacity=1000, max_depth=500, gamma=0.99, kernel=1, seed=1, tuning=tuning)
         eng.set_roots(roots).run(1000); torch.cuda.synchronize()
         best = 1e9
