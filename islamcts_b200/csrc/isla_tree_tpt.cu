@@ -896,8 +896,6 @@ int launch_search(TptParams& p, bool scripted, int sm_count, int tpw_forced, cud
 
 }  // namespace
 
-constexpr long long kFlowMaxTrees = 0;   // (set from the A/B measurement)
-
 // bytes of one tree's PV chunks
 static long long tpt_pv_stride(long long blocks, int A) {
     return (blocks + 31) / 32 * (A == 2 ? PvChunk<2>::kBytes : PvChunk<4>::kBytes);
@@ -976,11 +974,6 @@ int tpt_run(isla_engine* e, int n_sim, long long scripted_tree, const uint8_t* k
     p.tuning = e->cfg.tuning;
     const bool scripted = scripted_tree >= 0;
     const bool f64 = e->cfg.precision == ISLA_PRECISION_F64;
-    // Batches that cannot give every resident warp a worthwhile number of trees run on the worker / owner kernel
-    // (isla_tree_flow.cu; measured cross-over: profiles/README.md).  tuning bit 4 forces it, bit 8 forbids it.
-    if (e->cfg.env_id == ISLA_ENV_CARTPOLE && !scripted &&
-        ((e->cfg.tuning & 4) || (!(e->cfg.tuning & 8) && e->cfg.n_trees <= kFlowMaxTrees)))
-        return tpt_flow_launch(p, f64, e->sm_count, e->cfg.tuning, st);
     switch (e->cfg.env_id) {
     case ISLA_ENV_CARTPOLE:
         return f64 ? launch_search<ENV_CARTPOLE, double>(p, scripted, e->sm_count, tpw_forced, st)

@@ -1,5 +1,5 @@
-// Data layout and small device helpers shared by the two thread-per-tree search kernels (isla_tree_tpt.cu: lock-step
-// warps; isla_tree_flow.cu: worker / owner warps): node blocks, the PV cache chunks, the cooperative ring, cp.async.
+// Data layout and small device helpers of the thread-per-tree search kernel (isla_tree_tpt.cu; kept in a header since the
+// worker / owner A/B variant of round 2 shared them): node blocks, the PV cache chunks, the cooperative ring, cp.async.
 #pragma once
 #include <cmath>
 #include <cstring>

@@ -1,2 +1,3 @@
-timeout 600 python -m pytest tests/test_gpu_tree_vanilla.py -x -q -m gpu 2>&1 | tail -3
-timeout 900 python profiles/experiments/r2_sweep.py 1:0 256:0 4096:0 8192:0 16384:0 32768:0 65536:0
+ISLA_LIB_PATH=profiles/experiments/lib_pt.so timeout 600 python profiles/experiments/r2_sweep.py 8192:0 2>&1 | grep -v "^trees" | sort | uniq -c | sort -rn | head -0
+ISLA_LIB_PATH=profiles/experiments/lib_pt.so timeout 600 python profiles/experiments/r2_sweep.py 8192:0 2>&1 | tail -8
+ISLA_LIB_PATH=profiles/experiments/lib_pt.so timeout 600 python profiles/experiments/r2_sweep.py 65536:0 2>&1 | tail -5
