@@ -810,7 +810,185 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
     unsigned long long my_steps = 0;  // rollout env steps played by THIS thread
     int prev_levels = 0;              // recorded path entries of the previous simulation (warp 0, replicated)
 
+    // Widening wave (APW with random expansion, one rollout per leaf).  Whether a simulation widens the ROOT depends on
+    // counts only -- len(actions) <= ceil(k * ns**alpha), mcts_action_progressive_widening_hash.py:62 -- and a simulation
+    // that widens the root is: sample an action (tree stream, one draw), step the root state, create the child, roll out,
+    // back the return up into the new action node, the new state node and the root.  Consecutive such simulations touch
+    // disjoint nodes and consume consecutive draws, so a run of them is executed by the whole CTA at once, one thread per
+    // simulation, and applied in simulation order: node indices, stream positions, the root's running total (added in
+    // order by one lane) and every statistic are exactly those of the serial loop.  The run ends before the first
+    // simulation that would not widen, whose sampled action already exists (the reference then re-uses that node and
+    // descends), or whose first step terminates; those take the serial path.  BASELINE config C3 (k = 60, alpha = 0.8)
+    // widens the root on every one of its 10 000 simulations.
+    const bool wave_ok = !SCRIPTED && p.agent == ISLA_AGENT_APW && p.expansion == ISLA_EXPAND_RANDOM && R == 1 && CS == 1 &&
+                         p.hash_cap > 0 && nt >= 64;
+    __shared__ int wv_n, wv_ns0, wv_n0, wv_nS0, wv_nA0, wv_itop, wv_rng0, wv_bad, wv_off, wv_cap;
+    __shared__ unsigned wv_sims0;
+    constexpr int kWaveWords = ENV == ENV_CURVE ? 2 : 1;   // stream words per sampled action
+
     for (int sim = 0; sim < p.n_sim; ++sim) {
+        if (wave_ok) {
+            Pool& q = ctx.q;
+            if (tid == 0) {
+                int W = 0;
+                if (!ctx.fault) {
+                    const int ns0 = q.s_ns[0], n0 = q.s_ccnt[0];
+                    auto widens = [&](int ns_, int n_) {
+                        const double cap = ns_ < p.ln_count ? p.pw1_table[ns_] : ceil(__dmul_rn(p.k1, pow((double)ns_, p.alpha1)));
+                        return n_ == 0 || (double)n_ <= cap;
+                    };
+                    if (widens(ns0, n0) && widens(ns0 + 1, n0 + 1)) {
+                        long long w = nt;
+                        w = min(w, (long long)(p.n_sim - sim));
+                        w = min(w, p.s_cap - ctx.nS);
+                        w = min(w, p.a_cap - ctx.nA);
+                        W = (int)max(w, 0ll);
+                    }
+                    wv_ns0 = ns0; wv_n0 = n0; wv_nS0 = ctx.nS; wv_nA0 = ctx.nA; wv_itop = ctx.itop;
+                    wv_rng0 = (int)ctx.ts.consumed(); wv_sims0 = sims_done;
+                }
+                wv_n = W; wv_bad = W;
+            }
+            __syncthreads();
+            const int W = wv_n;
+            if (W >= 2) {
+                double* const w_val = red;              // [W] sampled action (first coordinate)
+                double* const w_val2 = red + 512;       // [W] second coordinate (CurveEnv box)
+                double* const w_g = red + 1024;         // [W] return backed up by simulation i
+                const int ns0 = wv_ns0, n0 = wv_n0;
+                double val = 0.0, val2 = 0.0, r0 = 0.0;
+                T st[S];
+                bool bad = false;
+                if (tid < W) {
+                    const int ns_i = ns0 + tid, n_i = n0 + tid;
+                    const double cap = ns_i < p.ln_count ? p.pw1_table[ns_i] : ceil(__dmul_rn(p.k1, pow((double)ns_i, p.alpha1)));
+                    bad = !(n_i == 0 || (double)n_i <= cap);
+                    // env.action_space.sample() of simulation i: draw number rng0 + i (x kWaveWords) of the tree stream
+                    Stream as;
+                    as.resume(p.seed, 0u, tree_id, kStreamTree, (uint32_t)(wv_rng0 + tid * kWaveWords));
+                    if constexpr (ENV == ENV_CURVE) {
+                        val = __dadd_rn(-5.0, __dmul_rn(10.0, u32_to_d01(as.next())));
+                        val2 = __dadd_rn(-30.0, __dmul_rn(60.0, u32_to_d01(as.next())));
+                    } else {
+                        float lo, hi; env_action_bounds(ENV, lo, hi);
+                        val = (double)box_sample_f32(as.next(), lo, hi);
+                    }
+                    w_val[tid] = val; w_val2[tid] = val2;
+                    // first step from the root state
+                    const T* sp = ctx.state_ptr(0);
+#pragma unroll
+                    for (int i = 0; i < S; ++i) st[i] = sp[i];
+                    T rT;
+                    const bool term = env_step_action<ENV, T>(st, val, val2, p.grid, rT);
+                    r0 = (double)rT;
+                    bad |= term;
+                    // the action already exists at the root (the reference re-uses the node)?  -- per-thread probe
+                    if (!bad) {
+                        const long long want = ctx.key_bits(val, val2);
+                        unsigned long long h = ctx.hash_slot(0, want);
+                        for (;;) {
+                            const int4 e = reinterpret_cast<const int4*>(ctx.hash)[h];
+                            if (e.z < 0) break;
+                            if (e.z == 0 && e.x == (int)(unsigned)(want & 0xffffffffll) && e.y == (int)(want >> 32) && ctx.confirm(0, e.w, val, val2)) { bad = true; break; }
+                            h = (h + 1) & (unsigned long long)(p.hash_cap - 1);
+                        }
+                    }
+                }
+                __syncthreads();
+                if (tid < W && !bad) {   // ... or is sampled twice within the run?
+                    const long long b0 = __double_as_longlong(val), b1 = __double_as_longlong(val2);
+                    for (int j = 0; j < tid; ++j)
+                        if (__double_as_longlong(w_val[j]) == b0 && __double_as_longlong(w_val2[j]) == b1) { bad = true; break; }
+                }
+                if (tid < W && bad) atomicMin(&wv_bad, tid);
+                __syncthreads();
+                const int We = wv_bad;   // simulations sim .. sim + We - 1 widen the root with fresh actions
+                if (We >= 2) {
+                    const int nS0 = wv_nS0, nA0 = wv_nA0;
+                    // the root's child-index array grows once (insertion order preserved)
+                    if (tid == 0) {
+                        int off = q.s_coff[0], cap = q.s_ccap[0];
+                        int ncap = cap;
+                        while (ncap < n0 + We) ncap = ncap == 0 ? 4 : ncap * 2;
+                        wv_off = off; wv_cap = cap;
+                        if (ncap != cap) {
+                            if (wv_itop + ncap > p.i_cap) { wv_cap = -1; }
+                            else { wv_off = wv_itop; wv_itop += ncap; wv_cap = -ncap - 2; }   // negative: moved, copy the old entries
+                        }
+                    }
+                    __syncthreads();
+                    if (wv_cap == -1) {
+                        if (leader) ctx.fault = ISLA_ERR_CAPACITY;
+                    } else {
+                        const int new_off = wv_off;
+                        if (wv_cap < -1) {
+                            const int old_off = q.s_coff[0];
+                            for (int i = tid; i < n0; i += nt) q.ipool[new_off + i] = q.ipool[old_off + i];
+                        }
+                        if (tid < We) {
+                            // simulation i: rollout from the new child (own Philox stream: cumulative simulation index)
+                            const int budget = p.budget_mode == ISLA_BUDGET_ZERO ? 0 : max(0, min(p.max_depth - 1, p.disc_count));
+                            T ss[S];
+#pragma unroll
+                            for (int i = 0; i < S; ++i) ss[i] = st[i];
+                            Stream rs;
+                            rs.init(p.seed, wv_sims0 + (unsigned)tid, tree_id, 0u);
+                            int t = 0; bool done = false;
+                            T rr = T(0);
+                            double Rr = 0.0;
+                            while (!done && t < budget) {
+                                done = rollout_step<ENV, T>(rs, ss, p.grid, rr, p.heur, p.noise, 0);
+                                if constexpr (!Rewards<ENV>::kClosedForm) Rr = __dadd_rn(Rr, __dmul_rn((double)rr, __ldg(p.disc_table + t)));
+                                ++t;
+                            }
+                            if constexpr (Rewards<ENV>::kClosedForm) Rr = Rewards<ENV>::rollout_return(t, (double)rr, p.disc_table, p.cum_table);
+                            my_steps += t;
+                            const double G = __dadd_rn(r0, __dmul_rn(p.gamma, Rr));
+                            w_g[tid] = G;
+                            // the new action node and its state node, as the serial expansion + backup leave them
+                            const int a = nA0 + tid, c = nS0 + tid;
+                            q.a_total[a] = G; q.a_value[a] = val; q.a_na[a] = 1; q.a_visits[a] = 1; q.a_child[a] = c;
+                            if (p.action_dim == 2) q.a_value2[a] = val2;
+                            q.s_total[c] = G; q.s_term_reward[c] = 0.0; q.s_ns[c] = 1; q.s_flags[c] = 0;
+                            q.s_coff[c] = 0; q.s_ccap[c] = 0; q.s_ccnt[c] = 0;
+                            T* d = ctx.state_ptr(c);
+#pragma unroll
+                            for (int i = 0; i < S; ++i) d[i] = st[i];
+                            q.ipool[new_off + n0 + tid] = a;
+                            // action hash set: claim an empty slot (all keys of the run are distinct and new)
+                            const long long bits = ctx.key_bits(val, val2);
+                            unsigned long long h = ctx.hash_slot(0, bits);
+                            int4* const tab = reinterpret_cast<int4*>(ctx.hash);
+                            for (;;) {
+                                if (atomicCAS(&tab[h].z, -1, 0) == -1) {
+                                    tab[h].x = (int)(unsigned)(bits & 0xffffffffll); tab[h].y = (int)(bits >> 32); tab[h].w = n0 + tid;
+                                    break;
+                                }
+                                h = (h + 1) & (unsigned long long)(p.hash_cap - 1);
+                            }
+                        }
+                        __syncthreads();
+                        if (tid == 0) {
+                            // the root, in simulation order: ns += 1, total += G (mcts_action_...:80-84)
+                            double tot = q.s_total[0];
+                            for (int i = 0; i < We; ++i) tot = __dadd_rn(tot, w_g[i]);
+                            q.s_total[0] = tot; q.s_ns[0] = ns0 + We; q.s_ccnt[0] = n0 + We;
+                            if (wv_cap < -1) { q.s_coff[0] = new_off; q.s_ccap[0] = -wv_cap - 2; }
+                        }
+                        if (leader) {
+                            ctx.nS = nS0 + We; ctx.nA = nA0 + We; ctx.itop = wv_itop;
+                            ctx.ts.resume(p.seed, 0u, tree_id, kStreamTree, (uint32_t)(wv_rng0 + We * kWaveWords));
+                            ctx.c_env += We; ctx.c_levels += We; ctx.c_nodes += We;
+                        }
+                        sims_done += We; s_done += We;
+                        prev_levels = 1;
+                        sim += We - 1;
+                    }
+                    __syncthreads();
+                    if (wv_cap != -1) continue;
+                }
+            }
+        }
         // ------------------------------------------------------------ warp 0: descent to the leaf
         int level = 0;           // number of recorded path entries
         bool need_roll = false;  // the leaf is a fresh non-terminal state: roll out from it
@@ -1430,6 +1608,9 @@ int pick_threads(const isla_config& cfg) {
         nt = 32;
         while (nt < R && nt < 512) nt <<= 1;
         if (cfg.expansion == ISLA_EXPAND_VOO) nt = 512;   // voo's rejection tries are evaluated CTA-wide
+        // apw with random expansion and one rollout per leaf: runs of root-widening simulations are played one thread per
+        // simulation (the widening wave of cta_search_kernel); worth a wide CTA while the trees do not fill the GPU anyway
+        if (cfg.agent == ISLA_AGENT_APW && cfg.expansion == ISLA_EXPAND_RANDOM && R == 1 && cfg.n_trees <= 296) nt = 512;
     }
     nt = (nt + 31) / 32 * 32;
     return nt > 512 ? 512 : nt;
