@@ -499,6 +499,11 @@ def other_configs(dev):
     t0 = _t.perf_counter(); res = eb.run(st0); dt = _t.perf_counter() - t0
     out["episodes_cartpole_100_lockstep"] = {"real_steps": res["real_steps"], "seconds": dt, "real_steps_per_s": res["real_steps"] / dt,
                                              "sims_per_s": res["real_steps"] * 1000 / dt, "mean_steps": float(res["n_steps"].mean())}
+    # Agent(param).fit() wall latency through the drop-in classes, a NEW agent per fit as the reference's episode loop builds
+    # one per real step (sweep.py:186): host work (env identification, engine from the pool, re-key, reset), the search
+    # launch, the arg-max epilogue and the read-back of the action and root statistics.  `without_engine_pool` re-creates
+    # the device engine for every agent (what round 1 did).
+    out["agent_fit_latency"] = agent_fit_latency(dev)
     # R: rollout micro-benchmark, 2^24 trajectories from the reset distribution, random policy, budget = max_depth
     flop = {0: 36, 1: 27, 2: 27, 3: 6}
     mufu = {0: 4, 1: 2, 2: 1, 3: 0}     # CartPole 1 sin + 1 cos + 2 div, Pendulum 1 sin + 1 mod, MountainCar 1 cos
@@ -518,6 +523,61 @@ def other_configs(dev):
                                                "unit": "TFLOP/s", "frac": total / t * flop[env_id] / peak_fp32,
                                                "mufu_frac": total / t * mufu[env_id] / peak_sfu}}
     return out
+
+
+def agent_fit_latency(dev):
+    import time as _t
+    import warnings
+    import torch
+    from islamcts_b200 import envs
+    from islamcts_b200.agents import Mcts, MctsApw, MctsDpw, MctsHash
+    from islamcts_b200.agents.abstract_mcts import clear_engine_pool
+    from islamcts_b200.agents.parameters.dpw_parameters import DpwParameters
+    from islamcts_b200.agents.parameters.mcts_parameters import MctsParameters
+    from islamcts_b200.agents.parameters.pw_parameters import PwParameters
+    from islamcts_b200.utils.action_selection_functions import continuous_default_policy, ucb1
+    warnings.simplefilter("ignore")
+
+    def common(env, obs, n_sim, C, gamma, max_depth, **kw):
+        return dict(root_data=obs, env=env, n_sim=n_sim, C=C, action_selection_fn=ucb1, gamma=gamma,
+                    rollout_selection_fn=continuous_default_policy, max_depth=max_depth,
+                    n_actions=getattr(env.action_space, "n", None), seed=1, device=str(dev), **kw)
+
+    cases = {
+        "c1_mcts_frozenlake_nsim100": ("FrozenLake-v1", lambda e, o: Mcts(MctsParameters(**common(e, o, 100, 0.5, 1.0, 1000)))),
+        "c2_mctshash_cartpole_nsim1000": ("CartPole-v1", lambda e, o: MctsHash(MctsParameters(**common(e, o, 1000, 1.0, 0.99, 500)))),
+        "c2_mctshash_cartpole_nsim1000_4096rollouts": ("CartPole-v1", lambda e, o: MctsHash(MctsParameters(
+            **common(e, o, 1000, 1.0, 0.99, 500, rollouts_per_leaf=4096)))),
+        "c3_mctsapw_pendulum_nsim10000": ("Pendulum-v1", lambda e, o: MctsApw(PwParameters(
+            **common(e, o, 10000, 1.0, 0.99, 200), alpha=0.8, k=60, action_expansion_function=continuous_default_policy))),
+        "c4_mctsdpw_mountaincar_nsim10000": ("MountainCarContinuous-v0", lambda e, o: MctsDpw(DpwParameters(
+            **common(e, o, 10000, 1.0, 0.99, 500), alphaApw=0.5, kApw=1, alphaSpw=0.5, kSpw=1))),
+    }
+    res = {}
+    for name, (env_name, make_agent) in cases.items():
+        env = envs.make(env_name, api=4, seed=3, device=str(dev))
+        obs = env.reset()
+
+        def one_fit():
+            ag = make_agent(env.unwrapped, obs)
+            ag.root.data = obs
+            return ag.fit()
+
+        reps = 3 if "nsim10000" in name and "dpw" in name else 8
+        entry = {}
+        for label, pooled in (("ms_per_fit", True), ("ms_per_fit_without_engine_pool", False)):
+            one_fit(); one_fit()
+            torch.cuda.synchronize(dev)
+            ts = []
+            for _ in range(reps):
+                if not pooled:
+                    clear_engine_pool()
+                t0 = _t.perf_counter(); one_fit(); ts.append(_t.perf_counter() - t0)
+            ts.sort()
+            entry[label] = 1e3 * ts[len(ts) // 2]
+        res[name] = entry
+    clear_engine_pool()
+    return res
 
 
 def main():

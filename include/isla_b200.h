@@ -180,9 +180,11 @@ int isla_engine_reseed(isla_engine* e, uint64_t seed, uint64_t tree_id_base);
 /* Real-step half of the episode loop (sweep.py:190,202-213) for n episodes at once, no host round trip: applies
  * actions_dev[n][action_dim] (ISLA_ENV_CURVE with a grid: the DiscreteCurveEnv index) to states_dev[n][state_dim] in
  * float64 for every episode with alive_dev[i] != 0, adds the reward to total_reward_dev[i], counts the step in
- * n_steps_dev[i] and clears alive_dev[i] when the env terminates or max_steps is reached; finished episodes are frozen. */
+ * n_steps_dev[i] and clears alive_dev[i] when the env terminates or max_steps is reached; finished episodes are frozen.
+ * timeout_reward: the reward booked for the step that reaches max_steps (the reference books -1000, sweep.py:206-209);
+ * NaN = the env's own reward. */
 int isla_episode_step(int32_t env_id, int32_t action_grid0, int32_t action_grid1, double* states_dev,
-                      const double* actions_dev, int64_t n, int32_t max_steps, uint8_t* alive_dev,
+                      const double* actions_dev, int64_t n, int32_t max_steps, double timeout_reward, uint8_t* alive_dev,
                       double* total_reward_dev, int32_t* n_steps_dev, void* stream);
 
 /* Device counters int64[8]: [0] env steps executed, [1] rollout steps, [2] tree levels visited,

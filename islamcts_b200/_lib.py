@@ -79,7 +79,7 @@ SYMBOLS = {
     "isla_engine_pool_offsets": (C.c_int, [_P, _P]),
     "isla_engine_counters": (C.c_int, [_P, _P, _P]),
     "isla_engine_reseed": (C.c_int, [_P, C.c_uint64, C.c_uint64]),
-    "isla_episode_step": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int64, C.c_int32, _P, _P, _P, _P]),
+    "isla_episode_step": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int64, C.c_int32, C.c_double, _P, _P, _P, _P]),
     "isla_merge_root_stats": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int64, _P, _P, _P]),
     "isla_engine_root_merge": (C.c_int, [_P, C.c_int64, _P, _P]),
     "isla_kernel_launches": (C.c_int64, []),

@@ -197,6 +197,56 @@ class _RootProxy(AbstractStateNode):
         return self._agent._full_root().total
 
 
+_DEPTH_MODE_WARNED = False
+
+
+def _warn_depth_mode_once(cls_name):
+    """Mcts / APW / SPW / DPW of the reference HEAD pass max_depth as the current depth and therefore play zero-length
+    rollouts; this package plays them to max_depth unless told otherwise."""
+    global _DEPTH_MODE_WARNED
+    if not _DEPTH_MODE_WARNED:
+        _DEPTH_MODE_WARNED = True
+        import warnings
+        warnings.warn(f"{cls_name}: depth_mode not given -> 'budgeted' (rollouts to max_depth).  The reference at HEAD plays "
+                      f"zero-length rollouts in this class; pass depth_mode='reference_head' (the default of the islaMcts "
+                      f"compat package) for HEAD-identical statistics.", stacklevel=4)
+
+
+# Engines are POOLED by configuration.  The reference's episode loop builds a new agent for every real step
+# (sweep.py:186, README.md:99-121); creating a device engine for each of them (workspace, host libm tables, the return
+# table, their uploads) cost more than the search itself (round 1: 27 ms per fit() for a 10 ms kernel).  An agent takes
+# a free engine of its configuration from the pool, re-keys it (new Philox seed) and resets the tree for its root; the
+# engine goes back to the pool when the agent is dropped.
+_ENGINE_POOL: dict = {}
+_ENGINE_POOL_MAX = 4   # free engines kept per configuration
+
+
+def _acquire_engine(env_id, capacity, kw):
+    key = (env_id, capacity, tuple(sorted((k, str(v)) for k, v in kw.items())))
+    free = _ENGINE_POOL.get(key)
+    if free:
+        return key, free.pop(), True
+    return key, None, False
+
+
+def _release_engine(key, eng):
+    if eng is None or key is None:
+        return
+    free = _ENGINE_POOL.setdefault(key, [])
+    if len(free) < _ENGINE_POOL_MAX:
+        free.append(eng)
+    else:
+        eng.close()
+
+
+def clear_engine_pool():
+    """Frees the pooled device engines (workspaces go back to the CUDA allocator)."""
+    for free in _ENGINE_POOL.values():
+        for e in free:
+            e.close()
+    _ENGINE_POOL.clear()
+
+
 class AbstractMcts:
     """Common driver.  Subclasses set AGENT (engine enum), HEAD_BUDGET (what the class does at reference HEAD)."""
 
@@ -213,6 +263,7 @@ class AbstractMcts:
         self.param.depths = []
         self._engine: Engine | None = None
         self._engine_key = None
+        self._pool_key = None
         self._root_proxy = None
         self._full_proxy = None
         self._root_stub = AbstractStateNode(param.root_data, param)
@@ -242,8 +293,10 @@ class AbstractMcts:
         if rk not in ("random", "grid"):
             raise NotImplementedError("rollout_selection_fn must be continuous_default_policy (env.action_space.sample()) "
                                       "or grid_policy(...)")
-        if p.depth_mode not in ("budgeted", "reference_head"):
+        if p.depth_mode not in (None, "budgeted", "reference_head"):
             raise ValueError("depth_mode must be 'budgeted' or 'reference_head'")
+        if p.depth_mode is None and self.HEAD_ZERO_ROLLOUTS:
+            _warn_depth_mode_once(type(self).__name__)
         zero = p.depth_mode == "reference_head" and self.HEAD_ZERO_ROLLOUTS
         kw = dict(agent=self.AGENT, n_trees=int(p.n_trees), max_depth=int(p.max_depth), C_=float(p.C), gamma=float(p.gamma),
                   budget_mode=_lib.BUDGET_ZERO if zero else _lib.BUDGET_TO_MAX_DEPTH,
@@ -266,22 +319,45 @@ class AbstractMcts:
     def _agent_kwargs(self, kw):
         pass
 
-    def _ensure_engine(self, env_id, root_state):
+    def _ensure_engine(self, env_id, root_state, noise=None):
         p = self.param
         kw = self._engine_kwargs(env_id)
-        key = (env_id, tuple(sorted((k, v) for k, v in kw.items())), tuple(root_state.tolist()))
+        # a tree is continued by the next fit() only from the same root under the same transition noise (slippery
+        # FrozenLake: the stored children were produced by the clone's draws as of the fit() that created them)
+        key = (env_id, tuple(sorted((k, v) for k, v in kw.items())), tuple(root_state.tolist()),
+               None if noise is None else noise.tobytes())
         if self._engine is not None and key == self._engine_key and self._sims_done + p.n_sim <= self._capacity:
             return                                     # fit() again continues the same tree
         if self._engine is not None and key == self._engine_key:
             raise _lib.IslaError(_lib.ERR_CAPACITY, "tree capacity exhausted; create a new agent")
         seed = p.seed if p.seed is not None else int(np.random.randint(0, 2**31 - 1))
         self._capacity = max(4 * int(p.n_sim), 64)
-        self._engine = Engine(env_id, sim_capacity=self._capacity, seed=seed, **kw)
+        self._drop_engine()
+        self._pool_key, eng, pooled = _acquire_engine(env_id, self._capacity, kw)
+        if pooled:
+            eng.reseed(seed, 0)
+        else:
+            eng = Engine(env_id, sim_capacity=self._capacity, seed=seed, **kw)
+        self._engine = eng
         if _kind(p.rollout_selection_fn, "rollout_selection_fn") == "grid":
-            self._engine.set_rollout_heuristic(p.rollout_selection_fn.table)
-        self._engine.set_roots(np.tile(root_state[None, :], (int(p.n_trees), 1)))
+            eng.set_rollout_heuristic(p.rollout_selection_fn.table)
+        elif pooled and env_id == _lib.ENV_FROZENLAKE:
+            eng.set_rollout_heuristic(None)
+        eng.set_roots(np.tile(root_state[None, :], (int(p.n_trees), 1)))
         self._engine_key = key
         self._sims_done = 0
+
+    def _drop_engine(self):
+        eng, self._engine = self._engine, None
+        if eng is not None:
+            _release_engine(self._pool_key, eng)
+        self._pool_key = None
+
+    def __del__(self):
+        try:
+            self._drop_engine()
+        except Exception:
+            pass
 
     # ------------------------------------------------------------------ fit
     def fit(self):
@@ -291,10 +367,13 @@ class AbstractMcts:
             raise ValueError("param.env is None")
         env_id = identify_env(p.env)
         root_state = env_root_state(p.env, env_id)
-        self._ensure_engine(env_id, root_state)
-        eng = self._engine
+        noise = None
         if env_id == _lib.ENV_FROZENLAKE:   # slippery lake: the clone's per-step draws, as of this fit()
-            eng.set_transition_noise(lake_transition_noise(p.env, max(int(p.max_depth), self._capacity) + 4))
+            noise = lake_transition_noise(p.env, max(int(p.max_depth), 4 * int(p.n_sim), 64) + 4)
+        self._ensure_engine(env_id, root_state, noise)
+        eng = self._engine
+        if env_id == _lib.ENV_FROZENLAKE:
+            eng.set_transition_noise(noise)
         eng.run(int(p.n_sim))
         self._sims_done += int(p.n_sim)
         self._root_proxy = None
@@ -316,11 +395,7 @@ class AbstractMcts:
         if eng.layout.kernel == _lib.KERNEL_CTA_PER_TREE:
             a, na, tot = eng.root_children(0)
         else:
-            na_t, tot_t = eng.root_stats()
-            order = eng.root_order(0)
-            a = np.array(order, dtype=np.float64)
-            na = np.array([int(na_t[0, k]) for k in order])
-            tot = np.array([float(tot_t[0, k]) for k in order])
+            a, na, tot = eng.root_edges(0)
         self.root_statistics = dict(action=a, na=na, total=tot)
         self.q_values = tot / na
 
@@ -375,11 +450,7 @@ class AbstractMcts:
         if eng.layout.kernel == _lib.KERNEL_CTA_PER_TREE:
             a, na, tot = eng.root_children(0)
         else:
-            na_t, tot_t = eng.root_stats()
-            order = eng.root_order(0)
-            a = np.array(order, dtype=np.float64)
-            na = np.array([int(na_t[0, k]) for k in order])
-            tot = np.array([float(tot_t[0, k]) for k in order])
+            a, na, tot = eng.root_edges(0)
         dmax, dmean = eng.depth_stats(0)
         actions = {}
         for i in range(len(na)):

@@ -38,8 +38,10 @@ class MctsParameters:
     state_variable: str | None = field(default=None, kw_only=True)
     # ---- build options of the B200 engine (not in the reference)
     # "budgeted": rollouts to max_depth with MctsHash's depth accounting (mcts_hash.py:34,116,126);
-    # "reference_head": the zero-length rollouts Mcts/APW/SPW/DPW perform at HEAD
-    depth_mode: str = field(default="budgeted", kw_only=True)
+    # "reference_head": the zero-length rollouts Mcts/APW/SPW/DPW perform at HEAD.
+    # None = "budgeted", with a one-time warning from the agents whose HEAD behaviour differs; the compat package
+    # ``islaMcts`` (code imported unchanged from the reference) defaults to "reference_head".
+    depth_mode: str | None = field(default=None, kw_only=True)
     rollouts_per_leaf: int = field(default=1, kw_only=True)   # leaf-parallel batch: mean of R rollouts, ONE visit
     n_trees: int = field(default=1, kw_only=True)             # root-parallel ensemble of independent trees
     seed: int | None = field(default=None, kw_only=True)      # Philox key; None = drawn from numpy's global RNG

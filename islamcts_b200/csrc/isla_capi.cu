@@ -271,11 +271,12 @@ int isla_engine_destroy(isla_engine* e) {
 
 int isla_engine_set_transition_noise(isla_engine* e, const double* u_host, int32_t n) {
     if (!e) { set_error("null engine"); return ISLA_ERR_INVALID; }
+    if (!u_host && !e->noise_dev) return ISLA_OK;          // deterministic lake, nothing to clear
     ISLA_CUDA_OK(cudaDeviceSynchronize());
-    if (e->noise_dev) { cudaFree(e->noise_dev); e->noise_dev = nullptr; e->noise_n = 0; }
+    if (e->noise_dev && (!u_host || n != e->noise_n)) { cudaFree(e->noise_dev); e->noise_dev = nullptr; e->noise_n = 0; }
     if (!u_host) return ISLA_OK;
     if (e->cfg.env_id != ISLA_ENV_FROZENLAKE || n < 1) { set_error("transition noise: FrozenLake (is_slippery=True) only, n >= 1"); return ISLA_ERR_INVALID; }
-    ISLA_CUDA_OK(cudaMalloc((void**)&e->noise_dev, (size_t)n * sizeof(double)));
+    if (!e->noise_dev) ISLA_CUDA_OK(cudaMalloc((void**)&e->noise_dev, (size_t)n * sizeof(double)));
     ISLA_CUDA_OK(cudaMemcpy(e->noise_dev, u_host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
     e->noise_n = n;
     return ISLA_OK;

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) rollout_kernel(const T* __restrict__ stat
 // real-step half of the episode loop: env.step(best action) for every live episode, float64, in place
 template <int ENV>
 __global__ void episode_step_kernel(double* __restrict__ states, const double* __restrict__ actions, long long n, ActionGrid grid,
-                                    int max_steps, uint8_t* __restrict__ alive, double* __restrict__ total_reward,
+                                    int max_steps, double timeout_reward, uint8_t* __restrict__ alive, double* __restrict__ total_reward,
                                     int32_t* __restrict__ n_steps) {
     constexpr int S = EnvTraits<ENV>::S;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,9 +152,11 @@ __global__ void episode_step_kernel(double* __restrict__ states, const double* _
     const bool term = env_step_action<ENV, double>(s, actions[i * AD], AD == 2 ? actions[i * AD + 1] : 0.0, grid, r);
 #pragma unroll
     for (int k = 0; k < S; ++k) states[i * S + k] = s[k];
-    total_reward[i] = __dadd_rn(total_reward[i], r);
     const int steps = n_steps[i] + 1;
     n_steps[i] = steps;
+    // the reference's sweep loop replaces the reward of the step that reaches the limit (sweep.py:206-209: reward = -1000)
+    if (steps >= max_steps && !isnan(timeout_reward)) r = timeout_reward;
+    total_reward[i] = __dadd_rn(total_reward[i], r);
     if (term || steps >= max_steps) alive[i] = 0;
 }
 
@@ -253,7 +255,7 @@ extern "C" int isla_env_step(int32_t env_id, int32_t precision, const void* stat
 }
 
 extern "C" int isla_episode_step(int32_t env_id, int32_t action_grid0, int32_t action_grid1, double* states_dev,
-                                 const double* actions_dev, int64_t n, int32_t max_steps, uint8_t* alive_dev,
+                                 const double* actions_dev, int64_t n, int32_t max_steps, double timeout_reward, uint8_t* alive_dev,
                                  double* total_reward_dev, int32_t* n_steps_dev, void* stream) {
     using namespace isla;
     if (n <= 0) return ISLA_OK;
@@ -268,11 +270,11 @@ extern "C" int isla_episode_step(int32_t env_id, int32_t action_grid0, int32_t a
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = (unsigned)((n + 127) / 128);
     switch (env_id) {
-    case ENV_CARTPOLE: episode_step_kernel<ENV_CARTPOLE><<<grid, 128, 0, st>>>(states_dev, actions_dev, n, ag, max_steps, alive_dev, total_reward_dev, n_steps_dev); break;
-    case ENV_PENDULUM: episode_step_kernel<ENV_PENDULUM><<<grid, 128, 0, st>>>(states_dev, actions_dev, n, ag, max_steps, alive_dev, total_reward_dev, n_steps_dev); break;
-    case ENV_MOUNTAINCAR: episode_step_kernel<ENV_MOUNTAINCAR><<<grid, 128, 0, st>>>(states_dev, actions_dev, n, ag, max_steps, alive_dev, total_reward_dev, n_steps_dev); break;
-    case ENV_FROZENLAKE: episode_step_kernel<ENV_FROZENLAKE><<<grid, 128, 0, st>>>(states_dev, actions_dev, n, ag, max_steps, alive_dev, total_reward_dev, n_steps_dev); break;
-    case ENV_CURVE: episode_step_kernel<ENV_CURVE><<<grid, 128, 0, st>>>(states_dev, actions_dev, n, ag, max_steps, alive_dev, total_reward_dev, n_steps_dev); break;
+    case ENV_CARTPOLE: episode_step_kernel<ENV_CARTPOLE><<<grid, 128, 0, st>>>(states_dev, actions_dev, n, ag, max_steps, timeout_reward, alive_dev, total_reward_dev, n_steps_dev); break;
+    case ENV_PENDULUM: episode_step_kernel<ENV_PENDULUM><<<grid, 128, 0, st>>>(states_dev, actions_dev, n, ag, max_steps, timeout_reward, alive_dev, total_reward_dev, n_steps_dev); break;
+    case ENV_MOUNTAINCAR: episode_step_kernel<ENV_MOUNTAINCAR><<<grid, 128, 0, st>>>(states_dev, actions_dev, n, ag, max_steps, timeout_reward, alive_dev, total_reward_dev, n_steps_dev); break;
+    case ENV_FROZENLAKE: episode_step_kernel<ENV_FROZENLAKE><<<grid, 128, 0, st>>>(states_dev, actions_dev, n, ag, max_steps, timeout_reward, alive_dev, total_reward_dev, n_steps_dev); break;
+    case ENV_CURVE: episode_step_kernel<ENV_CURVE><<<grid, 128, 0, st>>>(states_dev, actions_dev, n, ag, max_steps, timeout_reward, alive_dev, total_reward_dev, n_steps_dev); break;
     default: set_error("unknown env %d", env_id); return ISLA_ERR_INVALID;
     }
     ISLA_CUDA_OK(cudaGetLastError());

@@ -241,6 +241,17 @@ class Engine:
         L = self.layout
         return self._ws_bytes(L.gfirst_offset + tree * L.gfirst_stride, L.gfirst_stride).view(np.float64)
 
+    def root_edges(self, tree: int = 0):
+        """(action, na, total) numpy arrays of a thread-per-tree tree's visited root edges in root.actions (insertion)
+        order: one small device->host copy of the root's node block."""
+        L = self.layout
+        A = self.n_actions
+        b = self._ws_bytes(L.rec_offset + tree * L.rec_stride + A * 16, A * 16).view(_block_dtype(A))[0]
+        order = sorted((int(b["link"][k] >> LINK_RANK_SHIFT), k) for k in range(A) if b["na"][k] > 0)
+        ks = [k for _, k in order]
+        return (np.array(ks, dtype=np.float64), np.array([int(b["na"][k]) for k in ks], dtype=np.int64),
+                np.array([float(b["total"][k]) for k in ks], dtype=np.float64))
+
     def root_order(self, tree: int = 0):
         """Visited root actions of a thread-per-tree tree in insertion order (root.actions order)."""
         b = self.raw_blocks(tree)[1]

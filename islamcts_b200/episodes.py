@@ -21,11 +21,14 @@ from ._lib import check
 
 class EpisodeBatch:
     def __init__(self, env: str | int, agent: int = _lib.AGENT_VANILLA, n_episodes: int = 100, n_sim: int = 1000,
-                 max_steps: int = 100, seed: int = 0, device="cuda:0", action_grid=None, **engine_kwargs):
+                 max_steps: int = 100, seed: int = 0, device="cuda:0", action_grid=None, timeout_reward: float | None = -1000.0,
+                 **engine_kwargs):
         self.env_id = E.ENV_NAMES[env] if isinstance(env, str) else int(env)
         self.device = torch.device(device)
         self.n, self.n_sim, self.max_steps, self.seed = int(n_episodes), int(n_sim), int(max_steps), int(seed)
         self.grid = tuple(int(x) for x in action_grid) if action_grid else (0, 0)
+        # the reference's loop books reward = -1000 for the step that reaches the limit (sweep.py:206-209); None = env reward
+        self.timeout_reward = float("nan") if timeout_reward is None else float(timeout_reward)
         self.engine = E.Engine(self.env_id, agent=agent, n_trees=self.n, sim_capacity=self.n_sim, seed=seed, device=device,
                                action_grid=action_grid, **engine_kwargs)
         self.S = E.STATE_DIM[self.env_id]
@@ -47,7 +50,7 @@ class EpisodeBatch:
             actions.append(act)
             with torch.cuda.device(dev):
                 check(lib.isla_episode_step(self.env_id, self.grid[0], self.grid[1], C.c_void_p(states.data_ptr()),
-                                            C.c_void_p(act.data_ptr()), self.n, self.max_steps, C.c_void_p(alive.data_ptr()),
+                                            C.c_void_p(act.data_ptr()), self.n, self.max_steps, self.timeout_reward, C.c_void_p(alive.data_ptr()),
                                             C.c_void_p(total.data_ptr()), C.c_void_p(steps.data_ptr()),
                                             C.c_void_p(E._stream_ptr(dev))))
             if (k + 1) % check_every == 0 and not bool(alive.any().item()):

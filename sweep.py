@@ -14,7 +14,10 @@ import numpy as np
 
 def argument_parser():
     p = argparse.ArgumentParser(formatter_class=argparse.ArgumentDefaultsHelpFormatter)
-    p.add_argument('--environment', default="CartPole-v1", type=str, help='The environment to run')
+    p.add_argument('--environment', default=None, type=str,
+                   help='The environment to run: a gym id, "CurveEnv" or "DiscreteCurveEnv".  Default (like the reference, which '
+                        'parses this flag, ignores it and always builds its CurveEnv, sweep.py:22,175): CurveEnv, or DiscreteCurveEnv '
+                        'for the discrete-action algorithms (sweep_vanilla.py:177)')
     p.add_argument('--algorithm', default="vanilla", type=str, help='The algorithm to run')
     p.add_argument('--nsim', default=1000, type=int, help='The number of simulation the algorithm will run')
     p.add_argument('--c', default=1, type=float, help='exploration-exploitation factor')
@@ -42,6 +45,8 @@ def argument_parser():
     p.add_argument('--depth_mode', default="budgeted", choices=["budgeted", "reference_head"])
     p.add_argument('--precision', default="f32", choices=["f32", "f64"])
     p.add_argument('--max_steps', default=100, type=int, help='real steps per episode (the reference stops at 100, sweep.py:206)')
+    p.add_argument('--timeout_reward', default=-1000.0, type=float,
+                   help='reward booked for the step that reaches --max_steps (the reference: -1000, sweep.py:206-209)')
     p.add_argument('--lockstep', action='store_true',
                    help='advance all --n_episodes episodes together on the device (islamcts_b200.episodes.EpisodeBatch)')
     return p
@@ -129,7 +134,7 @@ def run_lockstep(args):
         states = np.stack(rows)
     t0 = time.time()
     out = EpisodeBatch(env_id, agent=agent, n_episodes=n, n_sim=args["nsim"], max_steps=args["max_steps"], seed=seed,
-                       action_grid=grid, **kw).run(states)
+                       action_grid=grid, timeout_reward=args["timeout_reward"], **kw).run(states)
     dt = time.time() - t0
     print(json.dumps({"episodes": n, "real_steps": out["real_steps"], "seconds": dt, "real_steps_per_s": out["real_steps"] / dt,
                       "mean_reward": float(out["total_reward"].mean()), "max_reward": float(out["total_reward"].max()),
@@ -138,6 +143,8 @@ def run_lockstep(args):
 
 def main(argv=None):
     args = argument_parser().parse_args(argv).__dict__
+    if args["environment"] is None:
+        args["environment"] = "DiscreteCurveEnv" if args["algorithm"] in ("vanilla", "spw") else "CurveEnv"
     if args["lockstep"]:
         return run_lockstep(args)
     from islamcts_b200 import envs
@@ -160,8 +167,10 @@ def main(argv=None):
             agent.root.data = observation
             action = agent.fit()
             observation, reward, done, _ = env.step(action)
-            total_reward += reward
             n_steps += 1
+            if n_steps >= args["max_steps"]:
+                reward = args["timeout_reward"]          # sweep.py:206-209: the step that reaches the limit books -1000
+            total_reward += reward
         rewards.append(total_reward)
         print(json.dumps({"episode": ep, "total_reward": total_reward, "n_steps": n_steps, "seconds": time.time() - t0,
                           "n_actions": len(agent.q_values)}), flush=True)

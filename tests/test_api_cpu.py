@@ -99,7 +99,16 @@ def test_compat_package_paths():
     from islaMcts.agents.parameters.mcts_parameters import MctsParameters as P2
     from islaMcts.utils.action_selection_functions import ucb1 as u2
     import islamcts_b200.agents.mcts_hash as real
-    assert MctsHash is real.MctsHash and P2 is MctsParameters and u2 is ucb1
+    assert MctsHash is real.MctsHash and u2 is ucb1
+    # the compat parameter records ARE the package's records, except that code imported unchanged from the reference gets the
+    # reference's HEAD semantics (zero-length rollouts in Mcts / APW / SPW / DPW) unless it says otherwise
+    assert issubclass(P2, MctsParameters)
+    kw = dict(root_data=None, env=None, n_sim=1, C=1, action_selection_fn=ucb1, gamma=1.0, rollout_selection_fn=None, max_depth=1, n_actions=2)
+    assert P2(**kw).depth_mode == "reference_head" and MctsParameters(**kw).depth_mode is None
+    from islaMcts.agents.parameters.pw_parameters import PwParameters as Pw2
+    from islaMcts.agents.parameters.dpw_parameters import DpwParameters as Dpw2
+    assert Pw2(**kw, alpha=0.5, k=1, action_expansion_function=None).depth_mode == "reference_head"
+    assert Dpw2(**kw, alphaApw=0.5, kApw=1, alphaSpw=0.5, kSpw=1).depth_mode == "reference_head"
 
 
 def test_curve_env_host_mirror_without_gpu():

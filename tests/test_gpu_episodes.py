@@ -7,7 +7,7 @@ from oracle import coracle
 pytestmark = pytest.mark.gpu
 
 
-def _oracle_episodes(env_id, agent, states, n_sim, max_steps, seed, grid=(0, 0), **cfg_kw):
+def _oracle_episodes(env_id, agent, states, n_sim, max_steps, seed, grid=(0, 0), timeout_reward=-1000.0, **cfg_kw):
     n = len(states)
     total, steps = np.zeros(n), np.zeros(n, np.int32)
     states = np.array(states, dtype=np.float64)
@@ -21,8 +21,10 @@ def _oracle_episodes(env_id, agent, states, n_sim, max_steps, seed, grid=(0, 0),
             if grid[0]:   # DiscreteCurveEnv index -> (acceleration, steering)
                 a = [np.linspace(-5, 5, grid[0])[int(act) // grid[1]], np.linspace(-30, 30, grid[1])[int(act) % grid[1]]]
             s, r, term, _ = coracle.env_step(env_id, s, a if env_id == 4 else act)
-            total[e] += r
             steps[e] += 1
+            if steps[e] >= max_steps and timeout_reward is not None:
+                r = timeout_reward                      # sweep.py:206-209 of the reference
+            total[e] += r
             if term:
                 break
         states[e] = s
