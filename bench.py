@@ -456,6 +456,14 @@ def other_configs(dev):
     engz = Engine(_lib.ENV_MOUNTAINCAR, agent=_lib.AGENT_DPW, n_trees=1, sim_capacity=10000, max_depth=500, C_=1.0, gamma=0.99,
                   alpha1=0.5, k1=1.0, alpha2=0.5, k2=1.0, kernel=_lib.KERNEL_CTA_PER_TREE, budget_mode=_lib.BUDGET_ZERO, seed=1, device=dev)
     tz = timeit(lambda: engz.set_roots(roots).run(10000), reps=2)
+    # the same search with 64 simulations in flight (opt-in tree-parallel mode, virtual loss): a different search, statistics
+    # compared in tests/test_gpu_tree_cta.py::test_tree_parallel_virtual_loss_statistics
+    engp = Engine(_lib.ENV_MOUNTAINCAR, agent=_lib.AGENT_DPW, n_trees=1, sim_capacity=10000, max_depth=500, C_=1.0, gamma=0.99,
+                  alpha1=0.5, k1=1.0, alpha2=0.5, k2=1.0, kernel=_lib.KERNEL_CTA_PER_TREE, seed=1, device=dev, tree_parallel=64, virtual_value=-5.0)
+    tp_ = timeit(lambda: engp.set_roots(roots).run(10000), reps=2)
+    cp_ = engp.counters()
+    out["c4_dpw_mountaincar_1tree_tree_parallel64"] = {"sims_per_s": 10000 / tp_, "env_steps_per_s": cp_["env_steps"] / tp_, "ms": tp_ * 1e3}
+    del engp
     out["c4_dpw_mountaincar_1tree_reference_head"] = {"sims_per_s": 10000 / tz, "ms": tz * 1e3, "cpu_reference": ref_cpu("c4")}
     del engz
     # CurveEnv (the env sweep.py / sweep_vanilla.py / examples/example_curve.py of the reference actually run), from an

@@ -71,7 +71,10 @@ typedef struct {
     int32_t action_grid1;       /*   (curve_env.py:184-199; n_actions = g0*g1 <= 128); both 0 = the continuous 2-D CurveEnv box */
     int32_t cluster_ctas;       /* CTA-per-tree kernel: thread blocks (one thread-block cluster) that share one tree's leaf-parallel
                                  * rollouts; 0 = auto (up to 8 when rollouts_per_leaf > 512), else 1, 2, 4 or 8 */
-    int32_t reserved1;
+    int32_t tree_parallel;      /* build extension, CTA-per-tree kernel: > 1 = that many simulations of ONE tree in flight at once
+                                 * (virtual loss: each descent provisionally credits its leaf with virtual_value, the rollouts of
+                                 * the batch run concurrently, the credits are then corrected in order); 0 / 1 = the reference's
+                                 * sequential loop (agents/mcts_hash.py:30-34).  Statistics differ from the sequential search. */
     double C;                   /* param.C */
     double gamma;               /* param.gamma */
     double alpha1, k1;          /* PwParameters.alpha/k ; DpwParameters.alphaApw/kApw */
@@ -80,6 +83,7 @@ typedef struct {
     uint64_t seed;              /* Philox key */
     uint64_t tree_id_base;      /* global id of tree 0 of this engine (rank offset under sharding) */
     int64_t n_trees;            /* independent trees held by this engine */
+    double virtual_value;       /* tree_parallel > 1: the rollout return a leaf is credited with until its real rollouts arrive */
 } isla_config;
 
 typedef struct isla_engine isla_engine;

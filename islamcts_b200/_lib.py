@@ -35,10 +35,10 @@ class IslaConfig(C.Structure):
         ("budget_mode", C.c_int32), ("rollouts_per_leaf", C.c_int32), ("expansion", C.c_int32),
         ("voo_n_samples", C.c_int32), ("voo_max_try", C.c_int32), ("precision", C.c_int32),
         ("kernel", C.c_int32), ("block_threads", C.c_int32), ("sim_capacity", C.c_int32), ("tuning", C.c_int32),
-        ("action_grid0", C.c_int32), ("action_grid1", C.c_int32), ("cluster_ctas", C.c_int32), ("reserved1", C.c_int32),
+        ("action_grid0", C.c_int32), ("action_grid1", C.c_int32), ("cluster_ctas", C.c_int32), ("tree_parallel", C.c_int32),
         ("C", C.c_double), ("gamma", C.c_double), ("alpha1", C.c_double), ("k1", C.c_double),
         ("alpha2", C.c_double), ("k2", C.c_double), ("epsilon", C.c_double),
-        ("seed", C.c_uint64), ("tree_id_base", C.c_uint64), ("n_trees", C.c_int64),
+        ("seed", C.c_uint64), ("tree_id_base", C.c_uint64), ("n_trees", C.c_int64), ("virtual_value", C.c_double),
     ]
 
 

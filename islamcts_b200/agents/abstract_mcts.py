@@ -300,7 +300,7 @@ class AbstractMcts:
         zero = p.depth_mode == "reference_head" and self.HEAD_ZERO_ROLLOUTS
         kw = dict(agent=self.AGENT, n_trees=int(p.n_trees), max_depth=int(p.max_depth), C_=float(p.C), gamma=float(p.gamma),
                   budget_mode=_lib.BUDGET_ZERO if zero else _lib.BUDGET_TO_MAX_DEPTH,
-                  rollouts_per_leaf=int(p.rollouts_per_leaf),
+                  rollouts_per_leaf=int(p.rollouts_per_leaf), tree_parallel=int(p.tree_parallel), virtual_value=float(p.virtual_value),
                   precision=_lib.PRECISION_F64 if p.precision == "f64" else _lib.PRECISION_F32, device=p.device)
         n, grid = env_action_info(p.env, env_id)
         if grid:

@@ -44,6 +44,10 @@ class MctsParameters:
     depth_mode: str | None = field(default=None, kw_only=True)
     rollouts_per_leaf: int = field(default=1, kw_only=True)   # leaf-parallel batch: mean of R rollouts, ONE visit
     n_trees: int = field(default=1, kw_only=True)             # root-parallel ensemble of independent trees
+    # tree-parallel search of ONE tree: that many simulations in flight at once (virtual loss; each leaf is provisionally
+    # credited with `virtual_value` until its rollouts arrive).  1 = the reference's sequential loop (exact statistics).
+    tree_parallel: int = field(default=1, kw_only=True)
+    virtual_value: float = field(default=0.0, kw_only=True)
     seed: int | None = field(default=None, kw_only=True)      # Philox key; None = drawn from numpy's global RNG
     precision: str = field(default="f32", kw_only=True)       # env arithmetic on the device: "f32" | "f64"
     device: str = field(default="cuda:0", kw_only=True)

@@ -116,7 +116,7 @@ int upload_tables(isla_engine* e) {
 
 static int resolve_kernel(const isla_config& c) {
     if (c.kernel == ISLA_KERNEL_THREAD_PER_TREE || c.kernel == ISLA_KERNEL_CTA_PER_TREE) return c.kernel;
-    const bool tpt_ok = c.agent == ISLA_AGENT_VANILLA && env_n_actions(c.env_id) > 0 && c.rollouts_per_leaf <= 1;
+    const bool tpt_ok = c.agent == ISLA_AGENT_VANILLA && env_n_actions(c.env_id) > 0 && c.rollouts_per_leaf <= 1 && c.tree_parallel <= 1;
     // narrow vanilla trees -> one thread each (the kernel spreads a small batch over many warps, see kTreesPerWarp; it is
     // at least as fast as the CTA engine even for ONE tree: CartPole nsim 1000 in 9.9 vs 12.9 ms);
     // wide (progressive widening, grids) / leaf-parallel trees -> one CTA (or cluster) each

@@ -70,6 +70,8 @@ struct CtaParams {
     int cluster;                           // CTAs (one thread-block cluster) sharing one tree's leaf-parallel rollouts
     const double* heur;                    // grid_policy table (FrozenLake rollouts), nullptr = random rollouts
     const double* noise; int noise_n;      // slippery FrozenLake: noise[k] of the k-th env.step of a simulation
+    int tree_parallel;                     // > 1: that many simulations of ONE tree in flight (virtual loss); else sequential
+    double virtual_value;                  // the return a leaf is provisionally credited with while its rollouts are in flight
 };
 
 enum : int { O_S_TOTAL = 0, O_S_TERMR, O_S_NS, O_S_FLAGS, O_S_COFF, O_S_CCAP, O_S_CCNT, O_S_STATE, O_A_TOTAL, O_A_VALUE,
@@ -151,6 +153,16 @@ struct RollShared {
     unsigned sim;
     double result;
     VooWork vw;
+};
+
+// Tree-parallel mode (opt-in build extension; north_star subsystem 2: "virtual loss for leaf-parallel batches"): the
+// record of one in-flight simulation between its descent and the arrival of its rollouts.
+constexpr int kTpMax = 64;
+struct TpRec {
+    double leaf[8];
+    double r_leaf, g_prov;
+    int budget, need, depth, leaf_a, leaf_s, level, pb;
+    unsigned sim;
 };
 
 __device__ __forceinline__ void bar_sync(int id, int nthreads) {
@@ -821,10 +833,20 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
     // descends), or whose first step terminates; those take the serial path.  BASELINE config C3 (k = 60, alpha = 0.8)
     // widens the root on every one of its 10 000 simulations.
     const bool wave_ok = !SCRIPTED && p.agent == ISLA_AGENT_APW && p.expansion == ISLA_EXPAND_RANDOM && R == 1 && CS == 1 &&
-                         p.hash_cap > 0 && nt >= 64;
+                         p.hash_cap > 0 && nt >= 64 && p.tree_parallel <= 1;
     __shared__ int wv_n, wv_ns0, wv_n0, wv_nS0, wv_nA0, wv_itop, wv_rng0, wv_bad, wv_off, wv_cap;
     __shared__ unsigned wv_sims0;
     constexpr int kWaveWords = ENV == ENV_CURVE ? 2 : 1;   // stream words per sampled action
+
+    // Tree-parallel mode: up to B simulations are selected one after the other -- each descent ends with a PROVISIONAL
+    // backup that credits its leaf with `virtual_value` (the virtual loss: visit counts move at once, so the next descent
+    // sees the path as taken and explores elsewhere) -- then the rollouts of all B leaves run concurrently on the CTA's
+    // threads, and the provisional credits are corrected to the real returns in simulation order.  Statistics differ from
+    // the sequential search (simulations of a batch do not see each other's returns); the default (B <= 1) is sequential.
+    const int tpB = SCRIPTED ? 1 : max(1, min(p.tree_parallel, kTpMax));
+    const bool tp = tpB > 1;
+    __shared__ TpRec tp_rec[kTpMax];
+    int tp_b = 0, tp_pb = 0;   // simulations in flight, path entries they occupy
 
     for (int sim = 0; sim < p.n_sim; ++sim) {
         if (wave_ok) {
@@ -995,6 +1017,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
         double G = 0.0, r_leaf = 0.0;
         int leaf_a = -1, leaf_s = -1;
         T cur[S];
+        const int pb = tp ? tp_pb : 0;   // first path entry of this simulation
         if (leader && !ctx.fault) {
             Pool& q = ctx.q;
             int s = 0;
@@ -1003,7 +1026,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                 // LEVELS of the previous path at once (the statistics are already backed up); the first level that
                 // has an unvisited action, an exact tie (needs a draw) or a different arg-max is where the serial
                 // descent resumes.  The old path's last level is always re-decided serially.
-                if (p.agent == ISLA_AGENT_VANILLA && prev_levels > 1) {
+                if (p.agent == ISLA_AGENT_VANILLA && prev_levels > 1 && !tp) {
                     const int Lv = prev_levels - 1;
                     int event = Lv;
                     for (int l0 = 0; l0 < Lv; l0 += 32) {
@@ -1177,10 +1200,10 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                 __syncwarp();
                 if (ctx.fault || ctx.tc.fault) break;
                 // record this level: the state node is always backed up, the action node unless skipped
-                if (level >= p.s_cap) { ctx.fault = ISLA_ERR_CAPACITY; break; }
+                if (pb + level >= p.s_cap) { ctx.fault = ISLA_ERR_CAPACITY; break; }
                 if (lane == 0) {
-                    q.p_s[level] = s; q.p_a[level] = a; q.p_r[level] = r;
-                    q.p_flag[level] = (descend ? 1 : 0) | (update_action ? 2 : 0);
+                    q.p_s[pb + level] = s; q.p_a[pb + level] = a; q.p_r[pb + level] = r;
+                    q.p_flag[pb + level] = (descend ? 1 : 0) | (update_action ? 2 : 0);
                 }
                 ++level;
                 if (!descend) break;
@@ -1219,6 +1242,112 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
         }
         }
         if (CS > 1) cg::this_cluster().sync();   // the owner's leaf record is final
+
+        if (tp) {
+            // ---------------------------------------------------------- tree-parallel: park this simulation, run the batch when full
+            if (leader) {
+                Pool& q = ctx.q;
+                const bool ok = !ctx.fault && !ctx.tc.fault && level > 0;
+                if (ok) {
+                    const double Gp = need_roll ? __dadd_rn(r_leaf, __dmul_rn(p.gamma, p.virtual_value)) : G;
+                    if (need_roll && lane == 0) { q.a_na[leaf_a] += 1; q.s_ns[leaf_s] += 1; q.a_total[leaf_a] += Gp; q.s_total[leaf_s] += Gp; }
+                    if (lane == 0) {
+                        double g = Gp;
+                        q.p_g[pb + level - 1] = g;
+                        for (int l = level - 2; l >= 0; --l) { g = __dadd_rn(q.p_r[pb + l], __dmul_rn(p.gamma, g)); q.p_g[pb + l] = g; }
+                    }
+                    __syncwarp();
+                    // (a node can occur once per path only: the updates of one simulation touch distinct nodes)
+                    for (int l = lane; l < level; l += 32) {
+                        const int s_ = q.p_s[pb + l], a_ = q.p_a[pb + l], fl = q.p_flag[pb + l];
+                        const double g = q.p_g[pb + l];
+                        if (l < level - 1 && (fl & 2)) { q.a_total[a_] += g; q.a_na[a_] += 1; }
+                        q.s_ns[s_] += 1; q.a_visits[a_] += 1; q.s_total[s_] += g;
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        TpRec& rc = tp_rec[tp_b];
+#pragma unroll
+                        for (int i = 0; i < S; ++i) rc.leaf[i] = (double)cur[i];
+                        rc.r_leaf = r_leaf; rc.g_prov = Gp;
+                        rc.budget = sh.budget; rc.need = need_roll ? 1 : 0; rc.depth = level;
+                        rc.leaf_a = leaf_a; rc.leaf_s = leaf_s; rc.level = level; rc.pb = pb; rc.sim = sims_done;
+                    }
+                    ++sims_done; ++s_done;
+                }
+                if (lane == 0) { sh.need = ok ? 1 : 0; sh.depth = ok ? level : 0; }
+            }
+            __syncthreads();
+            const int parked = sh.need, parked_levels = sh.depth;
+            if (parked) { ++tp_b; tp_pb += parked_levels; }
+            const bool flush = tp_b > 0 && (tp_b == tpB || sim == p.n_sim - 1 || !parked);
+            if (flush) {
+                const int nb = tp_b;
+                // every rollout (b, j) of the batch: index b * P + j
+                for (int i0 = 0; i0 < nb * P; i0 += nt) {
+                    const int i = i0 + tid;
+                    if (i < nb * P) {
+                        const int b = i / P, j = i - b * P;
+                        const TpRec& rc = tp_rec[b];
+                        double Rr = 0.0;
+                        if (rc.need && j < R) {
+                            T st[S];
+#pragma unroll
+                            for (int k = 0; k < S; ++k) st[k] = T(rc.leaf[k]);
+                            Stream rs;
+                            rs.init(p.seed, rc.sim, tree_id, (uint32_t)j);
+                            int t = 0; bool done = false;
+                            T rr = T(0);
+                            while (!done && t < rc.budget) {
+                                done = rollout_step<ENV, T>(rs, st, p.grid, rr, p.heur, p.noise, min(rc.depth + t, p.noise_n - 1));
+                                if constexpr (!Rewards<ENV>::kClosedForm) Rr = __dadd_rn(Rr, __dmul_rn((double)rr, __ldg(p.disc_table + t)));
+                                ++t;
+                            }
+                            if constexpr (Rewards<ENV>::kClosedForm) Rr = Rewards<ENV>::rollout_return(t, (double)rr, p.disc_table, p.cum_table);
+                            my_steps += t;
+                        }
+                        red[i] = Rr;
+                    }
+                }
+                __syncthreads();
+                for (int stride = P >> 1; stride > 0; stride >>= 1) {   // the fixed pairwise tree, per leaf
+                    for (int i = tid; i < nb * stride; i += nt) {
+                        const int b = i / stride, k = i - b * stride;
+                        red[b * P + k] = __dadd_rn(red[b * P + k], red[b * P + k + stride]);
+                    }
+                    __syncthreads();
+                }
+                // corrections, in simulation order: totals move from the provisional to the real return, counts stay
+                if (leader) {
+                    Pool& q = ctx.q;
+                    for (int b = 0; b < nb; ++b) {
+                        const TpRec& rc = tp_rec[b];
+                        if (!rc.need) continue;
+                        const double mean = R == 1 ? red[b * P] : __ddiv_rn(red[b * P], (double)R);
+                        const double Gr = __dadd_rn(rc.r_leaf, __dmul_rn(p.gamma, mean));
+                        const double d0 = __dsub_rn(Gr, rc.g_prov);
+                        if (lane == 0) {
+                            q.a_total[rc.leaf_a] += d0; q.s_total[rc.leaf_s] += d0;
+                            double d = d0;
+                            q.p_g[rc.pb + rc.level - 1] = d;
+                            for (int l = rc.level - 2; l >= 0; --l) { d = __dmul_rn(p.gamma, d); q.p_g[rc.pb + l] = d; }
+                        }
+                        __syncwarp();
+                        for (int l = lane; l < rc.level; l += 32) {
+                            const int s_ = q.p_s[rc.pb + l], a_ = q.p_a[rc.pb + l], fl = q.p_flag[rc.pb + l];
+                            const double d = q.p_g[rc.pb + l];
+                            if (l < rc.level - 1 && (fl & 2)) q.a_total[a_] += d;
+                            q.s_total[s_] += d;
+                        }
+                        __syncwarp();
+                    }
+                }
+                tp_b = 0; tp_pb = 0;
+            }
+            prev_levels = 0;
+            __syncthreads();   // sh.* and tp_rec are rewritten by the next descent
+            continue;
+        }
 
         // ------------------------------------------------------------ all threads: R rollouts from the leaf
         const bool need = sh0->need != 0;
@@ -1586,10 +1715,12 @@ CtaParams make_params(const isla_engine* e, int n_sim_launch = 0) {
     const long long fit_per_sm = p.stride_s > 0 ? (190 * 1024) / p.stride_s : 0;
     const long long sms = e->sm_count > 0 ? e->sm_count : 148;
     // (every CTA of a launch reserves the dynamic shared memory, the cluster's helper CTAs included)
-    p.pool_in_smem = (fit_per_sm >= 1 && e->cfg.n_trees * cs <= sms * fit_per_sm && !(e->cfg.tuning & 16)) ? 1 : 0;
+    // (tree-parallel batches record several paths at once: their entries need the full-size arrays in HBM)
+    p.pool_in_smem = (fit_per_sm >= 1 && e->cfg.n_trees * cs <= sms * fit_per_sm && !(e->cfg.tuning & 16) && e->cfg.tree_parallel <= 1) ? 1 : 0;
     p.hash_base = e->ws ? e->ws + L.hash_offset : nullptr; p.hash_cap = L.hash_cap;
     p.heur = e->heur_dev;
     p.noise = e->noise_dev; p.noise_n = e->noise_n;
+    p.tree_parallel = e->cfg.tree_parallel; p.virtual_value = e->cfg.virtual_value;
     return p;
 }
 
@@ -1608,6 +1739,7 @@ int pick_threads(const isla_config& cfg) {
         nt = 32;
         while (nt < R && nt < 512) nt <<= 1;
         if (cfg.expansion == ISLA_EXPAND_VOO) nt = 512;   // voo's rejection tries are evaluated CTA-wide
+        if (cfg.tree_parallel > 1) { while (nt < cfg.tree_parallel * R && nt < 512) nt <<= 1; }   // one thread per in-flight rollout
         // apw with random expansion and one rollout per leaf: runs of root-widening simulations are played one thread per
         // simulation (the widening wave of cta_search_kernel); worth a wide CTA while the trees do not fill the GPU anyway
         if (cfg.agent == ISLA_AGENT_APW && cfg.expansion == ISLA_EXPAND_RANDOM && R == 1 && cfg.n_trees <= 296) nt = 512;
@@ -1668,6 +1800,15 @@ int cta_fill_layout(const isla_config& cfg, isla_layout& lay) {
         set_error("n_actions=%d does not match env (%d)", cfg.n_actions, env_actions); return ISLA_ERR_INVALID;
     }
     if (cfg.expansion != ISLA_EXPAND_RANDOM && cfg.agent != ISLA_AGENT_APW) { set_error("voo / genetic2 expansion are APW options"); return ISLA_ERR_INVALID; }
+    if (cfg.tree_parallel > 1) {
+        int P2 = 1;
+        while (P2 < R) P2 <<= 1;
+        if (cfg.tree_parallel > kTpMax || (long long)cfg.tree_parallel * P2 > kMaxRollSmem) {
+            set_error("tree_parallel %d: at most %d simulations in flight and tree_parallel * rollouts_per_leaf <= %d", cfg.tree_parallel, kTpMax, kMaxRollSmem);
+            return ISLA_ERR_INVALID;
+        }
+        if (cfg.cluster_ctas > 1) { set_error("tree_parallel needs cluster_ctas <= 1"); return ISLA_ERR_INVALID; }
+    }
     if (cfg.cluster_ctas != 0 && cfg.cluster_ctas != 1 && cfg.cluster_ctas != 2 && cfg.cluster_ctas != 4 && cfg.cluster_ctas != 8) {
         set_error("cluster_ctas must be 0 (auto), 1, 2, 4 or 8"); return ISLA_ERR_INVALID;
     }

@@ -906,6 +906,7 @@ int tpt_fill_layout(const isla_config& cfg, isla_layout& lay) {
     if (A == 0 || cfg.agent != ISLA_AGENT_VANILLA) { set_error("thread-per-tree kernel: vanilla agent on a discrete env only"); return ISLA_ERR_INVALID; }
     if (cfg.n_actions != A) { set_error("n_actions=%d does not match env (%d)", cfg.n_actions, A); return ISLA_ERR_INVALID; }
     if (cfg.rollouts_per_leaf > 1) { set_error("thread-per-tree kernel: rollouts_per_leaf must be 1"); return ISLA_ERR_INVALID; }
+    if (cfg.tree_parallel > 1) { set_error("thread-per-tree kernel: tree_parallel needs the CTA-per-tree kernel"); return ISLA_ERR_INVALID; }
     const int64_t blocks = (int64_t)cfg.sim_capacity + 2;
     if (blocks >= (int64_t)kLinkBlockMask) { set_error("sim_capacity too large for the 28-bit block index"); return ISLA_ERR_INVALID; }
     const int rb = cfg.precision == ISLA_PRECISION_F64 ? 8 : 4;

@@ -57,7 +57,7 @@ class Engine:
                  voo_max_try: int = 1000, alpha1: float = 0.0, k1: float = 1.0, alpha2: float = 0.0, k2: float = 1.0,
                  precision: int = _lib.PRECISION_F32, kernel: int = _lib.KERNEL_AUTO, block_threads: int = 0,
                  seed: int = 0, tree_id_base: int = 0, device="cuda:0", tuning: int | None = None,
-                 action_grid=None, cluster_ctas: int = 0):
+                 action_grid=None, cluster_ctas: int = 0, tree_parallel: int = 0, virtual_value: float = 0.0):
         import os
         if tuning is None:
             tuning = int(os.environ.get("ISLA_TUNING", "0"))
@@ -68,8 +68,8 @@ class Engine:
             n_actions = g0 * g1 if env_id == _lib.ENV_CURVE else N_ACTIONS[env_id]
         self.cfg = IslaConfig(env_id, agent, int(n_actions or 0), int(max_depth), budget_mode, int(rollouts_per_leaf),
                               expansion, int(voo_n_samples), int(voo_max_try), precision, kernel, int(block_threads),
-                              int(sim_capacity), int(tuning), g0, g1, int(cluster_ctas), 0, float(C_), float(gamma), float(alpha1), float(k1), float(alpha2),
-                              float(k2), float(epsilon), int(seed), int(tree_id_base), int(n_trees))
+                              int(sim_capacity), int(tuning), g0, g1, int(cluster_ctas), int(tree_parallel), float(C_), float(gamma), float(alpha1), float(k1), float(alpha2),
+                              float(k2), float(epsilon), int(seed), int(tree_id_base), int(n_trees), float(virtual_value))
         nbytes = check(self.lib.isla_engine_workspace_bytes(C.byref(self.cfg)))
         with torch.cuda.device(self.device):
             self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)

@@ -41,6 +41,9 @@ def argument_parser():
     # build-only flags
     p.add_argument('--n_trees', default=1, type=int, help='root-parallel ensemble size')
     p.add_argument('--rollouts_per_leaf', default=1, type=int)
+    p.add_argument('--tree_parallel', default=1, type=int,
+                   help='simulations of ONE tree in flight at once (virtual loss); 1 = the reference\'s sequential loop')
+    p.add_argument('--virtual_value', default=0.0, type=float, help='provisional return credited to a leaf whose rollouts are in flight')
     p.add_argument('--seed', default=None, type=int)
     p.add_argument('--depth_mode', default="budgeted", choices=["budgeted", "reference_head"])
     p.add_argument('--precision', default="f32", choices=["f32", "f64"])
@@ -78,7 +81,8 @@ def create_agent(args, env, observation, seed=None):
     common = dict(root_data=observation, env=env, n_sim=args["nsim"], C=args["c"], action_selection_fn=get_function(args["as"], args),
                   gamma=args["gamma"], rollout_selection_fn=get_function(args["rollout"], args), max_depth=args["max_depth"],
                   n_actions=n_act, x_values=None, y_values=None, depths=None, n_trees=args["n_trees"],
-                  rollouts_per_leaf=args["rollouts_per_leaf"], seed=seed, depth_mode=args["depth_mode"],
+                  rollouts_per_leaf=args["rollouts_per_leaf"], tree_parallel=args["tree_parallel"], virtual_value=args["virtual_value"],
+                  seed=seed, depth_mode=args["depth_mode"],
                   precision=args["precision"])
     algo = args["algorithm"]
     if algo == "vanilla":

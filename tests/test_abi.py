@@ -30,7 +30,7 @@ def test_every_declared_symbol_is_exported(lib):
 def test_struct_sizes_match_header(lib):
     import ctypes as C
     from islamcts_b200 import _lib
-    assert C.sizeof(_lib.IslaConfig) == 18 * 4 + 7 * 8 + 3 * 8
+    assert C.sizeof(_lib.IslaConfig) == 18 * 4 + 7 * 8 + 3 * 8 + 8
     assert C.sizeof(_lib.IslaLayout) == 6 * 4 + 26 * 8
 
 
