@@ -368,8 +368,16 @@ class AbstractMcts:
         env_id = identify_env(p.env)
         root_state = env_root_state(p.env, env_id)
         noise = None
-        if env_id == _lib.ENV_FROZENLAKE:   # slippery lake: the clone's per-step draws, as of this fit()
-            noise = lake_transition_noise(p.env, max(int(p.max_depth), 4 * int(p.n_sim), 64) + 4)
+        live_env = self.AGENT in (_lib.AGENT_SPW, _lib.AGENT_DPW)
+        if env_id == _lib.ENV_FROZENLAKE:
+            # slippery lake.  Mcts / MctsHash / apw step a pickled clone per simulation: the clone's per-step draws, as of
+            # this fit().  spw / dpw step the LIVE env: the draws its generator will produce run on through the whole
+            # fit() (one per env.step of the search), and the env's generator is advanced by what the search consumed.
+            n_draws = max(int(p.max_depth), 4 * int(p.n_sim), 64) + 4
+            if live_env:
+                zero = p.depth_mode == "reference_head" and self.HEAD_ZERO_ROLLOUTS
+                n_draws = min(int(p.n_sim) * ((0 if zero else int(p.max_depth)) + 64) + 64, 1 << 24)
+            noise = lake_transition_noise(p.env, n_draws)
         self._ensure_engine(env_id, root_state, noise)
         eng = self._engine
         if env_id == _lib.ENV_FROZENLAKE:
@@ -381,6 +389,10 @@ class AbstractMcts:
         cnt = eng.counters()
         if cnt["faults"]:
             raise _lib.IslaError(_lib.ERR_CAPACITY, f"device search reported faults: {cnt}")
+        if noise is not None and live_env:
+            rng = getattr(getattr(p.env, "unwrapped", p.env), "np_random", None)
+            if rng is not None and hasattr(rng, "random"):
+                rng.random(int(cnt["env_steps"]))       # the search stepped the live env this many times
         return self._finish(eng, env_id)
 
     def _finish(self, eng, env_id):
@@ -471,7 +483,7 @@ class AbstractMcts:
         root = self._make_state(self._root_stub.data)
         root.ns, root.total = int(count[0]), float(total[0])
         stack = [(root, 0)]              # (node object, depth) of the open state nodes
-        cur_action = None
+        action_at = {}                   # state depth -> the action node last emitted below a state of that depth
         space = getattr(self.param.env, "action_space", None)
         dtype = getattr(space, "dtype", np.float32)
         for i in range(1, len(kind)):
@@ -490,11 +502,15 @@ class AbstractMcts:
                 node = AbstractActionNode(data, self.param)
                 node.na, node.total = int(count[i]), float(total[i])
                 parent.actions[key] = node
-                cur_action = node
-            else:                        # state node: the single child of the action node just emitted
+                action_at[int(depth[i])] = node
+            else:                        # state node: a child of the action node last emitted one level up (an action node
+                                         # has several on a stochastic env; keyed by position: the export carries no observation)
                 st = self._make_state(None)
                 st.ns, st.total, st.terminal = int(count[i]), float(total[i]), bool(term[i])
-                cur_action.children[len(cur_action.children)] = st
+                owner = action_at[int(depth[i]) - 1]
+                owner.children[len(owner.children)] = st
+                while stack[-1][1] >= depth[i]:
+                    stack.pop()
                 stack.append((st, int(depth[i])))
         return root
 

@@ -44,6 +44,7 @@ struct Pool {
     void* s_state;
     // action nodes
     double* a_total; double* a_value; double* a_value2; int* a_na; int* a_visits; int* a_child;
+    int* s_next;   // next entry of the parent action node's children dict (insertion order), -1 = last; a_child = the first
     // child index arrays, path
     int* ipool; int* p_s; int* p_a; double* p_r; int* p_flag; double* p_g;
     int* meta;
@@ -75,8 +76,8 @@ struct CtaParams {
 };
 
 enum : int { O_S_TOTAL = 0, O_S_TERMR, O_S_NS, O_S_FLAGS, O_S_COFF, O_S_CCAP, O_S_CCNT, O_S_STATE, O_A_TOTAL, O_A_VALUE,
-             O_A_NA, O_A_VISITS, O_A_CHILD, O_IPOOL, O_P_S, O_P_A, O_P_R, O_P_FLAG, O_META, O_P_G, O_A_VALUE2, O_COUNT };
-enum : int { CM_NS = 0, CM_NA = 1, CM_ITOP = 2, CM_SIMS = 3, CM_RNG = 4, CM_FAULT = 5, CM_TRACE_POS = 6, CM_WORDS = 8 };
+             O_A_NA, O_A_VISITS, O_A_CHILD, O_IPOOL, O_P_S, O_P_A, O_P_R, O_P_FLAG, O_META, O_P_G, O_A_VALUE2, O_S_NEXT, O_COUNT };
+enum : int { CM_NS = 0, CM_NA = 1, CM_ITOP = 2, CM_SIMS = 3, CM_RNG = 4, CM_FAULT = 5, CM_TRACE_POS = 6, CM_NOISE_POS = 7, CM_WORDS = 8 };
 
 __device__ __forceinline__ Pool make_pool_off(const long long* off, char* b) {
     Pool q;
@@ -92,6 +93,7 @@ __device__ __forceinline__ Pool make_pool_off(const long long* off, char* b) {
     q.meta = (int*)(b + off[O_META]);
     q.p_g = (double*)(b + off[O_P_G]);
     q.a_value2 = (double*)(b + off[O_A_VALUE2]);
+    q.s_next = (int*)(b + off[O_S_NEXT]);
     return q;
 }
 __device__ __forceinline__ Pool make_pool_at(const CtaParams& p, char* b) { return make_pool_off(p.off, b); }
@@ -108,6 +110,7 @@ __device__ __forceinline__ void copy_pool(const CtaParams& p, char* dst, const l
     };
     cp(O_S_TOTAL, nS * 8ll); cp(O_S_TERMR, nS * 8ll); cp(O_S_NS, nS * 4ll); cp(O_S_FLAGS, nS * 4ll);
     cp(O_S_COFF, nS * 4ll); cp(O_S_CCAP, nS * 4ll); cp(O_S_CCNT, nS * 4ll); cp(O_S_STATE, (long long)nS * p.state_bytes);
+    cp(O_S_NEXT, nS * 4ll);
     cp(O_A_TOTAL, nA * 8ll); cp(O_A_VALUE, nA * 8ll); cp(O_A_NA, nA * 4ll); cp(O_A_VISITS, nA * 4ll); cp(O_A_CHILD, nA * 4ll);
     if (p.action_dim == 2) cp(O_A_VALUE2, nA * 8ll);
     cp(O_IPOOL, itop * 4ll);
@@ -149,7 +152,9 @@ enum : int { VOO_EVAL = 0, VOO_EXIT = 1, VOO_FIND = 2 };
 struct RollShared {
     double leaf[8];
     int budget, need, exit_flag;
-    int depth;          // env.step calls of the simulation before the leaf's rollouts (slippery FrozenLake noise index)
+    int depth;          // transition-noise index of the leaf's first rollout step (slippery FrozenLake): the env.step calls of
+                        // the simulation so far (cloned env), or of the whole fit() so far (spw / dpw: live env)
+    int roll_steps;     // steps rollout 0 of the leaf played (advances the live env's noise index)
     unsigned sim;
     double result;
     VooWork vw;
@@ -259,6 +264,7 @@ struct Search {
     Pool q;
     int lane;
     int nS, nA, itop, fault;
+    int noise_pos;   // spw / dpw step the LIVE env: index of the next transition-noise draw, running through the whole fit()
     Stream ts;
     Cursor tc;
     uint32_t tree_id;
@@ -269,6 +275,7 @@ struct Search {
         hash = p.hash_base + tree * p.hash_cap * 16;
         lane = threadIdx.x & 31;
         nS = q.meta[CM_NS]; nA = q.meta[CM_NA]; itop = q.meta[CM_ITOP]; fault = q.meta[CM_FAULT];
+        noise_pos = q.meta[CM_NOISE_POS];
         tree_id = (uint32_t)(p.tree_id_base + (unsigned long long)tree);
         ts.resume(p.seed, 0u, tree_id, kStreamTree, (uint32_t)q.meta[CM_RNG]);
         tc = Cursor{p.trace_kinds, p.trace_values, p.trace_len, 0, 0};
@@ -328,7 +335,7 @@ struct Search {
         const int s = nS++;
         if (lane == 0) {
             q.s_total[s] = 0.0; q.s_term_reward[s] = term_reward; q.s_ns[s] = 0; q.s_flags[s] = terminal ? 1 : 0;
-            q.s_coff[s] = 0; q.s_ccap[s] = 0; q.s_ccnt[s] = 0;
+            q.s_coff[s] = 0; q.s_ccap[s] = 0; q.s_ccnt[s] = 0; q.s_next[s] = -1;
             T* d = state_ptr(s);
 #pragma unroll
             for (int i = 0; i < S; ++i) {
@@ -350,6 +357,37 @@ struct Search {
         }
         return a;
     }
+    // ---- the children dict of an action node (spw / dpw on a stochastic env: several next states per action), a singly
+    // linked list in insertion order: a_child = first, s_next = next.  Keys are the observations, compared bit for bit
+    // (`observation.tobytes()`, mcts_state_...:79); spw / dpw store the float32 observation as node.data.
+    __device__ int find_child(int a, const T (&st)[S], int& prev) const {
+        prev = -1;
+        for (int c = q.a_child[a]; c >= 0; prev = c, c = q.s_next[c]) {
+            const T* d = reinterpret_cast<const T*>(q.s_state) + (long long)c * S;
+            bool same = true;
+#pragma unroll
+            for (int i = 0; i < S; ++i) same &= (d[i] == T(float(st[i])));
+            if (same) return c;
+        }
+        return -1;
+    }
+    __device__ int count_children(int a) const {
+        int n = 0;
+        for (int c = q.a_child[a]; c >= 0; c = q.s_next[c]) ++n;
+        return n;
+    }
+    // children[obs_bytes] = node: an existing key keeps its place in the dict, a new key goes to the end
+    __device__ void put_child(int a, int old, int prev, int neu) {
+        if (lane == 0) {
+            if (old >= 0) {
+                q.s_next[neu] = q.s_next[old];
+                if (prev < 0) q.a_child[a] = neu; else q.s_next[prev] = neu;
+            } else if (prev < 0) q.a_child[a] = neu;
+            else q.s_next[prev] = neu;
+        }
+        __syncwarp();
+    }
+
     // append an action node to a state's child index array (insertion order), growing it by doubling
     __device__ void append_action(int s, int a) {
         int off = q.s_coff[s], cap = q.s_ccap[s], cnt = q.s_ccnt[s];
@@ -972,7 +1010,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                             q.a_total[a] = G; q.a_value[a] = val; q.a_na[a] = 1; q.a_visits[a] = 1; q.a_child[a] = c;
                             if (p.action_dim == 2) q.a_value2[a] = val2;
                             q.s_total[c] = G; q.s_term_reward[c] = 0.0; q.s_ns[c] = 1; q.s_flags[c] = 0;
-                            q.s_coff[c] = 0; q.s_ccap[c] = 0; q.s_ccnt[c] = 0;
+                            q.s_coff[c] = 0; q.s_ccap[c] = 0; q.s_ccnt[c] = 0; q.s_next[c] = -1;
                             T* d = ctx.state_ptr(c);
 #pragma unroll
                             for (int i = 0; i < S; ++i) d[i] = st[i];
@@ -1133,9 +1171,14 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                 T rT;
                 double step_a = q.a_value[a];
                 if constexpr (ENV == ENV_FROZENLAKE) {
-                    if (p.noise) {   // is_slippery=True: this is step `level` of the simulation
-                        if (level >= p.noise_n) { ctx.fault = ISLA_ERR_INVALID; break; }
-                        step_a = (double)lake_slip((int)step_a, __ldg(p.noise + level));
+                    if (p.noise) {
+                        // is_slippery=True.  Mcts / MctsHash / apw step a CLONE of the env per simulation: this is draw
+                        // `level` of the clone.  spw / dpw step the live env: the draws run on through the whole fit().
+                        const bool live_env = p.agent == ISLA_AGENT_SPW || p.agent == ISLA_AGENT_DPW;
+                        const int k = live_env ? ctx.noise_pos : level;
+                        if (k >= p.noise_n) { ctx.fault = ISLA_ERR_INVALID; break; }
+                        step_a = (double)lake_slip((int)step_a, __ldg(p.noise + k));
+                        if (live_env) ++ctx.noise_pos;
                     }
                 }
                 const bool term = env_step_action<ENV, T>(cur, step_a, p.action_dim == 2 ? q.a_value2[a] : 0.0, p.grid, rT);
@@ -1143,6 +1186,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                 ++ctx.c_env;
                 const int child = q.a_child[a];
                 bool descend = false, update_action = true;
+                int resampled = -1;   // spw / dpw: the child picked by the resampling branch
                 if (p.agent == ISLA_AGENT_VANILLA || p.agent == ISLA_AGENT_APW) {
                     if (term) {
                         // terminal: get-or-create the flagged child; total += r; na += 1; child.ns += 1
@@ -1161,19 +1205,24 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                 } else {
                     const double kk = p.agent == ISLA_AGENT_SPW ? p.k1 : p.k2;
                     const double al = p.agent == ISLA_AGENT_SPW ? p.alpha1 : p.alpha2;
-                    const int n_child = child >= 0 ? 1 : 0;
+                    // children dict of the action node: one entry per distinct observation (deterministic env: one)
+                    int prev = -1;
+                    const int old = ctx.find_child(a, cur, prev);      // the entry under this observation's key, if any
+                    const int n_child = ctx.count_children(a);
+                    if (old < 0) { prev = -1; for (int c = q.a_child[a]; c >= 0; c = q.s_next[c]) prev = c; }   // tail
                     const int na_now = q.a_na[a];
                     const double wcap = na_now < p.ln_count ? p.pw2_table[na_now] : __dmul_rn(kk, pow((double)na_now, al));
                     if (p.agent == ISLA_AGENT_SPW && term) {
                         // always a FRESH terminal child that overwrites the key (mcts_state_...:81-95)
                         const int c = ctx.new_state(cur, true, r);
-                        if (lane == 0 && !ctx.fault) { q.a_child[a] = c; q.a_total[a] += r; q.a_na[a] += 1; q.s_ns[c] += 1; }
+                        if (!ctx.fault) ctx.put_child(a, old, prev, c);
+                        if (lane == 0 && !ctx.fault) { q.a_total[a] += r; q.a_na[a] += 1; q.s_ns[c] += 1; }
                         G = r;
                     } else if (n_child == 0 || (double)n_child <= wcap) {
                         // widen: the new node REPLACES the child stored under the same observation key
                         const bool t2 = (p.agent == ISLA_AGENT_DPW) && term;
                         const int c = ctx.new_state(cur, t2, 0.0);
-                        if (lane == 0) q.a_child[a] = c;
+                        if (!ctx.fault) ctx.put_child(a, old, prev, c);
                         if (t2) {
                             if (lane == 0 && !ctx.fault) { q.a_total[a] += r; q.a_na[a] += 1; q.s_ns[c] += 1; }
                             G = r;
@@ -1181,18 +1230,51 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                             need_roll = true; leaf_a = a; leaf_s = c; r_leaf = r;
                         }
                     } else {
-                        // resample an existing child, weights na / ns_c (one candidate on a deterministic env)
-                        const bool child_term = q.s_flags[child] & 1;
-                        if (p.agent == ISLA_AGENT_DPW && child_term) {
+                        // resample an existing child: random.choices(children, weights = na / ns_c) (mcts_state_...:114-119;
+                        // dpw: the non-terminal children only, mcts_double_...:119-129)
+                        int n_cand = 0;
+                        double wtot = 0.0;
+                        for (int c = q.a_child[a]; c >= 0; c = q.s_next[c]) {
+                            if (p.agent == ISLA_AGENT_DPW && (q.s_flags[c] & 1)) continue;
+                            wtot = __dadd_rn(wtot, __ddiv_rn((double)na_now, (double)q.s_ns[c]));
+                            ++n_cand;
+                        }
+                        if (n_cand == 0) {
                             ctx.fault = ISLA_ERR_INVALID;  // reference: random.choices on an empty population raises
                         } else {
-                            if constexpr (SCRIPTED) { (void)ctx.tc.take(ISLA_K_CHOICES); } else { (void)ctx.ts.next(); }
+                            int pick_pos;
+                            if constexpr (SCRIPTED) {
+                                pick_pos = (int)ctx.tc.take(ISLA_K_CHOICES);
+                                if (pick_pos < 0 || pick_pos >= n_cand) { if (!ctx.tc.fault) ctx.tc.fault = ISLA_ERR_TRACE; pick_pos = 0; }
+                            } else {
+                                // one draw; first candidate whose cumulative weight exceeds u * total
+                                const double u = __dmul_rn(u32_to_d01(ctx.ts.next()), wtot);
+                                double cum = 0.0;
+                                int i = 0;
+                                pick_pos = n_cand - 1;
+                                for (int c = q.a_child[a]; c >= 0; c = q.s_next[c]) {
+                                    if (p.agent == ISLA_AGENT_DPW && (q.s_flags[c] & 1)) continue;
+                                    cum = __dadd_rn(cum, __ddiv_rn((double)na_now, (double)q.s_ns[c]));
+                                    if (cum > u) { pick_pos = i; break; }
+                                    ++i;
+                                }
+                            }
+                            int pick = -1, i = 0;
+                            for (int c = q.a_child[a]; c >= 0; c = q.s_next[c]) {
+                                if (p.agent == ISLA_AGENT_DPW && (q.s_flags[c] & 1)) continue;
+                                if (i == pick_pos) { pick = c; break; }
+                                ++i;
+                            }
+                            const bool child_term = q.s_flags[pick] & 1;
                             if (p.agent == ISLA_AGENT_SPW && child_term) {
-                                const double tr = q.s_term_reward[child];
-                                if (lane == 0) { q.a_total[a] += tr; q.a_na[a] += 1; q.s_ns[child] += 1; }
+                                const double tr = q.s_term_reward[pick];
+                                if (lane == 0) { q.a_total[a] += tr; q.a_na[a] += 1; q.s_ns[pick] += 1; }
                                 G = tr;
                             } else {
-                                descend = true; update_action = false;  // self.total / self.na untouched (:126-130)
+                                // the env continues from the resampled child's observation (:126-127); the reward of the
+                                // step just taken is kept; self.total / self.na stay untouched (:126-130)
+                                descend = true; update_action = false;
+                                resampled = pick;
                             }
                         }
                     }
@@ -1207,17 +1289,20 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                 }
                 ++level;
                 if (!descend) break;
-                s = child;
+                s = resampled >= 0 ? resampled : child;
             }
+            const bool live_env = p.noise && (p.agent == ISLA_AGENT_SPW || p.agent == ISLA_AGENT_DPW);
+            const int noise_base = live_env ? ctx.noise_pos : level;
             if constexpr (ENV == ENV_FROZENLAKE) {   // the noise table must cover every step the rollouts can take
                 const int b_ = p.budget_mode == ISLA_BUDGET_ZERO ? 0 : max(0, min(p.max_depth - level, p.disc_count));
-                if (p.noise && need_roll && level + b_ > p.noise_n) ctx.fault = ISLA_ERR_INVALID;
+                if (p.noise && need_roll && noise_base + b_ > p.noise_n) ctx.fault = ISLA_ERR_INVALID;
             }
             if (lane == 0) {
 #pragma unroll
                 for (int i = 0; i < S; ++i) sh.leaf[i] = (double)cur[i];
                 sh.budget = p.budget_mode == ISLA_BUDGET_ZERO ? 0 : max(0, min(p.max_depth - level, p.disc_count));
-                sh.depth = level;
+                sh.depth = noise_base;
+                sh.roll_steps = 0;
                 sh.need = (need_roll && !ctx.fault && !ctx.tc.fault) ? 1 : 0;
                 sh.sim = sims_done;
             }
@@ -1378,7 +1463,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                         Rr = __dadd_rn(Rr, __dmul_rn((double)rr, p.disc_table[t]));
                         ++t;
                     }
-                    if (tid == 0) { my_steps += t; red[0] = Rr; }
+                    if (tid == 0) { my_steps += t; red[0] = Rr; sh.roll_steps = t; }
                 }
                 __syncthreads();
             } else {
@@ -1412,6 +1497,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                             }
                             if constexpr (Rewards<ENV>::kClosedForm) Rr = Rewards<ENV>::rollout_return(t, (double)rr, p.disc_table, p.cum_table);
                             my_steps += t;
+                            if (j == 0) sh.roll_steps = t;
                         }
                         red[jl] = Rr;
                     }
@@ -1438,6 +1524,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
         // ------------------------------------------------------------ warp 0: leaf update + backup
         if (leader && !ctx.fault && !ctx.tc.fault && level > 0) {
             Pool& q = ctx.q;
+            if (need_roll && p.noise && (p.agent == ISLA_AGENT_SPW || p.agent == ISLA_AGENT_DPW)) ctx.noise_pos += sh.roll_steps;
             if (need_roll) {
                 const double mean = R == 1 ? red[0] : __ddiv_rn(red[0], (double)R);
                 G = __dadd_rn(r_leaf, __dmul_rn(p.gamma, mean));
@@ -1476,7 +1563,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
         if (lane == 0) {
             int* m = ctx.q.meta;
             m[CM_NS] = ctx.nS; m[CM_NA] = ctx.nA; m[CM_ITOP] = ctx.itop; m[CM_SIMS] = (int)sims_done;
-            m[CM_RNG] = (int)ctx.ts.consumed(); m[CM_FAULT] = flt;
+            m[CM_RNG] = (int)ctx.ts.consumed(); m[CM_FAULT] = flt; m[CM_NOISE_POS] = ctx.noise_pos;
             if constexpr (SCRIPTED) m[CM_TRACE_POS] = (int)ctx.tc.pos;
             atomicAdd(p.counters + CNT_ENV_STEPS, ctx.c_env);
             atomicAdd(p.counters + CNT_ROLLOUT_STEPS, ctx.c_roll);
@@ -1500,6 +1587,7 @@ __global__ void cta_set_roots_kernel(const CtaParams p, const double* roots, int
     if (tree >= p.n_trees) return;
     Pool q = make_pool(p, tree);
     q.s_total[0] = 0.0; q.s_term_reward[0] = 0.0; q.s_ns[0] = 0; q.s_flags[0] = 0; q.s_coff[0] = 0; q.s_ccap[0] = 0; q.s_ccnt[0] = 0;
+    q.s_next[0] = -1;
     T* st = reinterpret_cast<T*>(q.s_state);
     for (int i = 0; i < S; ++i) {
         T v = (T)roots[tree * S + i];
@@ -1623,8 +1711,7 @@ __global__ void __launch_bounds__(256) cta_depth_stats_kernel(const CtaParams p,
     __syncthreads();
     // the root's children (up to 10^4 under progressive widening) are spread over the CTA
     for (int i = tid; i < n_root; i += nt) {
-        const int c = q.a_child[q.ipool[root_off + i]];
-        if (c >= 0) { lvl[c] = 1; own[c] = i; }
+        for (int c = q.a_child[q.ipool[root_off + i]]; c >= 0; c = q.s_next[c]) { lvl[c] = 1; own[c] = i; }
     }
     __syncthreads();
     for (int cur = 1;; ++cur) {
@@ -1635,8 +1722,7 @@ __global__ void __launch_bounds__(256) cta_depth_stats_kernel(const CtaParams p,
             const int n = q.s_ccnt[s], off = q.s_coff[s], o = own[s];
             int pushed = 0;
             for (int i = 0; i < n; ++i) {
-                const int c = q.a_child[q.ipool[off + i]];
-                if (c >= 0) { lvl[c] = cur + 1; own[c] = o; ++pushed; }
+                for (int c = q.a_child[q.ipool[off + i]]; c >= 0; c = q.s_next[c]) { lvl[c] = cur + 1; own[c] = o; ++pushed; }
             }
             if (pushed) changed = 1;
             if (o < cap) {
@@ -1664,6 +1750,7 @@ static long long pool_layout(long long cap, int state_dim, int rb, int action_di
     take(O_META, CM_WORDS * 4);
     take(O_P_G, cap * 8);
     take(O_A_VALUE2, action_dim == 2 ? cap * 8 : 0);
+    take(O_S_NEXT, cap * 4);
     o[O_COUNT] = off;
     return off;
 }
@@ -1854,6 +1941,11 @@ int cta_run(isla_engine* e, int n_sim, long long scripted_tree, const uint8_t* k
     p.n_sim = n_sim; p.scripted_tree = scripted_tree; p.trace_kinds = kinds; p.trace_values = values; p.trace_len = trace_len;
     const bool scripted = scripted_tree >= 0;
     if (scripted && p.R != 1) { set_error("scripted runs need rollouts_per_leaf == 1"); return ISLA_ERR_INVALID; }
+    if (p.noise && (p.agent == ISLA_AGENT_SPW || p.agent == ISLA_AGENT_DPW) && (p.R != 1 || p.cluster > 1 || p.tree_parallel > 1)) {
+        set_error("spw / dpw on the slippery lake step the live env: its noise runs sequentially through the fit, so "
+                  "rollouts_per_leaf, cluster_ctas and tree_parallel must be 1");
+        return ISLA_ERR_INVALID;
+    }
     const int nt = scripted ? 32 : pick_threads(e->cfg);
     return e->lay.real_bytes == 8 ? launch_env<double>(e, p, nt, scripted, st) : launch_env<float>(e, p, nt, scripted, st);
 }

@@ -5,10 +5,11 @@ from __future__ import annotations
 import numpy as np
 
 _NAMES = ["s_total", "s_term_reward", "s_ns", "s_flags", "s_coff", "s_ccap", "s_ccnt", "s_state", "a_total", "a_value",
-          "a_na", "a_visits", "a_child", "ipool", "p_s", "p_a", "p_r", "p_flag", "meta", "p_g", "a_value2", "end"]
+          "a_na", "a_visits", "a_child", "ipool", "p_s", "p_a", "p_r", "p_flag", "meta", "p_g", "a_value2", "s_next", "end"]
 _DT = {"s_total": "<f8", "s_term_reward": "<f8", "s_ns": "<i4", "s_flags": "<i4", "s_coff": "<i4", "s_ccap": "<i4",
        "s_ccnt": "<i4", "a_total": "<f8", "a_value": "<f8", "a_na": "<i4", "a_visits": "<i4", "a_child": "<i4",
-       "ipool": "<i4", "p_s": "<i4", "p_a": "<i4", "p_r": "<f8", "p_flag": "<i4", "meta": "<i4", "p_g": "<f8", "a_value2": "<f8"}
+       "ipool": "<i4", "p_s": "<i4", "p_a": "<i4", "p_r": "<f8", "p_flag": "<i4", "meta": "<i4", "p_g": "<f8", "a_value2": "<f8",
+       "s_next": "<i4"}
 
 
 def read_pool(engine, tree: int) -> dict:
@@ -42,11 +43,16 @@ def export_pool(engine, tree: int = 0) -> dict:
             for i in range(n - 1, -1, -1):
                 stack.append((1, int(P["ipool"][off + i]), d))
         else:
+            # the action node's children dict: a_child = first entry, s_next = next (insertion order)
+            kids = []
             c = int(P["a_child"][idx])
+            while c >= 0:
+                kids.append(c)
+                c = int(P["s_next"][c])
             kinds.append(1); depths.append(d); counts.append(int(P["a_na"][idx])); totals.append(float(P["a_total"][idx]))
-            terms.append(0); fans.append(1 if c >= 0 else 0); acts.append(float(P["a_value"][idx]))
+            terms.append(0); fans.append(len(kids)); acts.append(float(P["a_value"][idx]))
             acts2.append(float(P["a_value2"][idx]) if two else 0.0)
-            if c >= 0:
+            for c in reversed(kids):
                 stack.append((0, c, d + 1))
     return dict(kind=np.asarray(kinds, np.uint8), depth=np.asarray(depths, np.int32), count=np.asarray(counts, np.int64),
                 total=np.asarray(totals, np.float64), terminal=np.asarray(terms, np.uint8),

@@ -853,7 +853,11 @@ int orc_tree_run(orc_tree* t, int n_sim, const uint8_t* kinds, const double* val
     for (int s = 0; s < n_sim && !t->fault; ++s) {
         /* fit(): param.env = my_deepcopy(initial_env, ...) -- mcts_hash.py:31 ; spw/dpw poke root_data */
         memcpy(t->env, t->root_state, sizeof t->env);
-        t->sim_step = 0;
+        /* Mcts / MctsHash / APW step a pickled CLONE of the env in every simulation (utils/mcts_utils.py:8-16): the clone's
+         * generator restarts, so the k-th env.step of every simulation draws noise[k].  SPW / DPW step the LIVE env
+         * (they only poke the state: mcts_state_...:24-25, mcts_double_...:25-26): its generator keeps running, so the
+         * noise index runs on through the whole fit() -- an action node then really gets several children. */
+        if (!(t->cfg.agent == ORC_AGENT_SPW || t->cfg.agent == ORC_AGENT_DPW)) t->sim_step = 0;
         if (t->cfg.agent == ORC_AGENT_SPW || t->cfg.agent == ORC_AGENT_DPW) env_set_from_obs(t, t->S[0].obs);
         t->cur_len = 0;
         state_visit(t, 0, 0);

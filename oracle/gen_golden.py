@@ -86,6 +86,12 @@ SCENARIOS = {
                                env_seed=7, rng_seed=22, slippery=True),
     "hash_lake_slippery": dict(agent="MctsHash", env="FrozenLake-v1", n_sim=220, C=0.5, gamma=0.95, max_depth=16,
                                budget="to_max_depth", env_seed=8, rng_seed=23, slippery=True),
+    # SPW on the slippery lake steps the LIVE env (no clone): every env.step draws fresh noise, so an action node gets
+    # several children -- widening for real (k=1), and resampling among them with weights na / ns (k=0.5, alpha=0.2)
+    "spw_lake_slippery": dict(agent="MctsSpw", env="FrozenLake-v1", n_sim=300, C=0.5, gamma=0.95, max_depth=30, alpha=0.5, k=1,
+                              budget="zero", env_seed=11, rng_seed=24, slippery=True),
+    "spw_lake_slippery_resample": dict(agent="MctsSpw", env="FrozenLake-v1", n_sim=400, C=0.7, gamma=0.9, max_depth=30, alpha=0.2,
+                                       k=0.5, budget="zero", env_seed=12, rng_seed=25, slippery=True),
     # SPW (with the state_variable shim) on CartPole: k=1 always re-expands; k=0.4 resamples and descends
     "spw_cartpole_k1": dict(agent="MctsSpw", env="CartPole-v1", n_sim=150, C=1.0, gamma=0.99, max_depth=500,
                             alpha=0.5, k=1, budget="zero", env_seed=0, rng_seed=9),
@@ -133,7 +139,7 @@ def run_scenario(name: str, sc: dict):
             obs, _, done, _ = env.step(np.asarray(a, dtype=np.float64) if env_name == "CurveEnv" else int(a))
             assert not done, "pre_steps must keep the car on the track"
         root_state = np.array([*env.car.state, float(env.n_step)], dtype=np.float64)
-    elif env_name == "FrozenLake-v1" and agent_key == "MctsHash":
+    elif env_name == "FrozenLake-v1" and agent_key in ("MctsHash", "MctsSpw"):
         env = _LakeHashEnv(api=4, seed=sc["env_seed"], is_slippery=sc.get("slippery", False))
         obs = env.reset()
         root_state = pyenvs.env_state_vector(env)
@@ -153,6 +159,8 @@ def run_scenario(name: str, sc: dict):
     root_data = obs
     if env_name == "FrozenLake-v1" and agent_key == "MctsHash":
         root_data = np.array([0, 0])  # fit() indexes root_data[0], root_data[1] (mcts_hash.py:37-38)
+    if env_name == "FrozenLake-v1" and agent_key == "MctsSpw":
+        root_data = np.int64(obs)     # poked into env.s by fit() (mcts_state_...:24-25)
     rollout_fn = R.continuous_default_policy
     if sc.get("rollout") == "grid":
         rollout_fn = R.asf.grid_policy(lake_manhattan_knowledge(), 4)
@@ -173,7 +181,7 @@ def run_scenario(name: str, sc: dict):
         param = R.PwParameters(**common, alpha=sc["alpha"], k=sc["k"], action_expansion_function=ae)
     elif agent_key == "MctsSpw":
         param = R.SpwParams(**common, alpha=sc["alpha"], k=sc["k"], action_expansion_function=None,
-                            state_variable="state")
+                            state_variable="s" if env_name == "FrozenLake-v1" else "state")
     elif agent_key == "MctsDpw":
         common["action_selection_fn"] = R.ucb1_index
         param = R.DpwParams(**common, alphaApw=sc["alpha1"], kApw=sc["k1"], alphaSpw=sc["alpha2"], kSpw=sc["k2"],
@@ -185,7 +193,8 @@ def run_scenario(name: str, sc: dict):
     noise = None
     if sc.get("slippery"):
         import copy
-        noise = copy.deepcopy(env.np_random).random(sc["max_depth"] + 4)
+        # (SPW steps the live env: its draws run on through the whole fit(), one per tree level at HEAD)
+        noise = copy.deepcopy(env.np_random).random(sc["max_depth"] + 4 if agent_key != "MctsSpw" else sc["n_sim"] * 64)
     fit_error = ""
     steps0 = pyenvs.STEP_COUNTER[0]
     with T.recording(tr, sc["rng_seed"]):
@@ -222,7 +231,8 @@ def run_scenario(name: str, sc: dict):
         q_values=np.asarray(agent.q_values, dtype=np.float64),
         root_action=root_action, root_action2=root_action2, root_na=root_na, root_total=root_total,
         root_depth_max=root_depth_max, root_depth_mean=root_depth_mean,
-        **({"noise": noise} if noise is not None else {}),
+        # (the live-env table of SPW is cut to what the fit() consumed)
+        **({"noise": noise if agent_key != "MctsSpw" else noise[: int(pyenvs.STEP_COUNTER[0] - steps0) + 8]} if noise is not None else {}),
         fit_action=np.float64(action_val),
         env_steps=np.int64(pyenvs.STEP_COUNTER[0] - steps0) if env_name not in ("CurveEnv", "DiscreteCurveEnv") else np.int64(-1),
         **{f"tree_{k}": v for k, v in ser.items()},

@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests/test_gpu_tree_cta.py -x -q -m gpu -k tree_parallel -s 2>&1 | tail -12
+timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | grep -v Warning | tail -6

@@ -356,3 +356,31 @@ def test_slippery_frozenlake_through_the_agent_api():
         if done:
             break
     assert 0 <= total_slips <= 4
+
+
+def test_spw_agent_on_slippery_lake_steps_the_live_env():
+    """MctsSpw on FrozenLake is_slippery=True through the drop-in classes: the search consumes the env's own generator
+    (the reference does not clone the env in spw / dpw), action nodes get several children keyed by observation, and
+    after fit() the env's generator stands where the reference's would: advanced by the env.step calls of the search."""
+    import copy
+    from islamcts_b200 import envs
+    from islamcts_b200.agents import MctsSpw
+    from islamcts_b200.agents.parameters.pw_parameters import PwParameters
+    from islamcts_b200.utils.action_selection_functions import continuous_default_policy, ucb1
+    env = envs.make("FrozenLake-v1", api=4, seed=5, is_slippery=True)
+    obs = env.reset()
+    before = copy.deepcopy(env.np_random)
+    p = PwParameters(root_data=obs, env=env.unwrapped, n_sim=300, C=0.5, action_selection_fn=ucb1, gamma=0.95,
+                     rollout_selection_fn=continuous_default_policy, max_depth=20, n_actions=4, alpha=0.5, k=1,
+                     action_expansion_function=None, depth_mode="reference_head", seed=3, state_variable="s")
+    ag = MctsSpw(p)
+    a = ag.fit()
+    assert 0 <= int(a) < 4 and len(ag.q_values) == 4
+    root = ag._full_root()
+    fan = [len(act.children) for act in root.actions.values()]
+    assert max(fan) >= 2                                           # several next states under one root action
+    assert root.ns == 300            # (an spw action node's na does not count the visits that resample and descend, :126-130)
+    steps = ag._engine.counters()["env_steps"]
+    assert steps >= 300
+    before.random(int(steps))
+    assert env.np_random.random() == before.random()               # the live generator moved by exactly the search's steps

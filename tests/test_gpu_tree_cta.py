@@ -310,3 +310,45 @@ def test_tree_parallel_virtual_loss_statistics(name, kw, vv, tol):
     print(f"{name}: root value sequential {v1.mean():.4f} tree-parallel {v16.mean():.4f} (s.e. {se:.4f}); lower-half visit share {f1.mean():.3f} / {f16.mean():.3f}")
     assert abs(v1.mean() - v16.mean()) <= max(4 * se, tol * abs(v1.mean())), (v1.mean(), v16.mean(), se)
     assert abs(f1.mean() - f16.mean()) <= 0.15, (f1.mean(), f16.mean())
+
+
+@pytest.mark.parametrize("k,alpha,budget_mode", [(1.0, 0.5, 0), (0.5, 0.2, 0), (1.0, 0.5, 1)])
+def test_spw_slippery_lake_multi_child_free_running_equals_oracle(k, alpha, budget_mode):
+    """SPW on FrozenLake is_slippery=True steps the LIVE env (mcts_state_progressive_widening_hash.py:24-25,78: no clone), so
+    every env.step draws fresh transition noise and an action node's `children` dict really holds several next states:
+    widening appends / overwrites by observation key, the resampling branch draws among them with weights na / ns_c
+    (:114-119).  Device and C oracle share the Philox streams and the noise table (which here runs on through the whole
+    search, budgeted rollouts included): trees node for node, incl. action nodes with 2 and 3 children."""
+    n_trees, n_sim = 16, 260
+    kw = dict(env_id=3, agent=2, n_actions=4, max_depth=12, C=0.5, gamma=0.95, alpha1=alpha, k1=k, budget_mode=budget_mode)
+    noise = np.random.default_rng(77).random(n_sim * 40)
+    roots = np.zeros((n_trees, 1))
+    eng = _engine(dict(kw), n_trees, n_sim, 1, seed=31, tree_id_base=9)
+    eng.set_transition_noise(noise)
+    eng.set_roots(roots).run(n_sim)
+    assert eng.counters()["faults"] == 0
+    multi = 0
+    for i in range(n_trees):
+        okw = dict(kw)
+        conf = coracle.make_config(okw.pop("env_id"), C_=okw.pop("C"), seed=31, tree_id=9 + i, **okw)
+        t = coracle.Tree(conf, roots[i])
+        assert t.set_noise(noise) == 0
+        assert t.run(n_sim) == 0
+        ser = t.serialise()
+        assert_tree_equal(eng.export_tree(i), {"tree_" + kk: v for kk, v in ser.items()}, rtol=1e-9, atol=1e-9, label=f"tree{i}: ")
+        multi += int(((ser["kind"] == 1) & (ser["fanout"] > 1)).sum())
+        if i % 5 == 0:
+            dmax, dmean = eng.depth_stats(i)
+            edmax, edmean = t.depth_stats()
+            np.testing.assert_array_equal(dmax, edmax)
+            np.testing.assert_allclose(dmean, edmean, rtol=1e-12)
+    assert multi > 20          # the scenario does exercise multi-child action nodes
+    # a table shorter than the search is a loud fault, and the live env admits one rollout per leaf only
+    short = _engine(dict(kw), 2, n_sim, 1, seed=31)
+    short.set_transition_noise(noise[:20]).set_roots(roots[:2]).run(n_sim)
+    assert short.counters()["faults"] > 0
+    from islamcts_b200 import _lib
+    bad = _engine(dict(kw), 2, n_sim, 1, seed=31, rollouts_per_leaf=4)
+    bad.set_transition_noise(noise)
+    with pytest.raises(_lib.IslaError):
+        bad.set_roots(roots[:2]).run(n_sim)
