@@ -208,6 +208,14 @@ int isla_merge_root_stats(const int64_t* na_dev, const double* total_dev, const 
  * q = total / na and the arg-max follow on every rank (mcts_hash.py:42-50). */
 int isla_engine_root_merge(isla_engine* e, int64_t n_roots, double* packed_out_dev, void* stream);
 
+/* Tree reuse between real steps (build extension; the reference builds a new agent -- a fresh tree -- for every real step,
+ * sweep.py:186): the subtree below root action action_dev[tree] of every tree (alive_dev[tree] != 0, or all if NULL)
+ * becomes the tree; its statistics are kept bit for bit, the chosen child's state becomes the root state, and the next
+ * isla_engine_run continues from there.  A subtree that would not leave room in the workspace for the n_sim_next
+ * simulations of the coming step (node blocks, or visit counts beyond the ln(n) table: both sized by sim_capacity) is
+ * dropped and the search restarts from the bare child state, as the per-step rebuild would.  Thread-per-tree engine. */
+int isla_engine_reroot(isla_engine* e, const int32_t* action_dev, const uint8_t* alive_dev, int32_t n_sim_next, void* stream);
+
 /* Kernels this library has launched in this process (bench.py's gpu_launches is a difference of two readings). */
 int64_t isla_kernel_launches(void);
 

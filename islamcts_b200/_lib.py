@@ -83,6 +83,7 @@ SYMBOLS = {
     "isla_merge_root_stats": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int64, _P, _P, _P]),
     "isla_engine_root_merge": (C.c_int, [_P, C.c_int64, _P, _P]),
     "isla_kernel_launches": (C.c_int64, []),
+    "isla_engine_reroot": (C.c_int, [_P, _P, _P, C.c_int32, _P]),
     "isla_env_step": (C.c_int, [C.c_int32, C.c_int32, _P, _P, C.c_int64, _P, _P, _P, _P]),
     "isla_rollout": (C.c_int, [C.c_int32, C.c_int32, _P, C.c_int64, C.c_int32, C.c_double, C.c_uint64, C.c_uint32,
                                C.c_int32, C.c_int32, _P, _P, _P]),

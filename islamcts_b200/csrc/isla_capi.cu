@@ -265,6 +265,7 @@ int isla_engine_destroy(isla_engine* e) {
     if (e && e->heur_dev) cudaFree(e->heur_dev);
     if (e && e->noise_dev) cudaFree(e->noise_dev);
     if (e && e->ret_dev) cudaFree(e->ret_dev);
+    if (e && e->reroot_tmp) cudaFree(e->reroot_tmp);
     delete e;
     return ISLA_OK;
 }
@@ -424,6 +425,16 @@ int isla_engine_root_merge(isla_engine* e, int64_t n_roots, double* packed_out_d
     ISLA_CUDA_OK(cudaGetLastError());
     count_launch(1);
     return ISLA_OK;
+}
+
+int isla_engine_reroot(isla_engine* e, const int32_t* action_dev, const uint8_t* alive_dev, int32_t n_sim_next, void* stream) {
+    if (!e || !action_dev) { set_error("null argument"); return ISLA_ERR_INVALID; }
+    if (e->kernel != ISLA_KERNEL_THREAD_PER_TREE) { set_error("reroot: thread-per-tree engine only"); return ISLA_ERR_INVALID; }
+    if (!e->roots_set) { set_error("isla_engine_set_roots must be called first"); return ISLA_ERR_INVALID; }
+    if (n_sim_next < 0) { set_error("n_sim_next < 0"); return ISLA_ERR_INVALID; }
+    const int rc = tpt_reroot(e, action_dev, alive_dev, n_sim_next, (cudaStream_t)stream);
+    if (rc == 0) count_launch(1);
+    return rc;
 }
 
 int64_t isla_kernel_launches(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }

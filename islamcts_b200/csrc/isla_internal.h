@@ -83,6 +83,8 @@ struct isla_engine {
     double* heur_dev = nullptr;   // grid_policy prior knowledge [16][4] (engine-owned), nullptr = random rollouts
     double* noise_dev = nullptr;  // slippery FrozenLake: per-step transition noise of a fit (engine-owned)
     int noise_n = 0;
+    char* reroot_tmp = nullptr;   // thread-per-tree engine: scratch arena of isla_engine_reroot (engine-owned, lazily sized)
+    size_t reroot_bytes = 0;
     double* ret_dev = nullptr;    // thread-per-tree engine: return table (engine-owned), ret_rows x ret_K
     int ret_rows = 0, ret_K = 0;
 };
@@ -96,6 +98,7 @@ int tpt_set_roots(isla_engine* e, const double* roots_dev, cudaStream_t st);
 int tpt_run(isla_engine* e, int n_sim, long long scripted_tree, const uint8_t* kinds, const double* values,
             long long trace_len, cudaStream_t st);
 int tpt_root_stats(isla_engine* e, int64_t* na_dev, double* total_dev, cudaStream_t st);
+int tpt_reroot(isla_engine* e, const int32_t* action_dev, const uint8_t* alive_dev, int n_sim_next, cudaStream_t st);
 int tpt_best(isla_engine* e, int scripted_pos, int32_t* best_dev, double* best_action_dev, cudaStream_t st);
 // CTA-per-tree engine (isla_tree_cta.cu)
 int cta_fill_layout(const isla_config& cfg, isla_layout& lay);

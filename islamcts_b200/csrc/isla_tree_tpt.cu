@@ -862,6 +862,88 @@ __global__ void __launch_bounds__(256) tpt_depth_stats_kernel(const char* blocks
     if (tid < n_root && tid < cap) dmean[tid] = leaves[tid] ? __ddiv_rn(dmean[tid], (double)leaves[tid]) : 0.0;
 }
 
+// Tree reuse between real steps (build extension; the reference builds a new agent per step,
+// sweep.py:186): the subtree below the root edge `action[tree]` becomes the tree.  One CTA per tree copies the subtree
+// breadth first into a scratch arena -- blocks renumbered in visiting order, the chosen child's block becomes block 1 and
+// its state the root state (slot 0) -- and then back over the tree's own arena, zeroing what is left of the old blocks
+// (fresh blocks are assumed zero).  Statistics are copied bit for bit; the re-rooted node is searched as a root from
+// now on (its ns = the sum of its edges' visits).  Scratch per tree: the PV area (the queue; free between launches) and
+// `tmp` (one tree's node blocks, states and creation returns).
+template <typename T>
+__global__ void __launch_bounds__(128) tpt_reroot_kernel(char* blocks_all, T* states_all, double* gfirst_all, int32_t* meta_all,
+                                                         char* pv_all, long long pv_stride, long long slots_per_tree, int A, int S,
+                                                         const int32_t* __restrict__ action, const uint8_t* __restrict__ alive,
+                                                         char* tmp_all, long long tmp_stride, long long n_trees, int max_blocks,
+                                                         int max_visits) {
+    const long long tree = blockIdx.x;
+    if (tree >= n_trees || (alive && !alive[tree])) return;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    char* const blocks = blocks_all + tree * slots_per_tree * 16;
+    T* const states = states_all + tree * slots_per_tree * S;
+    double* const gfirst = gfirst_all + tree * slots_per_tree;
+    int32_t* const meta = meta_all + tree * META_WORDS;
+    const int alloc = meta[META_ALLOC];
+    const int blk_bytes = A * 16;
+    int* const queue = reinterpret_cast<int*>(pv_all + tree * pv_stride);   // new block - 1 -> old block
+    char* const tblocks = tmp_all + tree * tmp_stride;
+    T* const tstates = reinterpret_cast<T*>(tblocks + slots_per_tree * 16);
+    double* const tg = reinterpret_cast<double*>(reinterpret_cast<char*>(tstates) + slots_per_tree * S * (long long)sizeof(T));
+    __shared__ int head, tail, lvl_end;
+    const int a0 = min(max(action[tree], 0), A - 1);
+    const uint32_t lk0 = *link_ptr_rt(blocks, 1, a0, A);
+    const int na0 = *na_ptr_rt(blocks, 1, a0, A);
+    int cb0 = (na0 > 0 && !(lk0 & kLinkTerminal)) ? (int)(lk0 & kLinkBlockMask) : 0;
+    // a subtree that would not leave room for the coming simulations (blocks, or visit counts beyond the ln(n) table) is
+    // dropped: the search restarts from the bare child state, as the per-step rebuild would
+    if (cb0 && na0 - 1 > max_visits) cb0 = 0;
+    // the new root's state: the chosen child's (slot 1 * A + a0 of the old tree)
+    if (tid < S) tstates[tid] = states[(long long)(1 * A + a0) * S + tid];
+    if (tid == 0) { head = 0; tail = 0; if (cb0) { queue[0] = cb0; tail = 1; } }
+    __syncthreads();
+    for (;;) {
+        if (tid == 0) lvl_end = tail;
+        __syncthreads();
+        const int lo = head, hi = lvl_end;
+        if (lo >= hi) break;
+        for (int qi = lo + tid; qi < hi; qi += nt) {
+            const int ob = queue[qi], nb = qi + 1;
+            for (int a = 0; a < A; ++a) {
+                const double tot = *total_ptr_rt(blocks, ob, a, A);
+                const int na = *na_ptr_rt(blocks, ob, a, A);
+                uint32_t lk = *link_ptr_rt(blocks, ob, a, A);
+                const int cb = (int)(lk & kLinkBlockMask);
+                if (cb != 0) {   // (a block has exactly one parent edge: its new index is assigned here)
+                    const int pos = atomicAdd(&tail, 1);
+                    queue[pos] = cb;
+                    lk = (lk & ~kLinkBlockMask) | (uint32_t)(pos + 1);
+                }
+                *total_ptr_rt(tblocks, nb, a, A) = tot;
+                *na_ptr_rt(tblocks, nb, a, A) = na;
+                *link_ptr_rt(tblocks, nb, a, A) = lk;
+                for (int k = 0; k < S; ++k) tstates[(long long)(nb * A + a) * S + k] = states[(long long)(ob * A + a) * S + k];
+                tg[(long long)nb * A + a] = gfirst[(long long)ob * A + a];
+            }
+        }
+        __syncthreads();
+        if (tid == 0) head = hi;
+        __syncthreads();
+    }
+    int n_new = tail;                  // blocks of the new tree: 1 .. n_new (none: the root has no edges yet)
+    if (n_new > max_blocks) n_new = 0; // (see above: too large to keep)
+    __syncthreads();
+    // back over the tree's own arena
+    const int new_alloc = (n_new > 0 ? n_new : 1) + 1;
+    for (int i = tid; i < (new_alloc * blk_bytes) / 16; i += nt) {
+        int4 v = make_int4(0, 0, 0, 0);
+        if (i >= blk_bytes / 16 && i < ((n_new + 1) * blk_bytes) / 16) v = reinterpret_cast<const int4*>(tblocks)[i];
+        reinterpret_cast<int4*>(blocks)[i] = v;
+    }
+    for (int i = (new_alloc * blk_bytes) / 16 + tid; i < (alloc * blk_bytes) / 16; i += nt) reinterpret_cast<int4*>(blocks)[i] = make_int4(0, 0, 0, 0);
+    for (long long i = tid; i < (long long)(n_new + 1) * A * S; i += nt) if (i < S || i >= (long long)A * S) states[i] = tstates[i];
+    for (long long i = (long long)A + tid; i < (long long)(n_new + 1) * A; i += nt) gfirst[i] = tg[i];
+    if (tid == 0) meta[META_ALLOC] = new_alloc;
+}
+
 template <int ENV, typename T>
 int launch_search(TptParams& p, bool scripted, int sm_count, int tpw_forced, cudaStream_t st) {
     constexpr int A = EnvTraits<ENV>::A;
@@ -986,6 +1068,35 @@ int tpt_run(isla_engine* e, int n_sim, long long scripted_tree, const uint8_t* k
         set_error("thread-per-tree kernel: env %d unsupported", e->cfg.env_id);
         return ISLA_ERR_INVALID;
     }
+}
+
+int tpt_reroot(isla_engine* e, const int32_t* action_dev, const uint8_t* alive_dev, int n_sim_next, cudaStream_t st) {
+    const isla_layout& L = e->lay;
+    const long long rb = L.real_bytes;
+    const long long tmp_stride = (L.slots_per_tree * (16 + L.state_dim * rb + 8) + 255) / 256 * 256;
+    const size_t need = (size_t)(e->cfg.n_trees * tmp_stride);
+    if (e->reroot_bytes < need) {
+        ISLA_CUDA_OK(cudaStreamSynchronize(st));
+        if (e->reroot_tmp) cudaFree(e->reroot_tmp);
+        e->reroot_tmp = nullptr; e->reroot_bytes = 0;
+        ISLA_CUDA_OK(cudaMalloc((void**)&e->reroot_tmp, need));
+        e->reroot_bytes = need;
+    }
+    const long long pvs = tpt_pv_stride((long long)e->cfg.sim_capacity + 2, L.n_actions);
+    if (pvs < (long long)(e->cfg.sim_capacity + 2) * 4) { set_error("reroot: PV scratch too small"); return ISLA_ERR_INVALID; }
+    const unsigned grid = (unsigned)e->cfg.n_trees;
+    const int max_blocks = e->cfg.sim_capacity - n_sim_next - 2, max_visits = e->cfg.sim_capacity - n_sim_next - 2;
+    if (max_blocks < 0) { set_error("reroot: sim_capacity %d leaves no room for %d more simulations", e->cfg.sim_capacity, n_sim_next); return ISLA_ERR_INVALID; }
+    if (rb == 4)
+        tpt_reroot_kernel<float><<<grid, 128, 0, st>>>(e->ws + L.rec_offset, (float*)(e->ws + L.state_offset), (double*)(e->ws + L.gfirst_offset),
+            (int32_t*)(e->ws + L.meta_offset), e->ws + L.path_offset, pvs, L.slots_per_tree, L.n_actions, L.state_dim, action_dev, alive_dev,
+            e->reroot_tmp, tmp_stride, e->cfg.n_trees, max_blocks, max_visits);
+    else
+        tpt_reroot_kernel<double><<<grid, 128, 0, st>>>(e->ws + L.rec_offset, (double*)(e->ws + L.state_offset), (double*)(e->ws + L.gfirst_offset),
+            (int32_t*)(e->ws + L.meta_offset), e->ws + L.path_offset, pvs, L.slots_per_tree, L.n_actions, L.state_dim, action_dev, alive_dev,
+            e->reroot_tmp, tmp_stride, e->cfg.n_trees, max_blocks, max_visits);
+    ISLA_CUDA_OK(cudaGetLastError());
+    return 0;
 }
 
 int tpt_root_stats(isla_engine* e, int64_t* na_dev, double* total_dev, cudaStream_t st) {

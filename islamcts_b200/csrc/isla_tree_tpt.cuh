@@ -78,6 +78,11 @@ template <int A> __device__ __forceinline__ uint32_t* link_ptr(char* base, int b
     return reinterpret_cast<uint32_t*>(base + (long long)blk * (A * 16) + A * 12) + a;
 }
 
+// the same accessors with the action count as a run-time value (epilogue / maintenance kernels)
+__device__ __forceinline__ double* total_ptr_rt(char* base, int blk, int a, int A) { return reinterpret_cast<double*>(base + (long long)blk * (A * 16)) + a; }
+__device__ __forceinline__ int32_t* na_ptr_rt(char* base, int blk, int a, int A) { return reinterpret_cast<int32_t*>(base + (long long)blk * (A * 16) + A * 8) + a; }
+__device__ __forceinline__ uint32_t* link_ptr_rt(char* base, int blk, int a, int A) { return reinterpret_cast<uint32_t*>(base + (long long)blk * (A * 16) + A * 12) + a; }
+
 // cp.async with the destination given as a 32-bit shared-window address
 __device__ __forceinline__ void cp_async16(unsigned smem, const void* g) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(g) : "memory");

@@ -169,6 +169,18 @@ class Engine:
                                                   C.c_void_p(_stream_ptr(self.device))))
         return out
 
+    def reroot(self, actions, n_sim_next: int, alive=None):
+        """Tree reuse (build extension): the subtree below root action actions[tree] becomes the tree (thread-per-tree
+        engine); the next run(n_sim_next) continues the search from the chosen child; a subtree too large for the workspace
+        is dropped (fresh root).  actions: int32 [n_trees] device tensor."""
+        a = torch.as_tensor(actions).to(self.device, torch.int32).contiguous()
+        al = None if alive is None else torch.as_tensor(alive).to(self.device, torch.uint8).contiguous()
+        self._keep = [a, al]
+        with torch.cuda.device(self.device):
+            check(self.lib.isla_engine_reroot(self._h, C.c_void_p(a.data_ptr()), C.c_void_p(al.data_ptr()) if al is not None else None,
+                                              int(n_sim_next), C.c_void_p(_stream_ptr(self.device))))
+        return self
+
     def best(self, scripted_pos: int = -1):
         """End of fit(): (rank in root.actions, action value) per tree -- device tensors (int32, float64;
         the action is [n_trees, 2] for the continuous CurveEnv box)."""

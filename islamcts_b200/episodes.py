@@ -22,15 +22,22 @@ from ._lib import check
 class EpisodeBatch:
     def __init__(self, env: str | int, agent: int = _lib.AGENT_VANILLA, n_episodes: int = 100, n_sim: int = 1000,
                  max_steps: int = 100, seed: int = 0, device="cuda:0", action_grid=None, timeout_reward: float | None = -1000.0,
-                 **engine_kwargs):
+                 reuse_tree: bool = False, **engine_kwargs):
         self.env_id = E.ENV_NAMES[env] if isinstance(env, str) else int(env)
         self.device = torch.device(device)
         self.n, self.n_sim, self.max_steps, self.seed = int(n_episodes), int(n_sim), int(max_steps), int(seed)
         self.grid = tuple(int(x) for x in action_grid) if action_grid else (0, 0)
         # the reference's loop books reward = -1000 for the step that reaches the limit (sweep.py:206-209); None = env reward
         self.timeout_reward = float("nan") if timeout_reward is None else float(timeout_reward)
-        self.engine = E.Engine(self.env_id, agent=agent, n_trees=self.n, sim_capacity=self.n_sim, seed=seed, device=device,
-                               action_grid=action_grid, **engine_kwargs)
+        # reuse_tree (opt-in build extension): instead of a fresh tree per real step (the reference's loop, sweep.py:186 --
+        # the default here), the subtree below the chosen root action is kept and searched on (isla_engine_reroot;
+        # thread-per-tree engine: vanilla search on CartPole / FrozenLake).  The search then continues from the state the
+        # TREE stored for that child (computed in the search's precision), the real env advances in float64 beside it.
+        self.reuse_tree = bool(reuse_tree)
+        if self.reuse_tree:
+            engine_kwargs.setdefault("kernel", _lib.KERNEL_THREAD_PER_TREE)
+        self.engine = E.Engine(self.env_id, agent=agent, n_trees=self.n, sim_capacity=self.n_sim * (8 if self.reuse_tree else 1) + 2,
+                               seed=seed, device=device, action_grid=action_grid, **engine_kwargs)
         self.S = E.STATE_DIM[self.env_id]
 
     def run(self, initial_states, check_every: int = 8) -> dict:
@@ -43,8 +50,11 @@ class EpisodeBatch:
         steps = torch.zeros(self.n, dtype=torch.int32, device=dev)
         actions = []
         for k in range(self.max_steps):
-            eng.reseed(self.seed + k, 0)                       # every real step searches with its own streams
-            eng.set_roots(states)
+            if self.reuse_tree and k > 0:
+                eng.reroot(act.to(torch.int32), self.n_sim)    # keep the subtree below the action just played (every tree)
+            else:
+                eng.reseed(self.seed + k, 0)                   # every real step searches with its own streams
+                eng.set_roots(states)
             eng.run(self.n_sim)
             _, act = eng.best()
             actions.append(act)

@@ -50,6 +50,8 @@ def argument_parser():
     p.add_argument('--max_steps', default=100, type=int, help='real steps per episode (the reference stops at 100, sweep.py:206)')
     p.add_argument('--timeout_reward', default=-1000.0, type=float,
                    help='reward booked for the step that reaches --max_steps (the reference: -1000, sweep.py:206-209)')
+    p.add_argument('--reuse_tree', action='store_true',
+                   help='--lockstep only: keep the subtree below the action played instead of a fresh tree per real step (vanilla)')
     p.add_argument('--lockstep', action='store_true',
                    help='advance all --n_episodes episodes together on the device (islamcts_b200.episodes.EpisodeBatch)')
     return p
@@ -138,7 +140,9 @@ def run_lockstep(args):
         states = np.stack(rows)
     t0 = time.time()
     out = EpisodeBatch(env_id, agent=agent, n_episodes=n, n_sim=args["nsim"], max_steps=args["max_steps"], seed=seed,
-                       action_grid=grid, timeout_reward=args["timeout_reward"], **kw).run(states)
+                       action_grid=grid, timeout_reward=args["timeout_reward"],
+                       reuse_tree=args["reuse_tree"] and algo == "vanilla" and env_id in (_lib.ENV_CARTPOLE, _lib.ENV_FROZENLAKE),
+                       **kw).run(states)
     dt = time.time() - t0
     print(json.dumps({"episodes": n, "real_steps": out["real_steps"], "seconds": dt, "real_steps_per_s": out["real_steps"] / dt,
                       "mean_reward": float(out["total_reward"].mean()), "max_reward": float(out["total_reward"].max()),

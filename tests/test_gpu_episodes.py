@@ -66,3 +66,62 @@ def test_curve_episodes_apw_box_and_vanilla_grid():
     np.testing.assert_array_equal(out["n_steps"], esteps)
     np.testing.assert_allclose(out["total_reward"], etot, rtol=1e-12)
     np.testing.assert_allclose(out["states"], estates, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("env_id,n_actions,prec", [(0, 2, 1), (0, 2, 0), (3, 4, 1)])
+def test_reroot_keeps_the_chosen_subtree_bit_for_bit(env_id, n_actions, prec):
+    """Tree reuse (opt-in build extension): isla_engine_reroot turns the subtree below the chosen root
+    action into the tree.  Its DFS serialisation must be the old tree's subtree exactly -- every count, total, flag and
+    action, one level up -- and the search continues on it: the root's visits are the kept ones plus the new simulations."""
+    import torch
+    from islamcts_b200.engine import Engine
+    n_trees, n_sim = 12, 260
+    roots = np.stack([coracle.env_reset(env_id, 4, i) for i in range(n_trees)])
+    eng = Engine(env_id, n_trees=n_trees, sim_capacity=2 * n_sim + 2, max_depth=60, C_=1.0 if env_id == 0 else 0.5, gamma=0.97,
+                 precision=prec, kernel=1, seed=8)
+    eng.set_roots(roots).run(n_sim)
+    old = [eng.export_tree(i) for i in range(n_trees)]
+    _, act = eng.best()
+    actions = act.to(torch.int32)
+    actions[1] = (actions[1] + 1) % n_actions            # not only arg-max edges
+    eng.reroot(actions, n_sim)
+    assert eng.counters()["faults"] == 0
+    kept = []
+    for i in range(n_trees):
+        o, n = old[i], eng.export_tree(i)
+        a = int(actions[i])
+        # the old tree's records below root action a: from its action record (exclusive) to the next depth-0 action record
+        top = np.flatnonzero((o["kind"] == 1) & (o["depth"] == 0))
+        j = top[list(o["action"][top]).index(float(a))]
+        nxt = top[top > j]
+        lo, hi = j + 1, (nxt[0] if len(nxt) else len(o["kind"]))
+        if hi - lo <= 1 or o["terminal"][lo]:            # a leaf / terminal child: the new tree is a bare root
+            assert len(n["kind"]) == 1 and n["count"][0] == 0
+            kept.append(0)
+            continue
+        for k in ("kind", "terminal", "fanout"):
+            np.testing.assert_array_equal(n[k][1:], o[k][lo + 1:hi])
+        np.testing.assert_array_equal(n["depth"][1:], o["depth"][lo + 1:hi] - 1)
+        np.testing.assert_array_equal(n["count"][1:], o["count"][lo + 1:hi])
+        assert np.array_equal(n["total"][1:], o["total"][lo + 1:hi])           # bit for bit
+        np.testing.assert_array_equal(n["action"][1:], o["action"][lo + 1:hi])
+        assert n["count"][0] == o["count"][lo] - 1       # the re-rooted node is a root now: ns = sum of its edges' visits
+        kept.append(int(n["count"][0]))
+    eng.run(n_sim)
+    assert eng.counters()["faults"] == 0
+    na, _ = eng.root_stats()
+    np.testing.assert_array_equal(na.sum(dim=1).cpu().numpy(), np.array(kept) + n_sim)
+
+
+def test_episodes_with_tree_reuse_run_to_the_end():
+    from islamcts_b200.episodes import EpisodeBatch
+    n, n_sim, max_steps = 24, 200, 12
+    states = np.stack([coracle.env_reset(0, 900, i) for i in range(n)])
+    out = {}
+    for reuse in (False, True):
+        eb = EpisodeBatch("CartPole-v1", n_episodes=n, n_sim=n_sim, max_steps=max_steps, seed=5, max_depth=60, C_=1.0, gamma=0.97,
+                          reuse_tree=reuse, timeout_reward=None)
+        out[reuse] = eb.run(states)
+        assert (out[reuse]["total_reward"] == out[reuse]["n_steps"]).all()      # CartPole pays 1 per real step
+    # kept subtrees cannot make the balancing worse than chance; both modes keep most episodes alive over 12 steps
+    assert out[True]["n_steps"].mean() >= 0.8 * out[False]["n_steps"].mean()
