@@ -50,8 +50,13 @@ namespace {
 //   3   return pass                G_l = r + gamma G_{l+1} written to the tree's pending-return row
 // The decisions are those of the sequential algorithm: a level's UCB sees exactly the statistics an eager backup
 // would have produced; draws happen only in 1b, in path order.
-template <int ENV, typename T, bool SCRIPTED>
+// COOP = false compiles the kernel WITHOUT the PV cache and the cooperative phase: every simulation descends from the root
+// on the node blocks and backs its return up eagerly (the same additions in the same order, so the same trees).  Used for
+// shallow trees that never reach the cooperative threshold (FrozenLake: paths of <= ~10 levels) and for scripted replays:
+// no ring in shared memory, no per-level cache traffic, fewer registers.
+template <int ENV, typename T, bool SCRIPTED, bool COOP>
 __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kernel(const TptParams p) {
+    static_assert(!(SCRIPTED && COOP), "scripted replays descend from the root");
     constexpr int A = EnvTraits<ENV>::A;
     constexpr int S = EnvTraits<ENV>::S;
     constexpr double kInterior = Rewards<ENV>::kInterior;
@@ -226,11 +231,12 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
         // ------------------------------------------------------------------ phase 1a: cooperative verification
         // (shallow trees -- FrozenLake, the first simulations -- have nothing to verify in parallel: their cache is
         //  written back at once and the descent starts at the root)
+        if constexpr (COOP) {
         if (live && pend && plen >= p.ret_K) write_back(0);   // deeper than the return table: no cooperative pass (rare)
         int warp_max_plen = (live && pend) ? plen : 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) warp_max_plen = max(warp_max_plen, __shfl_xor_sync(kFull, warp_max_plen, o));
-        if (SCRIPTED || warp_max_plen < ((p.tuning & 2) ? 1 : kCoopMin)) {   // tuning bit 1: verify cooperatively at any depth (tests)
+        if (warp_max_plen < ((p.tuning & 2) ? 1 : kCoopMin)) {   // tuning bit 2: verify cooperatively at any depth (tests)
             if (live && plen > 0) write_back(0);
         } else {
             // The rounds of all 32 trees form ONE sequence of tasks (tree j, levels l0..l0+31).  A producer cursor runs
@@ -516,6 +522,7 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
             cp_async_wait<0>();
 #endif
         }
+        }   // COOP
 
         PHASE_ADD(t_1a);
         // ------------------------------------------------------------------ phase 1b: serial continuation
@@ -593,8 +600,10 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                                 }
                             }
                             sb.own_base = on_ - (int)sims_done;   // na with the pending return added = own_base + sims_done
-                            store_sta<A>(PC::sta(pv, level), sb);
-                            __stcg(PC::tot(pv, level), ot);
+                            if constexpr (COOP) {
+                                store_sta<A>(PC::sta(pv, level), sb);
+                                __stcg(PC::tot(pv, level), ot);
+                            }
                             __stcg(PC::edge(pv, level), ((uint32_t)blk << 2) | (uint32_t)a_sel);
                         }
                         ++level;
@@ -724,7 +733,19 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
         // adds them to the cached statistics (lazy backup).
         if (mode == MODE_RETURN) {
             c_levels += (unsigned)level + 1u;
-            pend = level > 0;
+            if constexpr (COOP) {
+                pend = level > 0;
+            } else {
+                // eager backup along the recorded edges: total += G_l, na += 1 (the leaf edge itself was updated above)
+                for (int l = level - 1; l >= 0; --l) {
+                    const uint32_t e = __ldcg(PC::edge(pv, l));
+                    double* const tp = total_ptr<A>(blocks, (int)(e >> 2), (int)(e & 3u));
+                    int32_t* const np = na_ptr<A>(blocks, (int)(e >> 2), (int)(e & 3u));
+                    __stcg(tp, __dadd_rn(__ldcg(tp), ret_value(ret_j, level - l)));
+                    __stcg(np, __ldcg(np) + 1);
+                }
+                plen = 0; pend = false;
+            }
             ++sims_done; ++s_done;
         }
         __syncwarp();
@@ -947,10 +968,12 @@ __global__ void __launch_bounds__(128) tpt_reroot_kernel(char* blocks_all, T* st
 template <int ENV, typename T>
 int launch_search(TptParams& p, bool scripted, int sm_count, int tpw_forced, cudaStream_t st) {
     constexpr int A = EnvTraits<ENV>::A;
-    const size_t smem = (p.ln_in_smem ? (size_t)((p.ln_count + 3) & ~3) * 4 : 0) + (size_t)(kTptBlock / 32) * CoopRing<A>::kWarpBytes;
+    // FrozenLake's trees are too shallow for the cooperative phase (tuning bit 2 forces it: tests)
+    const bool coop = !scripted && (ENV != ENV_FROZENLAKE || (p.tuning & 2));
+    const size_t smem = (p.ln_in_smem ? (size_t)((p.ln_count + 3) & ~3) * 4 : 0) + (coop ? (size_t)(kTptBlock / 32) * CoopRing<A>::kWarpBytes : 0);
     if (scripted) {
         p.tpw = 1;
-        tpt_search_kernel<ENV, T, true><<<1, 32, smem, st>>>(p);
+        tpt_search_kernel<ENV, T, true, false><<<1, 32, smem, st>>>(p);
     } else {
         // Trees per warp.  A launch is bound by the serial instruction stream of a warp, and the phases that run one
         // lane per tree (serial continuation, expansion, rollout) cost the same for 1 or 32 busy lanes: so as many
@@ -958,7 +981,9 @@ int launch_search(TptParams& p, bool scripted, int sm_count, int tpw_forced, cud
         // rounded up (8192 trees: 4, 16 384: 7, 65 536: 28 on a B200 at 8 CTAs per SM); batches beyond 32 trees per
         // resident warp run in equal waves.  Measured: profiles/README.md (round 2).
         int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tpt_search_kernel<ENV, T, false>, kTptBlock, smem) != cudaSuccess || occ < 1) {
+        const cudaError_t oe = coop ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tpt_search_kernel<ENV, T, false, true>, kTptBlock, smem)
+                                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tpt_search_kernel<ENV, T, false, false>, kTptBlock, smem);
+        if (oe != cudaSuccess || occ < 1) {
             cudaGetLastError();
             occ = ISLA_TPT_MINBLOCKS;
         }
@@ -970,7 +995,8 @@ int launch_search(TptParams& p, bool scripted, int sm_count, int tpw_forced, cud
         p.tpw = (int)(tpw < 1 ? 1 : (tpw > 32 ? 32 : tpw));
         const int kTreesPerBlock = (kTptBlock / 32) * p.tpw;
         const unsigned grid = (unsigned)((p.n_trees + kTreesPerBlock - 1) / kTreesPerBlock);
-        tpt_search_kernel<ENV, T, false><<<grid, kTptBlock, smem, st>>>(p);
+        if (coop) tpt_search_kernel<ENV, T, false, true><<<grid, kTptBlock, smem, st>>>(p);
+        else tpt_search_kernel<ENV, T, false, false><<<grid, kTptBlock, smem, st>>>(p);
     }
     const cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? 0 : cuda_fail(err, "tpt_search_kernel launch");
