@@ -61,6 +61,20 @@ def lake_transition_noise(env, n: int):
     return np.asarray(copy.deepcopy(rng).random(int(n)), dtype=np.float64)
 
 
+def observation_of(env_id: int, state) -> Any:
+    """The observation the reference's env returns for the engine's env state (what node.data holds and what the
+    children dicts are keyed with): CartPole / MountainCar float32 state, Pendulum (cos, sin, thetadot) float32,
+    FrozenLake the cell as an int, CurveEnv the car's float64 (x, y, velocity, angle)."""
+    s = np.asarray(state, dtype=np.float64).reshape(-1)
+    if env_id == _lib.ENV_FROZENLAKE:
+        return int(s[0])
+    if env_id == _lib.ENV_PENDULUM:
+        return np.array([np.cos(s[0]), np.sin(s[0]), s[1]], dtype=np.float32)
+    if env_id == _lib.ENV_CURVE:
+        return np.array(s[:4], dtype=np.float64)
+    return np.asarray(s[: STATE_DIM[env_id]], dtype=np.float32)
+
+
 def env_action_info(env, env_id: int):
     """(number of discrete actions or 0, DiscreteCurveEnv grid or None) of the env object."""
     if env_id != _lib.ENV_CURVE:
@@ -253,6 +267,7 @@ class AbstractMcts:
     AGENT = _lib.AGENT_VANILLA
     HEAD_ZERO_ROLLOUTS = True      # Mcts/APW/SPW/DPW start the recursion at max_depth
     DISCRETE = True
+    HASH_KEYS = True               # children keyed by observation.tobytes() (mcts_hash.py:97); Mcts keys by the observation
 
     def __init__(self, param: MctsParameters):
         self.param = param
@@ -480,6 +495,8 @@ class AbstractMcts:
         kind, depth, count, total = ser["kind"], ser["depth"], ser["count"], ser["total"]
         term, action = ser["terminal"], ser["action"]
         action2 = ser.get("action2") if getattr(self._engine, "action_dim", 1) == 2 else None
+        states = ser.get("state")
+        env_id = self._engine.env_id
         root = self._make_state(self._root_stub.data)
         root.ns, root.total = int(count[0]), float(total[0])
         stack = [(root, 0)]              # (node object, depth) of the open state nodes
@@ -504,11 +521,19 @@ class AbstractMcts:
                 parent.actions[key] = node
                 action_at[int(depth[i])] = node
             else:                        # state node: a child of the action node last emitted one level up (an action node
-                                         # has several on a stochastic env; keyed by position: the export carries no observation)
-                st = self._make_state(None)
+                                         # has several on a stochastic env), keyed like the reference keys its children
+                                         # dict: by the observation (Mcts) or observation.tobytes() (the *Hash agents)
+                obs = observation_of(env_id, states[i]) if states is not None else None
+                st = self._make_state(obs)
                 st.ns, st.total, st.terminal = int(count[i]), float(total[i]), bool(term[i])
                 owner = action_at[int(depth[i]) - 1]
-                owner.children[len(owner.children)] = st
+                if obs is None:
+                    key = len(owner.children)
+                elif self.HASH_KEYS and hasattr(obs, "tobytes"):
+                    key = obs.tobytes()
+                else:
+                    key = obs if not isinstance(obs, np.ndarray) else obs.tobytes()
+                owner.children[key] = st
                 while stack[-1][1] >= depth[i]:
                     stack.pop()
                 stack.append((st, int(depth[i])))

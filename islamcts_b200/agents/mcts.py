@@ -9,3 +9,4 @@ class Mcts(AbstractMcts):
     ``max_depth`` so its rollouts have zero length (``depth_mode="reference_head"``); the default
     ``depth_mode="budgeted"`` plays them to ``max_depth`` as north_star asks."""
     HEAD_ZERO_ROLLOUTS = True
+    HASH_KEYS = False              # children[observation] (agents/mcts.py:83-84), not observation.tobytes()

@@ -278,13 +278,13 @@ class Engine:
     def export_tree(self, tree: int = 0) -> dict:
         """Canonical DFS serialisation (same format as oracle/trace.py) decoded on the host."""
         if self.layout.kernel == _lib.KERNEL_THREAD_PER_TREE:
-            return _export_tpt(self.raw_blocks(tree), self.raw_gfirst(tree), self.n_actions)
+            return _export_tpt(self.raw_blocks(tree), self.raw_gfirst(tree), self.n_actions, self.raw_states(tree))
         from .tree_export import export_pool  # CTA-per-tree general pools
         return export_pool(self, tree)
 
 
-def _export_tpt(blocks: np.ndarray, gfirst: np.ndarray, A: int) -> dict:
-    kinds, depths, counts, totals, terms, fans, acts = [], [], [], [], [], [], []
+def _export_tpt(blocks: np.ndarray, gfirst: np.ndarray, A: int, states: np.ndarray | None = None) -> dict:
+    kinds, depths, counts, totals, terms, fans, acts, slots = [], [], [], [], [], [], [], []
 
     def children(block):
         """visited edges of a block in insertion (rank) order -> list of (action, na, total, link)"""
@@ -313,17 +313,24 @@ def _export_tpt(blocks: np.ndarray, gfirst: np.ndarray, A: int) -> dict:
                     ns = 1 + sum(c[1] for c in ch)
                     tot = float(gfirst[slot]) + float(sum(c[2] for c in ch))
             kinds.append(0); depths.append(d); counts.append(ns); totals.append(tot); terms.append(term)
-            fans.append(len(ch)); acts.append(0.0)
+            fans.append(len(ch)); acts.append(0.0); slots.append(0 if edge is None else edge[4])
             for c in reversed(ch):
                 stack.append(("A", c, d))
         else:
             a, na, total, link, slot = edge
             kinds.append(1); depths.append(d); counts.append(na); totals.append(total)
-            terms.append(0); fans.append(1); acts.append(float(a))
+            terms.append(0); fans.append(1); acts.append(float(a)); slots.append(-1)
             stack.append(("S", edge, d + 1))
-    return dict(kind=np.asarray(kinds, np.uint8), depth=np.asarray(depths, np.int32), count=np.asarray(counts, np.int64),
-                total=np.asarray(totals, np.float64), terminal=np.asarray(terms, np.uint8),
-                fanout=np.asarray(fans, np.int32), action=np.asarray(acts, np.float64))
+    out = dict(kind=np.asarray(kinds, np.uint8), depth=np.asarray(depths, np.int32), count=np.asarray(counts, np.int64),
+               total=np.asarray(totals, np.float64), terminal=np.asarray(terms, np.uint8),
+               fanout=np.asarray(fans, np.int32), action=np.asarray(acts, np.float64))
+    if states is not None:
+        # env state of every state record (the slot of the edge that leads to it; the root's is slot 0); action records: 0
+        sl = np.asarray(slots, np.int64)
+        st = np.zeros((len(sl), states.shape[1]), dtype=np.float64)
+        st[sl >= 0] = states[sl[sl >= 0]]
+        out["state"] = st
+    return out
 
 
 # ---------------------------------------------------------------------- stateless batched primitives

@@ -31,7 +31,7 @@ def read_pool(engine, tree: int) -> dict:
 
 def export_pool(engine, tree: int = 0) -> dict:
     P = read_pool(engine, tree)
-    kinds, depths, counts, totals, terms, fans, acts, acts2 = [], [], [], [], [], [], [], []
+    kinds, depths, counts, totals, terms, fans, acts, acts2, sidx = [], [], [], [], [], [], [], [], []
     two = engine.action_dim == 2
     stack = [(0, 0, 0)]  # (kind, index, depth)
     while stack:
@@ -39,7 +39,7 @@ def export_pool(engine, tree: int = 0) -> dict:
         if kind == 0:
             n = int(P["s_ccnt"][idx]); off = int(P["s_coff"][idx])
             kinds.append(0); depths.append(d); counts.append(int(P["s_ns"][idx])); totals.append(float(P["s_total"][idx]))
-            terms.append(int(P["s_flags"][idx] & 1)); fans.append(n); acts.append(0.0); acts2.append(0.0)
+            terms.append(int(P["s_flags"][idx] & 1)); fans.append(n); acts.append(0.0); acts2.append(0.0); sidx.append(idx)
             for i in range(n - 1, -1, -1):
                 stack.append((1, int(P["ipool"][off + i]), d))
         else:
@@ -50,10 +50,14 @@ def export_pool(engine, tree: int = 0) -> dict:
                 kids.append(c)
                 c = int(P["s_next"][c])
             kinds.append(1); depths.append(d); counts.append(int(P["a_na"][idx])); totals.append(float(P["a_total"][idx]))
-            terms.append(0); fans.append(len(kids)); acts.append(float(P["a_value"][idx]))
+            terms.append(0); fans.append(len(kids)); acts.append(float(P["a_value"][idx])); sidx.append(-1)
             acts2.append(float(P["a_value2"][idx]) if two else 0.0)
             for c in reversed(kids):
                 stack.append((0, c, d + 1))
+    si = np.asarray(sidx, np.int64)
+    st = np.zeros((len(si), P["s_state"].shape[1]), dtype=np.float64)
+    st[si >= 0] = P["s_state"][si[si >= 0]]          # env state of every state record (action records: 0)
     return dict(kind=np.asarray(kinds, np.uint8), depth=np.asarray(depths, np.int32), count=np.asarray(counts, np.int64),
                 total=np.asarray(totals, np.float64), terminal=np.asarray(terms, np.uint8),
-                fanout=np.asarray(fans, np.int32), action=np.asarray(acts, np.float64), action2=np.asarray(acts2, np.float64))
+                fanout=np.asarray(fans, np.int32), action=np.asarray(acts, np.float64), action2=np.asarray(acts2, np.float64),
+                state=st)

@@ -384,3 +384,30 @@ def test_spw_agent_on_slippery_lake_steps_the_live_env():
     assert steps >= 300
     before.random(int(steps))
     assert env.np_random.random() == before.random()               # the live generator moved by exactly the search's steps
+
+
+def test_proxy_children_are_keyed_like_the_reference():
+    """action_node.children is a dict keyed by observation.tobytes() in the *Hash agents (mcts_hash.py:97) and by the
+    observation itself in Mcts (agents/mcts.py:83-84); child.data is that observation (round-1 advisor finding: the
+    proxies keyed children by position)."""
+    from islamcts_b200 import envs
+    from islamcts_b200.agents import Mcts, MctsHash
+    from islamcts_b200.agents.parameters.mcts_parameters import MctsParameters
+    from islamcts_b200.utils.action_selection_functions import continuous_default_policy, ucb1
+    env = envs.make("CartPole-v1", api=4, seed=2)
+    obs = env.reset()
+    ag = MctsHash(MctsParameters(root_data=obs, env=env.unwrapped, n_sim=200, C=1, action_selection_fn=ucb1, gamma=0.95,
+                                 rollout_selection_fn=continuous_default_policy, max_depth=50, n_actions=2, seed=4))
+    a = ag.fit()
+    node = ag.root.actions[int(a)]
+    nxt_obs, _, _, _ = env.step(a)                                   # the real env, float64 dynamics
+    (key, child), = node.children.items()
+    assert isinstance(key, bytes) and child.data.dtype == np.float32 and key == child.data.tobytes()
+    np.testing.assert_allclose(child.data, nxt_obs, rtol=1e-5, atol=1e-6)      # same observation up to float32 env rounding
+    lake = envs.make("FrozenLake-v1", api=5, seed=0)
+    o, _ = lake.reset()
+    m = Mcts(MctsParameters(root_data=o, env=lake.unwrapped, n_sim=60, C=0.5, action_selection_fn=ucb1, gamma=1.0,
+                            rollout_selection_fn=continuous_default_policy, max_depth=50, n_actions=4, seed=1, depth_mode="budgeted"))
+    m.fit()
+    right = m.root.actions[2]
+    assert list(right.children.keys()) == [1] and right.children[1].data == 1   # RIGHT from cell 0 leads to cell 1
