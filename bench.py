@@ -493,7 +493,7 @@ def other_configs(dev):
         steps = []
         def run_curve():
             ret, st = E.rollout(_lib.ENV_CURVE, poses, budget=500, gamma=0.95, seed=1234, sim=0, device=dev, action_grid=grid)
-            steps.append(st)
+            steps[:] = [st]
         t = timeit(run_curve, reps=3)
         total = int(steps[-1].sum().item())
         out[name] = {"trajectories": n, "env_steps_per_s": total / t, "mean_len": total / n, "ms": t * 1e3}
@@ -522,7 +522,7 @@ def other_configs(dev):
         steps = []
         def run():
             ret, st = E.rollout(env_id, None, n=n, budget=budget, gamma=gamma, seed=1234, sim=0, device=dev)
-            steps.append(st)
+            steps[:] = [st]
         t = timeit(run, reps=5)
         total = int(steps[-1].sum().item())
         out["rollout_" + name] = {"trajectories": n, "env_steps_per_s": total / t, "mean_len": total / n, "ms": t * 1e3,

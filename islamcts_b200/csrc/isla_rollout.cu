@@ -69,10 +69,20 @@ __global__ void __launch_bounds__(256) rollout_kernel_simple(const T* __restrict
     steps[i] = t;
 }
 
-// Persistent warps with lane refill: random-policy episodes have random lengths (CartPole: mean 22 steps, maximum over a
-// warp ~56), so a lane that finishes claims the next trajectory instead of idling.  Refills are batched (>= kRefillMin
-// idle lanes, warp-aggregated atomic) so that the refill code does not run in every iteration.
-constexpr int kRefillMin = 12;
+// Persistent warps for random-length episodes (CartPole under the random policy: mean 22 steps, maximum over a warp ~56).
+// A lane that finishes takes another trajectory instead of idling.  Starting a trajectory costs two Philox blocks (the
+// reset draw and the first 128 action bits) -- more than two env steps -- so starts are PRODUCED with all 32 lanes busy,
+// 32 at a time, into a per-warp queue in shared memory {start state, first action block, trajectory id}; taking one is two
+// LDS.  The warp meets every kInner env steps: finished lanes store their result and take the next queued start (rank by
+// ballot, no atomics), and the queue is topped up when it has room for 32 more (one global atomic per 32 trajectories).
+// Between meetings there is no warp-level instruction at all; a lane that finishes mid-way idles < kInner steps.
+// (Round 1 met after EVERY step and started trajectories with whatever lanes were waiting, >= 12: 104 warp instructions
+// per env step at 22 of 32 lanes busy; see profiles/README.md for the ncu numbers of both.)
+#ifndef ISLA_ROLL_INNER
+#define ISLA_ROLL_INNER 8
+#endif
+constexpr int kInner = ISLA_ROLL_INNER;
+constexpr int kQueue = 64;   // queued starts per warp (two productions)
 
 template <int ENV, typename T>
 __global__ void __launch_bounds__(256) rollout_kernel(const T* __restrict__ states, long long n, int budget, double gamma,
@@ -81,9 +91,15 @@ __global__ void __launch_bounds__(256) rollout_kernel(const T* __restrict__ stat
                                                       int32_t* __restrict__ steps, unsigned long long* __restrict__ next) {
     constexpr int S = EnvTraits<ENV>::S;
     constexpr unsigned kFull = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    long long idx = -1;
-    bool active = false, exhausted = false;
+    __shared__ T q_state[8][kQueue][S];
+    __shared__ uint32_t q_bits[8][kQueue][4];
+    __shared__ uint32_t q_idx[8][kQueue];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned head = 0, tail = 0;          // warp-uniform: queue positions (slot = position % kQueue)
+    bool exhausted = false;               // warp-uniform: no trajectory left to claim
+    bool active = false, pending = false; // pending: finished, result not stored yet
+    uint32_t idx = 0;
     T s[S];
 #pragma unroll
     for (int k = 0; k < S; ++k) s[k] = T(0);
@@ -93,44 +109,77 @@ __global__ void __launch_bounds__(256) rollout_kernel(const T* __restrict__ stat
     double R = 0.0;
     T last_r = T(0);
     for (;;) {
-        const unsigned idle = __ballot_sync(kFull, !active);
-        if (!exhausted && (idle == kFull || __popc(idle) >= kRefillMin)) {
-            const int nidle = __popc(idle);
+        if (pending) {
+            if constexpr (Rewards<ENV>::kClosedForm) R = Rewards<ENV>::rollout_return(t, (double)last_r, disc_table, cum_table);
+            returns[idx] = R;
+            steps[idx] = t;
+            pending = false;
+        }
+        if (!exhausted && tail - head <= (unsigned)(kQueue - 32)) {
+            __syncwarp();                                                    // every lane is done reading the slots reused below
             unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(next, (unsigned long long)nidle);  // warp-aggregated claim
+            if (lane == 0) base = atomicAdd(next, 32ull);
             base = __shfl_sync(kFull, base, 0);
-            if (!active) {
-                const long long mine = (long long)base + __popc(idle & ((1u << lane) - 1u));
-                if (mine < n) {
-                    idx = mine;
-                    if (states) {
+            const long long mine = (long long)base + lane;
+            if (mine < n) {
+                const int slot = (int)((tail + (unsigned)lane) % kQueue);
+                T st0[S];
+                if (states) {
 #pragma unroll
-                        for (int k = 0; k < S; ++k) s[k] = states[idx * S + k];
-                    } else {
-                        env_reset<ENV, T>(seed, (uint32_t)idx, s);
-                    }
-                    rs.init(seed, sim, (uint32_t)idx, 0u);
+                    for (int k = 0; k < S; ++k) st0[k] = states[mine * S + k];
+                } else {
+                    env_reset<ENV, T>(seed, (uint32_t)mine, st0);
+                }
+                uint32_t b[4];
+                philox4x32_10(0u, sim, (uint32_t)mine, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), b);   // block 0 of its action stream
+#pragma unroll
+                for (int k = 0; k < S; ++k) q_state[w][slot][k] = st0[k];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) q_bits[w][slot][k] = b[k];
+                q_idx[w][slot] = (uint32_t)mine;
+            }
+            const long long left = n - (long long)base;
+            tail += left >= 32 ? 32u : left > 0 ? (unsigned)left : 0u;
+            exhausted = left <= 32;
+            __syncwarp();
+        }
+        const unsigned want = __ballot_sync(kFull, !active);
+        if (want != 0u && head != tail) {
+            if (!active) {
+                const unsigned k = head + __popc(want & lt);
+                if ((int)(tail - k) > 0) {
+                    const int slot = (int)(k % kQueue);
+#pragma unroll
+                    for (int q = 0; q < S; ++q) s[q] = q_state[w][slot][q];
+                    idx = q_idx[w][slot];
+                    rs.init(seed, sim, idx, 0u);
+                    rs.blk = 1u; rs.idx = 0;                                 // its first block was drawn by the producer
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) rs.buf[q] = q_bits[w][slot][q];
                     t = 0; R = 0.0; last_r = T(0);
-                    active = true;
+                    active = budget > 0;
+                    pending = !active;
                 }
             }
-            exhausted = (long long)base + nidle >= n;
+            const unsigned avail = tail - head, nw = (unsigned)__popc(want);
+            head += nw < avail ? nw : avail;
         }
-        if (__ballot_sync(kFull, active) == 0u) break;
-        if (active) {
-            bool fin = t >= budget;
-            if (!fin) {
+        if (__ballot_sync(kFull, active || pending) == 0u) {
+            if (exhausted && head == tail) break;
+            continue;
+        }
+#if ISLA_ROLL_NOUNROLL
+#pragma unroll 1
+#else
+#pragma unroll
+#endif
+        for (int u = 0; u < kInner; ++u) {
+            if (active) {
                 const T a = sample_action<ENV, T>(rs);
                 const bool done = Env<ENV, T>::step(s, a, last_r);
                 if constexpr (!Rewards<ENV>::kClosedForm) R = __dadd_rn(R, __dmul_rn((double)last_r, __ldg(disc_table + t)));  // r * pow(gamma, t)
                 ++t;
-                fin = done || t >= budget;
-            }
-            if (fin) {
-                if constexpr (Rewards<ENV>::kClosedForm) R = Rewards<ENV>::rollout_return(t, (double)last_r, disc_table, cum_table);
-                returns[idx] = R;
-                steps[idx] = t;
-                active = false;
+                if (done || t >= budget) { active = false; pending = true; }
             }
         }
     }
@@ -306,14 +355,39 @@ static int get_tables(double gamma, int budget, const double** disc, const doubl
     return 0;
 }
 
+// Claim counters of the persistent rollout kernels: one ring of kClaimSlots counters per device, allocated once.  A launch
+// takes the next slot and zeroes it on its own stream (so up to kClaimSlots rollout launches may be in flight at once).
+// A cudaMallocAsync / cudaFreeAsync pair per call cost 0.3-4 ms whenever the pool had been trimmed at a synchronise --
+// more than the 1.1 ms kernel it served.
+constexpr int kClaimSlots = 256;
+struct ClaimRing { int dev; unsigned long long* ptr; unsigned nextslot; };
+static std::vector<ClaimRing> g_claims;
+
+static int claim_counter(unsigned long long** out, cudaStream_t st) {
+    int dev = 0;
+    ISLA_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    ClaimRing* ring = nullptr;
+    for (ClaimRing& r : g_claims)
+        if (r.dev == dev) ring = &r;
+    if (!ring) {
+        unsigned long long* p = nullptr;
+        ISLA_CUDA_OK(cudaMalloc((void**)&p, kClaimSlots * sizeof(unsigned long long)));
+        g_claims.push_back(ClaimRing{dev, p, 0u});
+        ring = &g_claims.back();
+    }
+    *out = ring->ptr + (ring->nextslot++ % kClaimSlots);
+    ISLA_CUDA_OK(cudaMemsetAsync(*out, 0, sizeof(unsigned long long), st));
+    return 0;
+}
+
 template <int ENV, typename T>
 int rollout_launch(const void* s, long long n, int budget, double gamma, unsigned long long seed, unsigned sim, ActionGrid ag,
                    const double* disc, const double* cum, double* ret, int32_t* steps, int sms, cudaStream_t st) {
     if constexpr (Rewards<ENV>::kClosedForm) {
         // random episode lengths: persistent grid (every resident CTA slot of the GPU), lane refill
         unsigned long long* next = nullptr;
-        ISLA_CUDA_OK(cudaMallocAsync((void**)&next, 8, st));
-        ISLA_CUDA_OK(cudaMemsetAsync(next, 0, 8, st));
+        if (int rc = claim_counter(&next, st)) return rc;
         if constexpr (ENV == ENV_FROZENLAKE) {
             int occ = 0;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rollout_kernel_units<ENV, T>, 256, 0) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 4; }
@@ -321,12 +395,13 @@ int rollout_launch(const void* s, long long n, int budget, double gamma, unsigne
             const unsigned grid = (unsigned)(want < (long long)sms * occ ? want : (long long)sms * occ);
             rollout_kernel_units<ENV, T><<<grid, 256, 0, st>>>((const T*)s, n, budget, gamma, seed, sim, disc, cum, ret, steps, next);
         } else {
+            int occ = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rollout_kernel<ENV, T>, 256, 0) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 4; }
             const long long want = (n + 255) / 256;
-            const unsigned grid = (unsigned)(want < (long long)sms * 6 ? want : (long long)sms * 6);
+            const unsigned grid = (unsigned)(want < (long long)sms * occ ? want : (long long)sms * occ);
             rollout_kernel<ENV, T><<<grid, 256, 0, st>>>((const T*)s, n, budget, gamma, seed, sim, disc, cum, ret, steps, next);
         }
         ISLA_CUDA_OK(cudaGetLastError());
-        ISLA_CUDA_OK(cudaFreeAsync(next, st));
     } else {
         rollout_kernel_simple<ENV, T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const T*)s, n, budget, seed, sim, ag, disc, ret, steps);
         ISLA_CUDA_OK(cudaGetLastError());

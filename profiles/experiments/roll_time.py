@@ -2,13 +2,15 @@ import sys, torch
 sys.path.insert(0, ".")
 from islamcts_b200 import engine as E
 dev = torch.device("cuda:0")
-def timeit(fn, reps=5):
+def timeit(fn, reps=15):
     fn(); torch.cuda.synchronize()
-    best = 1e9
+    ts = []
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record(); torch.cuda.synchronize(); best = min(best, e0.elapsed_time(e1))
-    return best * 1e-3
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    print("   min %.3f median %.3f max %.3f ms" % (ts[0], ts[len(ts) // 2], ts[-1]))
+    return ts[0] * 1e-3
 # bring the clocks up first: a cold process measures the ramp (CartPole 2.8 ms instead of 2.0 ms)
 x = torch.randn(8192, 8192, device=dev)
 for _ in range(30):
@@ -19,7 +21,7 @@ for env_id, name, budget, gamma in ((0, "cartpole", 500, 0.99), (3, "frozenlake"
     steps = []
     def run():
         ret, st = E.rollout(env_id, None, n=n, budget=budget, gamma=gamma, seed=1234, sim=0, device=dev)
-        steps.append((ret, st))
+        steps[:] = [(ret, st)]
     t = timeit(run)
     ret, st = steps[-1]
     total = int(st.sum().item())

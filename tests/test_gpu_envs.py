@@ -120,6 +120,24 @@ def test_rollout_f64_matches_oracle_streams(env_id, budget, gamma, grid):
         assert ret[i] == pytest.approx(eret, rel=1e-11, abs=1e-11)
 
 
+@pytest.mark.parametrize("env_id", [0, 3])
+@pytest.mark.parametrize("n,budget", [(1, 5), (31, 0), (33, 1), (64, 3), (2049, 500)])
+def test_rollout_queue_edges(env_id, n, budget):
+    """The persistent kernels' start queues at their edges: fewer trajectories than one production (32), a ragged last
+    production, budget 0 (a queued start finishes without a step) and budgets shorter than the warp's meeting period."""
+    from islamcts_b200 import engine as E
+    s0 = np.stack([coracle.env_reset(env_id, 8, i) for i in range(n)])
+    for precision in (1, 0):
+        ret, steps = E.rollout(env_id, s0, budget=budget, gamma=0.97, seed=123, sim=2, precision=precision)
+        ret, steps = ret.cpu().numpy(), steps.cpu().numpy()
+        for i in range(n):
+            eret, esteps = coracle.rollout(env_id, s0[i], budget, 0.97, 123, i, 2, 0)
+            if precision == 1 or env_id == 3:
+                assert steps[i] == esteps and ret[i] == pytest.approx(eret, rel=1e-11, abs=1e-11), (i, steps[i], esteps)
+            else:
+                assert abs(int(steps[i]) - esteps) <= (1 if budget > 3 else 0)    # fp32 may cross the threshold a step apart
+
+
 def test_rollout_reset_distribution_and_f32_agreement():
     from islamcts_b200 import engine as E
     n = 20000
