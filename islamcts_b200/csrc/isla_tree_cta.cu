@@ -155,6 +155,7 @@ struct RollShared {
     int depth;          // transition-noise index of the leaf's first rollout step (slippery FrozenLake): the env.step calls of
                         // the simulation so far (cloned env), or of the whole fit() so far (spw / dpw: live env)
     int roll_steps;     // steps rollout 0 of the leaf played (advances the live env's noise index)
+    int roll_next;      // this CTA's next unclaimed rollout of the current leaf (0 between rollout phases)
     unsigned sim;
     double result;
     VooWork vw;
@@ -857,6 +858,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
     const RollShared* const sh0 = CS > 1 ? cg::this_cluster().map_shared_rank(&sh, 0) : &sh;   // the owner's leaf record
     uint32_t sims_done = (uint32_t)ctx.q.meta[CM_SIMS];
     int s_done = 0;
+    if (tid == 0) sh.roll_next = 0;   // barriers follow before the first rollout phase reads it
     unsigned long long my_steps = 0;  // rollout env steps played by THIS thread
     int prev_levels = 0;              // recorded path entries of the previous simulation (warp 0, replicated)
 
@@ -1476,9 +1478,24 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                 double leaf[S];
 #pragma unroll
                 for (int i = 0; i < S; ++i) leaf[i] = sh0->leaf[i];
-                for (int j0 = 0; j0 < slice; j0 += nt) {
-                    const int jl = j0 + tid, j = jl * CS + (int)crank;
-                    if (jl < slice) {
+                // Episode lengths are random (CartPole: mean 22 steps, longest of a warp ~56): the slice is handed out
+                // dynamically.  The warp meets every kRollMeet env steps; lanes that finished store their return under
+                // the rollout's index (the reduction below does not care who played it) and claim the next unplayed
+                // rollouts of the CTA -- one shared-memory atomic per warp and meeting, ranks by ballot.  Between
+                // meetings the lanes only step.  (A fixed rollout-per-thread assignment in passes of the CTA size ran 12
+                // of 32 lanes on C2 as a batch: every pass waited for its longest episode.)
+#ifndef ISLA_CTA_MEET
+#define ISLA_CTA_MEET 8
+#endif
+#ifndef ISLA_CTA_UNROLL
+#define ISLA_CTA_UNROLL 1
+#endif
+                constexpr int kRollMeet = ISLA_CTA_MEET, kRollUnroll = ISLA_CTA_UNROLL;
+                if (slice <= nt) {
+                    // one rollout per thread at most: nothing to hand out (one tree on a cluster: the phase lasts as long as
+                    // its longest episode, and the lean loop keeps that chain short)
+                    if (tid < slice) {
+                        const int j = tid * CS + (int)crank;
                         double Rr = 0.0;
                         if (j < R) {
                             T st[S];
@@ -1490,8 +1507,6 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                             T rr = T(0);
                             while (!done && t < budget) {
                                 done = rollout_step<ENV, T>(rs, st, p.grid, rr, p.heur, p.noise, min(leaf_depth + t, p.noise_n - 1));
-                                // r * pow(gamma, t) summed left to right (abstract_mcts.py:87); envs with a constant
-                                // interior reward take the bit-identical closed form from the host prefix table below
                                 if constexpr (!Rewards<ENV>::kClosedForm) Rr = __dadd_rn(Rr, __dmul_rn((double)rr, __ldg(p.disc_table + t)));
                                 ++t;
                             }
@@ -1499,10 +1514,71 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                             my_steps += t;
                             if (j == 0) sh.roll_steps = t;
                         }
-                        red[jl] = Rr;
+                        red[tid] = Rr;
+                    }
+                } else {
+                    const unsigned lt = (1u << lane) - 1u;
+                    bool more = true;                   // warp-uniform: unclaimed rollouts may remain
+                    bool act = false, pend = false, done = false;
+                    int jl = 0, j = 0, t = 0;
+                    T st[S];
+#pragma unroll
+                    for (int i = 0; i < S; ++i) st[i] = T(0);
+                    T rr = T(0);
+                    double Rr = 0.0;
+                    Stream rs;
+                    rs.init(p.seed, sim_id, tree_id, 0u);
+                    for (;;) {
+                        if (pend) {
+                            if constexpr (Rewards<ENV>::kClosedForm) Rr = Rewards<ENV>::rollout_return(t, (double)rr, p.disc_table, p.cum_table);
+                            red[jl] = Rr;
+                            my_steps += t;
+                            if (j == 0) sh.roll_steps = t;
+                            pend = false;
+                        }
+                        const unsigned idle = __ballot_sync(kFull, !act);
+                        if (more && idle != 0u) {
+                            const int cnt = __popc(idle);
+                            int base = 0;
+                            if (lane == 0) base = atomicAdd(&sh.roll_next, cnt);
+                            base = __shfl_sync(kFull, base, 0);
+                            if (!act) {
+                                const int mine = base + __popc(idle & lt);
+                                if (mine < slice) {
+                                    jl = mine; j = jl * CS + (int)crank;
+                                    if (j < R) {
+#pragma unroll
+                                        for (int i = 0; i < S; ++i) st[i] = T(leaf[i]);
+                                        rs.init(p.seed, sim_id, tree_id, (uint32_t)j);
+                                        t = 0; done = false; rr = T(0); Rr = 0.0;
+                                        act = budget > 0;
+                                        pend = !act;
+                                    } else {
+                                        red[jl] = 0.0;   // padding of the power-of-two reduction tree
+                                    }
+                                }
+                            }
+                            more = base + cnt < slice;
+                        }
+                        if (!__any_sync(kFull, act || pend)) {
+                            if (!more) break;
+                            continue;
+                        }
+#pragma unroll kRollUnroll
+                        for (int u = 0; u < kRollMeet; ++u) {
+                            if (act) {
+                                done = rollout_step<ENV, T>(rs, st, p.grid, rr, p.heur, p.noise, min(leaf_depth + t, p.noise_n - 1));
+                                // r * pow(gamma, t) summed left to right (abstract_mcts.py:87); envs with a constant
+                                // interior reward take the bit-identical closed form from the host prefix table above
+                                if constexpr (!Rewards<ENV>::kClosedForm) Rr = __dadd_rn(Rr, __dmul_rn((double)rr, __ldg(p.disc_table + t)));
+                                ++t;
+                                if (done || t >= budget) { act = false; pend = true; }
+                            }
+                        }
                     }
                 }
                 __syncthreads();
+                if (tid == 0) sh.roll_next = 0;   // every claim of this phase has been made; barriers follow before the next
                 // fixed power-of-two tree: the sum does not depend on the CTA size nor on the cluster size
                 for (int stride = slice >> 1; stride > 0; stride >>= 1) {
                     for (int i = tid; i < stride; i += nt) red[i] = __dadd_rn(red[i], red[i + stride]);
@@ -1825,6 +1901,9 @@ int pick_threads(const isla_config& cfg) {
         const int R = cfg.rollouts_per_leaf > 0 ? cfg.rollouts_per_leaf : 1;
         nt = 32;
         while (nt < R && nt < 512) nt <<= 1;
+        // a batch that puts two or more trees on every SM: two 256-thread CTAs per SM overlap one tree's serial descent
+        // with the other's rollouts (the 128-register kernel fits 512 threads per SM either way; C2 x 296: 184 -> 208 G env-steps/s)
+        if (nt > 256 && cfg.n_trees >= 296) nt = 256;
         if (cfg.expansion == ISLA_EXPAND_VOO) nt = 512;   // voo's rejection tries are evaluated CTA-wide
         if (cfg.tree_parallel > 1) { while (nt < cfg.tree_parallel * R && nt < 512) nt <<= 1; }   // one thread per in-flight rollout
         // apw with random expansion and one rollout per leaf: runs of root-widening simulations are played one thread per
