@@ -157,14 +157,14 @@ __device__ __forceinline__ float reduce_pi(float x) {
 }
 template <> struct Env<ENV_PENDULUM, float> {
     static __device__ __forceinline__ bool step(float (&s)[2], float action, float& reward) {
-        constexpr float max_speed = 8.0f, max_torque = 2.0f, dt = 0.05f, pi = 3.14159265358979f, two_pi = 6.28318530717959f;
+        constexpr float max_speed = 8.0f, max_torque = 2.0f, dt = 0.05f;
         const float th = s[0], thdot = s[1];
         const float u = fminf(fmaxf(action, -max_torque), max_torque);
-        float ang = fmodf(th + pi, two_pi);
-        if (ang < 0.f) ang += two_pi;
-        ang -= pi;
+        // angle_normalize(th) = ((th + pi) % (2 pi)) - pi: the same reduction to [-pi, pi] the sine needs (the two differ only
+        // in which end of the interval th = (2k+1) pi lands on, and the cost uses ang * ang)
+        const float ang = reduce_pi(th);
         const float costs = ang * ang + 0.1f * (thdot * thdot) + 0.001f * (u * u);
-        float newthdot = thdot + (15.0f * __sinf(reduce_pi(th)) + 3.0f * u) * dt;
+        float newthdot = thdot + (15.0f * __sinf(ang) + 3.0f * u) * dt;
         newthdot = fminf(fmaxf(newthdot, -max_speed), max_speed);
         s[0] = th + newthdot * dt;
         s[1] = newthdot;
