@@ -450,4 +450,48 @@ __device__ __forceinline__ bool rollout_step(Stream& st, T (&s)[EnvTraits<ENV>::
     }
 }
 
+// One whole random-policy rollout of a continuous env with a one-dimensional Box action (Pendulum, MountainCarContinuous)
+// played by ONE thread, arranged for instruction-level parallelism.  A lone rollout is a dependent chain (state -> cos ->
+// velocity -> state ...) that issues one instruction every ~4.5 cycles; the action draws do not depend on the state.  So
+// the Philox block of the NEXT four steps is computed in the same straight-line block as the current four steps, and the
+// steps are predicated (computed on a copy, committed by selects) instead of branched, which lets the scheduler fill the
+// chain's latency slots with the generator.  Same stream words, same operations on the committed steps, same left-to-right
+// return sum as the step-by-step loop (rollout_step + r * disc[t]): bit-identical results.
+template <int ENV, typename T>
+__device__ __forceinline__ double rollout_fast1d(uint64_t seed, uint32_t c1, uint32_t c2, uint32_t c3, T (&st)[2], int budget,
+                                                 const double* __restrict__ disc_table, int& t_out, T& last_r) {
+    static_assert(EnvTraits<ENV>::kContinuous && EnvTraits<ENV>::AD == 1 && EnvTraits<ENV>::S == 2, "one-dimensional Box actions");
+    float lo, hi;
+    env_action_bounds(ENV, lo, hi);
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    uint32_t cur[4], nxt[4];
+    philox4x32_10(0u, c1, c2, c3, k0, k1, cur);
+    int t = 0;
+    double Rr = 0.0;
+    T rr = T(0);
+    bool go = budget > 0;
+    for (uint32_t blk = 1; go; ++blk) {
+        philox4x32_10(blk, c1, c2, c3, k0, k1, nxt);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            T ns[2] = {st[0], st[1]};
+            T r1;
+            const bool d = Env<ENV, T>::step(ns, T(box_sample_f32(cur[k], lo, hi)), r1);
+            const double term = __dmul_rn((double)r1, __ldg(disc_table + min(t, budget - 1)));   // r * pow(gamma, t)
+            if (go) {
+                st[0] = ns[0]; st[1] = ns[1];
+                rr = r1;
+                Rr = __dadd_rn(Rr, term);
+                ++t;
+                go = !d && t < budget;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cur[k] = nxt[k];
+    }
+    t_out = t;
+    last_r = rr;
+    return Rr;
+}
+
 }  // namespace isla

@@ -993,17 +993,22 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                             T ss[S];
 #pragma unroll
                             for (int i = 0; i < S; ++i) ss[i] = st[i];
-                            Stream rs;
-                            rs.init(p.seed, wv_sims0 + (unsigned)tid, tree_id, 0u);
-                            int t = 0; bool done = false;
+                            int t = 0;
                             T rr = T(0);
                             double Rr = 0.0;
-                            while (!done && t < budget) {
-                                done = rollout_step<ENV, T>(rs, ss, p.grid, rr, p.heur, p.noise, 0);
-                                if constexpr (!Rewards<ENV>::kClosedForm) Rr = __dadd_rn(Rr, __dmul_rn((double)rr, __ldg(p.disc_table + t)));
-                                ++t;
+                            if constexpr (EnvTraits<ENV>::kContinuous && EnvTraits<ENV>::AD == 1) {
+                                Rr = rollout_fast1d<ENV, T>(p.seed, wv_sims0 + (unsigned)tid, tree_id, 0u, ss, budget, p.disc_table, t, rr);
+                            } else {
+                                Stream rs;
+                                rs.init(p.seed, wv_sims0 + (unsigned)tid, tree_id, 0u);
+                                bool done = false;
+                                while (!done && t < budget) {
+                                    done = rollout_step<ENV, T>(rs, ss, p.grid, rr, p.heur, p.noise, 0);
+                                    if constexpr (!Rewards<ENV>::kClosedForm) Rr = __dadd_rn(Rr, __dmul_rn((double)rr, __ldg(p.disc_table + t)));
+                                    ++t;
+                                }
+                                if constexpr (Rewards<ENV>::kClosedForm) Rr = Rewards<ENV>::rollout_return(t, (double)rr, p.disc_table, p.cum_table);
                             }
-                            if constexpr (Rewards<ENV>::kClosedForm) Rr = Rewards<ENV>::rollout_return(t, (double)rr, p.disc_table, p.cum_table);
                             my_steps += t;
                             const double G = __dadd_rn(r0, __dmul_rn(p.gamma, Rr));
                             w_g[tid] = G;
@@ -1381,16 +1386,21 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                             T st[S];
 #pragma unroll
                             for (int k = 0; k < S; ++k) st[k] = T(rc.leaf[k]);
-                            Stream rs;
-                            rs.init(p.seed, rc.sim, tree_id, (uint32_t)j);
-                            int t = 0; bool done = false;
+                            int t = 0;
                             T rr = T(0);
-                            while (!done && t < rc.budget) {
-                                done = rollout_step<ENV, T>(rs, st, p.grid, rr, p.heur, p.noise, min(rc.depth + t, p.noise_n - 1));
-                                if constexpr (!Rewards<ENV>::kClosedForm) Rr = __dadd_rn(Rr, __dmul_rn((double)rr, __ldg(p.disc_table + t)));
-                                ++t;
+                            if constexpr (EnvTraits<ENV>::kContinuous && EnvTraits<ENV>::AD == 1) {
+                                Rr = rollout_fast1d<ENV, T>(p.seed, rc.sim, tree_id, (uint32_t)j, st, rc.budget, p.disc_table, t, rr);
+                            } else {
+                                Stream rs;
+                                rs.init(p.seed, rc.sim, tree_id, (uint32_t)j);
+                                bool done = false;
+                                while (!done && t < rc.budget) {
+                                    done = rollout_step<ENV, T>(rs, st, p.grid, rr, p.heur, p.noise, min(rc.depth + t, p.noise_n - 1));
+                                    if constexpr (!Rewards<ENV>::kClosedForm) Rr = __dadd_rn(Rr, __dmul_rn((double)rr, __ldg(p.disc_table + t)));
+                                    ++t;
+                                }
+                                if constexpr (Rewards<ENV>::kClosedForm) Rr = Rewards<ENV>::rollout_return(t, (double)rr, p.disc_table, p.cum_table);
                             }
-                            if constexpr (Rewards<ENV>::kClosedForm) Rr = Rewards<ENV>::rollout_return(t, (double)rr, p.disc_table, p.cum_table);
                             my_steps += t;
                         }
                         red[i] = Rr;
@@ -1501,16 +1511,21 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                             T st[S];
 #pragma unroll
                             for (int i = 0; i < S; ++i) st[i] = T(leaf[i]);
-                            Stream rs;
-                            rs.init(p.seed, sim_id, tree_id, (uint32_t)j);
-                            int t = 0; bool done = false;
+                            int t = 0;
                             T rr = T(0);
-                            while (!done && t < budget) {
-                                done = rollout_step<ENV, T>(rs, st, p.grid, rr, p.heur, p.noise, min(leaf_depth + t, p.noise_n - 1));
-                                if constexpr (!Rewards<ENV>::kClosedForm) Rr = __dadd_rn(Rr, __dmul_rn((double)rr, __ldg(p.disc_table + t)));
-                                ++t;
+                            if constexpr (EnvTraits<ENV>::kContinuous && EnvTraits<ENV>::AD == 1) {
+                                Rr = rollout_fast1d<ENV, T>(p.seed, sim_id, tree_id, (uint32_t)j, st, budget, p.disc_table, t, rr);
+                            } else {
+                                Stream rs;
+                                rs.init(p.seed, sim_id, tree_id, (uint32_t)j);
+                                bool done = false;
+                                while (!done && t < budget) {
+                                    done = rollout_step<ENV, T>(rs, st, p.grid, rr, p.heur, p.noise, min(leaf_depth + t, p.noise_n - 1));
+                                    if constexpr (!Rewards<ENV>::kClosedForm) Rr = __dadd_rn(Rr, __dmul_rn((double)rr, __ldg(p.disc_table + t)));
+                                    ++t;
+                                }
+                                if constexpr (Rewards<ENV>::kClosedForm) Rr = Rewards<ENV>::rollout_return(t, (double)rr, p.disc_table, p.cum_table);
                             }
-                            if constexpr (Rewards<ENV>::kClosedForm) Rr = Rewards<ENV>::rollout_return(t, (double)rr, p.disc_table, p.cum_table);
                             my_steps += t;
                             if (j == 0) sh.roll_steps = t;
                         }
