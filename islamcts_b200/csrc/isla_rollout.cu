@@ -54,16 +54,21 @@ __global__ void __launch_bounds__(256) rollout_kernel_simple(const T* __restrict
     } else {
         env_reset<ENV, T>(seed, (uint32_t)i, s);
     }
-    Stream rs;
-    rs.init(seed, sim, (uint32_t)i, 0u);
     double R = 0.0;
-    bool done = false;
     int t = 0;
-    while (!done && t < budget) {
-        T r;
-        done = rollout_step<ENV, T>(rs, s, grid, r);
-        R = __dadd_rn(R, __dmul_rn((double)r, __ldg(disc_table + t)));  // r * pow(gamma, t), host libm pow
-        ++t;
+    if constexpr (EnvTraits<ENV>::kContinuous && EnvTraits<ENV>::AD == 1) {
+        T last_r;
+        R = rollout_fast1d<ENV, T>(seed, sim, (uint32_t)i, 0u, s, budget, disc_table, t, last_r);   // four steps per Philox block, branch-free
+    } else {
+        Stream rs;
+        rs.init(seed, sim, (uint32_t)i, 0u);
+        bool done = false;
+        while (!done && t < budget) {
+            T r;
+            done = rollout_step<ENV, T>(rs, s, grid, r);
+            R = __dadd_rn(R, __dmul_rn((double)r, __ldg(disc_table + t)));  // r * pow(gamma, t), host libm pow
+            ++t;
+        }
     }
     returns[i] = R;
     steps[i] = t;
