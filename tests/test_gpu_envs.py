@@ -138,6 +138,30 @@ def test_rollout_queue_edges(env_id, n, budget):
                 assert abs(int(steps[i]) - esteps) <= (1 if budget > 3 else 0)    # fp32 may cross the threshold a step apart
 
 
+@pytest.mark.parametrize("env_id", [1, 2])
+@pytest.mark.parametrize("budget", [0, 1, 2, 3, 5, 7, 202])
+def test_rollout_four_step_blocks_at_their_edges(env_id, budget):
+    """Pendulum / MountainCar rollouts run four predicated steps per Philox block (rollout_fast1d): budgets that end inside a
+    block, and MountainCar episodes that reach the goal at every offset within a block, against the step-by-step oracle."""
+    from islamcts_b200 import engine as E
+    n = 257
+    rng = np.random.default_rng(31 + env_id)
+    if env_id == 2:
+        # near the goal (0.45) and moving right: most of these terminate within the first 1-12 steps
+        s0 = np.stack([rng.uniform(0.30, 0.449, n), rng.uniform(0.0, 0.06, n)], axis=1)
+    else:
+        s0 = np.stack([coracle.env_reset(env_id, 3, i) for i in range(n)])
+    ret, steps = E.rollout(env_id, s0, budget=budget, gamma=0.97, seed=77, sim=4, precision=1)
+    ret, steps = ret.cpu().numpy(), steps.cpu().numpy()
+    for i in range(n):
+        eret, esteps = coracle.rollout(env_id, s0[i], budget, 0.97, 77, i, 4, 0)
+        assert steps[i] == esteps, (i, steps[i], esteps)
+        assert ret[i] == eret or ret[i] == pytest.approx(eret, rel=1e-11, abs=1e-11)
+    if env_id == 2 and budget >= 7:
+        ended = steps[steps < budget]
+        assert len(ended) > 20 and len(set((ended % 4).tolist())) == 4   # goals reached at every offset within a block
+
+
 def test_rollout_reset_distribution_and_f32_agreement():
     from islamcts_b200 import engine as E
     n = 20000
