@@ -670,6 +670,45 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
             int t = 0;
             T last_r = T(0);
             bool go = rolling && budget > 0;
+#ifndef ISLA_TPT_ROLL_BLOCK
+#define ISLA_TPT_ROLL_BLOCK 2
+#endif
+#ifndef ISLA_TPT_ROLL_BLOCK_TPW
+#define ISLA_TPT_ROLL_BLOCK_TPW 16   // launches with at most this many trees per warp use the blocks (measured below)
+#endif
+            if (ENV == ENV_CARTPOLE && !SCRIPTED && ISLA_TPT_ROLL_BLOCK > 1 && p.tpw <= ISLA_TPT_ROLL_BLOCK_TPW) {
+                // Blocks of ISLA_TPT_ROLL_BLOCK predicated steps (computed on a copy, committed by selects): straight-line
+                // code in which the tail of one step (cart acceleration, position, thresholds) overlaps the head of the
+                // next (the pole-angle chain) -- a lone rollout is a dependent chain, and with a few trees per warp
+                // this phase is a third of the launch (blocks of 2: one tree 7.3 -> 6.3 ms, 8192 trees 398 -> 423 M sims/s,
+                // 16 384 trees 539 -> 567 M; the full batch, issue- and DRAM-bound, loses 1 % and keeps the plain loop;
+                // blocks of 4 / 8 waste more predicated steps than they overlap: 412 / 329 M at 8192 trees).  Step t of a rollout draws bit t of its stream (most significant
+                // bit of word t / 32 first, like next_bits(1)); blocks start at multiples of the block size, so a block
+                // never straddles a word.
+                constexpr int NB = ISLA_TPT_ROLL_BLOCK;
+                static_assert(32 % NB == 0, "a block of steps must not straddle a stream word");
+                uint32_t word = 0u;
+                while (__any_sync(kFull, go)) {
+                    if (go && (t & 31) == 0) word = rs.next();
+                    uint32_t bits = word << (t & 31);
+#pragma unroll
+                    for (int u = 0; u < NB; ++u) {
+                        T ns[S];
+#pragma unroll
+                        for (int i = 0; i < S; ++i) ns[i] = st[i];
+                        T r1;
+                        const bool done = Env<ENV, T>::step(ns, T(bits >> 31), r1);
+                        bits <<= 1;
+                        if (go) {
+#pragma unroll
+                            for (int i = 0; i < S; ++i) st[i] = ns[i];
+                            last_r = r1;
+                            ++t;
+                            go = !done && t < budget;
+                        }
+                    }
+                }
+            } else
             while (__any_sync(kFull, go)) {
                 if (go) {
                     T act;
