@@ -496,4 +496,38 @@ __device__ __forceinline__ double rollout_fast1d(uint64_t seed, uint32_t c1, uin
     return Rr;
 }
 
+// One whole random-policy CartPole rollout by one thread in blocks of NB predicated steps (computed on a copy, committed
+// by selects): the tail of one step overlaps the pole-angle chain of the next.  Step t draws bit t of the stream (most
+// significant bit of word t / 32 first, exactly next_bits(1)); a block never straddles a word.  Returns the step count;
+// the return follows from it in closed form (Rewards<ENV_CARTPOLE>).
+template <typename T, int NB>
+__device__ __forceinline__ int rollout_cartpole_blocks(uint64_t seed, uint32_t c1, uint32_t c2, uint32_t c3, T (&st)[4], int budget, T& last_r) {
+    static_assert(32 % NB == 0, "a block of steps must not straddle a stream word");
+    Stream rs;
+    rs.init(seed, c1, c2, c3);
+    int t = 0;
+    bool go = budget > 0;
+    uint32_t word = 0u;
+    T rr = T(0);
+    while (go) {
+        if ((t & 31) == 0) word = rs.next();
+        uint32_t bits = word << (t & 31);
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            T ns[4] = {st[0], st[1], st[2], st[3]};
+            T r1;
+            const bool done = Env<ENV_CARTPOLE, T>::step(ns, T(bits >> 31), r1);
+            bits <<= 1;
+            if (go) {
+                st[0] = ns[0]; st[1] = ns[1]; st[2] = ns[2]; st[3] = ns[3];
+                rr = r1;
+                ++t;
+                go = !done && t < budget;
+            }
+        }
+    }
+    last_r = rr;
+    return t;
+}
+
 }  // namespace isla

@@ -1515,6 +1515,9 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                             T rr = T(0);
                             if constexpr (EnvTraits<ENV>::kContinuous && EnvTraits<ENV>::AD == 1) {
                                 Rr = rollout_fast1d<ENV, T>(p.seed, sim_id, tree_id, (uint32_t)j, st, budget, p.disc_table, t, rr);
+                            } else if constexpr (ENV == ENV_CARTPOLE) {
+                                t = rollout_cartpole_blocks<T, 2>(p.seed, sim_id, tree_id, (uint32_t)j, st, budget, rr);
+                                Rr = Rewards<ENV>::rollout_return(t, (double)rr, p.disc_table, p.cum_table);
                             } else {
                                 Stream rs;
                                 rs.init(p.seed, sim_id, tree_id, (uint32_t)j);
