@@ -86,7 +86,11 @@ __global__ void __launch_bounds__(256) rollout_kernel_simple(const T* __restrict
 #ifndef ISLA_ROLL_INNER
 #define ISLA_ROLL_INNER 8
 #endif
-constexpr int kInner = ISLA_ROLL_INNER;
+#ifndef ISLA_ROLL_INNER_LAKE
+#define ISLA_ROLL_INNER_LAKE 4
+#endif
+// env steps between two meetings of a warp: CartPole episodes last 22 steps on average, FrozenLake's 7.7
+template <int ENV> constexpr int kInnerOf = ENV == ENV_FROZENLAKE ? ISLA_ROLL_INNER_LAKE : ISLA_ROLL_INNER;
 constexpr int kQueue = 64;   // queued starts per warp (two productions)
 
 template <int ENV, typename T>
@@ -95,6 +99,7 @@ __global__ void __launch_bounds__(256) rollout_kernel(const T* __restrict__ stat
                                                       const double* __restrict__ cum_table, double* __restrict__ returns,
                                                       int32_t* __restrict__ steps, unsigned long long* __restrict__ next) {
     constexpr int S = EnvTraits<ENV>::S;
+    constexpr int kInner = kInnerOf<ENV>;
     constexpr unsigned kFull = 0xffffffffu;
     __shared__ T q_state[8][kQueue][S];
     __shared__ uint32_t q_bits[8][kQueue][4];
@@ -190,111 +195,11 @@ __global__ void __launch_bounds__(256) rollout_kernel(const T* __restrict__ stat
     }
 }
 
-// The same persistent loop for SHORT episodes (FrozenLake: mean 7.7 steps), where the output is the bottleneck: a lane owns
-// UNITS of kUnit = 8
-// consecutive trajectories (claimed with one atomic per unit), plays them one after the other, parks the (return, steps)
-// pairs in shared memory and writes a finished unit with full-sector vector stores: 64 contiguous bytes of returns, 32 of
-// step counts.  (Round 1 claimed single trajectories per idle lane and wrote each 12-byte result on its own: partial-sector
-// writes into a 200 MB output cost 8 GB of DRAM read-modify-write traffic on FrozenLake, 40x the algorithmic bytes.)
-// Episode starts are batched (>= kRefillMin waiting lanes) so that the start-up code -- reset draw, stream re-key, unit
-// hand-over -- does not diverge every iteration.  Measured (profiles/README.md): FrozenLake DRAM reads 8 GB -> 12-75 MB per 2^24
-// trajectories; CartPole (22-step episodes, output traffic irrelevant) is faster with the per-trajectory claim above.
-#ifndef ISLA_ROLL_REFILL
-#define ISLA_ROLL_REFILL 14
-#endif
-#ifndef ISLA_ROLL_STATIC
-#define ISLA_ROLL_STATIC 0
-#endif
-#ifndef ISLA_ROLL_MINBLOCKS
-#define ISLA_ROLL_MINBLOCKS 1
-#endif
-constexpr int kUnitRefillMin = ISLA_ROLL_REFILL;
-constexpr int kUnit = 8;
-
-template <int ENV, typename T>
-__global__ void __launch_bounds__(256, ISLA_ROLL_MINBLOCKS) rollout_kernel_units(const T* __restrict__ states, long long n, int budget, double gamma,
-                                                      unsigned long long seed, unsigned sim, const double* __restrict__ disc_table,
-                                                      const double* __restrict__ cum_table, double* __restrict__ returns,
-                                                      int32_t* __restrict__ steps, unsigned long long* __restrict__ next) {
-    constexpr int S = EnvTraits<ENV>::S;
-    constexpr unsigned kFull = 0xffffffffu;
-    __shared__ double res_r[kUnit][256];
-    __shared__ int res_t[kUnit][256];
-    const int tid = threadIdx.x;
-    const long long n_units = (n + kUnit - 1) / kUnit;
-    long long unit = -1;
-    int j = kUnit;                     // trajectory of the unit to play next; kUnit = claim a new unit
-    bool running = false, exhausted = false;
-    T s[S];
-#pragma unroll
-    for (int k = 0; k < S; ++k) s[k] = T(0);
-    Stream rs;
-    rs.init(seed, sim, 0u, 0u);
-    int t = 0;
-    double R = 0.0;
-    T last_r = T(0);
-    auto flush = [&](long long u) {
-        const long long base = u * kUnit;
-        if (base + kUnit <= n) {
-            double* const pr = returns + base;          // 64-byte aligned: two full sectors
-            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(pr), "d"(res_r[0][tid]), "d"(res_r[1][tid]), "d"(res_r[2][tid]), "d"(res_r[3][tid]) : "memory");
-            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(pr + 4), "d"(res_r[4][tid]), "d"(res_r[5][tid]), "d"(res_r[6][tid]), "d"(res_r[7][tid]) : "memory");
-            int4* const pt = reinterpret_cast<int4*>(steps + base);   // one full sector
-            pt[0] = make_int4(res_t[0][tid], res_t[1][tid], res_t[2][tid], res_t[3][tid]);
-            pt[1] = make_int4(res_t[4][tid], res_t[5][tid], res_t[6][tid], res_t[7][tid]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < kUnit; ++k) if (base + k < n) { returns[base + k] = res_r[k][tid]; steps[base + k] = res_t[k][tid]; }
-        }
-    };
-    for (;;) {
-        const unsigned idle = __ballot_sync(kFull, !running);
-        if (idle == kFull || __popc(idle) >= kUnitRefillMin) {
-            if (!running && !exhausted) {
-                if (j == kUnit || unit * kUnit + j >= n) {
-                    if (unit >= 0) flush(unit);
-#if ISLA_ROLL_STATIC
-                    unit = unit < 0 ? (long long)blockIdx.x * blockDim.x + tid : unit + (long long)gridDim.x * blockDim.x;
-#else
-                    unit = (long long)atomicAdd(next, 1ull);
-#endif
-                    j = 0;
-                    if (unit >= n_units) { exhausted = true; unit = -1; }
-                }
-                if (!exhausted) {
-                    const long long idx = unit * kUnit + j;
-                    if (states) {
-#pragma unroll
-                        for (int k = 0; k < S; ++k) s[k] = states[idx * S + k];
-                    } else {
-                        env_reset<ENV, T>(seed, (uint32_t)idx, s);
-                    }
-                    rs.init(seed, sim, (uint32_t)idx, 0u);
-                    t = 0; R = 0.0; last_r = T(0);
-                    running = true;
-                }
-            }
-            if (__ballot_sync(kFull, running) == 0u) break;   // every lane has run out of units
-        }
-        if (running) {
-            bool fin = t >= budget;
-            if (!fin) {
-                const T a = sample_action<ENV, T>(rs);
-                const bool done = Env<ENV, T>::step(s, a, last_r);
-                if constexpr (!Rewards<ENV>::kClosedForm) R = __dadd_rn(R, __dmul_rn((double)last_r, __ldg(disc_table + t)));  // r * pow(gamma, t)
-                ++t;
-                fin = done || t >= budget;
-            }
-            if (fin) {
-                if constexpr (Rewards<ENV>::kClosedForm) R = Rewards<ENV>::rollout_return(t, (double)last_r, disc_table, cum_table);
-                res_r[j][tid] = R;
-                res_t[j][tid] = t;
-                ++j;
-                running = false;
-            }
-        }
-    }
-}
+// (FrozenLake, 7.7-step episodes, runs the same kernel with a meeting every 4 steps.  Its results are stored by the finished
+//  lanes of a meeting together, and the queue hands out consecutive ids, so the 12-byte results of a warp land in the same
+//  sectors within a few hundred cycles and merge in L2: DRAM reads 8.7 MB per 2^24 trajectories.  Round 1 claimed single
+//  trajectories per idle lane at arbitrary times -- 8 GB of read-modify-write traffic -- and an intermediate design parked
+//  units of 8 consecutive results in shared memory for full-sector stores: same traffic as now, 168 G env-steps/s against 289 G.)
 
 // real-step half of the episode loop: env.step(best action) for every live episode, float64, in place
 template <int ENV>
@@ -393,13 +298,7 @@ int rollout_launch(const void* s, long long n, int budget, double gamma, unsigne
         // random episode lengths: persistent grid (every resident CTA slot of the GPU), lane refill
         unsigned long long* next = nullptr;
         if (int rc = claim_counter(&next, st)) return rc;
-        if constexpr (ENV == ENV_FROZENLAKE) {
-            int occ = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rollout_kernel_units<ENV, T>, 256, 0) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 4; }
-            const long long want = (n + 256 * kUnit - 1) / (256 * kUnit);
-            const unsigned grid = (unsigned)(want < (long long)sms * occ ? want : (long long)sms * occ);
-            rollout_kernel_units<ENV, T><<<grid, 256, 0, st>>>((const T*)s, n, budget, gamma, seed, sim, disc, cum, ret, steps, next);
-        } else {
+        {
             int occ = 0;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rollout_kernel<ENV, T>, 256, 0) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 4; }
             const long long want = (n + 255) / 256;
