@@ -402,8 +402,9 @@ def other_configs(dev):
 
     out = {}
     g = torch.Generator().manual_seed(7)
-    # C1: vanilla FrozenLake nsim=100 C=0.5 gamma=1 max_depth=1000: one tree, and 65 536 trees (thread-per-tree)
-    for name, nt, kern in (("c1_frozenlake_1tree", 1, _lib.KERNEL_CTA_PER_TREE), ("c1_frozenlake_65536trees", 65536, _lib.KERNEL_THREAD_PER_TREE)):
+    # C1: vanilla FrozenLake nsim=100 C=0.5 gamma=1 max_depth=1000: one tree (the library's own kernel choice, as Mcts.fit()
+    # gets it), and 65 536 trees (thread-per-tree)
+    for name, nt, kern in (("c1_frozenlake_1tree", 1, _lib.KERNEL_AUTO), ("c1_frozenlake_65536trees", 65536, _lib.KERNEL_THREAD_PER_TREE)):
         eng = Engine(_lib.ENV_FROZENLAKE, n_trees=nt, sim_capacity=100, max_depth=1000, C_=0.5, gamma=1.0, kernel=kern, seed=1, device=dev)
         roots = torch.zeros((nt, 1), dtype=torch.float64, device=dev)
         t = timeit(lambda: eng.set_roots(roots).run(100))
