@@ -673,6 +673,9 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
 #ifndef ISLA_TPT_ROLL_BLOCK
 #define ISLA_TPT_ROLL_BLOCK 2
 #endif
+#ifndef ISLA_TPT_LAKE_BLOCK
+#define ISLA_TPT_LAKE_BLOCK 4
+#endif
 #ifndef ISLA_TPT_ROLL_BLOCK_TPW
 #define ISLA_TPT_ROLL_BLOCK_TPW 16   // launches with at most this many trees per warp use the blocks (measured below)
 #endif
@@ -699,6 +702,32 @@ __global__ void __launch_bounds__(kTptBlock, ISLA_TPT_MINBLOCKS) tpt_search_kern
                         T r1;
                         const bool done = Env<ENV, T>::step(ns, T(bits >> 31), r1);
                         bits <<= 1;
+                        if (go) {
+#pragma unroll
+                            for (int i = 0; i < S; ++i) st[i] = ns[i];
+                            last_r = r1;
+                            ++t;
+                            go = !done && t < budget;
+                        }
+                    }
+                }
+            } else if (ENV == ENV_FROZENLAKE && !SCRIPTED && ISLA_TPT_LAKE_BLOCK > 1 && !p.heur && !p.noise) {
+                // FrozenLake under the plain random policy: a step is a dozen instructions, the vote and branch around it
+                // nearly as many -- blocks of predicated steps, two stream bits per step (16 steps per word)
+                constexpr int NB = ISLA_TPT_LAKE_BLOCK;
+                static_assert(16 % NB == 0, "a block of steps must not straddle a stream word");
+                uint32_t word = 0u;
+                while (__any_sync(kFull, go)) {
+                    if (go && (t & 15) == 0) word = rs.next();
+                    uint32_t bits = word << (2 * (t & 15));
+#pragma unroll
+                    for (int u = 0; u < NB; ++u) {
+                        T ns[S];
+#pragma unroll
+                        for (int i = 0; i < S; ++i) ns[i] = st[i];
+                        T r1;
+                        const bool done = Env<ENV, T>::step(ns, T(bits >> 30), r1);
+                        bits <<= 2;
                         if (go) {
 #pragma unroll
                             for (int i = 0; i < S; ++i) st[i] = ns[i];

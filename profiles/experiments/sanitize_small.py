@@ -31,10 +31,19 @@ for kw in cases:
         e.best(); e.root_children(1); e.depth_stats(2)
         if e.counters()["faults"]:
             print("faults in", kw, R, [e.tree_meta(i)["fault"] for i in range(3)])
+# leaf batches larger than the CTA (rollouts handed out dynamically), tree-parallel batches
+for env_id, kw in ((0, dict(agent=0)), (3, dict(agent=0)), (1, dict(agent=1, alpha1=0.5, k1=2.0))):
+    e = Engine(env_id, n_trees=2, sim_capacity=60, max_depth=40, gamma=0.95, kernel=2, seed=9, rollouts_per_leaf=200, block_threads=64, **kw)
+    e.set_roots(np.zeros((2, e.state_dim)) if env_id == 3 else rng.uniform(-0.05, 0.05, (2, e.state_dim))).run(60)
+    e.best()
+    assert e.counters()["faults"] == 0
+e = Engine(2, n_trees=1, sim_capacity=400, max_depth=60, gamma=0.99, kernel=2, seed=2, agent=3, alpha1=0.5, k1=1.0, alpha2=0.5, k2=1.0, tree_parallel=16, virtual_value=-5.0)
+e.set_roots(np.array([[-0.5, 0.0]])).run(400); e.best()
 print("cta ok")
 ns, r, t = env_step(4, np.tile(pose, (64, 1)), rng.uniform([-5, -30], [5, 30], (64, 2)), precision=1)
 for env_id in range(5):
     rollout(env_id, None, n=5000, budget=50, gamma=0.9, seed=1)
+    rollout(env_id, None, n=70001, budget=7, gamma=0.9, seed=2)
 rollout(4, None, n=5000, budget=50, gamma=0.9, seed=1, action_grid=(5, 7))
 eb = EpisodeBatch("CartPole-v1", n_episodes=20, n_sim=60, max_steps=5, seed=1, max_depth=30)
 print(eb.run(rng.uniform(-0.05, 0.05, (20, 4)))["n_steps"])
