@@ -825,7 +825,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
     constexpr int S = EnvTraits<ENV>::S;
     __shared__ RollShared sh;
     __shared__ double red[kMaxRollSmem];
-    __shared__ double partials[8];   // rank 0: the rollout sums of the cluster's CTAs
+    __shared__ double partials[16];  // rank 0: the rollout sums of the cluster's CTAs
     // A tree whose leaves are evaluated by thousands of rollouts is served by a thread-block CLUSTER: rank 0 owns the
     // tree (descent, expansion, backup), every rank plays an interleaved power-of-two slice of the rollouts from the leaf
     // state it reads out of rank 0's shared memory (DSMEM), reduces it with the fixed pairwise tree and stores its sum
@@ -1969,6 +1969,10 @@ int launch(const CtaParams& p, int nt, bool scripted, cudaStream_t st) {
             attr.id = cudaLaunchAttributeClusterDimension;
             attr.val.clusterDim.x = (unsigned)p.cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
             cfg.attrs = &attr; cfg.numAttrs = 1;
+            if (p.cluster > 8) {   // beyond the portable size: opt in (sm_100 schedules 16-CTA clusters inside one GPC)
+                const cudaError_t ae = cudaFuncSetAttribute(cta_search_kernel<ENV, T, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+                if (ae != cudaSuccess) return cuda_fail(ae, "non-portable cluster size");
+            }
             const cudaError_t le = cudaLaunchKernelEx(&cfg, cta_search_kernel<ENV, T, false>, p);
             if (le != cudaSuccess) return cuda_fail(le, "cta_search_kernel cluster launch");
         } else {
@@ -2014,8 +2018,8 @@ int cta_fill_layout(const isla_config& cfg, isla_layout& lay) {
         }
         if (cfg.cluster_ctas > 1) { set_error("tree_parallel needs cluster_ctas <= 1"); return ISLA_ERR_INVALID; }
     }
-    if (cfg.cluster_ctas != 0 && cfg.cluster_ctas != 1 && cfg.cluster_ctas != 2 && cfg.cluster_ctas != 4 && cfg.cluster_ctas != 8) {
-        set_error("cluster_ctas must be 0 (auto), 1, 2, 4 or 8"); return ISLA_ERR_INVALID;
+    if (cfg.cluster_ctas != 0 && cfg.cluster_ctas != 1 && cfg.cluster_ctas != 2 && cfg.cluster_ctas != 4 && cfg.cluster_ctas != 8 && cfg.cluster_ctas != 16) {
+        set_error("cluster_ctas must be 0 (auto), 1, 2, 4, 8 or 16 (16: non-portable cluster size)"); return ISLA_ERR_INVALID;
     }
     if (cfg.expansion < ISLA_EXPAND_RANDOM || cfg.expansion > ISLA_EXPAND_GENETIC) { set_error("unknown expansion %d", cfg.expansion); return ISLA_ERR_INVALID; }
     if (cfg.expansion == ISLA_EXPAND_GENETIC && cfg.voo_n_samples < 1) { set_error("genetic_policy: n_samples must be >= 1"); return ISLA_ERR_INVALID; }

@@ -176,14 +176,14 @@ def test_voo_tries_evaluated_cta_wide_do_not_depend_on_cta_size():
 
 
 def test_cluster_of_ctas_shares_the_rollouts_bit_identically():
-    """Thread-block clusters (1, 2, 4, 8 CTAs per tree) play slices of the leaf's rollouts; the fixed reduction tree makes
+    """Thread-block clusters (1, 2, 4, 8, 16 CTAs per tree) play slices of the leaf's rollouts; the fixed reduction tree makes
     the backed-up means -- hence whole trees -- bit-identical, also for partial batches (R not a power of two)."""
     from islamcts_b200.engine import Engine
     n_trees, n_sim = 5, 120
     roots = np.stack([coracle.env_reset(0, 9, i) for i in range(n_trees)])
     for R in (2048, 1500):
         out = []
-        for cs, nt in ((1, 512), (2, 512), (4, 256), (8, 512), (0, 0)):
+        for cs, nt in ((1, 512), (2, 512), (4, 256), (8, 512), (16, 128), (0, 0)):   # 16: non-portable cluster size (opt-in)
             e = Engine(0, n_trees=n_trees, sim_capacity=n_sim, max_depth=60, gamma=0.97, precision=1, kernel=2,
                        rollouts_per_leaf=R, block_threads=nt, cluster_ctas=cs, seed=5)
             e.set_roots(roots).run(n_sim)
