@@ -131,6 +131,31 @@ def test_free_running_f64_equals_oracle(name, R):
     assert_tree_equal(eng.export_tree(5), exp, rtol=1e-9, atol=1e-9, label=f"{name}/tree5 after best: ")
 
 
+@pytest.mark.parametrize("name", ["vanilla_cartpole", "vanilla_lake", "apw_pendulum", "dpw_mountaincar_c4like", "spw_cartpole_k1",
+                                  "vanilla_curve_grid", "apw_curve"])
+@pytest.mark.parametrize("R,nt", [(130, 32), (70, 64)])
+def test_leaf_batches_larger_than_the_cta_equal_oracle(name, R, nt):
+    """More rollouts per leaf than threads in the CTA: the rollouts are handed out dynamically (finished lanes claim the
+    next ones at the warp's meetings), stored under their index and reduced by the fixed tree -- whole trees must still
+    equal the oracle's, for every env's rollout loop (CartPole blocks, the four-step continuous blocks, FrozenLake, CurveEnv)."""
+    kw = FREE[name]
+    n_trees, n_sim = 6, 90
+    roots = _roots(kw["env_id"], n_trees, 11)
+    eng = _engine(kw, n_trees, n_sim, 1, rollouts_per_leaf=R, block_threads=nt, seed=77, tree_id_base=5)
+    eng.set_roots(roots).run(n_sim)
+    assert eng.counters()["faults"] == 0
+    okw = dict(kw)
+    conf_kw = dict(agent=okw.pop("agent"), n_actions=okw.pop("n_actions", 0), C_=okw.pop("C"), rollouts_per_leaf=R, seed=77)
+    env_id = okw.pop("env_id")
+    steps = 0
+    for i in range(n_trees):
+        t = coracle.Tree(coracle.make_config(env_id, tree_id=5 + i, **conf_kw, **okw), roots[i])
+        assert t.run(n_sim) == 0
+        assert_tree_equal(eng.export_tree(i), {"tree_" + k: v for k, v in t.serialise().items()}, rtol=1e-9, atol=1e-9, label=f"{name}/tree{i}: ")
+        steps += t.counters()["rollout_steps"]
+    assert eng.counters()["rollout_steps"] == steps
+
+
 def test_result_independent_of_cta_size_and_equal_to_thread_per_tree():
     from islamcts_b200.engine import Engine
     n_trees, n_sim = 64, 150
