@@ -1546,6 +1546,8 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                     double Rr = 0.0;
                     Stream rs;
                     rs.init(p.seed, sim_id, tree_id, 0u);
+                    uint32_t dyn_word = 0u;   // CartPole blocks: the stream word holding the rollout's current 32 action bits
+                    (void)dyn_word;
                     for (;;) {
                         if (pend) {
                             if constexpr (Rewards<ENV>::kClosedForm) Rr = Rewards<ENV>::rollout_return(t, (double)rr, p.disc_table, p.cum_table);
@@ -1582,6 +1584,37 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                             if (!more) break;
                             continue;
                         }
+#ifndef ISLA_CTA_DYN_BLOCK
+#define ISLA_CTA_DYN_BLOCK 4
+#endif
+                        if constexpr (ENV == ENV_CARTPOLE && ISLA_CTA_DYN_BLOCK > 1) {
+                            // CartPole: blocks of predicated steps (the tail of one step overlaps the pole-angle chain of
+                            // the next; 16 warps per SM leave the latency of a dependent chain exposed).  Step t draws
+                            // bit t of the rollout's stream; a rollout starts at t = 0, so blocks never straddle a word.
+                            constexpr int NB = ISLA_CTA_DYN_BLOCK;
+                            static_assert(kRollMeet % NB == 0 && 32 % NB == 0, "blocks per meeting");
+#pragma unroll 1
+                            for (int u = 0; u < kRollMeet; u += NB) {
+                                if (act && (t & 31) == 0) dyn_word = rs.next();
+                                uint32_t bits = dyn_word << (t & 31);
+#pragma unroll
+                                for (int k = 0; k < NB; ++k) {
+                                    T ns[S];
+#pragma unroll
+                                    for (int i = 0; i < S; ++i) ns[i] = st[i];
+                                    T r1;
+                                    const bool d1 = Env<ENV, T>::step(ns, T(bits >> 31), r1);
+                                    bits <<= 1;
+                                    if (act) {
+#pragma unroll
+                                        for (int i = 0; i < S; ++i) st[i] = ns[i];
+                                        rr = r1;
+                                        ++t;
+                                        if (d1 || t >= budget) { act = false; pend = true; }
+                                    }
+                                }
+                            }
+                        } else
 #pragma unroll kRollUnroll
                         for (int u = 0; u < kRollMeet; ++u) {
                             if (act) {
