@@ -1494,6 +1494,9 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                 // rollouts of the CTA -- one shared-memory atomic per warp and meeting, ranks by ballot.  Between
                 // meetings the lanes only step.  (A fixed rollout-per-thread assignment in passes of the CTA size ran 12
                 // of 32 lanes on C2 as a batch: every pass waited for its longest episode.)
+#ifndef ISLA_CTA_STATIC_BLOCK
+#define ISLA_CTA_STATIC_BLOCK 4
+#endif
 #ifndef ISLA_CTA_MEET
 #define ISLA_CTA_MEET 8
 #endif
@@ -1516,7 +1519,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                             if constexpr (EnvTraits<ENV>::kContinuous && EnvTraits<ENV>::AD == 1) {
                                 Rr = rollout_fast1d<ENV, T>(p.seed, sim_id, tree_id, (uint32_t)j, st, budget, p.disc_table, t, rr);
                             } else if constexpr (ENV == ENV_CARTPOLE) {
-                                t = rollout_cartpole_blocks<T, 2>(p.seed, sim_id, tree_id, (uint32_t)j, st, budget, rr);
+                                t = rollout_cartpole_blocks<T, ISLA_CTA_STATIC_BLOCK>(p.seed, sim_id, tree_id, (uint32_t)j, st, budget, rr);
                                 Rr = Rewards<ENV>::rollout_return(t, (double)rr, p.disc_table, p.cum_table);
                             } else {
                                 Stream rs;
