@@ -888,6 +888,12 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
     __shared__ TpRec tp_rec[kTpMax];
     int tp_b = 0, tp_pb = 0;   // simulations in flight, path entries they occupy
 
+#ifdef ISLA_CTA_TIMING
+    long long tm_verify = 0, tm_descent = 0, tm_roll = 0, tm_backup = 0, tm_other = 0, tm_mark = clock64();
+#define CTA_TM(acc) do { const long long now_ = clock64(); acc += now_ - tm_mark; tm_mark = now_; } while (0)
+#else
+#define CTA_TM(acc)
+#endif
     for (int sim = 0; sim < p.n_sim; ++sim) {
         if (wave_ok) {
             Pool& q = ctx.q;
@@ -1063,6 +1069,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
         int leaf_a = -1, leaf_s = -1;
         T cur[S];
         const int pb = tp ? tp_pb : 0;   // first path entry of this simulation
+        CTA_TM(tm_other);
         if (leader && !ctx.fault) {
             Pool& q = ctx.q;
             int s = 0;
@@ -1124,6 +1131,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                     ctx.c_levels += (unsigned long long)event;
                 }
             }
+            CTA_TM(tm_verify);
             for (;;) {
                 ++ctx.c_levels;
                 // ---------------- state node: choose or create the action node
@@ -1320,6 +1328,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
         // end of the descent.  Until then the other warps serve voo's try batches (barrier 1 = work posted or descent
         // over, barrier 2 = batch evaluated); the last barrier-1 also publishes sh.need / sh.leaf / sh.budget.
         if (leader) {
+            CTA_TM(tm_descent);
             if (lane == 0) sh.vw.cmd = VOO_EXIT;
             __syncwarp();
             bar_sync(1, nt);
@@ -1652,6 +1661,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
         }
 
         // ------------------------------------------------------------ warp 0: leaf update + backup
+        CTA_TM(tm_roll);
         if (leader && !ctx.fault && !ctx.tc.fault && level > 0) {
             Pool& q = ctx.q;
             if (need_roll && p.noise && (p.agent == ISLA_AGENT_SPW || p.agent == ISLA_AGENT_DPW)) ctx.noise_pos += sh.roll_steps;
@@ -1665,8 +1675,21 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
             if (lane == 0) {
                 double g = G;
                 q.p_g[level - 1] = g;
-                for (int l = level - 2; l >= 0; --l) {
-                    g = __dadd_rn(q.p_r[l], __dmul_rn(p.gamma, g));             // r + gamma * build_tree_state(child)
+                int l = level - 2;
+                // eight levels at a time: the rewards are loaded before, the returns stored after the eight dependent
+                // (multiply, add) pairs, so the chain pays the arithmetic latency only (a deep vanilla path has 200 levels;
+                // with one load and one store inside every link the backup was a quarter of a C2 simulation)
+                for (; l >= 7; l -= 8) {
+                    double r[8], gs[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) r[k] = q.p_r[l - k];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { g = __dadd_rn(r[k], __dmul_rn(p.gamma, g)); gs[k] = g; }   // r + gamma * build_tree_state(child)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) q.p_g[l - k] = gs[k];
+                }
+                for (; l >= 0; --l) {
+                    g = __dadd_rn(q.p_r[l], __dmul_rn(p.gamma, g));
                     q.p_g[l] = g;
                 }
             }
@@ -1683,8 +1706,13 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
         } else {
             prev_levels = 0;
         }
+        CTA_TM(tm_backup);
         __syncthreads();
     }
+#ifdef ISLA_CTA_TIMING
+    if (tree == 0 && owner && tid == 0)
+        printf("cta tree 0 cycles: verify %lld descent %lld rollout-phase %lld backup %lld other %lld\n", tm_verify, tm_descent, tm_roll, tm_backup, tm_other);
+#endif
 
     if (my_steps) { atomicAdd(p.counters + CNT_ROLLOUT_STEPS, my_steps); atomicAdd(p.counters + CNT_ENV_STEPS, my_steps); }
     bool copy_back = p.pool_in_smem && owner;
