@@ -890,6 +890,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
 
 #ifdef ISLA_CTA_TIMING
     long long tm_verify = 0, tm_descent = 0, tm_roll = 0, tm_backup = 0, tm_other = 0, tm_mark = clock64();
+    long long tm_r_sync1 = 0, tm_r_own = 0, tm_r_wait = 0, tm_r_reduce = 0;   // parts of tm_roll (thread 0 of the owner)
 #define CTA_TM(acc) do { const long long now_ = clock64(); acc += now_ - tm_mark; tm_mark = now_; } while (0)
 #else
 #define CTA_TM(acc)
@@ -1343,6 +1344,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
         }
         }
         if (CS > 1) cg::this_cluster().sync();   // the owner's leaf record is final
+        CTA_TM(tm_r_sync1);
 
         if (tp) {
             // ---------------------------------------------------------- tree-parallel: park this simulation, run the batch when full
@@ -1640,7 +1642,9 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                         }
                     }
                 }
+                CTA_TM(tm_r_own);
                 __syncthreads();
+                CTA_TM(tm_r_wait);
                 if (tid == 0) sh.roll_next = 0;   // every claim of this phase has been made; barriers follow before the next
                 // fixed power-of-two tree: the sum does not depend on the CTA size nor on the cluster size
                 for (int stride = slice >> 1; stride > 0; stride >>= 1) {
@@ -1648,6 +1652,7 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
                     __syncthreads();
                 }
                 if (CS > 1 && tid == 0) cg::this_cluster().map_shared_rank(partials, 0)[crank] = red[0];
+                CTA_TM(tm_r_reduce);
             }
         }
         if (CS > 1) {
@@ -1711,7 +1716,8 @@ __global__ void __launch_bounds__(512) cta_search_kernel(const CtaParams p) {
     }
 #ifdef ISLA_CTA_TIMING
     if (tree == 0 && owner && tid == 0)
-        printf("cta tree 0 cycles: verify %lld descent %lld rollout-phase %lld backup %lld other %lld\n", tm_verify, tm_descent, tm_roll, tm_backup, tm_other);
+        printf("cta tree 0 cycles: verify %lld descent %lld rollout-phase %lld (+ leaf hand-over %lld, own rollout %lld, wait for the CTA %lld, reduction %lld) backup %lld other %lld\n",
+               tm_verify, tm_descent, tm_roll, tm_r_sync1, tm_r_own, tm_r_wait, tm_r_reduce, tm_backup, tm_other);
 #endif
 
     if (my_steps) { atomicAdd(p.counters + CNT_ROLLOUT_STEPS, my_steps); atomicAdd(p.counters + CNT_ENV_STEPS, my_steps); }

@@ -4,7 +4,7 @@ from islamcts_b200.engine import Engine
 g = torch.Generator().manual_seed(7)
 roots = (torch.rand((1, 4), generator=g, dtype=torch.float64) - 0.5) * 0.1
 ref = None
-for cs, bt in ((0, 0), (8, 512), (16, 256), (16, 512), (16, 128)):
+for cs, bt in ((0, 0), (8, 512), (8, 256), (8, 128), (16, 256), (16, 128), (16, 64), (4, 512), (4, 256)):
     try:
         eng = Engine(0, n_trees=1, sim_capacity=1000, max_depth=500, C_=1.0, gamma=0.99, kernel=2, rollouts_per_leaf=4096, seed=1, cluster_ctas=cs, block_threads=bt)
         eng.set_roots(roots).run(1000); torch.cuda.synchronize()
