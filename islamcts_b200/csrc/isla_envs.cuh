@@ -179,7 +179,11 @@ template <> struct Env<ENV_MOUNTAINCAR, float> {
         const float force = fminf(fmaxf(action, -1.0f), 1.0f);
         // 3 * position lies in [-3.6, 1.8]: the approximation's own range reduction (one multiply by 1/2pi, |x/2pi| < 0.58)
         // adds a phase error below 4e-7 there, so no explicit reduction to [-pi, pi] (4 dependent instructions of the chain)
-        velocity += force * power - 0.0025f * __cosf(3.0f * position);
+        // The loop-carried chain of a rollout runs through the position: one multiply into the cosine unit, one fused
+        // multiply-add out of it (force * power + velocity is ready before the cosine is).
+        float c;
+        asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(position * 3.0f));
+        velocity = fmaf(c, -0.0025f, force * power + velocity);
         velocity = fminf(fmaxf(velocity, -max_speed), max_speed);
         position += velocity;
         position = fminf(fmaxf(position, min_position), max_position);
