@@ -463,6 +463,9 @@ __device__ __forceinline__ bool rollout_step(Stream& st, T (&s)[EnvTraits<ENV>::
 // steps are predicated (computed on a copy, committed by selects) instead of branched, which lets the scheduler fill the
 // chain's latency slots with the generator.  Same stream words, same operations on the committed steps, same left-to-right
 // return sum as the step-by-step loop (rollout_step + r * disc[t]): bit-identical results.
+#ifndef ISLA_FAST1D_SPECULATE
+#define ISLA_FAST1D_SPECULATE 1
+#endif
 template <int ENV, typename T>
 __device__ __forceinline__ double rollout_fast1d(uint64_t seed, uint32_t c1, uint32_t c2, uint32_t c3, T (&st)[2], int budget,
                                                  const double* __restrict__ disc_table, int& t_out, T& last_r) {
@@ -476,7 +479,42 @@ __device__ __forceinline__ double rollout_fast1d(uint64_t seed, uint32_t c1, uin
     double Rr = 0.0;
     T rr = T(0);
     bool go = budget > 0;
-    for (uint32_t blk = 1; go; ++blk) {
+    uint32_t blk = 1;
+#if ISLA_FAST1D_SPECULATE
+    // Common case -- no step of a block ends the episode and the budget covers all four: step without looking, then
+    // commit the block at once.  The state chain then carries no select and no predicate, and the loop body is ONE
+    // straight-line region: the generator of the next block, the four float64 additions of the PREVIOUS block's terms
+    // (27 cycles each on this part) and the state chain interleave.  The first block in which an episode ends (rare: these
+    // envs run to the budget) and the last budget % 4 steps are played by the predicated loop below.
+    {
+        double pend[4] = {0.0, 0.0, 0.0, 0.0};   // terms of the last committed block, not yet added (adding 0.0 changes nothing)
+        while (go && t + 4 <= budget) {
+            philox4x32_10(blk, c1, c2, c3, k0, k1, nxt);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) Rr = __dadd_rn(Rr, pend[k]);
+            T s4[2] = {st[0], st[1]};
+            T rk[4];
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) any |= Env<ENV, T>::step(s4, T(box_sample_f32(cur[k], lo, hi)), rk[k]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) pend[k] = 0.0;
+            if (any) break;                        // redone step by step below (cur and blk still name this block)
+            st[0] = s4[0]; st[1] = s4[1];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) pend[k] = __dmul_rn((double)rk[k], __ldg(disc_table + t + k));   // r * pow(gamma, t): added left to right, one block later
+            rr = rk[3];
+            t += 4;
+            go = t < budget;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) cur[k] = nxt[k];
+            ++blk;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) Rr = __dadd_rn(Rr, pend[k]);
+    }
+#endif
+    for (; go; ++blk) {
         philox4x32_10(blk, c1, c2, c3, k0, k1, nxt);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
