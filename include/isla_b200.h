@@ -70,8 +70,8 @@ typedef struct {
     int32_t action_grid0;       /* ISLA_ENV_CURVE: DiscreteCurveEnv([g0, g1]) = g0 accelerations x g1 steering angles */
     int32_t action_grid1;       /*   (curve_env.py:184-199; n_actions = g0*g1 <= 128); both 0 = the continuous 2-D CurveEnv box */
     int32_t cluster_ctas;       /* CTA-per-tree kernel: thread blocks (one thread-block cluster) that share one tree's leaf-parallel
-                                 * rollouts; 0 = auto (up to 8 when rollouts_per_leaf > 512), else 1, 2, 4, 8 or 16 (16 = non-portable cluster
-                                 * size, opt-in only: C2 on one tree 27.0 -> 25.7 us per simulation with 256-thread CTAs) */
+                                 * rollouts; 0 = auto (up to 8 when rollouts_per_leaf > 512; 16 -- a non-portable cluster size -- for a few
+                                 * trees with >= 4096 rollouts per leaf where the device can place it, else 8), or 1, 2, 4, 8, 16 */
     int32_t tree_parallel;      /* build extension, CTA-per-tree kernel: > 1 = that many simulations of ONE tree in flight at once
                                  * (virtual loss: each descent provisionally credits its leaf with virtual_value, the rollouts of
                                  * the batch run concurrently, the credits are then corrected in order); 0 / 1 = the reference's

@@ -85,6 +85,7 @@ struct isla_engine {
     int noise_n = 0;
     char* reroot_tmp = nullptr;   // thread-per-tree engine: scratch arena of isla_engine_reroot (engine-owned, lazily sized)
     size_t reroot_bytes = 0;
+    bool no_cluster16 = false;   // a 16-CTA (non-portable) cluster launch was refused on this device: stay with 8
     double* ret_dev = nullptr;    // thread-per-tree engine: return table (engine-owned), ret_rows x ret_K
     int ret_rows = 0, ret_K = 0;
 };

@@ -2023,6 +2023,8 @@ int pick_threads(const isla_config& cfg) {
     return nt > 512 ? 512 : nt;
 }
 
+constexpr int kClusterRefused = 1;   // launch(): a non-portable cluster size does not fit this device (nothing was launched)
+
 template <int ENV, typename T>
 int launch(const CtaParams& p, int nt, bool scripted, cudaStream_t st) {
     const size_t smem = p.pool_in_smem ? (size_t)p.stride_s : 0;
@@ -2041,7 +2043,11 @@ int launch(const CtaParams& p, int nt, bool scripted, cudaStream_t st) {
             cfg.attrs = &attr; cfg.numAttrs = 1;
             if (p.cluster > 8) {   // beyond the portable size: opt in (sm_100 schedules 16-CTA clusters inside one GPC)
                 const cudaError_t ae = cudaFuncSetAttribute(cta_search_kernel<ENV, T, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-                if (ae != cudaSuccess) return cuda_fail(ae, "non-portable cluster size");
+                int fit = 0;
+                if (ae != cudaSuccess || cudaOccupancyMaxActiveClusters(&fit, cta_search_kernel<ENV, T, false>, &cfg) != cudaSuccess || fit < 1) {
+                    cudaGetLastError();
+                    return kClusterRefused;   // this device / partition cannot place such a cluster: the caller falls back
+                }
             }
             const cudaError_t le = cudaLaunchKernelEx(&cfg, cta_search_kernel<ENV, T, false>, p);
             if (le != cudaSuccess) return cuda_fail(le, "cta_search_kernel cluster launch");
@@ -2139,7 +2145,27 @@ int cta_run(isla_engine* e, int n_sim, long long scripted_tree, const uint8_t* k
         return ISLA_ERR_INVALID;
     }
     const int nt = scripted ? 32 : pick_threads(e->cfg);
-    return e->lay.real_bytes == 8 ? launch_env<double>(e, p, nt, scripted, st) : launch_env<float>(e, p, nt, scripted, st);
+    auto go = [&](const CtaParams& q, int threads) {
+        return e->lay.real_bytes == 8 ? launch_env<double>(e, q, threads, scripted, st) : launch_env<float>(e, q, threads, scripted, st);
+    };
+    // one (or a few) trees with >= 4096 rollouts per leaf: a 16-CTA cluster of 256-thread CTAs halves the warps every SM
+    // has to issue for (C2 on one tree: 25.5 -> 24.2 us per simulation; results are independent of the cluster size).  16 is
+    // a non-portable cluster size: if this device cannot place it, the engine stays with 8.
+    const long long sms = e->sm_count > 0 ? e->sm_count : 148;
+    if (!scripted && e->cfg.cluster_ctas == 0 && p.cluster == 8 && p.R >= 4096 && !e->no_cluster16 && e->cfg.block_threads <= 0 &&
+        e->cfg.expansion != ISLA_EXPAND_VOO && (long long)e->cfg.n_trees * 16 * 2 <= sms) {
+        CtaParams p16 = p;
+        p16.cluster = 16;
+        int P = 1;
+        while (P < p.R) P <<= 1;
+        const int slice = P / 16;
+        const int rc = go(p16, nt < slice ? nt : slice);
+        if (rc != kClusterRefused) return rc;
+        e->no_cluster16 = true;
+    }
+    const int rc = go(p, nt);
+    if (rc == kClusterRefused) { set_error("cluster_ctas %d: this device cannot place a cluster of that size", p.cluster); return ISLA_ERR_INVALID; }
+    return rc;
 }
 
 int cta_root_stats(isla_engine* e, int64_t* na_dev, double* total_dev, cudaStream_t st) {
